@@ -1,0 +1,70 @@
+"""Builds lako_b200/_lib/liblako_b200.so with nvcc for sm_100a (in-tree, so the .so travels to the GPU box).
+
+    python -m lako_b200.build [--force]
+"""
+import glob
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB_DIR = os.path.join(HERE, "_lib")
+LIB_PATH = os.path.join(LIB_DIR, "liblako_b200.so")
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+    "-Xcompiler", "-fPIC", "-Xptxas", "-v",
+]
+
+
+def sources():
+    return sorted(glob.glob(os.path.join(CSRC, "*.cu")))
+
+
+def needs_build():
+    if not os.path.exists(LIB_PATH):
+        return True
+    t = os.path.getmtime(LIB_PATH)
+    deps = sources() + glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(HERE, "..", "include", "*.h"))
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force=False, verbose=False):
+    if not force and not needs_build():
+        return LIB_PATH
+    os.makedirs(LIB_DIR, exist_ok=True)
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    objs = []
+    procs = []
+    for src in sources():
+        obj = os.path.join(LIB_DIR, os.path.basename(src)[:-3] + ".o")
+        objs.append(obj)
+        if not force and os.path.exists(obj) and os.path.getmtime(obj) > max(
+                [os.path.getmtime(src)] + [os.path.getmtime(h) for h in glob.glob(os.path.join(CSRC, "*.cuh"))]):
+            continue
+        cmd = [nvcc] + NVCC_FLAGS + ["-I", os.path.join(HERE, "..", "include"), "-c", src, "-o", obj]
+        procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    failed = False
+    for src, p in procs:
+        out, _ = p.communicate()
+        if p.returncode != 0:
+            failed = True
+            sys.stderr.write(f"nvcc failed for {src}:\n{out}\n")
+        elif verbose:
+            sys.stderr.write(out)
+        else:
+            for line in out.splitlines():
+                if "spill" in line and "0 bytes spill stores, 0 bytes spill loads" not in line:
+                    sys.stderr.write(f"[{os.path.basename(src)}] {line}\n")
+                if "warning" in line:
+                    sys.stderr.write(f"[{os.path.basename(src)}] {line}\n")
+    if failed:
+        raise RuntimeError("nvcc compilation failed")
+    cmd = [nvcc, "-shared", "-arch=sm_100a", "-o", LIB_PATH] + objs + ["-lcudart"]
+    subprocess.check_call(cmd)
+    return LIB_PATH
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -1,0 +1,534 @@
+// HBM-bound kernels of the FiDT5 path: fused residual-add + T5 RMSNorm (fwd/bwd), embedding
+// gather / scatter-add, fused log-softmax cross-entropy (fwd+bwd in one pass over the logits),
+// gradient-norm reduction and the fused clip + HF-AdamW(no bias correction) + bf16 re-cast step.
+//
+// Reference semantics:
+//   T5LayerNorm            HF:modeling_t5.py:55-68   x * rsqrt(mean(x^2) + eps) * w, fp32 accumulate
+//   embedding              HF:modeling_t5.py:682
+//   CrossEntropyLoss       HF:modeling_t5.py:1112-1117 (ignore_index=-100, mean over valid tokens)
+//   clip_grad_norm_        /root/reference/train_reader.py:76
+//   AdamW(correct_bias=0)  /root/reference/src/util.py:225
+// All are 128-bit vectorised and use warp-shuffle reductions; algorithmic bytes per element are
+// listed in DESIGN.md.
+#include "ops.cuh"
+
+namespace lako {
+
+// --------------------------------------------------------------------------------------------
+// residual-add + RMSNorm forward.  One warp per row, row cached in registers (d <= 1024, d % 128 == 0).
+//   x      fp32 [rows][d]   residual stream (updated in place when delta != nullptr)
+//   delta  bf16 [rows][d]   sub-layer output to add (may be null)
+//   out    bf16 [rows][d]   w * x * rstd * out_scale
+//   rstd   fp32 [rows]      saved for backward (may be null)
+// --------------------------------------------------------------------------------------------
+constexpr int NORM_MAX_VEC = 8;  // float4 per lane -> d <= 1024
+
+__global__ void __launch_bounds__(256) rmsnorm_fwd_kernel(float* __restrict__ x, const __nv_bfloat16* __restrict__ delta,
+                                                           const float* __restrict__ w, __nv_bfloat16* __restrict__ out,
+                                                           float* __restrict__ rstd_out, int rows, int d, float eps,
+                                                           float out_scale) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= rows) return;
+  const int nvec = d >> 7;
+  float4 xv[NORM_MAX_VEC];
+  float* xr = x + static_cast<size_t>(warp) * d;
+  const __nv_bfloat16* dr = delta ? delta + static_cast<size_t>(warp) * d : nullptr;
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < NORM_MAX_VEC; ++i) {
+    if (i < nvec) {
+      const int c = (i * 32 + lane) * 4;
+      float4 v = *reinterpret_cast<const float4*>(xr + c);
+      if (dr) {
+        uint2 dd = *reinterpret_cast<const uint2*>(dr + c);
+        v.x += bf16_lo(dd.x);
+        v.y += bf16_hi(dd.x);
+        v.z += bf16_lo(dd.y);
+        v.w += bf16_hi(dd.y);
+        *reinterpret_cast<float4*>(xr + c) = v;
+      }
+      xv[i] = v;
+      ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+    }
+  }
+  ss = warp_sum(ss);
+  const float r = rsqrtf(ss / static_cast<float>(d) + eps);
+  if (rstd_out && lane == 0) rstd_out[warp] = r;
+  if (out) {
+    __nv_bfloat16* orow = out + static_cast<size_t>(warp) * d;
+    const float rs = r * out_scale;
+#pragma unroll
+    for (int i = 0; i < NORM_MAX_VEC; ++i) {
+      if (i < nvec) {
+        const int c = (i * 32 + lane) * 4;
+        const float4 wv = *reinterpret_cast<const float4*>(w + c);
+        uint2 o;
+        o.x = pack_bf16x2(wv.x * (xv[i].x * rs), wv.y * (xv[i].y * rs));
+        o.y = pack_bf16x2(wv.z * (xv[i].z * rs), wv.w * (xv[i].w * rs));
+        *reinterpret_cast<uint2*>(orow + c) = o;
+      }
+    }
+  }
+}
+
+int rmsnorm_fwd(float* x, const __nv_bfloat16* delta, const float* w, __nv_bfloat16* out, float* rstd, int rows, int d,
+                float eps, float out_scale, cudaStream_t s) {
+  LAKO_REQUIRE(rows > 0 && d > 0 && d % 128 == 0 && d <= 128 * NORM_MAX_VEC, LAKO_ERR_UNSUPPORTED);
+  const int warps_per_block = 8;
+  const int grid = (rows + warps_per_block - 1) / warps_per_block;
+  rmsnorm_fwd_kernel<<<grid, warps_per_block * 32, 0, s>>>(x, delta, w, out, rstd, rows, d, eps, out_scale);
+  LAKO_CHECK_LAUNCH();
+  return LAKO_OK;
+}
+
+// --------------------------------------------------------------------------------------------
+// RMSNorm backward, fused with the residual-gradient accumulation.
+//   dy     bf16 [rows][d]  gradient w.r.t. the normalised output (from the dgrad GEMM); scaled by dy_scale
+//   x      fp32 [rows][d]  the (post-residual) input that was normalised; rstd fp32 [rows]
+//   dres   fp32 [rows][d]  running gradient of the residual stream: dres = (accumulate ? dres : 0) + dx
+//   dres_bf16 (optional)   bf16 copy of the updated dres (operand of the next dgrad/wgrad GEMMs)
+//   dw     fp32 [d]        += sum_rows dy * x * rstd   (block-reduced, one atomic per column per block)
+// --------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) rmsnorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy,
+                                                           const float* __restrict__ x, const float* __restrict__ rstd,
+                                                           const float* __restrict__ w, float* __restrict__ dres,
+                                                           __nv_bfloat16* __restrict__ dres_bf16,
+                                                           float* __restrict__ dw, int rows, int d, int accumulate,
+                                                           float dy_scale) {
+  __shared__ float s_dw[8][128 * NORM_MAX_VEC / 8];  // reused in column chunks below
+  const int lane = threadIdx.x & 31;
+  const int wib = threadIdx.x >> 5;
+  const int nvec = d >> 7;
+  float4 dwv[NORM_MAX_VEC];
+  float4 wv[NORM_MAX_VEC];
+#pragma unroll
+  for (int i = 0; i < NORM_MAX_VEC; ++i) {
+    dwv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (i < nvec) wv[i] = *reinterpret_cast<const float4*>(w + (i * 32 + lane) * 4);
+  }
+  const int warps_total = gridDim.x * (blockDim.x >> 5);
+  for (int row = blockIdx.x * (blockDim.x >> 5) + wib; row < rows; row += warps_total) {
+    const float r = rstd[row];
+    const float* xr = x + static_cast<size_t>(row) * d;
+    const __nv_bfloat16* dyr = dy + static_cast<size_t>(row) * d;
+    float4 g[NORM_MAX_VEC], xv[NORM_MAX_VEC];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < NORM_MAX_VEC; ++i) {
+      if (i < nvec) {
+        const int c = (i * 32 + lane) * 4;
+        xv[i] = *reinterpret_cast<const float4*>(xr + c);
+        const uint2 dd = *reinterpret_cast<const uint2*>(dyr + c);
+        float4 dyv = make_float4(bf16_lo(dd.x) * dy_scale, bf16_hi(dd.x) * dy_scale, bf16_lo(dd.y) * dy_scale,
+                                 bf16_hi(dd.y) * dy_scale);
+        dwv[i].x += dyv.x * xv[i].x * r;
+        dwv[i].y += dyv.y * xv[i].y * r;
+        dwv[i].z += dyv.z * xv[i].z * r;
+        dwv[i].w += dyv.w * xv[i].w * r;
+        g[i] = make_float4(dyv.x * wv[i].x, dyv.y * wv[i].y, dyv.z * wv[i].z, dyv.w * wv[i].w);
+        s += g[i].x * xv[i].x + g[i].y * xv[i].y + g[i].z * xv[i].z + g[i].w * xv[i].w;
+      }
+    }
+    s = warp_sum(s);
+    const float coef = r * r * r * s / static_cast<float>(d);
+    float* drr = dres + static_cast<size_t>(row) * d;
+#pragma unroll
+    for (int i = 0; i < NORM_MAX_VEC; ++i) {
+      if (i < nvec) {
+        const int c = (i * 32 + lane) * 4;
+        float4 o = make_float4(r * g[i].x - coef * xv[i].x, r * g[i].y - coef * xv[i].y, r * g[i].z - coef * xv[i].z,
+                               r * g[i].w - coef * xv[i].w);
+        if (accumulate) {
+          const float4 old = *reinterpret_cast<const float4*>(drr + c);
+          o.x += old.x;
+          o.y += old.y;
+          o.z += old.z;
+          o.w += old.w;
+        }
+        *reinterpret_cast<float4*>(drr + c) = o;
+        if (dres_bf16) {
+          uint2 ob;
+          ob.x = pack_bf16x2(o.x, o.y);
+          ob.y = pack_bf16x2(o.z, o.w);
+          *reinterpret_cast<uint2*>(dres_bf16 + static_cast<size_t>(row) * d + c) = ob;
+        }
+      }
+    }
+  }
+  // block reduction of dw: one float4 slot (i) at a time through shared memory
+  if (dw) {
+#pragma unroll
+    for (int i = 0; i < NORM_MAX_VEC; ++i) {
+      if (i < nvec) {
+        __syncthreads();
+        reinterpret_cast<float4*>(&s_dw[wib][0])[lane] = dwv[i];
+        __syncthreads();
+        if (threadIdx.x < 128) {
+          float acc = 0.f;
+          for (int ww = 0; ww < (blockDim.x >> 5); ++ww) acc += s_dw[ww][threadIdx.x];
+          atomicAdd(dw + i * 128 + threadIdx.x, acc);
+        }
+      }
+    }
+  }
+}
+
+int rmsnorm_bwd(const __nv_bfloat16* dy, const float* x, const float* rstd, const float* w, float* dres,
+                __nv_bfloat16* dres_bf16, float* dw, int rows, int d, int accumulate, float dy_scale,
+                cudaStream_t s) {
+  LAKO_REQUIRE(rows > 0 && d > 0 && d % 128 == 0 && d <= 128 * NORM_MAX_VEC, LAKO_ERR_UNSUPPORTED);
+  const int warps_per_block = 8;
+  int grid = (rows + warps_per_block - 1) / warps_per_block;
+  grid = min(grid, device_sm_count() * 4);
+  rmsnorm_bwd_kernel<<<grid, warps_per_block * 32, 0, s>>>(dy, x, rstd, w, dres, dres_bf16, dw, rows, d, accumulate,
+                                                            dy_scale);
+  LAKO_CHECK_LAUNCH();
+  return LAKO_OK;
+}
+
+// --------------------------------------------------------------------------------------------
+// embedding gather (fp32 table -> fp32 residual stream) and its scatter-add backward
+// --------------------------------------------------------------------------------------------
+__global__ void embed_gather_kernel(const long long* __restrict__ ids, const float* __restrict__ table,
+                                    float* __restrict__ out, int rows, int d, int vocab) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= rows) return;
+  long long id = ids[warp];
+  if (id < 0 || id >= vocab) id = 0;
+  const float4* src = reinterpret_cast<const float4*>(table + static_cast<size_t>(id) * d);
+  float4* dst = reinterpret_cast<float4*>(out + static_cast<size_t>(warp) * d);
+  for (int c = lane; c < (d >> 2); c += 32) dst[c] = __ldg(src + c);
+}
+
+int embed_gather(const long long* ids, const float* table, float* out, int rows, int d, int vocab, cudaStream_t s) {
+  LAKO_REQUIRE(rows > 0 && d % 4 == 0, LAKO_ERR_BAD_ARG);
+  embed_gather_kernel<<<(rows + 7) / 8, 256, 0, s>>>(ids, table, out, rows, d, vocab);
+  LAKO_CHECK_LAUNCH();
+  return LAKO_OK;
+}
+
+__global__ void embed_scatter_add_kernel(const long long* __restrict__ ids, const float* __restrict__ dres,
+                                         float* __restrict__ dtable, int rows, int d, int vocab) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= rows) return;
+  long long id = ids[warp];
+  if (id < 0 || id >= vocab) id = 0;
+  const float4* src = reinterpret_cast<const float4*>(dres + static_cast<size_t>(warp) * d);
+  float* dst = dtable + static_cast<size_t>(id) * d;
+  for (int c = lane; c < (d >> 2); c += 32) {
+    const float4 v = src[c];
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + c * 4), "f"(v.x), "f"(v.y), "f"(v.z),
+                 "f"(v.w)
+                 : "memory");
+  }
+}
+
+int embed_scatter_add(const long long* ids, const float* dres, float* dtable, int rows, int d, int vocab,
+                      cudaStream_t s) {
+  LAKO_REQUIRE(rows > 0 && d % 4 == 0, LAKO_ERR_BAD_ARG);
+  embed_scatter_add_kernel<<<(rows + 7) / 8, 256, 0, s>>>(ids, dres, dtable, rows, d, vocab);
+  LAKO_CHECK_LAUNCH();
+  return LAKO_OK;
+}
+
+// decoder input ids = shift_right(labels) (HF:modeling_t5.py:595-614): start token 0, -100 -> 0
+__global__ void shift_right_kernel(const long long* __restrict__ labels, long long* __restrict__ dec_ids, int B,
+                                   int T) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * T) return;
+  const int t = i % T;
+  long long v = (t == 0) ? 0 : labels[i - 1];
+  if (v == -100) v = 0;
+  dec_ids[i] = v;
+}
+int shift_right(const long long* labels, long long* dec_ids, int B, int T, cudaStream_t s) {
+  shift_right_kernel<<<(B * T + 255) / 256, 256, 0, s>>>(labels, dec_ids, B, T);
+  LAKO_CHECK_LAUNCH();
+  return LAKO_OK;
+}
+
+// --------------------------------------------------------------------------------------------
+// fused log-softmax cross-entropy, forward + backward in one launch.
+//   logits fp32 [rows][ld]; labels int64 [rows] (-100 = ignore)
+//   stats[0] += sum of row losses, stats[1] = number of valid rows (computed by count_valid_kernel,
+//   possibly all-reduced across ranks before this launch)
+//   dlogits bf16 [rows][ld_d] = (softmax - onehot) / stats[1]  (0 for ignored rows); may be null
+// One CTA per row; pass 1 = online max/sum, pass 2 re-reads the row (L2 resident) and writes dlogits.
+// --------------------------------------------------------------------------------------------
+__global__ void count_valid_kernel(const long long* __restrict__ labels, int n, float* __restrict__ stats) {
+  __shared__ int s_cnt;
+  if (threadIdx.x == 0) s_cnt = 0;
+  __syncthreads();
+  int c = 0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) c += (labels[i] != -100) ? 1 : 0;
+  atomicAdd(&s_cnt, c);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    stats[0] = 0.f;
+    stats[1] = static_cast<float>(s_cnt);
+  }
+}
+
+__global__ void __launch_bounds__(512) ce_fwd_bwd_kernel(const float* __restrict__ logits,
+                                                          const long long* __restrict__ labels,
+                                                          float* __restrict__ stats, float* __restrict__ row_loss,
+                                                          __nv_bfloat16* __restrict__ dlogits, int V, int ld, int ld_d) {
+  __shared__ float s_m[16], s_s[16];
+  __shared__ float s_bm, s_bs;
+  const int row = blockIdx.x;
+  const long long label = labels[row];
+  const float* lr = logits + static_cast<size_t>(row) * ld;
+  const bool valid = (label != -100);
+  float m = -INFINITY, ssum = 0.f;
+  if (valid) {
+    for (int c = threadIdx.x * 4; c < V; c += blockDim.x * 4) {
+      if (c + 4 <= V) {
+        const float4 v = *reinterpret_cast<const float4*>(lr + c);
+        const float mx = fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w));
+        if (mx > m) {
+          ssum *= __expf(m - mx);
+          m = mx;
+        }
+        ssum += __expf(v.x - m) + __expf(v.y - m) + __expf(v.z - m) + __expf(v.w - m);
+      } else {
+        for (int e = c; e < V; ++e) {
+          const float v = lr[e];
+          if (v > m) {
+            ssum *= __expf(m - v);
+            m = v;
+          }
+          ssum += __expf(v - m);
+        }
+      }
+    }
+    // warp then block reduction of (m, ssum)
+    const float wm = warp_max(m);
+    ssum *= (m == -INFINITY) ? 0.f : __expf(m - wm);  // threads/warps that saw no element carry (-inf, 0)
+    ssum = warp_sum(ssum);
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    if (l == 0) {
+      s_m[w] = wm;
+      s_s[w] = ssum;
+    }
+    __syncthreads();
+    if (w == 0) {
+      const int nw = blockDim.x >> 5;
+      float mm = (l < nw) ? s_m[l] : -INFINITY;
+      float sv = (l < nw) ? s_s[l] : 0.f;
+      const float bm = warp_max(mm);
+      sv *= (mm == -INFINITY) ? 0.f : __expf(mm - bm);
+      sv = warp_sum(sv);
+      if (l == 0) {
+        s_bm = bm;
+        s_bs = sv;
+      }
+    }
+    __syncthreads();
+  }
+  const float inv_count = 1.f / fmaxf(stats[1], 1.f);
+  float bm = 0.f, inv_sum = 0.f;
+  if (valid) {
+    bm = s_bm;
+    inv_sum = 1.f / s_bs;
+    if (threadIdx.x == 0) {
+      const float loss = logf(s_bs) + bm - lr[label];
+      if (row_loss) row_loss[row] = loss;
+      atomicAdd(&stats[0], loss);
+    }
+  } else if (threadIdx.x == 0 && row_loss) {
+    row_loss[row] = 0.f;
+  }
+  if (dlogits) {
+    __nv_bfloat16* dr = dlogits + static_cast<size_t>(row) * ld_d;
+    for (int c = threadIdx.x * 8; c < V; c += blockDim.x * 8) {
+      float g[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        g[e] = 0.f;
+        if (valid && c + e < V) {
+          g[e] = __expf(lr[c + e] - bm) * inv_sum;
+          if (c + e == label) g[e] -= 1.f;
+          g[e] *= inv_count;
+        }
+      }
+      if (c + 8 <= V) {
+        uint4 o;
+        o.x = pack_bf16x2(g[0], g[1]);
+        o.y = pack_bf16x2(g[2], g[3]);
+        o.z = pack_bf16x2(g[4], g[5]);
+        o.w = pack_bf16x2(g[6], g[7]);
+        *reinterpret_cast<uint4*>(dr + c) = o;
+      } else {
+        for (int e = 0; c + e < V; ++e) dr[c + e] = __float2bfloat16(g[e]);
+      }
+    }
+  }
+}
+
+int count_valid(const long long* labels, int n, float* stats, cudaStream_t s) {
+  count_valid_kernel<<<1, 256, 0, s>>>(labels, n, stats);
+  LAKO_CHECK_LAUNCH();
+  return LAKO_OK;
+}
+
+int ce_fwd_bwd(const float* logits, const long long* labels, float* stats, float* row_loss, __nv_bfloat16* dlogits,
+               int rows, int V, int ld, int ld_d, cudaStream_t s) {
+  LAKO_REQUIRE(rows > 0 && V > 0 && ld % 4 == 0 && (dlogits == nullptr || ld_d % 8 == 0), LAKO_ERR_BAD_ARG);
+  ce_fwd_bwd_kernel<<<rows, 512, 0, s>>>(logits, labels, stats, row_loss, dlogits, V, ld, ld_d);
+  LAKO_CHECK_LAUNCH();
+  return LAKO_OK;
+}
+
+// --------------------------------------------------------------------------------------------
+// casts / transposes / fills
+// --------------------------------------------------------------------------------------------
+__global__ void cast_f32_to_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, size_t n) {
+  const size_t i = (static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x) * 8;
+  if (i + 8 <= n) {
+    const float4 a = *reinterpret_cast<const float4*>(in + i);
+    const float4 b = *reinterpret_cast<const float4*>(in + i + 4);
+    uint4 o;
+    o.x = pack_bf16x2(a.x, a.y);
+    o.y = pack_bf16x2(a.z, a.w);
+    o.z = pack_bf16x2(b.x, b.y);
+    o.w = pack_bf16x2(b.z, b.w);
+    *reinterpret_cast<uint4*>(out + i) = o;
+  } else {
+    for (size_t e = i; e < n; ++e) out[e] = __float2bfloat16(in[e]);
+  }
+}
+int cast_f32_to_bf16(const float* in, __nv_bfloat16* out, size_t n, cudaStream_t s) {
+  if (n == 0) return LAKO_OK;
+  const size_t blocks = (n + 2047) / 2048;
+  cast_f32_to_bf16_kernel<<<static_cast<unsigned>(blocks), 256, 0, s>>>(in, out, n);
+  LAKO_CHECK_LAUNCH();
+  return LAKO_OK;
+}
+
+// out[c][r] = in[r][c], bf16, 32x32 tiles through padded smem
+__global__ void transpose_bf16_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out, int rows,
+                                      int cols, int ld_in, int ld_out) {
+  __shared__ __nv_bfloat16 tile[64][66];
+  const int r0 = blockIdx.y * 64, c0 = blockIdx.x * 64;
+  for (int i = threadIdx.y; i < 64; i += blockDim.y) {
+    const int r = r0 + i;
+    for (int j = threadIdx.x; j < 64; j += blockDim.x) {
+      const int c = c0 + j;
+      tile[i][j] = (r < rows && c < cols) ? in[static_cast<size_t>(r) * ld_in + c] : __float2bfloat16(0.f);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 64; i += blockDim.y) {
+    const int c = c0 + i;
+    for (int j = threadIdx.x; j < 64; j += blockDim.x) {
+      const int r = r0 + j;
+      if (r < rows && c < cols) out[static_cast<size_t>(c) * ld_out + r] = tile[j][i];
+    }
+  }
+}
+int transpose_bf16(const __nv_bfloat16* in, __nv_bfloat16* out, int rows, int cols, int ld_in, int ld_out,
+                   cudaStream_t s) {
+  dim3 grid((cols + 63) / 64, (rows + 63) / 64), block(32, 8);
+  transpose_bf16_kernel<<<grid, block, 0, s>>>(in, out, rows, cols, ld_in, ld_out);
+  LAKO_CHECK_LAUNCH();
+  return LAKO_OK;
+}
+
+// --------------------------------------------------------------------------------------------
+// gradient global-norm + fused clip / AdamW / bf16 re-cast over the flat parameter buffer
+// --------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ g, size_t n, float* __restrict__ out) {
+  __shared__ float s_w[8];
+  float acc = 0.f;
+  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x * 4;
+  for (size_t i = (static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x) * 4; i < n; i += stride) {
+    if (i + 4 <= n) {
+      const float4 v = *reinterpret_cast<const float4*>(g + i);
+      acc += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+    } else {
+      for (size_t e = i; e < n; ++e) acc += g[e] * g[e];
+    }
+  }
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float v = (threadIdx.x < 8) ? s_w[threadIdx.x] : 0.f;
+    v = warp_sum(v);
+    if (threadIdx.x == 0) atomicAdd(out, v);
+  }
+}
+int grad_sumsq(const float* g, size_t n, float* out, cudaStream_t s) {
+  // caller zeroes *out
+  const int grid = device_sm_count() * 8;
+  sumsq_kernel<<<grid, 256, 0, s>>>(g, n, out);
+  LAKO_CHECK_LAUNCH();
+  return LAKO_OK;
+}
+
+// p, m, v, g fp32 flat; w_bf16 = bf16 copy of the updated p.  sumsq points at the device scalar with
+// the (already all-reduced) sum of squared gradients; grad_scale pre-multiplies g (1/world for DP mean).
+__global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, float* __restrict__ m, float* __restrict__ v,
+                                                     const float* __restrict__ g, __nv_bfloat16* __restrict__ w_bf16,
+                                                     size_t n, const float* __restrict__ sumsq, float grad_scale,
+                                                     float clip, float lr, float beta1, float beta2, float eps,
+                                                     float wd) {
+  float coef = grad_scale;
+  if (clip > 0.f) {
+    const float norm = sqrtf(*sumsq) * grad_scale;
+    coef *= fminf(1.f, clip / (norm + 1e-6f));
+  }
+  const size_t i = (static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x) * 4;
+  if (i >= n) return;
+  if (i + 4 <= n) {
+    float4 pv = *reinterpret_cast<const float4*>(p + i);
+    float4 mv = *reinterpret_cast<const float4*>(m + i);
+    float4 vv = *reinterpret_cast<const float4*>(v + i);
+    const float4 gv = *reinterpret_cast<const float4*>(g + i);
+    float* pp = reinterpret_cast<float*>(&pv);
+    float* mp = reinterpret_cast<float*>(&mv);
+    float* vp = reinterpret_cast<float*>(&vv);
+    const float* gp = reinterpret_cast<const float*>(&gv);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float gg = gp[e] * coef;
+      mp[e] = beta1 * mp[e] + (1.f - beta1) * gg;
+      vp[e] = beta2 * vp[e] + (1.f - beta2) * gg * gg;
+      float np = pp[e] - lr * (mp[e] / (sqrtf(vp[e]) + eps));
+      np = np - lr * wd * np;
+      pp[e] = np;
+    }
+    *reinterpret_cast<float4*>(p + i) = pv;
+    *reinterpret_cast<float4*>(m + i) = mv;
+    *reinterpret_cast<float4*>(v + i) = vv;
+    uint2 o;
+    o.x = pack_bf16x2(pp[0], pp[1]);
+    o.y = pack_bf16x2(pp[2], pp[3]);
+    *reinterpret_cast<uint2*>(w_bf16 + i) = o;
+  } else {
+    for (size_t e = i; e < n; ++e) {
+      const float gg = g[e] * coef;
+      m[e] = beta1 * m[e] + (1.f - beta1) * gg;
+      v[e] = beta2 * v[e] + (1.f - beta2) * gg * gg;
+      float np = p[e] - lr * (m[e] / (sqrtf(v[e]) + eps));
+      np = np - lr * wd * np;
+      p[e] = np;
+      w_bf16[e] = __float2bfloat16(np);
+    }
+  }
+}
+int adamw_step(float* p, float* m, float* v, const float* g, __nv_bfloat16* w_bf16, size_t n, const float* sumsq,
+               float grad_scale, float clip, float lr, float beta1, float beta2, float eps, float wd,
+               cudaStream_t s) {
+  LAKO_REQUIRE(n > 0 && n % 4 == 0, LAKO_ERR_BAD_ARG);
+  const size_t blocks = (n / 4 + 255) / 256;
+  adamw_kernel<<<static_cast<unsigned>(blocks), 256, 0, s>>>(p, m, v, g, w_bf16, n, sumsq, grad_scale, clip, lr, beta1,
+                                                             beta2, eps, wd);
+  LAKO_CHECK_LAUNCH();
+  return LAKO_OK;
+}
+
+}  // namespace lako

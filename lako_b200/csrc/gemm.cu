@@ -1,0 +1,383 @@
+// bf16 GEMM on the sm_100a tensor cores: C[M,N] = alpha * A[M,K] * B[N,K]^T (+ epilogue).
+//
+// Replaces the cuBLAS calls behind every nn.Linear of the T5 blocks the reference inherits
+// (HF:modeling_t5.py:92-103 FFN, :277-299/:338 q,k,v,o projections, :1107-1110 LM head) and their
+// autograd backward (dgrad / wgrad).
+//
+// Design: persistent, warp-specialised CTA (one per SM):
+//   warp 0   : TMA producer  (cp.async.bulk.tensor, 128B-swizzled tiles, mbarrier expect-tx)
+//   warp 1   : MMA issuer    (one thread issues tcgen05.mma kind::f16, fp32 accumulators in TMEM)
+//   warp 2   : TMEM allocator
+//   warps 4-7: epilogue      (tcgen05.ld -> registers -> fused epilogue -> global)
+// Two TMEM accumulator stages (2 x BN columns) let the epilogue of tile i overlap the main loop of
+// tile i+1.  Operands may be K-major (row-major [rows][K]) or MN-major (row-major [K][rows]), so
+// forward (X W^T), dgrad (dY W) and wgrad (dY^T X) all run without materialising a transpose.
+// Split-K (wgrad: small output, very deep K) reduces with fp32 vector red.global into the
+// caller-zeroed gradient buffer.
+#include "ops.cuh"
+
+namespace lako {
+
+constexpr int BM = 128;
+constexpr int BK = 64;
+constexpr int GEMM_THREADS = 256;
+
+template <int BN>
+struct GemmCfg {
+  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = (BN == 256) ? 4 : 6;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+struct GemmParams {
+  void* C;
+  const void* aux;
+  int M, N, K;
+  int ldc, ld_aux;
+  int tiles_m, tiles_n, splitk, kb_total, kb_per_split;
+  float alpha;
+};
+
+template <int BN, bool A_MN, bool B_MN, int EPI>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+  using Cfg = GemmCfg<BN>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + STAGES * Cfg::A_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + STAGES;
+  uint64_t* tfull_bar = bars + 2 * STAGES;
+  uint64_t* tempty_bar = bars + 2 * STAGES + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int tiles_mn = p.tiles_m * p.tiles_n;
+  const int total_tiles = tiles_mn * p.splitk;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        const int ks = t / tiles_mn;
+        const int mn = t - ks * tiles_mn;
+        const int m0 = (mn / p.tiles_n) * BM;
+        const int n0 = (mn % p.tiles_n) * BN;
+        const int kb0 = ks * p.kb_per_split;
+        const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+          uint8_t* a = sA + stage * Cfg::A_BYTES;
+          uint8_t* b = sB + stage * Cfg::B_BYTES;
+          if constexpr (!A_MN) {
+            tma_load_2d(a, &tmA, &full_bar[stage], kb * BK, m0);
+          } else {
+#pragma unroll
+            for (int c = 0; c < BM / 64; ++c) tma_load_2d(a + c * 8192, &tmA, &full_bar[stage], m0 + c * 64, kb * BK);
+          }
+          if constexpr (!B_MN) {
+            tma_load_2d(b, &tmB, &full_bar[stage], kb * BK, n0);
+          } else {
+#pragma unroll
+            for (int c = 0; c < BN / 64; ++c) tma_load_2d(b + c * 8192, &tmB, &full_bar[stage], n0 + c * 64, kb * BK);
+          }
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(BM, BN, A_MN, B_MN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        const int ks = t / tiles_mn;
+        const int kb0 = ks * p.kb_per_split;
+        const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(sA + stage * Cfg::A_BYTES);
+          const uint32_t b_addr = smem_u32(sB + stage * Cfg::B_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            const uint64_t adesc = A_MN ? make_smem_desc_sw128(a_addr + k * 2048, 8192, 1024)
+                                        : make_smem_desc_sw128(a_addr + k * 32, 16, 1024);
+            const uint64_t bdesc = B_MN ? make_smem_desc_sw128(b_addr + k * 2048, 8192, 1024)
+                                        : make_smem_desc_sw128(b_addr + k * 32, 16, 1024);
+            umma_bf16(d_tmem, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(&tfull_bar[acc]);  // accumulator complete -> epilogue
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------ epilogue
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      const int ks = t / tiles_mn;
+      const int mn = t - ks * tiles_mn;
+      const int m0 = (mn / p.tiles_n) * BM;
+      const int n0 = (mn % p.tiles_n) * BN;
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      const int row = m0 + q * 32 + lane;
+      const bool row_ok = row < p.M;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        const int col0 = n0 + c * 32;
+        if (col0 >= p.N) break;  // warp-uniform
+        uint32_t r[32];
+        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + c * 32, r);
+        tmem_ld_wait();
+        if (!row_ok) continue;
+        float v[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) * p.alpha;
+        const bool full = (col0 + 32 <= p.N);
+        if constexpr (EPI == EPI_BF16 || EPI == EPI_BF16_RELU || EPI == EPI_BF16_MASK) {
+          __nv_bfloat16* crow = reinterpret_cast<__nv_bfloat16*>(p.C) + static_cast<size_t>(row) * p.ldc + col0;
+          if constexpr (EPI == EPI_BF16_RELU) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+          }
+          if constexpr (EPI == EPI_BF16_MASK) {
+            const __nv_bfloat16* arow =
+                reinterpret_cast<const __nv_bfloat16*>(p.aux) + static_cast<size_t>(row) * p.ld_aux + col0;
+            if (full) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                uint4 m = *reinterpret_cast<const uint4*>(arow + j * 8);
+                const uint32_t mw[4] = {m.x, m.y, m.z, m.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  if (!(bf16_lo(mw[e]) > 0.f)) v[j * 8 + e * 2] = 0.f;
+                  if (!(bf16_hi(mw[e]) > 0.f)) v[j * 8 + e * 2 + 1] = 0.f;
+                }
+              }
+            } else {
+              for (int i = 0; i < 32; ++i)
+                if (col0 + i < p.N && !(__bfloat162float(arow[i]) > 0.f)) v[i] = 0.f;
+            }
+          }
+          if (full) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              uint4 o;
+              o.x = pack_bf16x2(v[j * 8 + 0], v[j * 8 + 1]);
+              o.y = pack_bf16x2(v[j * 8 + 2], v[j * 8 + 3]);
+              o.z = pack_bf16x2(v[j * 8 + 4], v[j * 8 + 5]);
+              o.w = pack_bf16x2(v[j * 8 + 6], v[j * 8 + 7]);
+              *reinterpret_cast<uint4*>(crow + j * 8) = o;
+            }
+          } else {
+            for (int i = 0; i < 32; ++i)
+              if (col0 + i < p.N) crow[i] = __float2bfloat16(v[i]);
+          }
+        } else {
+          float* crow = reinterpret_cast<float*>(p.C) + static_cast<size_t>(row) * p.ldc + col0;
+          if constexpr (EPI == EPI_F32) {
+            if (full) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j)
+                *reinterpret_cast<float4*>(crow + j * 4) = make_float4(v[j * 4], v[j * 4 + 1], v[j * 4 + 2], v[j * 4 + 3]);
+            } else {
+              for (int i = 0; i < 32; ++i)
+                if (col0 + i < p.N) crow[i] = v[i];
+            }
+          } else {  // EPI_F32_ATOMIC
+            if (full) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j)
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(crow + j * 4), "f"(v[j * 4]),
+                             "f"(v[j * 4 + 1]), "f"(v[j * 4 + 2]), "f"(v[j * 4 + 3])
+                             : "memory");
+            } else {
+              for (int i = 0; i < 32; ++i)
+                if (col0 + i < p.N) atomicAdd(crow + i, v[i]);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+template <int BN, bool A_MN, bool B_MN, int EPI>
+static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t stream) {
+  using Cfg = GemmCfg<BN>;
+  auto kern = gemm_bf16_kernel<BN, A_MN, B_MN, EPI>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) {
+      set_last_error(cudaGetErrorString(e), __FILE__, __LINE__);
+      return LAKO_ERR_LAUNCH;
+    }
+    configured = true;
+  }
+  const int total = p.tiles_m * p.tiles_n * p.splitk;
+  const int grid = min(total, device_sm_count());
+  kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, p);
+  LAKO_CHECK_LAUNCH();
+  return LAKO_OK;
+}
+
+template <int BN, bool A_MN, bool B_MN>
+static int dispatch_epi(int epi, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p,
+                        cudaStream_t s) {
+  switch (epi) {
+    case EPI_BF16: return launch_gemm<BN, A_MN, B_MN, EPI_BF16>(tmA, tmB, p, s);
+    case EPI_BF16_RELU: return launch_gemm<BN, A_MN, B_MN, EPI_BF16_RELU>(tmA, tmB, p, s);
+    case EPI_F32: return launch_gemm<BN, A_MN, B_MN, EPI_F32>(tmA, tmB, p, s);
+    case EPI_F32_ATOMIC: return launch_gemm<BN, A_MN, B_MN, EPI_F32_ATOMIC>(tmA, tmB, p, s);
+    case EPI_BF16_MASK: return launch_gemm<BN, A_MN, B_MN, EPI_BF16_MASK>(tmA, tmB, p, s);
+  }
+  set_last_error("unknown epilogue", __FILE__, __LINE__);
+  return LAKO_ERR_BAD_ARG;
+}
+
+template <int BN>
+static int dispatch_major(int a_mn, int b_mn, int epi, const CUtensorMap& tmA, const CUtensorMap& tmB,
+                          const GemmParams& p, cudaStream_t s) {
+  if (!a_mn && !b_mn) return dispatch_epi<BN, false, false>(epi, tmA, tmB, p, s);
+  if (!a_mn && b_mn) return dispatch_epi<BN, false, true>(epi, tmA, tmB, p, s);
+  if (a_mn && !b_mn) return dispatch_epi<BN, true, false>(epi, tmA, tmB, p, s);
+  return dispatch_epi<BN, true, true>(epi, tmA, tmB, p, s);
+}
+
+// Host entry used by the C ABI and by the model orchestrator.
+//  A: a_mn==0 -> row-major [M][lda>=K];   a_mn==1 -> row-major [K][lda>=M]
+//  B: b_mn==0 -> row-major [N][ldb>=K];   b_mn==1 -> row-major [K][ldb>=N]
+//  splitk<=0 -> chosen automatically (only for EPI_F32_ATOMIC); bn: 0 auto, 128 or 256.
+int gemm_bf16(const void* A, const void* B, void* C, int M, int N, int K, int lda, int ldb, int ldc, int a_mn,
+              int b_mn, int epi, float alpha, const void* aux, int ld_aux, int splitk, int bn, cudaStream_t stream) {
+  int rc = check_arch();
+  if (rc) return rc;
+  LAKO_REQUIRE(M > 0 && N > 0 && K > 0, LAKO_ERR_BAD_ARG);
+  LAKO_REQUIRE(lda % 8 == 0 && ldb % 8 == 0, LAKO_ERR_BAD_ARG);
+  LAKO_REQUIRE(epi >= 0 && epi <= 4, LAKO_ERR_BAD_ARG);
+  LAKO_REQUIRE(epi != EPI_BF16_MASK || aux != nullptr, LAKO_ERR_BAD_ARG);
+  const bool out_bf16 = (epi == EPI_BF16 || epi == EPI_BF16_RELU || epi == EPI_BF16_MASK);
+  LAKO_REQUIRE((reinterpret_cast<uintptr_t>(C) & 15) == 0 && ldc % (out_bf16 ? 8 : 4) == 0, LAKO_ERR_BAD_ARG);
+  if (epi == EPI_BF16_MASK)
+    LAKO_REQUIRE((reinterpret_cast<uintptr_t>(aux) & 15) == 0 && ld_aux % 8 == 0, LAKO_ERR_BAD_ARG);
+
+  const int sms = device_sm_count();
+  if (bn != 128 && bn != 256) {
+    // prefer 128x256 tiles; fall back to 128x128 when that leaves most of the chip idle
+    const long t256 = static_cast<long>((M + BM - 1) / BM) * ((N + 255) / 256);
+    bn = (N <= 128 || (t256 < sms && epi != EPI_F32_ATOMIC)) ? 128 : 256;
+  }
+  GemmParams p;
+  p.C = C;
+  p.aux = aux;
+  p.M = M;
+  p.N = N;
+  p.K = K;
+  p.ldc = ldc;
+  p.ld_aux = ld_aux;
+  p.alpha = alpha;
+  p.tiles_m = (M + BM - 1) / BM;
+  p.tiles_n = (N + bn - 1) / bn;
+  p.kb_total = (K + BK - 1) / BK;
+  if (epi != EPI_F32_ATOMIC) {
+    splitk = 1;
+  } else if (splitk <= 0) {
+    const int tiles = p.tiles_m * p.tiles_n;
+    splitk = (tiles >= sms) ? 1 : (2 * sms + tiles - 1) / tiles;  // ~2 waves
+    const int max_split = max(1, p.kb_total / 4);                 // keep >= 4 k-blocks per split
+    splitk = min(splitk, max_split);
+  }
+  splitk = max(1, min(splitk, p.kb_total));
+  p.kb_per_split = (p.kb_total + splitk - 1) / splitk;
+  p.splitk = (p.kb_total + p.kb_per_split - 1) / p.kb_per_split;
+
+  CUtensorMap tmA, tmB;
+  if (!a_mn)
+    rc = get_tensor_map_2d(&tmA, A, K, M, lda, 64, BM);
+  else
+    rc = get_tensor_map_2d(&tmA, A, M, K, lda, 64, BK);
+  if (rc) return rc;
+  if (!b_mn)
+    rc = get_tensor_map_2d(&tmB, B, K, N, ldb, 64, bn);
+  else
+    rc = get_tensor_map_2d(&tmB, B, N, K, ldb, 64, BK);
+  if (rc) return rc;
+  if (bn == 256) return dispatch_major<256>(a_mn, b_mn, epi, tmA, tmB, p, stream);
+  return dispatch_major<128>(a_mn, b_mn, epi, tmA, tmB, p, stream);
+}
+
+}  // namespace lako
+
+extern "C" int lako_gemm_bf16(const void* A, const void* B, void* C, int M, int N, int K, int lda, int ldb, int ldc,
+                              int a_mn, int b_mn, int epi, float alpha, const void* aux, int ld_aux, int splitk,
+                              int bn, void* stream) {
+  return lako::gemm_bf16(A, B, C, M, N, K, lda, ldb, ldc, a_mn, b_mn, epi, alpha, aux, ld_aux, splitk, bn,
+                         static_cast<cudaStream_t>(stream));
+}
