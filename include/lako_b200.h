@@ -41,8 +41,8 @@ int lako_gemm_bf16(const void* A, const void* B, void* C, int M, int N, int K, i
                    int b_mn, int epi, float alpha, const void* aux, int ld_aux, int splitk, int bn, void* stream);
 
 /* ---- T5LayerNorm (RMSNorm) fused with the residual add: HF:55-68 + HF:375,149 ------------------- */
-int lako_rmsnorm_fwd(float* x, const void* delta_bf16, const float* w, void* out_bf16, float* rstd, int rows, int d,
-                     float eps, float out_scale, void* stream);
+int lako_rmsnorm_fwd(const float* x, const void* delta_bf16, float* x_out, const float* w, void* out_bf16, float* rstd,
+                     int rows, int d, float eps, float out_scale, void* stream);
 int lako_rmsnorm_bwd(const void* dy_bf16, const float* x, const float* rstd, const float* w, float* dres,
                      void* dres_bf16, float* dw, int rows, int d, int accumulate, float dy_scale, void* stream);
 
@@ -68,6 +68,91 @@ int lako_grad_sumsq(const float* g, size_t n, float* out_scalar, void* stream);
 int lako_adamw_step(float* p, float* m, float* v, const float* g, void* w_bf16, size_t n, const float* sumsq,
                     float grad_scale, float clip, float lr, float beta1, float beta2, float eps, float wd,
                     void* stream);
+
+
+/* ==== model-level entry points: the FiDT5 reader itself =========================================
+ * One flat parameter buffer holds every weight (fp32 master `w_f32`, bf16 compute copy `w_bf16`,
+ * fp32 gradients `g_f32`, all with the element offsets lako_fidt5_layout() reports); q,k,v of one
+ * attention are adjacent (one fused [3*inner][d] projection) and the cross-attention k,v of ALL
+ * decoder layers are adjacent (one fused [n_layers*2*inner][d] projection of the encoder memory). */
+#define LAKO_MAX_LAYERS 48
+
+typedef struct {
+  int d_model, n_heads, d_ff, n_layers, vocab, n_buckets; /* d_kv is 64 (t5-small..t5-11b) */
+  float eps;
+} lako_dims;
+
+typedef struct {
+  size_t shared;
+  size_t enc_ln0[LAKO_MAX_LAYERS], enc_qkv[LAKO_MAX_LAYERS], enc_o[LAKO_MAX_LAYERS], enc_ln1[LAKO_MAX_LAYERS],
+      enc_wi[LAKO_MAX_LAYERS], enc_wo[LAKO_MAX_LAYERS];
+  size_t enc_relbias, enc_final_ln;
+  size_t dec_ln0[LAKO_MAX_LAYERS], dec_qkv[LAKO_MAX_LAYERS], dec_o[LAKO_MAX_LAYERS], dec_ln1[LAKO_MAX_LAYERS],
+      dec_xq[LAKO_MAX_LAYERS], dec_xo[LAKO_MAX_LAYERS], dec_ln2[LAKO_MAX_LAYERS], dec_wi[LAKO_MAX_LAYERS],
+      dec_wo[LAKO_MAX_LAYERS];
+  size_t dec_xkv, dec_relbias, dec_final_ln;
+  size_t total; /* elements */
+} lako_layout;
+
+typedef struct {
+  lako_dims dims;
+  const float* w_f32; /* flat fp32 master weights (norm gains, embedding gather and bias tables read these) */
+  const void* w_bf16; /* flat bf16 copy (GEMM operands) */
+  float* g_f32;       /* flat fp32 gradients (backward accumulates; may be NULL for inference) */
+  const int* enc_buckets; /* int32 device tables: bucket(rel) at index rel + bucket_center, HF:188-234 */
+  const int* dec_buckets;
+  int bucket_center;
+} lako_fidt5;
+
+typedef struct {
+  const int64_t* ids;        /* [B][N][L] passage token ids (src/data.py:148 passage_ids) */
+  const unsigned char* mask; /* [B][N][L] 1 = token, 0 = pad (passage_masks, bool) */
+  const int64_t* labels;     /* [B][T], -100 = ignore (target_ids); NULL for generate */
+  int B, N, L, T;
+  void* workspace; /* >= lako_fidt5_workspace_bytes(...) */
+  size_t workspace_bytes;
+  float* logits; /* out: [B*T][vocab] fp32 */
+  float* stats;  /* out: stats[0] = sum of token losses, stats[1] = number of non-ignored targets */
+  int count_is_set; /* 1: stats[1] already holds the (global, all-reduced) count and stats[0] is zeroed */
+} lako_batch;
+
+int lako_fidt5_layout(const lako_dims* dims, lako_layout* out);
+/* mode 0 = forward only (eval loss), 1 = training (keeps activations for lako_fidt5_backward) */
+size_t lako_fidt5_workspace_bytes(const lako_dims* dims, int B, int N, int L, int T, int mode);
+/* FiDT5.forward (src/model.py:39-51) + T5 loss (HF:1105-1117) */
+int lako_fidt5_forward(const lako_fidt5* m, const lako_batch* b, int mode, void* stream);
+/* loss.backward() (train_reader.py:73) into g_f32; requires a mode-1 forward on the same workspace.
+ * loss_grad: device scalar d(objective)/d(loss) (NULL = 1) */
+int lako_fidt5_backward(const lako_fidt5* m, const lako_batch* b, const float* loss_grad, void* stream);
+/* FiDT5.generate (src/model.py:54-60), greedy with KV cache; synchronises the stream once per token
+ * to test for early stop.  tok_score_* (may be NULL) receive the step-0 cross-attention score sums
+ * that src/model.py:327-329 + :152-167 derive from score_storage. */
+size_t lako_fidt5_generate_workspace_bytes(const lako_dims* dims, int B, int N, int L, int max_length);
+int lako_fidt5_generate(const lako_fidt5* m, const lako_batch* b, int max_length, int64_t* out_ids, int* out_len,
+                        float* tok_score_first, float* tok_score_last, void* stream);
+
+/* ---- attention kernels (unit-test entry points; the model calls them internally) --------------- */
+int lako_build_bias_lut(const float* table, const int* buckets, float* lut, int H, int L, int bucket_center,
+                        void* stream);
+int lako_fold_dlut(const float* dlut, const int* buckets, float* dtable, int H, int L, int bucket_center, int nb,
+                   void* stream);
+/* encoder self-attention HF:253-344 per passage (src/model.py:230-232); qkv bf16 [P*L][3*H*64] */
+int lako_enc_attn_fwd(const void* qkv, const unsigned char* mask, const float* bias_lut, void* out, float* lse, int P,
+                      int L, int H, void* stream);
+int lako_enc_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse, const unsigned char* mask,
+                      const float* bias_lut, void* dqkv, float* dlut, int P, int L, int H, void* stream);
+/* cross-attention over the fused memory, src/model.py:286-349 */
+size_t lako_xattn_workspace_bytes(int B, int H, int T, int M);
+int lako_xattn_fwd(const void* q, const void* kv, const unsigned char* mask, void* out, float* lse, float* tok_score,
+                   float* workspace, int B, int T, int M, int H, int ldq, int ldkv, int koff, int voff, int ldo,
+                   void* stream);
+int lako_xattn_bwd(const void* q, const void* kv, const unsigned char* mask, const void* out, const void* dout,
+                   const float* lse, void* dkv, float* dq_f32, int B, int T, int M, int H, int ldq, int ldkv, int koff,
+                   int voff, int ldo, void* stream);
+/* causal decoder self-attention HF:253-344,438-445 */
+int lako_dself_fwd(const void* qkv, const float* lut, void* out, float* probs, int B, int T, int H, void* stream);
+int lako_dself_bwd(const void* qkv, const void* dout, const float* probs, void* dqkv, float* dlut, int B, int T, int H,
+                   void* stream);
 
 #ifdef __cplusplus
 }

@@ -16,10 +16,10 @@ using namespace lako;
 
 extern "C" {
 
-int lako_rmsnorm_fwd(float* x, const void* delta, const float* w, void* out, float* rstd, int rows, int d, float eps,
-                     float out_scale, void* stream) {
+int lako_rmsnorm_fwd(const float* x, const void* delta, float* x_out, const float* w, void* out, float* rstd, int rows,
+                     int d, float eps, float out_scale, void* stream) {
   ARCH_GUARD();
-  return rmsnorm_fwd(x, CBF(delta), w, BF(out), rstd, rows, d, eps, out_scale, ST(stream));
+  return rmsnorm_fwd(x, CBF(delta), x_out, w, BF(out), rstd, rows, d, eps, out_scale, ST(stream));
 }
 int lako_rmsnorm_bwd(const void* dy, const float* x, const float* rstd, const float* w, float* dres, void* dres_bf16,
                      float* dw, int rows, int d, int accumulate, float dy_scale, void* stream) {
@@ -65,6 +65,51 @@ int lako_adamw_step(float* p, float* m, float* v, const float* g, void* w_bf16, 
                     void* stream) {
   ARCH_GUARD();
   return adamw_step(p, m, v, g, BF(w_bf16), n, sumsq, grad_scale, clip, lr, beta1, beta2, eps, wd, ST(stream));
+}
+
+int lako_build_bias_lut(const float* table, const int* buckets, float* lut, int H, int L, int bucket_center,
+                        void* stream) {
+  ARCH_GUARD();
+  return build_bias_lut(table, buckets, lut, H, L, bucket_center, ST(stream));
+}
+int lako_fold_dlut(const float* dlut, const int* buckets, float* dtable, int H, int L, int bucket_center, int nb,
+                   void* stream) {
+  ARCH_GUARD();
+  return fold_dlut(dlut, buckets, dtable, H, L, bucket_center, nb, ST(stream));
+}
+int lako_enc_attn_fwd(const void* qkv, const unsigned char* mask, const float* bias_lut, void* out, float* lse, int P,
+                      int L, int H, void* stream) {
+  ARCH_GUARD();
+  return enc_attn_fwd(CBF(qkv), mask, bias_lut, BF(out), lse, P, L, H, ST(stream));
+}
+int lako_enc_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse, const unsigned char* mask,
+                      const float* bias_lut, void* dqkv, float* dlut, int P, int L, int H, void* stream) {
+  ARCH_GUARD();
+  return enc_attn_bwd(CBF(qkv), CBF(out), CBF(dout), lse, mask, bias_lut, BF(dqkv), dlut, P, L, H, ST(stream));
+}
+size_t lako_xattn_workspace_bytes(int B, int H, int T, int M) { return xattn_workspace_bytes(B, H, T, M); }
+int lako_xattn_fwd(const void* q, const void* kv, const unsigned char* mask, void* out, float* lse, float* tok_score,
+                   float* workspace, int B, int T, int M, int H, int ldq, int ldkv, int koff, int voff, int ldo,
+                   void* stream) {
+  ARCH_GUARD();
+  return xattn_fwd(CBF(q), CBF(kv), mask, BF(out), lse, tok_score, workspace, B, T, M, H, ldq, ldkv, koff, voff, ldo,
+                   ST(stream));
+}
+int lako_xattn_bwd(const void* q, const void* kv, const unsigned char* mask, const void* out, const void* dout,
+                   const float* lse, void* dkv, float* dq_f32, int B, int T, int M, int H, int ldq, int ldkv, int koff,
+                   int voff, int ldo, void* stream) {
+  ARCH_GUARD();
+  return xattn_bwd(CBF(q), CBF(kv), mask, CBF(out), CBF(dout), lse, BF(dkv), dq_f32, B, T, M, H, ldq, ldkv, koff, voff,
+                   ldo, ST(stream));
+}
+int lako_dself_fwd(const void* qkv, const float* lut, void* out, float* probs, int B, int T, int H, void* stream) {
+  ARCH_GUARD();
+  return dself_fwd(CBF(qkv), lut, BF(out), probs, B, T, H, ST(stream));
+}
+int lako_dself_bwd(const void* qkv, const void* dout, const float* probs, void* dqkv, float* dlut, int B, int T, int H,
+                   void* stream) {
+  ARCH_GUARD();
+  return dself_bwd(CBF(qkv), CBF(dout), probs, BF(dqkv), dlut, B, T, H, ST(stream));
 }
 
 }  // extern "C"

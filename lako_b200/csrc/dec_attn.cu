@@ -1,0 +1,603 @@
+// Decoder-side attention kernels of the FiDT5 reader (SIMT; these are < 1 % of the FLOPs, the cost
+// is streaming the fused encoder memory's K/V once per layer):
+//
+//  * cross-attention over the fused memory (M = n_passages * text_maxlength keys per question),
+//    split over key chunks (flash-decoding style partial softmax + combine), forward and backward.
+//    Reference: cross_attention_forward /root/reference/src/model.py:286-349 (q k^T + mask, fp32
+//    softmax, probs v), and the score capture at :327-329 consumed by get_crossattention_scores
+//    (:143-167): instead of keeping (B,H,1,M) pre-softmax scores per layer alive, the step-0 scores
+//    are summed over heads (and layers, by accumulation) into tok_score[B][M] on the fly.
+//  * causal decoder self-attention with the causal-bucket relative bias (HF:modeling_t5.py:253-344,
+//    438-445), forward/backward for teacher-forced training (T <= 64) and the KV-cached
+//    single-token step used by greedy generate.
+#include "ops.cuh"
+
+namespace lako {
+
+constexpr float MASK_MIN_F = -3.4028234663852886e38f;
+constexpr int XA_CH = 128;      // keys per CTA
+constexpr int XA_TMAX = 64;     // max decoder length handled by the training kernels
+constexpr int XA_KPAD = 72;     // padded smem row (bf16 elements): 144 B rows -> conflict-free 16 B loads
+
+struct XAttnParams {
+  const __nv_bfloat16* q;     // [B*T][ldq], head h at column h*64
+  const __nv_bfloat16* kv;    // [B*M][ldkv], K head h at column koff + h*64, V at voff + h*64
+  const unsigned char* mask;  // [B][M], 1 = valid
+  float* part;                // [B][H][splits][T][66]  (o[64], m, l)
+  float* tok_score;           // [B][M] += sum_h masked pre-softmax score of query 0 (may be null)
+  int T, M, H, ldq, ldkv, koff, voff, splits;
+};
+
+__device__ __forceinline__ void load_row64_bf16_to_regs(const __nv_bfloat16* row, uint32_t (&r)[32]) {
+  const uint4* p4 = reinterpret_cast<const uint4*>(row);
+#pragma unroll
+  for (int u = 0; u < 8; ++u) {
+    const uint4 v = p4[u];
+    r[u * 4 + 0] = v.x;
+    r[u * 4 + 1] = v.y;
+    r[u * 4 + 2] = v.z;
+    r[u * 4 + 3] = v.w;
+  }
+}
+
+// stage a [rows<=128][64] bf16 tile from global (row pitch ld) into padded smem, zero-filling rows >= nrows
+__device__ __forceinline__ void stage_tile(const __nv_bfloat16* g, int ld, int nrows, __nv_bfloat16* s, int tid,
+                                           int nthreads) {
+  for (int i = tid; i < XA_CH * 8; i += nthreads) {
+    const int r = i >> 3, u = i & 7;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (r < nrows) v = *reinterpret_cast<const uint4*>(g + static_cast<size_t>(r) * ld + u * 8);
+    *reinterpret_cast<uint4*>(s + r * XA_KPAD + u * 8) = v;
+  }
+}
+
+__global__ void __launch_bounds__(128) xattn_fwd_kernel(const XAttnParams p) {
+  __shared__ __align__(16) __nv_bfloat16 sK[XA_CH * XA_KPAD];
+  __shared__ __align__(16) __nv_bfloat16 sV[XA_CH * XA_KPAD];
+  extern __shared__ float dyn[];  // q [T][64] fp32, scores [T][XA_CH]
+  float* sQ = dyn;
+  float* sS = dyn + p.T * 64;
+  const int split = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int k0 = split * XA_CH;
+  const int nk = min(XA_CH, p.M - k0);
+  const __nv_bfloat16* kbase = p.kv + (static_cast<size_t>(b) * p.M + k0) * p.ldkv + p.koff + h * 64;
+  const __nv_bfloat16* vbase = p.kv + (static_cast<size_t>(b) * p.M + k0) * p.ldkv + p.voff + h * 64;
+  stage_tile(kbase, p.ldkv, nk, sK, tid, 128);
+  stage_tile(vbase, p.ldkv, nk, sV, tid, 128);
+  for (int i = tid; i < p.T * 64; i += 128) {
+    const int t = i >> 6, d = i & 63;
+    sQ[i] = __bfloat162float(p.q[(static_cast<size_t>(b) * p.T + t) * p.ldq + h * 64 + d]);
+  }
+  __syncthreads();
+  // scores: thread == key
+  {
+    const int j = tid;
+    uint32_t kr[32];
+    load_row64_bf16_to_regs(sK + j * XA_KPAD, kr);
+    const bool valid = (j < nk) && p.mask[static_cast<size_t>(b) * p.M + k0 + j];
+    for (int t = 0; t < p.T; ++t) {
+      const float4* q4 = reinterpret_cast<const float4*>(sQ + t * 64);
+      float acc = 0.f;
+#pragma unroll
+      for (int u = 0; u < 16; ++u) {
+        const float4 qq = q4[u];
+        acc += qq.x * bf16_lo(kr[u * 2]) + qq.y * bf16_hi(kr[u * 2]) + qq.z * bf16_lo(kr[u * 2 + 1]) +
+               qq.w * bf16_hi(kr[u * 2 + 1]);
+      }
+      if (t == 0 && p.tok_score && valid) atomicAdd(&p.tok_score[static_cast<size_t>(b) * p.M + k0 + j], acc);
+      sS[t * XA_CH + j] = (j < nk) ? (valid ? acc : MASK_MIN_F) : -INFINITY;
+    }
+  }
+  __syncthreads();
+  // per-query partial softmax over this chunk: warp per query
+  float* part = p.part + ((static_cast<size_t>(b) * p.H + h) * p.splits + split) * p.T * 66;
+  for (int t = warp; t < p.T; t += 4) {
+    float v[4], m = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      v[i] = sS[t * XA_CH + lane + i * 32];
+      m = fmaxf(m, v[i]);
+    }
+    m = warp_max(m);
+    float l = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float e = (v[i] == -INFINITY) ? 0.f : __expf(v[i] - m);
+      sS[t * XA_CH + lane + i * 32] = e;
+      l += e;
+    }
+    l = warp_sum(l);
+    if (lane == 0) {
+      part[t * 66 + 64] = m;
+      part[t * 66 + 65] = l;
+    }
+  }
+  __syncthreads();
+  // o[t][d] = sum_j p[t][j] V[j][d]: thread = (d, t parity)
+  {
+    const int d = tid & 63;
+    for (int t = tid >> 6; t < p.T; t += 2) {
+      float acc = 0.f;
+      for (int j = 0; j < nk; ++j) acc += sS[t * XA_CH + j] * __bfloat162float(sV[j * XA_KPAD + d]);
+      part[t * 66 + d] = acc;
+    }
+  }
+}
+
+// combine the split partials: out[b,t,h*64+d] = sum_s exp(m_s - m) o_s / sum_s exp(m_s - m) l_s
+__global__ void xattn_combine_kernel(const float* __restrict__ part, __nv_bfloat16* __restrict__ out,
+                                     float* __restrict__ lse, int T, int H, int splits, int ldo) {
+  const int t = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int d = threadIdx.x;  // 64 threads
+  const float* pp = part + ((static_cast<size_t>(b) * H + h) * splits) * T * 66 + t * 66;
+  float m = -INFINITY;
+  for (int s = 0; s < splits; ++s) m = fmaxf(m, pp[static_cast<size_t>(s) * T * 66 + 64]);
+  float l = 0.f, o = 0.f;
+  for (int s = 0; s < splits; ++s) {
+    const float* ps = pp + static_cast<size_t>(s) * T * 66;
+    const float w = __expf(ps[64] - m);
+    l += w * ps[65];
+    o += w * ps[d];
+  }
+  out[(static_cast<size_t>(b) * T + t) * ldo + h * 64 + d] = __float2bfloat16(o / l);
+  if (lse && d == 0) lse[(static_cast<size_t>(b) * H + h) * T + t] = m + logf(l);
+}
+
+size_t xattn_workspace_bytes(int B, int H, int T, int M) {
+  const int splits = (M + XA_CH - 1) / XA_CH;
+  return static_cast<size_t>(B) * H * splits * T * 66 * sizeof(float);
+}
+
+int xattn_fwd(const __nv_bfloat16* q, const __nv_bfloat16* kv, const unsigned char* mask, __nv_bfloat16* out, float* lse,
+              float* tok_score, float* workspace, int B, int T, int M, int H, int ldq, int ldkv, int koff, int voff,
+              int ldo, cudaStream_t s) {
+  LAKO_REQUIRE(B > 0 && T > 0 && T <= XA_TMAX && M > 0 && H > 0, LAKO_ERR_UNSUPPORTED);
+  LAKO_REQUIRE(ldkv % 8 == 0 && koff % 8 == 0 && voff % 8 == 0, LAKO_ERR_BAD_ARG);
+  XAttnParams p;
+  p.q = q;
+  p.kv = kv;
+  p.mask = mask;
+  p.part = workspace;
+  p.tok_score = tok_score;
+  p.T = T;
+  p.M = M;
+  p.H = H;
+  p.ldq = ldq;
+  p.ldkv = ldkv;
+  p.koff = koff;
+  p.voff = voff;
+  p.splits = (M + XA_CH - 1) / XA_CH;
+  const size_t dyn = static_cast<size_t>(T) * (64 + XA_CH) * sizeof(float);
+  static bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute(xattn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         XA_TMAX * (64 + XA_CH) * (int)sizeof(float));
+    configured = true;
+  }
+  dim3 grid(p.splits, H, B);
+  xattn_fwd_kernel<<<grid, 128, dyn, s>>>(p);
+  LAKO_CHECK_LAUNCH();
+  dim3 g2(T, H, B);
+  xattn_combine_kernel<<<g2, 64, 0, s>>>(workspace, out, lse, T, H, p.splits, ldo);
+  LAKO_CHECK_LAUNCH();
+  return LAKO_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// cross-attention backward.  Per CTA: one 128-key chunk of one (question, head).
+//   dK[j] = sum_t dS[t][j] q[t],  dV[j] = sum_t P[t][j] dO[t]   -> bf16 into dkv (same layout as kv)
+//   dq[t] += sum_j dS[t][j] K[j]                                  -> fp32 atomics into dq_f32 [B*T][inner]
+// two threads per key (each owns 32 of the 64 head dims).
+// ------------------------------------------------------------------------------------------------
+struct XAttnBwdParams {
+  const __nv_bfloat16* q;
+  const __nv_bfloat16* kv;
+  const unsigned char* mask;
+  const __nv_bfloat16* out;   // [B*T][ldo] forward output
+  const __nv_bfloat16* dout;  // [B*T][ldo]
+  const float* lse;           // [B][H][T]
+  __nv_bfloat16* dkv;         // [B*M][ldkv]
+  float* dq;                  // [B*T][H*64] fp32, pre-zeroed
+  int T, M, H, ldq, ldkv, koff, voff, ldo;
+};
+
+__global__ void __launch_bounds__(256) xattn_bwd_kernel(const XAttnBwdParams p) {
+  __shared__ __align__(16) __nv_bfloat16 sK[XA_CH * XA_KPAD];
+  __shared__ __align__(16) __nv_bfloat16 sV[XA_CH * XA_KPAD];
+  extern __shared__ float dyn[];  // q [T][64], dO [T][64], dS [T][XA_CH], D[T], lse[T]
+  float* sQ = dyn;
+  float* sDO = sQ + p.T * 64;
+  float* sDS = sDO + p.T * 64;
+  float* sD = sDS + p.T * XA_CH;
+  float* sL = sD + p.T;
+  const int split = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int k0 = split * XA_CH;
+  const int nk = min(XA_CH, p.M - k0);
+  const size_t kvrow0 = static_cast<size_t>(b) * p.M + k0;
+  stage_tile(p.kv + kvrow0 * p.ldkv + p.koff + h * 64, p.ldkv, nk, sK, tid, 256);
+  stage_tile(p.kv + kvrow0 * p.ldkv + p.voff + h * 64, p.ldkv, nk, sV, tid, 256);
+  for (int i = tid; i < p.T * 64; i += 256) {
+    const int t = i >> 6, d = i & 63;
+    const size_t row = static_cast<size_t>(b) * p.T + t;
+    sQ[i] = __bfloat162float(p.q[row * p.ldq + h * 64 + d]);
+    sDO[i] = __bfloat162float(p.dout[row * p.ldo + h * 64 + d]);
+  }
+  __syncthreads();
+  for (int t = warp; t < p.T; t += 8) {  // D[t] = sum_d dO * O
+    const size_t row = static_cast<size_t>(b) * p.T + t;
+    float acc = sDO[t * 64 + lane] * __bfloat162float(p.out[row * p.ldo + h * 64 + lane]) +
+                sDO[t * 64 + lane + 32] * __bfloat162float(p.out[row * p.ldo + h * 64 + lane + 32]);
+    acc = warp_sum(acc);
+    if (lane == 0) {
+      sD[t] = acc;
+      sL[t] = p.lse[(static_cast<size_t>(b) * p.H + h) * p.T + t];
+    }
+  }
+  __syncthreads();
+  {
+    const int j = tid >> 1, half = tid & 1;  // key, which 32 dims
+    uint32_t kr[16], vr[16];
+    {
+      const uint4* k4 = reinterpret_cast<const uint4*>(sK + j * XA_KPAD + half * 32);
+      const uint4* v4 = reinterpret_cast<const uint4*>(sV + j * XA_KPAD + half * 32);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const uint4 a = k4[u], c = v4[u];
+        kr[u * 4] = a.x; kr[u * 4 + 1] = a.y; kr[u * 4 + 2] = a.z; kr[u * 4 + 3] = a.w;
+        vr[u * 4] = c.x; vr[u * 4 + 1] = c.y; vr[u * 4 + 2] = c.z; vr[u * 4 + 3] = c.w;
+      }
+    }
+    const bool valid = (j < nk) && p.mask[static_cast<size_t>(b) * p.M + k0 + j];
+    float dk[32], dv[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) dk[i] = dv[i] = 0.f;
+    for (int t = 0; t < p.T; ++t) {
+      const float* qt = sQ + t * 64 + half * 32;
+      const float* dot = sDO + t * 64 + half * 32;
+      float s = 0.f, dp = 0.f;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        s += qt[2 * i] * bf16_lo(kr[i]) + qt[2 * i + 1] * bf16_hi(kr[i]);
+        dp += dot[2 * i] * bf16_lo(vr[i]) + dot[2 * i + 1] * bf16_hi(vr[i]);
+      }
+      s += __shfl_xor_sync(0xffffffffu, s, 1);
+      dp += __shfl_xor_sync(0xffffffffu, dp, 1);
+      float pr = 0.f;
+      if (j < nk) pr = __expf((valid ? s : MASK_MIN_F) - sL[t]);
+      const float ds = pr * (dp - sD[t]);
+      if (half == 0) sDS[t * XA_CH + j] = ds;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        dk[i] += ds * qt[i];
+        dv[i] += pr * dot[i];
+      }
+    }
+    if (j < nk) {
+      __nv_bfloat16* dkrow = p.dkv + (kvrow0 + j) * p.ldkv + p.koff + h * 64 + half * 32;
+      __nv_bfloat16* dvrow = p.dkv + (kvrow0 + j) * p.ldkv + p.voff + h * 64 + half * 32;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        uint4 o;
+        o.x = pack_bf16x2(dk[u * 8 + 0], dk[u * 8 + 1]);
+        o.y = pack_bf16x2(dk[u * 8 + 2], dk[u * 8 + 3]);
+        o.z = pack_bf16x2(dk[u * 8 + 4], dk[u * 8 + 5]);
+        o.w = pack_bf16x2(dk[u * 8 + 6], dk[u * 8 + 7]);
+        *reinterpret_cast<uint4*>(dkrow + u * 8) = o;
+        o.x = pack_bf16x2(dv[u * 8 + 0], dv[u * 8 + 1]);
+        o.y = pack_bf16x2(dv[u * 8 + 2], dv[u * 8 + 3]);
+        o.z = pack_bf16x2(dv[u * 8 + 4], dv[u * 8 + 5]);
+        o.w = pack_bf16x2(dv[u * 8 + 6], dv[u * 8 + 7]);
+        *reinterpret_cast<uint4*>(dvrow + u * 8) = o;
+      }
+    }
+  }
+  __syncthreads();
+  // dq[t][d] += sum_j dS[t][j] K[j][d]
+  {
+    const int d = tid & 63;
+    for (int t = tid >> 6; t < p.T; t += 4) {
+      float acc = 0.f;
+      for (int j = 0; j < nk; ++j) acc += sDS[t * XA_CH + j] * __bfloat162float(sK[j * XA_KPAD + d]);
+      atomicAdd(&p.dq[(static_cast<size_t>(b) * p.T + t) * (p.H * 64) + h * 64 + d], acc);
+    }
+  }
+}
+
+int xattn_bwd(const __nv_bfloat16* q, const __nv_bfloat16* kv, const unsigned char* mask, const __nv_bfloat16* out,
+              const __nv_bfloat16* dout, const float* lse, __nv_bfloat16* dkv, float* dq_f32, int B, int T, int M,
+              int H, int ldq, int ldkv, int koff, int voff, int ldo, cudaStream_t s) {
+  LAKO_REQUIRE(B > 0 && T > 0 && T <= XA_TMAX && M > 0 && H > 0, LAKO_ERR_UNSUPPORTED);
+  XAttnBwdParams p;
+  p.q = q; p.kv = kv; p.mask = mask; p.out = out; p.dout = dout; p.lse = lse; p.dkv = dkv; p.dq = dq_f32;
+  p.T = T; p.M = M; p.H = H; p.ldq = ldq; p.ldkv = ldkv; p.koff = koff; p.voff = voff; p.ldo = ldo;
+  const size_t dyn = (static_cast<size_t>(T) * (128 + XA_CH) + 2 * T) * sizeof(float);
+  static bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute(xattn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (XA_TMAX * (128 + XA_CH) + 2 * XA_TMAX) * (int)sizeof(float));
+    configured = true;
+  }
+  dim3 grid((M + XA_CH - 1) / XA_CH, H, B);
+  xattn_bwd_kernel<<<grid, 256, dyn, s>>>(p);
+  LAKO_CHECK_LAUNCH();
+  return LAKO_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// decoder self-attention, teacher-forced (training): one CTA per (head, question), T <= 64.
+// qkv bf16 [B*T][3*inner]; lut fp32 [H][2T-1] (causal buckets; only rel <= 0 is used).
+// ------------------------------------------------------------------------------------------------
+struct DSelfParams {
+  const __nv_bfloat16* qkv;
+  const float* lut;
+  __nv_bfloat16* out;       // [B*T][inner]
+  float* probs;             // [B][H][T][T] fp32 saved for backward
+  int T, H, inner;
+};
+
+__global__ void __launch_bounds__(128) dself_fwd_kernel(const DSelfParams p) {
+  extern __shared__ float dyn[];
+  float (*sQ)[65] = reinterpret_cast<float (*)[65]>(dyn);
+  float (*sK)[65] = reinterpret_cast<float (*)[65]>(dyn + XA_TMAX * 65);
+  float (*sV)[65] = reinterpret_cast<float (*)[65]>(dyn + 2 * XA_TMAX * 65);
+  float (*sP)[XA_TMAX] = reinterpret_cast<float (*)[XA_TMAX]>(dyn + 3 * XA_TMAX * 65);
+  const int h = blockIdx.x, b = blockIdx.y, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int T = p.T;
+  for (int i = tid; i < T * 64; i += 128) {
+    const int t = i >> 6, d = i & 63;
+    const __nv_bfloat16* row = p.qkv + (static_cast<size_t>(b) * T + t) * 3 * p.inner + h * 64 + d;
+    sQ[t][d] = __bfloat162float(row[0]);
+    sK[t][d] = __bfloat162float(row[p.inner]);
+    sV[t][d] = __bfloat162float(row[2 * p.inner]);
+  }
+  __syncthreads();
+  const float* lut = p.lut + h * (2 * T - 1) + (T - 1);
+  for (int t = warp; t < T; t += 4) {
+    float s[2], m = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int j = lane + i * 32;
+      s[i] = -INFINITY;
+      if (j < T) {
+        float acc = 0.f;
+        for (int d = 0; d < 64; ++d) acc += sQ[t][d] * sK[j][d];
+        s[i] = (j <= t) ? acc + lut[j - t] : MASK_MIN_F;
+      }
+      m = fmaxf(m, s[i]);
+    }
+    m = warp_max(m);
+    float e[2], l = 0.f;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      e[i] = (s[i] == -INFINITY) ? 0.f : __expf(s[i] - m);
+      l += e[i];
+    }
+    l = warp_sum(l);
+    const float inv = 1.f / l;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int j = lane + i * 32;
+      if (j < T) {
+        sP[warp][j] = e[i] * inv;
+        if (p.probs) p.probs[((static_cast<size_t>(b) * p.H + h) * T + t) * T + j] = e[i] * inv;
+      }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int d = lane + i * 32;
+      float acc = 0.f;
+      for (int j = 0; j <= t; ++j) acc += sP[warp][j] * sV[j][d];
+      p.out[(static_cast<size_t>(b) * T + t) * p.inner + h * 64 + d] = __float2bfloat16(acc);
+    }
+    __syncwarp();
+  }
+}
+
+int dself_fwd(const __nv_bfloat16* qkv, const float* lut, __nv_bfloat16* out, float* probs, int B, int T, int H,
+              cudaStream_t s) {
+  LAKO_REQUIRE(T > 0 && T <= XA_TMAX, LAKO_ERR_UNSUPPORTED);
+  DSelfParams p{qkv, lut, out, probs, T, H, H * 64};
+  constexpr int smem = (3 * XA_TMAX * 65 + 4 * XA_TMAX) * (int)sizeof(float);
+  static bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute(dself_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    configured = true;
+  }
+  dself_fwd_kernel<<<dim3(H, B), 128, smem, s>>>(p);
+  LAKO_CHECK_LAUNCH();
+  return LAKO_OK;
+}
+
+struct DSelfBwdParams {
+  const __nv_bfloat16* qkv;
+  const __nv_bfloat16* dout;  // [B*T][inner]
+  const float* probs;         // [B][H][T][T]
+  __nv_bfloat16* dqkv;        // [B*T][3*inner]
+  float* dlut;                // [H][2T-1] += dS by offset
+  int T, H, inner;
+};
+
+__global__ void __launch_bounds__(128) dself_bwd_kernel(const DSelfBwdParams p) {
+  extern __shared__ float dyn[];
+  float (*sQ)[65] = reinterpret_cast<float (*)[65]>(dyn);
+  float (*sK)[65] = reinterpret_cast<float (*)[65]>(dyn + XA_TMAX * 65);
+  float (*sV)[65] = reinterpret_cast<float (*)[65]>(dyn + 2 * XA_TMAX * 65);
+  float (*sDO)[65] = reinterpret_cast<float (*)[65]>(dyn + 3 * XA_TMAX * 65);
+  float (*sP)[XA_TMAX + 1] = reinterpret_cast<float (*)[XA_TMAX + 1]>(dyn + 4 * XA_TMAX * 65);
+  float (*sDS)[XA_TMAX + 1] = reinterpret_cast<float (*)[XA_TMAX + 1]>(dyn + 5 * XA_TMAX * 65);
+  const int h = blockIdx.x, b = blockIdx.y, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int T = p.T;
+  for (int i = tid; i < T * 64; i += 128) {
+    const int t = i >> 6, d = i & 63;
+    const size_t r = static_cast<size_t>(b) * T + t;
+    const __nv_bfloat16* row = p.qkv + r * 3 * p.inner + h * 64 + d;
+    sQ[t][d] = __bfloat162float(row[0]);
+    sK[t][d] = __bfloat162float(row[p.inner]);
+    sV[t][d] = __bfloat162float(row[2 * p.inner]);
+    sDO[t][d] = __bfloat162float(p.dout[r * p.inner + h * 64 + d]);
+  }
+  for (int i = tid; i < T * T; i += 128) sP[i / T][i % T] = p.probs[(static_cast<size_t>(b) * p.H + h) * T * T + i];
+  __syncthreads();
+  // dS = P * (dP - rowsum(P * dP)), dP[t][j] = dO[t] . V[j]
+  for (int t = warp; t < T; t += 4) {
+    float dp[2], dsum = 0.f;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int j = lane + i * 32;
+      dp[i] = 0.f;
+      if (j < T && j <= t) {
+        float acc = 0.f;
+        for (int d = 0; d < 64; ++d) acc += sDO[t][d] * sV[j][d];
+        dp[i] = acc;
+        dsum += sP[t][j] * acc;
+      }
+    }
+    dsum = warp_sum(dsum);
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int j = lane + i * 32;
+      if (j < T) {
+        const float ds = (j <= t) ? sP[t][j] * (dp[i] - dsum) : 0.f;
+        sDS[t][j] = ds;
+        if (j <= t && p.dlut && ds != 0.f) atomicAdd(&p.dlut[h * (2 * T - 1) + (T - 1) + (j - t)], ds);
+      }
+    }
+  }
+  __syncthreads();
+  // dQ[t] = sum_j dS[t][j] K[j];  dK[j] = sum_t dS[t][j] Q[t];  dV[j] = sum_t P[t][j] dO[t]
+  for (int i = tid; i < T * 64; i += 128) {
+    const int t = i >> 6, d = i & 63;
+    float dq = 0.f, dk = 0.f, dv = 0.f;
+    for (int j = 0; j <= t; ++j) dq += sDS[t][j] * sK[j][d];
+    for (int tt = t; tt < T; ++tt) {
+      dk += sDS[tt][t] * sQ[tt][d];
+      dv += sP[tt][t] * sDO[tt][d];
+    }
+    __nv_bfloat16* row = p.dqkv + (static_cast<size_t>(b) * T + t) * 3 * p.inner + h * 64 + d;
+    row[0] = __float2bfloat16(dq);
+    row[p.inner] = __float2bfloat16(dk);
+    row[2 * p.inner] = __float2bfloat16(dv);
+  }
+}
+
+int dself_bwd(const __nv_bfloat16* qkv, const __nv_bfloat16* dout, const float* probs, __nv_bfloat16* dqkv, float* dlut,
+              int B, int T, int H, cudaStream_t s) {
+  LAKO_REQUIRE(T > 0 && T <= XA_TMAX, LAKO_ERR_UNSUPPORTED);
+  DSelfBwdParams p{qkv, dout, probs, dqkv, dlut, T, H, H * 64};
+  constexpr int smem = 6 * XA_TMAX * 65 * (int)sizeof(float);
+  static bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute(dself_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    configured = true;
+  }
+  dself_bwd_kernel<<<dim3(H, B), 128, smem, s>>>(p);
+  LAKO_CHECK_LAUNCH();
+  return LAKO_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// KV-cached single-token decoder self-attention (greedy generate step `pos`):
+// appends this step's k,v to the cache and attends over positions 0..pos.
+// qkv bf16 [B][3*inner]; cache bf16 [B][H][Tmax][64] x2; lut fp32 [H][2*Tmax-1] (causal buckets)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(64) dself_step_kernel(const __nv_bfloat16* __restrict__ qkv,
+                                                        __nv_bfloat16* __restrict__ kcache,
+                                                        __nv_bfloat16* __restrict__ vcache,
+                                                        const float* __restrict__ lut, __nv_bfloat16* __restrict__ out,
+                                                        int pos, int Tmax, int H, int inner) {
+  __shared__ float sQ[64], sS[256];
+  const int h = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
+  const __nv_bfloat16* row = qkv + static_cast<size_t>(b) * 3 * inner + h * 64;
+  __nv_bfloat16* kc = kcache + (static_cast<size_t>(b) * H + h) * Tmax * 64;
+  __nv_bfloat16* vc = vcache + (static_cast<size_t>(b) * H + h) * Tmax * 64;
+  sQ[tid] = __bfloat162float(row[tid]);
+  kc[pos * 64 + tid] = row[inner + tid];
+  vc[pos * 64 + tid] = row[2 * inner + tid];
+  __syncthreads();
+  const float* l = lut + h * (2 * Tmax - 1) + (Tmax - 1);
+  for (int j = tid; j <= pos; j += 64) {
+    float acc = 0.f;
+    for (int d = 0; d < 64; ++d) acc += sQ[d] * __bfloat162float(kc[j * 64 + d]);
+    sS[j] = acc + l[j - pos];
+  }
+  __syncthreads();
+  float m = -INFINITY;
+  for (int j = 0; j <= pos; ++j) m = fmaxf(m, sS[j]);
+  float lsum = 0.f, acc = 0.f;
+  for (int j = 0; j <= pos; ++j) {
+    const float e = __expf(sS[j] - m);
+    lsum += e;
+    acc += e * __bfloat162float(vc[j * 64 + tid]);
+  }
+  out[static_cast<size_t>(b) * inner + h * 64 + tid] = __float2bfloat16(acc / lsum);
+}
+
+int dself_step(const __nv_bfloat16* qkv, __nv_bfloat16* kcache, __nv_bfloat16* vcache, const float* lut,
+               __nv_bfloat16* out, int B, int pos, int Tmax, int H, cudaStream_t s) {
+  LAKO_REQUIRE(pos >= 0 && pos < Tmax && Tmax <= 256, LAKO_ERR_UNSUPPORTED);
+  dself_step_kernel<<<dim3(H, B), 64, 0, s>>>(qkv, kcache, vcache, lut, out, pos, Tmax, H, H * 64);
+  LAKO_CHECK_LAUNCH();
+  return LAKO_OK;
+}
+
+// greedy token selection: argmax over fp32 logits [B][ld], EOS/pad bookkeeping as HF greedy search
+// (SURVEY 3.3): finished rows emit pad (0); a row finishes when it emits EOS (1).
+__global__ void __launch_bounds__(256) greedy_pick_kernel(const float* __restrict__ logits, int V, int ld,
+                                                          long long* __restrict__ out_ids, int out_ld, int step,
+                                                          int* __restrict__ unfinished, int* __restrict__ n_unfinished,
+                                                          long long* __restrict__ next_ids) {
+  __shared__ float s_v[8];
+  __shared__ int s_i[8];
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const float* lr = logits + static_cast<size_t>(b) * ld;
+  float best = -INFINITY;
+  int bi = 0x7fffffff;
+  for (int c = tid; c < V; c += 256) {
+    const float v = lr[c];
+    if (v > best || (v == best && c < bi)) {
+      best = v;
+      bi = c;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (ov > best || (ov == best && oi < bi)) {
+      best = ov;
+      bi = oi;
+    }
+  }
+  if ((tid & 31) == 0) {
+    s_v[tid >> 5] = best;
+    s_i[tid >> 5] = bi;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    for (int w = 1; w < 8; ++w)
+      if (s_v[w] > best || (s_v[w] == best && s_i[w] < bi)) {
+        best = s_v[w];
+        bi = s_i[w];
+      }
+    const int unf = unfinished[b];
+    const long long tok = unf ? bi : 0;
+    out_ids[static_cast<size_t>(b) * out_ld + step] = tok;
+    next_ids[b] = tok;
+    if (unf && tok == 1) {
+      unfinished[b] = 0;
+      atomicSub(n_unfinished, 1);
+    }
+  }
+}
+
+int greedy_pick(const float* logits, int B, int V, int ld, long long* out_ids, int out_ld, int step, int* unfinished,
+                int* n_unfinished, long long* next_ids, cudaStream_t s) {
+  greedy_pick_kernel<<<B, 256, 0, s>>>(logits, V, ld, out_ids, out_ld, step, unfinished, n_unfinished, next_ids);
+  LAKO_CHECK_LAUNCH();
+  return LAKO_OK;
+}
+
+}  // namespace lako

@@ -16,15 +16,17 @@ namespace lako {
 
 // --------------------------------------------------------------------------------------------
 // residual-add + RMSNorm forward.  One warp per row, row cached in registers (d <= 1024, d % 128 == 0).
-//   x      fp32 [rows][d]   residual stream (updated in place when delta != nullptr)
+//   x      fp32 [rows][d]   residual stream in
 //   delta  bf16 [rows][d]   sub-layer output to add (may be null)
+//   x_out  fp32 [rows][d]   x + delta (may alias x, may be null when delta is null)
 //   out    bf16 [rows][d]   w * x * rstd * out_scale
 //   rstd   fp32 [rows]      saved for backward (may be null)
 // --------------------------------------------------------------------------------------------
 constexpr int NORM_MAX_VEC = 8;  // float4 per lane -> d <= 1024
 
-__global__ void __launch_bounds__(256) rmsnorm_fwd_kernel(float* __restrict__ x, const __nv_bfloat16* __restrict__ delta,
-                                                           const float* __restrict__ w, __nv_bfloat16* __restrict__ out,
+__global__ void __launch_bounds__(256) rmsnorm_fwd_kernel(const float* x, const __nv_bfloat16* __restrict__ delta,
+                                                           float* x_out, const float* __restrict__ w,
+                                                           __nv_bfloat16* __restrict__ out,
                                                            float* __restrict__ rstd_out, int rows, int d, float eps,
                                                            float out_scale) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -32,7 +34,8 @@ __global__ void __launch_bounds__(256) rmsnorm_fwd_kernel(float* __restrict__ x,
   if (warp >= rows) return;
   const int nvec = d >> 7;
   float4 xv[NORM_MAX_VEC];
-  float* xr = x + static_cast<size_t>(warp) * d;
+  const float* xr = x + static_cast<size_t>(warp) * d;
+  float* xo = x_out ? x_out + static_cast<size_t>(warp) * d : nullptr;
   const __nv_bfloat16* dr = delta ? delta + static_cast<size_t>(warp) * d : nullptr;
   float ss = 0.f;
 #pragma unroll
@@ -46,8 +49,8 @@ __global__ void __launch_bounds__(256) rmsnorm_fwd_kernel(float* __restrict__ x,
         v.y += bf16_hi(dd.x);
         v.z += bf16_lo(dd.y);
         v.w += bf16_hi(dd.y);
-        *reinterpret_cast<float4*>(xr + c) = v;
       }
+      if (xo && (dr || xo != xr)) *reinterpret_cast<float4*>(xo + c) = v;
       xv[i] = v;
       ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
     }
@@ -72,12 +75,12 @@ __global__ void __launch_bounds__(256) rmsnorm_fwd_kernel(float* __restrict__ x,
   }
 }
 
-int rmsnorm_fwd(float* x, const __nv_bfloat16* delta, const float* w, __nv_bfloat16* out, float* rstd, int rows, int d,
-                float eps, float out_scale, cudaStream_t s) {
+int rmsnorm_fwd(const float* x, const __nv_bfloat16* delta, float* x_out, const float* w, __nv_bfloat16* out,
+                float* rstd, int rows, int d, float eps, float out_scale, cudaStream_t s) {
   LAKO_REQUIRE(rows > 0 && d > 0 && d % 128 == 0 && d <= 128 * NORM_MAX_VEC, LAKO_ERR_UNSUPPORTED);
   const int warps_per_block = 8;
   const int grid = (rows + warps_per_block - 1) / warps_per_block;
-  rmsnorm_fwd_kernel<<<grid, warps_per_block * 32, 0, s>>>(x, delta, w, out, rstd, rows, d, eps, out_scale);
+  rmsnorm_fwd_kernel<<<grid, warps_per_block * 32, 0, s>>>(x, delta, x_out, w, out, rstd, rows, d, eps, out_scale);
   LAKO_CHECK_LAUNCH();
   return LAKO_OK;
 }
@@ -404,6 +407,20 @@ int cast_f32_to_bf16(const float* in, __nv_bfloat16* out, size_t n, cudaStream_t
   if (n == 0) return LAKO_OK;
   const size_t blocks = (n + 2047) / 2048;
   cast_f32_to_bf16_kernel<<<static_cast<unsigned>(blocks), 256, 0, s>>>(in, out, n);
+  LAKO_CHECK_LAUNCH();
+  return LAKO_OK;
+}
+
+// x *= *scalar (device scalar); used to apply d(loss) != 1 to the stored dlogits
+__global__ void scale_bf16_dev_kernel(__nv_bfloat16* __restrict__ x, size_t n, const float* __restrict__ scalar) {
+  const float sc = *scalar;
+  if (sc == 1.0f) return;
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) x[i] = __float2bfloat16(__bfloat162float(x[i]) * sc);
+}
+int scale_bf16_dev(__nv_bfloat16* x, size_t n, const float* scalar, cudaStream_t s) {
+  if (n == 0) return LAKO_OK;
+  scale_bf16_dev_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, s>>>(x, n, scalar);
   LAKO_CHECK_LAUNCH();
   return LAKO_OK;
 }

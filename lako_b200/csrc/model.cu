@@ -1,0 +1,562 @@
+// Host-side orchestration of the FiDT5 reader path: enqueues the kernels of one forward (with the
+// loss), one backward and the greedy decode loop on the caller's stream.  Pure C++ so that a step is
+// ~1k kernel launches issued back-to-back without an interpreter in between.
+//
+// Reference call stacks:
+//   FiDT5.forward            /root/reference/src/model.py:39-51   -> lako_fidt5_forward
+//   EncoderWrapper.forward   /root/reference/src/model.py:227-234 -> encode()
+//   loss.backward()          /root/reference/train_reader.py:73   -> lako_fidt5_backward
+//   FiDT5.generate           /root/reference/src/model.py:54-60   -> lako_fidt5_generate
+//   score capture            /root/reference/src/model.py:327-329 -> tok_score accumulation in generate
+#include <vector>
+
+#include "ops.cuh"
+
+using namespace lako;
+
+// ------------------------------------------------------------------------------------------------
+// flat parameter layout
+// ------------------------------------------------------------------------------------------------
+extern "C" int lako_fidt5_layout(const lako_dims* dm, lako_layout* lo) {
+  if (!dm || !lo) return LAKO_ERR_BAD_ARG;
+  LAKO_REQUIRE(dm->n_layers > 0 && dm->n_layers <= LAKO_MAX_LAYERS, LAKO_ERR_UNSUPPORTED);
+  LAKO_REQUIRE(dm->d_model % 128 == 0 && dm->d_model <= 1024, LAKO_ERR_UNSUPPORTED);
+  LAKO_REQUIRE(dm->d_ff % 8 == 0 && dm->vocab % 8 == 0 && dm->n_heads > 0, LAKO_ERR_UNSUPPORTED);
+  const size_t d = dm->d_model, inner = static_cast<size_t>(dm->n_heads) * 64, ff = dm->d_ff;
+  size_t off = 0;
+  auto take = [&](size_t n) {
+    const size_t o = off;
+    off += (n + 7) / 8 * 8;
+    return o;
+  };
+  lo->shared = take(static_cast<size_t>(dm->vocab) * d);
+  for (int l = 0; l < dm->n_layers; ++l) {
+    lo->enc_ln0[l] = take(d);
+    lo->enc_qkv[l] = take(3 * inner * d);
+    lo->enc_o[l] = take(d * inner);
+    lo->enc_ln1[l] = take(d);
+    lo->enc_wi[l] = take(ff * d);
+    lo->enc_wo[l] = take(d * ff);
+  }
+  lo->enc_relbias = take(static_cast<size_t>(dm->n_buckets) * dm->n_heads);
+  lo->enc_final_ln = take(d);
+  for (int l = 0; l < dm->n_layers; ++l) {
+    lo->dec_ln0[l] = take(d);
+    lo->dec_qkv[l] = take(3 * inner * d);
+    lo->dec_o[l] = take(d * inner);
+    lo->dec_ln1[l] = take(d);
+    lo->dec_xq[l] = take(inner * d);
+    lo->dec_xo[l] = take(d * inner);
+    lo->dec_ln2[l] = take(d);
+    lo->dec_wi[l] = take(ff * d);
+    lo->dec_wo[l] = take(d * ff);
+  }
+  lo->dec_xkv = take(static_cast<size_t>(dm->n_layers) * 2 * inner * d);
+  lo->dec_relbias = take(static_cast<size_t>(dm->n_buckets) * dm->n_heads);
+  lo->dec_final_ln = take(d);
+  lo->total = off;
+  return LAKO_OK;
+}
+
+namespace {
+
+struct Bump {
+  uint8_t* base;
+  size_t off = 0;
+  explicit Bump(void* b) : base(static_cast<uint8_t*>(b)) {}
+  template <typename T>
+  T* take(size_t n) {
+    off = (off + 255) & ~size_t(255);
+    T* p = base ? reinterpret_cast<T*>(base + off) : nullptr;
+    off += n * sizeof(T);
+    return p;
+  }
+};
+
+typedef __nv_bfloat16 bf16;
+
+struct EncLayerAct {
+  bf16 *n_a, *qkv, *ao, *n_f, *h;
+  float *lse, *rstd_a, *rstd_f;
+};
+struct DecLayerAct {
+  bf16 *n_s, *qkv, *ao, *n_c, *q, *xo, *n_f, *h;
+  float *probs, *lse, *rstd_s, *rstd_c, *rstd_f;
+};
+
+struct Work {
+  // sizes
+  int B, N, L, T, P, M, Mtok, BT;
+  // encoder
+  std::vector<float*> X;  // 2*nl+1 residual-stream snapshots (train) or 2 ping-pong (eval)
+  std::vector<EncLayerAct> enc;
+  float *rstd_enc_final, *lut_enc, *dlut_enc;
+  bf16 *mem, *delta_enc, *kv_all;
+  // decoder
+  std::vector<float*> Y;  // 3*nl+1
+  std::vector<DecLayerAct> dec;
+  float *rstd_dec_final, *lut_dec, *dlut_dec, *logits, *stats, *row_loss, *xattn_ws;
+  bf16 *hn, *delta_dec, *dlogits;
+  long long* dec_ids;
+  // backward temporaries
+  float *dres_enc, *dres_dec, *dq_f32;
+  bf16 *dres_enc_b, *dn_enc, *dh_enc, *dao_enc, *dqkv_enc, *dkv_all, *dmem;
+  bf16 *dres_dec_b, *dn_dec, *dh_dec, *dao_dec, *dqkv_dec, *dq_dec, *dhn;
+  size_t bytes;
+};
+
+// mode: 0 = eval forward (no activations kept), 1 = train (keep everything backward needs)
+void carve(const lako_dims& dm, int B, int N, int L, int T, int mode, void* base, Work& w) {
+  const int nl = dm.n_layers;
+  const size_t d = dm.d_model, inner = static_cast<size_t>(dm.n_heads) * 64, ff = dm.d_ff, H = dm.n_heads;
+  w.B = B; w.N = N; w.L = L; w.T = T;
+  w.P = B * N; w.M = N * L; w.Mtok = B * N * L; w.BT = B * T;
+  const size_t Mt = w.Mtok, BT = w.BT;
+  Bump b(base);
+  const bool train = mode == 1;
+  const int nX = train ? 2 * nl + 1 : 2;
+  w.X.resize(2 * nl + 1);
+  {
+    std::vector<float*> bufs(nX);
+    for (int i = 0; i < nX; ++i) bufs[i] = b.take<float>(Mt * d);
+    for (int i = 0; i <= 2 * nl; ++i) w.X[i] = bufs[train ? i : (i & 1)];
+  }
+  w.enc.resize(nl);
+  EncLayerAct shared_e{};
+  if (!train) {
+    shared_e.n_a = b.take<bf16>(Mt * d);
+    shared_e.qkv = b.take<bf16>(Mt * 3 * inner);
+    shared_e.ao = b.take<bf16>(Mt * inner);
+    shared_e.n_f = shared_e.n_a;
+    shared_e.h = b.take<bf16>(Mt * ff);
+    shared_e.lse = nullptr;
+    shared_e.rstd_a = shared_e.rstd_f = nullptr;
+  }
+  for (int l = 0; l < nl; ++l) {
+    if (!train) {
+      w.enc[l] = shared_e;
+      continue;
+    }
+    EncLayerAct& a = w.enc[l];
+    a.n_a = b.take<bf16>(Mt * d);
+    a.qkv = b.take<bf16>(Mt * 3 * inner);
+    a.ao = b.take<bf16>(Mt * inner);
+    a.n_f = b.take<bf16>(Mt * d);
+    a.h = b.take<bf16>(Mt * ff);
+    a.lse = b.take<float>(static_cast<size_t>(w.P) * H * L);
+    a.rstd_a = b.take<float>(Mt);
+    a.rstd_f = b.take<float>(Mt);
+  }
+  w.rstd_enc_final = train ? b.take<float>(Mt) : nullptr;
+  w.lut_enc = b.take<float>(H * (2 * L - 1));
+  w.mem = b.take<bf16>(Mt * d);
+  w.delta_enc = b.take<bf16>(Mt * d);
+  w.kv_all = b.take<bf16>(Mt * nl * 2 * inner);
+  // decoder
+  const int nY = train ? 3 * nl + 1 : 2;
+  w.Y.resize(3 * nl + 1);
+  {
+    std::vector<float*> bufs(nY);
+    for (int i = 0; i < nY; ++i) bufs[i] = b.take<float>(BT * d);
+    for (int i = 0; i <= 3 * nl; ++i) w.Y[i] = bufs[train ? i : (i & 1)];
+  }
+  w.dec.resize(nl);
+  DecLayerAct shared_d{};
+  if (!train) {
+    shared_d.n_s = b.take<bf16>(BT * d);
+    shared_d.qkv = b.take<bf16>(BT * 3 * inner);
+    shared_d.ao = b.take<bf16>(BT * inner);
+    shared_d.n_c = shared_d.n_s;
+    shared_d.q = b.take<bf16>(BT * inner);
+    shared_d.xo = b.take<bf16>(BT * inner);
+    shared_d.n_f = shared_d.n_s;
+    shared_d.h = b.take<bf16>(BT * ff);
+    shared_d.probs = nullptr;
+    shared_d.lse = nullptr;
+  }
+  for (int l = 0; l < nl; ++l) {
+    if (!train) {
+      w.dec[l] = shared_d;
+      continue;
+    }
+    DecLayerAct& a = w.dec[l];
+    a.n_s = b.take<bf16>(BT * d);
+    a.qkv = b.take<bf16>(BT * 3 * inner);
+    a.ao = b.take<bf16>(BT * inner);
+    a.n_c = b.take<bf16>(BT * d);
+    a.q = b.take<bf16>(BT * inner);
+    a.xo = b.take<bf16>(BT * inner);
+    a.n_f = b.take<bf16>(BT * d);
+    a.h = b.take<bf16>(BT * ff);
+    a.probs = b.take<float>(static_cast<size_t>(B) * H * T * T);
+    a.lse = b.take<float>(static_cast<size_t>(B) * H * T);
+    a.rstd_s = b.take<float>(BT);
+    a.rstd_c = b.take<float>(BT);
+    a.rstd_f = b.take<float>(BT);
+  }
+  w.rstd_dec_final = train ? b.take<float>(BT) : nullptr;
+  w.lut_dec = b.take<float>(H * (2 * T - 1));
+  w.hn = b.take<bf16>(BT * d);
+  w.delta_dec = b.take<bf16>(BT * d);
+  w.logits = nullptr;  // caller-provided
+  w.stats = nullptr;   // caller-provided
+  w.row_loss = b.take<float>(BT);
+  w.xattn_ws = b.take<float>(xattn_workspace_bytes(B, dm.n_heads, T, w.M) / sizeof(float));
+  w.dec_ids = b.take<long long>(BT);
+  if (train) {
+    const size_t vpad = (static_cast<size_t>(dm.vocab) + 7) / 8 * 8;
+    w.dlogits = b.take<bf16>(BT * vpad);
+    w.dlut_enc = b.take<float>(H * (2 * L - 1));
+    w.dlut_dec = b.take<float>(H * (2 * T - 1));
+    w.dres_enc = b.take<float>(Mt * d);
+    w.dres_enc_b = b.take<bf16>(Mt * d);
+    w.dn_enc = b.take<bf16>(Mt * d);
+    w.dh_enc = b.take<bf16>(Mt * ff);
+    w.dao_enc = b.take<bf16>(Mt * inner);
+    w.dqkv_enc = b.take<bf16>(Mt * 3 * inner);
+    w.dkv_all = b.take<bf16>(Mt * nl * 2 * inner);
+    w.dmem = b.take<bf16>(Mt * d);
+    w.dres_dec = b.take<float>(BT * d);
+    w.dres_dec_b = b.take<bf16>(BT * d);
+    w.dn_dec = b.take<bf16>(BT * d);
+    w.dh_dec = b.take<bf16>(BT * ff);
+    w.dao_dec = b.take<bf16>(BT * inner);
+    w.dqkv_dec = b.take<bf16>(BT * 3 * inner);
+    w.dq_dec = b.take<bf16>(BT * inner);
+    w.dq_f32 = b.take<float>(BT * inner);
+    w.dhn = b.take<bf16>(BT * d);
+  }
+  w.bytes = (b.off + 255) & ~size_t(255);
+}
+
+#define RC(x)            \
+  do {                   \
+    int rc__ = (x);      \
+    if (rc__) return rc__; \
+  } while (0)
+
+// y[M,N] = x[M,K] W[N,K]^T
+inline int lin_fwd(const bf16* x, const bf16* W, void* y, int M, int N, int K, int epi, float alpha, cudaStream_t s) {
+  return gemm_bf16(x, W, y, M, N, K, K, K, N, 0, 0, epi, alpha, nullptr, 0, 1, 0, s);
+}
+// dx[M,K] = dy[M,N] W[N,K]   (optionally masked by aux > 0)
+inline int lin_dgrad(const bf16* dy, const bf16* W, bf16* dx, int M, int N, int K, const bf16* relu_aux, float alpha,
+                     cudaStream_t s) {
+  return gemm_bf16(dy, W, dx, M, K, N, N, K, K, 0, 1, relu_aux ? EPI_BF16_MASK : EPI_BF16, alpha, relu_aux, K, 1, 0, s);
+}
+// dW[N,K] += alpha * dy[M,N]^T x[M,K]
+inline int lin_wgrad(const bf16* dy, const bf16* x, float* dW, int M, int N, int K, float alpha, cudaStream_t s) {
+  return gemm_bf16(dy, x, dW, N, K, M, N, K, K, 1, 1, EPI_F32_ATOMIC, alpha, nullptr, 0, 0, 0, s);
+}
+
+struct Ptrs {
+  const lako_dims* dm;
+  lako_layout lo;
+  const float* wf;
+  const bf16* wb;
+  float* g;
+  int d, inner, ff, H, nl, V;
+  float eps;
+};
+
+int make_ptrs(const lako_fidt5* m, Ptrs& p) {
+  LAKO_REQUIRE(m && m->w_f32 && m->w_bf16, LAKO_ERR_BAD_ARG);
+  p.dm = &m->dims;
+  RC(lako_fidt5_layout(&m->dims, &p.lo));
+  p.wf = m->w_f32;
+  p.wb = static_cast<const bf16*>(m->w_bf16);
+  p.g = m->g_f32;
+  p.d = m->dims.d_model;
+  p.H = m->dims.n_heads;
+  p.inner = p.H * 64;
+  p.ff = m->dims.d_ff;
+  p.nl = m->dims.n_layers;
+  p.V = m->dims.vocab;
+  p.eps = m->dims.eps;
+  return LAKO_OK;
+}
+
+// ---- encoder: ids (P*L) -> mem bf16 [Mtok][d] and kv_all bf16 [Mtok][nl*2*inner]
+int encode(const Ptrs& p, const lako_fidt5* m, Work& w, const long long* ids, const unsigned char* mask, bool train,
+           cudaStream_t s) {
+  const int d = p.d, inner = p.inner, ff = p.ff, nl = p.nl, Mt = w.Mtok;
+  RC(embed_gather(ids, p.wf + p.lo.shared, w.X[0], Mt, d, p.V, s));
+  RC(build_bias_lut(p.wf + p.lo.enc_relbias, m->enc_buckets, w.lut_enc, p.H, w.L, m->bucket_center, s));
+  for (int l = 0; l < nl; ++l) {
+    EncLayerAct& a = w.enc[l];
+    if (l == 0)
+      RC(rmsnorm_fwd(w.X[0], nullptr, nullptr, p.wf + p.lo.enc_ln0[l], a.n_a, a.rstd_a, Mt, d, p.eps, 1.f, s));
+    else
+      RC(rmsnorm_fwd(w.X[2 * l - 1], w.delta_enc, w.X[2 * l], p.wf + p.lo.enc_ln0[l], a.n_a, a.rstd_a, Mt, d, p.eps,
+                     1.f, s));
+    RC(lin_fwd(a.n_a, p.wb + p.lo.enc_qkv[l], a.qkv, Mt, 3 * inner, d, EPI_BF16, 1.f, s));
+    RC(enc_attn_fwd(a.qkv, mask, w.lut_enc, a.ao, a.lse, w.P, w.L, p.H, s));
+    RC(lin_fwd(a.ao, p.wb + p.lo.enc_o[l], w.delta_enc, Mt, d, inner, EPI_BF16, 1.f, s));
+    RC(rmsnorm_fwd(w.X[2 * l], w.delta_enc, w.X[2 * l + 1], p.wf + p.lo.enc_ln1[l], a.n_f, a.rstd_f, Mt, d, p.eps, 1.f,
+                   s));
+    RC(lin_fwd(a.n_f, p.wb + p.lo.enc_wi[l], a.h, Mt, ff, d, EPI_BF16_RELU, 1.f, s));
+    RC(lin_fwd(a.h, p.wb + p.lo.enc_wo[l], w.delta_enc, Mt, d, ff, EPI_BF16, 1.f, s));
+  }
+  RC(rmsnorm_fwd(w.X[2 * nl - 1], w.delta_enc, w.X[2 * nl], p.wf + p.lo.enc_final_ln, w.mem, w.rstd_enc_final, Mt, d,
+                 p.eps, 1.f, s));
+  // cross-attention K/V of ALL decoder layers in one GEMM (13.8 % of the model's FLOPs)
+  RC(lin_fwd(w.mem, p.wb + p.lo.dec_xkv, w.kv_all, Mt, nl * 2 * inner, d, EPI_BF16, 1.f, s));
+  (void)train;
+  return LAKO_OK;
+}
+
+}  // namespace
+
+extern "C" size_t lako_fidt5_workspace_bytes(const lako_dims* dm, int B, int N, int L, int T, int mode) {
+  Work w;
+  carve(*dm, B, N, L, T, mode, nullptr, w);
+  return w.bytes + 256;
+}
+
+// FiDT5.forward(input_ids, attention_mask, labels) -> loss (stats[0]/stats[1]) and logits
+extern "C" int lako_fidt5_forward(const lako_fidt5* m, const lako_batch* bt, int mode, void* stream) {
+  RC(check_arch());
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  Ptrs p;
+  RC(make_ptrs(m, p));
+  LAKO_REQUIRE(bt && bt->ids && bt->mask && bt->labels && bt->workspace && bt->logits && bt->stats, LAKO_ERR_BAD_ARG);
+  LAKO_REQUIRE(bt->T >= 1 && bt->T <= 64 && bt->L >= 1 && bt->L <= 256, LAKO_ERR_UNSUPPORTED);
+  Work w;
+  carve(m->dims, bt->B, bt->N, bt->L, bt->T, mode, bt->workspace, w);
+  LAKO_REQUIRE(w.bytes <= bt->workspace_bytes, LAKO_ERR_WORKSPACE);
+  const bool train = mode == 1;
+  const int d = p.d, inner = p.inner, ff = p.ff, nl = p.nl, BT = w.BT;
+  RC(encode(p, m, w, reinterpret_cast<const long long*>(bt->ids), bt->mask, train, s));
+
+  const long long* labels = reinterpret_cast<const long long*>(bt->labels);
+  RC(shift_right(labels, w.dec_ids, bt->B, bt->T, s));
+  RC(embed_gather(w.dec_ids, p.wf + p.lo.shared, w.Y[0], BT, d, p.V, s));
+  RC(build_bias_lut(p.wf + p.lo.dec_relbias, m->dec_buckets, w.lut_dec, p.H, bt->T, m->bucket_center, s));
+  for (int l = 0; l < nl; ++l) {
+    DecLayerAct& a = w.dec[l];
+    if (l == 0)
+      RC(rmsnorm_fwd(w.Y[0], nullptr, nullptr, p.wf + p.lo.dec_ln0[l], a.n_s, a.rstd_s, BT, d, p.eps, 1.f, s));
+    else
+      RC(rmsnorm_fwd(w.Y[3 * l - 1], w.delta_dec, w.Y[3 * l], p.wf + p.lo.dec_ln0[l], a.n_s, a.rstd_s, BT, d, p.eps,
+                     1.f, s));
+    RC(lin_fwd(a.n_s, p.wb + p.lo.dec_qkv[l], a.qkv, BT, 3 * inner, d, EPI_BF16, 1.f, s));
+    RC(dself_fwd(a.qkv, w.lut_dec, a.ao, a.probs, bt->B, bt->T, p.H, s));
+    RC(lin_fwd(a.ao, p.wb + p.lo.dec_o[l], w.delta_dec, BT, d, inner, EPI_BF16, 1.f, s));
+    RC(rmsnorm_fwd(w.Y[3 * l], w.delta_dec, w.Y[3 * l + 1], p.wf + p.lo.dec_ln1[l], a.n_c, a.rstd_c, BT, d, p.eps, 1.f,
+                   s));
+    RC(lin_fwd(a.n_c, p.wb + p.lo.dec_xq[l], a.q, BT, inner, d, EPI_BF16, 1.f, s));
+    RC(xattn_fwd(a.q, w.kv_all, bt->mask, a.xo, a.lse, nullptr, w.xattn_ws, bt->B, bt->T, w.M, p.H, inner,
+                 nl * 2 * inner, l * 2 * inner, l * 2 * inner + inner, inner, s));
+    RC(lin_fwd(a.xo, p.wb + p.lo.dec_xo[l], w.delta_dec, BT, d, inner, EPI_BF16, 1.f, s));
+    RC(rmsnorm_fwd(w.Y[3 * l + 1], w.delta_dec, w.Y[3 * l + 2], p.wf + p.lo.dec_ln2[l], a.n_f, a.rstd_f, BT, d, p.eps,
+                   1.f, s));
+    RC(lin_fwd(a.n_f, p.wb + p.lo.dec_wi[l], a.h, BT, ff, d, EPI_BF16_RELU, 1.f, s));
+    RC(lin_fwd(a.h, p.wb + p.lo.dec_wo[l], w.delta_dec, BT, d, ff, EPI_BF16, 1.f, s));
+  }
+  RC(rmsnorm_fwd(w.Y[3 * nl - 1], w.delta_dec, w.Y[3 * nl], p.wf + p.lo.dec_final_ln, w.hn, w.rstd_dec_final, BT, d,
+                 p.eps, 1.f, s));
+  // tied LM head: logits = (h * d^-0.5) E^T  (HF:1107-1110), fp32 out
+  const float alpha = 1.0f / sqrtf(static_cast<float>(d));
+  RC(lin_fwd(w.hn, p.wb + p.lo.shared, bt->logits, BT, p.V, d, EPI_F32, alpha, s));
+  if (!bt->count_is_set) RC(count_valid(labels, BT, bt->stats, s));
+  const size_t vpad = (static_cast<size_t>(p.V) + 7) / 8 * 8;
+  RC(ce_fwd_bwd(bt->logits, labels, bt->stats, w.row_loss, train ? w.dlogits : nullptr, BT, p.V, p.V,
+                static_cast<int>(vpad), s));
+  return LAKO_OK;
+}
+
+// loss.backward(): accumulates into the flat gradient buffer g_f32 (caller zeroes it: model.zero_grad())
+extern "C" int lako_fidt5_backward(const lako_fidt5* m, const lako_batch* bt, const float* loss_grad, void* stream) {
+  RC(check_arch());
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  Ptrs p;
+  RC(make_ptrs(m, p));
+  LAKO_REQUIRE(p.g != nullptr && bt && bt->workspace, LAKO_ERR_BAD_ARG);
+  Work w;
+  carve(m->dims, bt->B, bt->N, bt->L, bt->T, 1, bt->workspace, w);
+  LAKO_REQUIRE(w.bytes <= bt->workspace_bytes, LAKO_ERR_WORKSPACE);
+  const int d = p.d, inner = p.inner, ff = p.ff, nl = p.nl, BT = w.BT, Mt = w.Mtok, H = p.H;
+  const size_t vpad = (static_cast<size_t>(p.V) + 7) / 8 * 8;
+  const float alpha = 1.0f / sqrtf(static_cast<float>(d));
+  float* g = p.g;
+
+  cudaMemsetAsync(w.dlut_enc, 0, sizeof(float) * H * (2 * w.L - 1), s);
+  cudaMemsetAsync(w.dlut_dec, 0, sizeof(float) * H * (2 * w.T - 1), s);
+
+  // ---- LM head
+  if (loss_grad) RC(scale_bf16_dev(w.dlogits, static_cast<size_t>(BT) * vpad, loss_grad, s));
+  RC(gemm_bf16(w.dlogits, p.wb + p.lo.shared, w.dhn, BT, d, p.V, static_cast<int>(vpad), d, d, 0, 1, EPI_BF16, alpha,
+               nullptr, 0, 1, 0, s));
+  RC(gemm_bf16(w.dlogits, w.hn, g + p.lo.shared, p.V, d, BT, static_cast<int>(vpad), d, d, 1, 1, EPI_F32_ATOMIC, alpha,
+               nullptr, 0, 1, 0, s));
+  RC(rmsnorm_bwd(w.dhn, w.Y[3 * nl], w.rstd_dec_final, p.wf + p.lo.dec_final_ln, w.dres_dec, w.dres_dec_b,
+                 g + p.lo.dec_final_ln, BT, d, 0, 1.f, s));
+  // ---- decoder layers
+  for (int l = nl - 1; l >= 0; --l) {
+    DecLayerAct& a = w.dec[l];
+    // FFN
+    RC(lin_dgrad(w.dres_dec_b, p.wb + p.lo.dec_wo[l], w.dh_dec, BT, d, ff, a.h, 1.f, s));
+    RC(lin_wgrad(w.dres_dec_b, a.h, g + p.lo.dec_wo[l], BT, d, ff, 1.f, s));
+    RC(lin_dgrad(w.dh_dec, p.wb + p.lo.dec_wi[l], w.dn_dec, BT, ff, d, nullptr, 1.f, s));
+    RC(lin_wgrad(w.dh_dec, a.n_f, g + p.lo.dec_wi[l], BT, ff, d, 1.f, s));
+    RC(rmsnorm_bwd(w.dn_dec, w.Y[3 * l + 2], a.rstd_f, p.wf + p.lo.dec_ln2[l], w.dres_dec, w.dres_dec_b,
+                   g + p.lo.dec_ln2[l], BT, d, 1, 1.f, s));
+    // cross-attention
+    RC(lin_dgrad(w.dres_dec_b, p.wb + p.lo.dec_xo[l], w.dao_dec, BT, d, inner, nullptr, 1.f, s));
+    RC(lin_wgrad(w.dres_dec_b, a.xo, g + p.lo.dec_xo[l], BT, d, inner, 1.f, s));
+    cudaMemsetAsync(w.dq_f32, 0, sizeof(float) * BT * inner, s);
+    RC(xattn_bwd(a.q, w.kv_all, bt->mask, a.xo, w.dao_dec, a.lse, w.dkv_all, w.dq_f32, bt->B, bt->T, w.M, H, inner,
+                 nl * 2 * inner, l * 2 * inner, l * 2 * inner + inner, inner, s));
+    RC(cast_f32_to_bf16(w.dq_f32, w.dq_dec, static_cast<size_t>(BT) * inner, s));
+    RC(lin_dgrad(w.dq_dec, p.wb + p.lo.dec_xq[l], w.dn_dec, BT, inner, d, nullptr, 1.f, s));
+    RC(lin_wgrad(w.dq_dec, a.n_c, g + p.lo.dec_xq[l], BT, inner, d, 1.f, s));
+    RC(rmsnorm_bwd(w.dn_dec, w.Y[3 * l + 1], a.rstd_c, p.wf + p.lo.dec_ln1[l], w.dres_dec, w.dres_dec_b,
+                   g + p.lo.dec_ln1[l], BT, d, 1, 1.f, s));
+    // self-attention
+    RC(lin_dgrad(w.dres_dec_b, p.wb + p.lo.dec_o[l], w.dao_dec, BT, d, inner, nullptr, 1.f, s));
+    RC(lin_wgrad(w.dres_dec_b, a.ao, g + p.lo.dec_o[l], BT, d, inner, 1.f, s));
+    RC(dself_bwd(a.qkv, w.dao_dec, a.probs, w.dqkv_dec, w.dlut_dec, bt->B, bt->T, H, s));
+    RC(lin_dgrad(w.dqkv_dec, p.wb + p.lo.dec_qkv[l], w.dn_dec, BT, 3 * inner, d, nullptr, 1.f, s));
+    RC(lin_wgrad(w.dqkv_dec, a.n_s, g + p.lo.dec_qkv[l], BT, 3 * inner, d, 1.f, s));
+    RC(rmsnorm_bwd(w.dn_dec, w.Y[3 * l], a.rstd_s, p.wf + p.lo.dec_ln0[l], w.dres_dec, w.dres_dec_b,
+                   g + p.lo.dec_ln0[l], BT, d, 1, 1.f, s));
+  }
+  RC(embed_scatter_add(w.dec_ids, w.dres_dec, g + p.lo.shared, BT, d, p.V, s));
+  RC(fold_dlut(w.dlut_dec, m->dec_buckets, g + p.lo.dec_relbias, H, w.T, m->bucket_center, m->dims.n_buckets, s));
+  // ---- fused memory: all decoder layers' cross K/V projections at once
+  const int nkv = nl * 2 * inner;
+  RC(lin_dgrad(w.dkv_all, p.wb + p.lo.dec_xkv, w.dmem, Mt, nkv, d, nullptr, 1.f, s));
+  RC(lin_wgrad(w.dkv_all, w.mem, g + p.lo.dec_xkv, Mt, nkv, d, 1.f, s));
+  RC(rmsnorm_bwd(w.dmem, w.X[2 * nl], w.rstd_enc_final, p.wf + p.lo.enc_final_ln, w.dres_enc, w.dres_enc_b,
+                 g + p.lo.enc_final_ln, Mt, d, 0, 1.f, s));
+  // ---- encoder layers
+  for (int l = nl - 1; l >= 0; --l) {
+    EncLayerAct& a = w.enc[l];
+    RC(lin_dgrad(w.dres_enc_b, p.wb + p.lo.enc_wo[l], w.dh_enc, Mt, d, ff, a.h, 1.f, s));
+    RC(lin_wgrad(w.dres_enc_b, a.h, g + p.lo.enc_wo[l], Mt, d, ff, 1.f, s));
+    RC(lin_dgrad(w.dh_enc, p.wb + p.lo.enc_wi[l], w.dn_enc, Mt, ff, d, nullptr, 1.f, s));
+    RC(lin_wgrad(w.dh_enc, a.n_f, g + p.lo.enc_wi[l], Mt, ff, d, 1.f, s));
+    RC(rmsnorm_bwd(w.dn_enc, w.X[2 * l + 1], a.rstd_f, p.wf + p.lo.enc_ln1[l], w.dres_enc, w.dres_enc_b,
+                   g + p.lo.enc_ln1[l], Mt, d, 1, 1.f, s));
+    RC(lin_dgrad(w.dres_enc_b, p.wb + p.lo.enc_o[l], w.dao_enc, Mt, d, inner, nullptr, 1.f, s));
+    RC(lin_wgrad(w.dres_enc_b, a.ao, g + p.lo.enc_o[l], Mt, d, inner, 1.f, s));
+    RC(enc_attn_bwd(a.qkv, a.ao, w.dao_enc, a.lse, bt->mask, w.lut_enc, w.dqkv_enc, w.dlut_enc, w.P, w.L, H, s));
+    RC(lin_dgrad(w.dqkv_enc, p.wb + p.lo.enc_qkv[l], w.dn_enc, Mt, 3 * inner, d, nullptr, 1.f, s));
+    RC(lin_wgrad(w.dqkv_enc, a.n_a, g + p.lo.enc_qkv[l], Mt, 3 * inner, d, 1.f, s));
+    RC(rmsnorm_bwd(w.dn_enc, w.X[2 * l], a.rstd_a, p.wf + p.lo.enc_ln0[l], w.dres_enc, w.dres_enc_b,
+                   g + p.lo.enc_ln0[l], Mt, d, 1, 1.f, s));
+  }
+  RC(embed_scatter_add(reinterpret_cast<const long long*>(bt->ids), w.dres_enc, g + p.lo.shared, Mt, d, p.V, s));
+  RC(fold_dlut(w.dlut_enc, m->enc_buckets, g + p.lo.enc_relbias, H, w.L, m->bucket_center, m->dims.n_buckets, s));
+  return LAKO_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// greedy generate with KV cache (+ optional step-0 cross-attention token scores)
+// ------------------------------------------------------------------------------------------------
+namespace {
+struct GenWork {
+  Work enc;  // encoder part (eval carve with T=1)
+  bf16 *kc, *vc;  // [nl][B][H][Tmax][64]
+  float *lut_dec, *logits;
+  int *unfinished, *n_unf;
+  long long* next_ids;
+  size_t bytes;
+};
+void carve_gen(const lako_dims& dm, int B, int N, int L, int Tmax, void* base, GenWork& gw) {
+  carve(dm, B, N, L, 1, 0, base, gw.enc);
+  Bump b(base);
+  b.off = gw.enc.bytes;
+  const size_t H = dm.n_heads, nl = dm.n_layers;
+  gw.kc = b.take<bf16>(nl * B * H * Tmax * 64);
+  gw.vc = b.take<bf16>(nl * B * H * Tmax * 64);
+  gw.lut_dec = b.take<float>(H * (2 * Tmax - 1));
+  gw.logits = b.take<float>(static_cast<size_t>(B) * dm.vocab);
+  gw.unfinished = b.take<int>(B);
+  gw.n_unf = b.take<int>(1);
+  gw.next_ids = b.take<long long>(B);
+  gw.bytes = (b.off + 255) & ~size_t(255);
+}
+__global__ void gen_init_kernel(int* unfinished, int* n_unf, long long* next_ids, long long* out_ids, int B,
+                                int out_ld) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < B) {
+    unfinished[i] = 1;
+    next_ids[i] = 0;  // decoder_start_token_id = pad = 0
+    for (int t = 0; t < out_ld; ++t) out_ids[static_cast<size_t>(i) * out_ld + t] = 0;
+  }
+  if (i == 0) *n_unf = B;
+}
+}  // namespace
+
+extern "C" size_t lako_fidt5_generate_workspace_bytes(const lako_dims* dm, int B, int N, int L, int max_length) {
+  GenWork gw;
+  carve_gen(*dm, B, N, L, max_length, nullptr, gw);
+  return gw.bytes + 256;
+}
+
+// out_ids int64 [B][max_length] (device), *out_len (host) = number of generated columns incl. the start
+// token.  tok_score_first/last fp32 [B][N*L] (device, pre-zeroed by the caller, may be null):
+// sum over heads and over the first ceil(nl/2) / the remaining decoder layers of the masked step-0
+// pre-softmax cross-attention scores.
+extern "C" int lako_fidt5_generate(const lako_fidt5* m, const lako_batch* bt, int max_length, int64_t* out_ids,
+                                   int* out_len, float* tok_score_first, float* tok_score_last, void* stream) {
+  RC(check_arch());
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  Ptrs p;
+  RC(make_ptrs(m, p));
+  LAKO_REQUIRE(bt && bt->ids && bt->mask && bt->workspace && out_ids && out_len, LAKO_ERR_BAD_ARG);
+  LAKO_REQUIRE(max_length >= 2 && max_length <= 256 && bt->L <= 256, LAKO_ERR_UNSUPPORTED);
+  GenWork gw;
+  carve_gen(m->dims, bt->B, bt->N, bt->L, max_length, bt->workspace, gw);
+  LAKO_REQUIRE(gw.bytes <= bt->workspace_bytes, LAKO_ERR_WORKSPACE);
+  Work& w = gw.enc;
+  const int d = p.d, inner = p.inner, ff = p.ff, nl = p.nl, B = bt->B, H = p.H;
+  RC(encode(p, m, w, reinterpret_cast<const long long*>(bt->ids), bt->mask, false, s));
+  RC(build_bias_lut(p.wf + p.lo.dec_relbias, m->dec_buckets, gw.lut_dec, H, max_length, m->bucket_center, s));
+  gen_init_kernel<<<(B + 127) / 128, 128, 0, s>>>(gw.unfinished, gw.n_unf, gw.next_ids,
+                                                   reinterpret_cast<long long*>(out_ids), B, max_length);
+  LAKO_CHECK_LAUNCH();
+  const float alpha = 1.0f / sqrtf(static_cast<float>(d));
+  const int first_half = (nl + 1) / 2;
+  const size_t cache_l = static_cast<size_t>(B) * H * max_length * 64;
+  DecLayerAct& a = w.dec[0];
+  int len = 1;
+  for (int step = 0; step + 1 < max_length; ++step) {
+    RC(embed_gather(gw.next_ids, p.wf + p.lo.shared, w.Y[0], B, d, p.V, s));
+    for (int l = 0; l < nl; ++l) {
+      if (l == 0)
+        RC(rmsnorm_fwd(w.Y[0], nullptr, nullptr, p.wf + p.lo.dec_ln0[l], a.n_s, nullptr, B, d, p.eps, 1.f, s));
+      else
+        RC(rmsnorm_fwd(w.Y[0], w.delta_dec, w.Y[0], p.wf + p.lo.dec_ln0[l], a.n_s, nullptr, B, d, p.eps, 1.f, s));
+      RC(lin_fwd(a.n_s, p.wb + p.lo.dec_qkv[l], a.qkv, B, 3 * inner, d, EPI_BF16, 1.f, s));
+      RC(dself_step(a.qkv, gw.kc + l * cache_l, gw.vc + l * cache_l, gw.lut_dec, a.ao, B, step, max_length, H, s));
+      RC(lin_fwd(a.ao, p.wb + p.lo.dec_o[l], w.delta_dec, B, d, inner, EPI_BF16, 1.f, s));
+      RC(rmsnorm_fwd(w.Y[0], w.delta_dec, w.Y[0], p.wf + p.lo.dec_ln1[l], a.n_c, nullptr, B, d, p.eps, 1.f, s));
+      RC(lin_fwd(a.n_c, p.wb + p.lo.dec_xq[l], a.q, B, inner, d, EPI_BF16, 1.f, s));
+      float* ts = nullptr;
+      if (step == 0) ts = (l < first_half) ? tok_score_first : tok_score_last;
+      RC(xattn_fwd(a.q, w.kv_all, bt->mask, a.xo, nullptr, ts, w.xattn_ws, B, 1, w.M, H, inner, nl * 2 * inner,
+                   l * 2 * inner, l * 2 * inner + inner, inner, s));
+      RC(lin_fwd(a.xo, p.wb + p.lo.dec_xo[l], w.delta_dec, B, d, inner, EPI_BF16, 1.f, s));
+      RC(rmsnorm_fwd(w.Y[0], w.delta_dec, w.Y[0], p.wf + p.lo.dec_ln2[l], a.n_f, nullptr, B, d, p.eps, 1.f, s));
+      RC(lin_fwd(a.n_f, p.wb + p.lo.dec_wi[l], a.h, B, ff, d, EPI_BF16_RELU, 1.f, s));
+      RC(lin_fwd(a.h, p.wb + p.lo.dec_wo[l], w.delta_dec, B, d, ff, EPI_BF16, 1.f, s));
+    }
+    RC(rmsnorm_fwd(w.Y[0], w.delta_dec, w.Y[0], p.wf + p.lo.dec_final_ln, w.hn, nullptr, B, d, p.eps, 1.f, s));
+    RC(lin_fwd(w.hn, p.wb + p.lo.shared, gw.logits, B, p.V, d, EPI_F32, alpha, s));
+    RC(greedy_pick(gw.logits, B, p.V, p.V, reinterpret_cast<long long*>(out_ids), max_length, step + 1, gw.unfinished,
+                   gw.n_unf, gw.next_ids, s));
+    len = step + 2;
+    int n_unf = 0;
+    cudaMemcpyAsync(&n_unf, gw.n_unf, sizeof(int), cudaMemcpyDeviceToHost, s);
+    cudaError_t e = cudaStreamSynchronize(s);
+    if (e != cudaSuccess) {
+      set_last_error(cudaGetErrorString(e), __FILE__, __LINE__);
+      return LAKO_ERR_LAUNCH;
+    }
+    if (n_unf == 0) break;
+  }
+  *out_len = len;
+  return LAKO_OK;
+}

@@ -10,8 +10,8 @@ int gemm_bf16(const void* A, const void* B, void* C, int M, int N, int K, int ld
 enum : int { EPI_BF16 = 0, EPI_BF16_RELU = 1, EPI_F32 = 2, EPI_F32_ATOMIC = 3, EPI_BF16_MASK = 4 };
 
 // elementwise.cu
-int rmsnorm_fwd(float* x, const __nv_bfloat16* delta, const float* w, __nv_bfloat16* out, float* rstd, int rows, int d,
-                float eps, float out_scale, cudaStream_t s);
+int rmsnorm_fwd(const float* x, const __nv_bfloat16* delta, float* x_out, const float* w, __nv_bfloat16* out,
+                float* rstd, int rows, int d, float eps, float out_scale, cudaStream_t s);
 int rmsnorm_bwd(const __nv_bfloat16* dy, const float* x, const float* rstd, const float* w, float* dres,
                 __nv_bfloat16* dres_bf16, float* dw, int rows, int d, int accumulate, float dy_scale, cudaStream_t s);
 int embed_gather(const long long* ids, const float* table, float* out, int rows, int d, int vocab, cudaStream_t s);
@@ -22,10 +22,39 @@ int count_valid(const long long* labels, int n, float* stats, cudaStream_t s);
 int ce_fwd_bwd(const float* logits, const long long* labels, float* stats, float* row_loss, __nv_bfloat16* dlogits,
                int rows, int V, int ld, int ld_d, cudaStream_t s);
 int cast_f32_to_bf16(const float* in, __nv_bfloat16* out, size_t n, cudaStream_t s);
+int scale_bf16_dev(__nv_bfloat16* x, size_t n, const float* scalar, cudaStream_t s);
 int transpose_bf16(const __nv_bfloat16* in, __nv_bfloat16* out, int rows, int cols, int ld_in, int ld_out,
                    cudaStream_t s);
 int grad_sumsq(const float* g, size_t n, float* out, cudaStream_t s);
 int adamw_step(float* p, float* m, float* v, const float* g, __nv_bfloat16* w_bf16, size_t n, const float* sumsq,
                float grad_scale, float clip, float lr, float beta1, float beta2, float eps, float wd, cudaStream_t s);
+
+
+// enc_attn.cu
+int build_bias_lut(const float* table, const int* buckets, float* lut, int H, int L, int bucket_center, cudaStream_t s);
+int fold_dlut(const float* dlut, const int* buckets, float* dtable, int H, int L, int bucket_center, int nb,
+              cudaStream_t s);
+int enc_attn_fwd(const __nv_bfloat16* qkv, const unsigned char* mask, const float* bias_lut, __nv_bfloat16* out,
+                 float* lse, int P, int L, int H, cudaStream_t s);
+int enc_attn_bwd(const __nv_bfloat16* qkv, const __nv_bfloat16* out, const __nv_bfloat16* dout, const float* lse,
+                 const unsigned char* mask, const float* bias_lut, __nv_bfloat16* dqkv, float* dlut, int P, int L,
+                 int H, cudaStream_t s);
+
+// dec_attn.cu
+size_t xattn_workspace_bytes(int B, int H, int T, int M);
+int xattn_fwd(const __nv_bfloat16* q, const __nv_bfloat16* kv, const unsigned char* mask, __nv_bfloat16* out, float* lse,
+              float* tok_score, float* workspace, int B, int T, int M, int H, int ldq, int ldkv, int koff, int voff,
+              int ldo, cudaStream_t s);
+int xattn_bwd(const __nv_bfloat16* q, const __nv_bfloat16* kv, const unsigned char* mask, const __nv_bfloat16* out,
+              const __nv_bfloat16* dout, const float* lse, __nv_bfloat16* dkv, float* dq_f32, int B, int T, int M,
+              int H, int ldq, int ldkv, int koff, int voff, int ldo, cudaStream_t s);
+int dself_fwd(const __nv_bfloat16* qkv, const float* lut, __nv_bfloat16* out, float* probs, int B, int T, int H,
+              cudaStream_t s);
+int dself_bwd(const __nv_bfloat16* qkv, const __nv_bfloat16* dout, const float* probs, __nv_bfloat16* dqkv, float* dlut,
+              int B, int T, int H, cudaStream_t s);
+int dself_step(const __nv_bfloat16* qkv, __nv_bfloat16* kcache, __nv_bfloat16* vcache, const float* lut,
+               __nv_bfloat16* out, int B, int pos, int Tmax, int H, cudaStream_t s);
+int greedy_pick(const float* logits, int B, int V, int ld, long long* out_ids, int out_ld, int step, int* unfinished,
+                int* n_unfinished, long long* next_ids, cudaStream_t s);
 
 }  // namespace lako

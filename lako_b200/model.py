@@ -1,0 +1,560 @@
+"""FiDT5 -- drop-in for the reference's `src.model.FiDT5` (/root/reference/src/model.py:20-214), with
+every device operation running in the hand-written sm_100a kernels of liblako_b200.so.
+
+Kept from the reference's Python surface:
+  forward(input_ids (B,N,L), attention_mask (B,N,L), labels (B,T)) -> (loss, logits)   model.py:39-51
+  generate(input_ids, attention_mask, max_length) -> int64 (B, <=max_length)           model.py:54-60
+  overwrite_forward_crossattention / reset_score_storage / get_crossattention_scores   model.py:92-98,143-213
+  load_t5 / wrap_encoder / unwrap_encoder / set_checkpoint                             model.py:62-90
+  state_dict()/load_state_dict() with the reference's key names (encoder.encoder.block.N.module...)
+  save_pretrained / from_pretrained, parameters(), .cuda()/.train()/.eval(), encoder.n_passages
+
+There is no PyTorch/CPU fallback: without the CUDA library, or off sm_100, calls raise.
+"""
+from __future__ import annotations
+
+import ctypes
+import heapq
+import json
+import math
+import os
+from types import SimpleNamespace
+
+import numpy as np
+import torch
+from torch import nn
+
+from . import _native as nat
+
+MAX_LAYERS = 48
+
+
+class _Dims(ctypes.Structure):
+    _fields_ = [("d_model", ctypes.c_int), ("n_heads", ctypes.c_int), ("d_ff", ctypes.c_int),
+                ("n_layers", ctypes.c_int), ("vocab", ctypes.c_int), ("n_buckets", ctypes.c_int),
+                ("eps", ctypes.c_float)]
+
+
+_SZ = ctypes.c_size_t * MAX_LAYERS
+
+
+class _Layout(ctypes.Structure):
+    _fields_ = [("shared", ctypes.c_size_t),
+                ("enc_ln0", _SZ), ("enc_qkv", _SZ), ("enc_o", _SZ), ("enc_ln1", _SZ), ("enc_wi", _SZ), ("enc_wo", _SZ),
+                ("enc_relbias", ctypes.c_size_t), ("enc_final_ln", ctypes.c_size_t),
+                ("dec_ln0", _SZ), ("dec_qkv", _SZ), ("dec_o", _SZ), ("dec_ln1", _SZ), ("dec_xq", _SZ), ("dec_xo", _SZ),
+                ("dec_ln2", _SZ), ("dec_wi", _SZ), ("dec_wo", _SZ),
+                ("dec_xkv", ctypes.c_size_t), ("dec_relbias", ctypes.c_size_t), ("dec_final_ln", ctypes.c_size_t),
+                ("total", ctypes.c_size_t)]
+
+
+class _Model(ctypes.Structure):
+    _fields_ = [("dims", _Dims), ("w_f32", ctypes.c_void_p), ("w_bf16", ctypes.c_void_p), ("g_f32", ctypes.c_void_p),
+                ("enc_buckets", ctypes.c_void_p), ("dec_buckets", ctypes.c_void_p), ("bucket_center", ctypes.c_int)]
+
+
+class _Batch(ctypes.Structure):
+    _fields_ = [("ids", ctypes.c_void_p), ("mask", ctypes.c_void_p), ("labels", ctypes.c_void_p),
+                ("B", ctypes.c_int), ("N", ctypes.c_int), ("L", ctypes.c_int), ("T", ctypes.c_int),
+                ("workspace", ctypes.c_void_p), ("workspace_bytes", ctypes.c_size_t),
+                ("logits", ctypes.c_void_p), ("stats", ctypes.c_void_p), ("count_is_set", ctypes.c_int)]
+
+
+class FiDT5Config:
+    """The subset of transformers.T5Config the reader path reads (t5-base defaults)."""
+
+    def __init__(self, vocab_size=32128, d_model=768, d_kv=64, d_ff=3072, num_layers=12, num_decoder_layers=None,
+                 num_heads=12, relative_attention_num_buckets=32, relative_attention_max_distance=128,
+                 dropout_rate=0.1, layer_norm_epsilon=1e-6, initializer_factor=1.0, feed_forward_proj="relu",
+                 pad_token_id=0, eos_token_id=1, decoder_start_token_id=0, **unused):
+        self.vocab_size, self.d_model, self.d_kv, self.d_ff = vocab_size, d_model, d_kv, d_ff
+        self.num_layers = num_layers
+        self.num_decoder_layers = num_layers if num_decoder_layers is None else num_decoder_layers
+        self.num_heads = num_heads
+        self.relative_attention_num_buckets = relative_attention_num_buckets
+        self.relative_attention_max_distance = relative_attention_max_distance
+        self.dropout_rate = dropout_rate
+        self.layer_norm_epsilon = layer_norm_epsilon
+        self.initializer_factor = initializer_factor
+        self.feed_forward_proj = feed_forward_proj
+        self.pad_token_id, self.eos_token_id, self.decoder_start_token_id = pad_token_id, eos_token_id, decoder_start_token_id
+
+    @classmethod
+    def from_any(cls, cfg):
+        if isinstance(cfg, cls):
+            return cfg
+        if isinstance(cfg, dict):
+            return cls(**cfg)
+        return cls(**{k: getattr(cfg, k) for k in (
+            "vocab_size", "d_model", "d_kv", "d_ff", "num_layers", "num_decoder_layers", "num_heads",
+            "relative_attention_num_buckets", "relative_attention_max_distance", "dropout_rate",
+            "layer_norm_epsilon", "initializer_factor", "feed_forward_proj") if hasattr(cfg, k)})
+
+    def to_dict(self):
+        return dict(self.__dict__)
+
+    @classmethod
+    def t5(cls, size):
+        table = {"small": dict(d_model=512, d_ff=2048, num_layers=6, num_heads=8),
+                 "base": dict(d_model=768, d_ff=3072, num_layers=12, num_heads=12),
+                 "large": dict(d_model=1024, d_ff=4096, num_layers=24, num_heads=16)}
+        return cls(**table[size])
+
+
+def relative_position_bucket(rel, bidirectional, num_buckets=32, max_distance=128):
+    """Integer bucket of rel = key_pos - query_pos, evaluated with the same float32 expression as
+    HF:modeling_t5.py:188-234 so that bucket boundaries agree bit-for-bit."""
+    ret = torch.zeros_like(rel)
+    if bidirectional:
+        num_buckets //= 2
+        ret = ret + (rel > 0).long() * num_buckets
+        rel = rel.abs()
+    else:
+        rel = -torch.minimum(rel, torch.zeros_like(rel))
+    max_exact = num_buckets // 2
+    is_small = rel < max_exact
+    large = max_exact + (torch.log(rel.float() / max_exact) / math.log(max_distance / max_exact)
+                         * (num_buckets - max_exact)).long()
+    large = torch.minimum(large, torch.full_like(large, num_buckets - 1))
+    return ret + torch.where(is_small, rel, large)
+
+
+BUCKET_CENTER = 511
+
+
+def bucket_table(bidirectional, num_buckets, max_distance):
+    rel = torch.arange(-BUCKET_CENTER, BUCKET_CENTER + 1, dtype=torch.long)
+    return relative_position_bucket(rel, bidirectional, num_buckets, max_distance).to(torch.int32)
+
+
+class _Node(nn.Module):
+    """Bare container used to reproduce the reference's module tree (and so its state_dict names)."""
+
+    def forward(self, *a, **k):  # pragma: no cover
+        raise RuntimeError("lako_b200 sub-modules are containers; call FiDT5.forward/generate")
+
+
+def _enc_name(i, wrapped=True):
+    return f"encoder.encoder.block.{i}.module.layer" if wrapped else f"encoder.block.{i}.layer"
+
+
+class _LossFn(torch.autograd.Function):
+    """Ties `loss.backward()` (train_reader.py:73) to lako_fidt5_backward: gradients are accumulated by
+    the CUDA side directly into the flat gradient buffer that every Parameter.grad is a view of."""
+
+    @staticmethod
+    def forward(ctx, anchor, model, batch_keep, loss, logits):
+        ctx.model = model
+        ctx.batch_keep = batch_keep
+        ctx.mark_non_differentiable(logits)
+        return loss.clone(), logits
+
+    @staticmethod
+    def backward(ctx, grad_loss, _grad_logits):
+        ctx.model._run_backward(ctx.batch_keep, grad_loss)
+        return torch.zeros(1, device=grad_loss.device), None, None, None, None
+
+
+class FiDT5(nn.Module):
+    def __init__(self, config, emb_std=None, seed=None):
+        super().__init__()
+        self.config = FiDT5Config.from_any(config)
+        c = self.config
+        if c.d_kv != 64:
+            raise nat.LakoError("lako_b200 kernels are specialised for d_kv = 64 (every public T5 size)")
+        if c.num_decoder_layers != c.num_layers:
+            raise nat.LakoError("encoder/decoder depth must match (t5-small/base/large/3b/11b)")
+        if "relu" not in c.feed_forward_proj or "gated" in c.feed_forward_proj:
+            raise nat.LakoError("only the ReLU FFN of T5 v1.0 (what LaKo uses) is implemented")
+        self._dims = _Dims(c.d_model, c.num_heads, c.d_ff, c.num_layers, c.vocab_size,
+                           c.relative_attention_num_buckets, c.layer_norm_epsilon)
+        self._layout = _Layout()
+        nat.check(nat.lib().lako_fidt5_layout(ctypes.byref(self._dims), ctypes.byref(self._layout)), "lako_fidt5_layout")
+        self._total = int(self._layout.total)
+        self._flat = torch.zeros(self._total, dtype=torch.float32)
+        self._flat_grad = None
+        self._bf16 = None
+        self._bf16_version = -1
+        self._enc_buckets = bucket_table(True, c.relative_attention_num_buckets, c.relative_attention_max_distance)
+        self._dec_buckets = bucket_table(False, c.relative_attention_num_buckets, c.relative_attention_max_distance)
+        self._specs = self._param_specs()
+        self._build_tree()
+        self._anchor = torch.zeros(1, requires_grad=True)
+        self._ws = {}
+        self._capture = False
+        self._tok_first = self._tok_last = None
+        self.use_checkpoint = False
+        self._init_weights(emb_std, seed)
+
+    # ------------------------------------------------------------------ parameters
+    def _param_specs(self):
+        """reference-name -> (offset, shape) into the flat buffer."""
+        c, lo = self.config, self._layout
+        d, inner, ff, H, nb = c.d_model, c.num_heads * 64, c.d_ff, c.num_heads, c.relative_attention_num_buckets
+        s = {"shared.weight": (lo.shared, (c.vocab_size, d))}
+        for i in range(c.num_layers):
+            p = _enc_name(i)
+            s[f"{p}.0.SelfAttention.q.weight"] = (lo.enc_qkv[i], (inner, d))
+            s[f"{p}.0.SelfAttention.k.weight"] = (lo.enc_qkv[i] + inner * d, (inner, d))
+            s[f"{p}.0.SelfAttention.v.weight"] = (lo.enc_qkv[i] + 2 * inner * d, (inner, d))
+            s[f"{p}.0.SelfAttention.o.weight"] = (lo.enc_o[i], (d, inner))
+            if i == 0:
+                s[f"{p}.0.SelfAttention.relative_attention_bias.weight"] = (lo.enc_relbias, (nb, H))
+            s[f"{p}.0.layer_norm.weight"] = (lo.enc_ln0[i], (d,))
+            s[f"{p}.1.DenseReluDense.wi.weight"] = (lo.enc_wi[i], (ff, d))
+            s[f"{p}.1.DenseReluDense.wo.weight"] = (lo.enc_wo[i], (d, ff))
+            s[f"{p}.1.layer_norm.weight"] = (lo.enc_ln1[i], (d,))
+        s["encoder.encoder.final_layer_norm.weight"] = (lo.enc_final_ln, (d,))
+        for i in range(c.num_layers):
+            p = f"decoder.block.{i}.layer"
+            s[f"{p}.0.SelfAttention.q.weight"] = (lo.dec_qkv[i], (inner, d))
+            s[f"{p}.0.SelfAttention.k.weight"] = (lo.dec_qkv[i] + inner * d, (inner, d))
+            s[f"{p}.0.SelfAttention.v.weight"] = (lo.dec_qkv[i] + 2 * inner * d, (inner, d))
+            s[f"{p}.0.SelfAttention.o.weight"] = (lo.dec_o[i], (d, inner))
+            if i == 0:
+                s[f"{p}.0.SelfAttention.relative_attention_bias.weight"] = (lo.dec_relbias, (nb, H))
+            s[f"{p}.0.layer_norm.weight"] = (lo.dec_ln0[i], (d,))
+            s[f"{p}.1.EncDecAttention.q.weight"] = (lo.dec_xq[i], (inner, d))
+            s[f"{p}.1.EncDecAttention.k.weight"] = (lo.dec_xkv + (2 * i) * inner * d, (inner, d))
+            s[f"{p}.1.EncDecAttention.v.weight"] = (lo.dec_xkv + (2 * i + 1) * inner * d, (inner, d))
+            s[f"{p}.1.EncDecAttention.o.weight"] = (lo.dec_xo[i], (d, inner))
+            s[f"{p}.1.layer_norm.weight"] = (lo.dec_ln1[i], (d,))
+            s[f"{p}.2.DenseReluDense.wi.weight"] = (lo.dec_wi[i], (ff, d))
+            s[f"{p}.2.DenseReluDense.wo.weight"] = (lo.dec_wo[i], (d, ff))
+            s[f"{p}.2.layer_norm.weight"] = (lo.dec_ln2[i], (d,))
+        s["decoder.final_layer_norm.weight"] = (lo.dec_final_ln, (d,))
+        return s
+
+    TIED = ("encoder.encoder.embed_tokens.weight", "decoder.embed_tokens.weight", "lm_head.weight")
+
+    def _view(self, flat, name):
+        off, shape = self._specs[name]
+        n = int(np.prod(shape))
+        return flat[off:off + n].view(shape)
+
+    def _register(self, name, param):
+        parts = name.split(".")
+        node = self
+        for comp in parts[:-1]:
+            if comp not in node._modules:
+                node.add_module(comp, _Node())
+            node = node._modules[comp]
+        node.register_parameter(parts[-1], param)
+
+    def _build_tree(self):
+        self._params = {}
+        for name in self._specs:
+            p = nn.Parameter(self._view(self._flat, name))
+            self._params[name] = p
+            self._register(name, p)
+        for name in self.TIED:
+            self._register(name, self._params["shared.weight"])
+        self.encoder.n_passages = 1
+
+    def _rebind(self):
+        for name, p in self._params.items():
+            p.data = self._view(self._flat, name)
+            if self._flat_grad is not None:
+                p.grad = self._view(self._flat_grad, name)
+
+    def _apply(self, fn, recurse=True):
+        new_flat = fn(self._flat)
+        if new_flat.dtype != torch.float32:
+            raise nat.LakoError("FiDT5 keeps fp32 master weights; bf16 compute copies are managed internally")
+        self._flat = new_flat.contiguous()
+        if self._flat_grad is not None:
+            self._flat_grad = fn(self._flat_grad)
+        self._enc_buckets = fn(self._enc_buckets)
+        self._dec_buckets = fn(self._dec_buckets)
+        with torch.no_grad():
+            self._anchor = fn(self._anchor.detach()).requires_grad_(True)
+        self._bf16 = None
+        self._bf16_version = -1
+        self._ws = {}
+        self._tok_first = self._tok_last = None
+        self._rebind()
+        return self
+
+    @torch.no_grad()
+    def _init_weights(self, emb_std=None, seed=None):
+        """HF T5 `_init_weights` distributions (HF:modeling_t5.py:540-590)."""
+        c = self.config
+        f = c.initializer_factor
+        g = torch.Generator().manual_seed(seed) if seed is not None else None
+        d, inner, ff = c.d_model, c.num_heads * 64, c.d_ff
+
+        def normal_(p, std):
+            p.copy_(torch.randn(p.shape, generator=g) * std)
+
+        for name, p in self._params.items():
+            if name == "shared.weight":
+                normal_(p, f * 1.0 if emb_std is None else emb_std)
+            elif "layer_norm" in name:
+                p.fill_(f)
+            elif name.endswith(".q.weight"):
+                normal_(p, f * (d * c.d_kv) ** -0.5)
+            elif name.endswith(".k.weight") or name.endswith(".v.weight") or "relative_attention_bias" in name:
+                normal_(p, f * d ** -0.5)
+            elif name.endswith(".o.weight"):
+                normal_(p, f * inner ** -0.5)
+            elif name.endswith("wi.weight"):
+                normal_(p, f * d ** -0.5)
+            elif name.endswith("wo.weight"):
+                normal_(p, f * ff ** -0.5)
+
+    # ------------------------------------------------------------------ state dict plumbing
+    def state_dict(self, *args, **kwargs):
+        sd = super().state_dict(*args, **kwargs)
+        return sd
+
+    def load_state_dict(self, state_dict, strict=True, assign=False):
+        own = set(self._specs) | set(self.TIED)
+        ignore = {"decoder.block.0.layer.1.EncDecAttention.relative_attention_bias.weight"}  # 3.0.2-era key (D1)
+        missing = [k for k in self._specs if k not in state_dict and k != "shared.weight"]
+        if "shared.weight" not in state_dict and not any(t in state_dict for t in self.TIED):
+            missing.append("shared.weight")
+        unexpected = [k for k in state_dict if k not in own and k not in ignore]
+        if strict and (missing or unexpected):
+            raise RuntimeError(f"load_state_dict: missing {missing[:5]} unexpected {unexpected[:5]}")
+        with torch.no_grad():
+            for k, v in state_dict.items():
+                if k in self._specs:
+                    self._params[k].copy_(v.to(torch.float32))
+                elif k in self.TIED and "shared.weight" not in state_dict:
+                    self._params["shared.weight"].copy_(v.to(torch.float32))
+        return SimpleNamespace(missing_keys=missing, unexpected_keys=unexpected)
+
+    # the reference wraps/unwraps the encoder to load plain T5 checkpoints (model.py:62-82); here it is a
+    # key translation since there is no nn.Module encoder to swap.
+    def wrap_encoder(self, use_checkpoint=False):
+        self.use_checkpoint = use_checkpoint
+
+    def unwrap_encoder(self):
+        pass
+
+    @staticmethod
+    def _t5_to_fid_key(k):
+        if k.startswith("encoder.block."):
+            parts = k.split(".")
+            return "encoder.encoder.block." + parts[2] + ".module." + ".".join(parts[3:])
+        if k.startswith("encoder.") and not k.startswith("encoder.encoder."):
+            return "encoder." + k
+        return k
+
+    def load_t5(self, state_dict):
+        self.load_state_dict({self._t5_to_fid_key(k): v for k, v in state_dict.items()})
+
+    def set_checkpoint(self, use_checkpoint):
+        # Activation recompute is not needed at 180 GB HBM for the shipped shapes; the flag is kept for
+        # API parity (model.py:84-90) and has no numerical effect there either.
+        self.use_checkpoint = use_checkpoint
+
+    def save_pretrained(self, path):
+        os.makedirs(path, exist_ok=True)
+        with open(os.path.join(path, "config.json"), "w") as f:
+            json.dump(self.config.to_dict(), f)
+        torch.save({k: v.detach().cpu() for k, v in self.state_dict().items()}, os.path.join(path, "pytorch_model.bin"))
+
+    @classmethod
+    def from_pretrained(cls, path):
+        with open(os.path.join(path, "config.json")) as f:
+            cfg = json.load(f)
+        model = cls(FiDT5Config(**cfg))
+        sd = torch.load(os.path.join(path, "pytorch_model.bin"), map_location="cpu")
+        model.load_state_dict(sd)
+        return model
+
+    # ------------------------------------------------------------------ device state
+    def _require_cuda(self):
+        if not self._flat.is_cuda:
+            raise nat.LakoError("FiDT5 runs only on a B200 (sm_100a): call .cuda() first; there is no CPU path")
+
+    def _ensure_grad(self):
+        if self._flat_grad is None or self._flat_grad.device != self._flat.device:
+            self._flat_grad = torch.zeros_like(self._flat)
+            self._rebind()
+
+    def zero_grad(self, set_to_none=False):
+        if self._flat_grad is not None:
+            self._flat_grad.zero_()
+            for name, p in self._params.items():
+                if p.grad is None:
+                    p.grad = self._view(self._flat_grad, name)
+
+    def _refresh_bf16(self):
+        if self._bf16 is None:
+            self._bf16 = torch.empty(self._total, dtype=torch.bfloat16, device=self._flat.device)
+            self._bf16_version = -1
+        sig = self._weights_signature()
+        if self._bf16_version != sig:
+            nat.check(nat.lib().lako_cast_f32_to_bf16(nat.ptr(self._flat), nat.ptr(self._bf16),
+                                                      ctypes.c_size_t(self._total), nat.stream_ptr()), "cast")
+            self._bf16_version = sig
+
+    def _weights_signature(self):
+        # in-place updates (optimizer.step, copy_) bump the version counters of the Parameters / the flat buffer
+        return self._flat._version + sum(p._version for p in self._params.values())
+
+    def mark_bf16_fresh(self):
+        """Called by the fused optimizer, which re-casts the weights itself."""
+        if self._bf16 is None:
+            self._bf16 = torch.empty(self._total, dtype=torch.bfloat16, device=self._flat.device)
+        self._bf16_version = self._weights_signature()
+
+    def _model_struct(self, with_grad):
+        self._refresh_bf16()
+        return _Model(self._dims, self._flat.data_ptr(), self._bf16.data_ptr(),
+                      self._flat_grad.data_ptr() if with_grad else 0,
+                      self._enc_buckets.data_ptr(), self._dec_buckets.data_ptr(), BUCKET_CENTER)
+
+    def _workspace(self, key, nbytes):
+        ws = self._ws.get(key[0])
+        if ws is None or ws[0] != key or ws[1].numel() < nbytes:
+            self._ws.pop(key[0], None)
+            ws = (key, torch.empty(nbytes, dtype=torch.uint8, device=self._flat.device))
+            self._ws[key[0]] = ws
+        return ws[1]
+
+    # ------------------------------------------------------------------ forward / backward
+    def forward(self, input_ids=None, attention_mask=None, labels=None, global_target_count=None, **kwargs):
+        self._require_cuda()
+        if labels is None:
+            raise nat.LakoError("FiDT5.forward needs labels (the reader is only called as model(..., labels=...)[0], "
+                                "train_reader.py:67-71); use generate() for inference")
+        if input_ids.dim() == 3:
+            self.encoder.n_passages = input_ids.size(1)
+        B = input_ids.size(0)
+        N = self.encoder.n_passages
+        ids = input_ids.reshape(B, N, -1).contiguous()
+        L = ids.size(2)
+        if attention_mask is None:
+            attention_mask = torch.ones_like(ids, dtype=torch.bool)
+        mask = attention_mask.reshape(B, N, L).to(torch.bool).contiguous()
+        labels = labels.contiguous()
+        T = labels.size(1)
+        train = torch.is_grad_enabled()
+        mode = 1 if train else 0
+        if train:
+            self._ensure_grad()
+        L_ = nat.lib()
+        L_.lako_fidt5_workspace_bytes.restype = ctypes.c_size_t
+        nbytes = L_.lako_fidt5_workspace_bytes(ctypes.byref(self._dims), B, N, L, T, mode)
+        ws = self._workspace(("fwd", B, N, L, T, mode), nbytes)
+        logits = torch.empty(B, T, self.config.vocab_size, dtype=torch.float32, device=ids.device)
+        stats = torch.zeros(2, dtype=torch.float32, device=ids.device)
+        count_is_set = 0
+        if global_target_count is not None:
+            stats[1] = global_target_count
+            count_is_set = 1
+        m = self._model_struct(with_grad=train)
+        bt = _Batch(ids.data_ptr(), mask.data_ptr(), labels.data_ptr(), B, N, L, T, ws.data_ptr(), ws.numel(),
+                    logits.data_ptr(), stats.data_ptr(), count_is_set)
+        nat.check(L_.lako_fidt5_forward(ctypes.byref(m), ctypes.byref(bt), mode, nat.stream_ptr()), "lako_fidt5_forward")
+        loss = stats[0] / torch.clamp(stats[1], min=1.0)
+        if train:
+            keep = (ids, mask, labels, ws, logits, stats, (B, N, L, T))
+            loss, logits = _LossFn.apply(self._anchor, self, keep, loss, logits)
+        return (loss, logits)
+
+    def _run_backward(self, keep, grad_loss):
+        ids, mask, labels, ws, logits, stats, (B, N, L, T) = keep
+        L_ = nat.lib()
+        m = self._model_struct(with_grad=True)
+        bt = _Batch(ids.data_ptr(), mask.data_ptr(), labels.data_ptr(), B, N, L, T, ws.data_ptr(), ws.numel(),
+                    logits.data_ptr(), stats.data_ptr(), 1)
+        gl = grad_loss.detach().to(torch.float32).reshape(1).contiguous()
+        nat.check(L_.lako_fidt5_backward(ctypes.byref(m), ctypes.byref(bt), nat.ptr(gl), nat.stream_ptr()),
+                  "lako_fidt5_backward")
+
+    # ------------------------------------------------------------------ generate + scores
+    @torch.no_grad()
+    def generate(self, input_ids, attention_mask, max_length):
+        self._require_cuda()
+        B, N, L = input_ids.shape
+        self.encoder.n_passages = N
+        ids = input_ids.contiguous()
+        mask = attention_mask.to(torch.bool).contiguous()
+        L_ = nat.lib()
+        L_.lako_fidt5_generate_workspace_bytes.restype = ctypes.c_size_t
+        nbytes = L_.lako_fidt5_generate_workspace_bytes(ctypes.byref(self._dims), B, N, L, max_length)
+        ws = self._workspace(("gen", B, N, L, max_length), nbytes)
+        out = torch.empty(B, max_length, dtype=torch.long, device=ids.device)
+        tf = tl = None
+        if self._capture and self._tok_first is None:
+            # reference semantics: scores are stored on the first decoder call after a reset (model.py:327-329)
+            self._tok_first = torch.zeros(B, N * L, dtype=torch.float32, device=ids.device)
+            self._tok_last = torch.zeros(B, N * L, dtype=torch.float32, device=ids.device)
+            tf, tl = self._tok_first, self._tok_last
+        m = self._model_struct(with_grad=False)
+        bt = _Batch(ids.data_ptr(), mask.data_ptr(), 0, B, N, L, 1, ws.data_ptr(), ws.numel(), 0, 0, 0)
+        out_len = ctypes.c_int(0)
+        nat.check(L_.lako_fidt5_generate(ctypes.byref(m), ctypes.byref(bt), max_length, nat.ptr(out),
+                                         ctypes.byref(out_len), nat.ptr(tf), nat.ptr(tl), nat.stream_ptr()),
+                  "lako_fidt5_generate")
+        return out[:, :out_len.value]
+
+    def overwrite_forward_crossattention(self):
+        """model.py:206-213: from now on the first decoder step after each reset records its scores."""
+        self._capture = True
+
+    def reset_score_storage(self):
+        """model.py:92-98."""
+        self._tok_first = self._tok_last = None
+
+    def token_scores(self, last_half):
+        """(B, N*L) fp32: masked step-0 pre-softmax cross-attention scores summed over heads and the selected
+        decoder layers -- what model.py:152-167 reduces score_storage to -- and the divisor of model.py:202."""
+        if self._tok_first is None:
+            raise nat.LakoError("no scores stored: call overwrite_forward_crossattention() and generate() first")
+        nl, H = self.config.num_layers, self.config.num_heads
+        if last_half:
+            return self._tok_last, (nl - (nl + 1) // 2) * H
+        return self._tok_first + self._tok_last, nl * H
+
+    @staticmethod
+    def find_index(fact_list, start):
+        try:
+            return fact_list.index(5, start)
+        except ValueError:
+            return -1
+
+    @staticmethod
+    def get_attention_score(fact_score_list, start, end, style):
+        if style == "mean":
+            return sum(fact_score_list[start:end]) / (end - start)
+        elif style == "max":
+            return max(fact_score_list[start:end])
+        elif style == "21mean":
+            num = max(int((end - start + 1) / 2), 1)
+            return sum(heapq.nlargest(num, fact_score_list[start:end])) / num
+
+    def get_crossattention_scores(self, opt, context_ids, tokenizer, context_mask):
+        """model.py:143-204 on the fused token-score tensor (same argument list, same float64 CPU result)."""
+        assert opt.stream == 2
+        fact_num = opt.n_context
+        bsz, n_passages, L = context_mask.shape
+        tok, div = self.token_scores(opt.use_last_half_layer_attention == "yes")
+        tok = tok.view(bsz, n_passages, L)
+        _, fact_scores = torch.chunk(tok, 2, dim=1)
+        fact_scores = fact_scores[:, 0].cpu().numpy()
+        ids_cpu = context_ids[:, 1].cpu().numpy()
+        out = []
+        for b in range(bsz):
+            fact_list = ids_cpu[b].tolist()
+            sc = fact_scores[b].tolist()
+            res, start = [], 2
+            for _ in range(fact_num):
+                end = self.find_index(fact_list, start) + 1
+                if end == 0:
+                    break
+                res.append(self.get_attention_score(sc, start, end, opt.attention_score_style))
+                start = end
+            if len(res) < fact_num and fact_list[-1] != 0:
+                end = len(fact_list)
+                if end > start:
+                    res.append(self.get_attention_score(sc, start, end, opt.attention_score_style))
+            while len(res) < fact_num:
+                res.append(-5)
+            assert len(res) == fact_num
+            out.append(np.array(res))
+        return torch.from_numpy(np.array(out)) / div

@@ -23,7 +23,7 @@ def test_rmsnorm_fwd_bwd(rows, d):
     x_in = x.clone()
     out = torch.empty(rows, d, device="cuda", dtype=torch.bfloat16)
     rstd = torch.empty(rows, device="cuda")
-    nat.check(L.lako_rmsnorm_fwd(nat.ptr(x), nat.ptr(delta), nat.ptr(w), nat.ptr(out), nat.ptr(rstd), rows, d,
+    nat.check(L.lako_rmsnorm_fwd(nat.ptr(x), nat.ptr(delta), nat.ptr(x), nat.ptr(w), nat.ptr(out), nat.ptr(rstd), rows, d,
                                  ctypes.c_float(1e-6), ctypes.c_float(1.0), nat.stream_ptr()))
     xr = (x_in + delta.float()).requires_grad_(True)
     wr = w.clone().requires_grad_(True)

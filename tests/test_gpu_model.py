@@ -1,0 +1,113 @@
+"""End-to-end parity of lako_b200.FiDT5 (CUDA, bf16 operands / fp32 accumulation) against
+(a) the golden outputs of the reference itself (tests/golden/*.pt) and (b) the fp32 oracle."""
+import glob
+import os
+import types
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.pt")))
+
+# tolerances from BASELINE.json north_star
+LOGIT_ATOL_BF16 = 2e-2
+SCORE_RTOL = 1e-2
+
+
+def _load(path):
+    from oracle import fidt5_oracle as O
+    from lako_b200.model import FiDT5, FiDT5Config
+    c = torch.load(path, weights_only=False)
+    cfg = O.T5Dims(**c["cfg"])
+    sd = O.perturb_norm_weights(O.init_state_dict(cfg, seed=c["seed"], emb_std=c["emb_std"]), seed=c["seed"] + 1)
+    if c.get("eos_alias") is not None:
+        sd["shared.weight"][1] = sd["shared.weight"][c["eos_alias"]] * 1.05
+    model = FiDT5(FiDT5Config(vocab_size=cfg.vocab, d_model=cfg.d_model, d_ff=cfg.d_ff, num_layers=cfg.n_layers,
+                              num_heads=cfg.n_heads))
+    model.load_state_dict(sd)
+    model = model.cuda()
+    return c, cfg, sd, model
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p) for p in GOLDEN])
+def test_forward_loss_logits_vs_reference(path):
+    c, cfg, sd, model = _load(path)
+    model.eval()
+    with torch.no_grad():
+        loss, logits = model(input_ids=c["ids"].cuda(), attention_mask=c["mask"].cuda(), labels=c["labels"].cuda())
+    err = (logits.cpu() - c["logits"]).abs().max().item()
+    print("max |dlogit|", err, "loss", loss.item(), "ref", c["loss"].item())
+    assert err < LOGIT_ATOL_BF16
+    assert abs(loss.item() - c["loss"].item()) < 5e-3
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p) for p in GOLDEN])
+def test_backward_vs_reference(path):
+    c, cfg, sd, model = _load(path)
+    model.train()
+    model.zero_grad()
+    loss, _ = model(input_ids=c["ids"].cuda(), attention_mask=c["mask"].cuda(), labels=c["labels"].cuda())
+    loss.backward()
+    torch.cuda.synchronize()
+    named = dict(model.named_parameters())
+    gn = torch.sqrt(sum((p.grad.double() ** 2).sum() for p in named.values())).item()
+    print("grad norm", gn, "ref", c["grad_norm"].item())
+    assert abs(gn - c["grad_norm"].item()) < 0.02 * c["grad_norm"].item()
+    for k, g in c["grads"].items():
+        mine = named[k].grad.cpu()
+        denom = g.abs().max().item() + 1e-8
+        rel = (mine - g).abs().max().item() / denom
+        print(f"{k}: rel max err {rel:.4f}")
+        assert rel < 0.05, (k, rel)
+    # second backward accumulates (loss.backward() semantics)
+    loss2, _ = model(input_ids=c["ids"].cuda(), attention_mask=c["mask"].cuda(), labels=c["labels"].cuda())
+    loss2.backward()
+    torch.cuda.synchronize()
+    gn2 = torch.sqrt(sum((p.grad.double() ** 2).sum() for p in named.values())).item()
+    assert abs(gn2 - 2 * gn) < 0.01 * gn
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p) for p in GOLDEN])
+def test_generate_and_scores_vs_reference(path):
+    c, cfg, sd, model = _load(path)
+    model.eval()
+    model.overwrite_forward_crossattention()
+    model.reset_score_storage()
+    out = model.generate(input_ids=c["ids"].cuda(), attention_mask=c["mask"].cuda(), max_length=c["max_length"])
+    assert out.cpu().tolist() == c["generated"].tolist()
+    if c["N"] % 2 == 0:
+        tok, div = model.token_scores(last_half=True)
+        ref = c["tok_scores_last_half"]
+        B, N, L = c["ids"].shape
+        err = (tok.cpu().view(B, N, L) - ref).abs().max().item()
+        assert err < SCORE_RTOL * ref.abs().max().item(), err
+        for style in ("mean", "max", "21mean"):
+            for lh in ("yes", "no"):
+                opt = types.SimpleNamespace(stream=2, n_context=c["n_context"], attention_score_style=style,
+                                            use_last_half_layer_attention=lh)
+                sc = model.get_crossattention_scores(opt, c["ids"], None, c["mask"].cuda())
+                ref = c[f"scores_{style}_{lh}"]
+                assert sc.dtype == torch.float64 and sc.shape == ref.shape
+                real = ref != (-5 / (div if lh == "yes" else cfg.n_layers * cfg.n_heads))
+                assert torch.allclose(sc, ref, rtol=SCORE_RTOL, atol=SCORE_RTOL * ref[real].abs().max().item())
+
+
+def test_state_dict_roundtrip_and_t5_names(tmp_path):
+    from oracle import fidt5_oracle as O
+    from lako_b200.model import FiDT5, FiDT5Config
+    cfg = O.T5_TINY
+    sd = O.init_state_dict(cfg, seed=3, emb_std=0.3)
+    conf = FiDT5Config(vocab_size=cfg.vocab, d_model=cfg.d_model, d_ff=cfg.d_ff, num_layers=cfg.n_layers,
+                       num_heads=cfg.n_heads)
+    m = FiDT5(conf).cuda()
+    m.load_state_dict(sd)
+    m.save_pretrained(str(tmp_path))
+    m2 = FiDT5.from_pretrained(str(tmp_path)).cuda()
+    for k, v in m.state_dict().items():
+        assert torch.equal(v, m2.state_dict()[k]), k
+    plain = {k.replace("encoder.encoder.", "encoder.").replace(".module.", "."): v for k, v in sd.items()}
+    m3 = FiDT5(conf)
+    m3.load_t5(plain)
+    assert torch.equal(m3.state_dict()["encoder.encoder.block.1.module.layer.1.DenseReluDense.wi.weight"],
+                       sd["encoder.encoder.block.1.module.layer.1.DenseReluDense.wi.weight"])
