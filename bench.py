@@ -1,0 +1,338 @@
+#!/usr/bin/env python
+"""bench.py -- FiDT5 reader training throughput (BASELINE.json metric) on N B200s of one node.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload cfg2|cfg4]
+
+A "step" = one pass of the hot path over one synthetic batch: FiDT5 forward (loss) + backward +
+gradient all-reduce (N>1) + clip + AdamW, i.e. train_reader.py:67-79 of the reference.  The
+workload at N=1 is BASELINE.json configs[1]: t5-base, batch 8 questions x 10 passages x 200 tokens,
+T=10 targets, bf16 operands with fp32 accumulation.  For N>1 every rank takes its own 8 questions
+(question-sharded data parallelism, weak scaling) and gradients are all-reduced over NCCL.
+
+Prints ONE JSON line (rank 0).  `value` is samples/s with inputs already resident in HBM; `e2e`
+is the same metric through the public API with pinned HOST buffers (H2D of ids/mask/labels and a
+D2H read of the loss inside the timed region).  `roofline` describes the dominant kernel (the
+tcgen05 GEMM) from CUDA-event timings taken live in this process; `cpu_baseline` times the oracle
+(CPU restatement of the reference) on a bounded sample on this box's host cores.
+
+--impl reference: the reference's own PyTorch CPU path for the same step, restated in
+oracle/fidt5_oracle.py (the reference is Python over an un-vendored transformers and cannot travel
+to the GPU box), timed on the host cores on a bounded sample (1 question / step).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (t5 size, per-GPU questions B, passages N, text_maxlength L, target length T)
+    "cfg2": ("base", 8, 10, 200, 10),
+    "cfg4": ("large", 8, 20, 250, 10),
+}
+METRIC = "fidt5_train_samples_per_sec"
+EMB_STD = 0.25
+
+
+def fwd_flops(cfgname, B, N, L, T):
+    """SURVEY.md 8(d) algorithmic FLOPs of one forward; train = 3x."""
+    dims = {"base": (768, 768, 3072, 12, 32128), "large": (1024, 1024, 4096, 24, 32128)}[cfgname]
+    d, inner, ff, nl, V = dims
+    enc = nl * (8 * N * L * d * inner + 4 * N * L * L * inner + 4 * N * L * d * ff)
+    dec = nl * (12 * T * d * inner + 4 * T * T * inner + 4 * N * L * d * inner + 4 * T * N * L * inner + 4 * T * d * ff)
+    return B * (enc + dec + 2 * T * d * V)
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return p, "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples = []
+        self.stop_flag = False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                      "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        sm, mx, reasons = [], 0, set()
+        for s in self.samples:
+            try:
+                sm.append(float(s[0]))
+                mx = max(mx, float(s[1]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), s[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def cpu_oracle_step_time(size, N, L, T, steps, warmup, seed=0):
+    """One train step (fwd + bwd + clip + HF-AdamW) of the oracle on the host cores, batch of 1 question."""
+    import torch
+    from oracle import fidt5_oracle as O
+    torch.set_num_threads(os.cpu_count() or 1)
+    cfg = {"base": O.T5_BASE, "large": O.T5_LARGE}[size]
+    sd = O.init_state_dict(cfg, seed=seed, emb_std=EMB_STD)
+    params = O.unique_params(sd)
+    for p in params.values():
+        p.requires_grad_(True)
+    opt = O.HFAdamW(list(params.values()), lr=1e-4, weight_decay=1e-4)
+    ids, mask, labels = O.synth_batch(1, N, L, T, cfg.vocab, seed=1234)
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        O.train_step(sd, cfg, opt, ids, mask, labels, lr_scale=1.0, clip=1.0)
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    return sum(times) / len(times), torch.get_num_threads()
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    size, B, N, L, T = WORKLOADS[args.workload]
+    steps = max(1, args.steps)
+    warmup = max(1, min(args.warmup, 2))
+    # bounded: cap the number of timed CPU steps so the arm ends within minutes
+    steps = min(steps, 5)
+    sec, cores = cpu_oracle_step_time(size, N, L, T, steps, warmup)
+    val = 1.0 / sec
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": "samples/s", "n_gpus": args.gpus,
+        "steps": steps, "warmup": warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: FiDT5 t5-{size} train step, n_passages={N}, text_maxlength={L}, "
+                               f"T={T}, dropout=0 (bounded sample: 1 question per step instead of {B})",
+                   "parallelism": "cpu"},
+        "cpu_baseline": {"value": val, "unit": "samples/s", "cores": cores, "kind": "port",
+                         "sample": f"{steps} train steps of 1 question ({N}x{L} tokens) after {warmup} warm-up"},
+        "e2e": {"value": val, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="lako_b200", choices=["lako_b200", "reference"])
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    import ctypes
+    import torch
+    import torch.distributed as dist
+    from lako_b200 import _native as nat
+    from lako_b200.model import FiDT5, FiDT5Config
+    from lako_b200.optim import FusedAdamW, train_step
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank)
+    warmup = max(3, args.warmup)
+    steps = max(1, args.steps)
+
+    size, B, N, L, T = WORKLOADS[args.workload]
+    conf = FiDT5Config.t5(size)
+    model = FiDT5(conf, emb_std=EMB_STD, seed=0).cuda()
+    model.train()
+    opt = FusedAdamW(model, lr=1e-4, weight_decay=1e-4, clip=1.0)
+
+    g = torch.Generator().manual_seed(1234 + rank)
+    n_batches = 4  # rotate distinct synthetic batches
+    host = []
+    for _ in range(n_batches):
+        ids = torch.randint(11, 32000, (B, N, L), generator=g)
+        lens = torch.randint(int(0.6 * L), L + 1, (B, N), generator=g)
+        mask = torch.arange(L)[None, None, :] < lens[:, :, None]
+        ids = ids * mask
+        tl = torch.randint(2, T + 1, (B,), generator=g)
+        labels = torch.randint(11, 32000, (B, T), generator=g)
+        tpos = torch.arange(T)[None, :]
+        labels = torch.where(tpos == (tl[:, None] - 1), torch.ones_like(labels), labels)
+        labels = labels.masked_fill(tpos >= tl[:, None], -100)
+        host.append((ids.pin_memory(), mask.pin_memory(), labels.pin_memory()))
+    resident = [(a.to(dev), b.to(dev), c.to(dev)) for a, b, c in host]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    lib = nat.lib()
+    lib.lako_launch_count.restype = ctypes.c_ulonglong
+
+    # ---- warm-up
+    for i in range(warmup):
+        train_step(model, opt, *resident[i % n_batches])
+    barrier()
+
+    # ---- timed region: K steps, inputs resident in HBM
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    launches0 = lib.lako_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for i in range(steps):
+        loss = train_step(model, opt, *resident[i % n_batches])
+    e1.record()
+    barrier()
+    launches = lib.lako_launch_count() - launches0
+    ms = e0.elapsed_time(e1)
+    if sampler:
+        sampler.stop_flag = True
+    t = torch.tensor([ms], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = t.item()
+    value = world * B * steps / (ms * 1e-3)
+    final_loss = loss.item()
+
+    # ---- e2e: same metric through the public API with pinned host buffers
+    e2e = None
+    if not args.no_e2e:
+        barrier()
+        e0.record()
+        for i in range(steps):
+            a, b, c = host[i % n_batches]
+            ids_d = a.to(dev, non_blocking=True)
+            mask_d = b.to(dev, non_blocking=True)
+            lab_d = c.to(dev, non_blocking=True)
+            l_ = train_step(model, opt, ids_d, mask_d, lab_d)
+            _ = l_.item()  # D2H of the step's loss (train_reader.py:82)
+        e1.record()
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        a, b, c = host[0]
+        e2e = {"value": world * B * steps / (t.item() * 1e-3), "unit": "samples/s",
+               "h2d_bytes_per_step": a.numel() * 8 + b.numel() + c.numel() * 8, "d2h_bytes_per_step": 4}
+
+    # ---- per-kernel timing (CUDA events on the launching stream, same process, right after the timed region)
+    roofline = None
+    kernel_share = None
+    if rank == 0:
+        lib.lako_prof_enable(1)
+        nprof = 2
+        pe0, pe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        pe0.record()
+        for i in range(nprof):
+            train_step(model, opt, *resident[i % n_batches])
+        pe1.record()
+        ncat = 6
+        msa = (ctypes.c_double * ncat)()
+        wka = (ctypes.c_double * ncat)()
+        cna = (ctypes.c_longlong * ncat)()
+        lib.lako_prof_collect(msa, wka, cna)
+        lib.lako_prof_enable(0)
+        step_ms_prof = pe0.elapsed_time(pe1) / nprof
+        names = ["gemm_tcgen05", "enc_attn_fwd", "enc_attn_bwd", "rmsnorm", "cross_attn", "other"]
+        peaks, which = measured_peaks()
+        kernel_share = {}
+        for i, nme in enumerate(names):
+            if cna[i] == 0:
+                continue
+            per_step_ms = msa[i] / nprof
+            ent = {"ms_per_step": round(per_step_ms, 4), "launches_per_step": cna[i] // nprof,
+                   "share_of_step": round(per_step_ms / step_ms_prof, 4)}
+            if nme == "rmsnorm":
+                ent["achieved_GBs"] = round(wka[i] / (msa[i] * 1e-3) / 1e9, 1)
+                ent["frac_hbm_peak"] = round(ent["achieved_GBs"] / peaks["hbm_gbs"], 4)
+            else:
+                ent["achieved_TFLOPs"] = round(wka[i] / (msa[i] * 1e-3) / 1e12, 1)
+            kernel_share[nme] = ent
+        gemm_tf = wka[0] / (msa[0] * 1e-3) / 1e12
+        peak = peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])
+        roofline = {"bound": "tensor", "kernel": "gemm_bf16_kernel (tcgen05)", "achieved": round(gemm_tf, 1),
+                    "peak": peak, "peak_source": f"{which} sustained cuBLAS bf16 (kernel timed inside a long step)",
+                    "unit": "TFLOP/s", "frac": round(gemm_tf / peak, 4), "traffic": None,
+                    "launches_per_step": cna[0] // nprof, "avg_launch_ms": round(msa[0] / max(1, cna[0]), 5)}
+
+    if world > 1:
+        dist.barrier()
+
+    # ---- CPU baseline (rank 0, N=1 only): oracle on a bounded sample
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        sec, cores = cpu_oracle_step_time(size, N, L, T, steps=2, warmup=1)
+        cpu_baseline = {"value": 1.0 / sec, "unit": "samples/s", "cores": cores, "kind": "port",
+                        "sample": f"2 oracle train steps of 1 question ({N}x{L} tokens, t5-{size}, fp32) after 1 warm-up"}
+
+    if rank == 0:
+        algo_tf = 3 * fwd_flops(size, B, N, L, T) / 1e12  # per rank per step
+        peaks, which = measured_peaks()
+        line = {
+            "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": steps, "warmup": warmup,
+            "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": f"{args.workload}: FiDT5 t5-{size} training step (fwd+bwd+clip+AdamW), per-GPU batch "
+                                   f"{B} questions, n_passages={N}, text_maxlength={L}, T={T}, dropout=0",
+                       "global_batch": world * B, "parallelism": f"dp{world}",
+                       "l2": "step working set (>4 GB of activations) far exceeds the 126 MB L2; batches rotate; no explicit flush",
+                       "emb_std": EMB_STD},
+            "model_tflops_per_gpu": round(algo_tf * steps / (ms * 1e-3), 1),
+            "frac_of_bf16_peak": round(algo_tf * steps / (ms * 1e-3) / peaks["bf16_tflops"], 4),
+            "peaks": {"bf16_tflops": peaks["bf16_tflops"], "bf16_tflops_sustained": peaks.get("bf16_tflops_sustained"),
+                      "hbm_gbs": peaks["hbm_gbs"], "source": which},
+            "final_loss": final_loss,
+            "gpu_launches": int(launches),
+            "e2e": e2e,
+            "roofline": roofline,
+            "kernels": kernel_share,
+            "cpu_baseline": cpu_baseline,
+            "clocks": sampler.summary() if sampler else None,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

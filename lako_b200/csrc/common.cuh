@@ -14,6 +14,7 @@ namespace lako {
 
 #define LAKO_CHECK_LAUNCH()                                  \
   do {                                                       \
+    lako::count_launch();                                    \
     cudaError_t e__ = cudaGetLastError();                    \
     if (e__ != cudaSuccess) {                                \
       lako::set_last_error(cudaGetErrorString(e__), __FILE__, __LINE__); \
@@ -30,6 +31,17 @@ namespace lako {
   } while (0)
 
 void set_last_error(const char* msg, const char* file, int line);
+void count_launch();
+
+// Optional per-category device timing (CUDA events on the launching stream), used by bench.py to report
+// the dominant kernel's achieved FLOP/s / GB/s.  Disabled by default: zero overhead beyond one branch.
+enum ProfCat : int { PROF_GEMM = 0, PROF_ENC_ATTN_FWD, PROF_ENC_ATTN_BWD, PROF_NORM, PROF_XATTN, PROF_OTHER, PROF_NCAT };
+struct ProfScope {
+  int cat;
+  void* rec;
+  ProfScope(int cat, double work, cudaStream_t s);
+  ~ProfScope();
+};
 
 #ifdef __CUDACC__
 

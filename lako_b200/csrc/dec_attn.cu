@@ -175,6 +175,7 @@ int xattn_fwd(const __nv_bfloat16* q, const __nv_bfloat16* kv, const unsigned ch
                          XA_TMAX * (64 + XA_CH) * (int)sizeof(float));
     configured = true;
   }
+  ProfScope prof(PROF_XATTN, 4.0 * B * H * static_cast<double>(T) * M * 64, s);
   dim3 grid(p.splits, H, B);
   xattn_fwd_kernel<<<grid, 128, dyn, s>>>(p);
   LAKO_CHECK_LAUNCH();
@@ -319,6 +320,7 @@ int xattn_bwd(const __nv_bfloat16* q, const __nv_bfloat16* kv, const unsigned ch
                          (XA_TMAX * (128 + XA_CH) + 2 * XA_TMAX) * (int)sizeof(float));
     configured = true;
   }
+  ProfScope prof(PROF_XATTN, 8.0 * B * H * static_cast<double>(T) * M * 64, s);
   dim3 grid((M + XA_CH - 1) / XA_CH, H, B);
   xattn_bwd_kernel<<<grid, 256, dyn, s>>>(p);
   LAKO_CHECK_LAUNCH();

@@ -78,6 +78,8 @@ __global__ void __launch_bounds__(256) rmsnorm_fwd_kernel(const float* x, const 
 int rmsnorm_fwd(const float* x, const __nv_bfloat16* delta, float* x_out, const float* w, __nv_bfloat16* out,
                 float* rstd, int rows, int d, float eps, float out_scale, cudaStream_t s) {
   LAKO_REQUIRE(rows > 0 && d > 0 && d % 128 == 0 && d <= 128 * NORM_MAX_VEC, LAKO_ERR_UNSUPPORTED);
+  // algorithmic bytes: read x (4) [+ delta (2) + write x (4)] + write normed (2)
+  ProfScope prof(PROF_NORM, static_cast<double>(rows) * d * (delta ? 12.0 : 6.0), s);
   const int warps_per_block = 8;
   const int grid = (rows + warps_per_block - 1) / warps_per_block;
   rmsnorm_fwd_kernel<<<grid, warps_per_block * 32, 0, s>>>(x, delta, x_out, w, out, rstd, rows, d, eps, out_scale);
@@ -181,6 +183,8 @@ int rmsnorm_bwd(const __nv_bfloat16* dy, const float* x, const float* rstd, cons
                 __nv_bfloat16* dres_bf16, float* dw, int rows, int d, int accumulate, float dy_scale,
                 cudaStream_t s) {
   LAKO_REQUIRE(rows > 0 && d > 0 && d % 128 == 0 && d <= 128 * NORM_MAX_VEC, LAKO_ERR_UNSUPPORTED);
+  // algorithmic bytes: read dy (2) + x (4) + dres (4 if accumulating); write dres (4) + bf16 copy (2)
+  ProfScope prof(PROF_NORM, static_cast<double>(rows) * d * (accumulate ? 16.0 : 12.0), s);
   const int warps_per_block = 8;
   int grid = (rows + warps_per_block - 1) / warps_per_block;
   grid = min(grid, device_sm_count() * 4);

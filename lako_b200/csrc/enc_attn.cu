@@ -250,6 +250,7 @@ int enc_attn_fwd(const __nv_bfloat16* qkv, const unsigned char* mask, const floa
   p.H = H;
   p.inner = inner;
   p.LK = (L + 15) / 16 * 16;
+  ProfScope prof(PROF_ENC_ATTN_FWD, 4.0 * P * H * static_cast<double>(L) * L * 64, s);
   dim3 grid((L + 127) / 128, H, P);
   enc_attn_fwd_kernel<<<grid, 128, EA_SMEM_BYTES, s>>>(tm, p);
   LAKO_CHECK_LAUNCH();
@@ -567,6 +568,7 @@ int enc_attn_bwd(const __nv_bfloat16* qkv, const __nv_bfloat16* out, const __nv_
   p.L = L;
   p.H = H;
   p.inner = inner;
+  ProfScope prof(PROF_ENC_ATTN_BWD, 10.0 * P * H * static_cast<double>(L) * L * 64, s);
   dim3 grid(H, P);
   enc_attn_bwd_kernel<<<grid, 256, EB_SMEM_BYTES, s>>>(tm_qkv, tm_do, p);
   LAKO_CHECK_LAUNCH();

@@ -369,6 +369,7 @@ int gemm_bf16(const void* A, const void* B, void* C, int M, int N, int K, int ld
   else
     rc = get_tensor_map_2d(&tmB, B, N, K, ldb, 64, BK);
   if (rc) return rc;
+  ProfScope prof(PROF_GEMM, 2.0 * M * N * static_cast<double>(K), stream);
   if (bn == 256) return dispatch_major<256>(a_mn, b_mn, epi, tmA, tmB, p, stream);
   return dispatch_major<128>(a_mn, b_mn, epi, tmA, tmB, p, stream);
 }

@@ -4,6 +4,7 @@
 #include <mutex>
 #include <string>
 #include <unordered_map>
+#include <vector>
 
 #include "common.cuh"
 
@@ -17,6 +18,44 @@ void set_last_error(const char* msg, const char* file, int line) {
   g_last_error = buf;
 }
 const char* last_error_cstr() { return g_last_error.c_str(); }
+
+static unsigned long long g_launches = 0;
+void count_launch() { ++g_launches; }
+
+// ---------------------------------------------------------------- profiling scopes
+struct ProfRec {
+  int cat;
+  double work;
+  cudaEvent_t e0, e1;
+  cudaStream_t stream;
+};
+static bool g_prof_on = false;
+static std::vector<ProfRec*> g_prof_recs;
+static std::vector<ProfRec*> g_prof_pool;
+
+ProfScope::ProfScope(int c, double work, cudaStream_t s) : cat(c), rec(nullptr) {
+  if (!g_prof_on) return;
+  ProfRec* r;
+  if (!g_prof_pool.empty()) {
+    r = g_prof_pool.back();
+    g_prof_pool.pop_back();
+  } else {
+    r = new ProfRec();
+    cudaEventCreate(&r->e0);
+    cudaEventCreate(&r->e1);
+  }
+  r->cat = c;
+  r->work = work;
+  r->stream = s;
+  cudaEventRecord(r->e0, s);
+  rec = r;
+}
+ProfScope::~ProfScope() {
+  if (!rec) return;
+  ProfRec* r = static_cast<ProfRec*>(rec);
+  cudaEventRecord(r->e1, r->stream);
+  g_prof_recs.push_back(r);
+}
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -142,6 +181,28 @@ int check_arch() {
 }
 
 }  // namespace lako
+
+extern "C" unsigned long long lako_launch_count() { return lako::g_launches; }
+extern "C" void lako_prof_enable(int on) { lako::g_prof_on = on != 0; }
+// Synchronises, then fills ms[cat], work[cat], count[cat] (arrays of LAKO_PROF_NCAT) and clears the records.
+extern "C" int lako_prof_collect(double* ms, double* work, long long* count) {
+  cudaDeviceSynchronize();
+  for (int i = 0; i < lako::PROF_NCAT; ++i) {
+    ms[i] = 0;
+    work[i] = 0;
+    count[i] = 0;
+  }
+  for (lako::ProfRec* r : lako::g_prof_recs) {
+    float t = 0.f;
+    cudaEventElapsedTime(&t, r->e0, r->e1);
+    ms[r->cat] += t;
+    work[r->cat] += r->work;
+    count[r->cat] += 1;
+    lako::g_prof_pool.push_back(r);
+  }
+  lako::g_prof_recs.clear();
+  return lako::PROF_NCAT;
+}
 
 extern "C" const char* lako_last_error() { return lako::last_error_cstr(); }
 extern "C" int lako_check_device() { return lako::check_arch(); }
