@@ -95,88 +95,109 @@ int rmsnorm_fwd(const float* x, const __nv_bfloat16* delta, float* x_out, const 
 //   dres_bf16 (optional)   bf16 copy of the updated dres (operand of the next dgrad/wgrad GEMMs)
 //   dw     fp32 [d]        += sum_rows dy * x * rstd   (block-reduced, one atomic per column per block)
 // --------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) rmsnorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy,
-                                                           const float* __restrict__ x, const float* __restrict__ rstd,
-                                                           const float* __restrict__ w, float* __restrict__ dres,
-                                                           __nv_bfloat16* __restrict__ dres_bf16,
-                                                           float* __restrict__ dw, int rows, int d, int accumulate,
-                                                           float dy_scale) {
-  __shared__ float s_dw[8][128 * NORM_MAX_VEC / 8];  // reused in column chunks below
+// NV = d / 128 float4 slots per lane.  The per-column weight-gradient partial sums live in a per-warp
+// private slice of shared memory (no atomics, 128-bit conflict-free accesses) instead of registers, which
+// keeps the kernel at ~70 registers so three 8-warp CTAs fit per SM and enough loads are in flight.
+template <int NV>
+__global__ void __launch_bounds__(256, 2) rmsnorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy,
+                                                              const float* __restrict__ x,
+                                                              const float* __restrict__ rstd,
+                                                              const float* __restrict__ w, float* __restrict__ dres,
+                                                              __nv_bfloat16* __restrict__ dres_bf16,
+                                                              float* __restrict__ dw, int rows, int accumulate,
+                                                              float dy_scale) {
+  constexpr int d = NV * 128;
+  extern __shared__ float4 s_norm[];
+  float4* s_w = s_norm;                // [d/4]
+  float4* s_dw = s_norm + d / 4;       // [8 warps][d/4]
   const int lane = threadIdx.x & 31;
   const int wib = threadIdx.x >> 5;
-  const int nvec = d >> 7;
-  float4 dwv[NORM_MAX_VEC];
-  float4 wv[NORM_MAX_VEC];
+  for (int i = threadIdx.x; i < d / 4; i += 256) s_w[i] = reinterpret_cast<const float4*>(w)[i];
+  float4* my_dw = s_dw + wib * (d / 4);
 #pragma unroll
-  for (int i = 0; i < NORM_MAX_VEC; ++i) {
-    dwv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (i < nvec) wv[i] = *reinterpret_cast<const float4*>(w + (i * 32 + lane) * 4);
-  }
-  const int warps_total = gridDim.x * (blockDim.x >> 5);
-  for (int row = blockIdx.x * (blockDim.x >> 5) + wib; row < rows; row += warps_total) {
+  for (int i = 0; i < NV; ++i) my_dw[i * 32 + lane] = make_float4(0.f, 0.f, 0.f, 0.f);
+  __syncthreads();
+  const int warps_total = gridDim.x * 8;
+  for (int row = blockIdx.x * 8 + wib; row < rows; row += warps_total) {
     const float r = rstd[row];
     const float* xr = x + static_cast<size_t>(row) * d;
     const __nv_bfloat16* dyr = dy + static_cast<size_t>(row) * d;
-    float4 g[NORM_MAX_VEC], xv[NORM_MAX_VEC];
+    float* drr = dres + static_cast<size_t>(row) * d;
+    float4 xv[NV];
+    uint2 dyp[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = (i * 32 + lane) * 4;
+      xv[i] = *reinterpret_cast<const float4*>(xr + c);
+      dyp[i] = *reinterpret_cast<const uint2*>(dyr + c);
+    }
     float s = 0.f;
 #pragma unroll
-    for (int i = 0; i < NORM_MAX_VEC; ++i) {
-      if (i < nvec) {
-        const int c = (i * 32 + lane) * 4;
-        xv[i] = *reinterpret_cast<const float4*>(xr + c);
-        const uint2 dd = *reinterpret_cast<const uint2*>(dyr + c);
-        float4 dyv = make_float4(bf16_lo(dd.x) * dy_scale, bf16_hi(dd.x) * dy_scale, bf16_lo(dd.y) * dy_scale,
-                                 bf16_hi(dd.y) * dy_scale);
-        dwv[i].x += dyv.x * xv[i].x * r;
-        dwv[i].y += dyv.y * xv[i].y * r;
-        dwv[i].z += dyv.z * xv[i].z * r;
-        dwv[i].w += dyv.w * xv[i].w * r;
-        g[i] = make_float4(dyv.x * wv[i].x, dyv.y * wv[i].y, dyv.z * wv[i].z, dyv.w * wv[i].w);
-        s += g[i].x * xv[i].x + g[i].y * xv[i].y + g[i].z * xv[i].z + g[i].w * xv[i].w;
-      }
+    for (int i = 0; i < NV; ++i) {
+      const float4 wv = s_w[i * 32 + lane];
+      const float4 dyv = make_float4(bf16_lo(dyp[i].x) * dy_scale, bf16_hi(dyp[i].x) * dy_scale,
+                                     bf16_lo(dyp[i].y) * dy_scale, bf16_hi(dyp[i].y) * dy_scale);
+      s += dyv.x * wv.x * xv[i].x + dyv.y * wv.y * xv[i].y + dyv.z * wv.z * xv[i].z + dyv.w * wv.w * xv[i].w;
+      float4 a = my_dw[i * 32 + lane];
+      a.x += dyv.x * xv[i].x * r;
+      a.y += dyv.y * xv[i].y * r;
+      a.z += dyv.z * xv[i].z * r;
+      a.w += dyv.w * xv[i].w * r;
+      my_dw[i * 32 + lane] = a;
     }
     s = warp_sum(s);
     const float coef = r * r * r * s / static_cast<float>(d);
-    float* drr = dres + static_cast<size_t>(row) * d;
 #pragma unroll
-    for (int i = 0; i < NORM_MAX_VEC; ++i) {
-      if (i < nvec) {
-        const int c = (i * 32 + lane) * 4;
-        float4 o = make_float4(r * g[i].x - coef * xv[i].x, r * g[i].y - coef * xv[i].y, r * g[i].z - coef * xv[i].z,
-                               r * g[i].w - coef * xv[i].w);
-        if (accumulate) {
-          const float4 old = *reinterpret_cast<const float4*>(drr + c);
-          o.x += old.x;
-          o.y += old.y;
-          o.z += old.z;
-          o.w += old.w;
-        }
-        *reinterpret_cast<float4*>(drr + c) = o;
-        if (dres_bf16) {
-          uint2 ob;
-          ob.x = pack_bf16x2(o.x, o.y);
-          ob.y = pack_bf16x2(o.z, o.w);
-          *reinterpret_cast<uint2*>(dres_bf16 + static_cast<size_t>(row) * d + c) = ob;
-        }
+    for (int i = 0; i < NV; ++i) {
+      const int c = (i * 32 + lane) * 4;
+      const float4 wv = s_w[i * 32 + lane];
+      const float4 dyv = make_float4(bf16_lo(dyp[i].x) * dy_scale, bf16_hi(dyp[i].x) * dy_scale,
+                                     bf16_lo(dyp[i].y) * dy_scale, bf16_hi(dyp[i].y) * dy_scale);
+      float4 o = make_float4(r * dyv.x * wv.x - coef * xv[i].x, r * dyv.y * wv.y - coef * xv[i].y,
+                             r * dyv.z * wv.z - coef * xv[i].z, r * dyv.w * wv.w - coef * xv[i].w);
+      if (accumulate) {
+        const float4 old = *reinterpret_cast<const float4*>(drr + c);
+        o.x += old.x;
+        o.y += old.y;
+        o.z += old.z;
+        o.w += old.w;
+      }
+      *reinterpret_cast<float4*>(drr + c) = o;
+      if (dres_bf16) {
+        uint2 ob;
+        ob.x = pack_bf16x2(o.x, o.y);
+        ob.y = pack_bf16x2(o.z, o.w);
+        *reinterpret_cast<uint2*>(dres_bf16 + static_cast<size_t>(row) * d + c) = ob;
       }
     }
   }
-  // block reduction of dw: one float4 slot (i) at a time through shared memory
   if (dw) {
+    __syncthreads();
+    const float* f_dw = reinterpret_cast<const float*>(s_dw);
+    for (int c = threadIdx.x; c < d; c += 256) {
+      float acc = 0.f;
 #pragma unroll
-    for (int i = 0; i < NORM_MAX_VEC; ++i) {
-      if (i < nvec) {
-        __syncthreads();
-        reinterpret_cast<float4*>(&s_dw[wib][0])[lane] = dwv[i];
-        __syncthreads();
-        if (threadIdx.x < 128) {
-          float acc = 0.f;
-          for (int ww = 0; ww < (blockDim.x >> 5); ++ww) acc += s_dw[ww][threadIdx.x];
-          atomicAdd(dw + i * 128 + threadIdx.x, acc);
-        }
-      }
+      for (int ww = 0; ww < 8; ++ww) acc += f_dw[ww * d + c];
+      atomicAdd(dw + c, acc);
     }
   }
+}
+
+template <int NV>
+static int launch_rmsnorm_bwd(const __nv_bfloat16* dy, const float* x, const float* rstd, const float* w, float* dres,
+                              __nv_bfloat16* dres_bf16, float* dw, int rows, int accumulate, float dy_scale,
+                              cudaStream_t s) {
+  constexpr int smem = (NV * 128 * 9) * (int)sizeof(float);
+  static bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute(rmsnorm_bwd_kernel<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    configured = true;
+  }
+  int grid = (rows + 7) / 8;
+  grid = min(grid, device_sm_count() * 2);
+  rmsnorm_bwd_kernel<NV><<<grid, 256, smem, s>>>(dy, x, rstd, w, dres, dres_bf16, dw, rows, accumulate, dy_scale);
+  LAKO_CHECK_LAUNCH();
+  return LAKO_OK;
 }
 
 int rmsnorm_bwd(const __nv_bfloat16* dy, const float* x, const float* rstd, const float* w, float* dres,
@@ -185,13 +206,16 @@ int rmsnorm_bwd(const __nv_bfloat16* dy, const float* x, const float* rstd, cons
   LAKO_REQUIRE(rows > 0 && d > 0 && d % 128 == 0 && d <= 128 * NORM_MAX_VEC, LAKO_ERR_UNSUPPORTED);
   // algorithmic bytes: read dy (2) + x (4) + dres (4 if accumulating); write dres (4) + bf16 copy (2)
   ProfScope prof(PROF_NORM, static_cast<double>(rows) * d * (accumulate ? 16.0 : 12.0), s);
-  const int warps_per_block = 8;
-  int grid = (rows + warps_per_block - 1) / warps_per_block;
-  grid = min(grid, device_sm_count() * 4);
-  rmsnorm_bwd_kernel<<<grid, warps_per_block * 32, 0, s>>>(dy, x, rstd, w, dres, dres_bf16, dw, rows, d, accumulate,
-                                                            dy_scale);
-  LAKO_CHECK_LAUNCH();
-  return LAKO_OK;
+  switch (d / 128) {
+    case 1: return launch_rmsnorm_bwd<1>(dy, x, rstd, w, dres, dres_bf16, dw, rows, accumulate, dy_scale, s);
+    case 2: return launch_rmsnorm_bwd<2>(dy, x, rstd, w, dres, dres_bf16, dw, rows, accumulate, dy_scale, s);
+    case 3: return launch_rmsnorm_bwd<3>(dy, x, rstd, w, dres, dres_bf16, dw, rows, accumulate, dy_scale, s);
+    case 4: return launch_rmsnorm_bwd<4>(dy, x, rstd, w, dres, dres_bf16, dw, rows, accumulate, dy_scale, s);
+    case 5: return launch_rmsnorm_bwd<5>(dy, x, rstd, w, dres, dres_bf16, dw, rows, accumulate, dy_scale, s);
+    case 6: return launch_rmsnorm_bwd<6>(dy, x, rstd, w, dres, dres_bf16, dw, rows, accumulate, dy_scale, s);
+    case 7: return launch_rmsnorm_bwd<7>(dy, x, rstd, w, dres, dres_bf16, dw, rows, accumulate, dy_scale, s);
+    default: return launch_rmsnorm_bwd<8>(dy, x, rstd, w, dres, dres_bf16, dw, rows, accumulate, dy_scale, s);
+  }
 }
 
 // --------------------------------------------------------------------------------------------

@@ -46,22 +46,46 @@ struct EncAttnParams {
   int L, H, inner, LK;        // LK = L rounded up to 16
 };
 
+constexpr float LOG2E_F = 1.4426950408889634f;
+constexpr int LUTCOPY = 520;  // floats per shifted LUT copy (max index (L-1) + 255 + 3 < 520 for L <= 256)
+
+// Four copies of the per-head bias LUT, copy j shifted left by j floats, so that every thread can fetch
+// the 4 consecutive biases of 4 consecutive keys with ONE aligned 128-bit shared load whatever its
+// query position is:  copy_j[x] = lut[x + j];  thread with base b = L-1-q uses j = b & 3 at offset b - j.
+__device__ __forceinline__ void stage_lut4(float* s_lut4, const float* __restrict__ lut, int nlut, int tid,
+                                           int nthreads) {
+  for (int i = tid; i < 4 * LUTCOPY; i += nthreads) {
+    const int j = i / LUTCOPY, x = i - j * LUTCOPY;
+    const int src = x + j;
+    s_lut4[i] = (src < nlut) ? lut[src] : 0.f;
+  }
+}
+// additive key mask: 0 valid, finfo.min for padded keys (HF semantics), -inf beyond the passage
+__device__ __forceinline__ void stage_kmask(float* s_kmask, const unsigned char* __restrict__ mask, int L, int tid,
+                                            int nthreads) {
+  for (int i = tid; i < 256; i += nthreads) s_kmask[i] = (i < L) ? (mask[i] ? 0.f : MASK_MIN) : -INFINITY;
+}
+
 // smem map (bytes from the 1024-aligned base):
 //   [0, 32K)   K tile rows 0..255   | after S is read: P chunks 0,1
 //   [32K, 48K) Q tile               | P chunk 2
 //   [48K, 64K) spare                | P chunk 3
 //   [64K, 96K) V tile rows 0..255
-//   then: lut (2048 B), mask (256 B), barriers
-constexpr int EA_K_OFF = 0, EA_Q_OFF = 32768, EA_V_OFF = 65536, EA_LUT_OFF = 98304, EA_MASK_OFF = 98304 + 2048,
-              EA_BAR_OFF = EA_MASK_OFF + 256;
+//   then: 4 shifted LUT copies, additive key mask, cross-half reduction scratch, barriers
+constexpr int EA_K_OFF = 0, EA_Q_OFF = 32768, EA_V_OFF = 65536, EA_LUT_OFF = 98304,
+              EA_KMASK_OFF = EA_LUT_OFF + 4 * LUTCOPY * 4, EA_RED_OFF = EA_KMASK_OFF + 1024,
+              EA_BAR_OFF = EA_RED_OFF + 2048;
 constexpr int EA_SMEM_BYTES = EA_BAR_OFF + 64 + 1024;
 
-__global__ void __launch_bounds__(128, 2)
+// 256 threads: warp w owns TMEM lane quarter (w & 3) = 32 query rows, and key half (w >> 2).
+__global__ void __launch_bounds__(256, 2)
 enc_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const EncAttnParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  float* s_lut = reinterpret_cast<float*>(smem + EA_LUT_OFF);
-  unsigned char* s_mask = smem + EA_MASK_OFF;
+  float* s_lut4 = reinterpret_cast<float*>(smem + EA_LUT_OFF);
+  float* s_kmask = reinterpret_cast<float*>(smem + EA_KMASK_OFF);
+  float* s_red_m = reinterpret_cast<float*>(smem + EA_RED_OFF);  // [2][128]
+  float* s_red_l = s_red_m + 256;                                // [2][128]
   uint64_t* bar_qk = reinterpret_cast<uint64_t*>(smem + EA_BAR_OFF);
   uint64_t* bar_v = bar_qk + 1;
   uint64_t* bar_s = bar_qk + 2;
@@ -69,6 +93,7 @@ enc_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const EncAttnPar
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_qk + 4);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int quarter = warp & 3, chalf = warp >> 2;
   const int q0 = blockIdx.x * 128, h = blockIdx.y, psg = blockIdx.z;
   const int L = p.L, LK = p.LK;
   const int row0 = psg * L;
@@ -83,9 +108,8 @@ enc_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const EncAttnPar
     fence_barrier_init();
   }
   if (warp == 0) tmem_alloc(tmem_slot, 256);
-  // stage the per-head bias LUT and the key mask
-  for (int i = tid; i < 2 * L - 1; i += 128) s_lut[i] = p.bias_lut[h * (2 * L - 1) + i];
-  for (int i = tid; i < 256; i += 128) s_mask[i] = (i < L) ? p.mask[psg * L + i] : 0;
+  stage_lut4(s_lut4, p.bias_lut + h * (2 * L - 1), 2 * L - 1, tid, 256);
+  stage_kmask(s_kmask, p.mask + static_cast<size_t>(psg) * L, L, tid, 256);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -111,60 +135,68 @@ enc_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const EncAttnPar
     umma_commit(bar_s);
   }
 
-  // ---- softmax: thread == query row
-  const int r = tid;           // row within tile == TMEM lane
-  const int q = q0 + r;        // query position in the passage
-  const uint32_t t_row = tmem + (static_cast<uint32_t>(warp * 32) << 16);
+  const int r = quarter * 32 + lane;   // query row within the tile == TMEM lane
+  const int q = q0 + r;                // query position in the passage
+  const int qc = min(q, L - 1);        // rows beyond the passage compute on a clamped position, never stored
+  const int b = L - 1 - qc;
+  const float* lutp = s_lut4 + (b & 3) * LUTCOPY + (b & ~3);
+  const uint32_t t_row = tmem + (static_cast<uint32_t>(quarter * 32) << 16);
+  const int nchunks = (LK + 31) / 32;
+  const int c_begin = chalf * 4, c_end = min(nchunks, chalf * 4 + 4);
+
   mbar_wait(bar_s, 0);
   tc_fence_after();
-  const int nchunks = (LK + 31) / 32;
-  const float* lut_q = s_lut + (L - 1 - q);  // lut_q[k] = bias(k - q); only dereferenced for q < L, k < L
+  // ---- pass 1: s = qk + bias + mask, row max; s goes back to TMEM
   float m = -INFINITY;
-  for (int c = 0; c < nchunks; ++c) {
+  for (int c = c_begin; c < c_end; ++c) {
     uint32_t v[32];
     tmem_ld_32x32(t_row + c * 32, v);
     tmem_ld_wait();
-    if (q < L) {
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        const int k = c * 32 + i;
-        if (k < L) {
-          const float s = s_mask[k] ? __uint_as_float(v[i]) + lut_q[k] : MASK_MIN;
-          m = fmaxf(m, s);
-        }
-      }
+    for (int g = 0; g < 8; ++g) {
+      const float4 lb = *reinterpret_cast<const float4*>(lutp + c * 32 + g * 4);
+      const float4 km = *reinterpret_cast<const float4*>(s_kmask + c * 32 + g * 4);
+      const float s0 = (__uint_as_float(v[g * 4 + 0]) + lb.x) + km.x;
+      const float s1 = (__uint_as_float(v[g * 4 + 1]) + lb.y) + km.y;
+      const float s2 = (__uint_as_float(v[g * 4 + 2]) + lb.z) + km.z;
+      const float s3 = (__uint_as_float(v[g * 4 + 3]) + lb.w) + km.w;
+      m = fmaxf(m, fmaxf(fmaxf(s0, s1), fmaxf(s2, s3)));
+      v[g * 4 + 0] = __float_as_uint(s0);
+      v[g * 4 + 1] = __float_as_uint(s1);
+      v[g * 4 + 2] = __float_as_uint(s2);
+      v[g * 4 + 3] = __float_as_uint(s3);
     }
+    tmem_st_32x32(t_row + c * 32, v);
   }
+  tmem_st_wait();
+  s_red_m[chalf * 128 + r] = m;
+  __syncthreads();
+  m = fmaxf(s_red_m[r], s_red_m[128 + r]);
+  // ---- pass 2: p = exp(s - m) (un-normalised), row sum, P -> shared (bf16, K-major 128B swizzle)
   float lsum = 0.f;
-  for (int c = 0; c < nchunks; ++c) {
+  for (int c = c_begin; c < c_end; ++c) {
     uint32_t v[32];
     tmem_ld_32x32(t_row + c * 32, v);
     tmem_ld_wait();
-    float pr[32];
-#pragma unroll
-    for (int i = 0; i < 32; ++i) {
-      const int k = c * 32 + i;
-      float e = 0.f;
-      if (q < L && k < L) {
-        const float s = s_mask[k] ? __uint_as_float(v[i]) + lut_q[k] : MASK_MIN;
-        e = __expf(s - m);
-      }
-      pr[i] = e;
-      lsum += e;
-    }
-    // P[r][k] bf16 into the K-major 128B-swizzled layout: 64-key chunks of [128 rows][128 B]
     uint8_t* chunk = smem + (c >> 1) * 16384 + r * 128;
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
+      float e[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        e[i] = fast_exp2((__uint_as_float(v[u * 8 + i]) - m) * LOG2E_F);
+        lsum += e[i];
+      }
       const int unit = (c & 1) * 4 + u;  // 16-byte unit index within the 128-byte row
       uint4 o;
-      o.x = pack_bf16x2(pr[u * 8 + 0], pr[u * 8 + 1]);
-      o.y = pack_bf16x2(pr[u * 8 + 2], pr[u * 8 + 3]);
-      o.z = pack_bf16x2(pr[u * 8 + 4], pr[u * 8 + 5]);
-      o.w = pack_bf16x2(pr[u * 8 + 6], pr[u * 8 + 7]);
+      o.x = pack_bf16x2(e[0], e[1]);
+      o.y = pack_bf16x2(e[2], e[3]);
+      o.z = pack_bf16x2(e[4], e[5]);
+      o.w = pack_bf16x2(e[6], e[7]);
       *reinterpret_cast<uint4*>(chunk + ((unit ^ (r & 7)) << 4)) = o;
     }
   }
+  s_red_l[chalf * 128 + r] = lsum;
   fence_proxy_async_smem();
   tc_fence_before();
   __syncthreads();
@@ -182,16 +214,16 @@ enc_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const EncAttnPar
                 make_smem_desc_sw128(va + j * 2048, 8192, 1024), idesc, j > 0);
     umma_commit(bar_o);
   }
+  lsum = s_red_l[r] + s_red_l[128 + r];
   mbar_wait(bar_o, 0);
   tc_fence_after();
   {
-    uint32_t o0[32], o1[32];
-    tmem_ld_32x32(t_row, o0);
-    tmem_ld_32x32(t_row + 32, o1);
+    uint32_t o0[32];
+    tmem_ld_32x32(t_row + chalf * 32, o0);  // this warp's 32 of the 64 head dims
     tmem_ld_wait();
     if (q < L) {
       const float inv = 1.f / lsum;
-      __nv_bfloat16* orow = p.out + static_cast<size_t>(row0 + q) * p.inner + h * 64;
+      __nv_bfloat16* orow = p.out + static_cast<size_t>(row0 + q) * p.inner + h * 64 + chalf * 32;
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         uint4 o;
@@ -201,16 +233,7 @@ enc_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const EncAttnPar
         o.w = pack_bf16x2(__uint_as_float(o0[u * 8 + 6]) * inv, __uint_as_float(o0[u * 8 + 7]) * inv);
         *reinterpret_cast<uint4*>(orow + u * 8) = o;
       }
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        uint4 o;
-        o.x = pack_bf16x2(__uint_as_float(o1[u * 8 + 0]) * inv, __uint_as_float(o1[u * 8 + 1]) * inv);
-        o.y = pack_bf16x2(__uint_as_float(o1[u * 8 + 2]) * inv, __uint_as_float(o1[u * 8 + 3]) * inv);
-        o.z = pack_bf16x2(__uint_as_float(o1[u * 8 + 4]) * inv, __uint_as_float(o1[u * 8 + 5]) * inv);
-        o.w = pack_bf16x2(__uint_as_float(o1[u * 8 + 6]) * inv, __uint_as_float(o1[u * 8 + 7]) * inv);
-        *reinterpret_cast<uint4*>(orow + 32 + u * 8) = o;
-      }
-      if (p.lse) p.lse[(static_cast<size_t>(psg) * p.H + h) * L + q] = m + logf(lsum);
+      if (p.lse && chalf == 0) p.lse[(static_cast<size_t>(psg) * p.H + h) * L + q] = m + logf(lsum);
     }
   }
   tc_fence_before();
@@ -252,7 +275,7 @@ int enc_attn_fwd(const __nv_bfloat16* qkv, const unsigned char* mask, const floa
   p.LK = (L + 15) / 16 * 16;
   ProfScope prof(PROF_ENC_ATTN_FWD, 4.0 * P * H * static_cast<double>(L) * L * 64, s);
   dim3 grid((L + 127) / 128, H, P);
-  enc_attn_fwd_kernel<<<grid, 128, EA_SMEM_BYTES, s>>>(tm, p);
+  enc_attn_fwd_kernel<<<grid, 256, EA_SMEM_BYTES, s>>>(tm, p);
   LAKO_CHECK_LAUNCH();
   return LAKO_OK;
 }
@@ -276,19 +299,22 @@ struct EncAttnBwdParams {
 };
 
 constexpr int EB_Q_OFF = 0, EB_DO_OFF = 32768, EB_K_OFF = 65536, EB_V_OFF = 98304, EB_P_OFF = 131072,
-              EB_DS_OFF = 163840, EB_LUT_OFF = 196608, EB_DLUT_OFF = EB_LUT_OFF + 2048, EB_MASK_OFF = EB_DLUT_OFF + 2048,
-              EB_LSE_OFF = EB_MASK_OFF + 256, EB_D_OFF = EB_LSE_OFF + 1024, EB_BAR_OFF = EB_D_OFF + 1024;
+              EB_DS_OFF = 163840, EB_LUT_OFF = 196608, EB_DLUT_OFF = EB_LUT_OFF + 4 * LUTCOPY * 4,
+              EB_KMASK_OFF = EB_DLUT_OFF + 2048, EB_LSE_OFF = EB_KMASK_OFF + 1024, EB_D_OFF = EB_LSE_OFF + 1024,
+              EB_BAR_OFF = EB_D_OFF + 1024;
 constexpr int EB_SMEM_BYTES = EB_BAR_OFF + 64 + 1024;
 constexpr int TM_S = 0, TM_DP = 128, TM_DQ = 256, TM_DK = 384, TM_DV = 448;
 
+// One CTA per (head, passage); 256 threads: warp w owns TMEM lane quarter (w & 3) and key half (w >> 2) of
+// each 128x128 (query tile x key tile) block.  TMEM: S 128 | dP 128 | dQ 2x64 | dK 64 | dV 64 columns.
 __global__ void __launch_bounds__(256, 1)
 enc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_do,
                     const EncAttnBwdParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  float* s_lut = reinterpret_cast<float*>(smem + EB_LUT_OFF);
+  float* s_lut4 = reinterpret_cast<float*>(smem + EB_LUT_OFF);
   float* s_dlut = reinterpret_cast<float*>(smem + EB_DLUT_OFF);
-  unsigned char* s_mask = smem + EB_MASK_OFF;
+  float* s_kmask = reinterpret_cast<float*>(smem + EB_KMASK_OFF);
   float* s_lse = reinterpret_cast<float*>(smem + EB_LSE_OFF);
   float* s_D = reinterpret_cast<float*>(smem + EB_D_OFF);
   uint64_t* bar_load = reinterpret_cast<uint64_t*>(smem + EB_BAR_OFF);
@@ -311,14 +337,12 @@ enc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
     fence_barrier_init();
   }
   if (warp == 0) tmem_alloc(tmem_slot, 512);
-  for (int i = tid; i < nlut; i += 256) {
-    s_lut[i] = p.bias_lut[h * nlut + i];
-    s_dlut[i] = 0.f;
-  }
+  stage_lut4(s_lut4, p.bias_lut + h * nlut, nlut, tid, 256);
+  stage_kmask(s_kmask, p.mask + static_cast<size_t>(psg) * L, L, tid, 256);
+  for (int i = tid; i < 512; i += 256) s_dlut[i] = 0.f;
   {
     const int q = tid;  // 256 threads cover the (<=256) query rows: D[q] = sum_d dO*O, lse[q]
-    s_mask[q] = (q < L) ? p.mask[psg * L + q] : 0;
-    float dsum = 0.f, l = 0.f;
+    float dsum = 0.f, l = INFINITY;  // lse = +inf for rows beyond the passage -> P = exp(s - inf) = 0
     if (q < L) {
       const uint4* o4 = reinterpret_cast<const uint4*>(p.out + static_cast<size_t>(row0 + q) * p.inner + h * 64);
       const uint4* d4 = reinterpret_cast<const uint4*>(p.dout + static_cast<size_t>(row0 + q) * p.inner + h * 64);
@@ -372,17 +396,20 @@ enc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
 
   const int r = quarter * 32 + lane;  // row within a 128-row tile == TMEM lane
   const uint32_t t_row = tmem + (static_cast<uint32_t>(quarter * 32) << 16);
+  const float keep = (lane == 0) ? 0.f : 1.f;  // systolic diagonal sums: lane 0 starts a new diagonal
   uint32_t mma_phase = 0;
 
   for (int kt = 0; kt < nt; ++kt) {
     for (int qt = 0; qt < nt; ++qt) {
       const int q = qt * 128 + r;
+      const int qc = min(q, L - 1);
+      const int b = L - 1 - qc;
+      const float* lutp = s_lut4 + (b & 3) * LUTCOPY + (b & ~3);
       mbar_wait(bar_mma, mma_phase);
       mma_phase ^= 1;
       tc_fence_after();
-      const float lse_q = s_lse[q < 256 ? q : 0];
-      const float D_q = s_D[q < 256 ? q : 0];
-      const float* lut_q = s_lut + (L - 1 - q);
+      const float lse_q = s_lse[q];
+      const float D_q = s_D[q];
       uint8_t* prow = smem + EB_P_OFF + chalf * 16384 + r * 128;
       uint8_t* dsrow = smem + EB_DS_OFF + chalf * 16384 + r * 128;
 #pragma unroll 1
@@ -391,32 +418,49 @@ enc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
         tmem_ld_32x32(t_row + TM_S + chalf * 64 + c * 32, sv);
         tmem_ld_32x32(t_row + TM_DP + chalf * 64 + c * 32, dpv);
         tmem_ld_wait();
-        float pr[32], ds[32];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const int k = kt * 128 + chalf * 64 + c * 32 + i;
-          float pv = 0.f;
-          if (q < L && k < L) {
-            const float s = s_mask[k] ? __uint_as_float(sv[i]) + lut_q[k] : MASK_MIN;
-            pv = __expf(s - lse_q);
-          }
-          pr[i] = pv;
-          ds[i] = pv * (__uint_as_float(dpv[i]) - D_q);
-        }
+        const int kbase = kt * 128 + chalf * 64 + c * 32;  // first key of this 32-column chunk
+        // bias-gradient index of the diagonal d = i - lane of this 32x32 sub-block: rel = k - q
+        const int idx0 = (kbase - (qt * 128 + quarter * 32)) + (L - 1);
+        float R = 0.f;
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
+          const float4 lb0 = *reinterpret_cast<const float4*>(lutp + kbase + u * 8);
+          const float4 lb1 = *reinterpret_cast<const float4*>(lutp + kbase + u * 8 + 4);
+          const float4 km0 = *reinterpret_cast<const float4*>(s_kmask + kbase + u * 8);
+          const float4 km1 = *reinterpret_cast<const float4*>(s_kmask + kbase + u * 8 + 4);
+          const float lbv[8] = {lb0.x, lb0.y, lb0.z, lb0.w, lb1.x, lb1.y, lb1.z, lb1.w};
+          const float kmv[8] = {km0.x, km0.y, km0.z, km0.w, km1.x, km1.y, km1.z, km1.w};
+          float pr[8], ds[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float sc = (__uint_as_float(sv[u * 8 + i]) + lbv[i]) + kmv[i];
+            pr[i] = fast_exp2((sc - lse_q) * LOG2E_F);
+            ds[i] = pr[i] * (__uint_as_float(dpv[u * 8 + i]) - D_q);
+            // systolic skewed reduction: R travels one lane up per column, collecting the diagonal k - q
+            R = fmaf(__shfl_up_sync(0xffffffffu, R, 1), keep, ds[i]);
+            const int col = u * 8 + i;
+            if (col < 31 && lane == 31) {
+              const int idx = idx0 + col - 31;
+              if (idx >= 0 && idx < nlut) atomicAdd(&s_dlut[idx], R);
+            }
+          }
           const int unit = ((c * 4 + u) ^ (r & 7)) << 4;
           uint4 o;
-          o.x = pack_bf16x2(pr[u * 8 + 0], pr[u * 8 + 1]);
-          o.y = pack_bf16x2(pr[u * 8 + 2], pr[u * 8 + 3]);
-          o.z = pack_bf16x2(pr[u * 8 + 4], pr[u * 8 + 5]);
-          o.w = pack_bf16x2(pr[u * 8 + 6], pr[u * 8 + 7]);
+          o.x = pack_bf16x2(pr[0], pr[1]);
+          o.y = pack_bf16x2(pr[2], pr[3]);
+          o.z = pack_bf16x2(pr[4], pr[5]);
+          o.w = pack_bf16x2(pr[6], pr[7]);
           *reinterpret_cast<uint4*>(prow + unit) = o;
-          o.x = pack_bf16x2(ds[u * 8 + 0], ds[u * 8 + 1]);
-          o.y = pack_bf16x2(ds[u * 8 + 2], ds[u * 8 + 3]);
-          o.z = pack_bf16x2(ds[u * 8 + 4], ds[u * 8 + 5]);
-          o.w = pack_bf16x2(ds[u * 8 + 6], ds[u * 8 + 7]);
+          o.x = pack_bf16x2(ds[0], ds[1]);
+          o.y = pack_bf16x2(ds[2], ds[3]);
+          o.z = pack_bf16x2(ds[4], ds[5]);
+          o.w = pack_bf16x2(ds[6], ds[7]);
           *reinterpret_cast<uint4*>(dsrow + unit) = o;
+        }
+        {
+          // after 32 columns lane l holds the complete diagonal d = 31 - l
+          const int idx = idx0 + 31 - lane;
+          if (idx >= 0 && idx < nlut) atomicAdd(&s_dlut[idx], R);
         }
       }
       fence_proxy_async_smem();
@@ -447,32 +491,14 @@ enc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
         if (nk < nt) issue_s_dp(nq, nk);
         umma_commit(bar_mma);
       }
-      // bias gradient: diagonal sums of this 128x128 dS block, read back (bf16) from shared memory.
-      // thread t owns the diagonal d = t - 127 (k_local - q_local); consecutive threads read
-      // consecutive keys of one row, so the reads are conflict-free.
-      {
-        const int d = tid - 127;
-        float acc = 0.f;
-        if (d < 128) {
-          const int qlo = d < 0 ? -d : 0, qhi = d > 0 ? 128 - d : 128;
-          for (int qq = qlo; qq < qhi; ++qq) {
-            const int kk = qq + d;
-            const uint8_t* a = smem + EB_DS_OFF + (kk >> 6) * 16384 + qq * 128 + ((((kk & 63) >> 3) ^ (qq & 7)) << 4) +
-                               ((kk & 7) << 1);
-            acc += __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(a));
-          }
-          const int rel = (kt - qt) * 128 + d;
-          if (rel > -L && rel < L && acc != 0.f) atomicAdd(&s_dlut[rel + L - 1], acc);
-        }
-      }
       if (qt == nt - 1) {
         // dK[kt], dV[kt] are final once the MMAs just issued complete
         mbar_wait(bar_mma, mma_phase);
         tc_fence_after();
         const int key = kt * 128 + r;
-        uint32_t a[32], b[32];
+        uint32_t a[32], bb[32];
         tmem_ld_32x32(t_row + TM_DK + chalf * 32, a);
-        tmem_ld_32x32(t_row + TM_DV + chalf * 32, b);
+        tmem_ld_32x32(t_row + TM_DV + chalf * 32, bb);
         tmem_ld_wait();
         if (key < L) {
           __nv_bfloat16* dk = p.dqkv + static_cast<size_t>(row0 + key) * 3 * p.inner + p.inner + h * 64 + chalf * 32;
@@ -485,20 +511,20 @@ enc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
             o.z = pack_bf16x2(__uint_as_float(a[u * 8 + 4]), __uint_as_float(a[u * 8 + 5]));
             o.w = pack_bf16x2(__uint_as_float(a[u * 8 + 6]), __uint_as_float(a[u * 8 + 7]));
             *reinterpret_cast<uint4*>(dk + u * 8) = o;
-            o.x = pack_bf16x2(__uint_as_float(b[u * 8 + 0]), __uint_as_float(b[u * 8 + 1]));
-            o.y = pack_bf16x2(__uint_as_float(b[u * 8 + 2]), __uint_as_float(b[u * 8 + 3]));
-            o.z = pack_bf16x2(__uint_as_float(b[u * 8 + 4]), __uint_as_float(b[u * 8 + 5]));
-            o.w = pack_bf16x2(__uint_as_float(b[u * 8 + 6]), __uint_as_float(b[u * 8 + 7]));
+            o.x = pack_bf16x2(__uint_as_float(bb[u * 8 + 0]), __uint_as_float(bb[u * 8 + 1]));
+            o.y = pack_bf16x2(__uint_as_float(bb[u * 8 + 2]), __uint_as_float(bb[u * 8 + 3]));
+            o.z = pack_bf16x2(__uint_as_float(bb[u * 8 + 4]), __uint_as_float(bb[u * 8 + 5]));
+            o.w = pack_bf16x2(__uint_as_float(bb[u * 8 + 6]), __uint_as_float(bb[u * 8 + 7]));
             *reinterpret_cast<uint4*>(dv + u * 8) = o;
           }
         }
         // the wait above did not consume the phase: the loop head waits on the same completion
         tc_fence_before();
+        __syncthreads();  // dK/dV TMEM reads done before the next key tile's first MMA overwrites them
       }
-      __syncthreads();  // diagonal reads of dS done before the next block overwrites it
     }
   }
-  // all MMAs are complete here only if the last loop iteration waited (qt == nt-1 -> yes)
+  // every MMA has completed (the last iteration waited for the final commit)
   {
     tc_fence_after();
 #pragma unroll 1
@@ -521,6 +547,7 @@ enc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
       }
     }
   }
+  __syncthreads();
   if (p.dlut) {
     for (int i = tid; i < nlut; i += 256) {
       const float v = s_dlut[i];

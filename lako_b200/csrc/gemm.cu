@@ -28,7 +28,8 @@ struct GemmCfg {
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES = (BN == 256) ? 4 : 6;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int STAGING_BYTES = 4 * 4096;  // per epilogue warp: 32 rows x 64 bf16, 16B-unit XOR swizzle
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 };
 
 struct GemmParams {
@@ -49,7 +50,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;
   uint8_t* sB = smem + STAGES * Cfg::A_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint8_t* sStage = smem + STAGES * Cfg::STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sStage + Cfg::STAGING_BYTES);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + STAGES;
   uint64_t* tfull_bar = bars + 2 * STAGES;
@@ -172,60 +174,80 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const int n0 = (mn % p.tiles_n) * BN;
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
-      const int row = m0 + q * 32 + lane;
-      const bool row_ok = row < p.M;
+      const uint32_t t_acc = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
+      if constexpr (EPI == EPI_BF16 || EPI == EPI_BF16_RELU || EPI == EPI_BF16_MASK) {
+        // bf16 output: TMEM (thread = row) -> registers -> per-warp swizzled smem -> coalesced 16 B stores
+        // (each store instruction writes four full 128 B row segments)
+        uint8_t* stg = sStage + q * 4096;
+        __nv_bfloat16* C = reinterpret_cast<__nv_bfloat16*>(p.C);
+        const __nv_bfloat16* AUX = reinterpret_cast<const __nv_bfloat16*>(p.aux);
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        const int col0 = n0 + c * 32;
-        if (col0 >= p.N) break;  // warp-uniform
-        uint32_t r[32];
-        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + c * 32, r);
-        tmem_ld_wait();
-        if (!row_ok) continue;
-        float v[32];
+        for (int g = 0; g < BN / 64; ++g) {
+          const int col0 = n0 + g * 64;
+          if (col0 >= p.N) break;  // warp-uniform
+          uint32_t r0[32], r1[32];
+          tmem_ld_32x32(t_acc + g * 64, r0);
+          tmem_ld_32x32(t_acc + g * 64 + 32, r1);
+          tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) * p.alpha;
-        const bool full = (col0 + 32 <= p.N);
-        if constexpr (EPI == EPI_BF16 || EPI == EPI_BF16_RELU || EPI == EPI_BF16_MASK) {
-          __nv_bfloat16* crow = reinterpret_cast<__nv_bfloat16*>(p.C) + static_cast<size_t>(row) * p.ldc + col0;
-          if constexpr (EPI == EPI_BF16_RELU) {
+          for (int u = 0; u < 8; ++u) {
+            const uint32_t* rr = (u < 4) ? r0 : r1;
+            const int o = (u & 3) * 8;
+            float v[8];
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+            for (int i = 0; i < 8; ++i) {
+              v[i] = __uint_as_float(rr[o + i]) * p.alpha;
+              if constexpr (EPI == EPI_BF16_RELU) v[i] = fmaxf(v[i], 0.f);
+            }
+            uint4 w;
+            w.x = pack_bf16x2(v[0], v[1]);
+            w.y = pack_bf16x2(v[2], v[3]);
+            w.z = pack_bf16x2(v[4], v[5]);
+            w.w = pack_bf16x2(v[6], v[7]);
+            *reinterpret_cast<uint4*>(stg + lane * 128 + ((u ^ (lane & 7)) << 4)) = w;
           }
-          if constexpr (EPI == EPI_BF16_MASK) {
-            const __nv_bfloat16* arow =
-                reinterpret_cast<const __nv_bfloat16*>(p.aux) + static_cast<size_t>(row) * p.ld_aux + col0;
-            if (full) {
+          __syncwarp();
+          const int unit = lane & 7;
+          const int col = col0 + unit * 8;
 #pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                uint4 m = *reinterpret_cast<const uint4*>(arow + j * 8);
-                const uint32_t mw[4] = {m.x, m.y, m.z, m.w};
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  if (!(bf16_lo(mw[e]) > 0.f)) v[j * 8 + e * 2] = 0.f;
-                  if (!(bf16_hi(mw[e]) > 0.f)) v[j * 8 + e * 2 + 1] = 0.f;
-                }
+          for (int it = 0; it < 8; ++it) {
+            const int rl = it * 4 + (lane >> 3);
+            const int row = m0 + q * 32 + rl;
+            uint4 w = *reinterpret_cast<const uint4*>(stg + rl * 128 + ((unit ^ (rl & 7)) << 4));
+            if (row < p.M && col < p.N) {
+              if constexpr (EPI == EPI_BF16_MASK) {
+                const uint4 a = *reinterpret_cast<const uint4*>(AUX + static_cast<size_t>(row) * p.ld_aux + col);
+                // keep dY where the forward activation was > 0 (sign bit clear and non-zero)
+                auto keep2 = [](uint32_t val, uint32_t act) -> uint32_t {
+                  const uint32_t lo = ((act & 0x7fffu) != 0 && (act & 0x8000u) == 0) ? 0x0000ffffu : 0u;
+                  const uint32_t hi = ((act & 0x7fff0000u) != 0 && (act & 0x80000000u) == 0) ? 0xffff0000u : 0u;
+                  return val & (lo | hi);
+                };
+                w.x = keep2(w.x, a.x);
+                w.y = keep2(w.y, a.y);
+                w.z = keep2(w.z, a.z);
+                w.w = keep2(w.w, a.w);
               }
-            } else {
-              for (int i = 0; i < 32; ++i)
-                if (col0 + i < p.N && !(__bfloat162float(arow[i]) > 0.f)) v[i] = 0.f;
+              *reinterpret_cast<uint4*>(C + static_cast<size_t>(row) * p.ldc + col) = w;
             }
           }
-          if (full) {
+          __syncwarp();
+        }
+      } else {
+        const int row = m0 + q * 32 + lane;
+        const bool row_ok = row < p.M;
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+          const int col0 = n0 + c * 32;
+          if (col0 >= p.N) break;  // warp-uniform
+          uint32_t r[32];
+          tmem_ld_32x32(t_acc + c * 32, r);
+          tmem_ld_wait();
+          if (!row_ok) continue;
+          float v[32];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              uint4 o;
-              o.x = pack_bf16x2(v[j * 8 + 0], v[j * 8 + 1]);
-              o.y = pack_bf16x2(v[j * 8 + 2], v[j * 8 + 3]);
-              o.z = pack_bf16x2(v[j * 8 + 4], v[j * 8 + 5]);
-              o.w = pack_bf16x2(v[j * 8 + 6], v[j * 8 + 7]);
-              *reinterpret_cast<uint4*>(crow + j * 8) = o;
-            }
-          } else {
-            for (int i = 0; i < 32; ++i)
-              if (col0 + i < p.N) crow[i] = __float2bfloat16(v[i]);
-          }
-        } else {
+          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) * p.alpha;
+          const bool full = (col0 + 32 <= p.N);
           float* crow = reinterpret_cast<float*>(p.C) + static_cast<size_t>(row) * p.ldc + col0;
           if constexpr (EPI == EPI_F32) {
             if (full) {
@@ -325,6 +347,7 @@ int gemm_bf16(const void* A, const void* B, void* C, int M, int N, int K, int ld
   LAKO_REQUIRE(epi != EPI_BF16_MASK || aux != nullptr, LAKO_ERR_BAD_ARG);
   const bool out_bf16 = (epi == EPI_BF16 || epi == EPI_BF16_RELU || epi == EPI_BF16_MASK);
   LAKO_REQUIRE((reinterpret_cast<uintptr_t>(C) & 15) == 0 && ldc % (out_bf16 ? 8 : 4) == 0, LAKO_ERR_BAD_ARG);
+  LAKO_REQUIRE(!out_bf16 || N % 8 == 0, LAKO_ERR_UNSUPPORTED);  // bf16 epilogue stores 8-element (16 B) units
   if (epi == EPI_BF16_MASK)
     LAKO_REQUIRE((reinterpret_cast<uintptr_t>(aux) & 15) == 0 && ld_aux % 8 == 0, LAKO_ERR_BAD_ARG);
 
