@@ -396,7 +396,8 @@ enc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
 
   const int r = quarter * 32 + lane;  // row within a 128-row tile == TMEM lane
   const uint32_t t_row = tmem + (static_cast<uint32_t>(quarter * 32) << 16);
-  const float keep = (lane == 0) ? 0.f : 1.f;  // systolic diagonal sums: lane 0 starts a new diagonal
+  const float keep = (lane == 0) ? 0.f : 1.f;      // systolic diagonal sums: lane 0 starts a new diagonal (up pass)
+  const float keep_dn = (lane == 31) ? 0.f : 1.f;  // lane 31 starts a new diagonal (down pass)
   uint32_t mma_phase = 0;
 
   for (int kt = 0; kt < nt; ++kt) {
@@ -421,7 +422,7 @@ enc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
         const int kbase = kt * 128 + chalf * 64 + c * 32;  // first key of this 32-column chunk
         // bias-gradient index of the diagonal d = i - lane of this 32x32 sub-block: rel = k - q
         const int idx0 = (kbase - (qt * 128 + quarter * 32)) + (L - 1);
-        float R = 0.f;
+        float ds[32];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
           const float4 lb0 = *reinterpret_cast<const float4*>(lutp + kbase + u * 8);
@@ -430,19 +431,12 @@ enc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
           const float4 km1 = *reinterpret_cast<const float4*>(s_kmask + kbase + u * 8 + 4);
           const float lbv[8] = {lb0.x, lb0.y, lb0.z, lb0.w, lb1.x, lb1.y, lb1.z, lb1.w};
           const float kmv[8] = {km0.x, km0.y, km0.z, km0.w, km1.x, km1.y, km1.z, km1.w};
-          float pr[8], ds[8];
+          float pr[8];
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const float sc = (__uint_as_float(sv[u * 8 + i]) + lbv[i]) + kmv[i];
             pr[i] = fast_exp2((sc - lse_q) * LOG2E_F);
-            ds[i] = pr[i] * (__uint_as_float(dpv[u * 8 + i]) - D_q);
-            // systolic skewed reduction: R travels one lane up per column, collecting the diagonal k - q
-            R = fmaf(__shfl_up_sync(0xffffffffu, R, 1), keep, ds[i]);
-            const int col = u * 8 + i;
-            if (col < 31 && lane == 31) {
-              const int idx = idx0 + col - 31;
-              if (idx >= 0 && idx < nlut) atomicAdd(&s_dlut[idx], R);
-            }
+            ds[u * 8 + i] = pr[i] * (__uint_as_float(dpv[u * 8 + i]) - D_q);
           }
           const int unit = ((c * 4 + u) ^ (r & 7)) << 4;
           uint4 o;
@@ -451,16 +445,27 @@ enc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
           o.z = pack_bf16x2(pr[4], pr[5]);
           o.w = pack_bf16x2(pr[6], pr[7]);
           *reinterpret_cast<uint4*>(prow + unit) = o;
-          o.x = pack_bf16x2(ds[0], ds[1]);
-          o.y = pack_bf16x2(ds[2], ds[3]);
-          o.z = pack_bf16x2(ds[4], ds[5]);
-          o.w = pack_bf16x2(ds[6], ds[7]);
+          o.x = pack_bf16x2(ds[u * 8 + 0], ds[u * 8 + 1]);
+          o.y = pack_bf16x2(ds[u * 8 + 2], ds[u * 8 + 3]);
+          o.z = pack_bf16x2(ds[u * 8 + 4], ds[u * 8 + 5]);
+          o.w = pack_bf16x2(ds[u * 8 + 6], ds[u * 8 + 7]);
           *reinterpret_cast<uint4*>(dsrow + unit) = o;
         }
+        // Bias gradient = diagonal sums (k - q constant) of this 32x32 sub-block, as two systolic passes over
+        // the warp, exact in fp32.  Ascending columns with the partial sum moving one lane UP per column leaves
+        // diagonal d = 31 - lane (>= 0) complete in every lane; descending columns moving one lane DOWN leaves
+        // d = -lane (<= 0).  Lane 0 / lane 31 start a fresh diagonal each step (keep_* = 0 there).
+        float Rup = 0.f, Rdn = 0.f;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          Rup = fmaf(__shfl_up_sync(0xffffffffu, Rup, 1), keep, ds[i]);
+          Rdn = fmaf(__shfl_down_sync(0xffffffffu, Rdn, 1), keep_dn, ds[31 - i]);
+        }
         {
-          // after 32 columns lane l holds the complete diagonal d = 31 - l
-          const int idx = idx0 + 31 - lane;
-          if (idx >= 0 && idx < nlut) atomicAdd(&s_dlut[idx], R);
+          const int iu = idx0 + 31 - lane;
+          if (iu >= 0 && iu < nlut) atomicAdd(&s_dlut[iu], Rup);
+          const int id = idx0 - lane;
+          if (lane != 0 && id >= 0 && id < nlut) atomicAdd(&s_dlut[id], Rdn);  // d = 0 is already in Rup (lane 31)
         }
       }
       fence_proxy_async_smem();

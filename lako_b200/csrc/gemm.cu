@@ -41,6 +41,109 @@ struct GemmParams {
   float alpha;
 };
 
+// Epilogue of one 128-row x BN-column accumulator tile for the warp owning TMEM lane quarter q.
+template <int BN, int EPI>
+__device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t t_acc, uint8_t* sStage, int m0, int n0,
+                                              int q, int lane) {
+  if constexpr (EPI == EPI_BF16 || EPI == EPI_BF16_RELU || EPI == EPI_BF16_MASK) {
+    // bf16 output: TMEM (thread = row) -> registers -> per-warp swizzled smem -> coalesced 16 B stores
+    // (each store instruction writes four full 128 B row segments)
+    uint8_t* stg = sStage + q * 4096;
+    __nv_bfloat16* C = reinterpret_cast<__nv_bfloat16*>(p.C);
+    const __nv_bfloat16* AUX = reinterpret_cast<const __nv_bfloat16*>(p.aux);
+#pragma unroll 1
+    for (int g = 0; g < BN / 64; ++g) {
+      const int col0 = n0 + g * 64;
+      if (col0 >= p.N) break;  // warp-uniform
+      uint32_t r0[32], r1[32];
+      tmem_ld_32x32(t_acc + g * 64, r0);
+      tmem_ld_32x32(t_acc + g * 64 + 32, r1);
+      tmem_ld_wait();
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const uint32_t* rr = (u < 4) ? r0 : r1;
+        const int o = (u & 3) * 8;
+        float v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          v[i] = __uint_as_float(rr[o + i]) * p.alpha;
+          if constexpr (EPI == EPI_BF16_RELU) v[i] = fmaxf(v[i], 0.f);
+        }
+        uint4 w;
+        w.x = pack_bf16x2(v[0], v[1]);
+        w.y = pack_bf16x2(v[2], v[3]);
+        w.z = pack_bf16x2(v[4], v[5]);
+        w.w = pack_bf16x2(v[6], v[7]);
+        *reinterpret_cast<uint4*>(stg + lane * 128 + ((u ^ (lane & 7)) << 4)) = w;
+      }
+      __syncwarp();
+      const int unit = lane & 7;
+      const int col = col0 + unit * 8;
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        const int rl = it * 4 + (lane >> 3);
+        const int row = m0 + q * 32 + rl;
+        uint4 w = *reinterpret_cast<const uint4*>(stg + rl * 128 + ((unit ^ (rl & 7)) << 4));
+        if (row < p.M && col < p.N) {
+          if constexpr (EPI == EPI_BF16_MASK) {
+            const uint4 a = *reinterpret_cast<const uint4*>(AUX + static_cast<size_t>(row) * p.ld_aux + col);
+            // keep dY where the forward activation was > 0 (sign bit clear and non-zero)
+            auto keep2 = [](uint32_t val, uint32_t act) -> uint32_t {
+              const uint32_t lo = ((act & 0x7fffu) != 0 && (act & 0x8000u) == 0) ? 0x0000ffffu : 0u;
+              const uint32_t hi = ((act & 0x7fff0000u) != 0 && (act & 0x80000000u) == 0) ? 0xffff0000u : 0u;
+              return val & (lo | hi);
+            };
+            w.x = keep2(w.x, a.x);
+            w.y = keep2(w.y, a.y);
+            w.z = keep2(w.z, a.z);
+            w.w = keep2(w.w, a.w);
+          }
+          *reinterpret_cast<uint4*>(C + static_cast<size_t>(row) * p.ldc + col) = w;
+        }
+      }
+      __syncwarp();
+    }
+  } else {
+    const int row = m0 + q * 32 + lane;
+    const bool row_ok = row < p.M;
+#pragma unroll 1
+    for (int c = 0; c < BN / 32; ++c) {
+      const int col0 = n0 + c * 32;
+      if (col0 >= p.N) break;  // warp-uniform
+      uint32_t r[32];
+      tmem_ld_32x32(t_acc + c * 32, r);
+      tmem_ld_wait();
+      if (!row_ok) continue;
+      float v[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) * p.alpha;
+      const bool full = (col0 + 32 <= p.N);
+      float* crow = reinterpret_cast<float*>(p.C) + static_cast<size_t>(row) * p.ldc + col0;
+      if constexpr (EPI == EPI_F32) {
+        if (full) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            *reinterpret_cast<float4*>(crow + j * 4) = make_float4(v[j * 4], v[j * 4 + 1], v[j * 4 + 2], v[j * 4 + 3]);
+        } else {
+          for (int i = 0; i < 32; ++i)
+            if (col0 + i < p.N) crow[i] = v[i];
+        }
+      } else {  // EPI_F32_ATOMIC
+        if (full) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(crow + j * 4), "f"(v[j * 4]),
+                         "f"(v[j * 4 + 1]), "f"(v[j * 4 + 2]), "f"(v[j * 4 + 3])
+                         : "memory");
+        } else {
+          for (int i = 0; i < 32; ++i)
+            if (col0 + i < p.N) atomicAdd(crow + i, v[i]);
+        }
+      }
+    }
+  }
+}
+
 template <int BN, bool A_MN, bool B_MN, int EPI>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
@@ -174,104 +277,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const int n0 = (mn % p.tiles_n) * BN;
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
-      const uint32_t t_acc = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
-      if constexpr (EPI == EPI_BF16 || EPI == EPI_BF16_RELU || EPI == EPI_BF16_MASK) {
-        // bf16 output: TMEM (thread = row) -> registers -> per-warp swizzled smem -> coalesced 16 B stores
-        // (each store instruction writes four full 128 B row segments)
-        uint8_t* stg = sStage + q * 4096;
-        __nv_bfloat16* C = reinterpret_cast<__nv_bfloat16*>(p.C);
-        const __nv_bfloat16* AUX = reinterpret_cast<const __nv_bfloat16*>(p.aux);
-#pragma unroll 1
-        for (int g = 0; g < BN / 64; ++g) {
-          const int col0 = n0 + g * 64;
-          if (col0 >= p.N) break;  // warp-uniform
-          uint32_t r0[32], r1[32];
-          tmem_ld_32x32(t_acc + g * 64, r0);
-          tmem_ld_32x32(t_acc + g * 64 + 32, r1);
-          tmem_ld_wait();
-#pragma unroll
-          for (int u = 0; u < 8; ++u) {
-            const uint32_t* rr = (u < 4) ? r0 : r1;
-            const int o = (u & 3) * 8;
-            float v[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              v[i] = __uint_as_float(rr[o + i]) * p.alpha;
-              if constexpr (EPI == EPI_BF16_RELU) v[i] = fmaxf(v[i], 0.f);
-            }
-            uint4 w;
-            w.x = pack_bf16x2(v[0], v[1]);
-            w.y = pack_bf16x2(v[2], v[3]);
-            w.z = pack_bf16x2(v[4], v[5]);
-            w.w = pack_bf16x2(v[6], v[7]);
-            *reinterpret_cast<uint4*>(stg + lane * 128 + ((u ^ (lane & 7)) << 4)) = w;
-          }
-          __syncwarp();
-          const int unit = lane & 7;
-          const int col = col0 + unit * 8;
-#pragma unroll
-          for (int it = 0; it < 8; ++it) {
-            const int rl = it * 4 + (lane >> 3);
-            const int row = m0 + q * 32 + rl;
-            uint4 w = *reinterpret_cast<const uint4*>(stg + rl * 128 + ((unit ^ (rl & 7)) << 4));
-            if (row < p.M && col < p.N) {
-              if constexpr (EPI == EPI_BF16_MASK) {
-                const uint4 a = *reinterpret_cast<const uint4*>(AUX + static_cast<size_t>(row) * p.ld_aux + col);
-                // keep dY where the forward activation was > 0 (sign bit clear and non-zero)
-                auto keep2 = [](uint32_t val, uint32_t act) -> uint32_t {
-                  const uint32_t lo = ((act & 0x7fffu) != 0 && (act & 0x8000u) == 0) ? 0x0000ffffu : 0u;
-                  const uint32_t hi = ((act & 0x7fff0000u) != 0 && (act & 0x80000000u) == 0) ? 0xffff0000u : 0u;
-                  return val & (lo | hi);
-                };
-                w.x = keep2(w.x, a.x);
-                w.y = keep2(w.y, a.y);
-                w.z = keep2(w.z, a.z);
-                w.w = keep2(w.w, a.w);
-              }
-              *reinterpret_cast<uint4*>(C + static_cast<size_t>(row) * p.ldc + col) = w;
-            }
-          }
-          __syncwarp();
-        }
-      } else {
-        const int row = m0 + q * 32 + lane;
-        const bool row_ok = row < p.M;
-#pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
-          const int col0 = n0 + c * 32;
-          if (col0 >= p.N) break;  // warp-uniform
-          uint32_t r[32];
-          tmem_ld_32x32(t_acc + c * 32, r);
-          tmem_ld_wait();
-          if (!row_ok) continue;
-          float v[32];
-#pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) * p.alpha;
-          const bool full = (col0 + 32 <= p.N);
-          float* crow = reinterpret_cast<float*>(p.C) + static_cast<size_t>(row) * p.ldc + col0;
-          if constexpr (EPI == EPI_F32) {
-            if (full) {
-#pragma unroll
-              for (int j = 0; j < 8; ++j)
-                *reinterpret_cast<float4*>(crow + j * 4) = make_float4(v[j * 4], v[j * 4 + 1], v[j * 4 + 2], v[j * 4 + 3]);
-            } else {
-              for (int i = 0; i < 32; ++i)
-                if (col0 + i < p.N) crow[i] = v[i];
-            }
-          } else {  // EPI_F32_ATOMIC
-            if (full) {
-#pragma unroll
-              for (int j = 0; j < 8; ++j)
-                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(crow + j * 4), "f"(v[j * 4]),
-                             "f"(v[j * 4 + 1]), "f"(v[j * 4 + 2]), "f"(v[j * 4 + 3])
-                             : "memory");
-            } else {
-              for (int i = 0; i < 32; ++i)
-                if (col0 + i < p.N) atomicAdd(crow + i, v[i]);
-            }
-          }
-        }
-      }
+      epilogue_tile<BN, EPI>(p, tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN, sStage, m0, n0, q, lane);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);
@@ -288,6 +294,221 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
   }
+}
+
+// ------------------------------------------------------------------------------------------------
+// CTA-pair variant: a 2-CTA cluster computes a 256 x 256 tile with tcgen05.mma.cta_group::2 (UMMA_M = 256).
+// Each CTA stages its own 128 rows of A and HALF of the B tile (128 of the 256 N rows); the tensor cores
+// of both SMs read the B halves from both CTAs' shared memory.  Per k-block the pair pulls 64 KB from L2
+// for 256x256x64 MACs, vs 96 KB for two independent 128x256 CTAs: the single-CTA kernel saturates the
+// L2->SM fabric (~6.3 KB/clk chip-wide) at ~50 % of the tensor peak, this one does not.
+// Roles per CTA as above; only the leader CTA (cluster rank 0) issues MMAs and its commits are multicast
+// to the mbarriers of both CTAs.
+// ------------------------------------------------------------------------------------------------
+struct Gemm2Cfg {
+  static constexpr int BN = 256;
+  static constexpr int A_BYTES = 128 * BK * 2;       // this CTA's 128 rows of A
+  static constexpr int B_BYTES = 128 * BK * 2;       // this CTA's half of the 256-row B tile
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = 6;
+  static constexpr int STAGING_BYTES = 4 * 4096;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + 1024 + 256;
+};
+
+template <bool A_MN, bool B_MN, int EPI>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
+gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+  using Cfg = Gemm2Cfg;
+  constexpr int STAGES = Cfg::STAGES;
+  constexpr int BN = Cfg::BN;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + STAGES * Cfg::A_BYTES;
+  uint8_t* sStage = smem + STAGES * Cfg::STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sStage + Cfg::STAGING_BYTES);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + STAGES;
+  uint64_t* tfull_bar = bars + 2 * STAGES;
+  uint64_t* tempty_bar = bars + 2 * STAGES + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full_bar[i], 2);   // one arrive.expect_tx per CTA of the pair (only the leader's copy is used)
+      mbar_init(&empty_bar[i], 1);  // multicast tcgen05.commit
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull_bar[i], 1);   // multicast tcgen05.commit
+      mbar_init(&tempty_bar[i], 8);  // 4 epilogue warps x 2 CTAs (only the leader's copy is used)
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc_2sm(tmem_slot, 512);
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int tiles_mn = p.tiles_m * p.tiles_n;  // tiles_m counts 256-row tiles here
+  const int total_tiles = tiles_mn * p.splitk;
+  const int cluster_id = blockIdx.x >> 1;
+  const int n_clusters = gridDim.x >> 1;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = cluster_id; t < total_tiles; t += n_clusters) {
+        const int ks = t / tiles_mn;
+        const int mn = t - ks * tiles_mn;
+        const int m0 = (mn / p.tiles_n) * 256 + static_cast<int>(rank) * 128;
+        const int n0 = (mn % p.tiles_n) * BN + static_cast<int>(rank) * 128;
+        const int kb0 = ks * p.kb_per_split;
+        const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          const uint32_t fb = mapa_u32(&full_bar[stage], 0);  // the leader's barrier
+          mbar_arrive_expect_tx_cluster(fb, Cfg::STAGE_BYTES);
+          uint8_t* a = sA + stage * Cfg::A_BYTES;
+          uint8_t* b = sB + stage * Cfg::B_BYTES;
+          if constexpr (!A_MN) {
+            tma_load_2d_2sm(a, &tmA, fb, kb * BK, m0);
+          } else {
+#pragma unroll
+            for (int c = 0; c < 2; ++c) tma_load_2d_2sm(a + c * 8192, &tmA, fb, m0 + c * 64, kb * BK);
+          }
+          if constexpr (!B_MN) {
+            tma_load_2d_2sm(b, &tmB, fb, kb * BK, n0);
+          } else {
+#pragma unroll
+            for (int c = 0; c < 2; ++c) tma_load_2d_2sm(b + c * 8192, &tmB, fb, n0 + c * 64, kb * BK);
+          }
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (leader && lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(256, BN, A_MN, B_MN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int t = cluster_id; t < total_tiles; t += n_clusters) {
+        const int ks = t / tiles_mn;
+        const int kb0 = ks * p.kb_per_split;
+        const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(sA + stage * Cfg::A_BYTES);
+          const uint32_t b_addr = smem_u32(sB + stage * Cfg::B_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            const uint64_t adesc = A_MN ? make_smem_desc_sw128(a_addr + k * 2048, 8192, 1024)
+                                        : make_smem_desc_sw128(a_addr + k * 32, 16, 1024);
+            const uint64_t bdesc = B_MN ? make_smem_desc_sw128(b_addr + k * 2048, 8192, 1024)
+                                        : make_smem_desc_sw128(b_addr + k * 32, 16, 1024);
+            umma_bf16_2sm(d_tmem, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit_2sm(&empty_bar[stage]);
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit_2sm(&tfull_bar[acc]);
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    const int q = warp & 3;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int t = cluster_id; t < total_tiles; t += n_clusters) {
+      const int ks = t / tiles_mn;
+      const int mn = t - ks * tiles_mn;
+      const int m0 = (mn / p.tiles_n) * 256 + static_cast<int>(rank) * 128;
+      const int n0 = (mn % p.tiles_n) * BN;
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      epilogue_tile<BN, EPI>(p, tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN, sStage, m0, n0, q, lane);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(mapa_u32(&tempty_bar[acc], 0));
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();  // the peer's smem / TMEM / barriers must outlive every remote access
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc_2sm(tmem_base, 512);
+  }
+}
+
+template <bool A_MN, bool B_MN, int EPI>
+static int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t stream) {
+  using Cfg = Gemm2Cfg;
+  auto kern = gemm2_bf16_kernel<A_MN, B_MN, EPI>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) {
+      set_last_error(cudaGetErrorString(e), __FILE__, __LINE__);
+      return LAKO_ERR_LAUNCH;
+    }
+    configured = true;
+  }
+  const int total = p.tiles_m * p.tiles_n * p.splitk;
+  const int clusters = min(total, device_sm_count() / 2);
+  kern<<<clusters * 2, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, p);
+  LAKO_CHECK_LAUNCH();
+  return LAKO_OK;
+}
+
+template <bool A_MN, bool B_MN>
+static int dispatch_epi2(int epi, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t s) {
+  switch (epi) {
+    case EPI_BF16: return launch_gemm2<A_MN, B_MN, EPI_BF16>(tmA, tmB, p, s);
+    case EPI_BF16_RELU: return launch_gemm2<A_MN, B_MN, EPI_BF16_RELU>(tmA, tmB, p, s);
+    case EPI_F32: return launch_gemm2<A_MN, B_MN, EPI_F32>(tmA, tmB, p, s);
+    case EPI_F32_ATOMIC: return launch_gemm2<A_MN, B_MN, EPI_F32_ATOMIC>(tmA, tmB, p, s);
+    case EPI_BF16_MASK: return launch_gemm2<A_MN, B_MN, EPI_BF16_MASK>(tmA, tmB, p, s);
+  }
+  set_last_error("unknown epilogue", __FILE__, __LINE__);
+  return LAKO_ERR_BAD_ARG;
+}
+
+static int dispatch_major2(int a_mn, int b_mn, int epi, const CUtensorMap& tmA, const CUtensorMap& tmB,
+                           const GemmParams& p, cudaStream_t s) {
+  if (!a_mn && !b_mn) return dispatch_epi2<false, false>(epi, tmA, tmB, p, s);
+  if (!a_mn && b_mn) return dispatch_epi2<false, true>(epi, tmA, tmB, p, s);
+  if (a_mn && !b_mn) return dispatch_epi2<true, false>(epi, tmA, tmB, p, s);
+  return dispatch_epi2<true, true>(epi, tmA, tmB, p, s);
 }
 
 template <int BN, bool A_MN, bool B_MN, int EPI>
@@ -352,6 +573,13 @@ int gemm_bf16(const void* A, const void* B, void* C, int M, int N, int K, int ld
     LAKO_REQUIRE((reinterpret_cast<uintptr_t>(aux) & 15) == 0 && ld_aux % 8 == 0, LAKO_ERR_BAD_ARG);
 
   const int sms = device_sm_count();
+  // bn: 0 = auto, 128 / 256 = single-CTA kernel with that tile width, 512 = CTA-pair kernel (256x256 per cluster)
+  bool use_pair = (bn == 512);
+  if (bn == 0 && M > 128 && N > 128) {
+    const long t_pair = static_cast<long>((M + 255) / 256) * ((N + 255) / 256);
+    use_pair = (t_pair >= sms / 4) || epi == EPI_F32_ATOMIC;
+  }
+  if (use_pair) bn = 256;
   if (bn != 128 && bn != 256) {
     // prefer 128x256 tiles; fall back to 128x128 when that leaves most of the chip idle
     const long t256 = static_cast<long>((M + BM - 1) / BM) * ((N + 255) / 256);
@@ -366,14 +594,15 @@ int gemm_bf16(const void* A, const void* B, void* C, int M, int N, int K, int ld
   p.ldc = ldc;
   p.ld_aux = ld_aux;
   p.alpha = alpha;
-  p.tiles_m = (M + BM - 1) / BM;
+  p.tiles_m = use_pair ? (M + 255) / 256 : (M + BM - 1) / BM;
   p.tiles_n = (N + bn - 1) / bn;
   p.kb_total = (K + BK - 1) / BK;
   if (epi != EPI_F32_ATOMIC) {
     splitk = 1;
   } else if (splitk <= 0) {
     const int tiles = p.tiles_m * p.tiles_n;
-    splitk = (tiles >= sms) ? 1 : (2 * sms + tiles - 1) / tiles;  // ~2 waves
+    const int slots = use_pair ? sms / 2 : sms;
+    splitk = (tiles >= slots) ? 1 : (2 * slots + tiles - 1) / tiles;  // ~2 waves
     const int max_split = max(1, p.kb_total / 4);                 // keep >= 4 k-blocks per split
     splitk = min(splitk, max_split);
   }
@@ -388,11 +617,12 @@ int gemm_bf16(const void* A, const void* B, void* C, int M, int N, int K, int ld
     rc = get_tensor_map_2d(&tmA, A, M, K, lda, 64, BK);
   if (rc) return rc;
   if (!b_mn)
-    rc = get_tensor_map_2d(&tmB, B, K, N, ldb, 64, bn);
+    rc = get_tensor_map_2d(&tmB, B, K, N, ldb, 64, use_pair ? 128 : bn);
   else
     rc = get_tensor_map_2d(&tmB, B, N, K, ldb, 64, BK);
   if (rc) return rc;
   ProfScope prof(PROF_GEMM, 2.0 * M * N * static_cast<double>(K), stream);
+  if (use_pair) return dispatch_major2(a_mn, b_mn, epi, tmA, tmB, p, stream);
   if (bn == 256) return dispatch_major<256>(a_mn, b_mn, epi, tmA, tmB, p, stream);
   return dispatch_major<128>(a_mn, b_mn, epi, tmA, tmB, p, stream);
 }

@@ -40,15 +40,26 @@ def _run(M, N, K, a_mn, b_mn, epi, bn=0, splitk=0, alpha=1.0):
 
 
 @pytest.mark.parametrize("a_mn,b_mn", [(False, False), (False, True), (True, False), (True, True)])
-@pytest.mark.parametrize("bn", [128, 256])
+@pytest.mark.parametrize("bn", [128, 256, 512])
 def test_gemm_majors(a_mn, b_mn, bn):
     from lako_b200 import _native as nat
     _run(256, 512, 256, a_mn, b_mn, nat.EPI_F32, bn=bn)
 
 
+@pytest.mark.parametrize("bn", [0, 512])
 @pytest.mark.parametrize("epi", [0, 1, 2, 3, 4])
-def test_gemm_epilogues(epi):
-    _run(384, 768, 320, False, False, epi, alpha=0.5)
+def test_gemm_epilogues(epi, bn):
+    _run(384, 768, 320, False, False, epi, alpha=0.5, bn=bn)
+
+
+@pytest.mark.parametrize("M,N,K", [(16000, 2304, 768), (300, 520, 136), (4000, 768, 3072), (257, 264, 64)])
+def test_gemm_pair_kernel_edges(M, N, K):
+    """CTA-pair (cta_group::2) kernel: ragged M/N/K, every operand-major combination."""
+    from lako_b200 import _native as nat
+    _run(M, N, K, False, False, nat.EPI_BF16, bn=512)
+    _run(M, N, K, False, True, nat.EPI_BF16_RELU, bn=512)
+    _run(M, N, K, True, False, nat.EPI_F32, bn=512)
+    _run(M, N, K, True, True, nat.EPI_F32_ATOMIC, bn=512, splitk=3)
 
 
 @pytest.mark.parametrize("M,N,K", [(80, 768, 768), (1, 136, 64), (200, 32128 // 8, 128), (130, 264, 72),
