@@ -176,9 +176,11 @@ int xattn_fwd(const __nv_bfloat16* q, const __nv_bfloat16* kv, const unsigned ch
     configured = true;
   }
   ProfScope prof(PROF_XATTN, 4.0 * B * H * static_cast<double>(T) * M * 64, s);
-  dim3 grid(p.splits, H, B);
-  xattn_fwd_kernel<<<grid, 128, dyn, s>>>(p);
-  LAKO_CHECK_LAUNCH();
+  (void)dyn;
+  {
+    int rc = xattn_fwd_mma(q, kv, mask, tok_score, workspace, B, T, M, H, ldq, ldkv, koff, voff, s);
+    if (rc) return rc;
+  }
   dim3 g2(T, H, B);
   xattn_combine_kernel<<<g2, 64, 0, s>>>(workspace, out, lse, T, H, p.splits, ldo);
   LAKO_CHECK_LAUNCH();
@@ -321,10 +323,9 @@ int xattn_bwd(const __nv_bfloat16* q, const __nv_bfloat16* kv, const unsigned ch
     configured = true;
   }
   ProfScope prof(PROF_XATTN, 8.0 * B * H * static_cast<double>(T) * M * 64, s);
-  dim3 grid((M + XA_CH - 1) / XA_CH, H, B);
-  xattn_bwd_kernel<<<grid, 256, dyn, s>>>(p);
-  LAKO_CHECK_LAUNCH();
-  return LAKO_OK;
+  (void)dyn;
+  (void)p;
+  return xattn_bwd_mma(q, kv, mask, out, dout, lse, dkv, dq_f32, B, T, M, H, ldq, ldkv, koff, voff, ldo, s);
 }
 
 // ------------------------------------------------------------------------------------------------

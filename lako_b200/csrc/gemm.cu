@@ -587,8 +587,11 @@ int gemm_bf16(const void* A, const void* B, void* C, int M, int N, int K, int ld
   const int sms = device_sm_count();
   // bn: 0 = auto, 128 / 256 = single-CTA kernel with that tile width, 512 = CTA-pair kernel (256x256 per cluster)
   bool use_pair = (bn == 512);
-  // (the pair kernel is functional but currently slower than the single-CTA kernel -- see DESIGN.md -- so it
-  //  is only used when asked for explicitly with bn == 512)
+  if (bn == 0 && M >= 512 && N >= 256) {
+    // the pair kernel needs ~1/3 less L2->SM operand traffic per FLOP; use it whenever the problem fills the chip
+    const long t_pair = static_cast<long>((M + 255) / 256) * ((N + 255) / 256);
+    use_pair = (t_pair >= sms / 4) || epi == EPI_F32_ATOMIC;
+  }
   if (use_pair) bn = 256;
   if (bn != 128 && bn != 256) {
     // prefer 128x256 tiles; fall back to 128x128 when that leaves most of the chip idle

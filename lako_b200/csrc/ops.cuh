@@ -48,6 +48,12 @@ int xattn_fwd(const __nv_bfloat16* q, const __nv_bfloat16* kv, const unsigned ch
 int xattn_bwd(const __nv_bfloat16* q, const __nv_bfloat16* kv, const unsigned char* mask, const __nv_bfloat16* out,
               const __nv_bfloat16* dout, const float* lse, __nv_bfloat16* dkv, float* dq_f32, int B, int T, int M,
               int H, int ldq, int ldkv, int koff, int voff, int ldo, cudaStream_t s);
+// xattn_mma.cu
+int xattn_fwd_mma(const __nv_bfloat16* q, const __nv_bfloat16* kv, const unsigned char* mask, float* tok_score,
+                  float* workspace, int B, int T, int M, int H, int ldq, int ldkv, int koff, int voff, cudaStream_t s);
+int xattn_bwd_mma(const __nv_bfloat16* q, const __nv_bfloat16* kv, const unsigned char* mask, const __nv_bfloat16* out,
+                  const __nv_bfloat16* dout, const float* lse, __nv_bfloat16* dkv, float* dq_f32, int B, int T, int M,
+                  int H, int ldq, int ldkv, int koff, int voff, int ldo, cudaStream_t s);
 int dself_fwd(const __nv_bfloat16* qkv, const float* lut, __nv_bfloat16* out, float* probs, int B, int T, int H,
               cudaStream_t s);
 int dself_bwd(const __nv_bfloat16* qkv, const __nv_bfloat16* dout, const float* probs, __nv_bfloat16* dqkv, float* dlut,

@@ -69,7 +69,7 @@ def test_enc_attn_fwd_bwd(P, L, H):
     assert terr < 0.02 * tab.grad.abs().max().item() + 1e-2, (terr, tab.grad.abs().max().item())
 
 
-@pytest.mark.parametrize("B,T,M,H,nl", [(2, 6, 96, 2, 2), (3, 10, 500, 3, 1), (1, 1, 333, 2, 2), (2, 20, 2000, 12, 1)])
+@pytest.mark.parametrize("B,T,M,H,nl", [(2, 6, 96, 2, 2), (3, 10, 500, 3, 1), (1, 1, 333, 2, 2), (2, 20, 2000, 12, 1), (2, 40, 300, 2, 1), (1, 64, 129, 1, 1)])
 def test_xattn_fwd_bwd(B, T, M, H, nl):
     nat = _nat()
     lib = nat.lib()
