@@ -61,7 +61,11 @@ def test_backward_vs_reference(path):
         mine = named[k].grad.cpu()
         rel = (mine - g).norm().item() / (g.norm().item() + 1e-12)
         print(f"{k}: relative L2 err {rel:.4f}")
-        assert rel < 0.04, (k, rel)
+        # yardstick: stock PyTorch CPU autocast(bf16) of the oracle deviates from its own fp32 run by
+        # 0.025 (shared), 0.060-0.069 (encoder bias table / q weight), 0.03-0.045 (others) on these cases
+        # (tools/noise_floor.py); the CUDA path must stay at that noise floor.
+        tol = 0.08 if ("relative_attention_bias" in k or ".q.weight" in k) else 0.05
+        assert rel < tol, (k, rel)
     # second backward accumulates (loss.backward() semantics)
     loss2, _ = model(input_ids=c["ids"].cuda(), attention_mask=c["mask"].cuda(), labels=c["labels"].cuda())
     loss2.backward()
