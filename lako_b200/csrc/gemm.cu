@@ -613,11 +613,22 @@ int gemm_bf16(const void* A, const void* B, void* C, int M, int N, int K, int ld
   if (epi != EPI_F32_ATOMIC) {
     splitk = 1;
   } else if (splitk <= 0) {
+    // wgrad: few output tiles, very deep K.  Pick the split count whose work-item count best fills whole
+    // waves of CTAs (or CTA pairs), preferring fewer splits (less atomic traffic) among near-equal fills.
     const int tiles = p.tiles_m * p.tiles_n;
     const int slots = use_pair ? sms / 2 : sms;
-    splitk = (tiles >= slots) ? 1 : (2 * slots + tiles - 1) / tiles;  // ~2 waves
-    const int max_split = max(1, p.kb_total / 4);                 // keep >= 4 k-blocks per split
-    splitk = min(splitk, max_split);
+    const int max_split = max(1, min(p.kb_total / 8, 64));  // keep >= 8 k-blocks per split
+    float best = -1.f;
+    splitk = 1;
+    for (int sk = 1; sk <= max_split; ++sk) {
+      const long items = static_cast<long>(tiles) * sk;
+      const long waves = (items + slots - 1) / slots;
+      const float fill = static_cast<float>(items) / static_cast<float>(waves * slots);
+      if (fill > best + 0.03f) {
+        best = fill;
+        splitk = sk;
+      }
+    }
   }
   splitk = max(1, min(splitk, p.kb_total));
   p.kb_per_split = (p.kb_total + splitk - 1) / splitk;

@@ -1,0 +1,121 @@
+"""CPU-side checks (no GPU): the C-ABI library loads and exports every symbol include/lako_b200.h declares,
+the flat layout / workspace sizing are consistent, host logic (bucket tables, state-dict names, score
+post-processing, LR schedule) matches the oracle, and the product refuses to run without a B200."""
+import ctypes
+import os
+import re
+import types
+
+import pytest
+import torch
+
+from oracle import fidt5_oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    from lako_b200 import _native as nat
+    lib = nat.lib()
+    hdr = open(os.path.join(ROOT, "include", "lako_b200.h")).read()
+    names = set(re.findall(r"\b(lako_[a-z0-9_]+)\s*\(", hdr))
+    assert len(names) >= 30
+    for n in sorted(names):
+        assert hasattr(lib, n), f"{n} declared in include/lako_b200.h but not exported"
+
+
+def test_layout_matches_parameter_count():
+    from lako_b200.model import FiDT5, FiDT5Config
+    m = FiDT5(FiDT5Config(vocab_size=512, d_model=128, d_ff=256, num_layers=2, num_heads=2))
+    n_params = sum(p.numel() for p in m.parameters())
+    ref = sum(v.numel() for v in O.unique_params(O.init_state_dict(O.T5_TINY)).values())
+    assert n_params == ref
+    assert m._total >= n_params
+    # every spec is inside the flat buffer and disjoint
+    spans = sorted((off, off + int(torch.tensor(shape).prod())) for off, shape in m._specs.values())
+    for (a0, a1), (b0, b1) in zip(spans, spans[1:]):
+        assert a1 <= b0
+    assert spans[-1][1] <= m._total
+    # fused q|k|v and fused cross k|v of all layers are contiguous slabs
+    lo = m._layout
+    inner, d = 128, 128
+    assert m._specs["decoder.block.1.layer.1.EncDecAttention.k.weight"][0] == lo.dec_xkv + 2 * inner * d
+    assert m._specs["encoder.encoder.block.0.module.layer.0.SelfAttention.v.weight"][0] == lo.enc_qkv[0] + 2 * inner * d
+
+
+def test_t5_sizes_parameter_counts():
+    from lako_b200 import _native as nat
+    from lako_b200.model import _Dims, _Layout
+    lib = nat.lib()
+    for dims, expect in (((768, 12, 3072, 12, 32128, 32), 222903552), ((1024, 16, 4096, 24, 32128, 32), 737668096)):
+        dm = _Dims(*dims, 1e-6)
+        lo = _Layout()
+        assert lib.lako_fidt5_layout(ctypes.byref(dm), ctypes.byref(lo)) == 0
+        assert lo.total == expect  # unique parameter counts of t5-base / t5-large
+        lib.lako_fidt5_workspace_bytes.restype = ctypes.c_size_t
+        ws_train = lib.lako_fidt5_workspace_bytes(ctypes.byref(dm), 8, 10, 200, 10, 1)
+        ws_eval = lib.lako_fidt5_workspace_bytes(ctypes.byref(dm), 8, 10, 200, 10, 0)
+        assert ws_eval < ws_train < 170 * 2 ** 30
+
+
+def test_state_dict_names_match_reference():
+    from lako_b200.model import FiDT5, FiDT5Config
+    m = FiDT5(FiDT5Config(vocab_size=512, d_model=128, d_ff=256, num_layers=2, num_heads=2))
+    assert set(m.state_dict().keys()) == set(O.init_state_dict(O.T5_TINY).keys())
+    sd = m.state_dict()
+    assert sd["lm_head.weight"].data_ptr() == sd["shared.weight"].data_ptr()
+    # 3.0.2-era extra key is accepted and ignored (deviation D1)
+    extra = dict(O.init_state_dict(O.T5_TINY))
+    extra["decoder.block.0.layer.1.EncDecAttention.relative_attention_bias.weight"] = torch.zeros(32, 2)
+    m.load_state_dict(extra)
+    with pytest.raises(RuntimeError):
+        m.load_state_dict({"bogus": torch.zeros(1)})
+
+
+def test_bucket_tables_match_oracle():
+    from lako_b200.model import BUCKET_CENTER, bucket_table
+    for bidir in (True, False):
+        mine = bucket_table(bidir, 32, 128)
+        ref = torch.from_numpy(O.bucket_table(bidir, BUCKET_CENTER + 1))
+        assert torch.equal(mine, ref)
+
+
+def test_no_cpu_fallback():
+    from lako_b200 import _native as nat
+    from lako_b200.model import FiDT5, FiDT5Config
+    m = FiDT5(FiDT5Config(vocab_size=512, d_model=128, d_ff=256, num_layers=2, num_heads=2))
+    ids, mask, labels = O.synth_batch(1, 2, 16, 4, 512)
+    with pytest.raises(nat.LakoError):
+        m(input_ids=ids, attention_mask=mask, labels=labels)
+    with pytest.raises(nat.LakoError):
+        m.generate(ids, mask, max_length=4)
+    if not torch.cuda.is_available():
+        assert nat.lib().lako_check_device() != 0
+
+
+def test_crossattention_score_postprocessing_matches_oracle():
+    """get_crossattention_scores host logic (src/model.py:143-204) on synthetic token scores."""
+    from lako_b200.model import FiDT5, FiDT5Config
+    m = FiDT5(FiDT5Config(vocab_size=512, d_model=128, d_ff=256, num_layers=2, num_heads=2))
+    B, N, L = 3, 2, 48
+    ids, mask, _ = O.synth_batch(B, N, L, 4, 512, seed=5, fact_format=True)
+    g = torch.Generator().manual_seed(0)
+    first = torch.randn(B, N * L, generator=g) * mask.reshape(B, -1)
+    last = torch.randn(B, N * L, generator=g) * mask.reshape(B, -1)
+    m._tok_first, m._tok_last = first, last
+    for style in ("mean", "max", "21mean"):
+        for lh in ("yes", "no"):
+            opt = types.SimpleNamespace(stream=2, n_context=5, attention_score_style=style,
+                                        use_last_half_layer_attention=lh)
+            got = m.get_crossattention_scores(opt, ids, None, mask)
+            tok = (last if lh == "yes" else first + last).view(B, N, L)
+            div = (1 if lh == "yes" else 2) * 2
+            ref = O.fact_scores_from_token_scores(tok, ids, 5, style, div)
+            assert got.dtype == torch.float64 and torch.allclose(got, ref)
+
+
+def test_schedule_matches_oracle():
+    from lako_b200.optim import WarmupLinearSchedule
+    s = WarmupLinearSchedule(6, 100)
+    for step in (0, 1, 5, 6, 7, 50, 99, 100, 150):
+        assert abs(s(step) - O.warmup_linear_lambda(step, 6, 100)) < 1e-12
