@@ -170,7 +170,9 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        import datetime
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank),
+                                timeout=datetime.timedelta(seconds=180))
     dev = torch.device("cuda", local_rank)
     warmup = max(3, args.warmup)
     steps = max(1, args.steps)
@@ -257,15 +259,17 @@ def main():
     # ---- per-kernel timing (CUDA events on the launching stream, same process, right after the timed region)
     roofline = None
     kernel_share = None
+    nprof = 2
     if rank == 0:
         lib.lako_prof_enable(1)
-        nprof = 2
-        pe0, pe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        torch.cuda.synchronize()
-        pe0.record()
-        for i in range(nprof):
-            train_step(model, opt, *resident[i % n_batches])
-        pe1.record()
+    pe0, pe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    pe0.record()
+    for i in range(nprof):  # every rank steps (the step contains collectives); only rank 0 records events
+        train_step(model, opt, *resident[i % n_batches])
+    pe1.record()
+    torch.cuda.synchronize()
+    if rank == 0:
         ncat = 6
         msa = (ctypes.c_double * ncat)()
         wka = (ctypes.c_double * ncat)()

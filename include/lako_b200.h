@@ -121,6 +121,11 @@ typedef struct {
   float* logits; /* out: [B*T][vocab] fp32 */
   float* stats;  /* out: stats[0] = sum of token losses, stats[1] = number of non-ignored targets */
   int count_is_set; /* 1: stats[1] already holds the (global, all-reduced) count and stats[0] is zeroed */
+  /* training dropout (HF dropout_rate, 0.1 in the reference; 0 disables).  Masks come from Philox4x32-10 keyed by
+   * (seed, step, call site, element) and are regenerated in backward -- pass the same values to both calls. */
+  float dropout_p;
+  unsigned int dropout_step;
+  unsigned long long dropout_seed;
 } lako_batch;
 
 int lako_fidt5_layout(const lako_dims* dims, lako_layout* out);

@@ -300,6 +300,51 @@ __device__ __forceinline__ float warp_max(float v) {
   return v;
 }
 
+// ------------------------------------------------------------------ dropout (Philox4x32-10, counter based)
+// One Philox call decides 8 consecutive elements: element e of a site belongs to group e >> 3 and uses the
+// (e & 7)-th 16-bit lane of the 128 random bits; keep iff lane >= thresh (thresh = round(p * 65536)).
+// The same (seed, step, site, group) is recomputed in backward, so no mask is ever stored.
+struct DropSpec {
+  unsigned long long seed;
+  unsigned int step;
+  unsigned int site;    // unique per (layer, dropout call site)
+  unsigned int thresh;  // 0 = dropout disabled
+  float scale;          // 1 / (1 - p)
+};
+__host__ __device__ inline DropSpec make_drop(unsigned long long seed, unsigned step, unsigned site, float p) {
+  DropSpec d;
+  d.seed = seed;
+  d.step = step;
+  d.site = site;
+  d.thresh = (p > 0.f) ? static_cast<unsigned>(p * 65536.f + 0.5f) : 0u;
+  d.scale = (p > 0.f) ? 1.f / (1.f - static_cast<float>(d.thresh) / 65536.f) : 1.f;
+  return d;
+}
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+    c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+    k.x += 0x9E3779B9u;
+    k.y += 0xBB67AE85u;
+  }
+  return c;
+}
+// 8-bit keep mask (bit j = keep element group*8 + j)
+__device__ __forceinline__ uint32_t drop_keep8(const DropSpec& d, unsigned long long group) {
+  const uint4 r = philox4x32_10(make_uint4(static_cast<uint32_t>(group), static_cast<uint32_t>(group >> 32), d.site, d.step),
+                                make_uint2(static_cast<uint32_t>(d.seed), static_cast<uint32_t>(d.seed >> 32)));
+  const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+  uint32_t m = 0;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    m |= ((w[j] & 0xffffu) >= d.thresh ? 1u : 0u) << (2 * j);
+    m |= ((w[j] >> 16) >= d.thresh ? 1u : 0u) << (2 * j + 1);
+  }
+  return m;
+}
+
 #endif  // __CUDACC__
 
 // ------------------------------------------------------------------ host: TMA descriptor cache (tma_host.cu)

@@ -151,7 +151,7 @@ size_t xattn_workspace_bytes(int B, int H, int T, int M) {
 
 int xattn_fwd(const __nv_bfloat16* q, const __nv_bfloat16* kv, const unsigned char* mask, __nv_bfloat16* out, float* lse,
               float* tok_score, float* workspace, int B, int T, int M, int H, int ldq, int ldkv, int koff, int voff,
-              int ldo, cudaStream_t s) {
+              int ldo, cudaStream_t s, DropSpec drop) {
   LAKO_REQUIRE(B > 0 && T > 0 && T <= XA_TMAX && M > 0 && H > 0, LAKO_ERR_UNSUPPORTED);
   LAKO_REQUIRE(ldkv % 8 == 0 && koff % 8 == 0 && voff % 8 == 0, LAKO_ERR_BAD_ARG);
   XAttnParams p;
@@ -178,7 +178,7 @@ int xattn_fwd(const __nv_bfloat16* q, const __nv_bfloat16* kv, const unsigned ch
   ProfScope prof(PROF_XATTN, 4.0 * B * H * static_cast<double>(T) * M * 64, s);
   (void)dyn;
   {
-    int rc = xattn_fwd_mma(q, kv, mask, tok_score, workspace, B, T, M, H, ldq, ldkv, koff, voff, s);
+    int rc = xattn_fwd_mma(q, kv, mask, tok_score, workspace, B, T, M, H, ldq, ldkv, koff, voff, s, drop);
     if (rc) return rc;
   }
   dim3 g2(T, H, B);
@@ -310,7 +310,7 @@ __global__ void __launch_bounds__(256) xattn_bwd_kernel(const XAttnBwdParams p) 
 
 int xattn_bwd(const __nv_bfloat16* q, const __nv_bfloat16* kv, const unsigned char* mask, const __nv_bfloat16* out,
               const __nv_bfloat16* dout, const float* lse, __nv_bfloat16* dkv, float* dq_f32, int B, int T, int M,
-              int H, int ldq, int ldkv, int koff, int voff, int ldo, cudaStream_t s) {
+              int H, int ldq, int ldkv, int koff, int voff, int ldo, cudaStream_t s, DropSpec drop) {
   LAKO_REQUIRE(B > 0 && T > 0 && T <= XA_TMAX && M > 0 && H > 0, LAKO_ERR_UNSUPPORTED);
   XAttnBwdParams p;
   p.q = q; p.kv = kv; p.mask = mask; p.out = out; p.dout = dout; p.lse = lse; p.dkv = dkv; p.dq = dq_f32;
@@ -325,7 +325,7 @@ int xattn_bwd(const __nv_bfloat16* q, const __nv_bfloat16* kv, const unsigned ch
   ProfScope prof(PROF_XATTN, 8.0 * B * H * static_cast<double>(T) * M * 64, s);
   (void)dyn;
   (void)p;
-  return xattn_bwd_mma(q, kv, mask, out, dout, lse, dkv, dq_f32, B, T, M, H, ldq, ldkv, koff, voff, ldo, s);
+  return xattn_bwd_mma(q, kv, mask, out, dout, lse, dkv, dq_f32, B, T, M, H, ldq, ldkv, koff, voff, ldo, s, drop);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -336,8 +336,9 @@ struct DSelfParams {
   const __nv_bfloat16* qkv;
   const float* lut;
   __nv_bfloat16* out;       // [B*T][inner]
-  float* probs;             // [B][H][T][T] fp32 saved for backward
+  float* probs;             // [B][H][T][T] fp32 saved for backward (un-dropped)
   int T, H, inner;
+  DropSpec drop;            // group = ((b*H+h)*T + t)*8 + j/8
 };
 
 __global__ void __launch_bounds__(128) dself_fwd_kernel(const DSelfParams p) {
@@ -383,8 +384,13 @@ __global__ void __launch_bounds__(128) dself_fwd_kernel(const DSelfParams p) {
     for (int i = 0; i < 2; ++i) {
       const int j = lane + i * 32;
       if (j < T) {
-        sP[warp][j] = e[i] * inv;
-        if (p.probs) p.probs[((static_cast<size_t>(b) * p.H + h) * T + t) * T + j] = e[i] * inv;
+        float pv = e[i] * inv;
+        if (p.probs) p.probs[((static_cast<size_t>(b) * p.H + h) * T + t) * T + j] = pv;
+        if (p.drop.thresh) {
+          const uint32_t k = drop_keep8(p.drop, (static_cast<unsigned long long>(b * p.H + h) * T + t) * 8 + (j >> 3));
+          pv = ((k >> (j & 7)) & 1u) ? pv * p.drop.scale : 0.f;
+        }
+        sP[warp][j] = pv;
       }
     }
     __syncwarp();
@@ -400,9 +406,9 @@ __global__ void __launch_bounds__(128) dself_fwd_kernel(const DSelfParams p) {
 }
 
 int dself_fwd(const __nv_bfloat16* qkv, const float* lut, __nv_bfloat16* out, float* probs, int B, int T, int H,
-              cudaStream_t s) {
+              cudaStream_t s, DropSpec drop) {
   LAKO_REQUIRE(T > 0 && T <= XA_TMAX, LAKO_ERR_UNSUPPORTED);
-  DSelfParams p{qkv, lut, out, probs, T, H, H * 64};
+  DSelfParams p{qkv, lut, out, probs, T, H, H * 64, drop};
   constexpr int smem = (3 * XA_TMAX * 65 + 4 * XA_TMAX) * (int)sizeof(float);
   static bool configured = false;
   if (!configured) {
@@ -421,6 +427,7 @@ struct DSelfBwdParams {
   __nv_bfloat16* dqkv;        // [B*T][3*inner]
   float* dlut;                // [H][2T-1] += dS by offset
   int T, H, inner;
+  DropSpec drop;
 };
 
 __global__ void __launch_bounds__(128) dself_bwd_kernel(const DSelfBwdParams p) {
@@ -431,6 +438,7 @@ __global__ void __launch_bounds__(128) dself_bwd_kernel(const DSelfBwdParams p) 
   float (*sDO)[65] = reinterpret_cast<float (*)[65]>(dyn + 3 * XA_TMAX * 65);
   float (*sP)[XA_TMAX + 1] = reinterpret_cast<float (*)[XA_TMAX + 1]>(dyn + 4 * XA_TMAX * 65);
   float (*sDS)[XA_TMAX + 1] = reinterpret_cast<float (*)[XA_TMAX + 1]>(dyn + 5 * XA_TMAX * 65);
+  float (*sPD)[XA_TMAX + 1] = reinterpret_cast<float (*)[XA_TMAX + 1]>(dyn + 6 * XA_TMAX * 65);  // dropped P
   const int h = blockIdx.x, b = blockIdx.y, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int T = p.T;
   for (int i = tid; i < T * 64; i += 128) {
@@ -454,6 +462,14 @@ __global__ void __launch_bounds__(128) dself_bwd_kernel(const DSelfBwdParams p) 
       if (j < T && j <= t) {
         float acc = 0.f;
         for (int d = 0; d < 64; ++d) acc += sDO[t][d] * sV[j][d];
+        float pd = sP[t][j];
+        if (p.drop.thresh) {
+          const uint32_t k = drop_keep8(p.drop, (static_cast<unsigned long long>(b * p.H + h) * T + t) * 8 + (j >> 3));
+          const bool keep = (k >> (j & 7)) & 1u;
+          acc = keep ? acc * p.drop.scale : 0.f;
+          pd = keep ? pd * p.drop.scale : 0.f;
+        }
+        sPD[t][j] = pd;
         dp[i] = acc;
         dsum += sP[t][j] * acc;
       }
@@ -477,7 +493,7 @@ __global__ void __launch_bounds__(128) dself_bwd_kernel(const DSelfBwdParams p) 
     for (int j = 0; j <= t; ++j) dq += sDS[t][j] * sK[j][d];
     for (int tt = t; tt < T; ++tt) {
       dk += sDS[tt][t] * sQ[tt][d];
-      dv += sP[tt][t] * sDO[tt][d];
+      dv += sPD[tt][t] * sDO[tt][d];
     }
     __nv_bfloat16* row = p.dqkv + (static_cast<size_t>(b) * T + t) * 3 * p.inner + h * 64 + d;
     row[0] = __float2bfloat16(dq);
@@ -487,10 +503,10 @@ __global__ void __launch_bounds__(128) dself_bwd_kernel(const DSelfBwdParams p) 
 }
 
 int dself_bwd(const __nv_bfloat16* qkv, const __nv_bfloat16* dout, const float* probs, __nv_bfloat16* dqkv, float* dlut,
-              int B, int T, int H, cudaStream_t s) {
+              int B, int T, int H, cudaStream_t s, DropSpec drop) {
   LAKO_REQUIRE(T > 0 && T <= XA_TMAX, LAKO_ERR_UNSUPPORTED);
-  DSelfBwdParams p{qkv, dout, probs, dqkv, dlut, T, H, H * 64};
-  constexpr int smem = 6 * XA_TMAX * 65 * (int)sizeof(float);
+  DSelfBwdParams p{qkv, dout, probs, dqkv, dlut, T, H, H * 64, drop};
+  constexpr int smem = 7 * XA_TMAX * 65 * (int)sizeof(float);
   static bool configured = false;
   if (!configured) {
     cudaFuncSetAttribute(dself_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);

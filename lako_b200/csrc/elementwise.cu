@@ -24,11 +24,17 @@ namespace lako {
 // --------------------------------------------------------------------------------------------
 constexpr int NORM_MAX_VEC = 8;  // float4 per lane -> d <= 1024
 
+// 4 keep bits for the float4 at element offset e (multiple of 4) of a dropout site
+__device__ __forceinline__ uint32_t keep4(const DropSpec& ds, size_t e) {
+  const uint32_t m = drop_keep8(ds, e >> 3);
+  return (e & 4) ? (m >> 4) : (m & 15u);
+}
+
 __global__ void __launch_bounds__(256) rmsnorm_fwd_kernel(const float* x, const __nv_bfloat16* __restrict__ delta,
                                                            float* x_out, const float* __restrict__ w,
                                                            __nv_bfloat16* __restrict__ out,
                                                            float* __restrict__ rstd_out, int rows, int d, float eps,
-                                                           float out_scale) {
+                                                           float out_scale, const DropSpec dd, const DropSpec od) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= rows) return;
@@ -44,11 +50,19 @@ __global__ void __launch_bounds__(256) rmsnorm_fwd_kernel(const float* x, const 
       const int c = (i * 32 + lane) * 4;
       float4 v = *reinterpret_cast<const float4*>(xr + c);
       if (dr) {
-        uint2 dd = *reinterpret_cast<const uint2*>(dr + c);
-        v.x += bf16_lo(dd.x);
-        v.y += bf16_hi(dd.x);
-        v.z += bf16_lo(dd.y);
-        v.w += bf16_hi(dd.y);
+        const uint2 dv = *reinterpret_cast<const uint2*>(dr + c);
+        float4 a = make_float4(bf16_lo(dv.x), bf16_hi(dv.x), bf16_lo(dv.y), bf16_hi(dv.y));
+        if (dd.thresh) {  // dropout on the sub-layer output before the residual add (HF:375, :149)
+          const uint32_t k = keep4(dd, static_cast<size_t>(warp) * d + c);
+          a.x = (k & 1) ? a.x * dd.scale : 0.f;
+          a.y = (k & 2) ? a.y * dd.scale : 0.f;
+          a.z = (k & 4) ? a.z * dd.scale : 0.f;
+          a.w = (k & 8) ? a.w * dd.scale : 0.f;
+        }
+        v.x += a.x;
+        v.y += a.y;
+        v.z += a.z;
+        v.w += a.w;
       }
       if (xo && (dr || xo != xr)) *reinterpret_cast<float4*>(xo + c) = v;
       xv[i] = v;
@@ -66,9 +80,17 @@ __global__ void __launch_bounds__(256) rmsnorm_fwd_kernel(const float* x, const 
       if (i < nvec) {
         const int c = (i * 32 + lane) * 4;
         const float4 wv = *reinterpret_cast<const float4*>(w + c);
+        float4 y = make_float4(wv.x * (xv[i].x * rs), wv.y * (xv[i].y * rs), wv.z * (xv[i].z * rs), wv.w * (xv[i].w * rs));
+        if (od.thresh) {  // dropout after the final layer norm of a stack (HF:767-768)
+          const uint32_t k = keep4(od, static_cast<size_t>(warp) * d + c);
+          y.x = (k & 1) ? y.x * od.scale : 0.f;
+          y.y = (k & 2) ? y.y * od.scale : 0.f;
+          y.z = (k & 4) ? y.z * od.scale : 0.f;
+          y.w = (k & 8) ? y.w * od.scale : 0.f;
+        }
         uint2 o;
-        o.x = pack_bf16x2(wv.x * (xv[i].x * rs), wv.y * (xv[i].y * rs));
-        o.y = pack_bf16x2(wv.z * (xv[i].z * rs), wv.w * (xv[i].w * rs));
+        o.x = pack_bf16x2(y.x, y.y);
+        o.y = pack_bf16x2(y.z, y.w);
         *reinterpret_cast<uint2*>(orow + c) = o;
       }
     }
@@ -76,13 +98,13 @@ __global__ void __launch_bounds__(256) rmsnorm_fwd_kernel(const float* x, const 
 }
 
 int rmsnorm_fwd(const float* x, const __nv_bfloat16* delta, float* x_out, const float* w, __nv_bfloat16* out,
-                float* rstd, int rows, int d, float eps, float out_scale, cudaStream_t s) {
+                float* rstd, int rows, int d, float eps, float out_scale, cudaStream_t s, DropSpec dd, DropSpec od) {
   LAKO_REQUIRE(rows > 0 && d > 0 && d % 128 == 0 && d <= 128 * NORM_MAX_VEC, LAKO_ERR_UNSUPPORTED);
   // algorithmic bytes: read x (4) [+ delta (2) + write x (4)] + write normed (2)
   ProfScope prof(PROF_NORM, static_cast<double>(rows) * d * (delta ? 12.0 : 6.0), s);
   const int warps_per_block = 8;
   const int grid = (rows + warps_per_block - 1) / warps_per_block;
-  rmsnorm_fwd_kernel<<<grid, warps_per_block * 32, 0, s>>>(x, delta, x_out, w, out, rstd, rows, d, eps, out_scale);
+  rmsnorm_fwd_kernel<<<grid, warps_per_block * 32, 0, s>>>(x, delta, x_out, w, out, rstd, rows, d, eps, out_scale, dd, od);
   LAKO_CHECK_LAUNCH();
   return LAKO_OK;
 }
@@ -105,7 +127,7 @@ __global__ void __launch_bounds__(256, 2) rmsnorm_bwd_kernel(const __nv_bfloat16
                                                               const float* __restrict__ w, float* __restrict__ dres,
                                                               __nv_bfloat16* __restrict__ dres_bf16,
                                                               float* __restrict__ dw, int rows, int accumulate,
-                                                              float dy_scale) {
+                                                              float dy_scale, const DropSpec yd, const DropSpec bd) {
   constexpr int d = NV * 128;
   extern __shared__ float4 s_norm[];
   float4* s_w = s_norm;                // [d/4]
@@ -130,6 +152,11 @@ __global__ void __launch_bounds__(256, 2) rmsnorm_bwd_kernel(const __nv_bfloat16
       const int c = (i * 32 + lane) * 4;
       xv[i] = *reinterpret_cast<const float4*>(xr + c);
       dyp[i] = *reinterpret_cast<const uint2*>(dyr + c);
+      if (yd.thresh) {  // gradient of the post-norm dropout: zero the dropped elements (the 1/(1-p) is in dy_scale)
+        const uint32_t k = keep4(yd, static_cast<size_t>(row) * d + c);
+        dyp[i].x &= ((k & 1) ? 0x0000ffffu : 0u) | ((k & 2) ? 0xffff0000u : 0u);
+        dyp[i].y &= ((k & 4) ? 0x0000ffffu : 0u) | ((k & 8) ? 0xffff0000u : 0u);
+      }
     }
     float s = 0.f;
 #pragma unroll
@@ -164,6 +191,13 @@ __global__ void __launch_bounds__(256, 2) rmsnorm_bwd_kernel(const __nv_bfloat16
       }
       *reinterpret_cast<float4*>(drr + c) = o;
       if (dres_bf16) {
+        if (bd.thresh) {  // the bf16 copy feeds the previous sub-layer's output GEMMs: apply ITS dropout mask
+          const uint32_t k = keep4(bd, static_cast<size_t>(row) * d + c);
+          o.x = (k & 1) ? o.x * bd.scale : 0.f;
+          o.y = (k & 2) ? o.y * bd.scale : 0.f;
+          o.z = (k & 4) ? o.z * bd.scale : 0.f;
+          o.w = (k & 8) ? o.w * bd.scale : 0.f;
+        }
         uint2 ob;
         ob.x = pack_bf16x2(o.x, o.y);
         ob.y = pack_bf16x2(o.z, o.w);
@@ -186,7 +220,7 @@ __global__ void __launch_bounds__(256, 2) rmsnorm_bwd_kernel(const __nv_bfloat16
 template <int NV>
 static int launch_rmsnorm_bwd(const __nv_bfloat16* dy, const float* x, const float* rstd, const float* w, float* dres,
                               __nv_bfloat16* dres_bf16, float* dw, int rows, int accumulate, float dy_scale,
-                              cudaStream_t s) {
+                              cudaStream_t s, DropSpec yd, DropSpec bd) {
   constexpr int smem = (NV * 128 * 9) * (int)sizeof(float);
   static bool configured = false;
   if (!configured) {
@@ -195,26 +229,26 @@ static int launch_rmsnorm_bwd(const __nv_bfloat16* dy, const float* x, const flo
   }
   int grid = (rows + 7) / 8;
   grid = min(grid, device_sm_count() * 2);
-  rmsnorm_bwd_kernel<NV><<<grid, 256, smem, s>>>(dy, x, rstd, w, dres, dres_bf16, dw, rows, accumulate, dy_scale);
+  rmsnorm_bwd_kernel<NV><<<grid, 256, smem, s>>>(dy, x, rstd, w, dres, dres_bf16, dw, rows, accumulate, dy_scale, yd, bd);
   LAKO_CHECK_LAUNCH();
   return LAKO_OK;
 }
 
 int rmsnorm_bwd(const __nv_bfloat16* dy, const float* x, const float* rstd, const float* w, float* dres,
                 __nv_bfloat16* dres_bf16, float* dw, int rows, int d, int accumulate, float dy_scale,
-                cudaStream_t s) {
+                cudaStream_t s, DropSpec yd, DropSpec bd) {
   LAKO_REQUIRE(rows > 0 && d > 0 && d % 128 == 0 && d <= 128 * NORM_MAX_VEC, LAKO_ERR_UNSUPPORTED);
   // algorithmic bytes: read dy (2) + x (4) + dres (4 if accumulating); write dres (4) + bf16 copy (2)
   ProfScope prof(PROF_NORM, static_cast<double>(rows) * d * (accumulate ? 16.0 : 12.0), s);
   switch (d / 128) {
-    case 1: return launch_rmsnorm_bwd<1>(dy, x, rstd, w, dres, dres_bf16, dw, rows, accumulate, dy_scale, s);
-    case 2: return launch_rmsnorm_bwd<2>(dy, x, rstd, w, dres, dres_bf16, dw, rows, accumulate, dy_scale, s);
-    case 3: return launch_rmsnorm_bwd<3>(dy, x, rstd, w, dres, dres_bf16, dw, rows, accumulate, dy_scale, s);
-    case 4: return launch_rmsnorm_bwd<4>(dy, x, rstd, w, dres, dres_bf16, dw, rows, accumulate, dy_scale, s);
-    case 5: return launch_rmsnorm_bwd<5>(dy, x, rstd, w, dres, dres_bf16, dw, rows, accumulate, dy_scale, s);
-    case 6: return launch_rmsnorm_bwd<6>(dy, x, rstd, w, dres, dres_bf16, dw, rows, accumulate, dy_scale, s);
-    case 7: return launch_rmsnorm_bwd<7>(dy, x, rstd, w, dres, dres_bf16, dw, rows, accumulate, dy_scale, s);
-    default: return launch_rmsnorm_bwd<8>(dy, x, rstd, w, dres, dres_bf16, dw, rows, accumulate, dy_scale, s);
+    case 1: return launch_rmsnorm_bwd<1>(dy, x, rstd, w, dres, dres_bf16, dw, rows, accumulate, dy_scale, s, yd, bd);
+    case 2: return launch_rmsnorm_bwd<2>(dy, x, rstd, w, dres, dres_bf16, dw, rows, accumulate, dy_scale, s, yd, bd);
+    case 3: return launch_rmsnorm_bwd<3>(dy, x, rstd, w, dres, dres_bf16, dw, rows, accumulate, dy_scale, s, yd, bd);
+    case 4: return launch_rmsnorm_bwd<4>(dy, x, rstd, w, dres, dres_bf16, dw, rows, accumulate, dy_scale, s, yd, bd);
+    case 5: return launch_rmsnorm_bwd<5>(dy, x, rstd, w, dres, dres_bf16, dw, rows, accumulate, dy_scale, s, yd, bd);
+    case 6: return launch_rmsnorm_bwd<6>(dy, x, rstd, w, dres, dres_bf16, dw, rows, accumulate, dy_scale, s, yd, bd);
+    case 7: return launch_rmsnorm_bwd<7>(dy, x, rstd, w, dres, dres_bf16, dw, rows, accumulate, dy_scale, s, yd, bd);
+    default: return launch_rmsnorm_bwd<8>(dy, x, rstd, w, dres, dres_bf16, dw, rows, accumulate, dy_scale, s, yd, bd);
   }
 }
 
@@ -222,7 +256,7 @@ int rmsnorm_bwd(const __nv_bfloat16* dy, const float* x, const float* rstd, cons
 // embedding gather (fp32 table -> fp32 residual stream) and its scatter-add backward
 // --------------------------------------------------------------------------------------------
 __global__ void embed_gather_kernel(const long long* __restrict__ ids, const float* __restrict__ table,
-                                    float* __restrict__ out, int rows, int d, int vocab) {
+                                    float* __restrict__ out, int rows, int d, int vocab, const DropSpec ds) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= rows) return;
@@ -230,18 +264,29 @@ __global__ void embed_gather_kernel(const long long* __restrict__ ids, const flo
   if (id < 0 || id >= vocab) id = 0;
   const float4* src = reinterpret_cast<const float4*>(table + static_cast<size_t>(id) * d);
   float4* dst = reinterpret_cast<float4*>(out + static_cast<size_t>(warp) * d);
-  for (int c = lane; c < (d >> 2); c += 32) dst[c] = __ldg(src + c);
+  for (int c = lane; c < (d >> 2); c += 32) {
+    float4 v = __ldg(src + c);
+    if (ds.thresh) {  // dropout on the embedded inputs (HF:734)
+      const uint32_t k = keep4(ds, static_cast<size_t>(warp) * d + c * 4);
+      v.x = (k & 1) ? v.x * ds.scale : 0.f;
+      v.y = (k & 2) ? v.y * ds.scale : 0.f;
+      v.z = (k & 4) ? v.z * ds.scale : 0.f;
+      v.w = (k & 8) ? v.w * ds.scale : 0.f;
+    }
+    dst[c] = v;
+  }
 }
 
-int embed_gather(const long long* ids, const float* table, float* out, int rows, int d, int vocab, cudaStream_t s) {
-  LAKO_REQUIRE(rows > 0 && d % 4 == 0, LAKO_ERR_BAD_ARG);
-  embed_gather_kernel<<<(rows + 7) / 8, 256, 0, s>>>(ids, table, out, rows, d, vocab);
+int embed_gather(const long long* ids, const float* table, float* out, int rows, int d, int vocab, cudaStream_t s,
+                 DropSpec ds) {
+  LAKO_REQUIRE(rows > 0 && d % 8 == 0, LAKO_ERR_BAD_ARG);
+  embed_gather_kernel<<<(rows + 7) / 8, 256, 0, s>>>(ids, table, out, rows, d, vocab, ds);
   LAKO_CHECK_LAUNCH();
   return LAKO_OK;
 }
 
 __global__ void embed_scatter_add_kernel(const long long* __restrict__ ids, const float* __restrict__ dres,
-                                         float* __restrict__ dtable, int rows, int d, int vocab) {
+                                         float* __restrict__ dtable, int rows, int d, int vocab, const DropSpec ds) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= rows) return;
@@ -250,7 +295,14 @@ __global__ void embed_scatter_add_kernel(const long long* __restrict__ ids, cons
   const float4* src = reinterpret_cast<const float4*>(dres + static_cast<size_t>(warp) * d);
   float* dst = dtable + static_cast<size_t>(id) * d;
   for (int c = lane; c < (d >> 2); c += 32) {
-    const float4 v = src[c];
+    float4 v = src[c];
+    if (ds.thresh) {
+      const uint32_t k = keep4(ds, static_cast<size_t>(warp) * d + c * 4);
+      v.x = (k & 1) ? v.x * ds.scale : 0.f;
+      v.y = (k & 2) ? v.y * ds.scale : 0.f;
+      v.z = (k & 4) ? v.z * ds.scale : 0.f;
+      v.w = (k & 8) ? v.w * ds.scale : 0.f;
+    }
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + c * 4), "f"(v.x), "f"(v.y), "f"(v.z),
                  "f"(v.w)
                  : "memory");
@@ -258,9 +310,9 @@ __global__ void embed_scatter_add_kernel(const long long* __restrict__ ids, cons
 }
 
 int embed_scatter_add(const long long* ids, const float* dres, float* dtable, int rows, int d, int vocab,
-                      cudaStream_t s) {
-  LAKO_REQUIRE(rows > 0 && d % 4 == 0, LAKO_ERR_BAD_ARG);
-  embed_scatter_add_kernel<<<(rows + 7) / 8, 256, 0, s>>>(ids, dres, dtable, rows, d, vocab);
+                      cudaStream_t s, DropSpec ds) {
+  LAKO_REQUIRE(rows > 0 && d % 8 == 0, LAKO_ERR_BAD_ARG);
+  embed_scatter_add_kernel<<<(rows + 7) / 8, 256, 0, s>>>(ids, dres, dtable, rows, d, vocab, ds);
   LAKO_CHECK_LAUNCH();
   return LAKO_OK;
 }

@@ -44,6 +44,7 @@ struct EncAttnParams {
   __nv_bfloat16* out;         // [P*L][inner]
   float* lse;                 // [P][H][L]
   int L, H, inner, LK;        // LK = L rounded up to 16
+  DropSpec drop;              // dropout on the attention probabilities (HF:332); group = ((psg*H+h)*L+q)*32 + key/8
 };
 
 constexpr float LOG2E_F = 1.4426950408889634f;
@@ -187,6 +188,11 @@ enc_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const EncAttnPar
         e[i] = fast_exp2((__uint_as_float(v[u * 8 + i]) - m) * LOG2E_F);
         lsum += e[i];
       }
+      if (p.drop.thresh) {  // the row sum normalises the UNdropped probabilities; only the P V operand is masked
+        const uint32_t k = drop_keep8(p.drop, (static_cast<unsigned long long>(psg * p.H + h) * L + qc) * 32 + c * 4 + u);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) e[i] = ((k >> i) & 1u) ? e[i] * p.drop.scale : 0.f;
+      }
       const int unit = (c & 1) * 4 + u;  // 16-byte unit index within the 128-byte row
       uint4 o;
       o.x = pack_bf16x2(e[0], e[1]);
@@ -246,7 +252,7 @@ enc_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const EncAttnPar
 
 // qkv bf16 [P*L][3*inner]; out bf16 [P*L][inner]; lse fp32 [P][H][L] (may be null)
 int enc_attn_fwd(const __nv_bfloat16* qkv, const unsigned char* mask, const float* bias_lut, __nv_bfloat16* out,
-                 float* lse, int P, int L, int H, cudaStream_t s) {
+                 float* lse, int P, int L, int H, cudaStream_t s, DropSpec drop) {
   int rc = check_arch();
   if (rc) return rc;
   LAKO_REQUIRE(P > 0 && H > 0 && L > 0, LAKO_ERR_BAD_ARG);
@@ -273,6 +279,7 @@ int enc_attn_fwd(const __nv_bfloat16* qkv, const unsigned char* mask, const floa
   p.H = H;
   p.inner = inner;
   p.LK = (L + 15) / 16 * 16;
+  p.drop = drop;
   ProfScope prof(PROF_ENC_ATTN_FWD, 4.0 * P * H * static_cast<double>(L) * L * 64, s);
   dim3 grid((L + 127) / 128, H, P);
   enc_attn_fwd_kernel<<<grid, 256, EA_SMEM_BYTES, s>>>(tm, p);
@@ -296,6 +303,7 @@ struct EncAttnBwdParams {
   __nv_bfloat16* dqkv;           // [P*L][3*inner]
   float* dlut;                   // [H][2L-1]  += sum over (q,k) diagonals of dS (bias gradient, pre-bucket)
   int L, H, inner;
+  DropSpec drop;
 };
 
 constexpr int EB_Q_OFF = 0, EB_DO_OFF = 32768, EB_K_OFF = 65536, EB_V_OFF = 98304, EB_P_OFF = 131072,
@@ -432,11 +440,19 @@ enc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
           const float lbv[8] = {lb0.x, lb0.y, lb0.z, lb0.w, lb1.x, lb1.y, lb1.z, lb1.w};
           const float kmv[8] = {km0.x, km0.y, km0.z, km0.w, km1.x, km1.y, km1.z, km1.w};
           float pr[8];
+          uint32_t keepm = 0xffu;
+          float dscale = 1.f;
+          if (p.drop.thresh) {
+            keepm = drop_keep8(p.drop, (static_cast<unsigned long long>(psg * p.H + h) * L + qc) * 32 + (kbase >> 3) + u);
+            dscale = p.drop.scale;
+          }
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const float sc = (__uint_as_float(sv[u * 8 + i]) + lbv[i]) + kmv[i];
             pr[i] = fast_exp2((sc - lse_q) * LOG2E_F);
-            ds[u * 8 + i] = pr[i] * (__uint_as_float(dpv[u * 8 + i]) - D_q);
+            const float dp = ((keepm >> i) & 1u) ? __uint_as_float(dpv[u * 8 + i]) * dscale : 0.f;
+            ds[u * 8 + i] = pr[i] * (dp - D_q);
+            pr[i] = ((keepm >> i) & 1u) ? pr[i] * dscale : 0.f;  // the dV = P_drop^T dO operand
           }
           const int unit = ((c * 4 + u) ^ (r & 7)) << 4;
           uint4 o;
@@ -569,7 +585,7 @@ enc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
 
 int enc_attn_bwd(const __nv_bfloat16* qkv, const __nv_bfloat16* out, const __nv_bfloat16* dout, const float* lse,
                  const unsigned char* mask, const float* bias_lut, __nv_bfloat16* dqkv, float* dlut, int P, int L,
-                 int H, cudaStream_t s) {
+                 int H, cudaStream_t s, DropSpec drop) {
   int rc = check_arch();
   if (rc) return rc;
   LAKO_REQUIRE(P > 0 && H > 0 && L > 0, LAKO_ERR_BAD_ARG);
@@ -600,6 +616,7 @@ int enc_attn_bwd(const __nv_bfloat16* qkv, const __nv_bfloat16* out, const __nv_
   p.L = L;
   p.H = H;
   p.inner = inner;
+  p.drop = drop;
   ProfScope prof(PROF_ENC_ATTN_BWD, 10.0 * P * H * static_cast<double>(L) * L * 64, s);
   dim3 grid(H, P);
   enc_attn_bwd_kernel<<<grid, 256, EB_SMEM_BYTES, s>>>(tm_qkv, tm_do, p);

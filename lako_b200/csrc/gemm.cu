@@ -39,6 +39,7 @@ struct GemmParams {
   int ldc, ld_aux;
   int tiles_m, tiles_n, splitk, kb_total, kb_per_split;
   float alpha;
+  DropSpec drop;  // EPI_BF16_RELU only: dropout after the activation (HF:95), element index = row * ldc + col
 };
 
 // Epilogue of one 128-row x BN-column accumulator tile for the warp owning TMEM lane quarter q.
@@ -80,6 +81,14 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t t_ac
         for (int i = 0; i < 8; ++i) {
           v[i] = __uint_as_float(rr[o + i]) * p.alpha;
           if constexpr (EPI == EPI_BF16_RELU) v[i] = fmaxf(v[i], 0.f);
+        }
+        if constexpr (EPI == EPI_BF16_RELU) {
+          if (p.drop.thresh) {
+            const size_t e = static_cast<size_t>(m0 + q * 32 + lane) * p.ldc + col0 + u * 8;
+            const uint32_t k = drop_keep8(p.drop, e >> 3);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = ((k >> i) & 1u) ? v[i] * p.drop.scale : 0.f;
+          }
         }
         uint4 w;
         w.x = pack_bf16x2(v[0], v[1]);
@@ -571,7 +580,8 @@ static int dispatch_major(int a_mn, int b_mn, int epi, const CUtensorMap& tmA, c
 //  B: b_mn==0 -> row-major [N][ldb>=K];   b_mn==1 -> row-major [K][ldb>=N]
 //  splitk<=0 -> chosen automatically (only for EPI_F32_ATOMIC); bn: 0 auto, 128 or 256.
 int gemm_bf16(const void* A, const void* B, void* C, int M, int N, int K, int lda, int ldb, int ldc, int a_mn,
-              int b_mn, int epi, float alpha, const void* aux, int ld_aux, int splitk, int bn, cudaStream_t stream) {
+              int b_mn, int epi, float alpha, const void* aux, int ld_aux, int splitk, int bn, cudaStream_t stream,
+              DropSpec drop) {
   int rc = check_arch();
   if (rc) return rc;
   LAKO_REQUIRE(M > 0 && N > 0 && K > 0, LAKO_ERR_BAD_ARG);
@@ -607,6 +617,7 @@ int gemm_bf16(const void* A, const void* B, void* C, int M, int N, int K, int ld
   p.ldc = ldc;
   p.ld_aux = ld_aux;
   p.alpha = alpha;
+  p.drop = drop;
   p.tiles_m = use_pair ? (M + 255) / 256 : (M + BM - 1) / BM;
   p.tiles_n = (N + bn - 1) / bn;
   p.kb_total = (K + BK - 1) / BK;
@@ -657,5 +668,5 @@ extern "C" int lako_gemm_bf16(const void* A, const void* B, void* C, int M, int 
                               int a_mn, int b_mn, int epi, float alpha, const void* aux, int ld_aux, int splitk,
                               int bn, void* stream) {
   return lako::gemm_bf16(A, B, C, M, N, K, lda, ldb, ldc, a_mn, b_mn, epi, alpha, aux, ld_aux, splitk, bn,
-                         static_cast<cudaStream_t>(stream));
+                         static_cast<cudaStream_t>(stream), lako::DropSpec{});
 }

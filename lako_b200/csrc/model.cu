@@ -236,8 +236,9 @@ void carve(const lako_dims& dm, int B, int N, int L, int T, int mode, void* base
   } while (0)
 
 // y[M,N] = x[M,K] W[N,K]^T
-inline int lin_fwd(const bf16* x, const bf16* W, void* y, int M, int N, int K, int epi, float alpha, cudaStream_t s) {
-  return gemm_bf16(x, W, y, M, N, K, K, K, N, 0, 0, epi, alpha, nullptr, 0, 1, 0, s);
+inline int lin_fwd(const bf16* x, const bf16* W, void* y, int M, int N, int K, int epi, float alpha, cudaStream_t s,
+                   DropSpec drop = DropSpec{}) {
+  return gemm_bf16(x, W, y, M, N, K, K, K, N, 0, 0, epi, alpha, nullptr, 0, 1, 0, s, drop);
 }
 // dx[M,K] = dy[M,N] W[N,K]   (optionally masked by aux > 0)
 inline int lin_dgrad(const bf16* dy, const bf16* W, bf16* dx, int M, int N, int K, const bf16* relu_aux, float alpha,
@@ -248,6 +249,19 @@ inline int lin_dgrad(const bf16* dy, const bf16* W, bf16* dx, int M, int N, int 
 inline int lin_wgrad(const bf16* dy, const bf16* x, float* dW, int M, int N, int K, float alpha, cudaStream_t s) {
   return gemm_bf16(dy, x, dW, N, K, M, N, K, K, 1, 1, EPI_F32_ATOMIC, alpha, nullptr, 0, 0, 0, s);
 }
+
+enum DropKind : unsigned {
+  E_EMB = 0, E_ATTN, E_O, E_RELU, E_FF, E_FINAL, D_EMB, D_SELF, D_O, D_XP, D_XO, D_RELU, D_FF, D_FINAL
+};
+struct Dropper {
+  unsigned long long seed;
+  unsigned step;
+  float p;
+  DropSpec operator()(int layer, unsigned kind) const {
+    return p > 0.f ? make_drop(seed, step, static_cast<unsigned>(layer) * 16u + kind, p) : DropSpec{};
+  }
+  DropSpec none() const { return DropSpec{}; }
+};
 
 struct Ptrs {
   const lako_dims* dm;
@@ -278,9 +292,9 @@ int make_ptrs(const lako_fidt5* m, Ptrs& p) {
 
 // ---- encoder: ids (P*L) -> mem bf16 [Mtok][d] and kv_all bf16 [Mtok][nl*2*inner]
 int encode(const Ptrs& p, const lako_fidt5* m, Work& w, const long long* ids, const unsigned char* mask, bool train,
-           cudaStream_t s) {
+           cudaStream_t s, const Dropper& dr) {
   const int d = p.d, inner = p.inner, ff = p.ff, nl = p.nl, Mt = w.Mtok;
-  RC(embed_gather(ids, p.wf + p.lo.shared, w.X[0], Mt, d, p.V, s));
+  RC(embed_gather(ids, p.wf + p.lo.shared, w.X[0], Mt, d, p.V, s, dr(0, E_EMB)));
   RC(build_bias_lut(p.wf + p.lo.enc_relbias, m->enc_buckets, w.lut_enc, p.H, w.L, m->bucket_center, s));
   for (int l = 0; l < nl; ++l) {
     EncLayerAct& a = w.enc[l];
@@ -288,17 +302,17 @@ int encode(const Ptrs& p, const lako_fidt5* m, Work& w, const long long* ids, co
       RC(rmsnorm_fwd(w.X[0], nullptr, nullptr, p.wf + p.lo.enc_ln0[l], a.n_a, a.rstd_a, Mt, d, p.eps, 1.f, s));
     else
       RC(rmsnorm_fwd(w.X[2 * l - 1], w.delta_enc, w.X[2 * l], p.wf + p.lo.enc_ln0[l], a.n_a, a.rstd_a, Mt, d, p.eps,
-                     1.f, s));
+                     1.f, s, dr(l - 1, E_FF)));
     RC(lin_fwd(a.n_a, p.wb + p.lo.enc_qkv[l], a.qkv, Mt, 3 * inner, d, EPI_BF16, 1.f, s));
-    RC(enc_attn_fwd(a.qkv, mask, w.lut_enc, a.ao, a.lse, w.P, w.L, p.H, s));
+    RC(enc_attn_fwd(a.qkv, mask, w.lut_enc, a.ao, a.lse, w.P, w.L, p.H, s, dr(l, E_ATTN)));
     RC(lin_fwd(a.ao, p.wb + p.lo.enc_o[l], w.delta_enc, Mt, d, inner, EPI_BF16, 1.f, s));
     RC(rmsnorm_fwd(w.X[2 * l], w.delta_enc, w.X[2 * l + 1], p.wf + p.lo.enc_ln1[l], a.n_f, a.rstd_f, Mt, d, p.eps, 1.f,
-                   s));
-    RC(lin_fwd(a.n_f, p.wb + p.lo.enc_wi[l], a.h, Mt, ff, d, EPI_BF16_RELU, 1.f, s));
+                   s, dr(l, E_O)));
+    RC(lin_fwd(a.n_f, p.wb + p.lo.enc_wi[l], a.h, Mt, ff, d, EPI_BF16_RELU, 1.f, s, dr(l, E_RELU)));
     RC(lin_fwd(a.h, p.wb + p.lo.enc_wo[l], w.delta_enc, Mt, d, ff, EPI_BF16, 1.f, s));
   }
   RC(rmsnorm_fwd(w.X[2 * nl - 1], w.delta_enc, w.X[2 * nl], p.wf + p.lo.enc_final_ln, w.mem, w.rstd_enc_final, Mt, d,
-                 p.eps, 1.f, s));
+                 p.eps, 1.f, s, dr(nl - 1, E_FF), dr(0, E_FINAL)));
   // cross-attention K/V of ALL decoder layers in one GEMM (13.8 % of the model's FLOPs)
   RC(lin_fwd(w.mem, p.wb + p.lo.dec_xkv, w.kv_all, Mt, nl * 2 * inner, d, EPI_BF16, 1.f, s));
   (void)train;
@@ -326,11 +340,13 @@ extern "C" int lako_fidt5_forward(const lako_fidt5* m, const lako_batch* bt, int
   LAKO_REQUIRE(w.bytes <= bt->workspace_bytes, LAKO_ERR_WORKSPACE);
   const bool train = mode == 1;
   const int d = p.d, inner = p.inner, ff = p.ff, nl = p.nl, BT = w.BT;
-  RC(encode(p, m, w, reinterpret_cast<const long long*>(bt->ids), bt->mask, train, s));
+  Dropper dr{bt->dropout_seed, bt->dropout_step, train ? bt->dropout_p : 0.f};
+  LAKO_REQUIRE(dr.p >= 0.f && dr.p < 0.9f, LAKO_ERR_BAD_ARG);
+  RC(encode(p, m, w, reinterpret_cast<const long long*>(bt->ids), bt->mask, train, s, dr));
 
   const long long* labels = reinterpret_cast<const long long*>(bt->labels);
   RC(shift_right(labels, w.dec_ids, bt->B, bt->T, s));
-  RC(embed_gather(w.dec_ids, p.wf + p.lo.shared, w.Y[0], BT, d, p.V, s));
+  RC(embed_gather(w.dec_ids, p.wf + p.lo.shared, w.Y[0], BT, d, p.V, s, dr(0, D_EMB)));
   RC(build_bias_lut(p.wf + p.lo.dec_relbias, m->dec_buckets, w.lut_dec, p.H, bt->T, m->bucket_center, s));
   for (int l = 0; l < nl; ++l) {
     DecLayerAct& a = w.dec[l];
@@ -338,23 +354,23 @@ extern "C" int lako_fidt5_forward(const lako_fidt5* m, const lako_batch* bt, int
       RC(rmsnorm_fwd(w.Y[0], nullptr, nullptr, p.wf + p.lo.dec_ln0[l], a.n_s, a.rstd_s, BT, d, p.eps, 1.f, s));
     else
       RC(rmsnorm_fwd(w.Y[3 * l - 1], w.delta_dec, w.Y[3 * l], p.wf + p.lo.dec_ln0[l], a.n_s, a.rstd_s, BT, d, p.eps,
-                     1.f, s));
+                     1.f, s, dr(l - 1, D_FF)));
     RC(lin_fwd(a.n_s, p.wb + p.lo.dec_qkv[l], a.qkv, BT, 3 * inner, d, EPI_BF16, 1.f, s));
-    RC(dself_fwd(a.qkv, w.lut_dec, a.ao, a.probs, bt->B, bt->T, p.H, s));
+    RC(dself_fwd(a.qkv, w.lut_dec, a.ao, a.probs, bt->B, bt->T, p.H, s, dr(l, D_SELF)));
     RC(lin_fwd(a.ao, p.wb + p.lo.dec_o[l], w.delta_dec, BT, d, inner, EPI_BF16, 1.f, s));
     RC(rmsnorm_fwd(w.Y[3 * l], w.delta_dec, w.Y[3 * l + 1], p.wf + p.lo.dec_ln1[l], a.n_c, a.rstd_c, BT, d, p.eps, 1.f,
-                   s));
+                   s, dr(l, D_O)));
     RC(lin_fwd(a.n_c, p.wb + p.lo.dec_xq[l], a.q, BT, inner, d, EPI_BF16, 1.f, s));
     RC(xattn_fwd(a.q, w.kv_all, bt->mask, a.xo, a.lse, nullptr, w.xattn_ws, bt->B, bt->T, w.M, p.H, inner,
-                 nl * 2 * inner, l * 2 * inner, l * 2 * inner + inner, inner, s));
+                 nl * 2 * inner, l * 2 * inner, l * 2 * inner + inner, inner, s, dr(l, D_XP)));
     RC(lin_fwd(a.xo, p.wb + p.lo.dec_xo[l], w.delta_dec, BT, d, inner, EPI_BF16, 1.f, s));
     RC(rmsnorm_fwd(w.Y[3 * l + 1], w.delta_dec, w.Y[3 * l + 2], p.wf + p.lo.dec_ln2[l], a.n_f, a.rstd_f, BT, d, p.eps,
-                   1.f, s));
-    RC(lin_fwd(a.n_f, p.wb + p.lo.dec_wi[l], a.h, BT, ff, d, EPI_BF16_RELU, 1.f, s));
+                   1.f, s, dr(l, D_XO)));
+    RC(lin_fwd(a.n_f, p.wb + p.lo.dec_wi[l], a.h, BT, ff, d, EPI_BF16_RELU, 1.f, s, dr(l, D_RELU)));
     RC(lin_fwd(a.h, p.wb + p.lo.dec_wo[l], w.delta_dec, BT, d, ff, EPI_BF16, 1.f, s));
   }
   RC(rmsnorm_fwd(w.Y[3 * nl - 1], w.delta_dec, w.Y[3 * nl], p.wf + p.lo.dec_final_ln, w.hn, w.rstd_dec_final, BT, d,
-                 p.eps, 1.f, s));
+                 p.eps, 1.f, s, dr(nl - 1, D_FF), dr(0, D_FINAL)));
   // tied LM head: logits = (h * d^-0.5) E^T  (HF:1107-1110), fp32 out
   const float alpha = 1.0f / sqrtf(static_cast<float>(d));
   RC(lin_fwd(w.hn, p.wb + p.lo.shared, bt->logits, BT, p.V, d, EPI_F32, alpha, s));
@@ -379,6 +395,8 @@ extern "C" int lako_fidt5_backward(const lako_fidt5* m, const lako_batch* bt, co
   const size_t vpad = (static_cast<size_t>(p.V) + 7) / 8 * 8;
   const float alpha = 1.0f / sqrtf(static_cast<float>(d));
   float* g = p.g;
+  Dropper dr{bt->dropout_seed, bt->dropout_step, bt->dropout_p};
+  const float dsc = dr.p > 0.f ? dr(0, 0).scale : 1.f;  // 1/(1-p), same for every site
 
   cudaMemsetAsync(w.dlut_enc, 0, sizeof(float) * H * (2 * w.L - 1), s);
   cudaMemsetAsync(w.dlut_dec, 0, sizeof(float) * H * (2 * w.T - 1), s);
@@ -390,63 +408,65 @@ extern "C" int lako_fidt5_backward(const lako_fidt5* m, const lako_batch* bt, co
   RC(gemm_bf16(w.dlogits, w.hn, g + p.lo.shared, p.V, d, BT, static_cast<int>(vpad), d, d, 1, 1, EPI_F32_ATOMIC, alpha,
                nullptr, 0, 1, 0, s));
   RC(rmsnorm_bwd(w.dhn, w.Y[3 * nl], w.rstd_dec_final, p.wf + p.lo.dec_final_ln, w.dres_dec, w.dres_dec_b,
-                 g + p.lo.dec_final_ln, BT, d, 0, 1.f, s));
+                 g + p.lo.dec_final_ln, BT, d, 0, dsc, s, dr(0, D_FINAL), dr(nl - 1, D_FF)));
   // ---- decoder layers
   for (int l = nl - 1; l >= 0; --l) {
     DecLayerAct& a = w.dec[l];
     // FFN
-    RC(lin_dgrad(w.dres_dec_b, p.wb + p.lo.dec_wo[l], w.dh_dec, BT, d, ff, a.h, 1.f, s));
+    RC(lin_dgrad(w.dres_dec_b, p.wb + p.lo.dec_wo[l], w.dh_dec, BT, d, ff, a.h, dsc, s));
     RC(lin_wgrad(w.dres_dec_b, a.h, g + p.lo.dec_wo[l], BT, d, ff, 1.f, s));
     RC(lin_dgrad(w.dh_dec, p.wb + p.lo.dec_wi[l], w.dn_dec, BT, ff, d, nullptr, 1.f, s));
     RC(lin_wgrad(w.dh_dec, a.n_f, g + p.lo.dec_wi[l], BT, ff, d, 1.f, s));
     RC(rmsnorm_bwd(w.dn_dec, w.Y[3 * l + 2], a.rstd_f, p.wf + p.lo.dec_ln2[l], w.dres_dec, w.dres_dec_b,
-                   g + p.lo.dec_ln2[l], BT, d, 1, 1.f, s));
+                   g + p.lo.dec_ln2[l], BT, d, 1, 1.f, s, dr.none(), dr(l, D_XO)));
     // cross-attention
     RC(lin_dgrad(w.dres_dec_b, p.wb + p.lo.dec_xo[l], w.dao_dec, BT, d, inner, nullptr, 1.f, s));
     RC(lin_wgrad(w.dres_dec_b, a.xo, g + p.lo.dec_xo[l], BT, d, inner, 1.f, s));
     cudaMemsetAsync(w.dq_f32, 0, sizeof(float) * BT * inner, s);
     RC(xattn_bwd(a.q, w.kv_all, bt->mask, a.xo, w.dao_dec, a.lse, w.dkv_all, w.dq_f32, bt->B, bt->T, w.M, H, inner,
-                 nl * 2 * inner, l * 2 * inner, l * 2 * inner + inner, inner, s));
+                 nl * 2 * inner, l * 2 * inner, l * 2 * inner + inner, inner, s, dr(l, D_XP)));
     RC(cast_f32_to_bf16(w.dq_f32, w.dq_dec, static_cast<size_t>(BT) * inner, s));
     RC(lin_dgrad(w.dq_dec, p.wb + p.lo.dec_xq[l], w.dn_dec, BT, inner, d, nullptr, 1.f, s));
     RC(lin_wgrad(w.dq_dec, a.n_c, g + p.lo.dec_xq[l], BT, inner, d, 1.f, s));
     RC(rmsnorm_bwd(w.dn_dec, w.Y[3 * l + 1], a.rstd_c, p.wf + p.lo.dec_ln1[l], w.dres_dec, w.dres_dec_b,
-                   g + p.lo.dec_ln1[l], BT, d, 1, 1.f, s));
+                   g + p.lo.dec_ln1[l], BT, d, 1, 1.f, s, dr.none(), dr(l, D_O)));
     // self-attention
     RC(lin_dgrad(w.dres_dec_b, p.wb + p.lo.dec_o[l], w.dao_dec, BT, d, inner, nullptr, 1.f, s));
     RC(lin_wgrad(w.dres_dec_b, a.ao, g + p.lo.dec_o[l], BT, d, inner, 1.f, s));
-    RC(dself_bwd(a.qkv, w.dao_dec, a.probs, w.dqkv_dec, w.dlut_dec, bt->B, bt->T, H, s));
+    RC(dself_bwd(a.qkv, w.dao_dec, a.probs, w.dqkv_dec, w.dlut_dec, bt->B, bt->T, H, s, dr(l, D_SELF)));
     RC(lin_dgrad(w.dqkv_dec, p.wb + p.lo.dec_qkv[l], w.dn_dec, BT, 3 * inner, d, nullptr, 1.f, s));
     RC(lin_wgrad(w.dqkv_dec, a.n_s, g + p.lo.dec_qkv[l], BT, 3 * inner, d, 1.f, s));
     RC(rmsnorm_bwd(w.dn_dec, w.Y[3 * l], a.rstd_s, p.wf + p.lo.dec_ln0[l], w.dres_dec, w.dres_dec_b,
-                   g + p.lo.dec_ln0[l], BT, d, 1, 1.f, s));
+                   g + p.lo.dec_ln0[l], BT, d, 1, 1.f, s, dr.none(), l > 0 ? dr(l - 1, D_FF) : dr.none()));
   }
-  RC(embed_scatter_add(w.dec_ids, w.dres_dec, g + p.lo.shared, BT, d, p.V, s));
+  RC(embed_scatter_add(w.dec_ids, w.dres_dec, g + p.lo.shared, BT, d, p.V, s, dr(0, D_EMB)));
   RC(fold_dlut(w.dlut_dec, m->dec_buckets, g + p.lo.dec_relbias, H, w.T, m->bucket_center, m->dims.n_buckets, s));
   // ---- fused memory: all decoder layers' cross K/V projections at once
   const int nkv = nl * 2 * inner;
   RC(lin_dgrad(w.dkv_all, p.wb + p.lo.dec_xkv, w.dmem, Mt, nkv, d, nullptr, 1.f, s));
   RC(lin_wgrad(w.dkv_all, w.mem, g + p.lo.dec_xkv, Mt, nkv, d, 1.f, s));
   RC(rmsnorm_bwd(w.dmem, w.X[2 * nl], w.rstd_enc_final, p.wf + p.lo.enc_final_ln, w.dres_enc, w.dres_enc_b,
-                 g + p.lo.enc_final_ln, Mt, d, 0, 1.f, s));
+                 g + p.lo.enc_final_ln, Mt, d, 0, dsc, s, dr(0, E_FINAL), dr(nl - 1, E_FF)));
   // ---- encoder layers
   for (int l = nl - 1; l >= 0; --l) {
     EncLayerAct& a = w.enc[l];
-    RC(lin_dgrad(w.dres_enc_b, p.wb + p.lo.enc_wo[l], w.dh_enc, Mt, d, ff, a.h, 1.f, s));
+    RC(lin_dgrad(w.dres_enc_b, p.wb + p.lo.enc_wo[l], w.dh_enc, Mt, d, ff, a.h, dsc, s));
     RC(lin_wgrad(w.dres_enc_b, a.h, g + p.lo.enc_wo[l], Mt, d, ff, 1.f, s));
     RC(lin_dgrad(w.dh_enc, p.wb + p.lo.enc_wi[l], w.dn_enc, Mt, ff, d, nullptr, 1.f, s));
     RC(lin_wgrad(w.dh_enc, a.n_f, g + p.lo.enc_wi[l], Mt, ff, d, 1.f, s));
     RC(rmsnorm_bwd(w.dn_enc, w.X[2 * l + 1], a.rstd_f, p.wf + p.lo.enc_ln1[l], w.dres_enc, w.dres_enc_b,
-                   g + p.lo.enc_ln1[l], Mt, d, 1, 1.f, s));
+                   g + p.lo.enc_ln1[l], Mt, d, 1, 1.f, s, dr.none(), dr(l, E_O)));
     RC(lin_dgrad(w.dres_enc_b, p.wb + p.lo.enc_o[l], w.dao_enc, Mt, d, inner, nullptr, 1.f, s));
     RC(lin_wgrad(w.dres_enc_b, a.ao, g + p.lo.enc_o[l], Mt, d, inner, 1.f, s));
-    RC(enc_attn_bwd(a.qkv, a.ao, w.dao_enc, a.lse, bt->mask, w.lut_enc, w.dqkv_enc, w.dlut_enc, w.P, w.L, H, s));
+    RC(enc_attn_bwd(a.qkv, a.ao, w.dao_enc, a.lse, bt->mask, w.lut_enc, w.dqkv_enc, w.dlut_enc, w.P, w.L, H, s,
+                    dr(l, E_ATTN)));
     RC(lin_dgrad(w.dqkv_enc, p.wb + p.lo.enc_qkv[l], w.dn_enc, Mt, 3 * inner, d, nullptr, 1.f, s));
     RC(lin_wgrad(w.dqkv_enc, a.n_a, g + p.lo.enc_qkv[l], Mt, 3 * inner, d, 1.f, s));
     RC(rmsnorm_bwd(w.dn_enc, w.X[2 * l], a.rstd_a, p.wf + p.lo.enc_ln0[l], w.dres_enc, w.dres_enc_b,
-                   g + p.lo.enc_ln0[l], Mt, d, 1, 1.f, s));
+                   g + p.lo.enc_ln0[l], Mt, d, 1, 1.f, s, dr.none(), l > 0 ? dr(l - 1, E_FF) : dr.none()));
   }
-  RC(embed_scatter_add(reinterpret_cast<const long long*>(bt->ids), w.dres_enc, g + p.lo.shared, Mt, d, p.V, s));
+  RC(embed_scatter_add(reinterpret_cast<const long long*>(bt->ids), w.dres_enc, g + p.lo.shared, Mt, d, p.V, s,
+                       dr(0, E_EMB)));
   RC(fold_dlut(w.dlut_enc, m->enc_buckets, g + p.lo.enc_relbias, H, w.L, m->bucket_center, m->dims.n_buckets, s));
   return LAKO_OK;
 }
@@ -512,7 +532,7 @@ extern "C" int lako_fidt5_generate(const lako_fidt5* m, const lako_batch* bt, in
   LAKO_REQUIRE(gw.bytes <= bt->workspace_bytes, LAKO_ERR_WORKSPACE);
   Work& w = gw.enc;
   const int d = p.d, inner = p.inner, ff = p.ff, nl = p.nl, B = bt->B, H = p.H;
-  RC(encode(p, m, w, reinterpret_cast<const long long*>(bt->ids), bt->mask, false, s));
+  RC(encode(p, m, w, reinterpret_cast<const long long*>(bt->ids), bt->mask, false, s, Dropper{0, 0, 0.f}));
   RC(build_bias_lut(p.wf + p.lo.dec_relbias, m->dec_buckets, gw.lut_dec, H, max_length, m->bucket_center, s));
   gen_init_kernel<<<(B + 127) / 128, 128, 0, s>>>(gw.unfinished, gw.n_unf, gw.next_ids,
                                                    reinterpret_cast<long long*>(out_ids), B, max_length);

@@ -6,17 +6,23 @@ namespace lako {
 
 // gemm.cu
 int gemm_bf16(const void* A, const void* B, void* C, int M, int N, int K, int lda, int ldb, int ldc, int a_mn,
-              int b_mn, int epi, float alpha, const void* aux, int ld_aux, int splitk, int bn, cudaStream_t stream);
+              int b_mn, int epi, float alpha, const void* aux, int ld_aux, int splitk, int bn, cudaStream_t stream,
+              DropSpec drop = DropSpec{});
 enum : int { EPI_BF16 = 0, EPI_BF16_RELU = 1, EPI_F32 = 2, EPI_F32_ATOMIC = 3, EPI_BF16_MASK = 4 };
 
 // elementwise.cu
+// DropSpec{} (thresh == 0) disables a dropout site.  dd: mask on `delta` before the residual add; od: mask on the
+// normalised output.  yd: mask on the incoming dy; bd: mask applied to the bf16 copy of the updated dres.
 int rmsnorm_fwd(const float* x, const __nv_bfloat16* delta, float* x_out, const float* w, __nv_bfloat16* out,
-                float* rstd, int rows, int d, float eps, float out_scale, cudaStream_t s);
+                float* rstd, int rows, int d, float eps, float out_scale, cudaStream_t s, DropSpec dd = DropSpec{},
+                DropSpec od = DropSpec{});
 int rmsnorm_bwd(const __nv_bfloat16* dy, const float* x, const float* rstd, const float* w, float* dres,
-                __nv_bfloat16* dres_bf16, float* dw, int rows, int d, int accumulate, float dy_scale, cudaStream_t s);
-int embed_gather(const long long* ids, const float* table, float* out, int rows, int d, int vocab, cudaStream_t s);
+                __nv_bfloat16* dres_bf16, float* dw, int rows, int d, int accumulate, float dy_scale, cudaStream_t s,
+                DropSpec yd = DropSpec{}, DropSpec bd = DropSpec{});
+int embed_gather(const long long* ids, const float* table, float* out, int rows, int d, int vocab, cudaStream_t s,
+                 DropSpec ds = DropSpec{});
 int embed_scatter_add(const long long* ids, const float* dres, float* dtable, int rows, int d, int vocab,
-                      cudaStream_t s);
+                      cudaStream_t s, DropSpec ds = DropSpec{});
 int shift_right(const long long* labels, long long* dec_ids, int B, int T, cudaStream_t s);
 int count_valid(const long long* labels, int n, float* stats, cudaStream_t s);
 int ce_fwd_bwd(const float* logits, const long long* labels, float* stats, float* row_loss, __nv_bfloat16* dlogits,
@@ -35,29 +41,30 @@ int build_bias_lut(const float* table, const int* buckets, float* lut, int H, in
 int fold_dlut(const float* dlut, const int* buckets, float* dtable, int H, int L, int bucket_center, int nb,
               cudaStream_t s);
 int enc_attn_fwd(const __nv_bfloat16* qkv, const unsigned char* mask, const float* bias_lut, __nv_bfloat16* out,
-                 float* lse, int P, int L, int H, cudaStream_t s);
+                 float* lse, int P, int L, int H, cudaStream_t s, DropSpec drop = DropSpec{});
 int enc_attn_bwd(const __nv_bfloat16* qkv, const __nv_bfloat16* out, const __nv_bfloat16* dout, const float* lse,
                  const unsigned char* mask, const float* bias_lut, __nv_bfloat16* dqkv, float* dlut, int P, int L,
-                 int H, cudaStream_t s);
+                 int H, cudaStream_t s, DropSpec drop = DropSpec{});
 
 // dec_attn.cu
 size_t xattn_workspace_bytes(int B, int H, int T, int M);
 int xattn_fwd(const __nv_bfloat16* q, const __nv_bfloat16* kv, const unsigned char* mask, __nv_bfloat16* out, float* lse,
               float* tok_score, float* workspace, int B, int T, int M, int H, int ldq, int ldkv, int koff, int voff,
-              int ldo, cudaStream_t s);
+              int ldo, cudaStream_t s, DropSpec drop = DropSpec{});
 int xattn_bwd(const __nv_bfloat16* q, const __nv_bfloat16* kv, const unsigned char* mask, const __nv_bfloat16* out,
               const __nv_bfloat16* dout, const float* lse, __nv_bfloat16* dkv, float* dq_f32, int B, int T, int M,
-              int H, int ldq, int ldkv, int koff, int voff, int ldo, cudaStream_t s);
+              int H, int ldq, int ldkv, int koff, int voff, int ldo, cudaStream_t s, DropSpec drop = DropSpec{});
 // xattn_mma.cu
 int xattn_fwd_mma(const __nv_bfloat16* q, const __nv_bfloat16* kv, const unsigned char* mask, float* tok_score,
-                  float* workspace, int B, int T, int M, int H, int ldq, int ldkv, int koff, int voff, cudaStream_t s);
+                  float* workspace, int B, int T, int M, int H, int ldq, int ldkv, int koff, int voff, cudaStream_t s,
+                  DropSpec drop = DropSpec{});
 int xattn_bwd_mma(const __nv_bfloat16* q, const __nv_bfloat16* kv, const unsigned char* mask, const __nv_bfloat16* out,
                   const __nv_bfloat16* dout, const float* lse, __nv_bfloat16* dkv, float* dq_f32, int B, int T, int M,
-                  int H, int ldq, int ldkv, int koff, int voff, int ldo, cudaStream_t s);
+                  int H, int ldq, int ldkv, int koff, int voff, int ldo, cudaStream_t s, DropSpec drop = DropSpec{});
 int dself_fwd(const __nv_bfloat16* qkv, const float* lut, __nv_bfloat16* out, float* probs, int B, int T, int H,
-              cudaStream_t s);
+              cudaStream_t s, DropSpec drop = DropSpec{});
 int dself_bwd(const __nv_bfloat16* qkv, const __nv_bfloat16* dout, const float* probs, __nv_bfloat16* dqkv, float* dlut,
-              int B, int T, int H, cudaStream_t s);
+              int B, int T, int H, cudaStream_t s, DropSpec drop = DropSpec{});
 int dself_step(const __nv_bfloat16* qkv, __nv_bfloat16* kcache, __nv_bfloat16* vcache, const float* lut,
                __nv_bfloat16* out, int B, int pos, int Tmax, int H, cudaStream_t s);
 int greedy_pick(const float* logits, int B, int V, int ld, long long* out_ids, int out_ld, int step, int* unfinished,

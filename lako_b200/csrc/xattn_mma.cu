@@ -64,6 +64,7 @@ struct XMParams {
   __nv_bfloat16* dkv;         // bwd
   float* dq;                  // bwd [B*T][H*64] fp32 (pre-zeroed)
   int T, TP, M, H, ldq, ldkv, koff, voff, ldo, splits;
+  DropSpec drop;  // attention-probability dropout; group = ((b*H+h)*T + t) * ceil(M/8) + key/8
 };
 
 // dynamic smem: sK 16K | sV 16K | sQ TP*128 | sX TP*128 (bwd: dO) | f32 scratch
@@ -149,6 +150,18 @@ __global__ void __launch_bounds__(128) xattn_fwd_mma_kernel(const XMParams p) {
       }
       lrow[0] += e[0] + e[1];
       lrow[1] += e[2] + e[3];
+      if (p.drop.thresh) {
+        const unsigned long long G = (p.M + 7) >> 3, kg = (k0 + kb + nt * 8) >> 3;
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+          const int t = mt * 16 + g + r * 8;
+          if (t < p.T) {
+            const uint32_t k = drop_keep8(p.drop, (static_cast<unsigned long long>(b * p.H + h) * p.T + t) * G + kg);
+            e[r * 2 + 0] = ((k >> (t4 * 2)) & 1u) ? e[r * 2 + 0] * p.drop.scale : 0.f;
+            e[r * 2 + 1] = ((k >> (t4 * 2 + 1)) & 1u) ? e[r * 2 + 1] * p.drop.scale : 0.f;
+          }
+        }
+      }
       pa[nt >> 1][(nt & 1) * 2 + 0] = pack_bf16x2(e[0], e[1]);
       pa[nt >> 1][(nt & 1) * 2 + 1] = pack_bf16x2(e[2], e[3]);
     }
@@ -301,12 +314,31 @@ __global__ void __launch_bounds__(128) xattn_bwd_mma_kernel(const XMParams p) {
       if (nt < NTT) {
         const int t = nt * 8 + t4 * 2;
         const float l0 = sLse[t], l1 = sLse[t + 1], d0 = sD[t], d1 = sD[t + 1];
-        const float p00 = fast_exp2(((st[nt][0] + mk0) - l0) * XM_LOG2E);
-        const float p01 = fast_exp2(((st[nt][1] + mk0) - l1) * XM_LOG2E);
-        const float p10 = fast_exp2(((st[nt][2] + mk1) - l0) * XM_LOG2E);
-        const float p11 = fast_exp2(((st[nt][3] + mk1) - l1) * XM_LOG2E);
-        const float s00 = p00 * (dpt[nt][0] - d0), s01 = p01 * (dpt[nt][1] - d1);
-        const float s10 = p10 * (dpt[nt][2] - d0), s11 = p11 * (dpt[nt][3] - d1);
+        float p00 = fast_exp2(((st[nt][0] + mk0) - l0) * XM_LOG2E);
+        float p01 = fast_exp2(((st[nt][1] + mk0) - l1) * XM_LOG2E);
+        float p10 = fast_exp2(((st[nt][2] + mk1) - l0) * XM_LOG2E);
+        float p11 = fast_exp2(((st[nt][3] + mk1) - l1) * XM_LOG2E);
+        float e00 = dpt[nt][0], e01 = dpt[nt][1], e10 = dpt[nt][2], e11 = dpt[nt][3];
+        float q00 = p00, q01 = p01, q10 = p10, q11 = p11;  // dropped copies feed dV = P_drop^T dO
+        if (p.drop.thresh) {
+          const unsigned long long G = (p.M + 7) >> 3, kg = (k0 + key0) >> 3, rb = static_cast<unsigned long long>(b * p.H + h) * p.T;
+          const float sc = p.drop.scale;
+          if (t < p.T) {
+            const uint32_t ka = drop_keep8(p.drop, (rb + t) * G + kg), kb2 = drop_keep8(p.drop, (rb + t) * G + kg + 1);
+            const bool k0b = (ka >> g) & 1u, k1b = (kb2 >> g) & 1u;
+            e00 = k0b ? e00 * sc : 0.f; q00 = k0b ? q00 * sc : 0.f;
+            e10 = k1b ? e10 * sc : 0.f; q10 = k1b ? q10 * sc : 0.f;
+          }
+          if (t + 1 < p.T) {
+            const uint32_t ka = drop_keep8(p.drop, (rb + t + 1) * G + kg), kb2 = drop_keep8(p.drop, (rb + t + 1) * G + kg + 1);
+            const bool k0b = (ka >> g) & 1u, k1b = (kb2 >> g) & 1u;
+            e01 = k0b ? e01 * sc : 0.f; q01 = k0b ? q01 * sc : 0.f;
+            e11 = k1b ? e11 * sc : 0.f; q11 = k1b ? q11 * sc : 0.f;
+          }
+        }
+        const float s00 = p00 * (e00 - d0), s01 = p01 * (e01 - d1);
+        const float s10 = p10 * (e10 - d0), s11 = p11 * (e11 - d1);
+        p00 = q00; p01 = q01; p10 = q10; p11 = q11;
         pa[nt >> 1][(nt & 1) * 2 + 0] = pack_bf16x2(p00, p01);
         pa[nt >> 1][(nt & 1) * 2 + 1] = pack_bf16x2(p10, p11);
         const uint32_t ds0 = pack_bf16x2(s00, s01), ds1 = pack_bf16x2(s10, s11);
@@ -407,13 +439,14 @@ static size_t xm_smem_bytes(int TP, bool bwd) {
 
 int xattn_fwd_mma(const __nv_bfloat16* q, const __nv_bfloat16* kv, const unsigned char* mask, float* tok_score,
                   float* workspace, int B, int T, int M, int H, int ldq, int ldkv, int koff, int voff,
-                  cudaStream_t s) {
+                  cudaStream_t s, DropSpec drop) {
   LAKO_REQUIRE(B > 0 && T > 0 && T <= 64 && M > 0 && H > 0, LAKO_ERR_UNSUPPORTED);
   LAKO_REQUIRE(ldq % 8 == 0 && ldkv % 8 == 0 && koff % 8 == 0 && voff % 8 == 0, LAKO_ERR_BAD_ARG);
   XMParams p{};
   p.q = q; p.kv = kv; p.mask = mask; p.part = workspace; p.tok_score = tok_score;
   p.T = T; p.TP = (T + 15) / 16 * 16; p.M = M; p.H = H; p.ldq = ldq; p.ldkv = ldkv; p.koff = koff; p.voff = voff;
   p.splits = (M + XM_CH - 1) / XM_CH;
+  p.drop = drop;
   static bool configured = false;
   if (!configured) {
     cudaFuncSetAttribute(xattn_fwd_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xm_smem_bytes(64, false));
@@ -426,7 +459,7 @@ int xattn_fwd_mma(const __nv_bfloat16* q, const __nv_bfloat16* kv, const unsigne
 
 int xattn_bwd_mma(const __nv_bfloat16* q, const __nv_bfloat16* kv, const unsigned char* mask, const __nv_bfloat16* out,
                   const __nv_bfloat16* dout, const float* lse, __nv_bfloat16* dkv, float* dq_f32, int B, int T, int M,
-                  int H, int ldq, int ldkv, int koff, int voff, int ldo, cudaStream_t s) {
+                  int H, int ldq, int ldkv, int koff, int voff, int ldo, cudaStream_t s, DropSpec drop) {
   LAKO_REQUIRE(B > 0 && T > 0 && T <= 64 && M > 0 && H > 0, LAKO_ERR_UNSUPPORTED);
   LAKO_REQUIRE(ldq % 8 == 0 && ldkv % 8 == 0 && koff % 8 == 0 && voff % 8 == 0 && ldo % 8 == 0, LAKO_ERR_BAD_ARG);
   XMParams p{};
@@ -434,6 +467,7 @@ int xattn_bwd_mma(const __nv_bfloat16* q, const __nv_bfloat16* kv, const unsigne
   p.T = T; p.TP = (T + 15) / 16 * 16; p.M = M; p.H = H; p.ldq = ldq; p.ldkv = ldkv; p.koff = koff; p.voff = voff;
   p.ldo = ldo;
   p.splits = (M + XM_CH - 1) / XM_CH;
+  p.drop = drop;
   static bool configured = false;
   if (!configured) {
     cudaFuncSetAttribute(xattn_bwd_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xm_smem_bytes(64, true));

@@ -57,7 +57,8 @@ class _Batch(ctypes.Structure):
     _fields_ = [("ids", ctypes.c_void_p), ("mask", ctypes.c_void_p), ("labels", ctypes.c_void_p),
                 ("B", ctypes.c_int), ("N", ctypes.c_int), ("L", ctypes.c_int), ("T", ctypes.c_int),
                 ("workspace", ctypes.c_void_p), ("workspace_bytes", ctypes.c_size_t),
-                ("logits", ctypes.c_void_p), ("stats", ctypes.c_void_p), ("count_is_set", ctypes.c_int)]
+                ("logits", ctypes.c_void_p), ("stats", ctypes.c_void_p), ("count_is_set", ctypes.c_int),
+                ("dropout_p", ctypes.c_float), ("dropout_step", ctypes.c_uint), ("dropout_seed", ctypes.c_ulonglong)]
 
 
 class FiDT5Config:
@@ -184,6 +185,9 @@ class FiDT5(nn.Module):
         self._capture = False
         self._tok_first = self._tok_last = None
         self.use_checkpoint = False
+        # training dropout (config.dropout_rate, 0.1 for every T5 size): Philox masks keyed by (seed, step)
+        self._drop_seed = None
+        self._drop_step = 0
         self._init_weights(emb_std, seed)
 
     # ------------------------------------------------------------------ parameters
@@ -415,6 +419,12 @@ class FiDT5(nn.Module):
             self._ws[key[0]] = ws
         return ws[1]
 
+    def set_dropout_seed(self, seed):
+        """Seed of the dropout masks (defaults to torch.initial_seed() at the first training forward; use a
+        different seed per data-parallel rank, as train_reader.py:39 does with torch.manual_seed(rank + seed))."""
+        self._drop_seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+        self._drop_step = 0
+
     # ------------------------------------------------------------------ forward / backward
     def forward(self, input_ids=None, attention_mask=None, labels=None, global_target_count=None, **kwargs):
         self._require_cuda()
@@ -446,22 +456,28 @@ class FiDT5(nn.Module):
         if global_target_count is not None:
             stats[1] = global_target_count
             count_is_set = 1
+        drop_p = float(self.config.dropout_rate) if (train and self.training) else 0.0
+        if drop_p > 0.0:
+            if self._drop_seed is None:
+                self._drop_seed = torch.initial_seed() & 0xFFFFFFFFFFFFFFFF
+            self._drop_step += 1
+        drop = (drop_p, self._drop_step & 0xFFFFFFFF, self._drop_seed or 0)
         m = self._model_struct(with_grad=train)
         bt = _Batch(ids.data_ptr(), mask.data_ptr(), labels.data_ptr(), B, N, L, T, ws.data_ptr(), ws.numel(),
-                    logits.data_ptr(), stats.data_ptr(), count_is_set)
+                    logits.data_ptr(), stats.data_ptr(), count_is_set, *drop)
         nat.check(L_.lako_fidt5_forward(ctypes.byref(m), ctypes.byref(bt), mode, nat.stream_ptr()), "lako_fidt5_forward")
         loss = stats[0] / torch.clamp(stats[1], min=1.0)
         if train:
-            keep = (ids, mask, labels, ws, logits, stats, (B, N, L, T))
+            keep = (ids, mask, labels, ws, logits, stats, (B, N, L, T), drop)
             loss, logits = _LossFn.apply(self._anchor, self, keep, loss, logits)
         return (loss, logits)
 
     def _run_backward(self, keep, grad_loss):
-        ids, mask, labels, ws, logits, stats, (B, N, L, T) = keep
+        ids, mask, labels, ws, logits, stats, (B, N, L, T), drop = keep
         L_ = nat.lib()
         m = self._model_struct(with_grad=True)
         bt = _Batch(ids.data_ptr(), mask.data_ptr(), labels.data_ptr(), B, N, L, T, ws.data_ptr(), ws.numel(),
-                    logits.data_ptr(), stats.data_ptr(), 1)
+                    logits.data_ptr(), stats.data_ptr(), 1, *drop)
         gl = grad_loss.detach().to(torch.float32).reshape(1).contiguous()
         nat.check(L_.lako_fidt5_backward(ctypes.byref(m), ctypes.byref(bt), nat.ptr(gl), nat.stream_ptr()),
                   "lako_fidt5_backward")
@@ -486,7 +502,7 @@ class FiDT5(nn.Module):
             self._tok_last = torch.zeros(B, N * L, dtype=torch.float32, device=ids.device)
             tf, tl = self._tok_first, self._tok_last
         m = self._model_struct(with_grad=False)
-        bt = _Batch(ids.data_ptr(), mask.data_ptr(), 0, B, N, L, 1, ws.data_ptr(), ws.numel(), 0, 0, 0)
+        bt = _Batch(ids.data_ptr(), mask.data_ptr(), 0, B, N, L, 1, ws.data_ptr(), ws.numel(), 0, 0, 0, 0.0, 0, 0)
         out_len = ctypes.c_int(0)
         nat.check(L_.lako_fidt5_generate(ctypes.byref(m), ctypes.byref(bt), max_length, nat.ptr(out),
                                          ctypes.byref(out_len), nat.ptr(tf), nat.ptr(tl), nat.stream_ptr()),

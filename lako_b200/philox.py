@@ -1,0 +1,47 @@
+"""Host restatement of the kernels' counter-based dropout mask (csrc/common.cuh: philox4x32_10 / drop_keep8),
+used by the tests to rebuild the exact keep-masks a kernel applied and by users who need to audit them."""
+import numpy as np
+
+M0, M1 = np.uint64(0xD2511F53), np.uint64(0xCD9E8D57)
+W0, W1 = np.uint32(0x9E3779B9), np.uint32(0xBB67AE85)
+MASK32 = np.uint64(0xFFFFFFFF)
+
+
+def philox4x32_10(c0, c1, c2, c3, k0, k1):
+    c0, c1, c2, c3 = (np.asarray(x, dtype=np.uint32) for x in (c0, c1, c2, c3))
+    k0 = np.uint32(k0)
+    k1 = np.uint32(k1)
+    with np.errstate(over="ignore"):
+        for _ in range(10):
+            p0 = M0 * c0.astype(np.uint64)
+            p1 = M1 * c2.astype(np.uint64)
+            hi0, lo0 = (p0 >> np.uint64(32)).astype(np.uint32), (p0 & MASK32).astype(np.uint32)
+            hi1, lo1 = (p1 >> np.uint64(32)).astype(np.uint32), (p1 & MASK32).astype(np.uint32)
+            c0, c1, c2, c3 = hi1 ^ c1 ^ k0, lo1, hi0 ^ c3 ^ k1, lo0
+            k0 = np.uint32((int(k0) + int(W0)) & 0xFFFFFFFF)
+            k1 = np.uint32((int(k1) + int(W1)) & 0xFFFFFFFF)
+    return c0, c1, c2, c3
+
+
+def thresh_of(p):
+    return int(p * 65536.0 + 0.5) if p > 0 else 0
+
+
+def scale_of(p):
+    return 1.0 / (1.0 - thresh_of(p) / 65536.0) if p > 0 else 1.0
+
+
+def keep_mask(seed, step, site, n_elems, p):
+    """bool numpy array [n_elems]: keep decision of element e (group e>>3, 16-bit lane e&7)."""
+    if p <= 0:
+        return np.ones(n_elems, dtype=bool)
+    groups = (n_elems + 7) // 8
+    g = np.arange(groups, dtype=np.uint64)
+    r = philox4x32_10((g & MASK32).astype(np.uint32), (g >> np.uint64(32)).astype(np.uint32),
+                      np.full(groups, site, dtype=np.uint32), np.full(groups, step, dtype=np.uint32),
+                      seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)
+    lanes = np.empty((groups, 8), dtype=np.uint32)
+    for j in range(4):
+        lanes[:, 2 * j] = r[j] & np.uint32(0xFFFF)
+        lanes[:, 2 * j + 1] = r[j] >> np.uint32(16)
+    return (lanes >= thresh_of(p)).reshape(-1)[:n_elems]
