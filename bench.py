@@ -111,7 +111,7 @@ def cpu_oracle_step_time(size, N, L, T, steps, warmup, seed=0):
     times = []
     for i in range(warmup + steps):
         t0 = time.perf_counter()
-        O.train_step(sd, cfg, opt, ids, mask, labels, lr_scale=1.0, clip=1.0)
+        O.train_step(sd, cfg, opt, ids, mask, labels, lr_scale=1.0, clip=1.0, dropout=0.1)
         dt = time.perf_counter() - t0
         if i >= warmup:
             times.append(dt)
@@ -134,7 +134,7 @@ def run_reference(args):
         "steps": steps, "warmup": warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"{args.workload}: FiDT5 t5-{size} train step, n_passages={N}, text_maxlength={L}, "
-                               f"T={T}, dropout=0 (bounded sample: 1 question per step instead of {B})",
+                               f"T={T}, dropout=0.1 (bounded sample: 1 question per step instead of {B})",
                    "parallelism": "cpu"},
         "cpu_baseline": {"value": val, "unit": "samples/s", "cores": cores, "kind": "port",
                          "sample": f"{steps} train steps of 1 question ({N}x{L} tokens) after {warmup} warm-up"},
@@ -317,7 +317,7 @@ def main():
             "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic",
             "config": {"workload": f"{args.workload}: FiDT5 t5-{size} training step (fwd+bwd+clip+AdamW), per-GPU batch "
-                                   f"{B} questions, n_passages={N}, text_maxlength={L}, T={T}, dropout=0",
+                                   f"{B} questions, n_passages={N}, text_maxlength={L}, T={T}, dropout=0.1 (model.train(), Philox masks)",
                        "global_batch": world * B, "parallelism": f"dp{world}",
                        "l2": "step working set (>4 GB of activations) far exceeds the 126 MB L2; batches rotate; no explicit flush",
                        "emb_std": EMB_STD},

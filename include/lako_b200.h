@@ -69,6 +69,11 @@ int lako_ce_fwd_bwd(const float* logits, const int64_t* labels, float* stats, fl
 int lako_cast_f32_to_bf16(const float* in, void* out_bf16, size_t n, void* stream);
 int lako_transpose_bf16(const void* in, void* out, int rows, int cols, int ld_in, int ld_out, void* stream);
 
+/* keep[e] (0/1) of element e of dropout site `site` at (seed, step): the exact Philox4x32-10 mask the kernels
+ * apply in forward and regenerate in backward (lako_b200/philox.py restates it on the host) */
+int lako_dropout_mask(unsigned char* keep, size_t n, unsigned long long seed, unsigned int step, unsigned int site,
+                      float p, void* stream);
+
 /* ---- train step tail: clip_grad_norm_ (train_reader.py:76) + HF AdamW(correct_bias=False)
  *      (src/util.py:225) + bf16 re-cast of the weights, over the flat parameter buffer ------------- */
 int lako_grad_sumsq(const float* g, size_t n, float* out_scalar, void* stream);

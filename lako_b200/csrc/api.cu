@@ -56,6 +56,11 @@ int lako_transpose_bf16(const void* in, void* out, int rows, int cols, int ld_in
   ARCH_GUARD();
   return transpose_bf16(CBF(in), BF(out), rows, cols, ld_in, ld_out, ST(stream));
 }
+int lako_dropout_mask(unsigned char* keep, size_t n, unsigned long long seed, unsigned int step, unsigned int site,
+                      float p, void* stream) {
+  ARCH_GUARD();
+  return dropout_mask(keep, n, seed, step, site, p, ST(stream));
+}
 int lako_grad_sumsq(const float* g, size_t n, float* out, void* stream) {
   ARCH_GUARD();
   return grad_sumsq(g, n, out, ST(stream));

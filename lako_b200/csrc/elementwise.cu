@@ -491,6 +491,22 @@ int cast_f32_to_bf16(const float* in, __nv_bfloat16* out, size_t n, cudaStream_t
   return LAKO_OK;
 }
 
+// keep[e] = dropout keep decision of element e of a site (audit / test entry for the Philox mask)
+__global__ void dropout_mask_kernel(unsigned char* __restrict__ keep, size_t n, const DropSpec ds) {
+  const size_t grp = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (grp * 8 >= n) return;
+  const uint32_t m = ds.thresh ? drop_keep8(ds, grp) : 0xffu;
+  for (int j = 0; j < 8 && grp * 8 + j < n; ++j) keep[grp * 8 + j] = (m >> j) & 1u;
+}
+int dropout_mask(unsigned char* keep, size_t n, unsigned long long seed, unsigned step, unsigned site, float p,
+                 cudaStream_t s) {
+  if (n == 0) return LAKO_OK;
+  const size_t groups = (n + 7) / 8;
+  dropout_mask_kernel<<<static_cast<unsigned>((groups + 255) / 256), 256, 0, s>>>(keep, n, make_drop(seed, step, site, p));
+  LAKO_CHECK_LAUNCH();
+  return LAKO_OK;
+}
+
 // x *= *scalar (device scalar); used to apply d(loss) != 1 to the stored dlogits
 __global__ void scale_bf16_dev_kernel(__nv_bfloat16* __restrict__ x, size_t n, const float* __restrict__ scalar) {
   const float sc = *scalar;

@@ -180,6 +180,13 @@ def _heads(x, cfg):
     return x.view(b, s, cfg.n_heads, cfg.d_kv).transpose(1, 2)
 
 
+_DROP = {"p": 0.0}  # training dropout of the oracle (torch RNG); 0 for every parity run
+
+
+def _drop(x):
+    return F.dropout(x, p=_DROP["p"], training=True) if _DROP["p"] > 0 else x
+
+
 def attention(sd, prefix, cfg, hidden, kv_states, bias_plus_mask, capture=None, cached_kv=None):
     """T5Attention (HF:modeling_t5.py:253-344) / cross_attention_forward (src/model.py:286-349).
 
@@ -195,7 +202,7 @@ def attention(sd, prefix, cfg, hidden, kv_states, bias_plus_mask, capture=None, 
     scores = scores + bias_plus_mask
     if capture is not None:
         capture.append(scores)
-    attn = F.softmax(scores.float(), dim=-1).type_as(scores)
+    attn = _drop(F.softmax(scores.float(), dim=-1).type_as(scores))   # HF:331-332
     out = torch.matmul(attn, v)
     b, _, s, _ = out.shape
     out = out.transpose(1, 2).contiguous().view(b, s, cfg.inner)
@@ -203,13 +210,13 @@ def attention(sd, prefix, cfg, hidden, kv_states, bias_plus_mask, capture=None, 
 
 
 def ffn(sd, prefix, x):
-    h = torch.relu(x @ sd[f"{prefix}.DenseReluDense.wi.weight"].T)
+    h = _drop(torch.relu(x @ sd[f"{prefix}.DenseReluDense.wi.weight"].T))   # HF:92-95
     return h @ sd[f"{prefix}.DenseReluDense.wo.weight"].T
 
 
 def encoder_forward(sd, cfg: T5Dims, ids, mask):
     """T5 encoder stack on (B*N, L) passages.  ids int64, mask bool -> (B*N, L, d)."""
-    x = sd["shared.weight"][ids]
+    x = _drop(sd["shared.weight"][ids])   # HF:734
     L = ids.shape[1]
     table = sd[f"{enc_prefix(0)}.0.SelfAttention.relative_attention_bias.weight"]
     bias = compute_bias(table, L, L, True, cfg).to(x.dtype)
@@ -219,10 +226,10 @@ def encoder_forward(sd, cfg: T5Dims, ids, mask):
         p = enc_prefix(i)
         n = rmsnorm(x, sd[f"{p}.0.layer_norm.weight"], cfg.eps)
         a, _ = attention(sd, f"{p}.0.SelfAttention", cfg, n, n, bias)
-        x = x + a
+        x = x + _drop(a)   # HF:375
         n = rmsnorm(x, sd[f"{p}.1.layer_norm.weight"], cfg.eps)
-        x = x + ffn(sd, f"{p}.1", n)
-    return rmsnorm(x, sd["encoder.encoder.final_layer_norm.weight"], cfg.eps)
+        x = x + _drop(ffn(sd, f"{p}.1", n))   # HF:149
+    return _drop(rmsnorm(x, sd["encoder.encoder.final_layer_norm.weight"], cfg.eps))   # HF:767-768
 
 
 def shift_right(labels):
@@ -236,7 +243,7 @@ def shift_right(labels):
 def decoder_forward(sd, cfg: T5Dims, dec_ids, memory, mem_mask, cache=None, capture=None):
     """T5 decoder stack.  dec_ids (B,T) (T=1 with cache for cached decode), memory (B,M,d),
     mem_mask (B,M) bool.  cache: dict with 'self' (list of (k,v)), 'cross' (list of (k,v)), 'len'."""
-    x = sd["shared.weight"][dec_ids]
+    x = _drop(sd["shared.weight"][dec_ids])
     B, T = dec_ids.shape
     past = 0 if cache is None else cache["len"]
     table = sd[f"{dec_prefix(0)}.0.SelfAttention.relative_attention_bias.weight"]
@@ -263,7 +270,7 @@ def decoder_forward(sd, cfg: T5Dims, dec_ids, memory, mem_mask, cache=None, capt
                 k_all, v_all = k_new, v_new
             cache["self"][i] = (k_all, v_all)
             a, _ = attention(sd, pre, cfg, n, None, self_bias, cached_kv=(k_all, v_all))
-        x = x + a
+        x = x + _drop(a)
         n = rmsnorm(x, sd[f"{p}.1.layer_norm.weight"], cfg.eps)
         cap = None
         if capture is not None and capture[i] is None:
@@ -274,12 +281,12 @@ def decoder_forward(sd, cfg: T5Dims, dec_ids, memory, mem_mask, cache=None, capt
             cache["cross"][i] = kv
         if cap is not None:
             capture[i] = cap[0]
-        x = x + a
+        x = x + _drop(a)
         n = rmsnorm(x, sd[f"{p}.2.layer_norm.weight"], cfg.eps)
-        x = x + ffn(sd, f"{p}.2", n)
+        x = x + _drop(ffn(sd, f"{p}.2", n))
     if cache is not None:
         cache["len"] = total
-    return rmsnorm(x, sd["decoder.final_layer_norm.weight"], cfg.eps)
+    return _drop(rmsnorm(x, sd["decoder.final_layer_norm.weight"], cfg.eps))
 
 
 def lm_logits(sd, cfg, h):
@@ -448,12 +455,17 @@ def unique_params(sd):
     return out
 
 
-def train_step(sd, cfg, opt: HFAdamW, input_ids, attention_mask, labels, lr_scale, clip=1.0):
-    """One iteration of train_reader.py:67-79 on the oracle. `sd` tensors must require grad."""
+def train_step(sd, cfg, opt: HFAdamW, input_ids, attention_mask, labels, lr_scale, clip=1.0, dropout=0.0):
+    """One iteration of train_reader.py:67-79 on the oracle. `sd` tensors must require grad.
+    dropout > 0 reproduces model.train() (p = 0.1 in the reference) with torch's RNG; parity runs use 0."""
     params = opt.params
     for p in params:
         p.grad = None
-    loss, _ = fidt5_forward(sd, cfg, input_ids, attention_mask, labels)
+    _DROP["p"] = dropout
+    try:
+        loss, _ = fidt5_forward(sd, cfg, input_ids, attention_mask, labels)
+    finally:
+        _DROP["p"] = 0.0
     loss.backward()
     grads = [p.grad for p in params]
     gnorm = clip_grad_norm_(grads, clip)

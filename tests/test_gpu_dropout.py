@@ -58,7 +58,7 @@ def test_dropout_changes_train_loss_not_eval():
     l2 = model(**args)[0].item()                     # next step -> different masks
     model.set_dropout_seed(123)
     l1b = model(**args)[0].item()                    # same seed and step -> identical
-    assert l1 == l1b and l1 != l2
+    assert abs(l1 - l1b) < 1e-5 and abs(l1 - l2) > 1e-5   # (loss reduction order is atomic -> last-bit jitter)
     assert abs(l1 - le) > 1e-4 and abs(l1 - le) < 0.5
 
 
@@ -104,27 +104,15 @@ def test_forward_backward_use_same_masks_directional_derivative():
     assert abs((v[0] - v[1]) / (2 * eps) - gn0) < 0.05 * gn0
 
 
-def test_rmsnorm_residual_dropout_matches_philox():
+def test_device_mask_equals_host_restatement():
+    """csrc/common.cuh drop_keep8 == lako_b200/philox.py keep_mask, bit for bit."""
     from lako_b200 import _native as nat
-    from lako_b200.philox import scale_of, thresh_of
-    lib = ctypes.CDLL(nat.LIB_PATH)  # internal C++ launcher is not exported; exercise it through the model instead
-    # residual-dropout site: run one tiny model forward in train mode with every other site's effect removed is not
-    # possible from the ABI, so check the mask through the embedding site, which is observable:
-    from oracle import fidt5_oracle as O
-    model, cfg, sd = _model(0.1)
-    del lib
-    # embedding dropout mask of the DECODER inputs is visible in d(loss)/d(shared.weight) rows: a dropped element of
-    # an embedded token gets exactly zero gradient from that position.  Use a batch whose decoder token ids are unique.
-    ids, mask, labels = O.synth_batch(1, 1, 16, 6, cfg.vocab, seed=9)
-    labels = torch.tensor([[301, 302, 303, 304, 1, -100]])
-    model.train()
-    model.set_dropout_seed(5)
-    model.zero_grad()
-    model(input_ids=ids.cuda(), attention_mask=mask.cuda(), labels=labels.cuda())[0].backward()
-    g = model.shared.weight.grad
-    # decoder inputs = shift_right(labels) = [0, 301, 302, 303, 304, 1]; row 302 is fed at position t=2 only and is
-    # a target at t=1 only (LM-head gradient is dense), so the embedding-path zeros are not observable directly.
-    # Instead verify the restated mask statistically against the kernel via the keep-rate of exact zeros in an
-    # encoder-only quantity: none available -> fall back to consistency (covered by the directional test).
-    assert torch.isfinite(g).all()
-    assert thresh_of(0.1) == 6554 and scale_of(0.0) == 1.0
+    from lako_b200.philox import keep_mask
+    lib = nat.lib()
+    for seed, step, site, n, p in ((1, 1, 0, 1000, 0.1), (0xDEADBEEFCAFE, 77, 16 * 11 + 4, 123457, 0.1),
+                                   (5, 2 ** 31, 3, 4096, 0.25), (9, 9, 9, 64, 0.0)):
+        keep = torch.zeros(n, dtype=torch.uint8, device="cuda")
+        nat.check(lib.lako_dropout_mask(nat.ptr(keep), ctypes.c_size_t(n), ctypes.c_ulonglong(seed), ctypes.c_uint(step),
+                                        ctypes.c_uint(site), ctypes.c_float(p), nat.stream_ptr()))
+        ref = torch.from_numpy(keep_mask(seed, step, site, n, p))
+        assert torch.equal(keep.cpu().bool(), ref), (seed, step, site)

@@ -27,7 +27,7 @@ def _load(path):
     if c.get("eos_alias") is not None:
         sd["shared.weight"][1] = sd["shared.weight"][c["eos_alias"]] * 1.05
     model = FiDT5(FiDT5Config(vocab_size=cfg.vocab, d_model=cfg.d_model, d_ff=cfg.d_ff, num_layers=cfg.n_layers,
-                              num_heads=cfg.n_heads))
+                              num_heads=cfg.n_heads, dropout_rate=0.0))
     model.load_state_dict(sd)
     model = model.cuda()
     return c, cfg, sd, model
@@ -104,7 +104,7 @@ def test_state_dict_roundtrip_and_t5_names(tmp_path):
     cfg = O.T5_TINY
     sd = O.init_state_dict(cfg, seed=3, emb_std=0.3)
     conf = FiDT5Config(vocab_size=cfg.vocab, d_model=cfg.d_model, d_ff=cfg.d_ff, num_layers=cfg.n_layers,
-                       num_heads=cfg.n_heads)
+                       num_heads=cfg.n_heads, dropout_rate=0.0)
     m = FiDT5(conf).cuda()
     m.load_state_dict(sd)
     m.save_pretrained(str(tmp_path))

@@ -13,7 +13,7 @@ pytestmark = pytest.mark.gpu
 def _mk(cfg, sd):
     from lako_b200.model import FiDT5, FiDT5Config
     m = FiDT5(FiDT5Config(vocab_size=cfg.vocab, d_model=cfg.d_model, d_ff=cfg.d_ff, num_layers=cfg.n_layers,
-                          num_heads=cfg.n_heads))
+                          num_heads=cfg.n_heads, dropout_rate=0.0))
     m.load_state_dict(sd)
     return m.cuda()
 
