@@ -69,7 +69,7 @@ int lako_ce_fwd_bwd(const float* logits, const int64_t* labels, float* stats, fl
 int lako_cast_f32_to_bf16(const float* in, void* out_bf16, size_t n, void* stream);
 int lako_transpose_bf16(const void* in, void* out, int rows, int cols, int ld_in, int ld_out, void* stream);
 
-/* keep[e] (0/1) of element e of dropout site `site` at (seed, step): the exact Philox4x32-10 mask the kernels
+/* keep[e] (0/1) of element e of dropout site `site` at (seed, step): the exact Philox4x32-7 mask the kernels
  * apply in forward and regenerate in backward (lako_b200/philox.py restates it on the host) */
 int lako_dropout_mask(unsigned char* keep, size_t n, unsigned long long seed, unsigned int step, unsigned int site,
                       float p, void* stream);
@@ -126,7 +126,7 @@ typedef struct {
   float* logits; /* out: [B*T][vocab] fp32 */
   float* stats;  /* out: stats[0] = sum of token losses, stats[1] = number of non-ignored targets */
   int count_is_set; /* 1: stats[1] already holds the (global, all-reduced) count and stats[0] is zeroed */
-  /* training dropout (HF dropout_rate, 0.1 in the reference; 0 disables).  Masks come from Philox4x32-10 keyed by
+  /* training dropout (HF dropout_rate, 0.1 in the reference; 0 disables).  Masks come from Philox4x32-7 keyed by
    * (seed, step, call site, element) and are regenerated in backward -- pass the same values to both calls. */
   float dropout_p;
   unsigned int dropout_step;

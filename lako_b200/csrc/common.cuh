@@ -300,7 +300,10 @@ __device__ __forceinline__ float warp_max(float v) {
   return v;
 }
 
-// ------------------------------------------------------------------ dropout (Philox4x32-10, counter based)
+// ------------------------------------------------------------------ dropout (Philox4x32-7, counter based)
+// 7 rounds is the smallest Crush-resistant Philox4x32 variant (Salmon et al., SC'11, table 2); dropout
+// needs decorrelated bits, not cryptographic strength, and the rounds are pure issue-slot cost in kernels
+// that are issue-bound (attention softmax).
 // One Philox call decides 8 consecutive elements: element e of a site belongs to group e >> 3 and uses the
 // (e & 7)-th 16-bit lane of the 128 random bits; keep iff lane >= thresh (thresh = round(p * 65536)).
 // The same (seed, step, site, group) is recomputed in backward, so no mask is ever stored.
@@ -320,9 +323,10 @@ __host__ __device__ inline DropSpec make_drop(unsigned long long seed, unsigned 
   d.scale = (p > 0.f) ? 1.f / (1.f - static_cast<float>(d.thresh) / 65536.f) : 1.f;
   return d;
 }
-__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+constexpr int PHILOX_ROUNDS = 7;
+__device__ __forceinline__ uint4 philox4x32(uint4 c, uint2 k) {
 #pragma unroll
-  for (int r = 0; r < 10; ++r) {
+  for (int r = 0; r < PHILOX_ROUNDS; ++r) {
     const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
     const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
     c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
@@ -333,7 +337,7 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
 }
 // 8-bit keep mask (bit j = keep element group*8 + j)
 __device__ __forceinline__ uint32_t drop_keep8(const DropSpec& d, unsigned long long group) {
-  const uint4 r = philox4x32_10(make_uint4(static_cast<uint32_t>(group), static_cast<uint32_t>(group >> 32), d.site, d.step),
+  const uint4 r = philox4x32(make_uint4(static_cast<uint32_t>(group), static_cast<uint32_t>(group >> 32), d.site, d.step),
                                 make_uint2(static_cast<uint32_t>(d.seed), static_cast<uint32_t>(d.seed >> 32)));
   const uint32_t w[4] = {r.x, r.y, r.z, r.w};
   uint32_t m = 0;

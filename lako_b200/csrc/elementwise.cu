@@ -29,6 +29,14 @@ __device__ __forceinline__ uint32_t keep4(const DropSpec& ds, size_t e) {
   const uint32_t m = drop_keep8(ds, e >> 3);
   return (e & 4) ? (m >> 4) : (m & 15u);
 }
+// Same, for warps whose lanes 2j / 2j+1 hold the two float4 halves of one 8-element group (all 32 lanes must
+// call it): the even lane runs Philox, the odd lane takes its half by shuffle.
+__device__ __forceinline__ uint32_t keep4_pair(const DropSpec& ds, size_t e, int lane) {
+  uint32_t m = 0;
+  if ((lane & 1) == 0) m = drop_keep8(ds, e >> 3);
+  m = __shfl_sync(0xffffffffu, m, lane & ~1);
+  return (lane & 1) ? (m >> 4) : (m & 15u);
+}
 
 __global__ void __launch_bounds__(256) rmsnorm_fwd_kernel(const float* x, const __nv_bfloat16* __restrict__ delta,
                                                            float* x_out, const float* __restrict__ w,
@@ -53,7 +61,7 @@ __global__ void __launch_bounds__(256) rmsnorm_fwd_kernel(const float* x, const 
         const uint2 dv = *reinterpret_cast<const uint2*>(dr + c);
         float4 a = make_float4(bf16_lo(dv.x), bf16_hi(dv.x), bf16_lo(dv.y), bf16_hi(dv.y));
         if (dd.thresh) {  // dropout on the sub-layer output before the residual add (HF:375, :149)
-          const uint32_t k = keep4(dd, static_cast<size_t>(warp) * d + c);
+          const uint32_t k = keep4_pair(dd, static_cast<size_t>(warp) * d + c, lane);
           a.x = (k & 1) ? a.x * dd.scale : 0.f;
           a.y = (k & 2) ? a.y * dd.scale : 0.f;
           a.z = (k & 4) ? a.z * dd.scale : 0.f;
@@ -82,7 +90,7 @@ __global__ void __launch_bounds__(256) rmsnorm_fwd_kernel(const float* x, const 
         const float4 wv = *reinterpret_cast<const float4*>(w + c);
         float4 y = make_float4(wv.x * (xv[i].x * rs), wv.y * (xv[i].y * rs), wv.z * (xv[i].z * rs), wv.w * (xv[i].w * rs));
         if (od.thresh) {  // dropout after the final layer norm of a stack (HF:767-768)
-          const uint32_t k = keep4(od, static_cast<size_t>(warp) * d + c);
+          const uint32_t k = keep4_pair(od, static_cast<size_t>(warp) * d + c, lane);
           y.x = (k & 1) ? y.x * od.scale : 0.f;
           y.y = (k & 2) ? y.y * od.scale : 0.f;
           y.z = (k & 4) ? y.z * od.scale : 0.f;
@@ -153,7 +161,7 @@ __global__ void __launch_bounds__(256, 2) rmsnorm_bwd_kernel(const __nv_bfloat16
       xv[i] = *reinterpret_cast<const float4*>(xr + c);
       dyp[i] = *reinterpret_cast<const uint2*>(dyr + c);
       if (yd.thresh) {  // gradient of the post-norm dropout: zero the dropped elements (the 1/(1-p) is in dy_scale)
-        const uint32_t k = keep4(yd, static_cast<size_t>(row) * d + c);
+        const uint32_t k = keep4_pair(yd, static_cast<size_t>(row) * d + c, lane);
         dyp[i].x &= ((k & 1) ? 0x0000ffffu : 0u) | ((k & 2) ? 0xffff0000u : 0u);
         dyp[i].y &= ((k & 4) ? 0x0000ffffu : 0u) | ((k & 8) ? 0xffff0000u : 0u);
       }
@@ -192,7 +200,7 @@ __global__ void __launch_bounds__(256, 2) rmsnorm_bwd_kernel(const __nv_bfloat16
       *reinterpret_cast<float4*>(drr + c) = o;
       if (dres_bf16) {
         if (bd.thresh) {  // the bf16 copy feeds the previous sub-layer's output GEMMs: apply ITS dropout mask
-          const uint32_t k = keep4(bd, static_cast<size_t>(row) * d + c);
+          const uint32_t k = keep4_pair(bd, static_cast<size_t>(row) * d + c, lane);
           o.x = (k & 1) ? o.x * bd.scale : 0.f;
           o.y = (k & 2) ? o.y * bd.scale : 0.f;
           o.z = (k & 4) ? o.z * bd.scale : 0.f;

@@ -151,16 +151,20 @@ __global__ void __launch_bounds__(128) xattn_fwd_mma_kernel(const XMParams p) {
       lrow[0] += e[0] + e[1];
       lrow[1] += e[2] + e[3];
       if (p.drop.thresh) {
+        // one Philox call covers the 8 keys of this n-tile for one query row; the quad (t4 = 0..3) shares it:
+        // lane t4 == 0 draws row g, lane t4 == 1 draws row g + 8
         const unsigned long long G = (p.M + 7) >> 3, kg = (k0 + kb + nt * 8) >> 3;
-#pragma unroll
-        for (int r = 0; r < 2; ++r) {
-          const int t = mt * 16 + g + r * 8;
-          if (t < p.T) {
-            const uint32_t k = drop_keep8(p.drop, (static_cast<unsigned long long>(b * p.H + h) * p.T + t) * G + kg);
-            e[r * 2 + 0] = ((k >> (t4 * 2)) & 1u) ? e[r * 2 + 0] * p.drop.scale : 0.f;
-            e[r * 2 + 1] = ((k >> (t4 * 2 + 1)) & 1u) ? e[r * 2 + 1] * p.drop.scale : 0.f;
-          }
+        uint32_t mine = 0xffu;
+        if (t4 < 2) {
+          const int t = mt * 16 + g + t4 * 8;
+          if (t < p.T) mine = drop_keep8(p.drop, (static_cast<unsigned long long>(b * p.H + h) * p.T + t) * G + kg);
         }
+        const uint32_t kr0 = __shfl_sync(0xffffffffu, mine, lane & ~3);
+        const uint32_t kr1 = __shfl_sync(0xffffffffu, mine, (lane & ~3) + 1);
+        e[0] = ((kr0 >> (t4 * 2)) & 1u) ? e[0] * p.drop.scale : 0.f;
+        e[1] = ((kr0 >> (t4 * 2 + 1)) & 1u) ? e[1] * p.drop.scale : 0.f;
+        e[2] = ((kr1 >> (t4 * 2)) & 1u) ? e[2] * p.drop.scale : 0.f;
+        e[3] = ((kr1 >> (t4 * 2 + 1)) & 1u) ? e[3] * p.drop.scale : 0.f;
       }
       pa[nt >> 1][(nt & 1) * 2 + 0] = pack_bf16x2(e[0], e[1]);
       pa[nt >> 1][(nt & 1) * 2 + 1] = pack_bf16x2(e[2], e[3]);
@@ -321,20 +325,23 @@ __global__ void __launch_bounds__(128) xattn_bwd_mma_kernel(const XMParams p) {
         float e00 = dpt[nt][0], e01 = dpt[nt][1], e10 = dpt[nt][2], e11 = dpt[nt][3];
         float q00 = p00, q01 = p01, q10 = p10, q11 = p11;  // dropped copies feed dV = P_drop^T dO
         if (p.drop.thresh) {
+          // masks of (query t | t+1) x (key group kg | kg+1): four Philox calls shared by the 8 lanes that hold
+          // the same query columns (same t4); lane g = 0..3 draws one each
           const unsigned long long G = (p.M + 7) >> 3, kg = (k0 + key0) >> 3, rb = static_cast<unsigned long long>(b * p.H + h) * p.T;
           const float sc = p.drop.scale;
-          if (t < p.T) {
-            const uint32_t ka = drop_keep8(p.drop, (rb + t) * G + kg), kb2 = drop_keep8(p.drop, (rb + t) * G + kg + 1);
-            const bool k0b = (ka >> g) & 1u, k1b = (kb2 >> g) & 1u;
-            e00 = k0b ? e00 * sc : 0.f; q00 = k0b ? q00 * sc : 0.f;
-            e10 = k1b ? e10 * sc : 0.f; q10 = k1b ? q10 * sc : 0.f;
+          uint32_t mine = 0xffu;
+          if (g < 4) {
+            const int tt = t + (g >> 1);
+            if (tt < p.T) mine = drop_keep8(p.drop, (rb + tt) * G + kg + (g & 1));
           }
-          if (t + 1 < p.T) {
-            const uint32_t ka = drop_keep8(p.drop, (rb + t + 1) * G + kg), kb2 = drop_keep8(p.drop, (rb + t + 1) * G + kg + 1);
-            const bool k0b = (ka >> g) & 1u, k1b = (kb2 >> g) & 1u;
-            e01 = k0b ? e01 * sc : 0.f; q01 = k0b ? q01 * sc : 0.f;
-            e11 = k1b ? e11 * sc : 0.f; q11 = k1b ? q11 * sc : 0.f;
-          }
+          const uint32_t m00 = __shfl_sync(0xffffffffu, mine, 0 * 4 + t4), m01 = __shfl_sync(0xffffffffu, mine, 1 * 4 + t4);
+          const uint32_t m10 = __shfl_sync(0xffffffffu, mine, 2 * 4 + t4), m11 = __shfl_sync(0xffffffffu, mine, 3 * 4 + t4);
+          const bool a00 = (m00 >> g) & 1u, a10 = (m01 >> g) & 1u;  // query t  : keys g, g+8
+          const bool a01 = (m10 >> g) & 1u, a11 = (m11 >> g) & 1u;  // query t+1: keys g, g+8
+          e00 = a00 ? e00 * sc : 0.f; q00 = a00 ? q00 * sc : 0.f;
+          e10 = a10 ? e10 * sc : 0.f; q10 = a10 ? q10 * sc : 0.f;
+          e01 = a01 ? e01 * sc : 0.f; q01 = a01 ? q01 * sc : 0.f;
+          e11 = a11 ? e11 * sc : 0.f; q11 = a11 ? q11 * sc : 0.f;
         }
         const float s00 = p00 * (e00 - d0), s01 = p01 * (e01 - d1);
         const float s10 = p10 * (e10 - d0), s11 = p11 * (e11 - d1);

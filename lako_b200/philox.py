@@ -1,4 +1,4 @@
-"""Host restatement of the kernels' counter-based dropout mask (csrc/common.cuh: philox4x32_10 / drop_keep8),
+"""Host restatement of the kernels' counter-based dropout mask (csrc/common.cuh: philox4x32 (7 rounds) / drop_keep8),
 used by the tests to rebuild the exact keep-masks a kernel applied and by users who need to audit them."""
 import numpy as np
 
@@ -7,12 +7,15 @@ W0, W1 = np.uint32(0x9E3779B9), np.uint32(0xBB67AE85)
 MASK32 = np.uint64(0xFFFFFFFF)
 
 
-def philox4x32_10(c0, c1, c2, c3, k0, k1):
+ROUNDS = 7
+
+
+def philox4x32(c0, c1, c2, c3, k0, k1):
     c0, c1, c2, c3 = (np.asarray(x, dtype=np.uint32) for x in (c0, c1, c2, c3))
     k0 = np.uint32(k0)
     k1 = np.uint32(k1)
     with np.errstate(over="ignore"):
-        for _ in range(10):
+        for _ in range(ROUNDS):
             p0 = M0 * c0.astype(np.uint64)
             p1 = M1 * c2.astype(np.uint64)
             hi0, lo0 = (p0 >> np.uint64(32)).astype(np.uint32), (p0 & MASK32).astype(np.uint32)
@@ -37,7 +40,7 @@ def keep_mask(seed, step, site, n_elems, p):
         return np.ones(n_elems, dtype=bool)
     groups = (n_elems + 7) // 8
     g = np.arange(groups, dtype=np.uint64)
-    r = philox4x32_10((g & MASK32).astype(np.uint32), (g >> np.uint64(32)).astype(np.uint32),
+    r = philox4x32((g & MASK32).astype(np.uint32), (g >> np.uint64(32)).astype(np.uint32),
                       np.full(groups, site, dtype=np.uint32), np.full(groups, step, dtype=np.uint32),
                       seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)
     lanes = np.empty((groups, 8), dtype=np.uint32)
