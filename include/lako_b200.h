@@ -43,7 +43,10 @@ int lako_check_device(void); /* 0 iff the current device is sm_100 */
  * cross-attention K/V projection src/model.py:311-312 ; and torch autograd's dgrad/wgrad for them.
  *  a_mn/b_mn: 0 = operand stored row-major [rows][K] (ld >= K), 1 = stored row-major [K][rows].
  *  epi: 0 bf16 store, 1 bf16 ReLU store, 2 fp32 store, 3 fp32 atomic accumulate (split-K allowed),
- *       4 bf16 store masked by aux[m,n] > 0 (ReLU backward).  bn: 0 = auto, 128 or 256. */
+ *       4 bf16 store masked by aux[m,n] > 0 (ReLU backward, aux bf16 [M][ld_aux]),
+ *       5 bf16 store masked by a 1-bit/element mask (aux uint8 [M][ld_aux bytes], bit n&7 of byte n>>3);
+ *       epi 1 with aux != NULL also WRITES that bit mask (output > 0).  bn: 0 auto, 128/256 single-CTA tile
+ *       width, 512 = CTA-pair kernel (256x256 per 2-CTA cluster). */
 int lako_gemm_bf16(const void* A, const void* B, void* C, int M, int N, int K, int lda, int ldb, int ldc, int a_mn,
                    int b_mn, int epi, float alpha, const void* aux, int ld_aux, int splitk, int bn, void* stream);
 

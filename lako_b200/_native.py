@@ -48,7 +48,7 @@ c_int = ctypes.c_int
 c_float = ctypes.c_float
 c_size_t = ctypes.c_size_t
 
-EPI_BF16, EPI_BF16_RELU, EPI_F32, EPI_F32_ATOMIC, EPI_BF16_MASK = range(5)
+EPI_BF16, EPI_BF16_RELU, EPI_F32, EPI_F32_ATOMIC, EPI_BF16_MASK, EPI_BF16_BITMASK = range(6)
 
 
 def gemm(A, B, C, M, N, K, lda, ldb, ldc, a_mn=False, b_mn=False, epi=EPI_BF16, alpha=1.0, aux=None, ld_aux=0,

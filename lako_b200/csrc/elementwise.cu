@@ -29,6 +29,28 @@ __device__ __forceinline__ uint32_t keep4(const DropSpec& ds, size_t e) {
   const uint32_t m = drop_keep8(ds, e >> 3);
   return (e & 4) ? (m >> 4) : (m & 15u);
 }
+// Keep-nibbles for a whole row handled as float4 slots c = (i*32 + lane)*4, i < nvec (all 32 lanes must call).
+// Lanes 2j / 2j+1 hold the two halves of one 8-element Philox group in every slot; for each PAIR of slots the
+// even lane draws slot i's group and the odd lane draws slot i+1's group at the same time, then they swap halves
+// by shuffle: one Philox call per lane per two slots, no divergent idle lanes.
+template <int MAXV>
+__device__ __forceinline__ void keep_row(const DropSpec& ds, size_t row_elem0, int lane, int nvec, uint32_t (&kk)[MAXV]) {
+#pragma unroll
+  for (int i = 0; i < MAXV; i += 2) {
+    if (i < nvec) {
+      int it = i + (lane & 1);
+      if (it >= nvec) it = i;
+      const size_t e = row_elem0 + static_cast<size_t>((it * 32 + (lane & ~1)) * 4);
+      const uint32_t m = drop_keep8(ds, e >> 3);
+      const uint32_t mo = __shfl_xor_sync(0xffffffffu, m, 1);
+      const uint32_t mi = (lane & 1) ? mo : m;                              // slot i   (drawn by the even lane)
+      const uint32_t mi1 = (i + 1 < nvec) ? ((lane & 1) ? m : mo) : 0xffu;  // slot i+1 (drawn by the odd lane)
+      kk[i] = (lane & 1) ? (mi >> 4) : (mi & 15u);
+      if (i + 1 < MAXV) kk[i + 1] = (lane & 1) ? (mi1 >> 4) : (mi1 & 15u);
+    }
+  }
+}
+
 // Same, for warps whose lanes 2j / 2j+1 hold the two float4 halves of one 8-element group (all 32 lanes must
 // call it): the even lane runs Philox, the odd lane takes its half by shuffle.
 __device__ __forceinline__ uint32_t keep4_pair(const DropSpec& ds, size_t e, int lane) {
@@ -51,6 +73,9 @@ __global__ void __launch_bounds__(256) rmsnorm_fwd_kernel(const float* x, const 
   const float* xr = x + static_cast<size_t>(warp) * d;
   float* xo = x_out ? x_out + static_cast<size_t>(warp) * d : nullptr;
   const __nv_bfloat16* dr = delta ? delta + static_cast<size_t>(warp) * d : nullptr;
+  uint32_t kdd[NORM_MAX_VEC], kod[NORM_MAX_VEC];
+  if (dr && dd.thresh) keep_row<NORM_MAX_VEC>(dd, static_cast<size_t>(warp) * d, lane, nvec, kdd);
+  if (out && od.thresh) keep_row<NORM_MAX_VEC>(od, static_cast<size_t>(warp) * d, lane, nvec, kod);
   float ss = 0.f;
 #pragma unroll
   for (int i = 0; i < NORM_MAX_VEC; ++i) {
@@ -61,7 +86,7 @@ __global__ void __launch_bounds__(256) rmsnorm_fwd_kernel(const float* x, const 
         const uint2 dv = *reinterpret_cast<const uint2*>(dr + c);
         float4 a = make_float4(bf16_lo(dv.x), bf16_hi(dv.x), bf16_lo(dv.y), bf16_hi(dv.y));
         if (dd.thresh) {  // dropout on the sub-layer output before the residual add (HF:375, :149)
-          const uint32_t k = keep4_pair(dd, static_cast<size_t>(warp) * d + c, lane);
+          const uint32_t k = kdd[i];
           a.x = (k & 1) ? a.x * dd.scale : 0.f;
           a.y = (k & 2) ? a.y * dd.scale : 0.f;
           a.z = (k & 4) ? a.z * dd.scale : 0.f;
@@ -90,7 +115,7 @@ __global__ void __launch_bounds__(256) rmsnorm_fwd_kernel(const float* x, const 
         const float4 wv = *reinterpret_cast<const float4*>(w + c);
         float4 y = make_float4(wv.x * (xv[i].x * rs), wv.y * (xv[i].y * rs), wv.z * (xv[i].z * rs), wv.w * (xv[i].w * rs));
         if (od.thresh) {  // dropout after the final layer norm of a stack (HF:767-768)
-          const uint32_t k = keep4_pair(od, static_cast<size_t>(warp) * d + c, lane);
+          const uint32_t k = kod[i];
           y.x = (k & 1) ? y.x * od.scale : 0.f;
           y.y = (k & 2) ? y.y * od.scale : 0.f;
           y.z = (k & 4) ? y.z * od.scale : 0.f;
@@ -155,13 +180,16 @@ __global__ void __launch_bounds__(256, 2) rmsnorm_bwd_kernel(const __nv_bfloat16
     float* drr = dres + static_cast<size_t>(row) * d;
     float4 xv[NV];
     uint2 dyp[NV];
+    uint32_t kyd[NV], kbd[NV];
+    if (yd.thresh) keep_row<NV>(yd, static_cast<size_t>(row) * d, lane, NV, kyd);
+    if (dres_bf16 && bd.thresh) keep_row<NV>(bd, static_cast<size_t>(row) * d, lane, NV, kbd);
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       const int c = (i * 32 + lane) * 4;
       xv[i] = *reinterpret_cast<const float4*>(xr + c);
       dyp[i] = *reinterpret_cast<const uint2*>(dyr + c);
       if (yd.thresh) {  // gradient of the post-norm dropout: zero the dropped elements (the 1/(1-p) is in dy_scale)
-        const uint32_t k = keep4_pair(yd, static_cast<size_t>(row) * d + c, lane);
+        const uint32_t k = kyd[i];
         dyp[i].x &= ((k & 1) ? 0x0000ffffu : 0u) | ((k & 2) ? 0xffff0000u : 0u);
         dyp[i].y &= ((k & 4) ? 0x0000ffffu : 0u) | ((k & 8) ? 0xffff0000u : 0u);
       }
@@ -200,7 +228,7 @@ __global__ void __launch_bounds__(256, 2) rmsnorm_bwd_kernel(const __nv_bfloat16
       *reinterpret_cast<float4*>(drr + c) = o;
       if (dres_bf16) {
         if (bd.thresh) {  // the bf16 copy feeds the previous sub-layer's output GEMMs: apply ITS dropout mask
-          const uint32_t k = keep4_pair(bd, static_cast<size_t>(row) * d + c, lane);
+          const uint32_t k = kbd[i];
           o.x = (k & 1) ? o.x * bd.scale : 0.f;
           o.y = (k & 2) ? o.y * bd.scale : 0.f;
           o.z = (k & 4) ? o.z * bd.scale : 0.f;

@@ -46,7 +46,7 @@ struct GemmParams {
 template <int BN, int EPI>
 __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t t_acc, uint8_t* sStage, int m0, int n0,
                                               int q, int lane) {
-  if constexpr (EPI == EPI_BF16 || EPI == EPI_BF16_RELU || EPI == EPI_BF16_MASK) {
+  if constexpr (EPI == EPI_BF16 || EPI == EPI_BF16_RELU || EPI == EPI_BF16_MASK || EPI == EPI_BF16_BITMASK) {
     // bf16 output: TMEM (thread = row) -> registers -> per-warp swizzled smem -> coalesced 16 B stores
     // (each store instruction writes four full 128 B row segments)
     uint8_t* stg = sStage + q * 4096;
@@ -71,6 +71,15 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t t_ac
       uint32_t r0[32], r1[32];
       tmem_ld_32x32(t_acc + g * 64, r0);
       tmem_ld_32x32(t_acc + g * 64 + 32, r1);
+      // 1 bit / element ReLU-activity mask, 8 bytes per thread-row per 64-column group: written by the ReLU
+      // epilogue (aux = uint8 [M][ld_aux bytes]) and consumed by the dgrad epilogue instead of re-reading h
+      uint2 bits = make_uint2(0u, 0u);
+      if constexpr (EPI == EPI_BF16_BITMASK) {
+        const int brow = m0 + q * 32 + lane;
+        if (brow < p.M)
+          bits = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const unsigned char*>(p.aux) +
+                                                      static_cast<size_t>(brow) * p.ld_aux + (col0 >> 3)));
+      }
       tmem_ld_wait();
 #pragma unroll
       for (int u = 0; u < 8; ++u) {
@@ -89,6 +98,18 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t t_ac
 #pragma unroll
             for (int i = 0; i < 8; ++i) v[i] = ((k >> i) & 1u) ? v[i] * p.drop.scale : 0.f;
           }
+          if (p.aux != nullptr) {
+            uint32_t byte = 0;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) byte |= (v[i] > 0.f ? 1u : 0u) << i;
+            if (u < 4) bits.x |= byte << (8 * u);
+            else bits.y |= byte << (8 * (u - 4));
+          }
+        }
+        if constexpr (EPI == EPI_BF16_BITMASK) {
+          const uint32_t byte = ((u < 4) ? (bits.x >> (8 * u)) : (bits.y >> (8 * (u - 4)))) & 0xffu;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) v[i] = ((byte >> i) & 1u) ? v[i] : 0.f;
         }
         uint4 w;
         w.x = pack_bf16x2(v[0], v[1]);
@@ -96,6 +117,12 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t t_ac
         w.z = pack_bf16x2(v[4], v[5]);
         w.w = pack_bf16x2(v[6], v[7]);
         *reinterpret_cast<uint4*>(stg + lane * 128 + ((u ^ (lane & 7)) << 4)) = w;
+      }
+      if constexpr (EPI == EPI_BF16_RELU) {
+        const int brow = m0 + q * 32 + lane;
+        if (p.aux != nullptr && brow < p.M && col0 + 64 <= p.N)
+          *reinterpret_cast<uint2*>(reinterpret_cast<unsigned char*>(const_cast<void*>(p.aux)) +
+                                    static_cast<size_t>(brow) * p.ld_aux + (col0 >> 3)) = bits;
       }
       __syncwarp();
       const int unit = lane & 7;
@@ -519,6 +546,7 @@ static int dispatch_epi2(int epi, const CUtensorMap& tmA, const CUtensorMap& tmB
     case EPI_F32: return launch_gemm2<A_MN, B_MN, EPI_F32>(tmA, tmB, p, s);
     case EPI_F32_ATOMIC: return launch_gemm2<A_MN, B_MN, EPI_F32_ATOMIC>(tmA, tmB, p, s);
     case EPI_BF16_MASK: return launch_gemm2<A_MN, B_MN, EPI_BF16_MASK>(tmA, tmB, p, s);
+    case EPI_BF16_BITMASK: return launch_gemm2<A_MN, B_MN, EPI_BF16_BITMASK>(tmA, tmB, p, s);
   }
   set_last_error("unknown epilogue", __FILE__, __LINE__);
   return LAKO_ERR_BAD_ARG;
@@ -561,6 +589,7 @@ static int dispatch_epi(int epi, const CUtensorMap& tmA, const CUtensorMap& tmB,
     case EPI_F32: return launch_gemm<BN, A_MN, B_MN, EPI_F32>(tmA, tmB, p, s);
     case EPI_F32_ATOMIC: return launch_gemm<BN, A_MN, B_MN, EPI_F32_ATOMIC>(tmA, tmB, p, s);
     case EPI_BF16_MASK: return launch_gemm<BN, A_MN, B_MN, EPI_BF16_MASK>(tmA, tmB, p, s);
+    case EPI_BF16_BITMASK: return launch_gemm<BN, A_MN, B_MN, EPI_BF16_BITMASK>(tmA, tmB, p, s);
   }
   set_last_error("unknown epilogue", __FILE__, __LINE__);
   return LAKO_ERR_BAD_ARG;
@@ -586,9 +615,11 @@ int gemm_bf16(const void* A, const void* B, void* C, int M, int N, int K, int ld
   if (rc) return rc;
   LAKO_REQUIRE(M > 0 && N > 0 && K > 0, LAKO_ERR_BAD_ARG);
   LAKO_REQUIRE(lda % 8 == 0 && ldb % 8 == 0, LAKO_ERR_BAD_ARG);
-  LAKO_REQUIRE(epi >= 0 && epi <= 4, LAKO_ERR_BAD_ARG);
-  LAKO_REQUIRE(epi != EPI_BF16_MASK || aux != nullptr, LAKO_ERR_BAD_ARG);
-  const bool out_bf16 = (epi == EPI_BF16 || epi == EPI_BF16_RELU || epi == EPI_BF16_MASK);
+  LAKO_REQUIRE(epi >= 0 && epi <= 5, LAKO_ERR_BAD_ARG);
+  LAKO_REQUIRE((epi != EPI_BF16_MASK && epi != EPI_BF16_BITMASK) || aux != nullptr, LAKO_ERR_BAD_ARG);
+  const bool out_bf16 = (epi == EPI_BF16 || epi == EPI_BF16_RELU || epi == EPI_BF16_MASK || epi == EPI_BF16_BITMASK);
+  if (epi == EPI_BF16_BITMASK || (epi == EPI_BF16_RELU && aux != nullptr))
+    LAKO_REQUIRE(N % 64 == 0 && ld_aux % 8 == 0 && (reinterpret_cast<uintptr_t>(aux) & 7) == 0, LAKO_ERR_BAD_ARG);
   LAKO_REQUIRE((reinterpret_cast<uintptr_t>(C) & 15) == 0 && ldc % (out_bf16 ? 8 : 4) == 0, LAKO_ERR_BAD_ARG);
   LAKO_REQUIRE(!out_bf16 || N % 8 == 0, LAKO_ERR_UNSUPPORTED);  // bf16 epilogue stores 8-element (16 B) units
   if (epi == EPI_BF16_MASK)

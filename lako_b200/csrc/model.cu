@@ -76,10 +76,12 @@ struct Bump {
 typedef __nv_bfloat16 bf16;
 
 struct EncLayerAct {
+  unsigned char* hbits;  // ReLU-activity bitmask [tokens][d_ff/8]
   bf16 *n_a, *qkv, *ao, *n_f, *h;
   float *lse, *rstd_a, *rstd_f;
 };
 struct DecLayerAct {
+  unsigned char* hbits;
   bf16 *n_s, *qkv, *ao, *n_c, *q, *xo, *n_f, *h;
   float *probs, *lse, *rstd_s, *rstd_c, *rstd_f;
 };
@@ -143,6 +145,7 @@ void carve(const lako_dims& dm, int B, int N, int L, int T, int mode, void* base
     a.ao = b.take<bf16>(Mt * inner);
     a.n_f = b.take<bf16>(Mt * d);
     a.h = b.take<bf16>(Mt * ff);
+    a.hbits = b.take<unsigned char>(Mt * ff / 8);
     a.lse = b.take<float>(static_cast<size_t>(w.P) * H * L);
     a.rstd_a = b.take<float>(Mt);
     a.rstd_f = b.take<float>(Mt);
@@ -188,6 +191,7 @@ void carve(const lako_dims& dm, int B, int N, int L, int T, int mode, void* base
     a.xo = b.take<bf16>(BT * inner);
     a.n_f = b.take<bf16>(BT * d);
     a.h = b.take<bf16>(BT * ff);
+    a.hbits = b.take<unsigned char>(BT * ff / 8);
     a.probs = b.take<float>(static_cast<size_t>(B) * H * T * T);
     a.lse = b.take<float>(static_cast<size_t>(B) * H * T);
     a.rstd_s = b.take<float>(BT);
@@ -237,13 +241,14 @@ void carve(const lako_dims& dm, int B, int N, int L, int T, int mode, void* base
 
 // y[M,N] = x[M,K] W[N,K]^T
 inline int lin_fwd(const bf16* x, const bf16* W, void* y, int M, int N, int K, int epi, float alpha, cudaStream_t s,
-                   DropSpec drop = DropSpec{}) {
-  return gemm_bf16(x, W, y, M, N, K, K, K, N, 0, 0, epi, alpha, nullptr, 0, 1, 0, s, drop);
+                   DropSpec drop = DropSpec{}, unsigned char* relu_bits = nullptr) {
+  return gemm_bf16(x, W, y, M, N, K, K, K, N, 0, 0, epi, alpha, relu_bits, N / 8, 1, 0, s, drop);
 }
 // dx[M,K] = dy[M,N] W[N,K]   (optionally masked by aux > 0)
-inline int lin_dgrad(const bf16* dy, const bf16* W, bf16* dx, int M, int N, int K, const bf16* relu_aux, float alpha,
-                     cudaStream_t s) {
-  return gemm_bf16(dy, W, dx, M, K, N, N, K, K, 0, 1, relu_aux ? EPI_BF16_MASK : EPI_BF16, alpha, relu_aux, K, 1, 0, s);
+inline int lin_dgrad(const bf16* dy, const bf16* W, bf16* dx, int M, int N, int K, const unsigned char* relu_bits,
+                     float alpha, cudaStream_t s) {
+  return gemm_bf16(dy, W, dx, M, K, N, N, K, K, 0, 1, relu_bits ? EPI_BF16_BITMASK : EPI_BF16, alpha, relu_bits, K / 8, 1,
+                   0, s);
 }
 // dW[N,K] += alpha * dy[M,N]^T x[M,K]
 inline int lin_wgrad(const bf16* dy, const bf16* x, float* dW, int M, int N, int K, float alpha, cudaStream_t s) {
@@ -308,7 +313,7 @@ int encode(const Ptrs& p, const lako_fidt5* m, Work& w, const long long* ids, co
     RC(lin_fwd(a.ao, p.wb + p.lo.enc_o[l], w.delta_enc, Mt, d, inner, EPI_BF16, 1.f, s));
     RC(rmsnorm_fwd(w.X[2 * l], w.delta_enc, w.X[2 * l + 1], p.wf + p.lo.enc_ln1[l], a.n_f, a.rstd_f, Mt, d, p.eps, 1.f,
                    s, dr(l, E_O)));
-    RC(lin_fwd(a.n_f, p.wb + p.lo.enc_wi[l], a.h, Mt, ff, d, EPI_BF16_RELU, 1.f, s, dr(l, E_RELU)));
+    RC(lin_fwd(a.n_f, p.wb + p.lo.enc_wi[l], a.h, Mt, ff, d, EPI_BF16_RELU, 1.f, s, dr(l, E_RELU), a.hbits));
     RC(lin_fwd(a.h, p.wb + p.lo.enc_wo[l], w.delta_enc, Mt, d, ff, EPI_BF16, 1.f, s));
   }
   RC(rmsnorm_fwd(w.X[2 * nl - 1], w.delta_enc, w.X[2 * nl], p.wf + p.lo.enc_final_ln, w.mem, w.rstd_enc_final, Mt, d,
@@ -366,7 +371,7 @@ extern "C" int lako_fidt5_forward(const lako_fidt5* m, const lako_batch* bt, int
     RC(lin_fwd(a.xo, p.wb + p.lo.dec_xo[l], w.delta_dec, BT, d, inner, EPI_BF16, 1.f, s));
     RC(rmsnorm_fwd(w.Y[3 * l + 1], w.delta_dec, w.Y[3 * l + 2], p.wf + p.lo.dec_ln2[l], a.n_f, a.rstd_f, BT, d, p.eps,
                    1.f, s, dr(l, D_XO)));
-    RC(lin_fwd(a.n_f, p.wb + p.lo.dec_wi[l], a.h, BT, ff, d, EPI_BF16_RELU, 1.f, s, dr(l, D_RELU)));
+    RC(lin_fwd(a.n_f, p.wb + p.lo.dec_wi[l], a.h, BT, ff, d, EPI_BF16_RELU, 1.f, s, dr(l, D_RELU), a.hbits));
     RC(lin_fwd(a.h, p.wb + p.lo.dec_wo[l], w.delta_dec, BT, d, ff, EPI_BF16, 1.f, s));
   }
   RC(rmsnorm_fwd(w.Y[3 * nl - 1], w.delta_dec, w.Y[3 * nl], p.wf + p.lo.dec_final_ln, w.hn, w.rstd_dec_final, BT, d,
@@ -413,7 +418,7 @@ extern "C" int lako_fidt5_backward(const lako_fidt5* m, const lako_batch* bt, co
   for (int l = nl - 1; l >= 0; --l) {
     DecLayerAct& a = w.dec[l];
     // FFN
-    RC(lin_dgrad(w.dres_dec_b, p.wb + p.lo.dec_wo[l], w.dh_dec, BT, d, ff, a.h, dsc, s));
+    RC(lin_dgrad(w.dres_dec_b, p.wb + p.lo.dec_wo[l], w.dh_dec, BT, d, ff, a.hbits, dsc, s));
     RC(lin_wgrad(w.dres_dec_b, a.h, g + p.lo.dec_wo[l], BT, d, ff, 1.f, s));
     RC(lin_dgrad(w.dh_dec, p.wb + p.lo.dec_wi[l], w.dn_dec, BT, ff, d, nullptr, 1.f, s));
     RC(lin_wgrad(w.dh_dec, a.n_f, g + p.lo.dec_wi[l], BT, ff, d, 1.f, s));
@@ -450,7 +455,7 @@ extern "C" int lako_fidt5_backward(const lako_fidt5* m, const lako_batch* bt, co
   // ---- encoder layers
   for (int l = nl - 1; l >= 0; --l) {
     EncLayerAct& a = w.enc[l];
-    RC(lin_dgrad(w.dres_enc_b, p.wb + p.lo.enc_wo[l], w.dh_enc, Mt, d, ff, a.h, dsc, s));
+    RC(lin_dgrad(w.dres_enc_b, p.wb + p.lo.enc_wo[l], w.dh_enc, Mt, d, ff, a.hbits, dsc, s));
     RC(lin_wgrad(w.dres_enc_b, a.h, g + p.lo.enc_wo[l], Mt, d, ff, 1.f, s));
     RC(lin_dgrad(w.dh_enc, p.wb + p.lo.enc_wi[l], w.dn_enc, Mt, ff, d, nullptr, 1.f, s));
     RC(lin_wgrad(w.dh_enc, a.n_f, g + p.lo.enc_wi[l], Mt, ff, d, 1.f, s));

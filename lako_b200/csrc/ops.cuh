@@ -8,7 +8,7 @@ namespace lako {
 int gemm_bf16(const void* A, const void* B, void* C, int M, int N, int K, int lda, int ldb, int ldc, int a_mn,
               int b_mn, int epi, float alpha, const void* aux, int ld_aux, int splitk, int bn, cudaStream_t stream,
               DropSpec drop = DropSpec{});
-enum : int { EPI_BF16 = 0, EPI_BF16_RELU = 1, EPI_F32 = 2, EPI_F32_ATOMIC = 3, EPI_BF16_MASK = 4 };
+enum : int { EPI_BF16 = 0, EPI_BF16_RELU = 1, EPI_F32 = 2, EPI_F32_ATOMIC = 3, EPI_BF16_MASK = 4, EPI_BF16_BITMASK = 5 };
 
 // elementwise.cu
 // DropSpec{} (thresh == 0) disables a dropout site.  dd: mask on `delta` before the residual add; od: mask on the

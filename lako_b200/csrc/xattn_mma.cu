@@ -77,7 +77,9 @@ __global__ void __launch_bounds__(128) xattn_fwd_mma_kernel(const XMParams p) {
   float* sMask = reinterpret_cast<float*>(sQ + p.TP * 128);  // [128]
   float* sM = sMask + 128;                                   // [4][16]
   float* sL = sM + 64;                                       // [4][16]
-  float* sO = sL + 64;                                       // [4][16][68]
+  // [4][16][68] partial outputs: with a single 16-query tile (T <= 16, the reader's case) K is dead by the time the
+  // partials are exchanged, so they alias the K tile and the CTA needs 35 KB instead of 52 KB (6 CTAs/SM, not 4)
+  float* sO = (p.TP == 16) ? reinterpret_cast<float*>(sK) : sL + 64;
   const int split = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t4 = lane & 3;
   const int k0 = split * XM_CH;
@@ -247,8 +249,8 @@ __global__ void __launch_bounds__(128) xattn_bwd_mma_kernel(const XMParams p) {
   float* sMask = reinterpret_cast<float*>(sDO + p.TP * 128);  // [128]
   float* sLse = sMask + 128;                                  // [64]
   float* sD = sLse + 64;                                      // [64]
-  float* sO = sD + 64;                                        // [4][16][68] dq partials
-  uint8_t* sDS = reinterpret_cast<uint8_t*>(sO + 4 * 16 * 68);  // [128 keys][TP*2 + 16 B] dS^T bf16
+  float* sO = (p.TP == 16) ? reinterpret_cast<float*>(sV) : sD + 64;  // [4][16][68] dq partials (alias: V is dead then)
+  uint8_t* sDS = reinterpret_cast<uint8_t*>(sD + 64 + ((p.TP == 16) ? 0 : 4 * 16 * 68));  // [128 keys][TP*2+16 B]
   const int dsp = p.TP * 2 + 16;
   const int split = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t4 = lane & 3;
@@ -391,7 +393,7 @@ __global__ void __launch_bounds__(128) xattn_bwd_mma_kernel(const XMParams p) {
       }
     }
   }
-  __syncwarp();
+  __syncthreads();  // every warp is done with V / Q / dO: the dq partial exchange may alias them
   // dq[t][d] += sum over this warp's 32 keys of dS[t][key] K[key][d]; A = dS from the [key][t] smem copy (.trans)
   for (int mt = 0; mt < KST; ++mt) {
     float dq[8][4];
@@ -437,9 +439,10 @@ __global__ void __launch_bounds__(128) xattn_bwd_mma_kernel(const XMParams p) {
 
 static size_t xm_smem_bytes(int TP, bool bwd) {
   size_t n = 32768 + static_cast<size_t>(TP) * 128;
-  if (!bwd) return n + (128 + 64 + 64 + 4 * 16 * 68) * sizeof(float);
+  const size_t scratch = (TP == 16) ? 0 : 4 * 16 * 68;  // partial-output exchange aliases a dead K / V tile when T <= 16
+  if (!bwd) return n + (128 + 64 + 64 + scratch) * sizeof(float);
   n += static_cast<size_t>(TP) * 128;
-  n += (128 + 64 + 64 + 4 * 16 * 68) * sizeof(float);
+  n += (128 + 64 + 64 + scratch) * sizeof(float);
   n += 128 * (static_cast<size_t>(TP) * 2 + 16);
   return n;
 }

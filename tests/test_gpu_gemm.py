@@ -87,3 +87,28 @@ def test_gemm_linear_helper_strided():
     torch.cuda.synchronize()
     ref = xs.float() @ w.float().T
     assert (y.float() - ref).abs().max().item() < 0.1
+
+
+@pytest.mark.parametrize("bn", [0, 512])
+def test_gemm_relu_bitmask_roundtrip(bn):
+    """ReLU epilogue writes a 1-bit/element activity mask; the dgrad epilogue (epi 5) consumes it."""
+    from lako_b200 import _native as nat
+    M, N, K = 520, 512, 192
+    A, B = _mk((M, K), 11), _mk((N, K), 12)
+    h = torch.zeros(M, N, device="cuda", dtype=torch.bfloat16)
+    bits = torch.zeros(M, N // 8, device="cuda", dtype=torch.uint8)
+    nat.gemm(A, B, h, M, N, K, K, K, N, False, False, nat.EPI_BF16_RELU, 1.0, bits, N // 8, 0, bn)
+    ref = (A.float() @ B.float().T).relu()
+    assert (h.float() - ref).abs().max().item() < 0.1
+    act = (ref > 0).view(M, N // 8, 8).to(torch.uint8)
+    packed = sum(act[..., i] << i for i in range(8)).to(torch.uint8)
+    agree = (packed == bits).float().mean().item()
+    assert agree > 0.999, agree          # only exact-zero ties may differ
+    dY = _mk((M, 256), 13)
+    W = _mk((256, N), 14)               # dX[M,N] = dY[M,256] @ W[256,N], masked
+    dX = torch.zeros(M, N, device="cuda", dtype=torch.bfloat16)
+    nat.gemm(dY, W, dX, M, N, 256, 256, N, N, False, True, nat.EPI_BF16_BITMASK, 0.5, bits, N // 8, 0, bn)
+    torch.cuda.synchronize()
+    unpacked = torch.stack([(bits >> i) & 1 for i in range(8)], dim=-1).view(M, N).bool()
+    ref2 = torch.where(unpacked, 0.5 * (dY.float() @ W.float()), torch.zeros(M, N, device="cuda"))
+    assert (dX.float() - ref2).abs().max().item() < 0.1
