@@ -30,9 +30,10 @@ extern "C" {
 const char* lako_last_error(void);
 /* number of kernels this library has launched in this process (bench.py's gpu_launches) */
 unsigned long long lako_launch_count(void);
-/* optional CUDA-event timing per kernel category: 0 gemm, 1 enc_attn_fwd, 2 enc_attn_bwd, 3 rmsnorm,
- * 4 cross-attention, 5 other; work[] is FLOPs (0,1,2,4) or bytes (3). */
-#define LAKO_PROF_NCAT 6
+/* optional CUDA-event timing per kernel category: 0 large forward GEMMs, 1 enc_attn_fwd, 2 enc_attn_bwd, 3 rmsnorm,
+ * 4 cross-attention, 5 other (AdamW, CE, embedding, decoder self-attention), 6 large dgrad GEMMs, 7 large wgrad GEMMs,
+ * 8 decoder-side (<= 128 token rows) GEMMs; work[] is FLOPs (0,1,2,4,6,7,8) or bytes (3,5). */
+#define LAKO_PROF_NCAT 9
 void lako_prof_enable(int on);
 int lako_prof_collect(double* ms, double* work, long long* count);
 int lako_check_device(void); /* 0 iff the current device is sm_100 */

@@ -35,7 +35,18 @@ void count_launch();
 
 // Optional per-category device timing (CUDA events on the launching stream), used by bench.py to report
 // the dominant kernel's achieved FLOP/s / GB/s.  Disabled by default: zero overhead beyond one branch.
-enum ProfCat : int { PROF_GEMM = 0, PROF_ENC_ATTN_FWD, PROF_ENC_ATTN_BWD, PROF_NORM, PROF_XATTN, PROF_OTHER, PROF_NCAT };
+enum ProfCat : int {
+  PROF_GEMM = 0,  // large forward GEMMs (M > 128)
+  PROF_ENC_ATTN_FWD,
+  PROF_ENC_ATTN_BWD,
+  PROF_NORM,
+  PROF_XATTN,
+  PROF_OTHER,
+  PROF_GEMM_DGRAD,  // large dgrad (B operand MN-major)
+  PROF_GEMM_WGRAD,  // large wgrad (both operands MN-major, fp32 atomic epilogue)
+  PROF_GEMM_SMALL,  // decoder-side GEMMs (<= 128 rows of tokens on one side)
+  PROF_NCAT
+};
 struct ProfScope {
   int cat;
   void* rec;

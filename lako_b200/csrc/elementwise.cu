@@ -612,6 +612,7 @@ __global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ g,
 }
 int grad_sumsq(const float* g, size_t n, float* out, cudaStream_t s) {
   // caller zeroes *out
+  ProfScope prof(PROF_OTHER, static_cast<double>(n) * 4.0, s);
   const int grid = device_sm_count() * 8;
   sumsq_kernel<<<grid, 256, 0, s>>>(g, n, out);
   LAKO_CHECK_LAUNCH();
@@ -673,6 +674,7 @@ int adamw_step(float* p, float* m, float* v, const float* g, __nv_bfloat16* w_bf
                float grad_scale, float clip, float lr, float beta1, float beta2, float eps, float wd,
                cudaStream_t s) {
   LAKO_REQUIRE(n > 0 && n % 4 == 0, LAKO_ERR_BAD_ARG);
+  ProfScope prof(PROF_OTHER, static_cast<double>(n) * 30.0, s);
   const size_t blocks = (n / 4 + 255) / 256;
   adamw_kernel<<<static_cast<unsigned>(blocks), 256, 0, s>>>(p, m, v, g, w_bf16, n, sumsq, grad_scale, clip, lr, beta1,
                                                              beta2, eps, wd);

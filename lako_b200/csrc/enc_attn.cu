@@ -327,7 +327,8 @@ enc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
   float* s_D = reinterpret_cast<float*>(smem + EB_D_OFF);
   uint64_t* bar_load = reinterpret_cast<uint64_t*>(smem + EB_BAR_OFF);
   uint64_t* bar_mma = bar_load + 1;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_load + 2);
+  uint64_t* bar_grad = bar_load + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_load + 3);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int quarter = warp & 3, chalf = warp >> 2;
@@ -342,6 +343,7 @@ enc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
     tma_prefetch_desc(&tm_do);
     mbar_init(bar_load, 1);
     mbar_init(bar_mma, 1);
+    mbar_init(bar_grad, 1);
     fence_barrier_init();
   }
   if (warp == 0) tmem_alloc(tmem_slot, 512);
@@ -406,7 +408,12 @@ enc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
   const uint32_t t_row = tmem + (static_cast<uint32_t>(quarter * 32) << 16);
   const float keep = (lane == 0) ? 0.f : 1.f;      // systolic diagonal sums: lane 0 starts a new diagonal (up pass)
   const float keep_dn = (lane == 31) ? 0.f : 1.f;  // lane 31 starts a new diagonal (down pass)
-  uint32_t mma_phase = 0;
+  // Two completion streams: bar_mma = "S and dP of the next block are in TMEM", bar_grad = "the gradient MMAs of the
+  // previous block have finished reading P / dS from shared memory".  The S/dP MMAs of block i+1 are issued AHEAD of
+  // the gradient MMAs of block i, so the softmax arithmetic of block i+1 (registers only) overlaps the 24 gradient
+  // MMAs of block i; only the P / dS stores wait for them.
+  uint32_t s_phase = 0, g_phase = 0;
+  bool g_pending = false;
 
   for (int kt = 0; kt < nt; ++kt) {
     for (int qt = 0; qt < nt; ++qt) {
@@ -414,14 +421,13 @@ enc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
       const int qc = min(q, L - 1);
       const int b = L - 1 - qc;
       const float* lutp = s_lut4 + (b & 3) * LUTCOPY + (b & ~3);
-      mbar_wait(bar_mma, mma_phase);
-      mma_phase ^= 1;
+      mbar_wait(bar_mma, s_phase);
+      s_phase ^= 1;
       tc_fence_after();
       const float lse_q = s_lse[q];
       const float D_q = s_D[q];
-      uint8_t* prow = smem + EB_P_OFF + chalf * 16384 + r * 128;
-      uint8_t* dsrow = smem + EB_DS_OFF + chalf * 16384 + r * 128;
-#pragma unroll 1
+      uint32_t ppk[2][16], dpk[2][16];  // bf16x2-packed P_drop and dS of this thread's 2 x 32 columns
+#pragma unroll
       for (int c = 0; c < 2; ++c) {
         uint32_t sv[32], dpv[32];
         tmem_ld_32x32(t_row + TM_S + chalf * 64 + c * 32, sv);
@@ -454,18 +460,11 @@ enc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
             ds[u * 8 + i] = pr[i] * (dp - D_q);
             pr[i] = ((keepm >> i) & 1u) ? pr[i] * dscale : 0.f;  // the dV = P_drop^T dO operand
           }
-          const int unit = ((c * 4 + u) ^ (r & 7)) << 4;
-          uint4 o;
-          o.x = pack_bf16x2(pr[0], pr[1]);
-          o.y = pack_bf16x2(pr[2], pr[3]);
-          o.z = pack_bf16x2(pr[4], pr[5]);
-          o.w = pack_bf16x2(pr[6], pr[7]);
-          *reinterpret_cast<uint4*>(prow + unit) = o;
-          o.x = pack_bf16x2(ds[u * 8 + 0], ds[u * 8 + 1]);
-          o.y = pack_bf16x2(ds[u * 8 + 2], ds[u * 8 + 3]);
-          o.z = pack_bf16x2(ds[u * 8 + 4], ds[u * 8 + 5]);
-          o.w = pack_bf16x2(ds[u * 8 + 6], ds[u * 8 + 7]);
-          *reinterpret_cast<uint4*>(dsrow + unit) = o;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            ppk[c][u * 4 + i] = pack_bf16x2(pr[2 * i], pr[2 * i + 1]);
+            dpk[c][u * 4 + i] = pack_bf16x2(ds[u * 8 + 2 * i], ds[u * 8 + 2 * i + 1]);
+          }
         }
         // Bias gradient = diagonal sums (k - q constant) of this 32x32 sub-block, as two systolic passes over
         // the warp, exact in fp32.  Ascending columns with the partial sum moving one lane UP per column leaves
@@ -484,11 +483,42 @@ enc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
           if (lane != 0 && id >= 0 && id < nlut) atomicAdd(&s_dlut[id], Rdn);  // d = 0 is already in Rup (lane 31)
         }
       }
+      // P / dS of the previous block may still be feeding its gradient MMAs: wait before overwriting them
+      if (g_pending) {
+        mbar_wait(bar_grad, g_phase);
+        g_phase ^= 1;
+        g_pending = false;
+      }
+      {
+        uint8_t* prow = smem + EB_P_OFF + chalf * 16384 + r * 128;
+        uint8_t* dsrow = smem + EB_DS_OFF + chalf * 16384 + r * 128;
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int unit = ((c * 4 + u) ^ (r & 7)) << 4;
+            *reinterpret_cast<uint4*>(prow + unit) =
+                make_uint4(ppk[c][u * 4], ppk[c][u * 4 + 1], ppk[c][u * 4 + 2], ppk[c][u * 4 + 3]);
+            *reinterpret_cast<uint4*>(dsrow + unit) =
+                make_uint4(dpk[c][u * 4], dpk[c][u * 4 + 1], dpk[c][u * 4 + 2], dpk[c][u * 4 + 3]);
+          }
+        }
+      }
       fence_proxy_async_smem();
       tc_fence_before();
       __syncthreads();
       if (tid == 0) {
         tc_fence_after();
+        // next block's S / dP first (their TMEM columns are free: every thread has read this block's S / dP)
+        int nq = qt + 1, nk = kt;
+        if (nq == nt) {
+          nq = 0;
+          nk = kt + 1;
+        }
+        if (nk < nt) {
+          issue_s_dp(nq, nk);
+          umma_commit(bar_mma);
+        }
         // dV[kt] += P^T dO[qt] ; dK[kt] += dS^T Q[qt]   (M = 128 keys, N = 64, K = 128 queries)
 #pragma unroll
         for (int j = 0; j < 8; ++j)
@@ -503,18 +533,14 @@ enc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
         for (int j = 0; j < 8; ++j)
           umma_bf16(tmem + TM_DQ + qt * 64, make_smem_desc_sw128(dsa + (j >> 2) * 16384 + (j & 3) * 32, 16, 1024),
                     make_smem_desc_sw128(ka + kt * 16384 + j * 2048, 8192, 1024), idesc_dq, (kt > 0 || j > 0));
-        // next block's S / dP go to different TMEM columns: queue them behind the gradient MMAs
-        int nq = qt + 1, nk = kt;
-        if (nq == nt) {
-          nq = 0;
-          nk = kt + 1;
-        }
-        if (nk < nt) issue_s_dp(nq, nk);
-        umma_commit(bar_mma);
+        umma_commit(bar_grad);
       }
+      g_pending = true;
       if (qt == nt - 1) {
-        // dK[kt], dV[kt] are final once the MMAs just issued complete
-        mbar_wait(bar_mma, mma_phase);
+        // dK[kt], dV[kt] are final once the gradient MMAs just issued complete
+        mbar_wait(bar_grad, g_phase);
+        g_phase ^= 1;
+        g_pending = false;
         tc_fence_after();
         const int key = kt * 128 + r;
         uint32_t a[32], bb[32];
@@ -539,7 +565,6 @@ enc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
             *reinterpret_cast<uint4*>(dv + u * 8) = o;
           }
         }
-        // the wait above did not consume the phase: the loop head waits on the same completion
         tc_fence_before();
         __syncthreads();  // dK/dV TMEM reads done before the next key tile's first MMA overwrites them
       }

@@ -687,7 +687,9 @@ int gemm_bf16(const void* A, const void* B, void* C, int M, int N, int K, int ld
   else
     rc = get_tensor_map_2d(&tmB, B, N, K, ldb, 64, BK);
   if (rc) return rc;
-  ProfScope prof(PROF_GEMM, 2.0 * M * N * static_cast<double>(K), stream);
+  const bool small = (M <= 128) || (a_mn && b_mn && K <= 128);
+  const int pcat = small ? PROF_GEMM_SMALL : (a_mn ? PROF_GEMM_WGRAD : (b_mn ? PROF_GEMM_DGRAD : PROF_GEMM));
+  ProfScope prof(pcat, 2.0 * M * N * static_cast<double>(K), stream);
   if (use_pair) return dispatch_major2(a_mn, b_mn, epi, tmA, tmB, p, stream);
   if (bn == 256) return dispatch_major<256>(a_mn, b_mn, epi, tmA, tmB, p, stream);
   return dispatch_major<128>(a_mn, b_mn, epi, tmA, tmB, p, stream);
