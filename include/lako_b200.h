@@ -30,6 +30,8 @@ extern "C" {
 const char* lako_last_error(void);
 /* number of kernels this library has launched in this process (bench.py's gpu_launches) */
 unsigned long long lako_launch_count(void);
+/* programmatic dependent launch of the library's kernels (default on; env LAKO_PDL=0 disables) */
+void lako_set_pdl(int on);
 /* optional CUDA-event timing per kernel category: 0 large forward GEMMs, 1 enc_attn_fwd, 2 enc_attn_bwd, 3 rmsnorm,
  * 4 cross-attention, 5 other (AdamW, CE, embedding, decoder self-attention), 6 large dgrad GEMMs, 7 large wgrad GEMMs,
  * 8 decoder-side (<= 128 token rows) GEMMs; work[] is FLOPs (0,1,2,4,6,7,8) or bytes (3,5). */

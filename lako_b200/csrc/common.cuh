@@ -32,6 +32,7 @@ namespace lako {
 
 void set_last_error(const char* msg, const char* file, int line);
 void count_launch();
+bool pdl_enabled();
 
 // Optional per-category device timing (CUDA events on the launching stream), used by bench.py to report
 // the dominant kernel's achieved FLOP/s / GB/s.  Disabled by default: zero overhead beyond one branch.
@@ -55,6 +56,13 @@ struct ProfScope {
 };
 
 #ifdef __CUDACC__
+
+// Programmatic dependent launch: every kernel releases its successor at entry (the successor's CTAs become
+// resident and run their prologue -- barrier init, TMEM allocation, descriptor prefetch -- while this grid is
+// still executing) and blocks in pdl_wait() before its first global-memory access until the predecessor grid
+// has completed and flushed.  Without the launch attribute both instructions are no-ops.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
@@ -361,6 +369,24 @@ __device__ __forceinline__ uint32_t drop_keep8(const DropSpec& d, unsigned long 
 }
 
 #endif  // __CUDACC__
+
+#ifdef __CUDACC__
+// host: launch with the programmatic-stream-serialization attribute (see pdl_wait above)
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+#endif
 
 // ------------------------------------------------------------------ host: TMA descriptor cache (tma_host.cu)
 // 2D bf16 row-major tensor [outer][inner] with row pitch `pitch_elems`; box = {box_inner, box_outer},

@@ -52,6 +52,8 @@ __device__ __forceinline__ void stage_tile(const __nv_bfloat16* g, int ld, int n
 }
 
 __global__ void __launch_bounds__(128) xattn_fwd_kernel(const XAttnParams p) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ __align__(16) __nv_bfloat16 sK[XA_CH * XA_KPAD];
   __shared__ __align__(16) __nv_bfloat16 sV[XA_CH * XA_KPAD];
   extern __shared__ float dyn[];  // q [T][64] fp32, scores [T][XA_CH]
@@ -128,6 +130,8 @@ __global__ void __launch_bounds__(128) xattn_fwd_kernel(const XAttnParams p) {
 // combine the split partials: out[b,t,h*64+d] = sum_s exp(m_s - m) o_s / sum_s exp(m_s - m) l_s
 __global__ void xattn_combine_kernel(const float* __restrict__ part, __nv_bfloat16* __restrict__ out,
                                      float* __restrict__ lse, int T, int H, int splits, int ldo) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int t = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   const int d = threadIdx.x;  // 64 threads
   const float* pp = part + ((static_cast<size_t>(b) * H + h) * splits) * T * 66 + t * 66;
@@ -182,7 +186,7 @@ int xattn_fwd(const __nv_bfloat16* q, const __nv_bfloat16* kv, const unsigned ch
     if (rc) return rc;
   }
   dim3 g2(T, H, B);
-  xattn_combine_kernel<<<g2, 64, 0, s>>>(workspace, out, lse, T, H, p.splits, ldo);
+  launch_pdl(xattn_combine_kernel, dim3(g2), dim3(64), 0, s, workspace, out, lse, T, H, p.splits, ldo);
   LAKO_CHECK_LAUNCH();
   return LAKO_OK;
 }
@@ -206,6 +210,8 @@ struct XAttnBwdParams {
 };
 
 __global__ void __launch_bounds__(256) xattn_bwd_kernel(const XAttnBwdParams p) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ __align__(16) __nv_bfloat16 sK[XA_CH * XA_KPAD];
   __shared__ __align__(16) __nv_bfloat16 sV[XA_CH * XA_KPAD];
   extern __shared__ float dyn[];  // q [T][64], dO [T][64], dS [T][XA_CH], D[T], lse[T]
@@ -342,6 +348,8 @@ struct DSelfParams {
 };
 
 __global__ void __launch_bounds__(128) dself_fwd_kernel(const DSelfParams p) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ float dyn[];
   float (*sQ)[65] = reinterpret_cast<float (*)[65]>(dyn);
   float (*sK)[65] = reinterpret_cast<float (*)[65]>(dyn + XA_TMAX * 65);
@@ -415,7 +423,7 @@ int dself_fwd(const __nv_bfloat16* qkv, const float* lut, __nv_bfloat16* out, fl
     cudaFuncSetAttribute(dself_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     configured = true;
   }
-  dself_fwd_kernel<<<dim3(H, B), 128, smem, s>>>(p);
+  launch_pdl(dself_fwd_kernel, dim3(dim3(H, B)), dim3(128), smem, s, p);
   LAKO_CHECK_LAUNCH();
   return LAKO_OK;
 }
@@ -431,6 +439,8 @@ struct DSelfBwdParams {
 };
 
 __global__ void __launch_bounds__(128) dself_bwd_kernel(const DSelfBwdParams p) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ float dyn[];
   float (*sQ)[65] = reinterpret_cast<float (*)[65]>(dyn);
   float (*sK)[65] = reinterpret_cast<float (*)[65]>(dyn + XA_TMAX * 65);
@@ -512,7 +522,7 @@ int dself_bwd(const __nv_bfloat16* qkv, const __nv_bfloat16* dout, const float* 
     cudaFuncSetAttribute(dself_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     configured = true;
   }
-  dself_bwd_kernel<<<dim3(H, B), 128, smem, s>>>(p);
+  launch_pdl(dself_bwd_kernel, dim3(dim3(H, B)), dim3(128), smem, s, p);
   LAKO_CHECK_LAUNCH();
   return LAKO_OK;
 }
@@ -527,6 +537,8 @@ __global__ void __launch_bounds__(64) dself_step_kernel(const __nv_bfloat16* __r
                                                         __nv_bfloat16* __restrict__ vcache,
                                                         const float* __restrict__ lut, __nv_bfloat16* __restrict__ out,
                                                         int pos, int Tmax, int H, int inner) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ float sQ[64], sS[256];
   const int h = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
   const __nv_bfloat16* row = qkv + static_cast<size_t>(b) * 3 * inner + h * 64;
@@ -557,7 +569,7 @@ __global__ void __launch_bounds__(64) dself_step_kernel(const __nv_bfloat16* __r
 int dself_step(const __nv_bfloat16* qkv, __nv_bfloat16* kcache, __nv_bfloat16* vcache, const float* lut,
                __nv_bfloat16* out, int B, int pos, int Tmax, int H, cudaStream_t s) {
   LAKO_REQUIRE(pos >= 0 && pos < Tmax && Tmax <= 256, LAKO_ERR_UNSUPPORTED);
-  dself_step_kernel<<<dim3(H, B), 64, 0, s>>>(qkv, kcache, vcache, lut, out, pos, Tmax, H, H * 64);
+  launch_pdl(dself_step_kernel, dim3(dim3(H, B)), dim3(64), 0, s, qkv, kcache, vcache, lut, out, pos, Tmax, H, H * 64);
   LAKO_CHECK_LAUNCH();
   return LAKO_OK;
 }
@@ -568,6 +580,8 @@ __global__ void __launch_bounds__(256) greedy_pick_kernel(const float* __restric
                                                           long long* __restrict__ out_ids, int out_ld, int step,
                                                           int* __restrict__ unfinished, int* __restrict__ n_unfinished,
                                                           long long* __restrict__ next_ids) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ float s_v[8];
   __shared__ int s_i[8];
   const int b = blockIdx.x, tid = threadIdx.x;
@@ -614,7 +628,7 @@ __global__ void __launch_bounds__(256) greedy_pick_kernel(const float* __restric
 
 int greedy_pick(const float* logits, int B, int V, int ld, long long* out_ids, int out_ld, int step, int* unfinished,
                 int* n_unfinished, long long* next_ids, cudaStream_t s) {
-  greedy_pick_kernel<<<B, 256, 0, s>>>(logits, V, ld, out_ids, out_ld, step, unfinished, n_unfinished, next_ids);
+  launch_pdl(greedy_pick_kernel, dim3(B), dim3(256), 0, s, logits, V, ld, out_ids, out_ld, step, unfinished, n_unfinished, next_ids);
   LAKO_CHECK_LAUNCH();
   return LAKO_OK;
 }

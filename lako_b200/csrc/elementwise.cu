@@ -65,6 +65,8 @@ __global__ void __launch_bounds__(256) rmsnorm_fwd_kernel(const float* x, const 
                                                            __nv_bfloat16* __restrict__ out,
                                                            float* __restrict__ rstd_out, int rows, int d, float eps,
                                                            float out_scale, const DropSpec dd, const DropSpec od) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= rows) return;
@@ -137,7 +139,7 @@ int rmsnorm_fwd(const float* x, const __nv_bfloat16* delta, float* x_out, const 
   ProfScope prof(PROF_NORM, static_cast<double>(rows) * d * (delta ? 12.0 : 6.0), s);
   const int warps_per_block = 8;
   const int grid = (rows + warps_per_block - 1) / warps_per_block;
-  rmsnorm_fwd_kernel<<<grid, warps_per_block * 32, 0, s>>>(x, delta, x_out, w, out, rstd, rows, d, eps, out_scale, dd, od);
+  launch_pdl(rmsnorm_fwd_kernel, dim3(grid), dim3(warps_per_block * 32), 0, s, x, delta, x_out, w, out, rstd, rows, d, eps, out_scale, dd, od);
   LAKO_CHECK_LAUNCH();
   return LAKO_OK;
 }
@@ -161,6 +163,8 @@ __global__ void __launch_bounds__(256, 2) rmsnorm_bwd_kernel(const __nv_bfloat16
                                                               __nv_bfloat16* __restrict__ dres_bf16,
                                                               float* __restrict__ dw, int rows, int accumulate,
                                                               float dy_scale, const DropSpec yd, const DropSpec bd) {
+  pdl_launch_dependents();
+  pdl_wait();
   constexpr int d = NV * 128;
   extern __shared__ float4 s_norm[];
   float4* s_w = s_norm;                // [d/4]
@@ -265,7 +269,7 @@ static int launch_rmsnorm_bwd(const __nv_bfloat16* dy, const float* x, const flo
   }
   int grid = (rows + 7) / 8;
   grid = min(grid, device_sm_count() * 2);
-  rmsnorm_bwd_kernel<NV><<<grid, 256, smem, s>>>(dy, x, rstd, w, dres, dres_bf16, dw, rows, accumulate, dy_scale, yd, bd);
+  launch_pdl(rmsnorm_bwd_kernel<NV>, dim3(grid), dim3(256), smem, s, dy, x, rstd, w, dres, dres_bf16, dw, rows, accumulate, dy_scale, yd, bd);
   LAKO_CHECK_LAUNCH();
   return LAKO_OK;
 }
@@ -293,6 +297,8 @@ int rmsnorm_bwd(const __nv_bfloat16* dy, const float* x, const float* rstd, cons
 // --------------------------------------------------------------------------------------------
 __global__ void embed_gather_kernel(const long long* __restrict__ ids, const float* __restrict__ table,
                                     float* __restrict__ out, int rows, int d, int vocab, const DropSpec ds) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= rows) return;
@@ -316,13 +322,15 @@ __global__ void embed_gather_kernel(const long long* __restrict__ ids, const flo
 int embed_gather(const long long* ids, const float* table, float* out, int rows, int d, int vocab, cudaStream_t s,
                  DropSpec ds) {
   LAKO_REQUIRE(rows > 0 && d % 8 == 0, LAKO_ERR_BAD_ARG);
-  embed_gather_kernel<<<(rows + 7) / 8, 256, 0, s>>>(ids, table, out, rows, d, vocab, ds);
+  launch_pdl(embed_gather_kernel, dim3((rows + 7) / 8), dim3(256), 0, s, ids, table, out, rows, d, vocab, ds);
   LAKO_CHECK_LAUNCH();
   return LAKO_OK;
 }
 
 __global__ void embed_scatter_add_kernel(const long long* __restrict__ ids, const float* __restrict__ dres,
                                          float* __restrict__ dtable, int rows, int d, int vocab, const DropSpec ds) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= rows) return;
@@ -348,7 +356,7 @@ __global__ void embed_scatter_add_kernel(const long long* __restrict__ ids, cons
 int embed_scatter_add(const long long* ids, const float* dres, float* dtable, int rows, int d, int vocab,
                       cudaStream_t s, DropSpec ds) {
   LAKO_REQUIRE(rows > 0 && d % 8 == 0, LAKO_ERR_BAD_ARG);
-  embed_scatter_add_kernel<<<(rows + 7) / 8, 256, 0, s>>>(ids, dres, dtable, rows, d, vocab, ds);
+  launch_pdl(embed_scatter_add_kernel, dim3((rows + 7) / 8), dim3(256), 0, s, ids, dres, dtable, rows, d, vocab, ds);
   LAKO_CHECK_LAUNCH();
   return LAKO_OK;
 }
@@ -356,6 +364,8 @@ int embed_scatter_add(const long long* ids, const float* dres, float* dtable, in
 // decoder input ids = shift_right(labels) (HF:modeling_t5.py:595-614): start token 0, -100 -> 0
 __global__ void shift_right_kernel(const long long* __restrict__ labels, long long* __restrict__ dec_ids, int B,
                                    int T) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B * T) return;
   const int t = i % T;
@@ -364,7 +374,7 @@ __global__ void shift_right_kernel(const long long* __restrict__ labels, long lo
   dec_ids[i] = v;
 }
 int shift_right(const long long* labels, long long* dec_ids, int B, int T, cudaStream_t s) {
-  shift_right_kernel<<<(B * T + 255) / 256, 256, 0, s>>>(labels, dec_ids, B, T);
+  launch_pdl(shift_right_kernel, dim3((B * T + 255) / 256), dim3(256), 0, s, labels, dec_ids, B, T);
   LAKO_CHECK_LAUNCH();
   return LAKO_OK;
 }
@@ -378,6 +388,8 @@ int shift_right(const long long* labels, long long* dec_ids, int B, int T, cudaS
 // One CTA per row; pass 1 = online max/sum, pass 2 re-reads the row (L2 resident) and writes dlogits.
 // --------------------------------------------------------------------------------------------
 __global__ void count_valid_kernel(const long long* __restrict__ labels, int n, float* __restrict__ stats) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ int s_cnt;
   if (threadIdx.x == 0) s_cnt = 0;
   __syncthreads();
@@ -395,6 +407,8 @@ __global__ void __launch_bounds__(512) ce_fwd_bwd_kernel(const float* __restrict
                                                           const long long* __restrict__ labels,
                                                           float* __restrict__ stats, float* __restrict__ row_loss,
                                                           __nv_bfloat16* __restrict__ dlogits, int V, int ld, int ld_d) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ float s_m[16], s_s[16];
   __shared__ float s_bm, s_bs;
   const int row = blockIdx.x;
@@ -488,7 +502,7 @@ __global__ void __launch_bounds__(512) ce_fwd_bwd_kernel(const float* __restrict
 }
 
 int count_valid(const long long* labels, int n, float* stats, cudaStream_t s) {
-  count_valid_kernel<<<1, 256, 0, s>>>(labels, n, stats);
+  launch_pdl(count_valid_kernel, dim3(1), dim3(256), 0, s, labels, n, stats);
   LAKO_CHECK_LAUNCH();
   return LAKO_OK;
 }
@@ -496,7 +510,7 @@ int count_valid(const long long* labels, int n, float* stats, cudaStream_t s) {
 int ce_fwd_bwd(const float* logits, const long long* labels, float* stats, float* row_loss, __nv_bfloat16* dlogits,
                int rows, int V, int ld, int ld_d, cudaStream_t s) {
   LAKO_REQUIRE(rows > 0 && V > 0 && ld % 4 == 0 && (dlogits == nullptr || ld_d % 8 == 0), LAKO_ERR_BAD_ARG);
-  ce_fwd_bwd_kernel<<<rows, 512, 0, s>>>(logits, labels, stats, row_loss, dlogits, V, ld, ld_d);
+  launch_pdl(ce_fwd_bwd_kernel, dim3(rows), dim3(512), 0, s, logits, labels, stats, row_loss, dlogits, V, ld, ld_d);
   LAKO_CHECK_LAUNCH();
   return LAKO_OK;
 }
@@ -505,6 +519,8 @@ int ce_fwd_bwd(const float* logits, const long long* labels, float* stats, float
 // casts / transposes / fills
 // --------------------------------------------------------------------------------------------
 __global__ void cast_f32_to_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, size_t n) {
+  pdl_launch_dependents();
+  pdl_wait();
   const size_t i = (static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x) * 8;
   if (i + 8 <= n) {
     const float4 a = *reinterpret_cast<const float4*>(in + i);
@@ -522,13 +538,15 @@ __global__ void cast_f32_to_bf16_kernel(const float* __restrict__ in, __nv_bfloa
 int cast_f32_to_bf16(const float* in, __nv_bfloat16* out, size_t n, cudaStream_t s) {
   if (n == 0) return LAKO_OK;
   const size_t blocks = (n + 2047) / 2048;
-  cast_f32_to_bf16_kernel<<<static_cast<unsigned>(blocks), 256, 0, s>>>(in, out, n);
+  launch_pdl(cast_f32_to_bf16_kernel, dim3(static_cast<unsigned>(blocks)), dim3(256), 0, s, in, out, n);
   LAKO_CHECK_LAUNCH();
   return LAKO_OK;
 }
 
 // keep[e] = dropout keep decision of element e of a site (audit / test entry for the Philox mask)
 __global__ void dropout_mask_kernel(unsigned char* __restrict__ keep, size_t n, const DropSpec ds) {
+  pdl_launch_dependents();
+  pdl_wait();
   const size_t grp = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (grp * 8 >= n) return;
   const uint32_t m = ds.thresh ? drop_keep8(ds, grp) : 0xffu;
@@ -538,13 +556,15 @@ int dropout_mask(unsigned char* keep, size_t n, unsigned long long seed, unsigne
                  cudaStream_t s) {
   if (n == 0) return LAKO_OK;
   const size_t groups = (n + 7) / 8;
-  dropout_mask_kernel<<<static_cast<unsigned>((groups + 255) / 256), 256, 0, s>>>(keep, n, make_drop(seed, step, site, p));
+  launch_pdl(dropout_mask_kernel, dim3(static_cast<unsigned>((groups + 255) / 256)), dim3(256), 0, s, keep, n, make_drop(seed, step, site, p));
   LAKO_CHECK_LAUNCH();
   return LAKO_OK;
 }
 
 // x *= *scalar (device scalar); used to apply d(loss) != 1 to the stored dlogits
 __global__ void scale_bf16_dev_kernel(__nv_bfloat16* __restrict__ x, size_t n, const float* __restrict__ scalar) {
+  pdl_launch_dependents();
+  pdl_wait();
   const float sc = *scalar;
   if (sc == 1.0f) return;
   const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -552,7 +572,7 @@ __global__ void scale_bf16_dev_kernel(__nv_bfloat16* __restrict__ x, size_t n, c
 }
 int scale_bf16_dev(__nv_bfloat16* x, size_t n, const float* scalar, cudaStream_t s) {
   if (n == 0) return LAKO_OK;
-  scale_bf16_dev_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, s>>>(x, n, scalar);
+  launch_pdl(scale_bf16_dev_kernel, dim3(static_cast<unsigned>((n + 255) / 256)), dim3(256), 0, s, x, n, scalar);
   LAKO_CHECK_LAUNCH();
   return LAKO_OK;
 }
@@ -560,6 +580,8 @@ int scale_bf16_dev(__nv_bfloat16* x, size_t n, const float* scalar, cudaStream_t
 // out[c][r] = in[r][c], bf16, 32x32 tiles through padded smem
 __global__ void transpose_bf16_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out, int rows,
                                       int cols, int ld_in, int ld_out) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ __nv_bfloat16 tile[64][66];
   const int r0 = blockIdx.y * 64, c0 = blockIdx.x * 64;
   for (int i = threadIdx.y; i < 64; i += blockDim.y) {
@@ -581,7 +603,7 @@ __global__ void transpose_bf16_kernel(const __nv_bfloat16* __restrict__ in, __nv
 int transpose_bf16(const __nv_bfloat16* in, __nv_bfloat16* out, int rows, int cols, int ld_in, int ld_out,
                    cudaStream_t s) {
   dim3 grid((cols + 63) / 64, (rows + 63) / 64), block(32, 8);
-  transpose_bf16_kernel<<<grid, block, 0, s>>>(in, out, rows, cols, ld_in, ld_out);
+  launch_pdl(transpose_bf16_kernel, dim3(grid), dim3(block), 0, s, in, out, rows, cols, ld_in, ld_out);
   LAKO_CHECK_LAUNCH();
   return LAKO_OK;
 }
@@ -590,6 +612,8 @@ int transpose_bf16(const __nv_bfloat16* in, __nv_bfloat16* out, int rows, int co
 // gradient global-norm + fused clip / AdamW / bf16 re-cast over the flat parameter buffer
 // --------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ g, size_t n, float* __restrict__ out) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ float s_w[8];
   float acc = 0.f;
   const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x * 4;
@@ -614,7 +638,7 @@ int grad_sumsq(const float* g, size_t n, float* out, cudaStream_t s) {
   // caller zeroes *out
   ProfScope prof(PROF_OTHER, static_cast<double>(n) * 4.0, s);
   const int grid = device_sm_count() * 8;
-  sumsq_kernel<<<grid, 256, 0, s>>>(g, n, out);
+  launch_pdl(sumsq_kernel, dim3(grid), dim3(256), 0, s, g, n, out);
   LAKO_CHECK_LAUNCH();
   return LAKO_OK;
 }
@@ -626,6 +650,8 @@ __global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, float
                                                      size_t n, const float* __restrict__ sumsq, float grad_scale,
                                                      float clip, float lr, float beta1, float beta2, float eps,
                                                      float wd) {
+  pdl_launch_dependents();
+  pdl_wait();
   float coef = grad_scale;
   if (clip > 0.f) {
     const float norm = sqrtf(*sumsq) * grad_scale;
@@ -676,7 +702,7 @@ int adamw_step(float* p, float* m, float* v, const float* g, __nv_bfloat16* w_bf
   LAKO_REQUIRE(n > 0 && n % 4 == 0, LAKO_ERR_BAD_ARG);
   ProfScope prof(PROF_OTHER, static_cast<double>(n) * 30.0, s);
   const size_t blocks = (n / 4 + 255) / 256;
-  adamw_kernel<<<static_cast<unsigned>(blocks), 256, 0, s>>>(p, m, v, g, w_bf16, n, sumsq, grad_scale, clip, lr, beta1,
+  launch_pdl(adamw_kernel, dim3(static_cast<unsigned>(blocks)), dim3(256), 0, s, p, m, v, g, w_bf16, n, sumsq, grad_scale, clip, lr, beta1,
                                                              beta2, eps, wd);
   LAKO_CHECK_LAUNCH();
   return LAKO_OK;

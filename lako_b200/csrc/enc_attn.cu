@@ -22,6 +22,8 @@ constexpr float MASK_MIN = -3.4028234663852886e38f;  // torch.finfo(float32).min
 // bias_lut[h][rel + L - 1] = table[bucket(rel)][h], rel = key_pos - query_pos
 __global__ void build_bias_lut_kernel(const float* __restrict__ table, const int* __restrict__ buckets,
                                       float* __restrict__ lut, int H, int L, int bucket_center) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int n = 2 * L - 1;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= H * n) return;
@@ -33,7 +35,7 @@ __global__ void build_bias_lut_kernel(const float* __restrict__ table, const int
 int build_bias_lut(const float* table, const int* buckets, float* lut, int H, int L, int bucket_center,
                    cudaStream_t s) {
   const int n = H * (2 * L - 1);
-  build_bias_lut_kernel<<<(n + 255) / 256, 256, 0, s>>>(table, buckets, lut, H, L, bucket_center);
+  launch_pdl(build_bias_lut_kernel, dim3((n + 255) / 256), dim3(256), 0, s, table, buckets, lut, H, L, bucket_center);
   LAKO_CHECK_LAUNCH();
   return LAKO_OK;
 }
@@ -99,6 +101,7 @@ enc_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const EncAttnPar
   const int L = p.L, LK = p.LK;
   const int row0 = psg * L;
   const int ktiles = (LK + 127) / 128;
+  pdl_launch_dependents();
 
   if (tid == 0) {
     tma_prefetch_desc(&tm_qkv);
@@ -109,6 +112,7 @@ enc_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const EncAttnPar
     fence_barrier_init();
   }
   if (warp == 0) tmem_alloc(tmem_slot, 256);
+  pdl_wait();
   stage_lut4(s_lut4, p.bias_lut + h * (2 * L - 1), 2 * L - 1, tid, 256);
   stage_kmask(s_kmask, p.mask + static_cast<size_t>(psg) * L, L, tid, 256);
   tc_fence_before();
@@ -282,7 +286,7 @@ int enc_attn_fwd(const __nv_bfloat16* qkv, const unsigned char* mask, const floa
   p.drop = drop;
   ProfScope prof(PROF_ENC_ATTN_FWD, 4.0 * P * H * static_cast<double>(L) * L * 64, s);
   dim3 grid((L + 127) / 128, H, P);
-  enc_attn_fwd_kernel<<<grid, 256, EA_SMEM_BYTES, s>>>(tm, p);
+  launch_pdl(enc_attn_fwd_kernel, grid, dim3(256), EA_SMEM_BYTES, s, tm, p);
   LAKO_CHECK_LAUNCH();
   return LAKO_OK;
 }
@@ -337,6 +341,7 @@ enc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
   const int row0 = psg * L;
   const int nt = (L + 127) / 128;  // 128-row tiles of queries == of keys
   const int nlut = 2 * L - 1;
+  pdl_launch_dependents();
 
   if (tid == 0) {
     tma_prefetch_desc(&tm_qkv);
@@ -347,6 +352,7 @@ enc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
     fence_barrier_init();
   }
   if (warp == 0) tmem_alloc(tmem_slot, 512);
+  pdl_wait();
   stage_lut4(s_lut4, p.bias_lut + h * nlut, nlut, tid, 256);
   stage_kmask(s_kmask, p.mask + static_cast<size_t>(psg) * L, L, tid, 256);
   for (int i = tid; i < 512; i += 256) s_dlut[i] = 0.f;
@@ -644,7 +650,7 @@ int enc_attn_bwd(const __nv_bfloat16* qkv, const __nv_bfloat16* out, const __nv_
   p.drop = drop;
   ProfScope prof(PROF_ENC_ATTN_BWD, 10.0 * P * H * static_cast<double>(L) * L * 64, s);
   dim3 grid(H, P);
-  enc_attn_bwd_kernel<<<grid, 256, EB_SMEM_BYTES, s>>>(tm_qkv, tm_do, p);
+  launch_pdl(enc_attn_bwd_kernel, grid, dim3(256), EB_SMEM_BYTES, s, tm_qkv, tm_do, p);
   LAKO_CHECK_LAUNCH();
   return LAKO_OK;
 }
@@ -652,6 +658,8 @@ int enc_attn_bwd(const __nv_bfloat16* qkv, const __nv_bfloat16* out, const __nv_
 // dtable[bucket][h] += sum over rel of dlut[h][rel] (fold the per-offset bias gradient into the 32 buckets)
 __global__ void fold_dlut_kernel(const float* __restrict__ dlut, const int* __restrict__ buckets,
                                  float* __restrict__ dtable, int H, int L, int bucket_center, int nb) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int h = blockIdx.x;
   const int n = 2 * L - 1;
   for (int b = threadIdx.x; b < nb; b += blockDim.x) {
@@ -663,7 +671,7 @@ __global__ void fold_dlut_kernel(const float* __restrict__ dlut, const int* __re
 }
 int fold_dlut(const float* dlut, const int* buckets, float* dtable, int H, int L, int bucket_center, int nb,
               cudaStream_t s) {
-  fold_dlut_kernel<<<H, 32, 0, s>>>(dlut, buckets, dtable, H, L, bucket_center, nb);
+  launch_pdl(fold_dlut_kernel, dim3(H), dim3(32), 0, s, dlut, buckets, dtable, H, L, bucket_center, nb);
   LAKO_CHECK_LAUNCH();
   return LAKO_OK;
 }

@@ -211,6 +211,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  pdl_launch_dependents();
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -232,6 +233,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
 
   const int tiles_mn = p.tiles_m * p.tiles_n;
   const int total_tiles = tiles_mn * p.splitk;
@@ -385,6 +387,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const int lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
   const bool leader = rank == 0;
+  pdl_launch_dependents();
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -406,6 +409,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
 
   const int tiles_mn = p.tiles_m * p.tiles_n;  // tiles_m counts 256-row tiles here
   const int total_tiles = tiles_mn * p.splitk;
@@ -533,7 +537,7 @@ static int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const Ge
   }
   const int total = p.tiles_m * p.tiles_n * p.splitk;
   const int clusters = min(total, device_sm_count() / 2);
-  kern<<<clusters * 2, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, p);
+  launch_pdl(kern, dim3(clusters * 2), dim3(GEMM_THREADS), Cfg::SMEM_BYTES, stream, tmA, tmB, p);
   LAKO_CHECK_LAUNCH();
   return LAKO_OK;
 }
@@ -575,7 +579,7 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
   }
   const int total = p.tiles_m * p.tiles_n * p.splitk;
   const int grid = min(total, device_sm_count());
-  kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, p);
+  launch_pdl(kern, dim3(grid), dim3(GEMM_THREADS), Cfg::SMEM_BYTES, stream, tmA, tmB, p);
   LAKO_CHECK_LAUNCH();
   return LAKO_OK;
 }

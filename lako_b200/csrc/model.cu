@@ -504,6 +504,8 @@ void carve_gen(const lako_dims& dm, int B, int N, int L, int Tmax, void* base, G
 }
 __global__ void gen_init_kernel(int* unfinished, int* n_unf, long long* next_ids, long long* out_ids, int B,
                                 int out_ld) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < B) {
     unfinished[i] = 1;
@@ -539,7 +541,7 @@ extern "C" int lako_fidt5_generate(const lako_fidt5* m, const lako_batch* bt, in
   const int d = p.d, inner = p.inner, ff = p.ff, nl = p.nl, B = bt->B, H = p.H;
   RC(encode(p, m, w, reinterpret_cast<const long long*>(bt->ids), bt->mask, false, s, Dropper{0, 0, 0.f}));
   RC(build_bias_lut(p.wf + p.lo.dec_relbias, m->dec_buckets, gw.lut_dec, H, max_length, m->bucket_center, s));
-  gen_init_kernel<<<(B + 127) / 128, 128, 0, s>>>(gw.unfinished, gw.n_unf, gw.next_ids,
+  launch_pdl(gen_init_kernel, dim3((B + 127) / 128), dim3(128), 0, s, gw.unfinished, gw.n_unf, gw.next_ids,
                                                    reinterpret_cast<long long*>(out_ids), B, max_length);
   LAKO_CHECK_LAUNCH();
   const float alpha = 1.0f / sqrtf(static_cast<float>(d));

@@ -1,6 +1,7 @@
 // Host-side TMA descriptor (CUtensorMap) construction with a small cache, device queries and the
 // last-error slot for the C ABI.  cuTensorMapEncodeTiled is fetched through
 // cudaGetDriverEntryPoint so the library links against cudart only.
+#include <cstdlib>
 #include <mutex>
 #include <string>
 #include <unordered_map>
@@ -19,6 +20,14 @@ void set_last_error(const char* msg, const char* file, int line) {
 }
 const char* last_error_cstr() { return g_last_error.c_str(); }
 
+static int g_pdl = -1;
+bool pdl_enabled() {
+  if (g_pdl < 0) {
+    const char* e = getenv("LAKO_PDL");
+    g_pdl = (e && e[0] == '0') ? 0 : 1;
+  }
+  return g_pdl != 0;
+}
 static unsigned long long g_launches = 0;
 void count_launch() { ++g_launches; }
 
@@ -182,6 +191,7 @@ int check_arch() {
 
 }  // namespace lako
 
+extern "C" void lako_set_pdl(int on) { lako::g_pdl = on ? 1 : 0; }
 extern "C" unsigned long long lako_launch_count() { return lako::g_launches; }
 extern "C" void lako_prof_enable(int on) { lako::g_prof_on = on != 0; }
 // Synchronises, then fills ms[cat], work[cat], count[cat] (arrays of LAKO_PROF_NCAT) and clears the records.

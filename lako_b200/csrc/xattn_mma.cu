@@ -70,6 +70,8 @@ struct XMParams {
 // dynamic smem: sK 16K | sV 16K | sQ TP*128 | sX TP*128 (bwd: dO) | f32 scratch
 // ------------------------------------------------------------------------------------------------ forward
 __global__ void __launch_bounds__(128) xattn_fwd_mma_kernel(const XMParams p) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ __align__(1024) uint8_t xs[];
   uint8_t* sK = xs;
   uint8_t* sV = xs + 16384;
@@ -241,6 +243,8 @@ __global__ void __launch_bounds__(128) xattn_fwd_mma_kernel(const XMParams p) {
 
 // ------------------------------------------------------------------------------------------------ backward
 __global__ void __launch_bounds__(128) xattn_bwd_mma_kernel(const XMParams p) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ __align__(1024) uint8_t xs[];
   uint8_t* sK = xs;
   uint8_t* sV = xs + 16384;
@@ -462,7 +466,7 @@ int xattn_fwd_mma(const __nv_bfloat16* q, const __nv_bfloat16* kv, const unsigne
     cudaFuncSetAttribute(xattn_fwd_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xm_smem_bytes(64, false));
     configured = true;
   }
-  xattn_fwd_mma_kernel<<<dim3(p.splits, H, B), 128, xm_smem_bytes(p.TP, false), s>>>(p);
+  launch_pdl(xattn_fwd_mma_kernel, dim3(dim3(p.splits, H, B)), dim3(128), xm_smem_bytes(p.TP, false), s, p);
   LAKO_CHECK_LAUNCH();
   return LAKO_OK;
 }
@@ -483,7 +487,7 @@ int xattn_bwd_mma(const __nv_bfloat16* q, const __nv_bfloat16* kv, const unsigne
     cudaFuncSetAttribute(xattn_bwd_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xm_smem_bytes(64, true));
     configured = true;
   }
-  xattn_bwd_mma_kernel<<<dim3(p.splits, H, B), 128, xm_smem_bytes(p.TP, true), s>>>(p);
+  launch_pdl(xattn_bwd_mma_kernel, dim3(dim3(p.splits, H, B)), dim3(128), xm_smem_bytes(p.TP, true), s, p);
   LAKO_CHECK_LAUNCH();
   return LAKO_OK;
 }

@@ -15,7 +15,7 @@ from lako_b200.model import bucket_table  # noqa: E402
 
 which = sys.argv[1] if len(sys.argv) > 1 else "all"
 lib = nat.lib()
-P, L, H, d, ff = 80, 200, 12, 768, 3072
+P, L, H, d, ff = (int(os.environ.get(k, v)) for k, v in (('P', 80), ('L', 200), ('H', 12), ('D', 768), ('FF', 3072)))
 inner = H * 64
 Mt = P * L
 torch.manual_seed(0)
