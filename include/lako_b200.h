@@ -137,6 +137,13 @@ typedef struct {
   float dropout_p;
   unsigned int dropout_step;
   unsigned long long dropout_seed;
+  /* Un-padded execution (optional).  When every passage's mask is a prefix (valid tokens first, pad after -- what
+   * src/data.py's Collator produces), pass the int32 DEVICE array cu_seqlens[B*N+1] of exclusive prefix sums of the
+   * passage lengths and packed_tokens = cu_seqlens[B*N] (host value).  All encoder-side work then runs on the
+   * packed tokens only; padded positions never influence loss, logits, gradients or scores in the reference either
+   * (they are masked as keys everywhere), so results are unchanged.  NULL = padded layout with `mask`. */
+  const int* cu_seqlens;
+  int packed_tokens;
 } lako_batch;
 
 int lako_fidt5_layout(const lako_dims* dims, lako_layout* out);

@@ -129,12 +129,15 @@ __global__ void __launch_bounds__(128) xattn_fwd_kernel(const XAttnParams p) {
 
 // combine the split partials: out[b,t,h*64+d] = sum_s exp(m_s - m) o_s / sum_s exp(m_s - m) l_s
 __global__ void xattn_combine_kernel(const float* __restrict__ part, __nv_bfloat16* __restrict__ out,
-                                     float* __restrict__ lse, int T, int H, int splits, int ldo) {
+                                     float* __restrict__ lse, int T, int H, int splits, int ldo,
+                                     const int* __restrict__ cu, int npsg) {
   pdl_launch_dependents();
   pdl_wait();
   const int t = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int stride_s = splits;  // workspace pitch (max chunks); a packed question may fill fewer
+  if (cu) splits = (cu[(b + 1) * npsg] - cu[b * npsg] + XA_CH - 1) / XA_CH;
   const int d = threadIdx.x;  // 64 threads
-  const float* pp = part + ((static_cast<size_t>(b) * H + h) * splits) * T * 66 + t * 66;
+  const float* pp = part + ((static_cast<size_t>(b) * H + h) * stride_s) * T * 66 + t * 66;
   float m = -INFINITY;
   for (int s = 0; s < splits; ++s) m = fmaxf(m, pp[static_cast<size_t>(s) * T * 66 + 64]);
   float l = 0.f, o = 0.f;
@@ -155,7 +158,7 @@ size_t xattn_workspace_bytes(int B, int H, int T, int M) {
 
 int xattn_fwd(const __nv_bfloat16* q, const __nv_bfloat16* kv, const unsigned char* mask, __nv_bfloat16* out, float* lse,
               float* tok_score, float* workspace, int B, int T, int M, int H, int ldq, int ldkv, int koff, int voff,
-              int ldo, cudaStream_t s, DropSpec drop) {
+              int ldo, cudaStream_t s, DropSpec drop, const int* cu, int npsg, const int* tok_index) {
   LAKO_REQUIRE(B > 0 && T > 0 && T <= XA_TMAX && M > 0 && H > 0, LAKO_ERR_UNSUPPORTED);
   LAKO_REQUIRE(ldkv % 8 == 0 && koff % 8 == 0 && voff % 8 == 0, LAKO_ERR_BAD_ARG);
   XAttnParams p;
@@ -182,11 +185,12 @@ int xattn_fwd(const __nv_bfloat16* q, const __nv_bfloat16* kv, const unsigned ch
   ProfScope prof(PROF_XATTN, 4.0 * B * H * static_cast<double>(T) * M * 64, s);
   (void)dyn;
   {
-    int rc = xattn_fwd_mma(q, kv, mask, tok_score, workspace, B, T, M, H, ldq, ldkv, koff, voff, s, drop);
+    int rc = xattn_fwd_mma(q, kv, mask, tok_score, workspace, B, T, M, H, ldq, ldkv, koff, voff, s, drop, cu, npsg,
+                           tok_index);
     if (rc) return rc;
   }
   dim3 g2(T, H, B);
-  launch_pdl(xattn_combine_kernel, dim3(g2), dim3(64), 0, s, workspace, out, lse, T, H, p.splits, ldo);
+  launch_pdl(xattn_combine_kernel, dim3(g2), dim3(64), 0, s, workspace, out, lse, T, H, p.splits, ldo, cu, npsg);
   LAKO_CHECK_LAUNCH();
   return LAKO_OK;
 }
@@ -316,7 +320,8 @@ __global__ void __launch_bounds__(256) xattn_bwd_kernel(const XAttnBwdParams p) 
 
 int xattn_bwd(const __nv_bfloat16* q, const __nv_bfloat16* kv, const unsigned char* mask, const __nv_bfloat16* out,
               const __nv_bfloat16* dout, const float* lse, __nv_bfloat16* dkv, float* dq_f32, int B, int T, int M,
-              int H, int ldq, int ldkv, int koff, int voff, int ldo, cudaStream_t s, DropSpec drop) {
+              int H, int ldq, int ldkv, int koff, int voff, int ldo, cudaStream_t s, DropSpec drop, const int* cu,
+              int npsg) {
   LAKO_REQUIRE(B > 0 && T > 0 && T <= XA_TMAX && M > 0 && H > 0, LAKO_ERR_UNSUPPORTED);
   XAttnBwdParams p;
   p.q = q; p.kv = kv; p.mask = mask; p.out = out; p.dout = dout; p.lse = lse; p.dkv = dkv; p.dq = dq_f32;
@@ -331,7 +336,8 @@ int xattn_bwd(const __nv_bfloat16* q, const __nv_bfloat16* kv, const unsigned ch
   ProfScope prof(PROF_XATTN, 8.0 * B * H * static_cast<double>(T) * M * 64, s);
   (void)dyn;
   (void)p;
-  return xattn_bwd_mma(q, kv, mask, out, dout, lse, dkv, dq_f32, B, T, M, H, ldq, ldkv, koff, voff, ldo, s, drop);
+  return xattn_bwd_mma(q, kv, mask, out, dout, lse, dkv, dq_f32, B, T, M, H, ldq, ldkv, koff, voff, ldo, s, drop, cu,
+                       npsg);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -295,14 +295,29 @@ int rmsnorm_bwd(const __nv_bfloat16* dy, const float* x, const float* rstd, cons
 // --------------------------------------------------------------------------------------------
 // embedding gather (fp32 table -> fp32 residual stream) and its scatter-add backward
 // --------------------------------------------------------------------------------------------
+// tok_index[cu[p] + pos] = p * L + pos : packed (un-padded) row -> flat index into the padded [P][L] id / score arrays
+__global__ void build_tok_index_kernel(const int* __restrict__ cu, int* __restrict__ tok_index, int P, int L) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int psg = blockIdx.x;
+  const int r0 = cu[psg], n = cu[psg + 1] - r0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) tok_index[r0 + i] = psg * L + i;
+}
+int build_tok_index(const int* cu, int* tok_index, int P, int L, cudaStream_t s) {
+  launch_pdl(build_tok_index_kernel, dim3(P), dim3(128), 0, s, cu, tok_index, P, L);
+  LAKO_CHECK_LAUNCH();
+  return LAKO_OK;
+}
+
 __global__ void embed_gather_kernel(const long long* __restrict__ ids, const float* __restrict__ table,
-                                    float* __restrict__ out, int rows, int d, int vocab, const DropSpec ds) {
+                                    float* __restrict__ out, int rows, int d, int vocab, const DropSpec ds,
+                                    const int* __restrict__ index) {
   pdl_launch_dependents();
   pdl_wait();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= rows) return;
-  long long id = ids[warp];
+  long long id = ids[index ? index[warp] : warp];
   if (id < 0 || id >= vocab) id = 0;
   const float4* src = reinterpret_cast<const float4*>(table + static_cast<size_t>(id) * d);
   float4* dst = reinterpret_cast<float4*>(out + static_cast<size_t>(warp) * d);
@@ -320,21 +335,22 @@ __global__ void embed_gather_kernel(const long long* __restrict__ ids, const flo
 }
 
 int embed_gather(const long long* ids, const float* table, float* out, int rows, int d, int vocab, cudaStream_t s,
-                 DropSpec ds) {
+                 DropSpec ds, const int* index) {
   LAKO_REQUIRE(rows > 0 && d % 8 == 0, LAKO_ERR_BAD_ARG);
-  launch_pdl(embed_gather_kernel, dim3((rows + 7) / 8), dim3(256), 0, s, ids, table, out, rows, d, vocab, ds);
+  launch_pdl(embed_gather_kernel, dim3((rows + 7) / 8), dim3(256), 0, s, ids, table, out, rows, d, vocab, ds, index);
   LAKO_CHECK_LAUNCH();
   return LAKO_OK;
 }
 
 __global__ void embed_scatter_add_kernel(const long long* __restrict__ ids, const float* __restrict__ dres,
-                                         float* __restrict__ dtable, int rows, int d, int vocab, const DropSpec ds) {
+                                         float* __restrict__ dtable, int rows, int d, int vocab, const DropSpec ds,
+                                         const int* __restrict__ index) {
   pdl_launch_dependents();
   pdl_wait();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= rows) return;
-  long long id = ids[warp];
+  long long id = ids[index ? index[warp] : warp];
   if (id < 0 || id >= vocab) id = 0;
   const float4* src = reinterpret_cast<const float4*>(dres + static_cast<size_t>(warp) * d);
   float* dst = dtable + static_cast<size_t>(id) * d;
@@ -354,9 +370,10 @@ __global__ void embed_scatter_add_kernel(const long long* __restrict__ ids, cons
 }
 
 int embed_scatter_add(const long long* ids, const float* dres, float* dtable, int rows, int d, int vocab,
-                      cudaStream_t s, DropSpec ds) {
+                      cudaStream_t s, DropSpec ds, const int* index) {
   LAKO_REQUIRE(rows > 0 && d % 8 == 0, LAKO_ERR_BAD_ARG);
-  launch_pdl(embed_scatter_add_kernel, dim3((rows + 7) / 8), dim3(256), 0, s, ids, dres, dtable, rows, d, vocab, ds);
+  launch_pdl(embed_scatter_add_kernel, dim3((rows + 7) / 8), dim3(256), 0, s, ids, dres, dtable, rows, d, vocab, ds,
+             index);
   LAKO_CHECK_LAUNCH();
   return LAKO_OK;
 }

@@ -45,7 +45,8 @@ struct EncAttnParams {
   const float* bias_lut;      // [H][2L-1]
   __nv_bfloat16* out;         // [P*L][inner]
   float* lse;                 // [P][H][L]
-  int L, H, inner, LK;        // LK = L rounded up to 16
+  int L, H, inner;            // L = text_maxlength (LUT size, lse pitch); per-passage length from cu when packed
+  const int* cu;              // packed (un-padded) token layout: passage p owns rows [cu[p], cu[p+1]); null = padded
   DropSpec drop;              // dropout on the attention probabilities (HF:332); group = ((psg*H+h)*L+q)*32 + key/8
 };
 
@@ -66,7 +67,8 @@ __device__ __forceinline__ void stage_lut4(float* s_lut4, const float* __restric
 // additive key mask: 0 valid, finfo.min for padded keys (HF semantics), -inf beyond the passage
 __device__ __forceinline__ void stage_kmask(float* s_kmask, const unsigned char* __restrict__ mask, int L, int tid,
                                             int nthreads) {
-  for (int i = tid; i < 256; i += nthreads) s_kmask[i] = (i < L) ? (mask[i] ? 0.f : MASK_MIN) : -INFINITY;
+  for (int i = tid; i < 256; i += nthreads)
+    s_kmask[i] = (i < L) ? ((mask == nullptr || mask[i]) ? 0.f : MASK_MIN) : -INFINITY;
 }
 
 // smem map (bytes from the 1024-aligned base):
@@ -98,10 +100,17 @@ enc_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const EncAttnPar
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int quarter = warp & 3, chalf = warp >> 2;
   const int q0 = blockIdx.x * 128, h = blockIdx.y, psg = blockIdx.z;
-  const int L = p.L, LK = p.LK;
-  const int row0 = psg * L;
-  const int ktiles = (LK + 127) / 128;
+  const int Lmax = p.L;  // LUT geometry / lse pitch
   pdl_launch_dependents();
+  int row0 = psg * Lmax, L = Lmax;  // L = this passage's token count
+  if (p.cu) {
+    pdl_wait();
+    row0 = p.cu[psg];
+    L = p.cu[psg + 1] - row0;
+    if (q0 >= L) return;  // whole query tile beyond the passage (nothing allocated yet)
+  }
+  const int LK = (L + 15) / 16 * 16;
+  const int ktiles = (LK + 127) / 128;
 
   if (tid == 0) {
     tma_prefetch_desc(&tm_qkv);
@@ -113,8 +122,8 @@ enc_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const EncAttnPar
   }
   if (warp == 0) tmem_alloc(tmem_slot, 256);
   pdl_wait();
-  stage_lut4(s_lut4, p.bias_lut + h * (2 * L - 1), 2 * L - 1, tid, 256);
-  stage_kmask(s_kmask, p.mask + static_cast<size_t>(psg) * L, L, tid, 256);
+  stage_lut4(s_lut4, p.bias_lut + h * (2 * Lmax - 1), 2 * Lmax - 1, tid, 256);
+  stage_kmask(s_kmask, p.mask ? p.mask + static_cast<size_t>(psg) * Lmax : nullptr, L, tid, 256);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -143,7 +152,7 @@ enc_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const EncAttnPar
   const int r = quarter * 32 + lane;   // query row within the tile == TMEM lane
   const int q = q0 + r;                // query position in the passage
   const int qc = min(q, L - 1);        // rows beyond the passage compute on a clamped position, never stored
-  const int b = L - 1 - qc;
+  const int b = Lmax - 1 - qc;
   const float* lutp = s_lut4 + (b & 3) * LUTCOPY + (b & ~3);
   const uint32_t t_row = tmem + (static_cast<uint32_t>(quarter * 32) << 16);
   const int nchunks = (LK + 31) / 32;
@@ -193,7 +202,7 @@ enc_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const EncAttnPar
         lsum += e[i];
       }
       if (p.drop.thresh) {  // the row sum normalises the UNdropped probabilities; only the P V operand is masked
-        const uint32_t k = drop_keep8(p.drop, (static_cast<unsigned long long>(psg * p.H + h) * L + qc) * 32 + c * 4 + u);
+        const uint32_t k = drop_keep8(p.drop, (static_cast<unsigned long long>(psg * p.H + h) * Lmax + qc) * 32 + c * 4 + u);
 #pragma unroll
         for (int i = 0; i < 8; ++i) e[i] = ((k >> i) & 1u) ? e[i] * p.drop.scale : 0.f;
       }
@@ -243,7 +252,7 @@ enc_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const EncAttnPar
         o.w = pack_bf16x2(__uint_as_float(o0[u * 8 + 6]) * inv, __uint_as_float(o0[u * 8 + 7]) * inv);
         *reinterpret_cast<uint4*>(orow + u * 8) = o;
       }
-      if (p.lse && chalf == 0) p.lse[(static_cast<size_t>(psg) * p.H + h) * L + q] = m + logf(lsum);
+      if (p.lse && chalf == 0) p.lse[(static_cast<size_t>(psg) * p.H + h) * Lmax + q] = m + logf(lsum);
     }
   }
   tc_fence_before();
@@ -256,14 +265,16 @@ enc_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const EncAttnPar
 
 // qkv bf16 [P*L][3*inner]; out bf16 [P*L][inner]; lse fp32 [P][H][L] (may be null)
 int enc_attn_fwd(const __nv_bfloat16* qkv, const unsigned char* mask, const float* bias_lut, __nv_bfloat16* out,
-                 float* lse, int P, int L, int H, cudaStream_t s, DropSpec drop) {
+                 float* lse, int P, int L, int H, cudaStream_t s, DropSpec drop, const int* cu, int packed_rows) {
   int rc = check_arch();
   if (rc) return rc;
   LAKO_REQUIRE(P > 0 && H > 0 && L > 0, LAKO_ERR_BAD_ARG);
   LAKO_REQUIRE(L <= 256, LAKO_ERR_UNSUPPORTED);  // single-tile softmax; longer passages need the looped variant
   const int inner = H * 64;
   CUtensorMap tm;
-  rc = get_tensor_map_2d(&tm, qkv, 3 * inner, static_cast<uint64_t>(P) * L, 3 * inner, 64, 128);
+  const uint64_t total_rows = cu ? static_cast<uint64_t>(packed_rows) : static_cast<uint64_t>(P) * L;
+  LAKO_REQUIRE(total_rows > 0, LAKO_ERR_BAD_ARG);
+  rc = get_tensor_map_2d(&tm, qkv, 3 * inner, total_rows, 3 * inner, 64, 128);
   if (rc) return rc;
   static bool configured = false;
   if (!configured) {
@@ -282,7 +293,7 @@ int enc_attn_fwd(const __nv_bfloat16* qkv, const unsigned char* mask, const floa
   p.L = L;
   p.H = H;
   p.inner = inner;
-  p.LK = (L + 15) / 16 * 16;
+  p.cu = cu;
   p.drop = drop;
   ProfScope prof(PROF_ENC_ATTN_FWD, 4.0 * P * H * static_cast<double>(L) * L * 64, s);
   dim3 grid((L + 127) / 128, H, P);
@@ -307,6 +318,7 @@ struct EncAttnBwdParams {
   __nv_bfloat16* dqkv;           // [P*L][3*inner]
   float* dlut;                   // [H][2L-1]  += sum over (q,k) diagonals of dS (bias gradient, pre-bucket)
   int L, H, inner;
+  const int* cu;                 // packed layout offsets (see EncAttnParams); null = padded
   DropSpec drop;
 };
 
@@ -337,11 +349,17 @@ enc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int quarter = warp & 3, chalf = warp >> 2;
   const int h = blockIdx.x, psg = blockIdx.y;
-  const int L = p.L;
-  const int row0 = psg * L;
-  const int nt = (L + 127) / 128;  // 128-row tiles of queries == of keys
-  const int nlut = 2 * L - 1;
+  const int Lmax = p.L;  // LUT geometry / lse pitch
+  const int nlut = 2 * Lmax - 1;
   pdl_launch_dependents();
+  int row0 = psg * Lmax, L = Lmax;  // L = this passage's token count
+  if (p.cu) {
+    pdl_wait();
+    row0 = p.cu[psg];
+    L = p.cu[psg + 1] - row0;
+    if (L <= 0) return;
+  }
+  const int nt = (L + 127) / 128;  // 128-row tiles of queries == of keys
 
   if (tid == 0) {
     tma_prefetch_desc(&tm_qkv);
@@ -354,7 +372,7 @@ enc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
   if (warp == 0) tmem_alloc(tmem_slot, 512);
   pdl_wait();
   stage_lut4(s_lut4, p.bias_lut + h * nlut, nlut, tid, 256);
-  stage_kmask(s_kmask, p.mask + static_cast<size_t>(psg) * L, L, tid, 256);
+  stage_kmask(s_kmask, p.mask ? p.mask + static_cast<size_t>(psg) * Lmax : nullptr, L, tid, 256);
   for (int i = tid; i < 512; i += 256) s_dlut[i] = 0.f;
   {
     const int q = tid;  // 256 threads cover the (<=256) query rows: D[q] = sum_d dO*O, lse[q]
@@ -369,7 +387,7 @@ enc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
                 bf16_hi(a.y) * bf16_hi(b.y) + bf16_lo(a.z) * bf16_lo(b.z) + bf16_hi(a.z) * bf16_hi(b.z) +
                 bf16_lo(a.w) * bf16_lo(b.w) + bf16_hi(a.w) * bf16_hi(b.w);
       }
-      l = p.lse[(static_cast<size_t>(psg) * p.H + h) * L + q];
+      l = p.lse[(static_cast<size_t>(psg) * p.H + h) * Lmax + q];
     }
     s_D[q] = dsum;
     s_lse[q] = l;
@@ -425,7 +443,7 @@ enc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
     for (int qt = 0; qt < nt; ++qt) {
       const int q = qt * 128 + r;
       const int qc = min(q, L - 1);
-      const int b = L - 1 - qc;
+      const int b = Lmax - 1 - qc;
       const float* lutp = s_lut4 + (b & 3) * LUTCOPY + (b & ~3);
       mbar_wait(bar_mma, s_phase);
       s_phase ^= 1;
@@ -441,7 +459,7 @@ enc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
         tmem_ld_wait();
         const int kbase = kt * 128 + chalf * 64 + c * 32;  // first key of this 32-column chunk
         // bias-gradient index of the diagonal d = i - lane of this 32x32 sub-block: rel = k - q
-        const int idx0 = (kbase - (qt * 128 + quarter * 32)) + (L - 1);
+        const int idx0 = (kbase - (qt * 128 + quarter * 32)) + (Lmax - 1);
         float ds[32];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
@@ -455,7 +473,7 @@ enc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
           uint32_t keepm = 0xffu;
           float dscale = 1.f;
           if (p.drop.thresh) {
-            keepm = drop_keep8(p.drop, (static_cast<unsigned long long>(psg * p.H + h) * L + qc) * 32 + (kbase >> 3) + u);
+            keepm = drop_keep8(p.drop, (static_cast<unsigned long long>(psg * p.H + h) * Lmax + qc) * 32 + (kbase >> 3) + u);
             dscale = p.drop.scale;
           }
 #pragma unroll
@@ -616,16 +634,18 @@ enc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
 
 int enc_attn_bwd(const __nv_bfloat16* qkv, const __nv_bfloat16* out, const __nv_bfloat16* dout, const float* lse,
                  const unsigned char* mask, const float* bias_lut, __nv_bfloat16* dqkv, float* dlut, int P, int L,
-                 int H, cudaStream_t s, DropSpec drop) {
+                 int H, cudaStream_t s, DropSpec drop, const int* cu, int packed_rows) {
   int rc = check_arch();
   if (rc) return rc;
   LAKO_REQUIRE(P > 0 && H > 0 && L > 0, LAKO_ERR_BAD_ARG);
   LAKO_REQUIRE(L <= 256, LAKO_ERR_UNSUPPORTED);
   const int inner = H * 64;
   CUtensorMap tm_qkv, tm_do;
-  rc = get_tensor_map_2d(&tm_qkv, qkv, 3 * inner, static_cast<uint64_t>(P) * L, 3 * inner, 64, 128);
+  const uint64_t total_rows = cu ? static_cast<uint64_t>(packed_rows) : static_cast<uint64_t>(P) * L;
+  LAKO_REQUIRE(total_rows > 0, LAKO_ERR_BAD_ARG);
+  rc = get_tensor_map_2d(&tm_qkv, qkv, 3 * inner, total_rows, 3 * inner, 64, 128);
   if (rc) return rc;
-  rc = get_tensor_map_2d(&tm_do, dout, inner, static_cast<uint64_t>(P) * L, inner, 64, 128);
+  rc = get_tensor_map_2d(&tm_do, dout, inner, total_rows, inner, 64, 128);
   if (rc) return rc;
   static bool configured = false;
   if (!configured) {
@@ -647,6 +667,7 @@ int enc_attn_bwd(const __nv_bfloat16* qkv, const __nv_bfloat16* out, const __nv_
   p.L = L;
   p.H = H;
   p.inner = inner;
+  p.cu = cu;
   p.drop = drop;
   ProfScope prof(PROF_ENC_ATTN_BWD, 10.0 * P * H * static_cast<double>(L) * L * 64, s);
   dim3 grid(H, P);

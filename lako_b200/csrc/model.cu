@@ -89,6 +89,10 @@ struct DecLayerAct {
 struct Work {
   // sizes
   int B, N, L, T, P, M, Mtok, BT;
+  // packed (un-padded) execution: Mrows = number of token rows actually processed
+  int Mrows;
+  const int* cu;
+  int* tok_index;
   // encoder
   std::vector<float*> X;  // 2*nl+1 residual-stream snapshots (train) or 2 ping-pong (eval)
   std::vector<EncLayerAct> enc;
@@ -207,6 +211,9 @@ void carve(const lako_dims& dm, int B, int N, int L, int T, int mode, void* base
   w.row_loss = b.take<float>(BT);
   w.xattn_ws = b.take<float>(xattn_workspace_bytes(B, dm.n_heads, T, w.M) / sizeof(float));
   w.dec_ids = b.take<long long>(BT);
+  w.tok_index = b.take<int>(Mt);
+  w.Mrows = w.Mtok;
+  w.cu = nullptr;
   if (train) {
     const size_t vpad = (static_cast<size_t>(dm.vocab) + 7) / 8 * 8;
     w.dlogits = b.take<bf16>(BT * vpad);
@@ -268,6 +275,18 @@ struct Dropper {
   DropSpec none() const { return DropSpec{}; }
 };
 
+inline int set_packing(Work& w, const lako_batch* bt, cudaStream_t s) {
+  w.cu = nullptr;
+  w.Mrows = w.Mtok;
+  if (bt->cu_seqlens) {
+    LAKO_REQUIRE(bt->packed_tokens > 0 && bt->packed_tokens <= w.Mtok, LAKO_ERR_BAD_ARG);
+    w.cu = bt->cu_seqlens;
+    w.Mrows = bt->packed_tokens;
+  }
+  (void)s;
+  return LAKO_OK;
+}
+
 struct Ptrs {
   const lako_dims* dm;
   lako_layout lo;
@@ -298,8 +317,10 @@ int make_ptrs(const lako_fidt5* m, Ptrs& p) {
 // ---- encoder: ids (P*L) -> mem bf16 [Mtok][d] and kv_all bf16 [Mtok][nl*2*inner]
 int encode(const Ptrs& p, const lako_fidt5* m, Work& w, const long long* ids, const unsigned char* mask, bool train,
            cudaStream_t s, const Dropper& dr) {
-  const int d = p.d, inner = p.inner, ff = p.ff, nl = p.nl, Mt = w.Mtok;
-  RC(embed_gather(ids, p.wf + p.lo.shared, w.X[0], Mt, d, p.V, s, dr(0, E_EMB)));
+  const int d = p.d, inner = p.inner, ff = p.ff, nl = p.nl, Mt = w.Mrows;
+  const unsigned char* amask = w.cu ? nullptr : mask;  // packed rows are all valid tokens
+  if (w.cu) RC(build_tok_index(w.cu, w.tok_index, w.P, w.L, s));
+  RC(embed_gather(ids, p.wf + p.lo.shared, w.X[0], Mt, d, p.V, s, dr(0, E_EMB), w.cu ? w.tok_index : nullptr));
   RC(build_bias_lut(p.wf + p.lo.enc_relbias, m->enc_buckets, w.lut_enc, p.H, w.L, m->bucket_center, s));
   for (int l = 0; l < nl; ++l) {
     EncLayerAct& a = w.enc[l];
@@ -309,7 +330,7 @@ int encode(const Ptrs& p, const lako_fidt5* m, Work& w, const long long* ids, co
       RC(rmsnorm_fwd(w.X[2 * l - 1], w.delta_enc, w.X[2 * l], p.wf + p.lo.enc_ln0[l], a.n_a, a.rstd_a, Mt, d, p.eps,
                      1.f, s, dr(l - 1, E_FF)));
     RC(lin_fwd(a.n_a, p.wb + p.lo.enc_qkv[l], a.qkv, Mt, 3 * inner, d, EPI_BF16, 1.f, s));
-    RC(enc_attn_fwd(a.qkv, mask, w.lut_enc, a.ao, a.lse, w.P, w.L, p.H, s, dr(l, E_ATTN)));
+    RC(enc_attn_fwd(a.qkv, amask, w.lut_enc, a.ao, a.lse, w.P, w.L, p.H, s, dr(l, E_ATTN), w.cu, Mt));
     RC(lin_fwd(a.ao, p.wb + p.lo.enc_o[l], w.delta_enc, Mt, d, inner, EPI_BF16, 1.f, s));
     RC(rmsnorm_fwd(w.X[2 * l], w.delta_enc, w.X[2 * l + 1], p.wf + p.lo.enc_ln1[l], a.n_f, a.rstd_f, Mt, d, p.eps, 1.f,
                    s, dr(l, E_O)));
@@ -347,6 +368,8 @@ extern "C" int lako_fidt5_forward(const lako_fidt5* m, const lako_batch* bt, int
   const int d = p.d, inner = p.inner, ff = p.ff, nl = p.nl, BT = w.BT;
   Dropper dr{bt->dropout_seed, bt->dropout_step, train ? bt->dropout_p : 0.f};
   LAKO_REQUIRE(dr.p >= 0.f && dr.p < 0.9f, LAKO_ERR_BAD_ARG);
+  RC(set_packing(w, bt, s));
+  const unsigned char* xmask = w.cu ? nullptr : bt->mask;
   RC(encode(p, m, w, reinterpret_cast<const long long*>(bt->ids), bt->mask, train, s, dr));
 
   const long long* labels = reinterpret_cast<const long long*>(bt->labels);
@@ -366,8 +389,8 @@ extern "C" int lako_fidt5_forward(const lako_fidt5* m, const lako_batch* bt, int
     RC(rmsnorm_fwd(w.Y[3 * l], w.delta_dec, w.Y[3 * l + 1], p.wf + p.lo.dec_ln1[l], a.n_c, a.rstd_c, BT, d, p.eps, 1.f,
                    s, dr(l, D_O)));
     RC(lin_fwd(a.n_c, p.wb + p.lo.dec_xq[l], a.q, BT, inner, d, EPI_BF16, 1.f, s));
-    RC(xattn_fwd(a.q, w.kv_all, bt->mask, a.xo, a.lse, nullptr, w.xattn_ws, bt->B, bt->T, w.M, p.H, inner,
-                 nl * 2 * inner, l * 2 * inner, l * 2 * inner + inner, inner, s, dr(l, D_XP)));
+    RC(xattn_fwd(a.q, w.kv_all, xmask, a.xo, a.lse, nullptr, w.xattn_ws, bt->B, bt->T, w.M, p.H, inner,
+                 nl * 2 * inner, l * 2 * inner, l * 2 * inner + inner, inner, s, dr(l, D_XP), w.cu, bt->N, nullptr));
     RC(lin_fwd(a.xo, p.wb + p.lo.dec_xo[l], w.delta_dec, BT, d, inner, EPI_BF16, 1.f, s));
     RC(rmsnorm_fwd(w.Y[3 * l + 1], w.delta_dec, w.Y[3 * l + 2], p.wf + p.lo.dec_ln2[l], a.n_f, a.rstd_f, BT, d, p.eps,
                    1.f, s, dr(l, D_XO)));
@@ -396,7 +419,9 @@ extern "C" int lako_fidt5_backward(const lako_fidt5* m, const lako_batch* bt, co
   Work w;
   carve(m->dims, bt->B, bt->N, bt->L, bt->T, 1, bt->workspace, w);
   LAKO_REQUIRE(w.bytes <= bt->workspace_bytes, LAKO_ERR_WORKSPACE);
-  const int d = p.d, inner = p.inner, ff = p.ff, nl = p.nl, BT = w.BT, Mt = w.Mtok, H = p.H;
+  RC(set_packing(w, bt, s));
+  const unsigned char* xmask = w.cu ? nullptr : bt->mask;
+  const int d = p.d, inner = p.inner, ff = p.ff, nl = p.nl, BT = w.BT, Mt = w.Mrows, H = p.H;
   const size_t vpad = (static_cast<size_t>(p.V) + 7) / 8 * 8;
   const float alpha = 1.0f / sqrtf(static_cast<float>(d));
   float* g = p.g;
@@ -428,8 +453,8 @@ extern "C" int lako_fidt5_backward(const lako_fidt5* m, const lako_batch* bt, co
     RC(lin_dgrad(w.dres_dec_b, p.wb + p.lo.dec_xo[l], w.dao_dec, BT, d, inner, nullptr, 1.f, s));
     RC(lin_wgrad(w.dres_dec_b, a.xo, g + p.lo.dec_xo[l], BT, d, inner, 1.f, s));
     cudaMemsetAsync(w.dq_f32, 0, sizeof(float) * BT * inner, s);
-    RC(xattn_bwd(a.q, w.kv_all, bt->mask, a.xo, w.dao_dec, a.lse, w.dkv_all, w.dq_f32, bt->B, bt->T, w.M, H, inner,
-                 nl * 2 * inner, l * 2 * inner, l * 2 * inner + inner, inner, s, dr(l, D_XP)));
+    RC(xattn_bwd(a.q, w.kv_all, xmask, a.xo, w.dao_dec, a.lse, w.dkv_all, w.dq_f32, bt->B, bt->T, w.M, H, inner,
+                 nl * 2 * inner, l * 2 * inner, l * 2 * inner + inner, inner, s, dr(l, D_XP), w.cu, bt->N));
     RC(cast_f32_to_bf16(w.dq_f32, w.dq_dec, static_cast<size_t>(BT) * inner, s));
     RC(lin_dgrad(w.dq_dec, p.wb + p.lo.dec_xq[l], w.dn_dec, BT, inner, d, nullptr, 1.f, s));
     RC(lin_wgrad(w.dq_dec, a.n_c, g + p.lo.dec_xq[l], BT, inner, d, 1.f, s));
@@ -463,15 +488,15 @@ extern "C" int lako_fidt5_backward(const lako_fidt5* m, const lako_batch* bt, co
                    g + p.lo.enc_ln1[l], Mt, d, 1, 1.f, s, dr.none(), dr(l, E_O)));
     RC(lin_dgrad(w.dres_enc_b, p.wb + p.lo.enc_o[l], w.dao_enc, Mt, d, inner, nullptr, 1.f, s));
     RC(lin_wgrad(w.dres_enc_b, a.ao, g + p.lo.enc_o[l], Mt, d, inner, 1.f, s));
-    RC(enc_attn_bwd(a.qkv, a.ao, w.dao_enc, a.lse, bt->mask, w.lut_enc, w.dqkv_enc, w.dlut_enc, w.P, w.L, H, s,
-                    dr(l, E_ATTN)));
+    RC(enc_attn_bwd(a.qkv, a.ao, w.dao_enc, a.lse, xmask, w.lut_enc, w.dqkv_enc, w.dlut_enc, w.P, w.L, H, s,
+                    dr(l, E_ATTN), w.cu, Mt));
     RC(lin_dgrad(w.dqkv_enc, p.wb + p.lo.enc_qkv[l], w.dn_enc, Mt, 3 * inner, d, nullptr, 1.f, s));
     RC(lin_wgrad(w.dqkv_enc, a.n_a, g + p.lo.enc_qkv[l], Mt, 3 * inner, d, 1.f, s));
     RC(rmsnorm_bwd(w.dn_enc, w.X[2 * l], a.rstd_a, p.wf + p.lo.enc_ln0[l], w.dres_enc, w.dres_enc_b,
                    g + p.lo.enc_ln0[l], Mt, d, 1, 1.f, s, dr.none(), l > 0 ? dr(l - 1, E_FF) : dr.none()));
   }
   RC(embed_scatter_add(reinterpret_cast<const long long*>(bt->ids), w.dres_enc, g + p.lo.shared, Mt, d, p.V, s,
-                       dr(0, E_EMB)));
+                       dr(0, E_EMB), w.cu ? w.tok_index : nullptr));
   RC(fold_dlut(w.dlut_enc, m->enc_buckets, g + p.lo.enc_relbias, H, w.L, m->bucket_center, m->dims.n_buckets, s));
   return LAKO_OK;
 }
@@ -539,6 +564,8 @@ extern "C" int lako_fidt5_generate(const lako_fidt5* m, const lako_batch* bt, in
   LAKO_REQUIRE(gw.bytes <= bt->workspace_bytes, LAKO_ERR_WORKSPACE);
   Work& w = gw.enc;
   const int d = p.d, inner = p.inner, ff = p.ff, nl = p.nl, B = bt->B, H = p.H;
+  RC(set_packing(w, bt, s));
+  const unsigned char* xmask = w.cu ? nullptr : bt->mask;
   RC(encode(p, m, w, reinterpret_cast<const long long*>(bt->ids), bt->mask, false, s, Dropper{0, 0, 0.f}));
   RC(build_bias_lut(p.wf + p.lo.dec_relbias, m->dec_buckets, gw.lut_dec, H, max_length, m->bucket_center, s));
   launch_pdl(gen_init_kernel, dim3((B + 127) / 128), dim3(128), 0, s, gw.unfinished, gw.n_unf, gw.next_ids,
@@ -563,8 +590,8 @@ extern "C" int lako_fidt5_generate(const lako_fidt5* m, const lako_batch* bt, in
       RC(lin_fwd(a.n_c, p.wb + p.lo.dec_xq[l], a.q, B, inner, d, EPI_BF16, 1.f, s));
       float* ts = nullptr;
       if (step == 0) ts = (l < first_half) ? tok_score_first : tok_score_last;
-      RC(xattn_fwd(a.q, w.kv_all, bt->mask, a.xo, nullptr, ts, w.xattn_ws, B, 1, w.M, H, inner, nl * 2 * inner,
-                   l * 2 * inner, l * 2 * inner + inner, inner, s));
+      RC(xattn_fwd(a.q, w.kv_all, xmask, a.xo, nullptr, ts, w.xattn_ws, B, 1, w.M, H, inner, nl * 2 * inner,
+                   l * 2 * inner, l * 2 * inner + inner, inner, s, DropSpec{}, w.cu, bt->N, w.cu ? w.tok_index : nullptr));
       RC(lin_fwd(a.xo, p.wb + p.lo.dec_xo[l], w.delta_dec, B, d, inner, EPI_BF16, 1.f, s));
       RC(rmsnorm_fwd(w.Y[0], w.delta_dec, w.Y[0], p.wf + p.lo.dec_ln2[l], a.n_f, nullptr, B, d, p.eps, 1.f, s));
       RC(lin_fwd(a.n_f, p.wb + p.lo.dec_wi[l], a.h, B, ff, d, EPI_BF16_RELU, 1.f, s));

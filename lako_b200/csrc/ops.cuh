@@ -20,9 +20,10 @@ int rmsnorm_bwd(const __nv_bfloat16* dy, const float* x, const float* rstd, cons
                 __nv_bfloat16* dres_bf16, float* dw, int rows, int d, int accumulate, float dy_scale, cudaStream_t s,
                 DropSpec yd = DropSpec{}, DropSpec bd = DropSpec{});
 int embed_gather(const long long* ids, const float* table, float* out, int rows, int d, int vocab, cudaStream_t s,
-                 DropSpec ds = DropSpec{});
+                 DropSpec ds = DropSpec{}, const int* index = nullptr);
 int embed_scatter_add(const long long* ids, const float* dres, float* dtable, int rows, int d, int vocab,
-                      cudaStream_t s, DropSpec ds = DropSpec{});
+                      cudaStream_t s, DropSpec ds = DropSpec{}, const int* index = nullptr);
+int build_tok_index(const int* cu, int* tok_index, int P, int L, cudaStream_t s);
 int shift_right(const long long* labels, long long* dec_ids, int B, int T, cudaStream_t s);
 int count_valid(const long long* labels, int n, float* stats, cudaStream_t s);
 int ce_fwd_bwd(const float* logits, const long long* labels, float* stats, float* row_loss, __nv_bfloat16* dlogits,
@@ -43,26 +44,30 @@ int build_bias_lut(const float* table, const int* buckets, float* lut, int H, in
 int fold_dlut(const float* dlut, const int* buckets, float* dtable, int H, int L, int bucket_center, int nb,
               cudaStream_t s);
 int enc_attn_fwd(const __nv_bfloat16* qkv, const unsigned char* mask, const float* bias_lut, __nv_bfloat16* out,
-                 float* lse, int P, int L, int H, cudaStream_t s, DropSpec drop = DropSpec{});
+                 float* lse, int P, int L, int H, cudaStream_t s, DropSpec drop = DropSpec{}, const int* cu = nullptr,
+                 int packed_rows = 0);
 int enc_attn_bwd(const __nv_bfloat16* qkv, const __nv_bfloat16* out, const __nv_bfloat16* dout, const float* lse,
                  const unsigned char* mask, const float* bias_lut, __nv_bfloat16* dqkv, float* dlut, int P, int L,
-                 int H, cudaStream_t s, DropSpec drop = DropSpec{});
+                 int H, cudaStream_t s, DropSpec drop = DropSpec{}, const int* cu = nullptr, int packed_rows = 0);
 
 // dec_attn.cu
 size_t xattn_workspace_bytes(int B, int H, int T, int M);
 int xattn_fwd(const __nv_bfloat16* q, const __nv_bfloat16* kv, const unsigned char* mask, __nv_bfloat16* out, float* lse,
               float* tok_score, float* workspace, int B, int T, int M, int H, int ldq, int ldkv, int koff, int voff,
-              int ldo, cudaStream_t s, DropSpec drop = DropSpec{});
+              int ldo, cudaStream_t s, DropSpec drop = DropSpec{}, const int* cu = nullptr, int npsg = 1,
+              const int* tok_index = nullptr);
 int xattn_bwd(const __nv_bfloat16* q, const __nv_bfloat16* kv, const unsigned char* mask, const __nv_bfloat16* out,
               const __nv_bfloat16* dout, const float* lse, __nv_bfloat16* dkv, float* dq_f32, int B, int T, int M,
-              int H, int ldq, int ldkv, int koff, int voff, int ldo, cudaStream_t s, DropSpec drop = DropSpec{});
+              int H, int ldq, int ldkv, int koff, int voff, int ldo, cudaStream_t s, DropSpec drop = DropSpec{},
+              const int* cu = nullptr, int npsg = 1);
 // xattn_mma.cu
 int xattn_fwd_mma(const __nv_bfloat16* q, const __nv_bfloat16* kv, const unsigned char* mask, float* tok_score,
                   float* workspace, int B, int T, int M, int H, int ldq, int ldkv, int koff, int voff, cudaStream_t s,
-                  DropSpec drop = DropSpec{});
+                  DropSpec drop = DropSpec{}, const int* cu = nullptr, int npsg = 1, const int* tok_index = nullptr);
 int xattn_bwd_mma(const __nv_bfloat16* q, const __nv_bfloat16* kv, const unsigned char* mask, const __nv_bfloat16* out,
                   const __nv_bfloat16* dout, const float* lse, __nv_bfloat16* dkv, float* dq_f32, int B, int T, int M,
-                  int H, int ldq, int ldkv, int koff, int voff, int ldo, cudaStream_t s, DropSpec drop = DropSpec{});
+                  int H, int ldq, int ldkv, int koff, int voff, int ldo, cudaStream_t s, DropSpec drop = DropSpec{},
+                  const int* cu = nullptr, int npsg = 1);
 int dself_fwd(const __nv_bfloat16* qkv, const float* lut, __nv_bfloat16* out, float* probs, int B, int T, int H,
               cudaStream_t s, DropSpec drop = DropSpec{});
 int dself_bwd(const __nv_bfloat16* qkv, const __nv_bfloat16* dout, const float* probs, __nv_bfloat16* dqkv, float* dlut,

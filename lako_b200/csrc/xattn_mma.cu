@@ -64,6 +64,10 @@ struct XMParams {
   __nv_bfloat16* dkv;         // bwd
   float* dq;                  // bwd [B*T][H*64] fp32 (pre-zeroed)
   int T, TP, M, H, ldq, ldkv, koff, voff, ldo, splits;
+  // packed (un-padded) memory: question b owns kv rows [cu[b*npsg], cu[(b+1)*npsg]); null = padded [B][M]
+  const int* cu;
+  int npsg;
+  const int* tok_index;  // packed row -> index into the padded [B][M] score buffer (packed layout only)
   DropSpec drop;  // attention-probability dropout; group = ((b*H+h)*T + t) * ceil(M/8) + key/8
 };
 
@@ -85,14 +89,21 @@ __global__ void __launch_bounds__(128) xattn_fwd_mma_kernel(const XMParams p) {
   const int split = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t4 = lane & 3;
   const int k0 = split * XM_CH;
-  const int nk = min(XM_CH, p.M - k0);
-  const size_t kvrow0 = static_cast<size_t>(b) * p.M + k0;
+  int kstart = b * p.M, Mb = p.M;
+  if (p.cu) {
+    kstart = p.cu[b * p.npsg];
+    Mb = p.cu[(b + 1) * p.npsg] - kstart;
+  }
+  if (k0 >= Mb) return;  // chunk beyond this question's memory (CTA-uniform)
+  const int nk = min(XM_CH, Mb - k0);
+  const size_t kvrow0 = static_cast<size_t>(kstart) + k0;
   stage_sw(sK, p.kv + kvrow0 * p.ldkv + p.koff + h * 64, p.ldkv, 128, nk, tid, 128);
   stage_sw(sV, p.kv + kvrow0 * p.ldkv + p.voff + h * 64, p.ldkv, 128, nk, tid, 128);
   stage_sw(sQ, p.q + static_cast<size_t>(b) * p.T * p.ldq + h * 64, p.ldq, p.TP, p.T, tid, 128);
   {
     const int j = tid;
-    sMask[j] = (j < nk) ? (p.mask[static_cast<size_t>(b) * p.M + k0 + j] ? 0.f : XM_MASK_MIN) : -INFINITY;
+    const bool valid = (p.mask == nullptr) || p.mask[static_cast<size_t>(b) * p.M + k0 + j];
+    sMask[j] = (j < nk) ? (valid ? 0.f : XM_MASK_MIN) : -INFINITY;
   }
   cp_async_wait_all();
   __syncthreads();
@@ -126,9 +137,14 @@ __global__ void __launch_bounds__(128) xattn_fwd_mma_kernel(const XMParams p) {
       const int key = kb + nt * 8 + t4 * 2;
       const float m0 = sMask[key], m1 = sMask[key + 1];
       if (p.tok_score && mt == 0 && g == 0) {  // query 0 lives in row g == 0
-        float* ts = p.tok_score + static_cast<size_t>(b) * p.M + k0 + key;
-        if (m0 == 0.f) atomicAdd(ts, sacc[nt][0]);
-        if (m1 == 0.f) atomicAdd(ts + 1, sacc[nt][1]);
+        if (p.tok_index) {
+          if (m0 == 0.f) atomicAdd(p.tok_score + p.tok_index[kvrow0 + key], sacc[nt][0]);
+          if (m1 == 0.f) atomicAdd(p.tok_score + p.tok_index[kvrow0 + key + 1], sacc[nt][1]);
+        } else {
+          float* ts = p.tok_score + static_cast<size_t>(b) * p.M + k0 + key;
+          if (m0 == 0.f) atomicAdd(ts, sacc[nt][0]);
+          if (m1 == 0.f) atomicAdd(ts + 1, sacc[nt][1]);
+        }
       }
       sacc[nt][0] += m0;
       sacc[nt][1] += m1;
@@ -259,13 +275,22 @@ __global__ void __launch_bounds__(128) xattn_bwd_mma_kernel(const XMParams p) {
   const int split = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t4 = lane & 3;
   const int k0 = split * XM_CH;
-  const int nk = min(XM_CH, p.M - k0);
-  const size_t kvrow0 = static_cast<size_t>(b) * p.M + k0;
+  int kstart = b * p.M, Mb = p.M;
+  if (p.cu) {
+    kstart = p.cu[b * p.npsg];
+    Mb = p.cu[(b + 1) * p.npsg] - kstart;
+  }
+  if (k0 >= Mb) return;
+  const int nk = min(XM_CH, Mb - k0);
+  const size_t kvrow0 = static_cast<size_t>(kstart) + k0;
   stage_sw(sK, p.kv + kvrow0 * p.ldkv + p.koff + h * 64, p.ldkv, 128, nk, tid, 128);
   stage_sw(sV, p.kv + kvrow0 * p.ldkv + p.voff + h * 64, p.ldkv, 128, nk, tid, 128);
   stage_sw(sQ, p.q + static_cast<size_t>(b) * p.T * p.ldq + h * 64, p.ldq, p.TP, p.T, tid, 128);
   stage_sw(sDO, p.dout + static_cast<size_t>(b) * p.T * p.ldo + h * 64, p.ldo, p.TP, p.T, tid, 128);
-  sMask[tid] = (tid < nk) ? (p.mask[static_cast<size_t>(b) * p.M + k0 + tid] ? 0.f : XM_MASK_MIN) : -INFINITY;
+  {
+    const bool valid = (p.mask == nullptr) || p.mask[static_cast<size_t>(b) * p.M + k0 + tid];
+    sMask[tid] = (tid < nk) ? (valid ? 0.f : XM_MASK_MIN) : -INFINITY;
+  }
   for (int t = warp; t < 64; t += 4) {  // D[t] = sum_d dO*O ; lse = +inf beyond T -> P = 0
     float acc = 0.f;
     if (t < p.T) {
@@ -453,7 +478,7 @@ static size_t xm_smem_bytes(int TP, bool bwd) {
 
 int xattn_fwd_mma(const __nv_bfloat16* q, const __nv_bfloat16* kv, const unsigned char* mask, float* tok_score,
                   float* workspace, int B, int T, int M, int H, int ldq, int ldkv, int koff, int voff,
-                  cudaStream_t s, DropSpec drop) {
+                  cudaStream_t s, DropSpec drop, const int* cu, int npsg, const int* tok_index) {
   LAKO_REQUIRE(B > 0 && T > 0 && T <= 64 && M > 0 && H > 0, LAKO_ERR_UNSUPPORTED);
   LAKO_REQUIRE(ldq % 8 == 0 && ldkv % 8 == 0 && koff % 8 == 0 && voff % 8 == 0, LAKO_ERR_BAD_ARG);
   XMParams p{};
@@ -461,6 +486,9 @@ int xattn_fwd_mma(const __nv_bfloat16* q, const __nv_bfloat16* kv, const unsigne
   p.T = T; p.TP = (T + 15) / 16 * 16; p.M = M; p.H = H; p.ldq = ldq; p.ldkv = ldkv; p.koff = koff; p.voff = voff;
   p.splits = (M + XM_CH - 1) / XM_CH;
   p.drop = drop;
+  p.cu = cu;
+  p.npsg = npsg;
+  p.tok_index = tok_index;
   static bool configured = false;
   if (!configured) {
     cudaFuncSetAttribute(xattn_fwd_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xm_smem_bytes(64, false));
@@ -473,7 +501,8 @@ int xattn_fwd_mma(const __nv_bfloat16* q, const __nv_bfloat16* kv, const unsigne
 
 int xattn_bwd_mma(const __nv_bfloat16* q, const __nv_bfloat16* kv, const unsigned char* mask, const __nv_bfloat16* out,
                   const __nv_bfloat16* dout, const float* lse, __nv_bfloat16* dkv, float* dq_f32, int B, int T, int M,
-                  int H, int ldq, int ldkv, int koff, int voff, int ldo, cudaStream_t s, DropSpec drop) {
+                  int H, int ldq, int ldkv, int koff, int voff, int ldo, cudaStream_t s, DropSpec drop, const int* cu,
+                  int npsg) {
   LAKO_REQUIRE(B > 0 && T > 0 && T <= 64 && M > 0 && H > 0, LAKO_ERR_UNSUPPORTED);
   LAKO_REQUIRE(ldq % 8 == 0 && ldkv % 8 == 0 && koff % 8 == 0 && voff % 8 == 0 && ldo % 8 == 0, LAKO_ERR_BAD_ARG);
   XMParams p{};
@@ -482,6 +511,8 @@ int xattn_bwd_mma(const __nv_bfloat16* q, const __nv_bfloat16* kv, const unsigne
   p.ldo = ldo;
   p.splits = (M + XM_CH - 1) / XM_CH;
   p.drop = drop;
+  p.cu = cu;
+  p.npsg = npsg;
   static bool configured = false;
   if (!configured) {
     cudaFuncSetAttribute(xattn_bwd_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xm_smem_bytes(64, true));

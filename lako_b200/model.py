@@ -58,7 +58,8 @@ class _Batch(ctypes.Structure):
                 ("B", ctypes.c_int), ("N", ctypes.c_int), ("L", ctypes.c_int), ("T", ctypes.c_int),
                 ("workspace", ctypes.c_void_p), ("workspace_bytes", ctypes.c_size_t),
                 ("logits", ctypes.c_void_p), ("stats", ctypes.c_void_p), ("count_is_set", ctypes.c_int),
-                ("dropout_p", ctypes.c_float), ("dropout_step", ctypes.c_uint), ("dropout_seed", ctypes.c_ulonglong)]
+                ("dropout_p", ctypes.c_float), ("dropout_step", ctypes.c_uint), ("dropout_seed", ctypes.c_ulonglong),
+                ("cu_seqlens", ctypes.c_void_p), ("packed_tokens", ctypes.c_int)]
 
 
 class FiDT5Config:
@@ -188,6 +189,9 @@ class FiDT5(nn.Module):
         # training dropout (config.dropout_rate, 0.1 for every T5 size): Philox masks keyed by (seed, step)
         self._drop_seed = None
         self._drop_step = 0
+        # un-padded execution: when every passage mask is a prefix mask (what src/data.py's Collator emits), the
+        # encoder side runs on the valid tokens only.  Set to False to force the padded layout.
+        self.unpad = True
         self._init_weights(emb_std, seed)
 
     # ------------------------------------------------------------------ parameters
@@ -419,6 +423,24 @@ class FiDT5(nn.Module):
             self._ws[key[0]] = ws
         return ws[1]
 
+    def _packing(self, mask):
+        """(cu_seqlens int32 device tensor [B*N+1], total valid tokens) if every passage mask is a prefix mask,
+        else (None, 0).  Costs one small D2H copy (B*N+1 ints) per call."""
+        if not self.unpad:
+            return None, 0
+        B, N, L = mask.shape
+        lens = mask.sum(-1, dtype=torch.int32)
+        prefix = (mask == (torch.arange(L, device=mask.device)[None, None, :] < lens[..., None])).all()
+        info = torch.cat([lens.reshape(-1), prefix.reshape(1).to(torch.int32)]).cpu()
+        if int(info[-1]) == 0:
+            return None, 0
+        cu = torch.zeros(B * N + 1, dtype=torch.int32)
+        cu[1:] = torch.cumsum(info[:-1], 0)
+        total = int(cu[-1])
+        if total == 0:
+            return None, 0
+        return cu.to(mask.device), total
+
     def set_dropout_seed(self, seed):
         """Seed of the dropout masks (defaults to torch.initial_seed() at the first training forward; use a
         different seed per data-parallel rank, as train_reader.py:39 does with torch.manual_seed(rank + seed))."""
@@ -462,22 +484,24 @@ class FiDT5(nn.Module):
                 self._drop_seed = torch.initial_seed() & 0xFFFFFFFFFFFFFFFF
             self._drop_step += 1
         drop = (drop_p, self._drop_step & 0xFFFFFFFF, self._drop_seed or 0)
+        cu, packed = self._packing(mask)
+        pack = (cu.data_ptr() if cu is not None else 0, packed)
         m = self._model_struct(with_grad=train)
         bt = _Batch(ids.data_ptr(), mask.data_ptr(), labels.data_ptr(), B, N, L, T, ws.data_ptr(), ws.numel(),
-                    logits.data_ptr(), stats.data_ptr(), count_is_set, *drop)
+                    logits.data_ptr(), stats.data_ptr(), count_is_set, *drop, *pack)
         nat.check(L_.lako_fidt5_forward(ctypes.byref(m), ctypes.byref(bt), mode, nat.stream_ptr()), "lako_fidt5_forward")
         loss = stats[0] / torch.clamp(stats[1], min=1.0)
         if train:
-            keep = (ids, mask, labels, ws, logits, stats, (B, N, L, T), drop)
+            keep = (ids, mask, labels, ws, logits, stats, (B, N, L, T), drop, cu, pack)
             loss, logits = _LossFn.apply(self._anchor, self, keep, loss, logits)
         return (loss, logits)
 
     def _run_backward(self, keep, grad_loss):
-        ids, mask, labels, ws, logits, stats, (B, N, L, T), drop = keep
+        ids, mask, labels, ws, logits, stats, (B, N, L, T), drop, _cu, pack = keep
         L_ = nat.lib()
         m = self._model_struct(with_grad=True)
         bt = _Batch(ids.data_ptr(), mask.data_ptr(), labels.data_ptr(), B, N, L, T, ws.data_ptr(), ws.numel(),
-                    logits.data_ptr(), stats.data_ptr(), 1, *drop)
+                    logits.data_ptr(), stats.data_ptr(), 1, *drop, *pack)
         gl = grad_loss.detach().to(torch.float32).reshape(1).contiguous()
         nat.check(L_.lako_fidt5_backward(ctypes.byref(m), ctypes.byref(bt), nat.ptr(gl), nat.stream_ptr()),
                   "lako_fidt5_backward")
@@ -501,8 +525,10 @@ class FiDT5(nn.Module):
             self._tok_first = torch.zeros(B, N * L, dtype=torch.float32, device=ids.device)
             self._tok_last = torch.zeros(B, N * L, dtype=torch.float32, device=ids.device)
             tf, tl = self._tok_first, self._tok_last
+        cu, packed = self._packing(mask)
         m = self._model_struct(with_grad=False)
-        bt = _Batch(ids.data_ptr(), mask.data_ptr(), 0, B, N, L, 1, ws.data_ptr(), ws.numel(), 0, 0, 0, 0.0, 0, 0)
+        bt = _Batch(ids.data_ptr(), mask.data_ptr(), 0, B, N, L, 1, ws.data_ptr(), ws.numel(), 0, 0, 0, 0.0, 0, 0,
+                    cu.data_ptr() if cu is not None else 0, packed)
         out_len = ctypes.c_int(0)
         nat.check(L_.lako_fidt5_generate(ctypes.byref(m), ctypes.byref(bt), max_length, nat.ptr(out),
                                          ctypes.byref(out_len), nat.ptr(tf), nat.ptr(tl), nat.stream_ptr()),

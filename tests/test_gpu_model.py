@@ -116,3 +116,47 @@ def test_state_dict_roundtrip_and_t5_names(tmp_path):
     m3.load_t5(plain)
     assert torch.equal(m3.state_dict()["encoder.encoder.block.1.module.layer.1.DenseReluDense.wi.weight"],
                        sd["encoder.encoder.block.1.module.layer.1.DenseReluDense.wi.weight"])
+
+
+@pytest.mark.parametrize("path", GOLDEN[:2], ids=[os.path.basename(p) for p in GOLDEN[:2]])
+def test_padded_and_packed_paths_agree(path):
+    """The un-padded (packed) execution and the padded layout give the same loss / logits / gradients / tokens."""
+    c, cfg, sd, model = _load(path)
+    args = dict(input_ids=c["ids"].cuda(), attention_mask=c["mask"].cuda(), labels=c["labels"].cuda())
+    res = {}
+    for unpad in (True, False):
+        model.unpad = unpad
+        model.train()
+        model.zero_grad()
+        loss, logits = model(**args)
+        loss.backward()
+        torch.cuda.synchronize()
+        model.eval()
+        model.overwrite_forward_crossattention()
+        model.reset_score_storage()
+        gen = model.generate(c["ids"].cuda(), c["mask"].cuda(), max_length=c["max_length"])
+        tok = model._tok_last.clone()
+        res[unpad] = (loss.item(), logits.detach().clone(), model._flat_grad.clone(), gen.cpu(), tok)
+    a, b = res[True], res[False]
+    assert abs(a[0] - b[0]) < 2e-3
+    assert (a[1] - b[1]).abs().max().item() < 2e-2
+    assert ((a[2] - b[2]).norm() / b[2].norm()).item() < 0.05
+    assert a[3].tolist() == b[3].tolist() == c["generated"].tolist()
+    assert (a[4] - b[4]).abs().max().item() < 2e-2 * b[4].abs().max().item()
+
+
+def test_non_prefix_mask_falls_back_to_padded_layout():
+    """A mask with holes cannot be packed; the padded kernels must reproduce the oracle."""
+    from oracle import fidt5_oracle as O
+    c, cfg, sd, model = _load(GOLDEN[1])
+    mask = c["mask"].clone()
+    mask[:, :, 3] = False          # a hole inside every passage
+    mask[0, 1, 10:20] = False
+    cu, total = model._packing(mask.cuda())
+    assert cu is None and total == 0
+    model.eval()
+    with torch.no_grad():
+        loss, logits = model(input_ids=c["ids"].cuda(), attention_mask=mask.cuda(), labels=c["labels"].cuda())
+        ref_loss, ref_logits = O.fidt5_forward(sd, cfg, c["ids"], mask, c["labels"])
+    assert (logits.cpu() - ref_logits).abs().max().item() < LOGIT_ATOL_BF16
+    assert abs(loss.item() - ref_loss.item()) < 5e-3
