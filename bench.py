@@ -198,6 +198,7 @@ def main():
         labels = labels.masked_fill(tpos >= tl[:, None], -100)
         host.append((ids.pin_memory(), mask.pin_memory(), labels.pin_memory()))
     resident = [(a.to(dev), b.to(dev), c.to(dev)) for a, b, c in host]
+    valid_frac = float(sum(b.float().mean().item() for _, b, _ in host) / len(host))
 
     def barrier():
         if world > 1:
@@ -326,8 +327,12 @@ def main():
                        "global_batch": world * B, "parallelism": f"dp{world}",
                        "l2": "step working set (>4 GB of activations) far exceeds the 126 MB L2; batches rotate; no explicit flush",
                        "emb_std": EMB_STD},
+            # algorithmic (dense) FLOPs per second; the encoder side executes only the non-pad tokens
+            # (valid_token_fraction of them), which the reference's own path spends time on as well
             "model_tflops_per_gpu": round(algo_tf * steps / (ms * 1e-3), 1),
             "frac_of_bf16_peak": round(algo_tf * steps / (ms * 1e-3) / peaks["bf16_tflops"], 4),
+            "valid_token_fraction": round(valid_frac, 4),
+            "unpadded_execution": bool(model.unpad),
             "peaks": {"bf16_tflops": peaks["bf16_tflops"], "bf16_tflops_sustained": peaks.get("bf16_tflops_sustained"),
                       "hbm_gbs": peaks["hbm_gbs"], "source": which},
             "final_loss": final_loss,

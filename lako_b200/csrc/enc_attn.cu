@@ -160,9 +160,13 @@ enc_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const EncAttnPar
 
   mbar_wait(bar_s, 0);
   tc_fence_after();
+  // Warps whose 32 query rows all lie beyond the passage do no softmax work: their P rows only feed O rows that
+  // are never stored (the MMA is row-independent), so whatever bits sit in shared memory there are harmless.
+  const bool warp_live = (q0 + quarter * 32) < L;
+  const int c_lim = warp_live ? c_end : c_begin;
   // ---- pass 1: s = qk + bias + mask, row max; s goes back to TMEM
   float m = -INFINITY;
-  for (int c = c_begin; c < c_end; ++c) {
+  for (int c = c_begin; c < c_lim; ++c) {
     uint32_t v[32];
     tmem_ld_32x32(t_row + c * 32, v);
     tmem_ld_wait();
@@ -188,7 +192,7 @@ enc_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const EncAttnPar
   m = fmaxf(s_red_m[r], s_red_m[128 + r]);
   // ---- pass 2: p = exp(s - m) (un-normalised), row sum, P -> shared (bf16, K-major 128B swizzle)
   float lsum = 0.f;
-  for (int c = c_begin; c < c_end; ++c) {
+  for (int c = c_begin; c < c_lim; ++c) {
     uint32_t v[32];
     tmem_ld_32x32(t_row + c * 32, v);
     tmem_ld_wait();
@@ -451,13 +455,21 @@ enc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
       const float lse_q = s_lse[q];
       const float D_q = s_D[q];
       uint32_t ppk[2][16], dpk[2][16];  // bf16x2-packed P_drop and dS of this thread's 2 x 32 columns
+      const bool rows_live = (qt * 128 + quarter * 32) < L;  // warp-uniform: any of this warp's queries in the passage
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
+        const int kbase = kt * 128 + chalf * 64 + c * 32;  // first key of this 32-column chunk
+        if (!rows_live || kbase >= L) {
+          // nothing of this 32x32 sub-block lies inside the passage: P = dS = 0 (dV / dK sum over all 128 rows of
+          // the tile, so the zeros must really be written), no exp / Philox / diagonal sums
+#pragma unroll
+          for (int i = 0; i < 16; ++i) ppk[c][i] = dpk[c][i] = 0u;
+          continue;
+        }
         uint32_t sv[32], dpv[32];
         tmem_ld_32x32(t_row + TM_S + chalf * 64 + c * 32, sv);
         tmem_ld_32x32(t_row + TM_DP + chalf * 64 + c * 32, dpv);
         tmem_ld_wait();
-        const int kbase = kt * 128 + chalf * 64 + c * 32;  // first key of this 32-column chunk
         // bias-gradient index of the diagonal d = i - lane of this 32x32 sub-block: rel = k - q
         const int idx0 = (kbase - (qt * 128 + quarter * 32)) + (Lmax - 1);
         float ds[32];

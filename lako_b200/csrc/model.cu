@@ -8,6 +8,7 @@
 //   loss.backward()          /root/reference/train_reader.py:73   -> lako_fidt5_backward
 //   FiDT5.generate           /root/reference/src/model.py:54-60   -> lako_fidt5_generate
 //   score capture            /root/reference/src/model.py:327-329 -> tok_score accumulation in generate
+#include <cstdlib>
 #include <vector>
 
 #include "ops.cuh"
@@ -86,7 +87,12 @@ struct DecLayerAct {
   float *probs, *lse, *rstd_s, *rstd_c, *rstd_f;
 };
 
+struct DecGrad {  // per-layer bf16 gradient operands of the decoder (kept so wgrads can run off the critical path)
+  bf16 *g0, *g1, *g2, *dh, *dq, *dqkv;
+};
+
 struct Work {
+  std::vector<DecGrad> dg;
   // sizes
   int B, N, L, T, P, M, Mtok, BT;
   // packed (un-padded) execution: Mrows = number of token rows actually processed
@@ -229,6 +235,15 @@ void carve(const lako_dims& dm, int B, int N, int L, int T, int mode, void* base
     w.dmem = b.take<bf16>(Mt * d);
     w.dres_dec = b.take<float>(BT * d);
     w.dres_dec_b = b.take<bf16>(BT * d);
+    w.dg.resize(nl);
+    for (int l = 0; l < nl; ++l) {
+      w.dg[l].g0 = b.take<bf16>(BT * d);
+      w.dg[l].g1 = b.take<bf16>(BT * d);
+      w.dg[l].g2 = b.take<bf16>(BT * d);
+      w.dg[l].dh = b.take<bf16>(BT * ff);
+      w.dg[l].dq = b.take<bf16>(BT * inner);
+      w.dg[l].dqkv = b.take<bf16>(BT * 3 * inner);
+    }
     w.dn_dec = b.take<bf16>(BT * d);
     w.dh_dec = b.take<bf16>(BT * ff);
     w.dao_dec = b.take<bf16>(BT * inner);
@@ -274,6 +289,28 @@ struct Dropper {
   }
   DropSpec none() const { return DropSpec{}; }
 };
+
+// Side stream for the decoder's weight-gradient GEMMs: they are off the dgrad critical path, and the decoder chain
+// (80-row GEMMs) leaves most SMs idle, so they run concurrently with it.  Forked / joined with events on the caller's
+// stream, so the call still behaves as if everything ran in order on that stream.
+struct SideCtx {
+  cudaStream_t side = nullptr;
+  cudaEvent_t fork = nullptr, join = nullptr;
+  bool ok = false;
+};
+inline SideCtx& side_ctx() {
+  static SideCtx c;
+  if (!c.ok) {
+    const char* e = getenv("LAKO_SIDE_STREAM");
+    if (!(e && e[0] == '0') && cudaStreamCreateWithFlags(&c.side, cudaStreamNonBlocking) == cudaSuccess &&
+        cudaEventCreateWithFlags(&c.fork, cudaEventDisableTiming) == cudaSuccess &&
+        cudaEventCreateWithFlags(&c.join, cudaEventDisableTiming) == cudaSuccess)
+      c.ok = true;
+    else
+      c.side = nullptr;
+  }
+  return c;
+}
 
 inline int set_packing(Work& w, const lako_batch* bt, cudaStream_t s) {
   w.cu = nullptr;
@@ -431,43 +468,57 @@ extern "C" int lako_fidt5_backward(const lako_fidt5* m, const lako_batch* bt, co
   cudaMemsetAsync(w.dlut_enc, 0, sizeof(float) * H * (2 * w.L - 1), s);
   cudaMemsetAsync(w.dlut_dec, 0, sizeof(float) * H * (2 * w.T - 1), s);
 
+  SideCtx& sc = side_ctx();
+  cudaStream_t ws = sc.side ? sc.side : s;  // stream of the decoder wgrads
+  auto fork = [&]() {                       // make everything enqueued on s so far visible to the side stream
+    if (sc.side) {
+      cudaEventRecord(sc.fork, s);
+      cudaStreamWaitEvent(sc.side, sc.fork, 0);
+    }
+  };
   // ---- LM head
   if (loss_grad) RC(scale_bf16_dev(w.dlogits, static_cast<size_t>(BT) * vpad, loss_grad, s));
   RC(gemm_bf16(w.dlogits, p.wb + p.lo.shared, w.dhn, BT, d, p.V, static_cast<int>(vpad), d, d, 0, 1, EPI_BF16, alpha,
                nullptr, 0, 1, 0, s));
+  fork();
   RC(gemm_bf16(w.dlogits, w.hn, g + p.lo.shared, p.V, d, BT, static_cast<int>(vpad), d, d, 1, 1, EPI_F32_ATOMIC, alpha,
-               nullptr, 0, 1, 0, s));
-  RC(rmsnorm_bwd(w.dhn, w.Y[3 * nl], w.rstd_dec_final, p.wf + p.lo.dec_final_ln, w.dres_dec, w.dres_dec_b,
+               nullptr, 0, 1, 0, ws));
+  RC(rmsnorm_bwd(w.dhn, w.Y[3 * nl], w.rstd_dec_final, p.wf + p.lo.dec_final_ln, w.dres_dec, w.dg[nl - 1].g0,
                  g + p.lo.dec_final_ln, BT, d, 0, dsc, s, dr(0, D_FINAL), dr(nl - 1, D_FF)));
-  // ---- decoder layers
+  // ---- decoder layers: the dgrad chain on s; each layer's six wgrads on the side stream once the layer's
+  //      gradient operands (kept per layer) are complete
   for (int l = nl - 1; l >= 0; --l) {
     DecLayerAct& a = w.dec[l];
+    DecGrad& dg = w.dg[l];
     // FFN
-    RC(lin_dgrad(w.dres_dec_b, p.wb + p.lo.dec_wo[l], w.dh_dec, BT, d, ff, a.hbits, dsc, s));
-    RC(lin_wgrad(w.dres_dec_b, a.h, g + p.lo.dec_wo[l], BT, d, ff, 1.f, s));
-    RC(lin_dgrad(w.dh_dec, p.wb + p.lo.dec_wi[l], w.dn_dec, BT, ff, d, nullptr, 1.f, s));
-    RC(lin_wgrad(w.dh_dec, a.n_f, g + p.lo.dec_wi[l], BT, ff, d, 1.f, s));
-    RC(rmsnorm_bwd(w.dn_dec, w.Y[3 * l + 2], a.rstd_f, p.wf + p.lo.dec_ln2[l], w.dres_dec, w.dres_dec_b,
+    RC(lin_dgrad(dg.g0, p.wb + p.lo.dec_wo[l], dg.dh, BT, d, ff, a.hbits, dsc, s));
+    RC(lin_dgrad(dg.dh, p.wb + p.lo.dec_wi[l], w.dn_dec, BT, ff, d, nullptr, 1.f, s));
+    RC(rmsnorm_bwd(w.dn_dec, w.Y[3 * l + 2], a.rstd_f, p.wf + p.lo.dec_ln2[l], w.dres_dec, dg.g1,
                    g + p.lo.dec_ln2[l], BT, d, 1, 1.f, s, dr.none(), dr(l, D_XO)));
     // cross-attention
-    RC(lin_dgrad(w.dres_dec_b, p.wb + p.lo.dec_xo[l], w.dao_dec, BT, d, inner, nullptr, 1.f, s));
-    RC(lin_wgrad(w.dres_dec_b, a.xo, g + p.lo.dec_xo[l], BT, d, inner, 1.f, s));
+    RC(lin_dgrad(dg.g1, p.wb + p.lo.dec_xo[l], w.dao_dec, BT, d, inner, nullptr, 1.f, s));
     cudaMemsetAsync(w.dq_f32, 0, sizeof(float) * BT * inner, s);
     RC(xattn_bwd(a.q, w.kv_all, xmask, a.xo, w.dao_dec, a.lse, w.dkv_all, w.dq_f32, bt->B, bt->T, w.M, H, inner,
                  nl * 2 * inner, l * 2 * inner, l * 2 * inner + inner, inner, s, dr(l, D_XP), w.cu, bt->N));
-    RC(cast_f32_to_bf16(w.dq_f32, w.dq_dec, static_cast<size_t>(BT) * inner, s));
-    RC(lin_dgrad(w.dq_dec, p.wb + p.lo.dec_xq[l], w.dn_dec, BT, inner, d, nullptr, 1.f, s));
-    RC(lin_wgrad(w.dq_dec, a.n_c, g + p.lo.dec_xq[l], BT, inner, d, 1.f, s));
-    RC(rmsnorm_bwd(w.dn_dec, w.Y[3 * l + 1], a.rstd_c, p.wf + p.lo.dec_ln1[l], w.dres_dec, w.dres_dec_b,
+    RC(cast_f32_to_bf16(w.dq_f32, dg.dq, static_cast<size_t>(BT) * inner, s));
+    RC(lin_dgrad(dg.dq, p.wb + p.lo.dec_xq[l], w.dn_dec, BT, inner, d, nullptr, 1.f, s));
+    RC(rmsnorm_bwd(w.dn_dec, w.Y[3 * l + 1], a.rstd_c, p.wf + p.lo.dec_ln1[l], w.dres_dec, dg.g2,
                    g + p.lo.dec_ln1[l], BT, d, 1, 1.f, s, dr.none(), dr(l, D_O)));
     // self-attention
-    RC(lin_dgrad(w.dres_dec_b, p.wb + p.lo.dec_o[l], w.dao_dec, BT, d, inner, nullptr, 1.f, s));
-    RC(lin_wgrad(w.dres_dec_b, a.ao, g + p.lo.dec_o[l], BT, d, inner, 1.f, s));
-    RC(dself_bwd(a.qkv, w.dao_dec, a.probs, w.dqkv_dec, w.dlut_dec, bt->B, bt->T, H, s, dr(l, D_SELF)));
-    RC(lin_dgrad(w.dqkv_dec, p.wb + p.lo.dec_qkv[l], w.dn_dec, BT, 3 * inner, d, nullptr, 1.f, s));
-    RC(lin_wgrad(w.dqkv_dec, a.n_s, g + p.lo.dec_qkv[l], BT, 3 * inner, d, 1.f, s));
-    RC(rmsnorm_bwd(w.dn_dec, w.Y[3 * l], a.rstd_s, p.wf + p.lo.dec_ln0[l], w.dres_dec, w.dres_dec_b,
-                   g + p.lo.dec_ln0[l], BT, d, 1, 1.f, s, dr.none(), l > 0 ? dr(l - 1, D_FF) : dr.none()));
+    RC(lin_dgrad(dg.g2, p.wb + p.lo.dec_o[l], w.dao_dec, BT, d, inner, nullptr, 1.f, s));
+    RC(dself_bwd(a.qkv, w.dao_dec, a.probs, dg.dqkv, w.dlut_dec, bt->B, bt->T, H, s, dr(l, D_SELF)));
+    RC(lin_dgrad(dg.dqkv, p.wb + p.lo.dec_qkv[l], w.dn_dec, BT, 3 * inner, d, nullptr, 1.f, s));
+    RC(rmsnorm_bwd(w.dn_dec, w.Y[3 * l], a.rstd_s, p.wf + p.lo.dec_ln0[l], w.dres_dec,
+                   l > 0 ? w.dg[l - 1].g0 : w.dres_dec_b, g + p.lo.dec_ln0[l], BT, d, 1, 1.f, s, dr.none(),
+                   l > 0 ? dr(l - 1, D_FF) : dr.none()));
+    // weight gradients of this layer
+    fork();
+    RC(lin_wgrad(dg.g0, a.h, g + p.lo.dec_wo[l], BT, d, ff, 1.f, ws));
+    RC(lin_wgrad(dg.dh, a.n_f, g + p.lo.dec_wi[l], BT, ff, d, 1.f, ws));
+    RC(lin_wgrad(dg.g1, a.xo, g + p.lo.dec_xo[l], BT, d, inner, 1.f, ws));
+    RC(lin_wgrad(dg.dq, a.n_c, g + p.lo.dec_xq[l], BT, inner, d, 1.f, ws));
+    RC(lin_wgrad(dg.g2, a.ao, g + p.lo.dec_o[l], BT, d, inner, 1.f, ws));
+    RC(lin_wgrad(dg.dqkv, a.n_s, g + p.lo.dec_qkv[l], BT, 3 * inner, d, 1.f, ws));
   }
   RC(embed_scatter_add(w.dec_ids, w.dres_dec, g + p.lo.shared, BT, d, p.V, s, dr(0, D_EMB)));
   RC(fold_dlut(w.dlut_dec, m->dec_buckets, g + p.lo.dec_relbias, H, w.T, m->bucket_center, m->dims.n_buckets, s));
@@ -498,6 +549,10 @@ extern "C" int lako_fidt5_backward(const lako_fidt5* m, const lako_batch* bt, co
   RC(embed_scatter_add(reinterpret_cast<const long long*>(bt->ids), w.dres_enc, g + p.lo.shared, Mt, d, p.V, s,
                        dr(0, E_EMB), w.cu ? w.tok_index : nullptr));
   RC(fold_dlut(w.dlut_enc, m->enc_buckets, g + p.lo.enc_relbias, H, w.L, m->bucket_center, m->dims.n_buckets, s));
+  if (sc.side) {  // join: nothing after this call may start before the side-stream wgrads are done
+    cudaEventRecord(sc.join, sc.side);
+    cudaStreamWaitEvent(s, sc.join, 0);
+  }
   return LAKO_OK;
 }
 
