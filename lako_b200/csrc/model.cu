@@ -290,19 +290,23 @@ struct Dropper {
   DropSpec none() const { return DropSpec{}; }
 };
 
-// Side stream for the decoder's weight-gradient GEMMs: they are off the dgrad critical path, and the decoder chain
-// (80-row GEMMs) leaves most SMs idle, so they run concurrently with it.  Forked / joined with events on the caller's
+// Optional side stream for the decoder's weight-gradient GEMMs: they are off the dgrad critical path, and the decoder
+// chain (80-row GEMMs) leaves most SMs idle, so they can run concurrently with it.  Forked / joined with events on the caller's
 // stream, so the call still behaves as if everything ran in order on that stream.
 struct SideCtx {
   cudaStream_t side = nullptr;
   cudaEvent_t fork = nullptr, join = nullptr;
-  bool ok = false;
+  bool ok = false, tried = false;
 };
 inline SideCtx& side_ctx() {
   static SideCtx c;
-  if (!c.ok) {
+  if (!c.ok && !c.tried) {
+    c.tried = true;
+    // Off by default: measured on B200 it is worth < 1 % at t5-base and costs up to 10 % of the end-to-end number
+    // at t5-large when the host synchronises every step (the side kernels then trail into the encoder backward
+    // and take SMs from its GEMMs).  LAKO_SIDE_STREAM=1 enables it.
     const char* e = getenv("LAKO_SIDE_STREAM");
-    if (!(e && e[0] == '0') && cudaStreamCreateWithFlags(&c.side, cudaStreamNonBlocking) == cudaSuccess &&
+    if ((e && e[0] == '1') && cudaStreamCreateWithFlags(&c.side, cudaStreamNonBlocking) == cudaSuccess &&
         cudaEventCreateWithFlags(&c.fork, cudaEventDisableTiming) == cudaSuccess &&
         cudaEventCreateWithFlags(&c.join, cudaEventDisableTiming) == cudaSuccess)
       c.ok = true;
