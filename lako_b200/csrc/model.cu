@@ -451,9 +451,25 @@ extern "C" int lako_fidt5_forward(const lako_fidt5* m, const lako_batch* bt, int
 }
 
 // loss.backward(): accumulates into the flat gradient buffer g_f32 (caller zeroes it: model.zero_grad())
+// Gradient-ready stages for overlapping the data-parallel all-reduce with the rest of backward: when
+// bt->stage_events holds 3 cudaEvent_t, event 0 is recorded once the decoder-side gradients (flat range
+// [dec_ln0[0], total)) are final, event 1 once encoder layers [n/2, n) ([enc_ln0[n/2], enc_relbias)) are final, event 2
+// at the end (everything else).  lako_fidt5_grad_stages() reports the element ranges.
+extern "C" int lako_fidt5_grad_stages(const lako_dims* dm, size_t* ranges /* [4][2] begin,end */) {
+  lako_layout lo;
+  RC(lako_fidt5_layout(dm, &lo));
+  const int h = dm->n_layers / 2;
+  ranges[0] = lo.dec_ln0[0];   ranges[1] = lo.total;        // stage 0
+  ranges[2] = lo.enc_ln0[h];   ranges[3] = lo.enc_relbias;  // stage 1
+  ranges[4] = 0;               ranges[5] = lo.enc_ln0[h];   // stage 2a: shared + encoder layers [0, n/2)
+  ranges[6] = lo.enc_relbias;  ranges[7] = lo.dec_ln0[0];   // stage 2b: encoder bias table + final norm
+  return LAKO_OK;
+}
+
 extern "C" int lako_fidt5_backward(const lako_fidt5* m, const lako_batch* bt, const float* loss_grad, void* stream) {
   RC(check_arch());
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  cudaEvent_t* stage_ev = reinterpret_cast<cudaEvent_t*>(bt ? bt->stage_events : nullptr);
   Ptrs p;
   RC(make_ptrs(m, p));
   LAKO_REQUIRE(p.g != nullptr && bt && bt->workspace, LAKO_ERR_BAD_ARG);
@@ -530,10 +546,18 @@ extern "C" int lako_fidt5_backward(const lako_fidt5* m, const lako_batch* bt, co
   const int nkv = nl * 2 * inner;
   RC(lin_dgrad(w.dkv_all, p.wb + p.lo.dec_xkv, w.dmem, Mt, nkv, d, nullptr, 1.f, s));
   RC(lin_wgrad(w.dkv_all, w.mem, g + p.lo.dec_xkv, Mt, nkv, d, 1.f, s));
+  if (stage_ev) {
+    if (sc.side) {  // the decoder wgrads may be on the side stream
+      cudaEventRecord(sc.join, sc.side);
+      cudaStreamWaitEvent(s, sc.join, 0);
+    }
+    cudaEventRecord(stage_ev[0], s);
+  }
   RC(rmsnorm_bwd(w.dmem, w.X[2 * nl], w.rstd_enc_final, p.wf + p.lo.enc_final_ln, w.dres_enc, w.dres_enc_b,
                  g + p.lo.enc_final_ln, Mt, d, 0, dsc, s, dr(0, E_FINAL), dr(nl - 1, E_FF)));
   // ---- encoder layers
   for (int l = nl - 1; l >= 0; --l) {
+    if (stage_ev && l == nl / 2 - 1) cudaEventRecord(stage_ev[1], s);  // layers [n/2, n) are final
     EncLayerAct& a = w.enc[l];
     RC(lin_dgrad(w.dres_enc_b, p.wb + p.lo.enc_wo[l], w.dh_enc, Mt, d, ff, a.hbits, dsc, s));
     RC(lin_wgrad(w.dres_enc_b, a.h, g + p.lo.enc_wo[l], Mt, d, ff, 1.f, s));
@@ -556,6 +580,10 @@ extern "C" int lako_fidt5_backward(const lako_fidt5* m, const lako_batch* bt, co
   if (sc.side) {  // join: nothing after this call may start before the side-stream wgrads are done
     cudaEventRecord(sc.join, sc.side);
     cudaStreamWaitEvent(s, sc.join, 0);
+  }
+  if (stage_ev) {
+    if (nl / 2 - 1 < 0) cudaEventRecord(stage_ev[1], s);  // single-layer model: stage 1 completes with the last layer
+    cudaEventRecord(stage_ev[2], s);
   }
   return LAKO_OK;
 }

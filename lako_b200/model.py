@@ -59,7 +59,7 @@ class _Batch(ctypes.Structure):
                 ("workspace", ctypes.c_void_p), ("workspace_bytes", ctypes.c_size_t),
                 ("logits", ctypes.c_void_p), ("stats", ctypes.c_void_p), ("count_is_set", ctypes.c_int),
                 ("dropout_p", ctypes.c_float), ("dropout_step", ctypes.c_uint), ("dropout_seed", ctypes.c_ulonglong),
-                ("cu_seqlens", ctypes.c_void_p), ("packed_tokens", ctypes.c_int)]
+                ("cu_seqlens", ctypes.c_void_p), ("packed_tokens", ctypes.c_int), ("stage_events", ctypes.c_void_p)]
 
 
 class FiDT5Config:
@@ -192,6 +192,9 @@ class FiDT5(nn.Module):
         # un-padded execution: when every passage mask is a prefix mask (what src/data.py's Collator emits), the
         # encoder side runs on the valid tokens only.  Set to False to force the padded layout.
         self.unpad = True
+        # data-parallel overlap: CUDA events recorded by backward as gradient ranges become final (optim.py)
+        self._stage_events = None
+        self._stage_ranges = None
         self._init_weights(emb_std, seed)
 
     # ------------------------------------------------------------------ parameters
@@ -488,7 +491,7 @@ class FiDT5(nn.Module):
         pack = (cu.data_ptr() if cu is not None else 0, packed)
         m = self._model_struct(with_grad=train)
         bt = _Batch(ids.data_ptr(), mask.data_ptr(), labels.data_ptr(), B, N, L, T, ws.data_ptr(), ws.numel(),
-                    logits.data_ptr(), stats.data_ptr(), count_is_set, *drop, *pack)
+                    logits.data_ptr(), stats.data_ptr(), count_is_set, *drop, *pack, 0)
         nat.check(L_.lako_fidt5_forward(ctypes.byref(m), ctypes.byref(bt), mode, nat.stream_ptr()), "lako_fidt5_forward")
         loss = stats[0] / torch.clamp(stats[1], min=1.0)
         if train:
@@ -496,12 +499,26 @@ class FiDT5(nn.Module):
             loss, logits = _LossFn.apply(self._anchor, self, keep, loss, logits)
         return (loss, logits)
 
+    def enable_grad_stage_events(self):
+        """Create the 3 stage events + flat ranges used to overlap the gradient all-reduce with backward."""
+        if self._stage_events is None:
+            evs = [torch.cuda.Event() for _ in range(3)]
+            for e in evs:
+                e.record()          # forces creation of the underlying cudaEvent_t
+            ranges = (ctypes.c_size_t * 8)()
+            nat.check(nat.lib().lako_fidt5_grad_stages(ctypes.byref(self._dims), ranges), "lako_fidt5_grad_stages")
+            self._stage_events = evs
+            self._stage_handles = (ctypes.c_void_p * 3)(*[e.cuda_event for e in evs])
+            self._stage_ranges = [(int(ranges[2 * i]), int(ranges[2 * i + 1])) for i in range(4)]
+        return self._stage_events, self._stage_ranges
+
     def _run_backward(self, keep, grad_loss):
         ids, mask, labels, ws, logits, stats, (B, N, L, T), drop, _cu, pack = keep
         L_ = nat.lib()
         m = self._model_struct(with_grad=True)
+        stage = ctypes.cast(self._stage_handles, ctypes.c_void_p).value if self._stage_events is not None else 0
         bt = _Batch(ids.data_ptr(), mask.data_ptr(), labels.data_ptr(), B, N, L, T, ws.data_ptr(), ws.numel(),
-                    logits.data_ptr(), stats.data_ptr(), 1, *drop, *pack)
+                    logits.data_ptr(), stats.data_ptr(), 1, *drop, *pack, stage)
         gl = grad_loss.detach().to(torch.float32).reshape(1).contiguous()
         nat.check(L_.lako_fidt5_backward(ctypes.byref(m), ctypes.byref(bt), nat.ptr(gl), nat.stream_ptr()),
                   "lako_fidt5_backward")
@@ -528,7 +545,7 @@ class FiDT5(nn.Module):
         cu, packed = self._packing(mask)
         m = self._model_struct(with_grad=False)
         bt = _Batch(ids.data_ptr(), mask.data_ptr(), 0, B, N, L, 1, ws.data_ptr(), ws.numel(), 0, 0, 0, 0.0, 0, 0,
-                    cu.data_ptr() if cu is not None else 0, packed)
+                    cu.data_ptr() if cu is not None else 0, packed, 0)
         out_len = ctypes.c_int(0)
         nat.check(L_.lako_fidt5_generate(ctypes.byref(m), ctypes.byref(bt), max_length, nat.ptr(out),
                                          ctypes.byref(out_len), nat.ptr(tf), nat.ptr(tl), nat.stream_ptr()),

@@ -47,6 +47,12 @@ class FusedAdamW:
         self.group = process_group
         self.chunk = allreduce_chunk_elems
         self.last_lr = lr
+        self._comm_stream = None
+        if self.world() > 1 and model._flat.is_cuda:
+            # overlap: backward records an event when a range of the flat gradient is final; the all-reduce of that
+            # range then runs on a communication stream while the rest of backward is still executing
+            model.enable_grad_stage_events()
+            self._comm_stream = torch.cuda.Stream()
 
     def world(self):
         if dist.is_available() and dist.is_initialized():
@@ -58,6 +64,17 @@ class FusedAdamW:
         With the loss normalised by the GLOBAL target count on every rank (FiDT5.forward's
         global_target_count), the sum equals the single-process gradient of the global batch."""
         g = self.model._flat_grad
+        if self._comm_stream is not None and self.model._stage_events is not None:
+            evs, ranges = self.model._stage_events, self.model._stage_ranges
+            main = torch.cuda.current_stream()
+            with torch.cuda.stream(self._comm_stream):
+                for stage, rs in ((0, ranges[0:1]), (1, ranges[1:2]), (2, ranges[2:4])):
+                    self._comm_stream.wait_event(evs[stage])
+                    for lo, hi in rs:
+                        for off in range(lo, hi, self.chunk):
+                            dist.all_reduce(g[off:min(hi, off + self.chunk)], op=dist.ReduceOp.SUM, group=self.group)
+            main.wait_stream(self._comm_stream)
+            return
         works = []
         for off in range(0, g.numel(), self.chunk):
             works.append(dist.all_reduce(g[off:off + self.chunk], op=dist.ReduceOp.SUM, group=self.group, async_op=True))

@@ -33,7 +33,7 @@ def _worker(rank, world, port, out):
     shim = type("M", (), {})()
     shim._flat_grad = flat
     opt = FusedAdamW.__new__(FusedAdamW)
-    opt.model, opt.group, opt.chunk = shim, None, 100000
+    opt.model, opt.group, opt.chunk, opt._comm_stream = shim, None, 100000, None
     opt.allreduce_grads()
     if rank == 0:
         torch.save(flat, out)
