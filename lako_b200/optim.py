@@ -133,4 +133,9 @@ def train_step(model, optimizer, input_ids, attention_mask, labels, group=None):
     loss.backward()
     optimizer.step()
     model.zero_grad()
-    return loss.detach()
+    loss = loss.detach()
+    if distributed:
+        # each rank holds (its token-loss sum) / (global target count); the sum over ranks is the global mean
+        loss = loss.clone()
+        dist.all_reduce(loss, op=dist.ReduceOp.SUM, group=group)
+    return loss
