@@ -144,8 +144,9 @@ typedef struct {
    * (they are masked as keys everywhere), so results are unchanged.  NULL = padded layout with `mask`. */
   const int* cu_seqlens;
   int packed_tokens;
-  /* backward only, optional: 3 cudaEvent_t recorded as gradient ranges become final (lako_fidt5_grad_stages), so the
-   * caller can start the data-parallel all-reduce of a range while backward is still running */
+  /* backward only, optional: LAKO_N_GRAD_STAGES cudaEvent_t recorded as gradient ranges become final
+   * (lako_fidt5_grad_stages), so the caller can start the data-parallel all-reduce of a range while backward is
+   * still running */
   void* stage_events;
 } lako_batch;
 
@@ -157,7 +158,9 @@ int lako_fidt5_forward(const lako_fidt5* m, const lako_batch* b, int mode, void*
 /* loss.backward() (train_reader.py:73) into g_f32; requires a mode-1 forward on the same workspace.
  * loss_grad: device scalar d(objective)/d(loss) (NULL = 1) */
 int lako_fidt5_backward(const lako_fidt5* m, const lako_batch* b, const float* loss_grad, void* stream);
-/* ranges[4][2] = {begin,end} element ranges of g_f32 that are final at stage events 0, 1, 2 (two ranges at stage 2) */
+#define LAKO_N_GRAD_STAGES 6
+/* ranges[7][2] = {begin,end} element ranges of g_f32: range i < 5 is final at stage event i (0 = decoder side,
+ * 1..4 = encoder layer quarters, top first), ranges 5 and 6 at stage event 5 (end of backward) */
 int lako_fidt5_grad_stages(const lako_dims* dims, size_t* ranges);
 /* FiDT5.generate (src/model.py:54-60), greedy with KV cache; synchronises the stream once per token
  * to test for early stop.  tok_score_* (may be NULL) receive the step-0 cross-attention score sums

@@ -451,18 +451,34 @@ extern "C" int lako_fidt5_forward(const lako_fidt5* m, const lako_batch* bt, int
 }
 
 // loss.backward(): accumulates into the flat gradient buffer g_f32 (caller zeroes it: model.zero_grad())
-// Gradient-ready stages for overlapping the data-parallel all-reduce with the rest of backward: when
-// bt->stage_events holds 3 cudaEvent_t, event 0 is recorded once the decoder-side gradients (flat range
-// [dec_ln0[0], total)) are final, event 1 once encoder layers [n/2, n) ([enc_ln0[n/2], enc_relbias)) are final, event 2
-// at the end (everything else).  lako_fidt5_grad_stages() reports the element ranges.
-extern "C" int lako_fidt5_grad_stages(const lako_dims* dm, size_t* ranges /* [4][2] begin,end */) {
+// Gradient-ready stages for overlapping the data-parallel all-reduce with the rest of backward.  When
+// bt->stage_events holds LAKO_N_GRAD_STAGES cudaEvent_t: event 0 is recorded once the decoder-side gradients (flat
+// range [dec_ln0[0], total)) are final, events 1..4 as each quarter of the encoder layers (top quarter first)
+// becomes final, event 5 at the end (shared embedding, encoder bias table and final norm).
+// lako_fidt5_grad_stages() reports the element ranges: ranges[i] for i < 5 belongs to stage i, ranges[5] and
+// ranges[6] to stage 5.
+static inline int enc_group_begin(int nl, int k) {  // first layer of encoder group k (k = 0 is the TOP quarter)
+  const int gsz = (nl + 3) / 4;
+  const int lo = nl - (k + 1) * gsz;
+  return lo < 0 ? 0 : lo;
+}
+extern "C" int lako_fidt5_grad_stages(const lako_dims* dm, size_t* ranges /* [7][2] begin,end */) {
   lako_layout lo;
   RC(lako_fidt5_layout(dm, &lo));
-  const int h = dm->n_layers / 2;
-  ranges[0] = lo.dec_ln0[0];   ranges[1] = lo.total;        // stage 0
-  ranges[2] = lo.enc_ln0[h];   ranges[3] = lo.enc_relbias;  // stage 1
-  ranges[4] = 0;               ranges[5] = lo.enc_ln0[h];   // stage 2a: shared + encoder layers [0, n/2)
-  ranges[6] = lo.enc_relbias;  ranges[7] = lo.dec_ln0[0];   // stage 2b: encoder bias table + final norm
+  const int nl = dm->n_layers;
+  ranges[0] = lo.dec_ln0[0];
+  ranges[1] = lo.total;
+  for (int k = 0; k < 4; ++k) {
+    const int b = enc_group_begin(nl, k);
+    const int e = (k == 0) ? nl : enc_group_begin(nl, k - 1);
+    ranges[2 + 2 * k] = lo.enc_ln0[b];
+    ranges[3 + 2 * k] = (e >= nl) ? lo.enc_relbias : lo.enc_ln0[e];
+    if (b >= e) ranges[3 + 2 * k] = ranges[2 + 2 * k];  // empty group (fewer than 4 layers)
+  }
+  ranges[10] = 0;
+  ranges[11] = lo.enc_ln0[0];
+  ranges[12] = lo.enc_relbias;
+  ranges[13] = lo.dec_ln0[0];
   return LAKO_OK;
 }
 
@@ -557,7 +573,6 @@ extern "C" int lako_fidt5_backward(const lako_fidt5* m, const lako_batch* bt, co
                  g + p.lo.enc_final_ln, Mt, d, 0, dsc, s, dr(0, E_FINAL), dr(nl - 1, E_FF)));
   // ---- encoder layers
   for (int l = nl - 1; l >= 0; --l) {
-    if (stage_ev && l == nl / 2 - 1) cudaEventRecord(stage_ev[1], s);  // layers [n/2, n) are final
     EncLayerAct& a = w.enc[l];
     RC(lin_dgrad(w.dres_enc_b, p.wb + p.lo.enc_wo[l], w.dh_enc, Mt, d, ff, a.hbits, dsc, s));
     RC(lin_wgrad(w.dres_enc_b, a.h, g + p.lo.enc_wo[l], Mt, d, ff, 1.f, s));
@@ -573,6 +588,10 @@ extern "C" int lako_fidt5_backward(const lako_fidt5* m, const lako_batch* bt, co
     RC(lin_wgrad(w.dqkv_enc, a.n_a, g + p.lo.enc_qkv[l], Mt, 3 * inner, d, 1.f, s));
     RC(rmsnorm_bwd(w.dn_enc, w.X[2 * l], a.rstd_a, p.wf + p.lo.enc_ln0[l], w.dres_enc, w.dres_enc_b,
                    g + p.lo.enc_ln0[l], Mt, d, 1, 1.f, s, dr.none(), l > 0 ? dr(l - 1, E_FF) : dr.none()));
+    if (stage_ev)
+      for (int k = 0; k < 4; ++k)
+        if (l == enc_group_begin(nl, k) && (k == 0 || enc_group_begin(nl, k - 1) > l))
+          cudaEventRecord(stage_ev[1 + k], s);  // encoder group k (layers >= l of that quarter) is final
   }
   RC(embed_scatter_add(reinterpret_cast<const long long*>(bt->ids), w.dres_enc, g + p.lo.shared, Mt, d, p.V, s,
                        dr(0, E_EMB), w.cu ? w.tok_index : nullptr));
@@ -581,10 +600,7 @@ extern "C" int lako_fidt5_backward(const lako_fidt5* m, const lako_batch* bt, co
     cudaEventRecord(sc.join, sc.side);
     cudaStreamWaitEvent(s, sc.join, 0);
   }
-  if (stage_ev) {
-    if (nl / 2 - 1 < 0) cudaEventRecord(stage_ev[1], s);  // single-layer model: stage 1 completes with the last layer
-    cudaEventRecord(stage_ev[2], s);
-  }
+  if (stage_ev) cudaEventRecord(stage_ev[5], s);
   return LAKO_OK;
 }
 

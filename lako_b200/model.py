@@ -500,16 +500,16 @@ class FiDT5(nn.Module):
         return (loss, logits)
 
     def enable_grad_stage_events(self):
-        """Create the 3 stage events + flat ranges used to overlap the gradient all-reduce with backward."""
+        """Create the 6 stage events + flat ranges used to overlap the gradient all-reduce with backward."""
         if self._stage_events is None:
-            evs = [torch.cuda.Event() for _ in range(3)]
+            evs = [torch.cuda.Event() for _ in range(6)]
             for e in evs:
                 e.record()          # forces creation of the underlying cudaEvent_t
-            ranges = (ctypes.c_size_t * 8)()
+            ranges = (ctypes.c_size_t * 14)()
             nat.check(nat.lib().lako_fidt5_grad_stages(ctypes.byref(self._dims), ranges), "lako_fidt5_grad_stages")
             self._stage_events = evs
-            self._stage_handles = (ctypes.c_void_p * 3)(*[e.cuda_event for e in evs])
-            self._stage_ranges = [(int(ranges[2 * i]), int(ranges[2 * i + 1])) for i in range(4)]
+            self._stage_handles = (ctypes.c_void_p * 6)(*[e.cuda_event for e in evs])
+            self._stage_ranges = [(int(ranges[2 * i]), int(ranges[2 * i + 1])) for i in range(7)]
         return self._stage_events, self._stage_ranges
 
     def _run_backward(self, keep, grad_loss):

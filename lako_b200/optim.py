@@ -68,7 +68,8 @@ class FusedAdamW:
             evs, ranges = self.model._stage_events, self.model._stage_ranges
             main = torch.cuda.current_stream()
             with torch.cuda.stream(self._comm_stream):
-                for stage, rs in ((0, ranges[0:1]), (1, ranges[1:2]), (2, ranges[2:4])):
+                for stage, rs in ((0, ranges[0:1]), (1, ranges[1:2]), (2, ranges[2:3]), (3, ranges[3:4]), (4, ranges[4:5]),
+                                  (5, ranges[5:7])):
                     self._comm_stream.wait_event(evs[stage])
                     for lo, hi in rs:
                         for off in range(lo, hi, self.chunk):

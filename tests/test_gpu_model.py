@@ -160,3 +160,24 @@ def test_non_prefix_mask_falls_back_to_padded_layout():
         ref_loss, ref_logits = O.fidt5_forward(sd, cfg, c["ids"], mask, c["labels"])
     assert (logits.cpu() - ref_logits).abs().max().item() < LOGIT_ATOL_BF16
     assert abs(loss.item() - ref_loss.item()) < 5e-3
+
+
+def test_grad_stage_events_partition_and_fire():
+    """Stage events used to overlap the DP all-reduce: ranges tile the flat gradient, every event completes, and
+    enabling them does not change the gradients."""
+    c, cfg, sd, model = _load(GOLDEN[1])
+    args = dict(input_ids=c["ids"].cuda(), attention_mask=c["mask"].cuda(), labels=c["labels"].cuda())
+    model.train()
+    model.zero_grad()
+    model(**args)[0].backward()
+    torch.cuda.synchronize()
+    g0 = model._flat_grad.clone()
+    evs, ranges = model.enable_grad_stage_events()
+    live = sorted(r for r in ranges if r[1] > r[0])
+    assert live[0][0] == 0 and live[-1][1] == model._total
+    assert all(a[1] == b[0] for a, b in zip(live, live[1:]))
+    model.zero_grad()
+    model(**args)[0].backward()
+    torch.cuda.synchronize()
+    assert all(e.query() for e in evs)
+    assert ((model._flat_grad - g0).norm() / g0.norm()).item() < 1e-3   # atomics reorder sums, nothing else changes
