@@ -1,5 +1,7 @@
-// Decoder-side attention kernels of the FiDT5 reader (SIMT; these are < 1 % of the FLOPs, the cost
-// is streaming the fused encoder memory's K/V once per layer):
+// Decoder-side attention of the FiDT5 reader (< 1 % of the FLOPs; the cost is streaming the fused
+// encoder memory's K/V once per layer).  The cross-attention chunk kernels themselves are the
+// mma.sync kernels in xattn_mma.cu; this file holds their combine step, the host wrappers and the
+// SIMT decoder self-attention:
 //
 //  * cross-attention over the fused memory (M = n_passages * text_maxlength keys per question),
 //    split over key chunks (flash-decoding style partial softmax + combine), forward and backward.
@@ -17,115 +19,6 @@ namespace lako {
 constexpr float MASK_MIN_F = -3.4028234663852886e38f;
 constexpr int XA_CH = 128;      // keys per CTA
 constexpr int XA_TMAX = 64;     // max decoder length handled by the training kernels
-constexpr int XA_KPAD = 72;     // padded smem row (bf16 elements): 144 B rows -> conflict-free 16 B loads
-
-struct XAttnParams {
-  const __nv_bfloat16* q;     // [B*T][ldq], head h at column h*64
-  const __nv_bfloat16* kv;    // [B*M][ldkv], K head h at column koff + h*64, V at voff + h*64
-  const unsigned char* mask;  // [B][M], 1 = valid
-  float* part;                // [B][H][splits][T][66]  (o[64], m, l)
-  float* tok_score;           // [B][M] += sum_h masked pre-softmax score of query 0 (may be null)
-  int T, M, H, ldq, ldkv, koff, voff, splits;
-};
-
-__device__ __forceinline__ void load_row64_bf16_to_regs(const __nv_bfloat16* row, uint32_t (&r)[32]) {
-  const uint4* p4 = reinterpret_cast<const uint4*>(row);
-#pragma unroll
-  for (int u = 0; u < 8; ++u) {
-    const uint4 v = p4[u];
-    r[u * 4 + 0] = v.x;
-    r[u * 4 + 1] = v.y;
-    r[u * 4 + 2] = v.z;
-    r[u * 4 + 3] = v.w;
-  }
-}
-
-// stage a [rows<=128][64] bf16 tile from global (row pitch ld) into padded smem, zero-filling rows >= nrows
-__device__ __forceinline__ void stage_tile(const __nv_bfloat16* g, int ld, int nrows, __nv_bfloat16* s, int tid,
-                                           int nthreads) {
-  for (int i = tid; i < XA_CH * 8; i += nthreads) {
-    const int r = i >> 3, u = i & 7;
-    uint4 v = make_uint4(0, 0, 0, 0);
-    if (r < nrows) v = *reinterpret_cast<const uint4*>(g + static_cast<size_t>(r) * ld + u * 8);
-    *reinterpret_cast<uint4*>(s + r * XA_KPAD + u * 8) = v;
-  }
-}
-
-__global__ void __launch_bounds__(128) xattn_fwd_kernel(const XAttnParams p) {
-  pdl_launch_dependents();
-  pdl_wait();
-  __shared__ __align__(16) __nv_bfloat16 sK[XA_CH * XA_KPAD];
-  __shared__ __align__(16) __nv_bfloat16 sV[XA_CH * XA_KPAD];
-  extern __shared__ float dyn[];  // q [T][64] fp32, scores [T][XA_CH]
-  float* sQ = dyn;
-  float* sS = dyn + p.T * 64;
-  const int split = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int k0 = split * XA_CH;
-  const int nk = min(XA_CH, p.M - k0);
-  const __nv_bfloat16* kbase = p.kv + (static_cast<size_t>(b) * p.M + k0) * p.ldkv + p.koff + h * 64;
-  const __nv_bfloat16* vbase = p.kv + (static_cast<size_t>(b) * p.M + k0) * p.ldkv + p.voff + h * 64;
-  stage_tile(kbase, p.ldkv, nk, sK, tid, 128);
-  stage_tile(vbase, p.ldkv, nk, sV, tid, 128);
-  for (int i = tid; i < p.T * 64; i += 128) {
-    const int t = i >> 6, d = i & 63;
-    sQ[i] = __bfloat162float(p.q[(static_cast<size_t>(b) * p.T + t) * p.ldq + h * 64 + d]);
-  }
-  __syncthreads();
-  // scores: thread == key
-  {
-    const int j = tid;
-    uint32_t kr[32];
-    load_row64_bf16_to_regs(sK + j * XA_KPAD, kr);
-    const bool valid = (j < nk) && p.mask[static_cast<size_t>(b) * p.M + k0 + j];
-    for (int t = 0; t < p.T; ++t) {
-      const float4* q4 = reinterpret_cast<const float4*>(sQ + t * 64);
-      float acc = 0.f;
-#pragma unroll
-      for (int u = 0; u < 16; ++u) {
-        const float4 qq = q4[u];
-        acc += qq.x * bf16_lo(kr[u * 2]) + qq.y * bf16_hi(kr[u * 2]) + qq.z * bf16_lo(kr[u * 2 + 1]) +
-               qq.w * bf16_hi(kr[u * 2 + 1]);
-      }
-      if (t == 0 && p.tok_score && valid) atomicAdd(&p.tok_score[static_cast<size_t>(b) * p.M + k0 + j], acc);
-      sS[t * XA_CH + j] = (j < nk) ? (valid ? acc : MASK_MIN_F) : -INFINITY;
-    }
-  }
-  __syncthreads();
-  // per-query partial softmax over this chunk: warp per query
-  float* part = p.part + ((static_cast<size_t>(b) * p.H + h) * p.splits + split) * p.T * 66;
-  for (int t = warp; t < p.T; t += 4) {
-    float v[4], m = -INFINITY;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      v[i] = sS[t * XA_CH + lane + i * 32];
-      m = fmaxf(m, v[i]);
-    }
-    m = warp_max(m);
-    float l = 0.f;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const float e = (v[i] == -INFINITY) ? 0.f : __expf(v[i] - m);
-      sS[t * XA_CH + lane + i * 32] = e;
-      l += e;
-    }
-    l = warp_sum(l);
-    if (lane == 0) {
-      part[t * 66 + 64] = m;
-      part[t * 66 + 65] = l;
-    }
-  }
-  __syncthreads();
-  // o[t][d] = sum_j p[t][j] V[j][d]: thread = (d, t parity)
-  {
-    const int d = tid & 63;
-    for (int t = tid >> 6; t < p.T; t += 2) {
-      float acc = 0.f;
-      for (int j = 0; j < nk; ++j) acc += sS[t * XA_CH + j] * __bfloat162float(sV[j * XA_KPAD + d]);
-      part[t * 66 + d] = acc;
-    }
-  }
-}
 
 // combine the split partials: out[b,t,h*64+d] = sum_s exp(m_s - m) o_s / sum_s exp(m_s - m) l_s
 __global__ void xattn_combine_kernel(const float* __restrict__ part, __nv_bfloat16* __restrict__ out,
@@ -161,161 +54,14 @@ int xattn_fwd(const __nv_bfloat16* q, const __nv_bfloat16* kv, const unsigned ch
               int ldo, cudaStream_t s, DropSpec drop, const int* cu, int npsg, const int* tok_index) {
   LAKO_REQUIRE(B > 0 && T > 0 && T <= XA_TMAX && M > 0 && H > 0, LAKO_ERR_UNSUPPORTED);
   LAKO_REQUIRE(ldkv % 8 == 0 && koff % 8 == 0 && voff % 8 == 0, LAKO_ERR_BAD_ARG);
-  XAttnParams p;
-  p.q = q;
-  p.kv = kv;
-  p.mask = mask;
-  p.part = workspace;
-  p.tok_score = tok_score;
-  p.T = T;
-  p.M = M;
-  p.H = H;
-  p.ldq = ldq;
-  p.ldkv = ldkv;
-  p.koff = koff;
-  p.voff = voff;
-  p.splits = (M + XA_CH - 1) / XA_CH;
-  const size_t dyn = static_cast<size_t>(T) * (64 + XA_CH) * sizeof(float);
-  static bool configured = false;
-  if (!configured) {
-    cudaFuncSetAttribute(xattn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         XA_TMAX * (64 + XA_CH) * (int)sizeof(float));
-    configured = true;
-  }
+  const int splits = (M + XA_CH - 1) / XA_CH;
   ProfScope prof(PROF_XATTN, 4.0 * B * H * static_cast<double>(T) * M * 64, s);
-  (void)dyn;
-  {
-    int rc = xattn_fwd_mma(q, kv, mask, tok_score, workspace, B, T, M, H, ldq, ldkv, koff, voff, s, drop, cu, npsg,
-                           tok_index);
-    if (rc) return rc;
-  }
-  dim3 g2(T, H, B);
-  launch_pdl(xattn_combine_kernel, dim3(g2), dim3(64), 0, s, workspace, out, lse, T, H, p.splits, ldo, cu, npsg);
+  int rc = xattn_fwd_mma(q, kv, mask, tok_score, workspace, B, T, M, H, ldq, ldkv, koff, voff, s, drop, cu, npsg,
+                         tok_index);
+  if (rc) return rc;
+  launch_pdl(xattn_combine_kernel, dim3(T, H, B), dim3(64), 0, s, workspace, out, lse, T, H, splits, ldo, cu, npsg);
   LAKO_CHECK_LAUNCH();
   return LAKO_OK;
-}
-
-// ------------------------------------------------------------------------------------------------
-// cross-attention backward.  Per CTA: one 128-key chunk of one (question, head).
-//   dK[j] = sum_t dS[t][j] q[t],  dV[j] = sum_t P[t][j] dO[t]   -> bf16 into dkv (same layout as kv)
-//   dq[t] += sum_j dS[t][j] K[j]                                  -> fp32 atomics into dq_f32 [B*T][inner]
-// two threads per key (each owns 32 of the 64 head dims).
-// ------------------------------------------------------------------------------------------------
-struct XAttnBwdParams {
-  const __nv_bfloat16* q;
-  const __nv_bfloat16* kv;
-  const unsigned char* mask;
-  const __nv_bfloat16* out;   // [B*T][ldo] forward output
-  const __nv_bfloat16* dout;  // [B*T][ldo]
-  const float* lse;           // [B][H][T]
-  __nv_bfloat16* dkv;         // [B*M][ldkv]
-  float* dq;                  // [B*T][H*64] fp32, pre-zeroed
-  int T, M, H, ldq, ldkv, koff, voff, ldo;
-};
-
-__global__ void __launch_bounds__(256) xattn_bwd_kernel(const XAttnBwdParams p) {
-  pdl_launch_dependents();
-  pdl_wait();
-  __shared__ __align__(16) __nv_bfloat16 sK[XA_CH * XA_KPAD];
-  __shared__ __align__(16) __nv_bfloat16 sV[XA_CH * XA_KPAD];
-  extern __shared__ float dyn[];  // q [T][64], dO [T][64], dS [T][XA_CH], D[T], lse[T]
-  float* sQ = dyn;
-  float* sDO = sQ + p.T * 64;
-  float* sDS = sDO + p.T * 64;
-  float* sD = sDS + p.T * XA_CH;
-  float* sL = sD + p.T;
-  const int split = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int k0 = split * XA_CH;
-  const int nk = min(XA_CH, p.M - k0);
-  const size_t kvrow0 = static_cast<size_t>(b) * p.M + k0;
-  stage_tile(p.kv + kvrow0 * p.ldkv + p.koff + h * 64, p.ldkv, nk, sK, tid, 256);
-  stage_tile(p.kv + kvrow0 * p.ldkv + p.voff + h * 64, p.ldkv, nk, sV, tid, 256);
-  for (int i = tid; i < p.T * 64; i += 256) {
-    const int t = i >> 6, d = i & 63;
-    const size_t row = static_cast<size_t>(b) * p.T + t;
-    sQ[i] = __bfloat162float(p.q[row * p.ldq + h * 64 + d]);
-    sDO[i] = __bfloat162float(p.dout[row * p.ldo + h * 64 + d]);
-  }
-  __syncthreads();
-  for (int t = warp; t < p.T; t += 8) {  // D[t] = sum_d dO * O
-    const size_t row = static_cast<size_t>(b) * p.T + t;
-    float acc = sDO[t * 64 + lane] * __bfloat162float(p.out[row * p.ldo + h * 64 + lane]) +
-                sDO[t * 64 + lane + 32] * __bfloat162float(p.out[row * p.ldo + h * 64 + lane + 32]);
-    acc = warp_sum(acc);
-    if (lane == 0) {
-      sD[t] = acc;
-      sL[t] = p.lse[(static_cast<size_t>(b) * p.H + h) * p.T + t];
-    }
-  }
-  __syncthreads();
-  {
-    const int j = tid >> 1, half = tid & 1;  // key, which 32 dims
-    uint32_t kr[16], vr[16];
-    {
-      const uint4* k4 = reinterpret_cast<const uint4*>(sK + j * XA_KPAD + half * 32);
-      const uint4* v4 = reinterpret_cast<const uint4*>(sV + j * XA_KPAD + half * 32);
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const uint4 a = k4[u], c = v4[u];
-        kr[u * 4] = a.x; kr[u * 4 + 1] = a.y; kr[u * 4 + 2] = a.z; kr[u * 4 + 3] = a.w;
-        vr[u * 4] = c.x; vr[u * 4 + 1] = c.y; vr[u * 4 + 2] = c.z; vr[u * 4 + 3] = c.w;
-      }
-    }
-    const bool valid = (j < nk) && p.mask[static_cast<size_t>(b) * p.M + k0 + j];
-    float dk[32], dv[32];
-#pragma unroll
-    for (int i = 0; i < 32; ++i) dk[i] = dv[i] = 0.f;
-    for (int t = 0; t < p.T; ++t) {
-      const float* qt = sQ + t * 64 + half * 32;
-      const float* dot = sDO + t * 64 + half * 32;
-      float s = 0.f, dp = 0.f;
-#pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        s += qt[2 * i] * bf16_lo(kr[i]) + qt[2 * i + 1] * bf16_hi(kr[i]);
-        dp += dot[2 * i] * bf16_lo(vr[i]) + dot[2 * i + 1] * bf16_hi(vr[i]);
-      }
-      s += __shfl_xor_sync(0xffffffffu, s, 1);
-      dp += __shfl_xor_sync(0xffffffffu, dp, 1);
-      float pr = 0.f;
-      if (j < nk) pr = __expf((valid ? s : MASK_MIN_F) - sL[t]);
-      const float ds = pr * (dp - sD[t]);
-      if (half == 0) sDS[t * XA_CH + j] = ds;
-#pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        dk[i] += ds * qt[i];
-        dv[i] += pr * dot[i];
-      }
-    }
-    if (j < nk) {
-      __nv_bfloat16* dkrow = p.dkv + (kvrow0 + j) * p.ldkv + p.koff + h * 64 + half * 32;
-      __nv_bfloat16* dvrow = p.dkv + (kvrow0 + j) * p.ldkv + p.voff + h * 64 + half * 32;
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        uint4 o;
-        o.x = pack_bf16x2(dk[u * 8 + 0], dk[u * 8 + 1]);
-        o.y = pack_bf16x2(dk[u * 8 + 2], dk[u * 8 + 3]);
-        o.z = pack_bf16x2(dk[u * 8 + 4], dk[u * 8 + 5]);
-        o.w = pack_bf16x2(dk[u * 8 + 6], dk[u * 8 + 7]);
-        *reinterpret_cast<uint4*>(dkrow + u * 8) = o;
-        o.x = pack_bf16x2(dv[u * 8 + 0], dv[u * 8 + 1]);
-        o.y = pack_bf16x2(dv[u * 8 + 2], dv[u * 8 + 3]);
-        o.z = pack_bf16x2(dv[u * 8 + 4], dv[u * 8 + 5]);
-        o.w = pack_bf16x2(dv[u * 8 + 6], dv[u * 8 + 7]);
-        *reinterpret_cast<uint4*>(dvrow + u * 8) = o;
-      }
-    }
-  }
-  __syncthreads();
-  // dq[t][d] += sum_j dS[t][j] K[j][d]
-  {
-    const int d = tid & 63;
-    for (int t = tid >> 6; t < p.T; t += 4) {
-      float acc = 0.f;
-      for (int j = 0; j < nk; ++j) acc += sDS[t * XA_CH + j] * __bfloat162float(sK[j * XA_KPAD + d]);
-      atomicAdd(&p.dq[(static_cast<size_t>(b) * p.T + t) * (p.H * 64) + h * 64 + d], acc);
-    }
-  }
 }
 
 int xattn_bwd(const __nv_bfloat16* q, const __nv_bfloat16* kv, const unsigned char* mask, const __nv_bfloat16* out,
@@ -323,19 +69,7 @@ int xattn_bwd(const __nv_bfloat16* q, const __nv_bfloat16* kv, const unsigned ch
               int H, int ldq, int ldkv, int koff, int voff, int ldo, cudaStream_t s, DropSpec drop, const int* cu,
               int npsg) {
   LAKO_REQUIRE(B > 0 && T > 0 && T <= XA_TMAX && M > 0 && H > 0, LAKO_ERR_UNSUPPORTED);
-  XAttnBwdParams p;
-  p.q = q; p.kv = kv; p.mask = mask; p.out = out; p.dout = dout; p.lse = lse; p.dkv = dkv; p.dq = dq_f32;
-  p.T = T; p.M = M; p.H = H; p.ldq = ldq; p.ldkv = ldkv; p.koff = koff; p.voff = voff; p.ldo = ldo;
-  const size_t dyn = (static_cast<size_t>(T) * (128 + XA_CH) + 2 * T) * sizeof(float);
-  static bool configured = false;
-  if (!configured) {
-    cudaFuncSetAttribute(xattn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         (XA_TMAX * (128 + XA_CH) + 2 * XA_TMAX) * (int)sizeof(float));
-    configured = true;
-  }
   ProfScope prof(PROF_XATTN, 8.0 * B * H * static_cast<double>(T) * M * 64, s);
-  (void)dyn;
-  (void)p;
   return xattn_bwd_mma(q, kv, mask, out, dout, lse, dkv, dq_f32, B, T, M, H, ldq, ldkv, koff, voff, ldo, s, drop, cu,
                        npsg);
 }

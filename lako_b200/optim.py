@@ -8,6 +8,7 @@ src/util.py:149-168 (WarmupLinearScheduler), :185-245 (AdamW(correct_bias=False)
 from __future__ import annotations
 
 import ctypes
+import os
 
 import torch
 import torch.distributed as dist
@@ -48,7 +49,8 @@ class FusedAdamW:
         self.chunk = allreduce_chunk_elems
         self.last_lr = lr
         self._comm_stream = None
-        if self.world() > 1 and model._flat.is_cuda:
+        self._skip_allreduce = os.environ.get("LAKO_SKIP_ALLREDUCE") == "1"   # diagnostics only: wrong gradients
+        if self.world() > 1 and model._flat.is_cuda and os.environ.get("LAKO_DP_OVERLAP", "1") != "0":
             # overlap: backward records an event when a range of the flat gradient is final; the all-reduce of that
             # range then runs on a communication stream while the rest of backward is still executing
             model.enable_grad_stage_events()
@@ -88,7 +90,7 @@ class FusedAdamW:
         g = model._flat_grad
         if g is None:
             raise nat.LakoError("FusedAdamW.step() before any backward")
-        if self.world() > 1:
+        if self.world() > 1 and not self._skip_allreduce:
             self.allreduce_grads()
         lr = self.lr * (self.schedule(self.step_count) if self.schedule is not None else 1.0)
         # the scheduler is stepped AFTER optimizer.step() in the reference (train_reader.py:77-78), so
