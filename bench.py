@@ -70,6 +70,32 @@ class ClockSampler(threading.Thread):
         self.stop_flag = False
 
     def run(self):
+        try:
+            self._run_nvml()
+        except Exception:
+            self._run_smi()
+
+    def _run_nvml(self):
+        """NVML polled every 10 ms (a 100 ms timed region still gets ~10 samples); same fields as the nvidia-smi query."""
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+        mx = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+        get_reasons = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+            pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
+        bits = ((0x8, 3), (0x40, 4), (0x20, 5), (0x4, 6))  # hw_slowdown, hw_thermal, sw_thermal, sw_power_cap
+        while not self.stop_flag:
+            sm = pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
+            pw = pynvml.nvmlDeviceGetPowerUsage(h) / 1000.0
+            r = get_reasons(h)
+            row = [str(sm), str(mx), f"{pw:.0f}"] + ["Not Active"] * 4
+            for bit, col in bits:
+                if r & bit:
+                    row[col] = "Active"
+            self.samples.append(row)
+            time.sleep(0.01)
+
+    def _run_smi(self):
         while not self.stop_flag:
             try:
                 out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
@@ -81,19 +107,21 @@ class ClockSampler(threading.Thread):
             time.sleep(0.2)
 
     def summary(self):
-        sm, mx, reasons = [], 0, set()
+        sm, pw, mx, reasons = [], [], 0, set()
         for s in self.samples:
             try:
                 sm.append(float(s[0]))
                 mx = max(mx, float(s[1]))
+                pw.append(float(s[2]))
             except Exception:
                 continue
             for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), s[3:7]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
         sm.sort()
+        pw.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "sm_min_mhz": sm[0] if sm else None, "power_w": pw[len(pw) // 2] if pw else None}
 
 
 def cpu_oracle_step_time(size, N, L, T, steps, warmup, seed=0):

@@ -6,7 +6,8 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "_lib", "liblako_b200.so")
+# LAKO_B200_LIB points at another build of the SAME library (A/B timing of kernel variants on one box)
+LIB_PATH = os.environ.get("LAKO_B200_LIB") or os.path.join(_HERE, "_lib", "liblako_b200.so")
 
 _lib = None
 

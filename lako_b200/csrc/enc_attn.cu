@@ -333,9 +333,12 @@ constexpr int EB_Q_OFF = 0, EB_DO_OFF = 32768, EB_K_OFF = 65536, EB_V_OFF = 9830
 constexpr int EB_SMEM_BYTES = EB_BAR_OFF + 64 + 1024;
 constexpr int TM_S = 0, TM_DP = 128, TM_DQ = 256, TM_DK = 384, TM_DV = 448;
 
-// One CTA per (head, passage); 256 threads: warp w owns TMEM lane quarter (w & 3) and key half (w >> 2) of
-// each 128x128 (query tile x key tile) block.  TMEM: S 128 | dP 128 | dQ 2x64 | dK 64 | dV 64 columns.
-__global__ void __launch_bounds__(256, 1)
+// One CTA per (head, passage); 512 threads = 16 warps (the softmax arithmetic between the MMAs is latency bound, so
+// the CTA carries as many warps as the register file allows): warp w owns TMEM lane quarter (w & 3) = 32 query rows
+// and key columns (w >> 2)*32..+32 of each 128x128 (query tile x key tile) block.
+// TMEM: S 128 | dP 128 | dQ 2x64 | dK 64 | dV 64 columns.
+constexpr int EB_THREADS = 512;
+__global__ void __launch_bounds__(EB_THREADS, 1)
 enc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_do,
                     const EncAttnBwdParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -351,7 +354,7 @@ enc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_load + 3);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int quarter = warp & 3, chalf = warp >> 2;
+  const int quarter = warp & 3, cq = warp >> 2;
   const int h = blockIdx.x, psg = blockIdx.y;
   const int Lmax = p.L;  // LUT geometry / lse pitch
   const int nlut = 2 * Lmax - 1;
@@ -375,26 +378,39 @@ enc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
   }
   if (warp == 0) tmem_alloc(tmem_slot, 512);
   pdl_wait();
-  stage_lut4(s_lut4, p.bias_lut + h * nlut, nlut, tid, 256);
-  stage_kmask(s_kmask, p.mask ? p.mask + static_cast<size_t>(psg) * Lmax : nullptr, L, tid, 256);
-  for (int i = tid; i < 512; i += 256) s_dlut[i] = 0.f;
+  if (tid == 0) {  // operand tiles: start the TMA traffic before the SIMT staging below
+    mbar_arrive_expect_tx(bar_load, 16384 * 4 * nt);
+    for (int t = 0; t < nt; ++t) {
+      tma_load_2d(smem + EB_Q_OFF + t * 16384, &tm_qkv, bar_load, h * 64, row0 + t * 128);
+      tma_load_2d(smem + EB_K_OFF + t * 16384, &tm_qkv, bar_load, p.inner + h * 64, row0 + t * 128);
+      tma_load_2d(smem + EB_V_OFF + t * 16384, &tm_qkv, bar_load, 2 * p.inner + h * 64, row0 + t * 128);
+      tma_load_2d(smem + EB_DO_OFF + t * 16384, &tm_do, bar_load, h * 64, row0 + t * 128);
+    }
+  }
+  stage_lut4(s_lut4, p.bias_lut + h * nlut, nlut, tid, EB_THREADS);
+  stage_kmask(s_kmask, p.mask ? p.mask + static_cast<size_t>(psg) * Lmax : nullptr, L, tid, EB_THREADS);
+  s_dlut[tid] = 0.f;
   {
-    const int q = tid;  // 256 threads cover the (<=256) query rows: D[q] = sum_d dO*O, lse[q]
-    float dsum = 0.f, l = INFINITY;  // lse = +inf for rows beyond the passage -> P = exp(s - inf) = 0
+    // two threads per query row (256 rows max): D[q] = sum_d dO*O over 32 of the 64 head dims each, lse[q]
+    const int q = tid >> 1, part = tid & 1;
+    float dsum = 0.f;
     if (q < L) {
-      const uint4* o4 = reinterpret_cast<const uint4*>(p.out + static_cast<size_t>(row0 + q) * p.inner + h * 64);
-      const uint4* d4 = reinterpret_cast<const uint4*>(p.dout + static_cast<size_t>(row0 + q) * p.inner + h * 64);
+      const uint4* o4 = reinterpret_cast<const uint4*>(p.out + static_cast<size_t>(row0 + q) * p.inner + h * 64) + part * 4;
+      const uint4* d4 = reinterpret_cast<const uint4*>(p.dout + static_cast<size_t>(row0 + q) * p.inner + h * 64) + part * 4;
 #pragma unroll
-      for (int u = 0; u < 8; ++u) {
+      for (int u = 0; u < 4; ++u) {
         const uint4 a = o4[u], b = d4[u];
         dsum += bf16_lo(a.x) * bf16_lo(b.x) + bf16_hi(a.x) * bf16_hi(b.x) + bf16_lo(a.y) * bf16_lo(b.y) +
                 bf16_hi(a.y) * bf16_hi(b.y) + bf16_lo(a.z) * bf16_lo(b.z) + bf16_hi(a.z) * bf16_hi(b.z) +
                 bf16_lo(a.w) * bf16_lo(b.w) + bf16_hi(a.w) * bf16_hi(b.w);
       }
-      l = p.lse[(static_cast<size_t>(psg) * p.H + h) * Lmax + q];
     }
-    s_D[q] = dsum;
-    s_lse[q] = l;
+    dsum += __shfl_xor_sync(0xffffffffu, dsum, 1);
+    if (part == 0) {
+      s_D[q] = dsum;
+      // lse = +inf for rows beyond the passage -> P = exp(s - inf) = 0
+      s_lse[q] = (q < L) ? p.lse[(static_cast<size_t>(psg) * p.H + h) * Lmax + q] : INFINITY;
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -419,13 +435,6 @@ enc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
   };
 
   if (tid == 0) {
-    mbar_arrive_expect_tx(bar_load, 16384 * 4 * nt);
-    for (int t = 0; t < nt; ++t) {
-      tma_load_2d(smem + EB_Q_OFF + t * 16384, &tm_qkv, bar_load, h * 64, row0 + t * 128);
-      tma_load_2d(smem + EB_K_OFF + t * 16384, &tm_qkv, bar_load, p.inner + h * 64, row0 + t * 128);
-      tma_load_2d(smem + EB_V_OFF + t * 16384, &tm_qkv, bar_load, 2 * p.inner + h * 64, row0 + t * 128);
-      tma_load_2d(smem + EB_DO_OFF + t * 16384, &tm_do, bar_load, h * 64, row0 + t * 128);
-    }
     mbar_wait(bar_load, 0);
     tc_fence_after();
     issue_s_dp(0, 0);
@@ -434,8 +443,7 @@ enc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
 
   const int r = quarter * 32 + lane;  // row within a 128-row tile == TMEM lane
   const uint32_t t_row = tmem + (static_cast<uint32_t>(quarter * 32) << 16);
-  const float keep = (lane == 0) ? 0.f : 1.f;      // systolic diagonal sums: lane 0 starts a new diagonal (up pass)
-  const float keep_dn = (lane == 31) ? 0.f : 1.f;  // lane 31 starts a new diagonal (down pass)
+  const float keep = (lane == 0) ? 0.f : 1.f;  // systolic diagonal sums: lane 0 starts a new diagonal
   // Two completion streams: bar_mma = "S and dP of the next block are in TMEM", bar_grad = "the gradient MMAs of the
   // previous block have finished reading P / dS from shared memory".  The S/dP MMAs of block i+1 are issued AHEAD of
   // the gradient MMAs of block i, so the softmax arithmetic of block i+1 (registers only) overlaps the 24 gradient
@@ -454,25 +462,26 @@ enc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
       tc_fence_after();
       const float lse_q = s_lse[q];
       const float D_q = s_D[q];
-      uint32_t ppk[2][16], dpk[2][16];  // bf16x2-packed P_drop and dS of this thread's 2 x 32 columns
+      uint32_t ppk[16], dpk[16];  // bf16x2-packed P_drop and dS of this thread's 32 columns
       const bool rows_live = (qt * 128 + quarter * 32) < L;  // warp-uniform: any of this warp's queries in the passage
+      const int kbase = kt * 128 + cq * 32;                  // first key of this warp's 32-column chunk
+      if (!rows_live || kbase >= L) {
+        // nothing of this 32x32 sub-block lies inside the passage: P = dS = 0 (dV / dK sum over all 128 rows of
+        // the tile, so the zeros must really be written), no exp / Philox / diagonal sums
 #pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        const int kbase = kt * 128 + chalf * 64 + c * 32;  // first key of this 32-column chunk
-        if (!rows_live || kbase >= L) {
-          // nothing of this 32x32 sub-block lies inside the passage: P = dS = 0 (dV / dK sum over all 128 rows of
-          // the tile, so the zeros must really be written), no exp / Philox / diagonal sums
-#pragma unroll
-          for (int i = 0; i < 16; ++i) ppk[c][i] = dpk[c][i] = 0u;
-          continue;
-        }
+        for (int i = 0; i < 16; ++i) ppk[i] = dpk[i] = 0u;
+      } else {
         uint32_t sv[32], dpv[32];
-        tmem_ld_32x32(t_row + TM_S + chalf * 64 + c * 32, sv);
-        tmem_ld_32x32(t_row + TM_DP + chalf * 64 + c * 32, dpv);
+        tmem_ld_32x32(t_row + TM_S + cq * 32, sv);
+        tmem_ld_32x32(t_row + TM_DP + cq * 32, dpv);
         tmem_ld_wait();
         // bias-gradient index of the diagonal d = i - lane of this 32x32 sub-block: rel = k - q
         const int idx0 = (kbase - (qt * 128 + quarter * 32)) + (Lmax - 1);
-        float ds[32];
+        // Bias gradient = diagonal sums (k - q constant) of this 32x32 sub-block, as one systolic pass over the warp,
+        // exact in fp32: with ascending columns and the partial sum moving one lane UP per column, lane 0 starts a
+        // fresh diagonal each step (keep = 0 there), lane 31 holds the COMPLETE diagonal d = i - 31 (<= 0) after
+        // column i (parked in lane i's Rdone), and after the last column lane l holds the complete d = 31 - l (>= 0).
+        float Rup = 0.f, Rdone = 0.f;
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
           const float4 lb0 = *reinterpret_cast<const float4*>(lutp + kbase + u * 8);
@@ -481,7 +490,7 @@ enc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
           const float4 km1 = *reinterpret_cast<const float4*>(s_kmask + kbase + u * 8 + 4);
           const float lbv[8] = {lb0.x, lb0.y, lb0.z, lb0.w, lb1.x, lb1.y, lb1.z, lb1.w};
           const float kmv[8] = {km0.x, km0.y, km0.z, km0.w, km1.x, km1.y, km1.z, km1.w};
-          float pr[8];
+          float pr[8], ds[8];
           uint32_t keepm = 0xffu;
           float dscale = 1.f;
           if (p.drop.thresh) {
@@ -493,30 +502,26 @@ enc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
             const float sc = (__uint_as_float(sv[u * 8 + i]) + lbv[i]) + kmv[i];
             pr[i] = fast_exp2((sc - lse_q) * LOG2E_F);
             const float dp = ((keepm >> i) & 1u) ? __uint_as_float(dpv[u * 8 + i]) * dscale : 0.f;
-            ds[u * 8 + i] = pr[i] * (dp - D_q);
+            ds[i] = pr[i] * (dp - D_q);
             pr[i] = ((keepm >> i) & 1u) ? pr[i] * dscale : 0.f;  // the dV = P_drop^T dO operand
           }
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
-            ppk[c][u * 4 + i] = pack_bf16x2(pr[2 * i], pr[2 * i + 1]);
-            dpk[c][u * 4 + i] = pack_bf16x2(ds[u * 8 + 2 * i], ds[u * 8 + 2 * i + 1]);
+            ppk[u * 4 + i] = pack_bf16x2(pr[2 * i], pr[2 * i + 1]);
+            dpk[u * 4 + i] = pack_bf16x2(ds[2 * i], ds[2 * i + 1]);
           }
-        }
-        // Bias gradient = diagonal sums (k - q constant) of this 32x32 sub-block, as two systolic passes over
-        // the warp, exact in fp32.  Ascending columns with the partial sum moving one lane UP per column leaves
-        // diagonal d = 31 - lane (>= 0) complete in every lane; descending columns moving one lane DOWN leaves
-        // d = -lane (<= 0).  Lane 0 / lane 31 start a fresh diagonal each step (keep_* = 0 there).
-        float Rup = 0.f, Rdn = 0.f;
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          Rup = fmaf(__shfl_up_sync(0xffffffffu, Rup, 1), keep, ds[i]);
-          Rdn = fmaf(__shfl_down_sync(0xffffffffu, Rdn, 1), keep_dn, ds[31 - i]);
+          for (int i = 0; i < 8; ++i) {
+            Rup = fmaf(__shfl_up_sync(0xffffffffu, Rup, 1), keep, ds[i]);
+            const float done = __shfl_sync(0xffffffffu, Rup, 31);
+            Rdone = (lane == u * 8 + i) ? done : Rdone;
+          }
         }
         {
           const int iu = idx0 + 31 - lane;
           if (iu >= 0 && iu < nlut) atomicAdd(&s_dlut[iu], Rup);
-          const int id = idx0 - lane;
-          if (lane != 0 && id >= 0 && id < nlut) atomicAdd(&s_dlut[id], Rdn);  // d = 0 is already in Rup (lane 31)
+          const int id = idx0 + lane - 31;
+          if (lane != 31 && id >= 0 && id < nlut) atomicAdd(&s_dlut[id], Rdone);  // d = 0 is already in Rup (lane 31)
         }
       }
       // P / dS of the previous block may still be feeding its gradient MMAs: wait before overwriting them
@@ -526,18 +531,14 @@ enc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
         g_pending = false;
       }
       {
-        uint8_t* prow = smem + EB_P_OFF + chalf * 16384 + r * 128;
-        uint8_t* dsrow = smem + EB_DS_OFF + chalf * 16384 + r * 128;
+        // 64-key chunk (cq >> 1) of the K-major P / dS tiles; this warp's 32 keys are 16-byte units (cq & 1)*4..+4
+        uint8_t* prow = smem + EB_P_OFF + (cq >> 1) * 16384 + r * 128;
+        uint8_t* dsrow = smem + EB_DS_OFF + (cq >> 1) * 16384 + r * 128;
 #pragma unroll
-        for (int c = 0; c < 2; ++c) {
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const int unit = ((c * 4 + u) ^ (r & 7)) << 4;
-            *reinterpret_cast<uint4*>(prow + unit) =
-                make_uint4(ppk[c][u * 4], ppk[c][u * 4 + 1], ppk[c][u * 4 + 2], ppk[c][u * 4 + 3]);
-            *reinterpret_cast<uint4*>(dsrow + unit) =
-                make_uint4(dpk[c][u * 4], dpk[c][u * 4 + 1], dpk[c][u * 4 + 2], dpk[c][u * 4 + 3]);
-          }
+        for (int u = 0; u < 4; ++u) {
+          const int unit = (((cq & 1) * 4 + u) ^ (r & 7)) << 4;
+          *reinterpret_cast<uint4*>(prow + unit) = make_uint4(ppk[u * 4], ppk[u * 4 + 1], ppk[u * 4 + 2], ppk[u * 4 + 3]);
+          *reinterpret_cast<uint4*>(dsrow + unit) = make_uint4(dpk[u * 4], dpk[u * 4 + 1], dpk[u * 4 + 2], dpk[u * 4 + 3]);
         }
       }
       fence_proxy_async_smem();
@@ -579,15 +580,15 @@ enc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
         g_pending = false;
         tc_fence_after();
         const int key = kt * 128 + r;
-        uint32_t a[32], bb[32];
-        tmem_ld_32x32(t_row + TM_DK + chalf * 32, a);
-        tmem_ld_32x32(t_row + TM_DV + chalf * 32, bb);
+        uint32_t a[16], bb[16];
+        tmem_ld_32x16(t_row + TM_DK + cq * 16, a);
+        tmem_ld_32x16(t_row + TM_DV + cq * 16, bb);
         tmem_ld_wait();
         if (key < L) {
-          __nv_bfloat16* dk = p.dqkv + static_cast<size_t>(row0 + key) * 3 * p.inner + p.inner + h * 64 + chalf * 32;
+          __nv_bfloat16* dk = p.dqkv + static_cast<size_t>(row0 + key) * 3 * p.inner + p.inner + h * 64 + cq * 16;
           __nv_bfloat16* dv = dk + p.inner;
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
+          for (int u = 0; u < 2; ++u) {
             uint4 o;
             o.x = pack_bf16x2(__uint_as_float(a[u * 8 + 0]), __uint_as_float(a[u * 8 + 1]));
             o.y = pack_bf16x2(__uint_as_float(a[u * 8 + 2]), __uint_as_float(a[u * 8 + 3]));
@@ -612,13 +613,13 @@ enc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
 #pragma unroll 1
     for (int qt = 0; qt < nt; ++qt) {
       const int q = qt * 128 + r;
-      uint32_t a[32];
-      tmem_ld_32x32(t_row + TM_DQ + qt * 64 + chalf * 32, a);
+      uint32_t a[16];
+      tmem_ld_32x16(t_row + TM_DQ + qt * 64 + cq * 16, a);
       tmem_ld_wait();
       if (q < L) {
-        __nv_bfloat16* dq = p.dqkv + static_cast<size_t>(row0 + q) * 3 * p.inner + h * 64 + chalf * 32;
+        __nv_bfloat16* dq = p.dqkv + static_cast<size_t>(row0 + q) * 3 * p.inner + h * 64 + cq * 16;
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < 2; ++u) {
           uint4 o;
           o.x = pack_bf16x2(__uint_as_float(a[u * 8 + 0]), __uint_as_float(a[u * 8 + 1]));
           o.y = pack_bf16x2(__uint_as_float(a[u * 8 + 2]), __uint_as_float(a[u * 8 + 3]));
@@ -631,7 +632,7 @@ enc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
   }
   __syncthreads();
   if (p.dlut) {
-    for (int i = tid; i < nlut; i += 256) {
+    for (int i = tid; i < nlut; i += EB_THREADS) {
       const float v = s_dlut[i];
       if (v != 0.f) atomicAdd(&p.dlut[h * nlut + i], v);
     }
@@ -683,7 +684,7 @@ int enc_attn_bwd(const __nv_bfloat16* qkv, const __nv_bfloat16* out, const __nv_
   p.drop = drop;
   ProfScope prof(PROF_ENC_ATTN_BWD, 10.0 * P * H * static_cast<double>(L) * L * 64, s);
   dim3 grid(H, P);
-  launch_pdl(enc_attn_bwd_kernel, grid, dim3(256), EB_SMEM_BYTES, s, tm_qkv, tm_do, p);
+  launch_pdl(enc_attn_bwd_kernel, grid, dim3(EB_THREADS), EB_SMEM_BYTES, s, tm_qkv, tm_do, p);
   LAKO_CHECK_LAUNCH();
   return LAKO_OK;
 }
