@@ -48,6 +48,7 @@ struct EncAttnParams {
   int L, H, inner;            // L = text_maxlength (LUT size, lse pitch); per-passage length from cu when packed
   const int* cu;              // packed (un-padded) token layout: passage p owns rows [cu[p], cu[p+1]); null = padded
   DropSpec drop;              // dropout on the attention probabilities (HF:332); group = ((psg*H+h)*L+q)*32 + key/8
+  uint32_t* keepbits;         // [P][H][L][8] keep mask of the 256 keys of every query row, saved for the backward
 };
 
 constexpr float LOG2E_F = 1.4426950408889634f;
@@ -197,6 +198,7 @@ enc_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const EncAttnPar
     tmem_ld_32x32(t_row + c * 32, v);
     tmem_ld_wait();
     uint8_t* chunk = smem + (c >> 1) * 16384 + r * 128;
+    uint32_t kword = 0u;
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       float e[8];
@@ -207,6 +209,7 @@ enc_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const EncAttnPar
       }
       if (p.drop.thresh) {  // the row sum normalises the UNdropped probabilities; only the P V operand is masked
         const uint32_t k = drop_keep8(p.drop, (static_cast<unsigned long long>(psg * p.H + h) * Lmax + qc) * 32 + c * 4 + u);
+        kword |= k << (u * 8);
 #pragma unroll
         for (int i = 0; i < 8; ++i) e[i] = ((k >> i) & 1u) ? e[i] * p.drop.scale : 0.f;
       }
@@ -218,6 +221,8 @@ enc_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const EncAttnPar
       o.w = pack_bf16x2(e[6], e[7]);
       *reinterpret_cast<uint4*>(chunk + ((unit ^ (r & 7)) << 4)) = o;
     }
+    if (p.keepbits && p.drop.thresh && q < L)
+      p.keepbits[((static_cast<size_t>(psg) * p.H + h) * Lmax + q) * 8 + c] = kword;
   }
   s_red_l[chalf * 128 + r] = lsum;
   fence_proxy_async_smem();
@@ -269,7 +274,8 @@ enc_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const EncAttnPar
 
 // qkv bf16 [P*L][3*inner]; out bf16 [P*L][inner]; lse fp32 [P][H][L] (may be null)
 int enc_attn_fwd(const __nv_bfloat16* qkv, const unsigned char* mask, const float* bias_lut, __nv_bfloat16* out,
-                 float* lse, int P, int L, int H, cudaStream_t s, DropSpec drop, const int* cu, int packed_rows) {
+                 float* lse, int P, int L, int H, cudaStream_t s, DropSpec drop, const int* cu, int packed_rows,
+                 uint32_t* keepbits) {
   int rc = check_arch();
   if (rc) return rc;
   LAKO_REQUIRE(P > 0 && H > 0 && L > 0, LAKO_ERR_BAD_ARG);
@@ -299,6 +305,7 @@ int enc_attn_fwd(const __nv_bfloat16* qkv, const unsigned char* mask, const floa
   p.inner = inner;
   p.cu = cu;
   p.drop = drop;
+  p.keepbits = keepbits;
   ProfScope prof(PROF_ENC_ATTN_FWD, 4.0 * P * H * static_cast<double>(L) * L * 64, s);
   dim3 grid((L + 127) / 128, H, P);
   launch_pdl(enc_attn_fwd_kernel, grid, dim3(256), EA_SMEM_BYTES, s, tm, p);
@@ -324,6 +331,7 @@ struct EncAttnBwdParams {
   int L, H, inner;
   const int* cu;                 // packed layout offsets (see EncAttnParams); null = padded
   DropSpec drop;
+  const uint32_t* keepbits;      // keep masks saved by the forward (null: regenerate them with Philox)
 };
 
 constexpr int EB_Q_OFF = 0, EB_DO_OFF = 32768, EB_K_OFF = 65536, EB_V_OFF = 98304, EB_P_OFF = 131072,
@@ -333,11 +341,20 @@ constexpr int EB_Q_OFF = 0, EB_DO_OFF = 32768, EB_K_OFF = 65536, EB_V_OFF = 9830
 constexpr int EB_SMEM_BYTES = EB_BAR_OFF + 64 + 1024;
 constexpr int TM_S = 0, TM_DP = 128, TM_DQ = 256, TM_DK = 384, TM_DV = 448;
 
-// One CTA per (head, passage); 512 threads = 16 warps (the softmax arithmetic between the MMAs is latency bound, so
-// the CTA carries as many warps as the register file allows): warp w owns TMEM lane quarter (w & 3) = 32 query rows
-// and key columns (w >> 2)*32..+32 of each 128x128 (query tile x key tile) block.
+// One CTA per (head, passage); 16 softmax warps (the arithmetic between the MMAs is latency bound, so the CTA carries
+// as many warps as the register file allows) + 1 warp that issues the TMA loads and every MMA: softmax warp w owns
+// TMEM lane quarter (w & 3) = 32 query rows and key columns (w >> 2)*32..+32 of each 128x128 (query tile x key tile)
+// block.  The issuing warp runs ahead: S/dP of block i+1 and the 24 gradient MMAs of block i overlap the softmax
+// arithmetic of block i+1 (a softmax thread that also issued the MMAs held the whole CTA back ~35 % per block).
 // TMEM: S 128 | dP 128 | dQ 2x64 | dK 64 | dV 64 columns.
-constexpr int EB_THREADS = 512;
+constexpr int EB_SOFTMAX_THREADS = 512;
+constexpr int EB_THREADS = EB_SOFTMAX_THREADS + 32;
+#ifdef LAKO_TRACE
+__device__ long long g_eb_trace[64];
+#define EB_TRACE(i) do { if (tid == 0 && blockIdx.x == 0 && blockIdx.y == 0) g_eb_trace[i] = clock64(); } while (0)
+#else
+#define EB_TRACE(i) do { } while (0)
+#endif
 __global__ void __launch_bounds__(EB_THREADS, 1)
 enc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_do,
                     const EncAttnBwdParams p) {
@@ -351,13 +368,16 @@ enc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
   uint64_t* bar_load = reinterpret_cast<uint64_t*>(smem + EB_BAR_OFF);
   uint64_t* bar_mma = bar_load + 1;
   uint64_t* bar_grad = bar_load + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_load + 3);
+  uint64_t* bar_ready = bar_load + 3;  // all softmax threads: S/dP consumed, P/dS of the block stored
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_load + 4);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int quarter = warp & 3, cq = warp >> 2;
+  const bool issuer = tid == EB_SOFTMAX_THREADS;  // lane 0 of the 17th warp
   const int h = blockIdx.x, psg = blockIdx.y;
   const int Lmax = p.L;  // LUT geometry / lse pitch
   const int nlut = 2 * Lmax - 1;
+  EB_TRACE(0);
   pdl_launch_dependents();
   int row0 = psg * Lmax, L = Lmax;  // L = this passage's token count
   if (p.cu) {
@@ -368,17 +388,19 @@ enc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
   }
   const int nt = (L + 127) / 128;  // 128-row tiles of queries == of keys
 
-  if (tid == 0) {
+  if (issuer) {
     tma_prefetch_desc(&tm_qkv);
     tma_prefetch_desc(&tm_do);
     mbar_init(bar_load, 1);
     mbar_init(bar_mma, 1);
     mbar_init(bar_grad, 1);
+    mbar_init(bar_ready, EB_SOFTMAX_THREADS);
     fence_barrier_init();
   }
   if (warp == 0) tmem_alloc(tmem_slot, 512);
   pdl_wait();
-  if (tid == 0) {  // operand tiles: start the TMA traffic before the SIMT staging below
+  EB_TRACE(1);
+  if (issuer) {  // operand tiles: start the TMA traffic before the SIMT staging below
     mbar_arrive_expect_tx(bar_load, 16384 * 4 * nt);
     for (int t = 0; t < nt; ++t) {
       tma_load_2d(smem + EB_Q_OFF + t * 16384, &tm_qkv, bar_load, h * 64, row0 + t * 128);
@@ -387,19 +409,47 @@ enc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
       tma_load_2d(smem + EB_DO_OFF + t * 16384, &tm_do, bar_load, h * 64, row0 + t * 128);
     }
   }
-  stage_lut4(s_lut4, p.bias_lut + h * nlut, nlut, tid, EB_THREADS);
-  stage_kmask(s_kmask, p.mask ? p.mask + static_cast<size_t>(psg) * Lmax : nullptr, L, tid, EB_THREADS);
-  s_dlut[tid] = 0.f;
-  {
-    // two threads per query row (256 rows max): D[q] = sum_d dO*O over 32 of the 64 head dims each, lse[q]
+  if (tid < EB_SOFTMAX_THREADS) {
+    // Staging of the bias LUT (4 shifted copies, see stage_lut4), the additive key mask, lse and D[q] = sum_d dO*O.
+    // Every global load is issued before the first dependent instruction, so the prologue exposes ONE memory
+    // latency, not one per table.
+    const float* lut = p.bias_lut + h * nlut;
+    constexpr int NLV = (4 * LUTCOPY + EB_SOFTMAX_THREADS - 1) / EB_SOFTMAX_THREADS;
+    float lv[NLV];
+#pragma unroll
+    for (int j = 0; j < NLV; ++j) {
+      const int i = tid + j * EB_SOFTMAX_THREADS;
+      const int c = i / LUTCOPY, src = i - c * LUTCOPY + c;
+      lv[j] = (i < 4 * LUTCOPY && src < nlut) ? __ldg(lut + src) : 0.f;
+    }
+    unsigned char mk = 1;
+    if (tid < L && p.mask) mk = __ldg(p.mask + static_cast<size_t>(psg) * Lmax + tid);
+    // two threads per query row (256 rows max): each sums 32 of the 64 head dims
     const int q = tid >> 1, part = tid & 1;
-    float dsum = 0.f;
+    uint4 ov[4], dv[4];
+    float lse_q = INFINITY;  // rows beyond the passage -> P = exp(s - inf) = 0
     if (q < L) {
       const uint4* o4 = reinterpret_cast<const uint4*>(p.out + static_cast<size_t>(row0 + q) * p.inner + h * 64) + part * 4;
       const uint4* d4 = reinterpret_cast<const uint4*>(p.dout + static_cast<size_t>(row0 + q) * p.inner + h * 64) + part * 4;
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
-        const uint4 a = o4[u], b = d4[u];
+        ov[u] = __ldg(o4 + u);
+        dv[u] = __ldg(d4 + u);
+      }
+      if (part == 0) lse_q = __ldg(p.lse + (static_cast<size_t>(psg) * p.H + h) * Lmax + q);
+    }
+#pragma unroll
+    for (int j = 0; j < NLV; ++j) {
+      const int i = tid + j * EB_SOFTMAX_THREADS;
+      if (i < 4 * LUTCOPY) s_lut4[i] = lv[j];
+    }
+    if (tid < 256) s_kmask[tid] = (tid < L) ? (mk ? 0.f : MASK_MIN) : -INFINITY;
+    s_dlut[tid] = 0.f;
+    float dsum = 0.f;
+    if (q < L) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const uint4 a = ov[u], b = dv[u];
         dsum += bf16_lo(a.x) * bf16_lo(b.x) + bf16_hi(a.x) * bf16_hi(b.x) + bf16_lo(a.y) * bf16_lo(b.y) +
                 bf16_hi(a.y) * bf16_hi(b.y) + bf16_lo(a.z) * bf16_lo(b.z) + bf16_hi(a.z) * bf16_hi(b.z) +
                 bf16_lo(a.w) * bf16_lo(b.w) + bf16_hi(a.w) * bf16_hi(b.w);
@@ -408,13 +458,13 @@ enc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
     dsum += __shfl_xor_sync(0xffffffffu, dsum, 1);
     if (part == 0) {
       s_D[q] = dsum;
-      // lse = +inf for rows beyond the passage -> P = exp(s - inf) = 0
-      s_lse[q] = (q < L) ? p.lse[(static_cast<size_t>(psg) * p.H + h) * Lmax + q] : INFINITY;
+      s_lse[q] = lse_q;
     }
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  EB_TRACE(2);
   const uint32_t tmem = *tmem_slot;
 
   const uint32_t qa = smem_u32(smem + EB_Q_OFF), doa = smem_u32(smem + EB_DO_OFF), ka = smem_u32(smem + EB_K_OFF),
@@ -434,13 +484,49 @@ enc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
                 make_smem_desc_sw128(va + kt * 16384 + k * 32, 16, 1024), idesc_s, k > 0);
   };
 
-  if (tid == 0) {
-    mbar_wait(bar_load, 0);
-    tc_fence_after();
-    issue_s_dp(0, 0);
-    umma_commit(bar_mma);
-  }
-
+  if (warp == EB_SOFTMAX_THREADS / 32) {
+    // ---------------- issuing warp: one thread drives every MMA of the CTA
+    if (issuer) {
+      mbar_wait(bar_load, 0);
+      tc_fence_after();
+      issue_s_dp(0, 0);
+      umma_commit(bar_mma);
+      uint32_t r_phase = 0;
+      for (int kt = 0; kt < nt; ++kt) {
+        for (int qt = 0; qt < nt; ++qt) {
+          mbar_wait(bar_ready, r_phase);  // S/dP of this block consumed, its P / dS in shared memory
+          r_phase ^= 1;
+          tc_fence_after();
+          // next block's S / dP first (their TMEM columns are free again)
+          int nq = qt + 1, nk = kt;
+          if (nq == nt) {
+            nq = 0;
+            nk = kt + 1;
+          }
+          if (nk < nt) {
+            issue_s_dp(nq, nk);
+            umma_commit(bar_mma);
+          }
+          // dV[kt] += P^T dO[qt] ; dK[kt] += dS^T Q[qt]   (M = 128 keys, N = 64, K = 128 queries)
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            umma_bf16(tmem + TM_DV, make_smem_desc_sw128(pa + j * 2048, 16384, 1024),
+                      make_smem_desc_sw128(doa + qt * 16384 + j * 2048, 8192, 1024), idesc_tn, (qt > 0 || j > 0));
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            umma_bf16(tmem + TM_DK, make_smem_desc_sw128(dsa + j * 2048, 16384, 1024),
+                      make_smem_desc_sw128(qa + qt * 16384 + j * 2048, 8192, 1024), idesc_tn, (qt > 0 || j > 0));
+          // dQ[qt] += dS K[kt]   (M = 128 queries, N = 64, K = 128 keys)
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            umma_bf16(tmem + TM_DQ + qt * 64, make_smem_desc_sw128(dsa + (j >> 2) * 16384 + (j & 3) * 32, 16, 1024),
+                      make_smem_desc_sw128(ka + kt * 16384 + j * 2048, 8192, 1024), idesc_dq, (kt > 0 || j > 0));
+          umma_commit(bar_grad);
+        }
+      }
+    }
+  } else {
+  // ---------------- softmax warps
   const int r = quarter * 32 + lane;  // row within a 128-row tile == TMEM lane
   const uint32_t t_row = tmem + (static_cast<uint32_t>(quarter * 32) << 16);
   const float keep = (lane == 0) ? 0.f : 1.f;  // systolic diagonal sums: lane 0 starts a new diagonal
@@ -457,121 +543,107 @@ enc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
       const int qc = min(q, L - 1);
       const int b = Lmax - 1 - qc;
       const float* lutp = s_lut4 + (b & 3) * LUTCOPY + (b & ~3);
+      const bool rows_live = (qt * 128 + quarter * 32) < L;  // warp-uniform: any of this warp's queries in the passage
+      const int kbase = kt * 128 + cq * 32;                  // first key of this warp's 32-column chunk
+      // the forward's keep mask of this row's 32 keys (fetched ahead of the MMA wait)
+      uint32_t kword = 0xffffffffu;
+      if (p.keepbits && p.drop.thresh && q < L && kbase < L)
+        kword = __ldg(p.keepbits + ((static_cast<size_t>(psg) * p.H + h) * Lmax + q) * 8 + (kbase >> 5));
       mbar_wait(bar_mma, s_phase);
       s_phase ^= 1;
       tc_fence_after();
+      EB_TRACE(8 + (kt * 2 + qt) * 6 + 0);
       const float lse_q = s_lse[q];
       const float D_q = s_D[q];
-      uint32_t ppk[16], dpk[16];  // bf16x2-packed P_drop and dS of this thread's 32 columns
-      const bool rows_live = (qt * 128 + quarter * 32) < L;  // warp-uniform: any of this warp's queries in the passage
-      const int kbase = kt * 128 + cq * 32;                  // first key of this warp's 32-column chunk
-      if (!rows_live || kbase >= L) {
-        // nothing of this 32x32 sub-block lies inside the passage: P = dS = 0 (dV / dK sum over all 128 rows of
-        // the tile, so the zeros must really be written), no exp / Philox / diagonal sums
+      const bool live = rows_live && kbase < L;
+      // !live: nothing of this 32x32 sub-block lies inside the passage: P = dS = 0 (dV / dK sum over all 128 rows of
+      // the tile, so the zeros must really be written), no exp / Philox / diagonal sums.
+      // bias-gradient index of the diagonal d = i - lane of this 32x32 sub-block: rel = k - q
+      const int idx0 = (kbase - (qt * 128 + quarter * 32)) + (Lmax - 1);
+      // Bias gradient = diagonal sums (k - q constant) of this 32x32 sub-block, as one systolic pass over the warp,
+      // exact in fp32: with ascending columns and the partial sum moving one lane UP per column, lane 0 starts a
+      // fresh diagonal each step (keep = 0 there), lane 31 holds the COMPLETE diagonal d = i - 31 (<= 0) after
+      // column i (parked in lane i's Rdone), and after the last column lane l holds the complete d = 31 - l (>= 0).
+      float Rup = 0.f, Rdone = 0.f;
+      // 64-key chunk (cq >> 1) of the K-major P / dS tiles; this warp's 32 keys are 16-byte units (cq & 1)*4..+4
+      uint8_t* prow = smem + EB_P_OFF + (cq >> 1) * 16384 + r * 128;
+      uint8_t* dsrow = smem + EB_DS_OFF + (cq >> 1) * 16384 + r * 128;
 #pragma unroll
-        for (int i = 0; i < 16; ++i) ppk[i] = dpk[i] = 0u;
-      } else {
-        uint32_t sv[32], dpv[32];
-        tmem_ld_32x32(t_row + TM_S + cq * 32, sv);
-        tmem_ld_32x32(t_row + TM_DP + cq * 32, dpv);
-        tmem_ld_wait();
-        // bias-gradient index of the diagonal d = i - lane of this 32x32 sub-block: rel = k - q
-        const int idx0 = (kbase - (qt * 128 + quarter * 32)) + (Lmax - 1);
-        // Bias gradient = diagonal sums (k - q constant) of this 32x32 sub-block, as one systolic pass over the warp,
-        // exact in fp32: with ascending columns and the partial sum moving one lane UP per column, lane 0 starts a
-        // fresh diagonal each step (keep = 0 there), lane 31 holds the COMPLETE diagonal d = i - 31 (<= 0) after
-        // column i (parked in lane i's Rdone), and after the last column lane l holds the complete d = 31 - l (>= 0).
-        float Rup = 0.f, Rdone = 0.f;
+      for (int hh = 0; hh < 2; ++hh) {  // two 16-column halves keep the live register set small
+        uint32_t ppk[8], dpk[8];        // bf16x2-packed P_drop and dS of 16 columns
+        if (!live) {
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const float4 lb0 = *reinterpret_cast<const float4*>(lutp + kbase + u * 8);
-          const float4 lb1 = *reinterpret_cast<const float4*>(lutp + kbase + u * 8 + 4);
-          const float4 km0 = *reinterpret_cast<const float4*>(s_kmask + kbase + u * 8);
-          const float4 km1 = *reinterpret_cast<const float4*>(s_kmask + kbase + u * 8 + 4);
-          const float lbv[8] = {lb0.x, lb0.y, lb0.z, lb0.w, lb1.x, lb1.y, lb1.z, lb1.w};
-          const float kmv[8] = {km0.x, km0.y, km0.z, km0.w, km1.x, km1.y, km1.z, km1.w};
-          float pr[8], ds[8];
-          uint32_t keepm = 0xffu;
-          float dscale = 1.f;
-          if (p.drop.thresh) {
-            keepm = drop_keep8(p.drop, (static_cast<unsigned long long>(psg * p.H + h) * Lmax + qc) * 32 + (kbase >> 3) + u);
-            dscale = p.drop.scale;
-          }
+          for (int i = 0; i < 8; ++i) ppk[i] = dpk[i] = 0u;
+        } else {
+          uint32_t sv[16], dpv[16];
+          tmem_ld_32x16(t_row + TM_S + cq * 32 + hh * 16, sv);
+          tmem_ld_32x16(t_row + TM_DP + cq * 32 + hh * 16, dpv);
+          tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const float sc = (__uint_as_float(sv[u * 8 + i]) + lbv[i]) + kmv[i];
-            pr[i] = fast_exp2((sc - lse_q) * LOG2E_F);
-            const float dp = ((keepm >> i) & 1u) ? __uint_as_float(dpv[u * 8 + i]) * dscale : 0.f;
-            ds[i] = pr[i] * (dp - D_q);
-            pr[i] = ((keepm >> i) & 1u) ? pr[i] * dscale : 0.f;  // the dV = P_drop^T dO operand
-          }
+          for (int uu = 0; uu < 2; ++uu) {
+            const int u = hh * 2 + uu;
+            const float4 lb0 = *reinterpret_cast<const float4*>(lutp + kbase + u * 8);
+            const float4 lb1 = *reinterpret_cast<const float4*>(lutp + kbase + u * 8 + 4);
+            const float4 km0 = *reinterpret_cast<const float4*>(s_kmask + kbase + u * 8);
+            const float4 km1 = *reinterpret_cast<const float4*>(s_kmask + kbase + u * 8 + 4);
+            const float lbv[8] = {lb0.x, lb0.y, lb0.z, lb0.w, lb1.x, lb1.y, lb1.z, lb1.w};
+            const float kmv[8] = {km0.x, km0.y, km0.z, km0.w, km1.x, km1.y, km1.z, km1.w};
+            float pr[8], ds[8];
+            uint32_t keepm = 0xffu;
+            float dscale = 1.f;
+            if (p.drop.thresh) {
+              keepm = p.keepbits ? ((kword >> (u * 8)) & 0xffu)
+                                 : drop_keep8(p.drop, (static_cast<unsigned long long>(psg * p.H + h) * Lmax + qc) * 32 +
+                                                          (kbase >> 3) + u);
+              dscale = p.drop.scale;
+            }
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            ppk[u * 4 + i] = pack_bf16x2(pr[2 * i], pr[2 * i + 1]);
-            dpk[u * 4 + i] = pack_bf16x2(ds[2 * i], ds[2 * i + 1]);
-          }
+            for (int i = 0; i < 8; ++i) {
+              const float sc = (__uint_as_float(sv[uu * 8 + i]) + lbv[i]) + kmv[i];
+              pr[i] = fast_exp2((sc - lse_q) * LOG2E_F);
+              const float dp = ((keepm >> i) & 1u) ? __uint_as_float(dpv[uu * 8 + i]) * dscale : 0.f;
+              ds[i] = pr[i] * (dp - D_q);
+              pr[i] = ((keepm >> i) & 1u) ? pr[i] * dscale : 0.f;  // the dV = P_drop^T dO operand
+            }
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            Rup = fmaf(__shfl_up_sync(0xffffffffu, Rup, 1), keep, ds[i]);
-            const float done = __shfl_sync(0xffffffffu, Rup, 31);
-            Rdone = (lane == u * 8 + i) ? done : Rdone;
+            for (int i = 0; i < 4; ++i) {
+              ppk[uu * 4 + i] = pack_bf16x2(pr[2 * i], pr[2 * i + 1]);
+              dpk[uu * 4 + i] = pack_bf16x2(ds[2 * i], ds[2 * i + 1]);
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              Rup = fmaf(__shfl_up_sync(0xffffffffu, Rup, 1), keep, ds[i]);
+              const float done = __shfl_sync(0xffffffffu, Rup, 31);
+              Rdone = (lane == u * 8 + i) ? done : Rdone;
+            }
           }
         }
-        {
-          const int iu = idx0 + 31 - lane;
-          if (iu >= 0 && iu < nlut) atomicAdd(&s_dlut[iu], Rup);
-          const int id = idx0 + lane - 31;
-          if (lane != 31 && id >= 0 && id < nlut) atomicAdd(&s_dlut[id], Rdone);  // d = 0 is already in Rup (lane 31)
+        // P / dS of the previous block may still be feeding its gradient MMAs (issued together with this block's
+        // S / dP, so they are all but finished by now): wait before overwriting them
+        if (hh == 0 && g_pending) {
+          mbar_wait(bar_grad, g_phase);
+          g_phase ^= 1;
+          g_pending = false;
         }
-      }
-      // P / dS of the previous block may still be feeding its gradient MMAs: wait before overwriting them
-      if (g_pending) {
-        mbar_wait(bar_grad, g_phase);
-        g_phase ^= 1;
-        g_pending = false;
-      }
-      {
-        // 64-key chunk (cq >> 1) of the K-major P / dS tiles; this warp's 32 keys are 16-byte units (cq & 1)*4..+4
-        uint8_t* prow = smem + EB_P_OFF + (cq >> 1) * 16384 + r * 128;
-        uint8_t* dsrow = smem + EB_DS_OFF + (cq >> 1) * 16384 + r * 128;
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int unit = (((cq & 1) * 4 + u) ^ (r & 7)) << 4;
-          *reinterpret_cast<uint4*>(prow + unit) = make_uint4(ppk[u * 4], ppk[u * 4 + 1], ppk[u * 4 + 2], ppk[u * 4 + 3]);
-          *reinterpret_cast<uint4*>(dsrow + unit) = make_uint4(dpk[u * 4], dpk[u * 4 + 1], dpk[u * 4 + 2], dpk[u * 4 + 3]);
+        for (int uu = 0; uu < 2; ++uu) {
+          const int unit = (((cq & 1) * 4 + hh * 2 + uu) ^ (r & 7)) << 4;
+          *reinterpret_cast<uint4*>(prow + unit) = make_uint4(ppk[uu * 4], ppk[uu * 4 + 1], ppk[uu * 4 + 2], ppk[uu * 4 + 3]);
+          *reinterpret_cast<uint4*>(dsrow + unit) = make_uint4(dpk[uu * 4], dpk[uu * 4 + 1], dpk[uu * 4 + 2], dpk[uu * 4 + 3]);
         }
       }
+      if (live) {
+        const int iu = idx0 + 31 - lane;
+        if (iu >= 0 && iu < nlut) atomicAdd(&s_dlut[iu], Rup);
+        const int id = idx0 + lane - 31;
+        if (lane != 31 && id >= 0 && id < nlut) atomicAdd(&s_dlut[id], Rdone);  // d = 0 is already in Rup (lane 31)
+      }
+      EB_TRACE(8 + (kt * 2 + qt) * 6 + 2);
       fence_proxy_async_smem();
       tc_fence_before();
-      __syncthreads();
-      if (tid == 0) {
-        tc_fence_after();
-        // next block's S / dP first (their TMEM columns are free: every thread has read this block's S / dP)
-        int nq = qt + 1, nk = kt;
-        if (nq == nt) {
-          nq = 0;
-          nk = kt + 1;
-        }
-        if (nk < nt) {
-          issue_s_dp(nq, nk);
-          umma_commit(bar_mma);
-        }
-        // dV[kt] += P^T dO[qt] ; dK[kt] += dS^T Q[qt]   (M = 128 keys, N = 64, K = 128 queries)
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-          umma_bf16(tmem + TM_DV, make_smem_desc_sw128(pa + j * 2048, 16384, 1024),
-                    make_smem_desc_sw128(doa + qt * 16384 + j * 2048, 8192, 1024), idesc_tn, (qt > 0 || j > 0));
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-          umma_bf16(tmem + TM_DK, make_smem_desc_sw128(dsa + j * 2048, 16384, 1024),
-                    make_smem_desc_sw128(qa + qt * 16384 + j * 2048, 8192, 1024), idesc_tn, (qt > 0 || j > 0));
-        // dQ[qt] += dS K[kt]   (M = 128 queries, N = 64, K = 128 keys)
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-          umma_bf16(tmem + TM_DQ + qt * 64, make_smem_desc_sw128(dsa + (j >> 2) * 16384 + (j & 3) * 32, 16, 1024),
-                    make_smem_desc_sw128(ka + kt * 16384 + j * 2048, 8192, 1024), idesc_dq, (kt > 0 || j > 0));
-        umma_commit(bar_grad);
-      }
+      mbar_arrive(bar_ready);
+      EB_TRACE(8 + (kt * 2 + qt) * 6 + 3);
+      EB_TRACE(8 + (kt * 2 + qt) * 6 + 4);
       g_pending = true;
       if (qt == nt - 1) {
         // dK[kt], dV[kt] are final once the gradient MMAs just issued complete
@@ -602,11 +674,14 @@ enc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
             *reinterpret_cast<uint4*>(dv + u * 8) = o;
           }
         }
+        // the next key tile's first gradient MMA (which overwrites dK / dV) is only issued after every softmax
+        // thread has arrived on bar_ready for that block, i.e. after these TMEM reads
         tc_fence_before();
-        __syncthreads();  // dK/dV TMEM reads done before the next key tile's first MMA overwrites them
       }
+      EB_TRACE(8 + (kt * 2 + qt) * 6 + 5);
     }
   }
+  EB_TRACE(4);
   // every MMA has completed (the last iteration waited for the final commit)
   {
     tc_fence_after();
@@ -630,7 +705,9 @@ enc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
       }
     }
   }
+  }  // softmax warps
   __syncthreads();
+  EB_TRACE(5);
   if (p.dlut) {
     for (int i = tid; i < nlut; i += EB_THREADS) {
       const float v = s_dlut[i];
@@ -643,11 +720,18 @@ enc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
     tc_fence_after();
     tmem_dealloc(tmem, 512);
   }
+  EB_TRACE(6);
 }
+
+#ifdef LAKO_TRACE
+extern "C" int lako_debug_eb_trace(long long* out) {
+  return cudaMemcpyFromSymbol(out, g_eb_trace, sizeof(long long) * 64) == cudaSuccess ? 0 : 1;
+}
+#endif
 
 int enc_attn_bwd(const __nv_bfloat16* qkv, const __nv_bfloat16* out, const __nv_bfloat16* dout, const float* lse,
                  const unsigned char* mask, const float* bias_lut, __nv_bfloat16* dqkv, float* dlut, int P, int L,
-                 int H, cudaStream_t s, DropSpec drop, const int* cu, int packed_rows) {
+                 int H, cudaStream_t s, DropSpec drop, const int* cu, int packed_rows, const uint32_t* keepbits) {
   int rc = check_arch();
   if (rc) return rc;
   LAKO_REQUIRE(P > 0 && H > 0 && L > 0, LAKO_ERR_BAD_ARG);
@@ -682,6 +766,7 @@ int enc_attn_bwd(const __nv_bfloat16* qkv, const __nv_bfloat16* out, const __nv_
   p.inner = inner;
   p.cu = cu;
   p.drop = drop;
+  p.keepbits = keepbits;
   ProfScope prof(PROF_ENC_ATTN_BWD, 10.0 * P * H * static_cast<double>(L) * L * 64, s);
   dim3 grid(H, P);
   launch_pdl(enc_attn_bwd_kernel, grid, dim3(EB_THREADS), EB_SMEM_BYTES, s, tm_qkv, tm_do, p);

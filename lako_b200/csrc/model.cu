@@ -80,6 +80,7 @@ struct EncLayerAct {
   unsigned char* hbits;  // ReLU-activity bitmask [tokens][d_ff/8]
   bf16 *n_a, *qkv, *ao, *n_f, *h;
   float *lse, *rstd_a, *rstd_f;
+  uint32_t* akeep;  // attention-dropout keep masks [P][H][L][8] (forward -> backward)
 };
 struct DecLayerAct {
   unsigned char* hbits;
@@ -142,6 +143,7 @@ void carve(const lako_dims& dm, int B, int N, int L, int T, int mode, void* base
     shared_e.n_f = shared_e.n_a;
     shared_e.h = b.take<bf16>(Mt * ff);
     shared_e.lse = nullptr;
+    shared_e.akeep = nullptr;
     shared_e.rstd_a = shared_e.rstd_f = nullptr;
   }
   for (int l = 0; l < nl; ++l) {
@@ -157,6 +159,7 @@ void carve(const lako_dims& dm, int B, int N, int L, int T, int mode, void* base
     a.h = b.take<bf16>(Mt * ff);
     a.hbits = b.take<unsigned char>(Mt * ff / 8);
     a.lse = b.take<float>(static_cast<size_t>(w.P) * H * L);
+    a.akeep = b.take<uint32_t>(static_cast<size_t>(w.P) * H * L * 8);
     a.rstd_a = b.take<float>(Mt);
     a.rstd_f = b.take<float>(Mt);
   }
@@ -371,7 +374,7 @@ int encode(const Ptrs& p, const lako_fidt5* m, Work& w, const long long* ids, co
       RC(rmsnorm_fwd(w.X[2 * l - 1], w.delta_enc, w.X[2 * l], p.wf + p.lo.enc_ln0[l], a.n_a, a.rstd_a, Mt, d, p.eps,
                      1.f, s, dr(l - 1, E_FF)));
     RC(lin_fwd(a.n_a, p.wb + p.lo.enc_qkv[l], a.qkv, Mt, 3 * inner, d, EPI_BF16, 1.f, s));
-    RC(enc_attn_fwd(a.qkv, amask, w.lut_enc, a.ao, a.lse, w.P, w.L, p.H, s, dr(l, E_ATTN), w.cu, Mt));
+    RC(enc_attn_fwd(a.qkv, amask, w.lut_enc, a.ao, a.lse, w.P, w.L, p.H, s, dr(l, E_ATTN), w.cu, Mt, a.akeep));
     RC(lin_fwd(a.ao, p.wb + p.lo.enc_o[l], w.delta_enc, Mt, d, inner, EPI_BF16, 1.f, s));
     RC(rmsnorm_fwd(w.X[2 * l], w.delta_enc, w.X[2 * l + 1], p.wf + p.lo.enc_ln1[l], a.n_f, a.rstd_f, Mt, d, p.eps, 1.f,
                    s, dr(l, E_O)));
@@ -583,7 +586,7 @@ extern "C" int lako_fidt5_backward(const lako_fidt5* m, const lako_batch* bt, co
     RC(lin_dgrad(w.dres_enc_b, p.wb + p.lo.enc_o[l], w.dao_enc, Mt, d, inner, nullptr, 1.f, s));
     RC(lin_wgrad(w.dres_enc_b, a.ao, g + p.lo.enc_o[l], Mt, d, inner, 1.f, s));
     RC(enc_attn_bwd(a.qkv, a.ao, w.dao_enc, a.lse, xmask, w.lut_enc, w.dqkv_enc, w.dlut_enc, w.P, w.L, H, s,
-                    dr(l, E_ATTN), w.cu, Mt));
+                    dr(l, E_ATTN), w.cu, Mt, a.akeep));
     RC(lin_dgrad(w.dqkv_enc, p.wb + p.lo.enc_qkv[l], w.dn_enc, Mt, 3 * inner, d, nullptr, 1.f, s));
     RC(lin_wgrad(w.dqkv_enc, a.n_a, g + p.lo.enc_qkv[l], Mt, 3 * inner, d, 1.f, s));
     RC(rmsnorm_bwd(w.dn_enc, w.X[2 * l], a.rstd_a, p.wf + p.lo.enc_ln0[l], w.dres_enc, w.dres_enc_b,

@@ -45,10 +45,11 @@ int fold_dlut(const float* dlut, const int* buckets, float* dtable, int H, int L
               cudaStream_t s);
 int enc_attn_fwd(const __nv_bfloat16* qkv, const unsigned char* mask, const float* bias_lut, __nv_bfloat16* out,
                  float* lse, int P, int L, int H, cudaStream_t s, DropSpec drop = DropSpec{}, const int* cu = nullptr,
-                 int packed_rows = 0);
+                 int packed_rows = 0, uint32_t* keepbits = nullptr);
 int enc_attn_bwd(const __nv_bfloat16* qkv, const __nv_bfloat16* out, const __nv_bfloat16* dout, const float* lse,
                  const unsigned char* mask, const float* bias_lut, __nv_bfloat16* dqkv, float* dlut, int P, int L,
-                 int H, cudaStream_t s, DropSpec drop = DropSpec{}, const int* cu = nullptr, int packed_rows = 0);
+                 int H, cudaStream_t s, DropSpec drop = DropSpec{}, const int* cu = nullptr, int packed_rows = 0,
+                 const uint32_t* keepbits = nullptr);
 
 // dec_attn.cu
 size_t xattn_workspace_bytes(int B, int H, int T, int M);
