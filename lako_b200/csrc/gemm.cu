@@ -42,18 +42,19 @@ struct GemmParams {
   DropSpec drop;  // EPI_BF16_RELU only: dropout after the activation (HF:95), element index = row * ldc + col
 };
 
-// Epilogue of one 128-row x BN-column accumulator tile for the warp owning TMEM lane quarter q.
+// Epilogue of one 128-row x BN-column accumulator tile for a warp owning TMEM lane quarter q: its 64-column
+// groups [g_begin, g_end) (several warps may share a lane quarter), staged through 4 KB slot `slot` of sStage.
 template <int BN, int EPI>
 __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t t_acc, uint8_t* sStage, int m0, int n0,
-                                              int q, int lane) {
+                                              int q, int lane, int g_begin = 0, int g_end = BN / 64, int slot = -1) {
   if constexpr (EPI == EPI_BF16 || EPI == EPI_BF16_RELU || EPI == EPI_BF16_MASK || EPI == EPI_BF16_BITMASK) {
     // bf16 output: TMEM (thread = row) -> registers -> per-warp swizzled smem -> coalesced 16 B stores
     // (each store instruction writes four full 128 B row segments)
-    uint8_t* stg = sStage + q * 4096;
+    uint8_t* stg = sStage + (slot < 0 ? q : slot) * 4096;
     __nv_bfloat16* C = reinterpret_cast<__nv_bfloat16*>(p.C);
     const __nv_bfloat16* AUX = reinterpret_cast<const __nv_bfloat16*>(p.aux);
 #pragma unroll 1
-    for (int g = 0; g < BN / 64; ++g) {
+    for (int g = g_begin; g < g_end; ++g) {
       const int col0 = n0 + g * 64;
       if (col0 >= p.N) break;  // warp-uniform
       // ReLU-mask operand: fetch this lane's eight 16 B pieces up front so their latency overlaps the TMEM load
@@ -155,7 +156,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t t_ac
     const int row = m0 + q * 32 + lane;
     const bool row_ok = row < p.M;
 #pragma unroll 1
-    for (int c = 0; c < BN / 32; ++c) {
+    for (int c = g_begin * 2; c < g_end * 2; ++c) {
       const int col0 = n0 + c * 32;
       if (col0 >= p.N) break;  // warp-uniform
       uint32_t r[32];
@@ -361,12 +362,15 @@ struct Gemm2Cfg {
   static constexpr int B_BYTES = 128 * BK * 2;       // this CTA's half of the 256-row B tile
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES = 6;
-  static constexpr int STAGING_BYTES = 4 * 4096;
+  static constexpr int EPI_WARPS = 8;  // two warps per TMEM lane quarter, 128 of the 256 columns each: with K as short
+                                       // as d_model the epilogue (not the MMA) bounds a tile when 4 warps drain it
+  static constexpr int THREADS = 128 + EPI_WARPS * 32;
+  static constexpr int STAGING_BYTES = EPI_WARPS * 4096;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + 1024 + 256;
 };
 
 template <bool A_MN, bool B_MN, int EPI>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Gemm2Cfg::THREADS, 1)
 gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
   using Cfg = Gemm2Cfg;
   constexpr int STAGES = Cfg::STAGES;
@@ -400,7 +404,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);   // multicast tcgen05.commit
-      mbar_init(&tempty_bar[i], 8);  // 4 epilogue warps x 2 CTAs (only the leader's copy is used)
+      mbar_init(&tempty_bar[i], 2 * Cfg::EPI_WARPS);  // epilogue warps x 2 CTAs (only the leader's copy is used)
     }
     fence_barrier_init();
   }
@@ -503,7 +507,10 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const int n0 = (mn % p.tiles_n) * BN;
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
-      epilogue_tile<BN, EPI>(p, tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN, sStage, m0, n0, q, lane);
+      constexpr int G_PER_WARP = (BN / 64) / (Cfg::EPI_WARPS / 4);
+      const int part = (warp - 4) >> 2;
+      epilogue_tile<BN, EPI>(p, tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN, sStage, m0, n0, q, lane,
+                             part * G_PER_WARP, (part + 1) * G_PER_WARP, warp - 4);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(mapa_u32(&tempty_bar[acc], 0));
@@ -537,7 +544,7 @@ static int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const Ge
   }
   const int total = p.tiles_m * p.tiles_n * p.splitk;
   const int clusters = min(total, device_sm_count() / 2);
-  launch_pdl(kern, dim3(clusters * 2), dim3(GEMM_THREADS), Cfg::SMEM_BYTES, stream, tmA, tmB, p);
+  launch_pdl(kern, dim3(clusters * 2), dim3(Cfg::THREADS), Cfg::SMEM_BYTES, stream, tmA, tmB, p);
   LAKO_CHECK_LAUNCH();
   return LAKO_OK;
 }
