@@ -44,8 +44,13 @@ def run(tag, M, N, K, a_mn, b_mn, epi):
     print(f"{tag:28s} M{M:6d} N{N:6d} K{K:6d}  1cta {res[0]:7.0f}  pair {res[1]:7.0f}  cublas {res[2]:7.0f} TF/s", flush=True)
 
 
-for name, (Mt, d, inner, ff, nl) in {"base": (16000, 768, 768, 3072, 12), "large": (40000, 1024, 1024, 4096, 24)}.items():
-    print("==", name)
+# GB_MT_BASE / GB_MT_LARGE override the token counts (e.g. the packed row counts of the bench batches); GB_ONLY=base|large
+CASES = {"base": (int(os.environ.get("GB_MT_BASE", 16000)), 768, 768, 3072, 12),
+         "large": (int(os.environ.get("GB_MT_LARGE", 40000)), 1024, 1024, 4096, 24)}
+for name, (Mt, d, inner, ff, nl) in CASES.items():
+    if os.environ.get("GB_ONLY", name) != name:
+        continue
+    print("==", name, "tokens", Mt)
     run("fwd qkv", Mt, 3 * inner, d, False, False, nat.EPI_BF16)
     run("fwd o", Mt, d, inner, False, False, nat.EPI_BF16)
     run("fwd wi relu", Mt, ff, d, False, False, nat.EPI_BF16_RELU)
