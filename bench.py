@@ -259,11 +259,16 @@ def main():
     launches0 = lib.lako_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    prof_range = bool(os.environ.get("LAKO_PROFILER_RANGE"))  # ncu --profile-from-start off: capture the timed steps only
+    if prof_range:
+        torch.cuda.profiler.start()
     e0.record()
     for i in range(steps):
         loss = train_step(model, opt, *resident[i % n_batches])
     e1.record()
     barrier()
+    if prof_range:
+        torch.cuda.profiler.stop()
     launches = lib.lako_launch_count() - launches0
     ms = e0.elapsed_time(e1)
     if sampler:
@@ -337,10 +342,17 @@ def main():
         g_ms, g_wk, g_n = sum(msa[i] for i in gi), sum(wka[i] for i in gi), sum(cna[i] for i in gi)
         gemm_tf = g_wk / (g_ms * 1e-3) / 1e12
         peak = peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])
+        # dram__bytes_read.sum + dram__bytes_write.sum per GEMM launch from the committed ncu capture of this command
+        traffic = None
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json")))
+            traffic = tj.get(args.workload, {}).get("gemm_dram_bytes_per_launch")
+        except Exception:
+            pass
         roofline = {"bound": "tensor", "kernel": "gemm_bf16_kernel / gemm2_bf16_kernel (tcgen05), all launches",
                     "achieved": round(gemm_tf, 1),
                     "peak": peak, "peak_source": f"{which} sustained cuBLAS bf16 (kernel timed inside a long step)",
-                    "unit": "TFLOP/s", "frac": round(gemm_tf / peak, 4), "traffic": None,
+                    "unit": "TFLOP/s", "frac": round(gemm_tf / peak, 4), "traffic": traffic,
                     "launches_per_step": g_n // nprof, "avg_launch_ms": round(g_ms / max(1, g_n), 5),
                     "share_of_step": round(g_ms / nprof / step_ms_prof, 4)}
 

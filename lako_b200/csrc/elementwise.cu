@@ -535,7 +535,8 @@ int ce_fwd_bwd(const float* logits, const long long* labels, float* stats, float
 // --------------------------------------------------------------------------------------------
 // casts / transposes / fills
 // --------------------------------------------------------------------------------------------
-__global__ void cast_f32_to_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, size_t n) {
+// rezero: the source is a split-K accumulation scratch; leave it zeroed for its next user
+__global__ void cast_f32_to_bf16_kernel(float* __restrict__ in, __nv_bfloat16* __restrict__ out, size_t n, int rezero) {
   pdl_launch_dependents();
   pdl_wait();
   const size_t i = (static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x) * 8;
@@ -548,14 +549,22 @@ __global__ void cast_f32_to_bf16_kernel(const float* __restrict__ in, __nv_bfloa
     o.z = pack_bf16x2(b.x, b.y);
     o.w = pack_bf16x2(b.z, b.w);
     *reinterpret_cast<uint4*>(out + i) = o;
+    if (rezero) {
+      *reinterpret_cast<float4*>(in + i) = make_float4(0.f, 0.f, 0.f, 0.f);
+      *reinterpret_cast<float4*>(in + i + 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
   } else {
-    for (size_t e = i; e < n; ++e) out[e] = __float2bfloat16(in[e]);
+    for (size_t e = i; e < n; ++e) {
+      out[e] = __float2bfloat16(in[e]);
+      if (rezero) in[e] = 0.f;
+    }
   }
 }
-int cast_f32_to_bf16(const float* in, __nv_bfloat16* out, size_t n, cudaStream_t s) {
+int cast_f32_to_bf16(const float* in, __nv_bfloat16* out, size_t n, cudaStream_t s, bool rezero) {
   if (n == 0) return LAKO_OK;
   const size_t blocks = (n + 2047) / 2048;
-  launch_pdl(cast_f32_to_bf16_kernel, dim3(static_cast<unsigned>(blocks)), dim3(256), 0, s, in, out, n);
+  launch_pdl(cast_f32_to_bf16_kernel, dim3(static_cast<unsigned>(blocks)), dim3(256), 0, s, const_cast<float*>(in), out, n,
+             rezero ? 1 : 0);
   LAKO_CHECK_LAUNCH();
   return LAKO_OK;
 }

@@ -113,6 +113,7 @@ struct Work {
   long long* dec_ids;
   // backward temporaries
   float *dres_enc, *dres_dec, *dq_f32;
+  float* dsk_f32;  // [BT][d] split-K accumulation scratch of the decoder's deep-K dgrads (kept zeroed between uses)
   bf16 *dres_enc_b, *dn_enc, *dh_enc, *dao_enc, *dqkv_enc, *dkv_all, *dmem;
   bf16 *dres_dec_b, *dn_dec, *dh_dec, *dao_dec, *dqkv_dec, *dq_dec, *dhn;
   size_t bytes;
@@ -253,6 +254,7 @@ void carve(const lako_dims& dm, int B, int N, int L, int T, int mode, void* base
     w.dqkv_dec = b.take<bf16>(BT * 3 * inner);
     w.dq_dec = b.take<bf16>(BT * inner);
     w.dq_f32 = b.take<float>(BT * inner);
+    w.dsk_f32 = b.take<float>(BT * d);
     w.dhn = b.take<bf16>(BT * d);
   }
   w.bytes = (b.off + 255) & ~size_t(255);
@@ -274,6 +276,15 @@ inline int lin_dgrad(const bf16* dy, const bf16* W, bf16* dx, int M, int N, int 
                      float alpha, cudaStream_t s) {
   return gemm_bf16(dy, W, dx, M, K, N, N, K, K, 0, 1, relu_bits ? EPI_BF16_BITMASK : EPI_BF16, alpha, relu_bits, K / 8, 1,
                    0, s);
+}
+// Same product for the decoder's few-row, deep-N cases (LM head, FFN-in, fused qkv): an 80-row dgrad has only a handful of
+// output tiles, so a single CTA per tile would stream all of N serially.  Split N over many CTAs accumulating into the
+// zeroed fp32 scratch, then round to bf16 (the cast leaves the scratch zeroed again).
+inline int lin_dgrad_splitk(const bf16* dy, int ld_dy, const bf16* W, bf16* dx, float* scratch, int M, int N, int K,
+                            float alpha, cudaStream_t s) {
+  int rc = gemm_bf16(dy, W, scratch, M, K, N, ld_dy, K, K, 0, 1, EPI_F32_ATOMIC, alpha, nullptr, 0, 0, 0, s);
+  if (rc) return rc;
+  return cast_f32_to_bf16(scratch, dx, static_cast<size_t>(M) * K, s, true);
 }
 // dW[N,K] += alpha * dy[M,N]^T x[M,K]
 inline int lin_wgrad(const bf16* dy, const bf16* x, float* dW, int M, int N, int K, float alpha, cudaStream_t s) {
@@ -506,6 +517,8 @@ extern "C" int lako_fidt5_backward(const lako_fidt5* m, const lako_batch* bt, co
 
   cudaMemsetAsync(w.dlut_enc, 0, sizeof(float) * H * (2 * w.L - 1), s);
   cudaMemsetAsync(w.dlut_dec, 0, sizeof(float) * H * (2 * w.T - 1), s);
+  cudaMemsetAsync(w.dsk_f32, 0, sizeof(float) * BT * d, s);
+  cudaMemsetAsync(w.dq_f32, 0, sizeof(float) * BT * inner, s);
 
   SideCtx& sc = side_ctx();
   cudaStream_t ws = sc.side ? sc.side : s;  // stream of the decoder wgrads
@@ -517,8 +530,7 @@ extern "C" int lako_fidt5_backward(const lako_fidt5* m, const lako_batch* bt, co
   };
   // ---- LM head
   if (loss_grad) RC(scale_bf16_dev(w.dlogits, static_cast<size_t>(BT) * vpad, loss_grad, s));
-  RC(gemm_bf16(w.dlogits, p.wb + p.lo.shared, w.dhn, BT, d, p.V, static_cast<int>(vpad), d, d, 0, 1, EPI_BF16, alpha,
-               nullptr, 0, 1, 0, s));
+  RC(lin_dgrad_splitk(w.dlogits, static_cast<int>(vpad), p.wb + p.lo.shared, w.dhn, w.dsk_f32, BT, p.V, d, alpha, s));
   fork();
   RC(gemm_bf16(w.dlogits, w.hn, g + p.lo.shared, p.V, d, BT, static_cast<int>(vpad), d, d, 1, 1, EPI_F32_ATOMIC, alpha,
                nullptr, 0, 1, 0, ws));
@@ -531,22 +543,21 @@ extern "C" int lako_fidt5_backward(const lako_fidt5* m, const lako_batch* bt, co
     DecGrad& dg = w.dg[l];
     // FFN
     RC(lin_dgrad(dg.g0, p.wb + p.lo.dec_wo[l], dg.dh, BT, d, ff, a.hbits, dsc, s));
-    RC(lin_dgrad(dg.dh, p.wb + p.lo.dec_wi[l], w.dn_dec, BT, ff, d, nullptr, 1.f, s));
+    RC(lin_dgrad_splitk(dg.dh, ff, p.wb + p.lo.dec_wi[l], w.dn_dec, w.dsk_f32, BT, ff, d, 1.f, s));
     RC(rmsnorm_bwd(w.dn_dec, w.Y[3 * l + 2], a.rstd_f, p.wf + p.lo.dec_ln2[l], w.dres_dec, dg.g1,
                    g + p.lo.dec_ln2[l], BT, d, 1, 1.f, s, dr.none(), dr(l, D_XO)));
     // cross-attention
     RC(lin_dgrad(dg.g1, p.wb + p.lo.dec_xo[l], w.dao_dec, BT, d, inner, nullptr, 1.f, s));
-    cudaMemsetAsync(w.dq_f32, 0, sizeof(float) * BT * inner, s);
     RC(xattn_bwd(a.q, w.kv_all, xmask, a.xo, w.dao_dec, a.lse, w.dkv_all, w.dq_f32, bt->B, bt->T, w.M, H, inner,
                  nl * 2 * inner, l * 2 * inner, l * 2 * inner + inner, inner, s, dr(l, D_XP), w.cu, bt->N));
-    RC(cast_f32_to_bf16(w.dq_f32, dg.dq, static_cast<size_t>(BT) * inner, s));
+    RC(cast_f32_to_bf16(w.dq_f32, dg.dq, static_cast<size_t>(BT) * inner, s, true));
     RC(lin_dgrad(dg.dq, p.wb + p.lo.dec_xq[l], w.dn_dec, BT, inner, d, nullptr, 1.f, s));
     RC(rmsnorm_bwd(w.dn_dec, w.Y[3 * l + 1], a.rstd_c, p.wf + p.lo.dec_ln1[l], w.dres_dec, dg.g2,
                    g + p.lo.dec_ln1[l], BT, d, 1, 1.f, s, dr.none(), dr(l, D_O)));
     // self-attention
     RC(lin_dgrad(dg.g2, p.wb + p.lo.dec_o[l], w.dao_dec, BT, d, inner, nullptr, 1.f, s));
     RC(dself_bwd(a.qkv, w.dao_dec, a.probs, dg.dqkv, w.dlut_dec, bt->B, bt->T, H, s, dr(l, D_SELF)));
-    RC(lin_dgrad(dg.dqkv, p.wb + p.lo.dec_qkv[l], w.dn_dec, BT, 3 * inner, d, nullptr, 1.f, s));
+    RC(lin_dgrad_splitk(dg.dqkv, 3 * inner, p.wb + p.lo.dec_qkv[l], w.dn_dec, w.dsk_f32, BT, 3 * inner, d, 1.f, s));
     RC(rmsnorm_bwd(w.dn_dec, w.Y[3 * l], a.rstd_s, p.wf + p.lo.dec_ln0[l], w.dres_dec,
                    l > 0 ? w.dg[l - 1].g0 : w.dres_dec_b, g + p.lo.dec_ln0[l], BT, d, 1, 1.f, s, dr.none(),
                    l > 0 ? dr(l - 1, D_FF) : dr.none()));

@@ -28,7 +28,7 @@ int shift_right(const long long* labels, long long* dec_ids, int B, int T, cudaS
 int count_valid(const long long* labels, int n, float* stats, cudaStream_t s);
 int ce_fwd_bwd(const float* logits, const long long* labels, float* stats, float* row_loss, __nv_bfloat16* dlogits,
                int rows, int V, int ld, int ld_d, cudaStream_t s);
-int cast_f32_to_bf16(const float* in, __nv_bfloat16* out, size_t n, cudaStream_t s);
+int cast_f32_to_bf16(const float* in, __nv_bfloat16* out, size_t n, cudaStream_t s, bool rezero = false);
 int dropout_mask(unsigned char* keep, size_t n, unsigned long long seed, unsigned step, unsigned site, float p,
                  cudaStream_t s);
 int scale_bf16_dev(__nv_bfloat16* x, size_t n, const float* scalar, cudaStream_t s);
