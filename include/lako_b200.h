@@ -52,6 +52,13 @@ int lako_check_device(void); /* 0 iff the current device is sm_100 */
  *       width, 512 = CTA-pair kernel (256x256 per 2-CTA cluster). */
 int lako_gemm_bf16(const void* A, const void* B, void* C, int M, int N, int K, int lda, int ldb, int ldc, int a_mn,
                    int b_mn, int epi, float alpha, const void* aux, int ld_aux, int splitk, int bn, void* stream);
+/* nbatch same-shape weight-gradient products in one launch: C_z[M][ldc] (fp32) += alpha * A_z^T B_z with
+   A_z row-major [K][lda >= M], B_z row-major [K][ldb >= N] (host arrays of device pointers).  Replaces the per-layer
+   dW accumulation autograd performs for every decoder Linear (HF modeling_t5.py: nn.Linear backward of
+   T5Attention q/k/v/o :189-192, T5DenseReluDense wi/wo :83-84) when the per-layer problems are too small to fill
+   the chip one at a time. */
+int lako_gemm_bf16_wgrad_batched(const void* const* A, const void* const* B, float* const* C, int nbatch, int M, int N,
+                                 int K, int lda, int ldb, int ldc, float alpha, void* stream);
 
 /* ---- T5LayerNorm (RMSNorm) fused with the residual add: HF:55-68 + HF:375,149 ------------------- */
 int lako_rmsnorm_fwd(const float* x, const void* delta_bf16, float* x_out, const float* w, void* out_bf16, float* rstd,

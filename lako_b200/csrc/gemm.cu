@@ -369,9 +369,11 @@ struct Gemm2Cfg {
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + 1024 + 256;
 };
 
+// Body shared by the single-problem kernel and the batched one: `nbatch` problems of identical shape, problem z
+// with its own tensor maps tmAs[z] / tmBs[z] and output Cs[z] (Cs == nullptr: one problem writing p.C).
 template <bool A_MN, bool B_MN, int EPI>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Gemm2Cfg::THREADS, 1)
-gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+__device__ __forceinline__ void gemm2_body(const CUtensorMap* tmAs, const CUtensorMap* tmBs, void* const* Cs, int nbatch,
+                                           const GemmParams& p) {
   using Cfg = Gemm2Cfg;
   constexpr int STAGES = Cfg::STAGES;
   constexpr int BN = Cfg::BN;
@@ -394,8 +396,8 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   pdl_launch_dependents();
 
   if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tmA);
-    tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(tmAs);
+    tma_prefetch_desc(tmBs);
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < STAGES; ++i) {
@@ -416,7 +418,8 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   pdl_wait();
 
   const int tiles_mn = p.tiles_m * p.tiles_n;  // tiles_m counts 256-row tiles here
-  const int total_tiles = tiles_mn * p.splitk;
+  const int per_problem = tiles_mn * p.splitk;
+  const int total_tiles = per_problem * nbatch;
   const int cluster_id = blockIdx.x >> 1;
   const int n_clusters = gridDim.x >> 1;
 
@@ -425,8 +428,12 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       int stage = 0;
       uint32_t phase = 0;
       for (int t = cluster_id; t < total_tiles; t += n_clusters) {
-        const int ks = t / tiles_mn;
-        const int mn = t - ks * tiles_mn;
+        const int z = t / per_problem;
+        const int tz = t - z * per_problem;
+        const CUtensorMap& tmA = tmAs[z];
+        const CUtensorMap& tmB = tmBs[z];
+        const int ks = tz / tiles_mn;
+        const int mn = tz - ks * tiles_mn;
         const int m0 = (mn / p.tiles_n) * 256 + static_cast<int>(rank) * 128;
         const int n0 = (mn % p.tiles_n) * BN + static_cast<int>(rank) * 128;
         const int kb0 = ks * p.kb_per_split;
@@ -464,7 +471,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       int acc = 0;
       uint32_t acc_phase = 0;
       for (int t = cluster_id; t < total_tiles; t += n_clusters) {
-        const int ks = t / tiles_mn;
+        const int ks = (t % per_problem) / tiles_mn;
         const int kb0 = ks * p.kb_per_split;
         const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
@@ -500,16 +507,19 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const int q = warp & 3;
     int acc = 0;
     uint32_t acc_phase = 0;
+    GemmParams pz = p;
     for (int t = cluster_id; t < total_tiles; t += n_clusters) {
-      const int ks = t / tiles_mn;
-      const int mn = t - ks * tiles_mn;
+      const int z = t / per_problem;
+      const int tz = t - z * per_problem;
+      if (Cs) pz.C = Cs[z];
+      const int mn = tz % tiles_mn;
       const int m0 = (mn / p.tiles_n) * 256 + static_cast<int>(rank) * 128;
       const int n0 = (mn % p.tiles_n) * BN;
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       constexpr int G_PER_WARP = (BN / 64) / (Cfg::EPI_WARPS / 4);
       const int part = (warp - 4) >> 2;
-      epilogue_tile<BN, EPI>(p, tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN, sStage, m0, n0, q, lane,
+      epilogue_tile<BN, EPI>(pz, tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN, sStage, m0, n0, q, lane,
                              part * G_PER_WARP, (part + 1) * G_PER_WARP, warp - 4);
       tc_fence_before();
       __syncwarp();
@@ -527,6 +537,27 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     tc_fence_after();
     tmem_dealloc_2sm(tmem_base, 512);
   }
+}
+
+template <bool A_MN, bool B_MN, int EPI>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Gemm2Cfg::THREADS, 1)
+gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+  gemm2_body<A_MN, B_MN, EPI>(&tmA, &tmB, nullptr, 1, p);
+}
+
+// Up to GEMM_MAX_BATCH same-shape problems in one launch (the decoder's per-layer weight gradients: each is a
+// few-microsecond problem whose launch + pipeline fill costs more than its work).
+constexpr int GEMM_MAX_BATCH = 24;
+struct Gemm2Batch {
+  CUtensorMap a[GEMM_MAX_BATCH];
+  CUtensorMap b[GEMM_MAX_BATCH];
+  void* c[GEMM_MAX_BATCH];
+  int n;
+};
+template <bool A_MN, bool B_MN, int EPI>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Gemm2Cfg::THREADS, 1)
+gemm2_batched_kernel(const __grid_constant__ Gemm2Batch bt, const GemmParams p) {
+  gemm2_body<A_MN, B_MN, EPI>(bt.a, bt.b, bt.c, bt.n, p);
 }
 
 template <bool A_MN, bool B_MN, int EPI>
@@ -706,7 +737,71 @@ int gemm_bf16(const void* A, const void* B, void* C, int M, int N, int K, int ld
   return dispatch_major<128>(a_mn, b_mn, epi, tmA, tmB, p, stream);
 }
 
+// dW_z[M][N] += alpha * A_z^T B_z for z < nbatch: A_z row-major [K][lda >= M], B_z row-major [K][ldb >= N] (both
+// MN-major operands), C_z fp32 [M][ldc] accumulated with red.global.add -- the weight-gradient form, for many small
+// same-shape problems (one per decoder layer) in ONE launch of the CTA-pair kernel.
+int gemm_bf16_wgrad_batched(const void* const* A, const void* const* B, float* const* C, int nbatch, int M, int N, int K,
+                            int lda, int ldb, int ldc, float alpha, cudaStream_t stream) {
+  int rc = check_arch();
+  if (rc) return rc;
+  LAKO_REQUIRE(nbatch > 0 && M > 0 && N > 0 && K > 0, LAKO_ERR_BAD_ARG);
+  LAKO_REQUIRE(lda % 8 == 0 && ldb % 8 == 0 && ldc % 4 == 0, LAKO_ERR_BAD_ARG);
+  GemmParams p;
+  p.C = nullptr;
+  p.aux = nullptr;
+  p.M = M;
+  p.N = N;
+  p.K = K;
+  p.ldc = ldc;
+  p.ld_aux = 0;
+  p.alpha = alpha;
+  p.drop = DropSpec{};
+  p.tiles_m = (M + 255) / 256;
+  p.tiles_n = (N + 255) / 256;
+  p.kb_total = (K + BK - 1) / BK;
+  p.splitk = 1;
+  p.kb_per_split = p.kb_total;
+  auto kern = gemm2_batched_kernel<true, true, EPI_F32_ATOMIC>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Gemm2Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) {
+      set_last_error(cudaGetErrorString(e), __FILE__, __LINE__);
+      return LAKO_ERR_LAUNCH;
+    }
+    configured = true;
+  }
+  for (int z0 = 0; z0 < nbatch; z0 += GEMM_MAX_BATCH) {
+    Gemm2Batch bt;
+    bt.n = min(GEMM_MAX_BATCH, nbatch - z0);
+    for (int z = 0; z < bt.n; ++z) {
+      LAKO_REQUIRE((reinterpret_cast<uintptr_t>(C[z0 + z]) & 15) == 0, LAKO_ERR_BAD_ARG);
+      rc = get_tensor_map_2d(&bt.a[z], A[z0 + z], M, K, lda, 64, BK);
+      if (rc) return rc;
+      rc = get_tensor_map_2d(&bt.b[z], B[z0 + z], N, K, ldb, 64, BK);
+      if (rc) return rc;
+      bt.c[z] = C[z0 + z];
+    }
+    for (int z = bt.n; z < GEMM_MAX_BATCH; ++z) {  // keep the unused slots valid descriptors
+      bt.a[z] = bt.a[0];
+      bt.b[z] = bt.b[0];
+      bt.c[z] = bt.c[0];
+    }
+    ProfScope prof(PROF_GEMM_SMALL, 2.0 * M * N * static_cast<double>(K) * bt.n, stream);
+    const int total = p.tiles_m * p.tiles_n * bt.n;
+    const int clusters = min(total, device_sm_count() / 2);
+    launch_pdl(kern, dim3(clusters * 2), dim3(Gemm2Cfg::THREADS), Gemm2Cfg::SMEM_BYTES, stream, bt, p);
+    LAKO_CHECK_LAUNCH();
+  }
+  return LAKO_OK;
+}
+
 }  // namespace lako
+
+extern "C" int lako_gemm_bf16_wgrad_batched(const void* const* A, const void* const* B, float* const* C, int nbatch, int M,
+                                            int N, int K, int lda, int ldb, int ldc, float alpha, void* stream) {
+  return lako::gemm_bf16_wgrad_batched(A, B, C, nbatch, M, N, K, lda, ldb, ldc, alpha, static_cast<cudaStream_t>(stream));
+}
 
 extern "C" int lako_gemm_bf16(const void* A, const void* B, void* C, int M, int N, int K, int lda, int ldb, int ldc,
                               int a_mn, int b_mn, int epi, float alpha, const void* aux, int ld_aux, int splitk,

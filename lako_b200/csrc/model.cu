@@ -304,32 +304,6 @@ struct Dropper {
   DropSpec none() const { return DropSpec{}; }
 };
 
-// Optional side stream for the decoder's weight-gradient GEMMs: they are off the dgrad critical path, and the decoder
-// chain (80-row GEMMs) leaves most SMs idle, so they can run concurrently with it.  Forked / joined with events on the caller's
-// stream, so the call still behaves as if everything ran in order on that stream.
-struct SideCtx {
-  cudaStream_t side = nullptr;
-  cudaEvent_t fork = nullptr, join = nullptr;
-  bool ok = false, tried = false;
-};
-inline SideCtx& side_ctx() {
-  static SideCtx c;
-  if (!c.ok && !c.tried) {
-    c.tried = true;
-    // Off by default: measured on B200 it is worth < 1 % at t5-base and costs up to 10 % of the end-to-end number
-    // at t5-large when the host synchronises every step (the side kernels then trail into the encoder backward
-    // and take SMs from its GEMMs).  LAKO_SIDE_STREAM=1 enables it.
-    const char* e = getenv("LAKO_SIDE_STREAM");
-    if ((e && e[0] == '1') && cudaStreamCreateWithFlags(&c.side, cudaStreamNonBlocking) == cudaSuccess &&
-        cudaEventCreateWithFlags(&c.fork, cudaEventDisableTiming) == cudaSuccess &&
-        cudaEventCreateWithFlags(&c.join, cudaEventDisableTiming) == cudaSuccess)
-      c.ok = true;
-    else
-      c.side = nullptr;
-  }
-  return c;
-}
-
 inline int set_packing(Work& w, const lako_batch* bt, cudaStream_t s) {
   w.cu = nullptr;
   w.Mrows = w.Mtok;
@@ -520,24 +494,15 @@ extern "C" int lako_fidt5_backward(const lako_fidt5* m, const lako_batch* bt, co
   cudaMemsetAsync(w.dsk_f32, 0, sizeof(float) * BT * d, s);
   cudaMemsetAsync(w.dq_f32, 0, sizeof(float) * BT * inner, s);
 
-  SideCtx& sc = side_ctx();
-  cudaStream_t ws = sc.side ? sc.side : s;  // stream of the decoder wgrads
-  auto fork = [&]() {                       // make everything enqueued on s so far visible to the side stream
-    if (sc.side) {
-      cudaEventRecord(sc.fork, s);
-      cudaStreamWaitEvent(sc.side, sc.fork, 0);
-    }
-  };
   // ---- LM head
   if (loss_grad) RC(scale_bf16_dev(w.dlogits, static_cast<size_t>(BT) * vpad, loss_grad, s));
   RC(lin_dgrad_splitk(w.dlogits, static_cast<int>(vpad), p.wb + p.lo.shared, w.dhn, w.dsk_f32, BT, p.V, d, alpha, s));
-  fork();
   RC(gemm_bf16(w.dlogits, w.hn, g + p.lo.shared, p.V, d, BT, static_cast<int>(vpad), d, d, 1, 1, EPI_F32_ATOMIC, alpha,
-               nullptr, 0, 1, 0, ws));
+               nullptr, 0, 1, 0, s));
   RC(rmsnorm_bwd(w.dhn, w.Y[3 * nl], w.rstd_dec_final, p.wf + p.lo.dec_final_ln, w.dres_dec, w.dg[nl - 1].g0,
                  g + p.lo.dec_final_ln, BT, d, 0, dsc, s, dr(0, D_FINAL), dr(nl - 1, D_FF)));
-  // ---- decoder layers: the dgrad chain on s; each layer's six wgrads on the side stream once the layer's
-  //      gradient operands (kept per layer) are complete
+  // ---- decoder layers: the dgrad chain only; the gradient operands are kept per layer and all layers' weight
+  //      gradients are formed afterwards, one batched launch per weight kind
   for (int l = nl - 1; l >= 0; --l) {
     DecLayerAct& a = w.dec[l];
     DecGrad& dg = w.dg[l];
@@ -561,14 +526,27 @@ extern "C" int lako_fidt5_backward(const lako_fidt5* m, const lako_batch* bt, co
     RC(rmsnorm_bwd(w.dn_dec, w.Y[3 * l], a.rstd_s, p.wf + p.lo.dec_ln0[l], w.dres_dec,
                    l > 0 ? w.dg[l - 1].g0 : w.dres_dec_b, g + p.lo.dec_ln0[l], BT, d, 1, 1.f, s, dr.none(),
                    l > 0 ? dr(l - 1, D_FF) : dr.none()));
-    // weight gradients of this layer
-    fork();
-    RC(lin_wgrad(dg.g0, a.h, g + p.lo.dec_wo[l], BT, d, ff, 1.f, ws));
-    RC(lin_wgrad(dg.dh, a.n_f, g + p.lo.dec_wi[l], BT, ff, d, 1.f, ws));
-    RC(lin_wgrad(dg.g1, a.xo, g + p.lo.dec_xo[l], BT, d, inner, 1.f, ws));
-    RC(lin_wgrad(dg.dq, a.n_c, g + p.lo.dec_xq[l], BT, inner, d, 1.f, ws));
-    RC(lin_wgrad(dg.g2, a.ao, g + p.lo.dec_o[l], BT, d, inner, 1.f, ws));
-    RC(lin_wgrad(dg.dqkv, a.n_s, g + p.lo.dec_qkv[l], BT, 3 * inner, d, 1.f, ws));
+  }
+  {
+    // dW[N][K] += dy[BT][N]^T x[BT][K] for every layer at once (each problem alone is a few microseconds of work
+    // behind a fixed launch + pipeline-fill cost)
+    const void* dy[LAKO_MAX_LAYERS];
+    const void* xin[LAKO_MAX_LAYERS];
+    float* dW[LAKO_MAX_LAYERS];
+    auto batched = [&](auto get_dy, auto get_x, const size_t* off, int N, int K) -> int {
+      for (int l = 0; l < nl; ++l) {
+        dy[l] = get_dy(l);
+        xin[l] = get_x(l);
+        dW[l] = g + off[l];
+      }
+      return gemm_bf16_wgrad_batched(dy, xin, dW, nl, N, K, BT, N, K, K, 1.f, s);
+    };
+    RC(batched([&](int l) { return w.dg[l].g0; }, [&](int l) { return w.dec[l].h; }, p.lo.dec_wo, d, ff));
+    RC(batched([&](int l) { return w.dg[l].dh; }, [&](int l) { return w.dec[l].n_f; }, p.lo.dec_wi, ff, d));
+    RC(batched([&](int l) { return w.dg[l].g1; }, [&](int l) { return w.dec[l].xo; }, p.lo.dec_xo, d, inner));
+    RC(batched([&](int l) { return w.dg[l].dq; }, [&](int l) { return w.dec[l].n_c; }, p.lo.dec_xq, inner, d));
+    RC(batched([&](int l) { return w.dg[l].g2; }, [&](int l) { return w.dec[l].ao; }, p.lo.dec_o, d, inner));
+    RC(batched([&](int l) { return w.dg[l].dqkv; }, [&](int l) { return w.dec[l].n_s; }, p.lo.dec_qkv, 3 * inner, d));
   }
   RC(embed_scatter_add(w.dec_ids, w.dres_dec, g + p.lo.shared, BT, d, p.V, s, dr(0, D_EMB)));
   RC(fold_dlut(w.dlut_dec, m->dec_buckets, g + p.lo.dec_relbias, H, w.T, m->bucket_center, m->dims.n_buckets, s));
@@ -576,13 +554,7 @@ extern "C" int lako_fidt5_backward(const lako_fidt5* m, const lako_batch* bt, co
   const int nkv = nl * 2 * inner;
   RC(lin_dgrad(w.dkv_all, p.wb + p.lo.dec_xkv, w.dmem, Mt, nkv, d, nullptr, 1.f, s));
   RC(lin_wgrad(w.dkv_all, w.mem, g + p.lo.dec_xkv, Mt, nkv, d, 1.f, s));
-  if (stage_ev) {
-    if (sc.side) {  // the decoder wgrads may be on the side stream
-      cudaEventRecord(sc.join, sc.side);
-      cudaStreamWaitEvent(s, sc.join, 0);
-    }
-    cudaEventRecord(stage_ev[0], s);
-  }
+  if (stage_ev) cudaEventRecord(stage_ev[0], s);
   RC(rmsnorm_bwd(w.dmem, w.X[2 * nl], w.rstd_enc_final, p.wf + p.lo.enc_final_ln, w.dres_enc, w.dres_enc_b,
                  g + p.lo.enc_final_ln, Mt, d, 0, dsc, s, dr(0, E_FINAL), dr(nl - 1, E_FF)));
   // ---- encoder layers
@@ -610,10 +582,6 @@ extern "C" int lako_fidt5_backward(const lako_fidt5* m, const lako_batch* bt, co
   RC(embed_scatter_add(reinterpret_cast<const long long*>(bt->ids), w.dres_enc, g + p.lo.shared, Mt, d, p.V, s,
                        dr(0, E_EMB), w.cu ? w.tok_index : nullptr));
   RC(fold_dlut(w.dlut_enc, m->enc_buckets, g + p.lo.enc_relbias, H, w.L, m->bucket_center, m->dims.n_buckets, s));
-  if (sc.side) {  // join: nothing after this call may start before the side-stream wgrads are done
-    cudaEventRecord(sc.join, sc.side);
-    cudaStreamWaitEvent(s, sc.join, 0);
-  }
   if (stage_ev) cudaEventRecord(stage_ev[5], s);
   return LAKO_OK;
 }

@@ -8,6 +8,8 @@ namespace lako {
 int gemm_bf16(const void* A, const void* B, void* C, int M, int N, int K, int lda, int ldb, int ldc, int a_mn,
               int b_mn, int epi, float alpha, const void* aux, int ld_aux, int splitk, int bn, cudaStream_t stream,
               DropSpec drop = DropSpec{});
+int gemm_bf16_wgrad_batched(const void* const* A, const void* const* B, float* const* C, int nbatch, int M, int N, int K,
+                            int lda, int ldb, int ldc, float alpha, cudaStream_t stream);
 enum : int { EPI_BF16 = 0, EPI_BF16_RELU = 1, EPI_F32 = 2, EPI_F32_ATOMIC = 3, EPI_BF16_MASK = 4, EPI_BF16_BITMASK = 5 };
 
 // elementwise.cu

@@ -114,3 +114,23 @@ def test_gemm_relu_bitmask_roundtrip(bn):
     unpacked = torch.stack([(bits >> i) & 1 for i in range(8)], dim=-1).view(M, N).bool()
     ref2 = torch.where(unpacked, 0.5 * (dY.float() @ W.float()), torch.zeros(M, N, device="cuda"))
     assert (dX.float() - ref2).abs().max().item() < 0.1
+
+
+@pytest.mark.parametrize("nb,M,N,K", [(3, 768, 3072, 80), (12, 2304, 768, 80), (26, 264, 520, 72)])
+def test_gemm_wgrad_batched(nb, M, N, K):
+    """nb same-shape dW_z += A_z^T B_z problems in one launch of the CTA-pair kernel (decoder weight gradients);
+    26 problems exercise the chunking over the 24 descriptors one launch carries."""
+    import ctypes
+    from lako_b200 import _native as nat
+    lib = nat.lib()
+    As = [_mk((K, M), 10 + z) for z in range(nb)]   # row-major [K][M]: dy of layer z
+    Bs = [_mk((K, N), 50 + z) for z in range(nb)]   # row-major [K][N]: layer input
+    Cs = [torch.full((M, N), float(z), device="cuda") for z in range(nb)]
+    arr = lambda ts: (ctypes.c_void_p * nb)(*[t.data_ptr() for t in ts])
+    nat.check(lib.lako_gemm_bf16_wgrad_batched(arr(As), arr(Bs), arr(Cs), nb, M, N, K, M, N, N, ctypes.c_float(0.5),
+                                               nat.stream_ptr()), "wgrad_batched")
+    torch.cuda.synchronize()
+    for z in range(nb):
+        ref = 0.5 * (As[z].float().T @ Bs[z].float()) + float(z)
+        err = (Cs[z] - ref).abs().max().item()
+        assert err < 2e-2 * (K ** 0.5) * 0.25 + 1e-3, f"problem {z}: max err {err}"
