@@ -258,20 +258,25 @@ __global__ void __launch_bounds__(128) xattn_fwd_mma_kernel(const XMParams p) {
 }
 
 // ------------------------------------------------------------------------------------------------ backward
-__global__ void __launch_bounds__(128) xattn_bwd_mma_kernel(const XMParams p) {
+// TPC = decoder length padded to 16 (compile time: the query-side register tiles scale with it; the training
+// shapes use 16, which keeps the kernel near 100 registers and five CTAs per SM).
+template <int TPC>
+__global__ void __launch_bounds__(128, TPC == 16 ? 5 : 3) xattn_bwd_mma_kernel(const XMParams p) {
+  constexpr int NTT = TPC / 8;   // n-tiles over queries (<= 8)
+  constexpr int KST = TPC / 16;  // k-steps over queries (<= 4)
   pdl_launch_dependents();
   pdl_wait();
   extern __shared__ __align__(1024) uint8_t xs[];
   uint8_t* sK = xs;
   uint8_t* sV = xs + 16384;
   uint8_t* sQ = xs + 32768;
-  uint8_t* sDO = sQ + p.TP * 128;
-  float* sMask = reinterpret_cast<float*>(sDO + p.TP * 128);  // [128]
+  uint8_t* sDO = sQ + TPC * 128;
+  float* sMask = reinterpret_cast<float*>(sDO + TPC * 128);  // [128]
   float* sLse = sMask + 128;                                  // [64]
   float* sD = sLse + 64;                                      // [64]
-  float* sO = (p.TP == 16) ? reinterpret_cast<float*>(sV) : sD + 64;  // [4][16][68] dq partials (alias: V is dead then)
-  uint8_t* sDS = reinterpret_cast<uint8_t*>(sD + 64 + ((p.TP == 16) ? 0 : 4 * 16 * 68));  // [128 keys][TP*2+16 B]
-  const int dsp = p.TP * 2 + 16;
+  float* sO = (TPC == 16) ? reinterpret_cast<float*>(sV) : sD + 64;  // [4][16][68] dq partials (alias: V is dead then)
+  uint8_t* sDS = reinterpret_cast<uint8_t*>(sD + 64 + ((TPC == 16) ? 0 : 4 * 16 * 68));  // [128 keys][TP*2+16 B]
+  const int dsp = TPC * 2 + 16;
   const int split = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t4 = lane & 3;
   const int k0 = split * XM_CH;
@@ -283,15 +288,31 @@ __global__ void __launch_bounds__(128) xattn_bwd_mma_kernel(const XMParams p) {
   if (k0 >= Mb) return;
   const int nk = min(XM_CH, Mb - k0);
   const size_t kvrow0 = static_cast<size_t>(kstart) + k0;
-  stage_sw(sK, p.kv + kvrow0 * p.ldkv + p.koff + h * 64, p.ldkv, 128, nk, tid, 128);
-  stage_sw(sV, p.kv + kvrow0 * p.ldkv + p.voff + h * 64, p.ldkv, 128, nk, tid, 128);
-  stage_sw(sQ, p.q + static_cast<size_t>(b) * p.T * p.ldq + h * 64, p.ldq, p.TP, p.T, tid, 128);
-  stage_sw(sDO, p.dout + static_cast<size_t>(b) * p.T * p.ldo + h * 64, p.ldo, p.TP, p.T, tid, 128);
+  {
+    // K and V chunk tiles: thread (r0 = tid / 8, c = tid % 8) copies 16 B column c of rows r0, r0 + 16, ...; the
+    // swizzle term (r & 7) does not change along that walk, so the loop is two adds per copy
+    const int r0 = tid >> 3, c = tid & 7;
+    const __nv_bfloat16* gk = p.kv + (kvrow0 + r0) * p.ldkv + p.koff + h * 64 + c * 8;
+    const ptrdiff_t vdelta = static_cast<ptrdiff_t>(p.voff) - p.koff;
+    const size_t gstep = static_cast<size_t>(16) * p.ldkv;
+    const uint32_t so = swz(r0, c);
+    const uint32_t bK = smem_u32(sK) + so, bV = smem_u32(sV) + so;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const bool ok = r0 + j * 16 < nk;
+      const __nv_bfloat16* src = ok ? gk + j * gstep : p.kv;
+      cp_async16(bK + j * 2048, src, ok);
+      cp_async16(bV + j * 2048, ok ? src + vdelta : p.kv, ok);
+    }
+  }
+  stage_sw(sQ, p.q + static_cast<size_t>(b) * p.T * p.ldq + h * 64, p.ldq, TPC, p.T, tid, 128);
+  stage_sw(sDO, p.dout + static_cast<size_t>(b) * p.T * p.ldo + h * 64, p.ldo, TPC, p.T, tid, 128);
   {
     const bool valid = (p.mask == nullptr) || p.mask[static_cast<size_t>(b) * p.M + k0 + tid];
     sMask[tid] = (tid < nk) ? (valid ? 0.f : XM_MASK_MIN) : -INFINITY;
   }
-  for (int t = warp; t < 64; t += 4) {  // D[t] = sum_d dO*O ; lse = +inf beyond T -> P = 0
+#pragma unroll
+  for (int t = warp; t < TPC; t += 4) {  // D[t] = sum_d dO*O ; lse = +inf beyond T -> P = 0
     float acc = 0.f;
     if (t < p.T) {
       const size_t row = static_cast<size_t>(b) * p.T + t;
@@ -310,8 +331,6 @@ __global__ void __launch_bounds__(128) xattn_bwd_mma_kernel(const XMParams p) {
   __syncthreads();
   const uint32_t aK = smem_u32(sK), aV = smem_u32(sV), aQ = smem_u32(sQ), aDO = smem_u32(sDO), aDS = smem_u32(sDS);
   const int kb = warp * 32;
-  const int NTT = p.TP / 8;   // n-tiles over queries (<= 8)
-  const int KST = p.TP / 16;  // k-steps over queries (<= 4)
 
 #pragma unroll 1
   for (int km = 0; km < 2; ++km) {  // 16-key tiles of this warp
@@ -515,10 +534,20 @@ int xattn_bwd_mma(const __nv_bfloat16* q, const __nv_bfloat16* kv, const unsigne
   p.npsg = npsg;
   static bool configured = false;
   if (!configured) {
-    cudaFuncSetAttribute(xattn_bwd_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xm_smem_bytes(64, true));
+    cudaFuncSetAttribute(xattn_bwd_mma_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xm_smem_bytes(16, true));
+    cudaFuncSetAttribute(xattn_bwd_mma_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xm_smem_bytes(32, true));
+    cudaFuncSetAttribute(xattn_bwd_mma_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xm_smem_bytes(64, true));
     configured = true;
   }
-  launch_pdl(xattn_bwd_mma_kernel, dim3(dim3(p.splits, H, B)), dim3(128), xm_smem_bytes(p.TP, true), s, p);
+  const dim3 grid(p.splits, H, B);
+  if (p.TP == 16) {
+    launch_pdl(xattn_bwd_mma_kernel<16>, grid, dim3(128), xm_smem_bytes(16, true), s, p);
+  } else if (p.TP == 32) {
+    launch_pdl(xattn_bwd_mma_kernel<32>, grid, dim3(128), xm_smem_bytes(32, true), s, p);
+  } else {
+    p.TP = 64;
+    launch_pdl(xattn_bwd_mma_kernel<64>, grid, dim3(128), xm_smem_bytes(64, true), s, p);
+  }
   LAKO_CHECK_LAUNCH();
   return LAKO_OK;
 }
