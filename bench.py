@@ -68,6 +68,7 @@ class ClockSampler(threading.Thread):
         self.index = index
         self.samples = []
         self.stop_flag = False
+        self.window = None  # (t0, t1) host times of the timed region; samples outside it are dropped
 
     def run(self):
         try:
@@ -76,7 +77,7 @@ class ClockSampler(threading.Thread):
             self._run_smi()
 
     def _run_nvml(self):
-        """NVML polled every 10 ms (a 100 ms timed region still gets ~10 samples); same fields as the nvidia-smi query."""
+        """NVML polled every ~5 ms; same fields as the nvidia-smi query."""
         import pynvml
         pynvml.nvmlInit()
         h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
@@ -92,8 +93,8 @@ class ClockSampler(threading.Thread):
             for bit, col in bits:
                 if r & bit:
                     row[col] = "Active"
-            self.samples.append(row)
-            time.sleep(0.01)
+            self.samples.append((time.perf_counter(), row))
+            time.sleep(0.004)
 
     def _run_smi(self):
         while not self.stop_flag:
@@ -101,14 +102,15 @@ class ClockSampler(threading.Thread):
                 out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                       "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
                 if out:
-                    self.samples.append([x.strip() for x in out.split(",")])
+                    self.samples.append((time.perf_counter(), [x.strip() for x in out.split(",")]))
             except Exception:
                 pass
             time.sleep(0.2)
 
     def summary(self):
         sm, pw, mx, reasons = [], [], 0, set()
-        for s in self.samples:
+        rows = [r for t, r in self.samples if self.window is None or self.window[0] <= t <= self.window[1]]
+        for s in rows:
             try:
                 sm.append(float(s[0]))
                 mx = max(mx, float(s[1]))
@@ -247,32 +249,37 @@ def main():
     lib = nat.lib()
     lib.lako_launch_count.restype = ctypes.c_ulonglong
 
+    # the sampler thread starts before the warm-up (NVML initialisation takes a while); only its samples taken
+    # inside the timed region are reported
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
     # ---- warm-up
     for i in range(warmup):
         train_step(model, opt, *resident[i % n_batches])
     barrier()
 
     # ---- timed region: K steps, inputs resident in HBM
-    sampler = ClockSampler(local_rank) if rank == 0 else None
-    if sampler:
-        sampler.start()
     launches0 = lib.lako_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     prof_range = bool(os.environ.get("LAKO_PROFILER_RANGE"))  # ncu --profile-from-start off: capture the timed steps only
     if prof_range:
         torch.cuda.profiler.start()
+    t_win0 = time.perf_counter()
     e0.record()
     for i in range(steps):
         loss = train_step(model, opt, *resident[i % n_batches])
     e1.record()
     barrier()
+    t_win1 = time.perf_counter()
     if prof_range:
         torch.cuda.profiler.stop()
     launches = lib.lako_launch_count() - launches0
     ms = e0.elapsed_time(e1)
     if sampler:
         sampler.stop_flag = True
+        sampler.window = (t_win0, t_win1)
     t = torch.tensor([ms], device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

@@ -195,6 +195,7 @@ class FiDT5(nn.Module):
         # data-parallel overlap: CUDA events recorded by backward as gradient ranges become final (optim.py)
         self._stage_events = None
         self._stage_ranges = None
+        self._master_sync = None   # set by a sharded FusedAdamW: all-gathers the fp32 masters before they are read
         self._init_weights(emb_std, seed)
 
     # ------------------------------------------------------------------ parameters
@@ -315,6 +316,8 @@ class FiDT5(nn.Module):
 
     # ------------------------------------------------------------------ state dict plumbing
     def state_dict(self, *args, **kwargs):
+        if self._master_sync is not None:   # sharded data-parallel optimizer: a collective, call it on every rank
+            self._master_sync()
         sd = super().state_dict(*args, **kwargs)
         return sd
 

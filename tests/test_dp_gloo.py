@@ -54,3 +54,59 @@ def test_dp2_equals_single_process(tmp_path):
     loss.backward()
     ref = torch.cat([p.grad.reshape(-1) for p in params.values()])
     assert torch.allclose(got, ref, atol=1e-6, rtol=1e-4)
+
+
+def _sharded_worker(rank, world, port, out):
+    """Host logic of the sharded optimizer step (reduce-scatter -> per-piece clip/update -> all-gather of the bf16
+    weights -> on-demand all-gather of the fp32 masters) with torch stand-ins for the two CUDA kernels."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from lako_b200.optim import FusedAdamW, shard_plan
+    n = 4 * 16 * world
+    ranges = [(2 * 16 * world, n), (0, 16 * world), (16 * world, 16 * world), (16 * world, 2 * 16 * world)]  # one empty
+    g0 = torch.Generator().manual_seed(5)
+    w = torch.randn(n, generator=g0)
+    grads = [torch.randn(n, generator=g0) for _ in range(world)]
+    shim = type("M", (), {})()
+    shim._flat, shim._flat_grad, shim._bf16 = w.clone(), grads[rank].clone(), w.to(torch.bfloat16)
+    shim._stage_events, shim._stage_ranges = None, ranges
+    shim.mark_bf16_fresh = lambda: None
+    opt = FusedAdamW.__new__(FusedAdamW)
+    opt.model, opt.group, opt._comm_stream, opt.clip = shim, None, None, 1.0
+    opt.sumsq = torch.zeros(1)
+    opt._plan = shard_plan(ranges, world, rank)
+    assert opt._plan is not None and len(opt._plan) == 3
+    assert shard_plan([(0, 8 * world + 8)], world, rank) is None or world == 1
+
+    def sumsq_piece(off, cnt):
+        opt.sumsq += (shim._flat_grad[off:off + cnt] ** 2).sum()
+
+    def update_piece(off, cnt, lr):  # clipped SGD stands in for the AdamW kernel
+        coef = min(1.0, 1.0 / (float(opt.sumsq.sqrt()) + 1e-6))
+        shim._flat[off:off + cnt] -= lr * coef * shim._flat_grad[off:off + cnt]
+        shim._bf16[off:off + cnt] = shim._flat[off:off + cnt].to(torch.bfloat16)
+
+    opt._sumsq_piece, opt._update_piece = sumsq_piece, update_piece
+    opt._step_sharded(0.1)
+    bf16_after = shim._bf16.clone()
+    stale = shim._flat.clone()
+    opt._masters_stale = True
+    opt.sync_master_weights()
+    if rank == 0:
+        torch.save({"bf16": bf16_after, "w": shim._flat, "stale": stale, "norm2": opt.sumsq.clone(), "w0": w,
+                    "gsum": sum(grads)}, out)
+    dist.destroy_process_group()
+
+
+def test_dp2_sharded_step_host_logic(tmp_path):
+    out = str(tmp_path / "s.pt")
+    mp.spawn(_sharded_worker, args=(2, 29733, out), nprocs=2, join=True)
+    r = torch.load(out)
+    gsum, w0 = r["gsum"], r["w0"]
+    assert torch.allclose(r["norm2"], (gsum ** 2).sum().reshape(1), rtol=1e-5)
+    coef = min(1.0, 1.0 / (float((gsum ** 2).sum().sqrt()) + 1e-6))
+    ref = w0 - 0.1 * coef * gsum
+    assert torch.allclose(r["w"], ref, atol=1e-6)                       # masters complete after the sync
+    assert torch.equal(r["bf16"], ref.to(torch.bfloat16))               # compute weights identical on every rank
+    assert not torch.allclose(r["stale"], ref, atol=1e-6)               # ... while foreign master slices were stale
