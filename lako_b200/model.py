@@ -429,12 +429,28 @@ class FiDT5(nn.Module):
             self._ws[key[0]] = ws
         return ws[1]
 
-    def _packing(self, mask):
+    def _packing(self, mask, lengths=None):
         """(cu_seqlens int32 device tensor [B*N+1], total valid tokens) if every passage mask is a prefix mask,
-        else (None, 0).  Costs one small D2H copy (B*N+1 ints) per call."""
+        else (None, 0).  Costs one small D2H copy (B*N+1 ints) per call -- unless the caller passes `lengths`, the
+        HOST tensor / list [B][N] of valid-prefix lengths (a by-product of src/data.py's Collator, which builds the
+        masks on the host): then nothing is read back and the host keeps running ahead of the device; the claim
+        "mask[b,n,:] == arange(L) < lengths[b,n]" is checked on the device (asynchronous device-side assert)."""
         if not self.unpad:
             return None, 0
         B, N, L = mask.shape
+        if lengths is not None:
+            lens_h = torch.as_tensor(lengths, dtype=torch.int32).reshape(-1).cpu()
+            if lens_h.numel() != B * N:
+                raise nat.LakoError(f"passage_lengths must have {B * N} entries, got {lens_h.numel()}")
+            cu = torch.zeros(B * N + 1, dtype=torch.int32)
+            cu[1:] = torch.cumsum(lens_h, 0)
+            total = int(cu[-1])
+            if total == 0 or int(lens_h.min()) < 0 or int(lens_h.max()) > L:
+                raise nat.LakoError("passage_lengths out of range")
+            cu_d = cu.to(mask.device, non_blocking=True)
+            lens_d = (cu_d[1:] - cu_d[:-1]).reshape(B, N, 1)
+            torch._assert_async((mask == (torch.arange(L, device=mask.device)[None, None, :] < lens_d)).all())
+            return cu_d, total
         lens = mask.sum(-1, dtype=torch.int32)
         prefix = (mask == (torch.arange(L, device=mask.device)[None, None, :] < lens[..., None])).all()
         info = torch.cat([lens.reshape(-1), prefix.reshape(1).to(torch.int32)]).cpu()
@@ -454,7 +470,8 @@ class FiDT5(nn.Module):
         self._drop_step = 0
 
     # ------------------------------------------------------------------ forward / backward
-    def forward(self, input_ids=None, attention_mask=None, labels=None, global_target_count=None, **kwargs):
+    def forward(self, input_ids=None, attention_mask=None, labels=None, global_target_count=None, passage_lengths=None,
+                **kwargs):
         self._require_cuda()
         if labels is None:
             raise nat.LakoError("FiDT5.forward needs labels (the reader is only called as model(..., labels=...)[0], "
@@ -490,7 +507,7 @@ class FiDT5(nn.Module):
                 self._drop_seed = torch.initial_seed() & 0xFFFFFFFFFFFFFFFF
             self._drop_step += 1
         drop = (drop_p, self._drop_step & 0xFFFFFFFF, self._drop_seed or 0)
-        cu, packed = self._packing(mask)
+        cu, packed = self._packing(mask, passage_lengths)
         pack = (cu.data_ptr() if cu is not None else 0, packed)
         m = self._model_struct(with_grad=train)
         bt = _Batch(ids.data_ptr(), mask.data_ptr(), labels.data_ptr(), B, N, L, T, ws.data_ptr(), ws.numel(),

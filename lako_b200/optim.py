@@ -237,12 +237,14 @@ def global_target_count(labels, group=None):
     return cnt
 
 
-def train_step(model, optimizer, input_ids, attention_mask, labels, group=None):
+def train_step(model, optimizer, input_ids, attention_mask, labels, group=None, passage_lengths=None):
     """train_reader.py:67-79 for one batch: forward, backward, (all-reduce), clip, AdamW, zero_grad.
-    Returns the (global-mean) loss as a device scalar; no host synchronisation."""
+    Returns the (global-mean) loss as a device scalar.  With `passage_lengths` (host [B][N] valid-prefix lengths, see
+    FiDT5._packing) the step contains no host synchronisation at all."""
     distributed = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
     cnt = global_target_count(labels, group) if distributed else None
-    loss = model(input_ids=input_ids, attention_mask=attention_mask, labels=labels, global_target_count=cnt)[0]
+    loss = model(input_ids=input_ids, attention_mask=attention_mask, labels=labels, global_target_count=cnt,
+                 passage_lengths=passage_lengths)[0]
     loss.backward()
     optimizer.step()
     model.zero_grad()

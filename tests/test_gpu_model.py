@@ -145,6 +145,26 @@ def test_padded_and_packed_paths_agree(path):
     assert (a[4] - b[4]).abs().max().item() < 2e-2 * b[4].abs().max().item()
 
 
+def test_host_passage_lengths_skip_the_readback():
+    """Passing the Collator's host-side prefix lengths gives the same step as letting forward() read them back."""
+    c, cfg, sd, model = _load(GOLDEN[0])
+    mask = c["mask"]
+    if not bool((mask == (torch.arange(mask.size(-1)) < mask.sum(-1, keepdim=True))).all()):
+        pytest.skip("golden case is not a prefix mask")
+    args = dict(input_ids=c["ids"].cuda(), attention_mask=mask.cuda(), labels=c["labels"].cuda())
+    res = []
+    for lengths in (None, mask.sum(-1, dtype=torch.int32)):
+        model.train()
+        model.zero_grad()
+        loss, logits = model(passage_lengths=lengths, **args)
+        loss.backward()
+        torch.cuda.synchronize()
+        res.append((loss.item(), logits.detach().clone(), model._flat_grad.clone()))
+    assert abs(res[0][0] - res[1][0]) < 1e-5
+    assert (res[0][1] - res[1][1]).abs().max().item() < 1e-5
+    assert ((res[0][2] - res[1][2]).norm() / res[0][2].norm()).item() < 1e-4   # fp32 atomics reorder only
+
+
 def test_non_prefix_mask_falls_back_to_padded_layout():
     """A mask with holes cannot be packed; the padded kernels must reproduce the oracle."""
     from oracle import fidt5_oracle as O
