@@ -155,6 +155,8 @@ int rmsnorm_fwd(const float* x, const __nv_bfloat16* delta, float* x_out, const 
 // NV = d / 128 float4 slots per lane.  The per-column weight-gradient partial sums live in a per-warp
 // private slice of shared memory (no atomics, 128-bit conflict-free accesses) instead of registers, which
 // keeps the kernel at ~70 registers so three 8-warp CTAs fit per SM and enough loads are in flight.
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
 template <int NV>
 __global__ void __launch_bounds__(256, 2) rmsnorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy,
                                                               const float* __restrict__ x,
@@ -182,6 +184,18 @@ __global__ void __launch_bounds__(256, 2) rmsnorm_bwd_kernel(const __nv_bfloat16
     const float* xr = x + static_cast<size_t>(row) * d;
     const __nv_bfloat16* dyr = dy + static_cast<size_t>(row) * d;
     float* drr = dres + static_cast<size_t>(row) * d;
+    // L2 prefetch of what this warp touches next: the residual gradient of this row (read only after the
+    // row reduction below) and the operands of its next row -- more bytes in flight per SM than the two
+    // resident CTAs' register loads alone provide
+    {
+      constexpr int L32 = d * 4 / 128;  // 128-byte lines of an fp32 row
+      if (accumulate && lane < L32) prefetch_l2(drr + lane * 32);
+      const int nrow = row + warps_total;
+      if (nrow < rows) {
+        if (lane < L32) prefetch_l2(x + static_cast<size_t>(nrow) * d + lane * 32);
+        if (lane < L32 / 2) prefetch_l2(dy + static_cast<size_t>(nrow) * d + lane * 64);
+      }
+    }
     float4 xv[NV];
     uint2 dyp[NV];
     uint32_t kyd[NV], kbd[NV];
