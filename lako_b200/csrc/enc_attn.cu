@@ -368,8 +368,9 @@ enc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
   uint64_t* bar_load = reinterpret_cast<uint64_t*>(smem + EB_BAR_OFF);
   uint64_t* bar_mma = bar_load + 1;
   uint64_t* bar_grad = bar_load + 2;
-  uint64_t* bar_ready = bar_load + 3;  // all softmax threads: S/dP consumed, P/dS of the block stored
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_load + 4);
+  uint64_t* bar_ready = bar_load + 3;  // all softmax threads: P / dS of the block stored
+  uint64_t* bar_sfree = bar_load + 4;  // all softmax threads: S / dP of the block are in registers (TMEM columns free)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_load + 5);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int quarter = warp & 3, cq = warp >> 2;
@@ -395,6 +396,7 @@ enc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
     mbar_init(bar_mma, 1);
     mbar_init(bar_grad, 1);
     mbar_init(bar_ready, EB_SOFTMAX_THREADS);
+    mbar_init(bar_sfree, EB_SOFTMAX_THREADS);
     fence_barrier_init();
   }
   if (warp == 0) tmem_alloc(tmem_slot, 512);
@@ -494,10 +496,10 @@ enc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
       uint32_t r_phase = 0;
       for (int kt = 0; kt < nt; ++kt) {
         for (int qt = 0; qt < nt; ++qt) {
-          mbar_wait(bar_ready, r_phase);  // S/dP of this block consumed, its P / dS in shared memory
-          r_phase ^= 1;
+          // The softmax threads release the S / dP columns as soon as their values are in registers (about half way
+          // through the block's arithmetic): the next block's S / dP are computed underneath the rest of it.
+          mbar_wait(bar_sfree, r_phase);
           tc_fence_after();
-          // next block's S / dP first (their TMEM columns are free again)
           int nq = qt + 1, nk = kt;
           if (nq == nt) {
             nq = 0;
@@ -507,6 +509,9 @@ enc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
             issue_s_dp(nq, nk);
             umma_commit(bar_mma);
           }
+          mbar_wait(bar_ready, r_phase);  // P / dS of this block are in shared memory
+          r_phase ^= 1;
+          tc_fence_after();
           // dV[kt] += P^T dO[qt] ; dK[kt] += dS^T Q[qt]   (M = 128 keys, N = 64, K = 128 queries)
 #pragma unroll
           for (int j = 0; j < 8; ++j)
@@ -574,11 +579,16 @@ enc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
         if (!live) {
 #pragma unroll
           for (int i = 0; i < 8; ++i) ppk[i] = dpk[i] = 0u;
+          if (hh == 1) mbar_arrive(bar_sfree);
         } else {
           uint32_t sv[16], dpv[16];
           tmem_ld_32x16(t_row + TM_S + cq * 32 + hh * 16, sv);
           tmem_ld_32x16(t_row + TM_DP + cq * 32 + hh * 16, dpv);
           tmem_ld_wait();
+          if (hh == 1) {  // this thread's last read of the block's S / dP
+            tc_fence_before();
+            mbar_arrive(bar_sfree);
+          }
 #pragma unroll
           for (int uu = 0; uu < 2; ++uu) {
             const int u = hh * 2 + uu;
