@@ -171,14 +171,21 @@ enc_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const EncAttnPar
     uint32_t v[32];
     tmem_ld_32x32(t_row + c * 32, v);
     tmem_ld_wait();
+    const bool need_km = (p.mask != nullptr) || (c * 32 + 32 > L);  // warp-uniform
 #pragma unroll
     for (int g = 0; g < 8; ++g) {
       const float4 lb = *reinterpret_cast<const float4*>(lutp + c * 32 + g * 4);
-      const float4 km = *reinterpret_cast<const float4*>(s_kmask + c * 32 + g * 4);
-      const float s0 = (__uint_as_float(v[g * 4 + 0]) + lb.x) + km.x;
-      const float s1 = (__uint_as_float(v[g * 4 + 1]) + lb.y) + km.y;
-      const float s2 = (__uint_as_float(v[g * 4 + 2]) + lb.z) + km.z;
-      const float s3 = (__uint_as_float(v[g * 4 + 3]) + lb.w) + km.w;
+      float s0 = __uint_as_float(v[g * 4 + 0]) + lb.x;
+      float s1 = __uint_as_float(v[g * 4 + 1]) + lb.y;
+      float s2 = __uint_as_float(v[g * 4 + 2]) + lb.z;
+      float s3 = __uint_as_float(v[g * 4 + 3]) + lb.w;
+      if (need_km) {
+        const float4 km = *reinterpret_cast<const float4*>(s_kmask + c * 32 + g * 4);
+        s0 += km.x;
+        s1 += km.y;
+        s2 += km.z;
+        s3 += km.w;
+      }
       m = fmaxf(m, fmaxf(fmaxf(s0, s1), fmaxf(s2, s3)));
       v[g * 4 + 0] = __float_as_uint(s0);
       v[g * 4 + 1] = __float_as_uint(s1);
@@ -192,6 +199,7 @@ enc_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const EncAttnPar
   __syncthreads();
   m = fmaxf(s_red_m[r], s_red_m[128 + r]);
   // ---- pass 2: p = exp(s - m) (un-normalised), row sum, P -> shared (bf16, K-major 128B swizzle)
+  const float nm = -m * LOG2E_F;
   float lsum = 0.f;
   for (int c = c_begin; c < c_lim; ++c) {
     uint32_t v[32];
@@ -204,7 +212,7 @@ enc_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const EncAttnPar
       float e[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        e[i] = fast_exp2((__uint_as_float(v[u * 8 + i]) - m) * LOG2E_F);
+        e[i] = fast_exp2(fmaf(__uint_as_float(v[u * 8 + i]), LOG2E_F, nm));
         lsum += e[i];
       }
       if (p.drop.thresh) {  // the row sum normalises the UNdropped probabilities; only the P V operand is masked
@@ -558,9 +566,10 @@ enc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
       s_phase ^= 1;
       tc_fence_after();
       EB_TRACE(8 + (kt * 2 + qt) * 6 + 0);
-      const float lse_q = s_lse[q];
+      const float nlse_q = -s_lse[q] * LOG2E_F;  // lse = +inf beyond the passage -> exp2(-inf) = 0
       const float D_q = s_D[q];
       const bool live = rows_live && kbase < L;
+      const bool need_km = (p.mask != nullptr) || (kbase + 32 > L);
       // !live: nothing of this 32x32 sub-block lies inside the passage: P = dS = 0 (dV / dK sum over all 128 rows of
       // the tile, so the zeros must really be written), no exp / Philox / diagonal sums.
       // bias-gradient index of the diagonal d = i - lane of this 32x32 sub-block: rel = k - q
@@ -594,11 +603,17 @@ enc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
             const int u = hh * 2 + uu;
             const float4 lb0 = *reinterpret_cast<const float4*>(lutp + kbase + u * 8);
             const float4 lb1 = *reinterpret_cast<const float4*>(lutp + kbase + u * 8 + 4);
-            const float4 km0 = *reinterpret_cast<const float4*>(s_kmask + kbase + u * 8);
-            const float4 km1 = *reinterpret_cast<const float4*>(s_kmask + kbase + u * 8 + 4);
             const float lbv[8] = {lb0.x, lb0.y, lb0.z, lb0.w, lb1.x, lb1.y, lb1.z, lb1.w};
-            const float kmv[8] = {km0.x, km0.y, km0.z, km0.w, km1.x, km1.y, km1.z, km1.w};
-            float pr[8], ds[8];
+            float sc[8], pr[8], ds[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) sc[i] = __uint_as_float(sv[uu * 8 + i]) + lbv[i];
+            if (need_km) {  // warp-uniform: a key mask was given, or the chunk straddles the end of the passage
+              const float4 km0 = *reinterpret_cast<const float4*>(s_kmask + kbase + u * 8);
+              const float4 km1 = *reinterpret_cast<const float4*>(s_kmask + kbase + u * 8 + 4);
+              const float kmv[8] = {km0.x, km0.y, km0.z, km0.w, km1.x, km1.y, km1.z, km1.w};
+#pragma unroll
+              for (int i = 0; i < 8; ++i) sc[i] += kmv[i];
+            }
             uint32_t keepm = 0xffu;
             float dscale = 1.f;
             if (p.drop.thresh) {
@@ -609,11 +624,10 @@ enc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
             }
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-              const float sc = (__uint_as_float(sv[uu * 8 + i]) + lbv[i]) + kmv[i];
-              pr[i] = fast_exp2((sc - lse_q) * LOG2E_F);
-              const float dp = ((keepm >> i) & 1u) ? __uint_as_float(dpv[uu * 8 + i]) * dscale : 0.f;
-              ds[i] = pr[i] * (dp - D_q);
-              pr[i] = ((keepm >> i) & 1u) ? pr[i] * dscale : 0.f;  // the dV = P_drop^T dO operand
+              const float pv = fast_exp2(fmaf(sc[i], LOG2E_F, nlse_q));          // P = exp(s - lse)
+              const float mi = ((keepm >> i) & 1u) ? dscale : 0.f;                 // dropout keep * 1/(1-p)
+              ds[i] = pv * fmaf(__uint_as_float(dpv[uu * 8 + i]), mi, -D_q);      // dS = P (dP_drop - D)
+              pr[i] = pv * mi;                                                     // the dV = P_drop^T dO operand
             }
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
