@@ -14,6 +14,7 @@
 // forward (X W^T), dgrad (dY W) and wgrad (dY^T X) all run without materialising a transpose.
 // Split-K (wgrad: small output, very deep K) reduces with fp32 vector red.global into the
 // caller-zeroed gradient buffer.
+#include <cstdlib>
 #include "ops.cuh"
 
 namespace lako {
@@ -44,9 +45,12 @@ struct GemmParams {
 
 // Epilogue of one 128-row x BN-column accumulator tile for a warp owning TMEM lane quarter q: its 64-column
 // groups [g_begin, g_end) (several warps may share a lane quarter), staged through 4 KB slot `slot` of sStage.
+// tmC != nullptr: the staged 32 x 64 bf16 sub-tile leaves shared memory through one TMA store (which also clips the
+// M / N edges) instead of 8 LDS + 8 STG per lane.
 template <int BN, int EPI>
 __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t t_acc, uint8_t* sStage, int m0, int n0,
-                                              int q, int lane, int g_begin = 0, int g_end = BN / 64, int slot = -1) {
+                                              int q, int lane, int g_begin = 0, int g_end = BN / 64, int slot = -1,
+                                              const CUtensorMap* tmC = nullptr) {
   if constexpr (EPI == EPI_BF16 || EPI == EPI_BF16_RELU || EPI == EPI_BF16_MASK || EPI == EPI_BF16_BITMASK) {
     // bf16 output: TMEM (thread = row) -> registers -> per-warp swizzled smem -> coalesced 16 B stores
     // (each store instruction writes four full 128 B row segments)
@@ -72,6 +76,12 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t t_ac
       uint32_t r0[32], r1[32];
       tmem_ld_32x32(t_acc + g * 64, r0);
       tmem_ld_32x32(t_acc + g * 64 + 32, r1);
+      if constexpr (EPI != EPI_BF16_MASK) {
+        if (tmC) {  // the previous group's TMA store must have finished reading the staging slot
+          if (lane == 0) tma_store_wait_read<0>();
+          __syncwarp();
+        }
+      }
       // 1 bit / element ReLU-activity mask, 8 bytes per thread-row per 64-column group: written by the ReLU
       // epilogue (aux = uint8 [M][ld_aux bytes]) and consumed by the dgrad epilogue instead of re-reading h
       uint2 bits = make_uint2(0u, 0u);
@@ -124,6 +134,17 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t t_ac
         if (p.aux != nullptr && brow < p.M && col0 + 64 <= p.N)
           *reinterpret_cast<uint2*>(reinterpret_cast<unsigned char*>(const_cast<void*>(p.aux)) +
                                     static_cast<size_t>(brow) * p.ld_aux + (col0 >> 3)) = bits;
+      }
+      if constexpr (EPI != EPI_BF16_MASK) {
+        if (tmC) {
+          fence_proxy_async_smem();  // generic-proxy writes of the slot -> visible to the TMA (async proxy)
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(tmC, stg, col0, m0 + q * 32);
+            tma_store_commit();
+          }
+          continue;
+        }
       }
       __syncwarp();
       const int unit = lane & 7;
@@ -373,7 +394,7 @@ struct Gemm2Cfg {
 // with its own tensor maps tmAs[z] / tmBs[z] and output Cs[z] (Cs == nullptr: one problem writing p.C).
 template <bool A_MN, bool B_MN, int EPI>
 __device__ __forceinline__ void gemm2_body(const CUtensorMap* tmAs, const CUtensorMap* tmBs, void* const* Cs, int nbatch,
-                                           const GemmParams& p) {
+                                           const GemmParams& p, const CUtensorMap* tmC = nullptr) {
   using Cfg = Gemm2Cfg;
   constexpr int STAGES = Cfg::STAGES;
   constexpr int BN = Cfg::BN;
@@ -520,7 +541,7 @@ __device__ __forceinline__ void gemm2_body(const CUtensorMap* tmAs, const CUtens
       constexpr int G_PER_WARP = (BN / 64) / (Cfg::EPI_WARPS / 4);
       const int part = (warp - 4) >> 2;
       epilogue_tile<BN, EPI>(pz, tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN, sStage, m0, n0, q, lane,
-                             part * G_PER_WARP, (part + 1) * G_PER_WARP, warp - 4);
+                             part * G_PER_WARP, (part + 1) * G_PER_WARP, warp - 4, tmC);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(mapa_u32(&tempty_bar[acc], 0));
@@ -531,6 +552,7 @@ __device__ __forceinline__ void gemm2_body(const CUtensorMap* tmAs, const CUtens
     }
   }
 
+  if (tmC && warp >= 4 && lane == 0) tma_store_wait_all<0>();  // this warp's TMA stores are complete
   tc_fence_before();
   cluster_sync_all();  // the peer's smem / TMEM / barriers must outlive every remote access
   if (warp == 2) {
@@ -541,8 +563,10 @@ __device__ __forceinline__ void gemm2_body(const CUtensorMap* tmAs, const CUtens
 
 template <bool A_MN, bool B_MN, int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Gemm2Cfg::THREADS, 1)
-gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
-  gemm2_body<A_MN, B_MN, EPI>(&tmA, &tmB, nullptr, 1, p);
+gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                  const __grid_constant__ CUtensorMap tmC, const GemmParams p, const int use_tmc) {
+  constexpr bool kBf16Out = EPI == EPI_BF16 || EPI == EPI_BF16_RELU || EPI == EPI_BF16_BITMASK;
+  gemm2_body<A_MN, B_MN, EPI>(&tmA, &tmB, nullptr, 1, p, (kBf16Out && use_tmc) ? &tmC : nullptr);
 }
 
 // Up to GEMM_MAX_BATCH same-shape problems in one launch (the decoder's per-layer weight gradients: each is a
@@ -561,7 +585,8 @@ gemm2_batched_kernel(const __grid_constant__ Gemm2Batch bt, const GemmParams p) 
 }
 
 template <bool A_MN, bool B_MN, int EPI>
-static int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t stream) {
+static int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, int use_tmc,
+                        const GemmParams& p, cudaStream_t stream) {
   using Cfg = Gemm2Cfg;
   auto kern = gemm2_bf16_kernel<A_MN, B_MN, EPI>;
   static bool configured = false;
@@ -575,31 +600,32 @@ static int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const Ge
   }
   const int total = p.tiles_m * p.tiles_n * p.splitk;
   const int clusters = min(total, device_sm_count() / 2);
-  launch_pdl(kern, dim3(clusters * 2), dim3(Cfg::THREADS), Cfg::SMEM_BYTES, stream, tmA, tmB, p);
+  launch_pdl(kern, dim3(clusters * 2), dim3(Cfg::THREADS), Cfg::SMEM_BYTES, stream, tmA, tmB, tmC, p, use_tmc);
   LAKO_CHECK_LAUNCH();
   return LAKO_OK;
 }
 
 template <bool A_MN, bool B_MN>
-static int dispatch_epi2(int epi, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t s) {
+static int dispatch_epi2(int epi, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, int use_tmc,
+                         const GemmParams& p, cudaStream_t s) {
   switch (epi) {
-    case EPI_BF16: return launch_gemm2<A_MN, B_MN, EPI_BF16>(tmA, tmB, p, s);
-    case EPI_BF16_RELU: return launch_gemm2<A_MN, B_MN, EPI_BF16_RELU>(tmA, tmB, p, s);
-    case EPI_F32: return launch_gemm2<A_MN, B_MN, EPI_F32>(tmA, tmB, p, s);
-    case EPI_F32_ATOMIC: return launch_gemm2<A_MN, B_MN, EPI_F32_ATOMIC>(tmA, tmB, p, s);
-    case EPI_BF16_MASK: return launch_gemm2<A_MN, B_MN, EPI_BF16_MASK>(tmA, tmB, p, s);
-    case EPI_BF16_BITMASK: return launch_gemm2<A_MN, B_MN, EPI_BF16_BITMASK>(tmA, tmB, p, s);
+    case EPI_BF16: return launch_gemm2<A_MN, B_MN, EPI_BF16>(tmA, tmB, tmC, use_tmc, p, s);
+    case EPI_BF16_RELU: return launch_gemm2<A_MN, B_MN, EPI_BF16_RELU>(tmA, tmB, tmC, use_tmc, p, s);
+    case EPI_F32: return launch_gemm2<A_MN, B_MN, EPI_F32>(tmA, tmB, tmC, use_tmc, p, s);
+    case EPI_F32_ATOMIC: return launch_gemm2<A_MN, B_MN, EPI_F32_ATOMIC>(tmA, tmB, tmC, use_tmc, p, s);
+    case EPI_BF16_MASK: return launch_gemm2<A_MN, B_MN, EPI_BF16_MASK>(tmA, tmB, tmC, use_tmc, p, s);
+    case EPI_BF16_BITMASK: return launch_gemm2<A_MN, B_MN, EPI_BF16_BITMASK>(tmA, tmB, tmC, use_tmc, p, s);
   }
   set_last_error("unknown epilogue", __FILE__, __LINE__);
   return LAKO_ERR_BAD_ARG;
 }
 
 static int dispatch_major2(int a_mn, int b_mn, int epi, const CUtensorMap& tmA, const CUtensorMap& tmB,
-                           const GemmParams& p, cudaStream_t s) {
-  if (!a_mn && !b_mn) return dispatch_epi2<false, false>(epi, tmA, tmB, p, s);
-  if (!a_mn && b_mn) return dispatch_epi2<false, true>(epi, tmA, tmB, p, s);
-  if (a_mn && !b_mn) return dispatch_epi2<true, false>(epi, tmA, tmB, p, s);
-  return dispatch_epi2<true, true>(epi, tmA, tmB, p, s);
+                           const CUtensorMap& tmC, int use_tmc, const GemmParams& p, cudaStream_t s) {
+  if (!a_mn && !b_mn) return dispatch_epi2<false, false>(epi, tmA, tmB, tmC, use_tmc, p, s);
+  if (!a_mn && b_mn) return dispatch_epi2<false, true>(epi, tmA, tmB, tmC, use_tmc, p, s);
+  if (a_mn && !b_mn) return dispatch_epi2<true, false>(epi, tmA, tmB, tmC, use_tmc, p, s);
+  return dispatch_epi2<true, true>(epi, tmA, tmB, tmC, use_tmc, p, s);
 }
 
 template <int BN, bool A_MN, bool B_MN, int EPI>
@@ -732,7 +758,23 @@ int gemm_bf16(const void* A, const void* B, void* C, int M, int N, int K, int ld
   const bool small = (M <= 128) || (a_mn && b_mn && K <= 128);
   const int pcat = small ? PROF_GEMM_SMALL : (a_mn ? PROF_GEMM_WGRAD : (b_mn ? PROF_GEMM_DGRAD : PROF_GEMM));
   ProfScope prof(pcat, 2.0 * M * N * static_cast<double>(K), stream);
-  if (use_pair) return dispatch_major2(a_mn, b_mn, epi, tmA, tmB, p, stream);
+  if (use_pair) {
+    // bf16 results leave through TMA stores of 32 x 64 boxes (128B swizzle, the staging layout of the epilogue)
+    CUtensorMap tmC = tmA;
+    int use_tmc = 0;
+    if (out_bf16 && epi != EPI_BF16_MASK) {
+      static const bool tma_epi = [] {
+        const char* e = getenv("LAKO_TMA_EPILOGUE");
+        return !(e && e[0] == '0');
+      }();
+      if (tma_epi) {
+        rc = get_tensor_map_2d(&tmC, C, N, M, ldc, 64, 32);
+        if (rc) return rc;
+        use_tmc = 1;
+      }
+    }
+    return dispatch_major2(a_mn, b_mn, epi, tmA, tmB, tmC, use_tmc, p, stream);
+  }
   if (bn == 256) return dispatch_major<256>(a_mn, b_mn, epi, tmA, tmB, p, stream);
   return dispatch_major<128>(a_mn, b_mn, epi, tmA, tmB, p, stream);
 }
