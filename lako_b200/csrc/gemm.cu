@@ -183,10 +183,31 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t t_ac
       uint32_t r[32];
       tmem_ld_32x32(t_acc + c * 32, r);
       tmem_ld_wait();
-      if (!row_ok) continue;
       float v[32];
 #pragma unroll
       for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) * p.alpha;
+      if constexpr (EPI == EPI_F32_ATOMIC) {
+        if (tmC) {
+          // Stage the 32 x 32 fp32 chunk (128 B rows, 16 B units XOR-swizzled like the TMA's 128B mode; rows past M
+          // hold zeros and are clipped) and let ONE TMA reduce-add store accumulate it: whole-line updates by the
+          // memory system instead of 256 16-byte red operations per warp.
+          uint8_t* stg = sStage + (slot < 0 ? q : slot) * 4096;
+          if (lane == 0) tma_store_wait_read<0>();  // the previous chunk's store has read the slot
+          __syncwarp();
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            *reinterpret_cast<float4*>(stg + lane * 128 + ((j ^ (lane & 7)) << 4)) =
+                make_float4(v[j * 4], v[j * 4 + 1], v[j * 4 + 2], v[j * 4 + 3]);
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_reduce_add_2d(tmC, stg, col0, m0 + q * 32);
+            tma_store_commit();
+          }
+          continue;
+        }
+      }
+      if (!row_ok) continue;
       const bool full = (col0 + 32 <= p.N);
       float* crow = reinterpret_cast<float*>(p.C) + static_cast<size_t>(row) * p.ldc + col0;
       if constexpr (EPI == EPI_F32) {
@@ -565,8 +586,8 @@ template <bool A_MN, bool B_MN, int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Gemm2Cfg::THREADS, 1)
 gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const __grid_constant__ CUtensorMap tmC, const GemmParams p, const int use_tmc) {
-  constexpr bool kBf16Out = EPI == EPI_BF16 || EPI == EPI_BF16_RELU || EPI == EPI_BF16_BITMASK;
-  gemm2_body<A_MN, B_MN, EPI>(&tmA, &tmB, nullptr, 1, p, (kBf16Out && use_tmc) ? &tmC : nullptr);
+  constexpr bool kTmaOut = EPI == EPI_BF16 || EPI == EPI_BF16_RELU || EPI == EPI_BF16_BITMASK || EPI == EPI_F32_ATOMIC;
+  gemm2_body<A_MN, B_MN, EPI>(&tmA, &tmB, nullptr, 1, p, (kTmaOut && use_tmc) ? &tmC : nullptr);
 }
 
 // Up to GEMM_MAX_BATCH same-shape problems in one launch (the decoder's per-layer weight gradients: each is a
@@ -769,6 +790,17 @@ int gemm_bf16(const void* A, const void* B, void* C, int M, int N, int K, int ld
       }();
       if (tma_epi) {
         rc = get_tensor_map_2d(&tmC, C, N, M, ldc, 64, 32);
+        if (rc) return rc;
+        use_tmc = 1;
+      }
+    } else if (epi == EPI_F32_ATOMIC) {
+      // gradient accumulation / split-K partial sums: TMA reduce-add stores of 32 x 32 fp32 boxes
+      static const bool tma_red = [] {
+        const char* e = getenv("LAKO_TMA_REDUCE");
+        return !(e && e[0] == '0');
+      }();
+      if (tma_red) {
+        rc = get_tensor_map_2d_f32(&tmC, C, N, M, ldc, 32, 32);
         if (rc) return rc;
         use_tmc = 1;
       }

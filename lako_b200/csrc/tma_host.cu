@@ -105,7 +105,8 @@ static std::mutex g_map_mu;
 static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> g_maps;
 
 static int encode(CUtensorMap* out, const MapKey& key, int rank, const void* base, const cuuint64_t* dims,
-                  const cuuint64_t* strides_bytes, const cuuint32_t* box) {
+                  const cuuint64_t* strides_bytes, const cuuint32_t* box,
+                  CUtensorMapDataType dtype = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16) {
   {
     std::lock_guard<std::mutex> lk(g_map_mu);
     auto it = g_maps.find(key);
@@ -120,7 +121,7 @@ static int encode(CUtensorMap* out, const MapKey& key, int rank, const void* bas
     return LAKO_ERR_DRIVER;
   }
   cuuint32_t estr[3] = {1, 1, 1};
-  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(base), dims, strides_bytes, box, estr,
+  CUresult r = fn(out, dtype, rank, const_cast<void*>(base), dims, strides_bytes, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -148,6 +149,20 @@ int get_tensor_map_2d(CUtensorMap* out, const void* base, uint64_t inner, uint64
   cuuint64_t strides[1] = {pitch_elems * 2};
   cuuint32_t box[2] = {box_inner, box_outer};
   return encode(out, key, 2, base, dims, strides, box);
+}
+
+// fp32 [outer][pitch_elems] matrix, box = box_inner (<= 32 floats = 128 B) x box_outer rows, 128B swizzle: the
+// destination of the split-K / gradient-accumulation epilogue's TMA reduce-add stores
+int get_tensor_map_2d_f32(CUtensorMap* out, const void* base, uint64_t inner, uint64_t outer, uint64_t pitch_elems,
+                          uint32_t box_inner, uint32_t box_outer) {
+  LAKO_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, LAKO_ERR_BAD_ARG);
+  LAKO_REQUIRE((pitch_elems * 4) % 16 == 0, LAKO_ERR_BAD_ARG);
+  LAKO_REQUIRE(box_inner * 4 <= 128 && box_outer <= 256 && box_outer >= 1, LAKO_ERR_BAD_ARG);
+  MapKey key{{4, reinterpret_cast<uint64_t>(base), inner, outer, pitch_elems, box_inner, box_outer, 0, 0, 0}};
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {pitch_elems * 4};
+  cuuint32_t box[2] = {box_inner, box_outer};
+  return encode(out, key, 2, base, dims, strides, box, CU_TENSOR_MAP_DATA_TYPE_FLOAT32);
 }
 
 int get_tensor_map_3d(CUtensorMap* out, const void* base, uint64_t inner, uint64_t d1, uint64_t d2,
