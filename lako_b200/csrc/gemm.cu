@@ -562,7 +562,7 @@ __device__ __forceinline__ void gemm2_body(const CUtensorMap* tmAs, const CUtens
       constexpr int G_PER_WARP = (BN / 64) / (Cfg::EPI_WARPS / 4);
       const int part = (warp - 4) >> 2;
       epilogue_tile<BN, EPI>(pz, tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN, sStage, m0, n0, q, lane,
-                             part * G_PER_WARP, (part + 1) * G_PER_WARP, warp - 4, tmC);
+                             part * G_PER_WARP, (part + 1) * G_PER_WARP, warp - 4, tmC ? tmC + z : nullptr);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(mapa_u32(&tempty_bar[acc], 0));
@@ -596,13 +596,14 @@ constexpr int GEMM_MAX_BATCH = 24;
 struct Gemm2Batch {
   CUtensorMap a[GEMM_MAX_BATCH];
   CUtensorMap b[GEMM_MAX_BATCH];
+  CUtensorMap cmap[GEMM_MAX_BATCH];  // fp32 outputs as TMA reduce-add destinations
   void* c[GEMM_MAX_BATCH];
   int n;
 };
 template <bool A_MN, bool B_MN, int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Gemm2Cfg::THREADS, 1)
 gemm2_batched_kernel(const __grid_constant__ Gemm2Batch bt, const GemmParams p) {
-  gemm2_body<A_MN, B_MN, EPI>(bt.a, bt.b, bt.c, bt.n, p);
+  gemm2_body<A_MN, B_MN, EPI>(bt.a, bt.b, bt.c, bt.n, p, EPI == EPI_F32_ATOMIC ? bt.cmap : nullptr);
 }
 
 template <bool A_MN, bool B_MN, int EPI>
@@ -854,11 +855,14 @@ int gemm_bf16_wgrad_batched(const void* const* A, const void* const* B, float* c
       if (rc) return rc;
       rc = get_tensor_map_2d(&bt.b[z], B[z0 + z], N, K, ldb, 64, BK);
       if (rc) return rc;
+      rc = get_tensor_map_2d_f32(&bt.cmap[z], C[z0 + z], N, M, ldc, 32, 32);
+      if (rc) return rc;
       bt.c[z] = C[z0 + z];
     }
     for (int z = bt.n; z < GEMM_MAX_BATCH; ++z) {  // keep the unused slots valid descriptors
       bt.a[z] = bt.a[0];
       bt.b[z] = bt.b[0];
+      bt.cmap[z] = bt.cmap[0];
       bt.c[z] = bt.c[0];
     }
     ProfScope prof(PROF_GEMM_SMALL, 2.0 * M * N * static_cast<double>(K) * bt.n, stream);
