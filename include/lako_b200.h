@@ -182,6 +182,9 @@ int lako_build_bias_lut(const float* table, const int* buckets, float* lut, int 
 int lako_fold_dlut(const float* dlut, const int* buckets, float* dtable, int H, int L, int bucket_center, int nb,
                    void* stream);
 /* encoder self-attention HF:253-344 per passage (src/model.py:230-232); qkv bf16 [P*L][3*H*64] */
+/* test support: overwrite every TMEM column of every SM with NaN bit patterns (tcgen05.alloc hands out columns
+   uncleared; a kernel that reads columns it did not write would pick these up) */
+int lako_debug_poison_tmem(void* stream);
 int lako_enc_attn_fwd(const void* qkv, const unsigned char* mask, const float* bias_lut, void* out, float* lse, int P,
                       int L, int H, void* stream);
 int lako_enc_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse, const unsigned char* mask,

@@ -110,7 +110,11 @@ enc_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const EncAttnPar
     L = p.cu[psg + 1] - row0;
     if (q0 >= L) return;  // whole query tile beyond the passage (nothing allocated yet)
   }
-  const int LK = (L + 15) / 16 * 16;
+  // Keys are processed in 32-column chunks, so S must be DEFINED for a whole number of chunks: with N rounded to 16
+  // only, the tail columns of the last chunk would be whatever the TMEM columns held before (tcgen05.alloc does not
+  // clear them; NaN bits left there by another kernel or process survive "+ bias - inf" and poison the row sum).
+  // Rows of the K tile past the passage are the next passage's rows or TMA zero fill -- finite, and masked below.
+  const int LK = (L + 31) / 32 * 32;
   const int ktiles = (LK + 127) / 128;
 
   if (tid == 0) {
@@ -278,6 +282,41 @@ enc_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const EncAttnPar
     tc_fence_after();
     tmem_dealloc(tmem, 256);
   }
+}
+
+// Test support: fill all 512 TMEM columns of every SM with NaN bit patterns (what a previous tenant of the GPU may
+// leave behind), so that tests can prove no kernel consumes TMEM it did not write.
+__global__ void __launch_bounds__(128, 1) poison_tmem_kernel() {
+  __shared__ uint32_t slot;
+  const int warp = threadIdx.x >> 5;
+  if (warp == 0) tmem_alloc(&slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = slot;
+  uint32_t v[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = 0x7fc00000u;
+  for (int c = 0; c < 16; ++c) tmem_st_32x32(tmem + (static_cast<uint32_t>(warp * 32) << 16) + c * 32, v);
+  tmem_st_wait();
+  // keep the SM occupied long enough that the block scheduler places one CTA on every SM
+  const long long t0 = clock64();
+  while (clock64() - t0 < 200000) {
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+int poison_tmem(cudaStream_t s) {
+  int rc = check_arch();
+  if (rc) return rc;
+  cudaFuncSetAttribute(poison_tmem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  poison_tmem_kernel<<<device_sm_count() * 2, 128, 200 * 1024, s>>>();  // 200 KB dynamic smem: one CTA per SM at a time
+  LAKO_CHECK_LAUNCH();
+  return LAKO_OK;
 }
 
 // qkv bf16 [P*L][3*inner]; out bf16 [P*L][inner]; lse fp32 [P][H][L] (may be null)

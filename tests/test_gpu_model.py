@@ -124,10 +124,12 @@ def test_padded_and_packed_paths_agree(path):
     c, cfg, sd, model = _load(path)
     args = dict(input_ids=c["ids"].cuda(), attention_mask=c["mask"].cuda(), labels=c["labels"].cuda())
     res = {}
+    from lako_b200 import _native as nat
     for unpad in (True, False):
         model.unpad = unpad
         model.train()
         model.zero_grad()
+        nat.check(nat.lib().lako_debug_poison_tmem(nat.stream_ptr()))   # stale TMEM must never reach a result
         loss, logits = model(**args)
         loss.backward()
         torch.cuda.synchronize()
