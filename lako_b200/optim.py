@@ -224,6 +224,29 @@ class FusedAdamW:
     def grad_norm(self):
         return torch.sqrt(self.sumsq)
 
+    # ---------------------------------------------------------------- checkpoint (src/util.py:105-146)
+    @torch.no_grad()
+    def state_dict(self):
+        """What src/util.py:save stores as checkpoint["optimizer"] (and, for the built-in schedule, what it stores as
+        checkpoint["scheduler"]: the step count).  In sharded data-parallel mode the Adam moments are all-gathered
+        first -- a collective, call it on every rank."""
+        if self._plan is not None and self.step_count > 0:
+            for lo, hi, plo, phi in self._plan:
+                self._all_gather(self.m, lo, hi, plo, phi)
+                self._all_gather(self.v, lo, hi, plo, phi)
+        return {"step": self.step_count, "exp_avg": self.m.detach().clone(), "exp_avg_sq": self.v.detach().clone(),
+                "lr": self.lr, "weight_decay": self.wd, "betas": tuple(self.betas), "eps": self.eps, "clip": self.clip}
+
+    @torch.no_grad()
+    def load_state_dict(self, sd):
+        if sd["exp_avg"].numel() != self.m.numel():
+            raise nat.LakoError("optimizer state does not match the model's flat parameter buffer")
+        self.m.copy_(sd["exp_avg"].to(self.m.device))
+        self.v.copy_(sd["exp_avg_sq"].to(self.v.device))
+        self.step_count = int(sd["step"])
+        self.lr, self.wd, self.eps, self.clip = sd["lr"], sd["weight_decay"], sd["eps"], sd["clip"]
+        self.betas = tuple(sd["betas"])
+
     def zero_grad(self):
         self.model.zero_grad()
 

@@ -119,3 +119,36 @@ def test_schedule_matches_oracle():
     s = WarmupLinearSchedule(6, 100)
     for step in (0, 1, 5, 6, 7, 50, 99, 100, 150):
         assert abs(s(step) - O.warmup_linear_lambda(step, 6, 100)) < 1e-12
+
+
+def test_fused_adamw_checkpoint_roundtrip():
+    """FusedAdamW.state_dict / load_state_dict (what src/util.py:105-146 saves and restores) on a CPU-resident model:
+    only the host-side bookkeeping is exercised here, the update kernel itself needs the GPU."""
+    from lako_b200.model import FiDT5, FiDT5Config
+    from lako_b200.optim import FusedAdamW, shard_plan
+    cfg = FiDT5Config(vocab_size=64, d_model=128, d_ff=256, num_layers=2, num_heads=2)
+    model = FiDT5(cfg, seed=0)
+    a = FusedAdamW(model, lr=3e-4, weight_decay=0.01, clip=1.0)
+    a.m.normal_()
+    a.v.uniform_()
+    a.step_count = 17
+    sd = a.state_dict()
+    b = FusedAdamW(model, lr=1.0, weight_decay=0.5, clip=0.0)
+    b.load_state_dict(sd)
+    assert b.step_count == 17 and b.lr == 3e-4 and b.wd == 0.01 and b.clip == 1.0
+    assert torch.equal(b.m, a.m) and torch.equal(b.v, a.v)
+    # the gradient-stage ranges of a real layout split evenly over 2 / 4 / 8 ranks (the sharded mode's precondition)
+    import ctypes
+    from lako_b200 import _native as nat
+    ranges = (ctypes.c_size_t * 14)()
+    for size in ("base", "large"):
+        dims = FiDT5Config.t5(size)  # layouts only: no weights are allocated
+        from lako_b200.model import _Dims
+        d = _Dims(dims.d_model, dims.num_heads, dims.d_ff, dims.num_layers, dims.vocab_size,
+                  dims.relative_attention_num_buckets, dims.layer_norm_epsilon)
+        nat.check(nat.lib().lako_fidt5_grad_stages(ctypes.byref(d), ranges), "lako_fidt5_grad_stages")
+        rs = [(int(ranges[2 * i]), int(ranges[2 * i + 1])) for i in range(7)]
+        for world in (2, 4, 8):
+            plan = shard_plan(rs, world, world - 1)
+            assert plan is not None, (size, world)
+            assert sum(hi - lo for lo, hi, _, _ in plan) == sum(hi - lo for lo, hi in rs)
