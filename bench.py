@@ -372,6 +372,33 @@ def main():
     if world > 1:
         dist.barrier()
 
+    # ---- supplementary: greedy generate() + score capture at the same shapes (test_reader.py:36-84), rank 0 only,
+    #      outside every timed region of the training metric
+    gen = None
+    if rank == 0 and not args.no_e2e:
+        try:
+            model.eval()
+            model.overwrite_forward_crossattention()
+            model.reset_score_storage()
+            ids_g, mask_g, _ = resident[0]
+            ml = 50
+            model.generate(input_ids=ids_g, attention_mask=mask_g, max_length=ml)
+            torch.cuda.synchronize()
+            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            g0.record()
+            reps = 3
+            for _ in range(reps):
+                out_g = model.generate(input_ids=ids_g, attention_mask=mask_g, max_length=ml)
+            g1.record()
+            torch.cuda.synchronize()
+            gms = g0.elapsed_time(g1) / reps
+            gen = {"questions_per_s": round(B / (gms * 1e-3), 1), "ms_per_call": round(gms, 2), "max_length": ml,
+                   "columns_generated": int(out_g.shape[1]), "score_capture": True}
+            model.train()
+        except Exception as e:  # never let the supplementary probe break the contract line
+            gen = {"error": str(e)[:200]}
+            model.train()
+
     # ---- CPU baseline (rank 0, N=1 only): oracle on a bounded sample
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -406,6 +433,7 @@ def main():
             "roofline": roofline,
             "kernels": kernel_share,
             "cpu_baseline": cpu_baseline,
+            "generate": gen,
             "clocks": sampler.summary() if sampler else None,
         }
         print(json.dumps(line), flush=True)

@@ -1,3 +1,6 @@
+"""Small-shape training probe (t5-base, B=4, N=4, L=96, T=8; SEED selects the batch): prints three step losses.
+Used to reproduce the stale-TMEM NaN (profiles/README.md item 13): small workloads leave some SMs' TMEM untouched by
+any GEMM before the first attention kernel runs.  Env: SEED, UNPAD=0 (padded layout), EVAL=1 (forward only)."""
 import os, sys
 import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
