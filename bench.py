@@ -438,6 +438,7 @@ def main():
         }
         print(json.dumps(line), flush=True)
     if world > 1:
+        dist.barrier()  # rank 0 did the supplementary probes; leave together
         dist.destroy_process_group()
 
 
