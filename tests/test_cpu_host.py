@@ -152,3 +152,25 @@ def test_fused_adamw_checkpoint_roundtrip():
             plan = shard_plan(rs, world, world - 1)
             assert plan is not None, (size, world)
             assert sum(hi - lo for lo, hi, _, _ in plan) == sum(hi - lo for lo, hi in rs)
+
+
+def test_packing_plan_prefix_masks_and_host_lengths():
+    """FiDT5._packing: prefix masks -> cu_seqlens of the valid prefixes (read back, or taken from the Collator's
+    host-side lengths without touching the device); any other mask -> padded layout."""
+    from lako_b200.model import FiDT5, FiDT5Config
+    model = FiDT5(FiDT5Config(vocab_size=64, d_model=128, d_ff=256, num_layers=1, num_heads=2), seed=0)
+    B, N, L = 2, 3, 10
+    lens = torch.tensor([[10, 4, 7], [1, 9, 5]])
+    mask = torch.arange(L)[None, None, :] < lens[:, :, None]
+    cu, total = model._packing(mask)
+    assert total == int(lens.sum()) and cu.tolist() == [0, 10, 14, 21, 22, 31, 36]
+    cu2, total2 = model._packing(mask, lens)          # host lengths: same plan, no read-back
+    assert total2 == total and cu2.tolist() == cu.tolist()
+    holes = mask.clone()
+    holes[0, 0, 3] = False                            # not a prefix mask: cannot be packed
+    assert model._packing(holes) == (None, 0)
+    model.unpad = False
+    assert model._packing(mask) == (None, 0)
+    model.unpad = True
+    with pytest.raises(Exception):
+        model._packing(mask, torch.tensor([1, 2, 3]))  # wrong number of lengths
