@@ -152,7 +152,7 @@ typedef struct {
   const int* cu_seqlens;
   int packed_tokens;
   /* backward only, optional: LAKO_N_GRAD_STAGES cudaEvent_t recorded as gradient ranges become final
-   * (lako_fidt5_grad_stages), so the caller can start the data-parallel all-reduce of a range while backward is
+   * (lako_fidt5_grad_stages), so the caller can start the data-parallel reduce-scatter / all-reduce of a range while backward is
    * still running */
   void* stage_events;
 } lako_batch;

@@ -6,8 +6,8 @@
 // fp32 softmax, probs @ v.   One "unit" = (passage, head); L = text_maxlength <= 256, d_kv = 64.
 //
 // Because a whole passage fits one tile (L <= 256 keys), softmax is single pass (no online
-// rescaling): S = Q K^T lands in TMEM (128 lanes x LK fp32 columns), each of the 128 threads owns
-// one query row, reads it with tcgen05.ld, adds the bias from a per-head LUT in shared memory
+// rescaling): S = Q K^T lands in TMEM (128 lanes x LK fp32 columns), two threads share a query row
+// (one key half each), read it with tcgen05.ld, adds the bias from a per-head LUT in shared memory
 // (2L-1 entries), writes un-normalised bf16 probabilities into 128B-swizzled shared memory, and
 // the second MMA O = P V (V as an MN-major operand straight from the qkv buffer) accumulates into
 // the same TMEM columns.  Q/K/V tiles come in by TMA from the fused qkv activation
