@@ -155,6 +155,12 @@ typedef struct {
    * (lako_fidt5_grad_stages), so the caller can start the data-parallel reduce-scatter / all-reduce of a range while backward is
    * still running */
   void* stage_events;
+  /* 1: `labels` holds decoder_input_ids (HF's other calling convention): no shift, no loss, logits only */
+  int labels_are_decoder_ids;
+  /* 0 = bf16 tensor-core operands, fp32 accumulation (default).  1 = fp32: 3xTF32-split tcgen05 GEMMs on the fp32
+   * master weights + fp32 attention kernels; forward (mode 0) and generate only -- the reference is fp32-only
+   * (train_reader.py:67) and north_star's 1e-4 logit tolerance is stated for this mode. */
+  int precision;
 } lako_batch;
 
 int lako_fidt5_layout(const lako_dims* dims, lako_layout* out);
@@ -173,8 +179,8 @@ int lako_fidt5_grad_stages(const lako_dims* dims, size_t* ranges);
  * to test for early stop.  tok_score_* (may be NULL) receive the step-0 cross-attention score sums
  * that src/model.py:327-329 + :152-167 derive from score_storage. */
 size_t lako_fidt5_generate_workspace_bytes(const lako_dims* dims, int B, int N, int L, int max_length);
-int lako_fidt5_generate(const lako_fidt5* m, const lako_batch* b, int max_length, int64_t* out_ids, int* out_len,
-                        float* tok_score_first, float* tok_score_last, void* stream);
+int lako_fidt5_generate(const lako_fidt5* m, const lako_batch* b, int max_length, int min_length, int64_t* out_ids,
+                        int* out_len, float* tok_score_first, float* tok_score_last, void* stream);
 
 /* ---- attention kernels (unit-test entry points; the model calls them internally) --------------- */
 int lako_build_bias_lut(const float* table, const int* buckets, float* lut, int H, int L, int bucket_center,

@@ -319,7 +319,7 @@ int dself_step(const __nv_bfloat16* qkv, __nv_bfloat16* kcache, __nv_bfloat16* v
 __global__ void __launch_bounds__(256) greedy_pick_kernel(const float* __restrict__ logits, int V, int ld,
                                                           long long* __restrict__ out_ids, int out_ld, int step,
                                                           int* __restrict__ unfinished, int* __restrict__ n_unfinished,
-                                                          long long* __restrict__ next_ids) {
+                                                          long long* __restrict__ next_ids, int ban_eos) {
   pdl_launch_dependents();
   pdl_wait();
   __shared__ float s_v[8];
@@ -330,6 +330,7 @@ __global__ void __launch_bounds__(256) greedy_pick_kernel(const float* __restric
   int bi = 0x7fffffff;
   for (int c = tid; c < V; c += 256) {
     const float v = lr[c];
+    if (ban_eos && c == 1) continue;  // HF MinLengthLogitsProcessor: EOS logit = -inf below min_length
     if (v > best || (v == best && c < bi)) {
       best = v;
       bi = c;
@@ -355,6 +356,7 @@ __global__ void __launch_bounds__(256) greedy_pick_kernel(const float* __restric
         best = s_v[w];
         bi = s_i[w];
       }
+    if (bi < 0 || bi >= V) bi = 0;  // all-NaN row: no comparison succeeded
     const int unf = unfinished[b];
     const long long tok = unf ? bi : 0;
     out_ids[static_cast<size_t>(b) * out_ld + step] = tok;
@@ -367,8 +369,9 @@ __global__ void __launch_bounds__(256) greedy_pick_kernel(const float* __restric
 }
 
 int greedy_pick(const float* logits, int B, int V, int ld, long long* out_ids, int out_ld, int step, int* unfinished,
-                int* n_unfinished, long long* next_ids, cudaStream_t s) {
-  launch_pdl(greedy_pick_kernel, dim3(B), dim3(256), 0, s, logits, V, ld, out_ids, out_ld, step, unfinished, n_unfinished, next_ids);
+                int* n_unfinished, long long* next_ids, cudaStream_t s, int ban_eos) {
+  launch_pdl(greedy_pick_kernel, dim3(B), dim3(256), 0, s, logits, V, ld, out_ids, out_ld, step, unfinished, n_unfinished, next_ids,
+             ban_eos);
   LAKO_CHECK_LAUNCH();
   return LAKO_OK;
 }

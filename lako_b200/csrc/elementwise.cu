@@ -445,7 +445,7 @@ __global__ void __launch_bounds__(512) ce_fwd_bwd_kernel(const float* __restrict
   const int row = blockIdx.x;
   const long long label = labels[row];
   const float* lr = logits + static_cast<size_t>(row) * ld;
-  const bool valid = (label != -100);
+  const bool valid = (label >= 0 && label < V);  // -100 = ignore_index; any other out-of-range label is ignored too
   float m = -INFINITY, ssum = 0.f;
   if (valid) {
     for (int c = threadIdx.x * 4; c < V; c += blockDim.x * 4) {

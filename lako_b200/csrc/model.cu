@@ -402,7 +402,12 @@ extern "C" int lako_fidt5_forward(const lako_fidt5* m, const lako_batch* bt, int
   RC(encode(p, m, w, reinterpret_cast<const long long*>(bt->ids), bt->mask, train, s, dr));
 
   const long long* labels = reinterpret_cast<const long long*>(bt->labels);
-  RC(shift_right(labels, w.dec_ids, bt->B, bt->T, s));
+  if (bt->labels_are_decoder_ids) {
+    LAKO_REQUIRE(!train, LAKO_ERR_BAD_ARG);
+    cudaMemcpyAsync(w.dec_ids, labels, sizeof(long long) * BT, cudaMemcpyDeviceToDevice, s);
+  } else {
+    RC(shift_right(labels, w.dec_ids, bt->B, bt->T, s));
+  }
   RC(embed_gather(w.dec_ids, p.wf + p.lo.shared, w.Y[0], BT, d, p.V, s, dr(0, D_EMB)));
   RC(build_bias_lut(p.wf + p.lo.dec_relbias, m->dec_buckets, w.lut_dec, p.H, bt->T, m->bucket_center, s));
   for (int l = 0; l < nl; ++l) {
@@ -431,6 +436,7 @@ extern "C" int lako_fidt5_forward(const lako_fidt5* m, const lako_batch* bt, int
   // tied LM head: logits = (h * d^-0.5) E^T  (HF:1107-1110), fp32 out
   const float alpha = 1.0f / sqrtf(static_cast<float>(d));
   RC(lin_fwd(w.hn, p.wb + p.lo.shared, bt->logits, BT, p.V, d, EPI_F32, alpha, s));
+  if (bt->labels_are_decoder_ids) return LAKO_OK;  // logits only
   if (!bt->count_is_set) RC(count_valid(labels, BT, bt->stats, s));
   const size_t vpad = (static_cast<size_t>(p.V) + 7) / 8 * 8;
   RC(ce_fwd_bwd(bt->logits, labels, bt->stats, w.row_loss, train ? w.dlogits : nullptr, BT, p.V, p.V,
@@ -636,8 +642,9 @@ extern "C" size_t lako_fidt5_generate_workspace_bytes(const lako_dims* dm, int B
 // token.  tok_score_first/last fp32 [B][N*L] (device, pre-zeroed by the caller, may be null):
 // sum over heads and over the first ceil(nl/2) / the remaining decoder layers of the masked step-0
 // pre-softmax cross-attention scores.
-extern "C" int lako_fidt5_generate(const lako_fidt5* m, const lako_batch* bt, int max_length, int64_t* out_ids,
-                                   int* out_len, float* tok_score_first, float* tok_score_last, void* stream) {
+extern "C" int lako_fidt5_generate(const lako_fidt5* m, const lako_batch* bt, int max_length, int min_length,
+                                   int64_t* out_ids, int* out_len, float* tok_score_first, float* tok_score_last,
+                                   void* stream) {
   RC(check_arch());
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   Ptrs p;
@@ -685,7 +692,7 @@ extern "C" int lako_fidt5_generate(const lako_fidt5* m, const lako_batch* bt, in
     RC(rmsnorm_fwd(w.Y[0], w.delta_dec, w.Y[0], p.wf + p.lo.dec_final_ln, w.hn, nullptr, B, d, p.eps, 1.f, s));
     RC(lin_fwd(w.hn, p.wb + p.lo.shared, gw.logits, B, p.V, d, EPI_F32, alpha, s));
     RC(greedy_pick(gw.logits, B, p.V, p.V, reinterpret_cast<long long*>(out_ids), max_length, step + 1, gw.unfinished,
-                   gw.n_unf, gw.next_ids, s));
+                   gw.n_unf, gw.next_ids, s, (step + 1 < min_length) ? 1 : 0));
     len = step + 2;
     int n_unf = 0;
     cudaMemcpyAsync(&n_unf, gw.n_unf, sizeof(int), cudaMemcpyDeviceToHost, s);

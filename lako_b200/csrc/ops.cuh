@@ -79,6 +79,6 @@ int dself_bwd(const __nv_bfloat16* qkv, const __nv_bfloat16* dout, const float* 
 int dself_step(const __nv_bfloat16* qkv, __nv_bfloat16* kcache, __nv_bfloat16* vcache, const float* lut,
                __nv_bfloat16* out, int B, int pos, int Tmax, int H, cudaStream_t s);
 int greedy_pick(const float* logits, int B, int V, int ld, long long* out_ids, int out_ld, int step, int* unfinished,
-                int* n_unfinished, long long* next_ids, cudaStream_t s);
+                int* n_unfinished, long long* next_ids, cudaStream_t s, int ban_eos = 0);
 
 }  // namespace lako

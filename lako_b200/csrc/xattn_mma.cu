@@ -102,7 +102,7 @@ __global__ void __launch_bounds__(128) xattn_fwd_mma_kernel(const XMParams p) {
   stage_sw(sQ, p.q + static_cast<size_t>(b) * p.T * p.ldq + h * 64, p.ldq, p.TP, p.T, tid, 128);
   {
     const int j = tid;
-    const bool valid = (p.mask == nullptr) || p.mask[static_cast<size_t>(b) * p.M + k0 + j];
+    const bool valid = j >= nk || (p.mask == nullptr) || p.mask[static_cast<size_t>(b) * p.M + k0 + j];
     sMask[j] = (j < nk) ? (valid ? 0.f : XM_MASK_MIN) : -INFINITY;
   }
   cp_async_wait_all();
@@ -308,7 +308,7 @@ __global__ void __launch_bounds__(128, TPC == 16 ? 5 : 3) xattn_bwd_mma_kernel(c
   stage_sw(sQ, p.q + static_cast<size_t>(b) * p.T * p.ldq + h * 64, p.ldq, TPC, p.T, tid, 128);
   stage_sw(sDO, p.dout + static_cast<size_t>(b) * p.T * p.ldo + h * 64, p.ldo, TPC, p.T, tid, 128);
   {
-    const bool valid = (p.mask == nullptr) || p.mask[static_cast<size_t>(b) * p.M + k0 + tid];
+    const bool valid = tid >= nk || (p.mask == nullptr) || p.mask[static_cast<size_t>(b) * p.M + k0 + tid];
     sMask[tid] = (tid < nk) ? (valid ? 0.f : XM_MASK_MIN) : -INFINITY;
   }
 #pragma unroll

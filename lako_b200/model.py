@@ -59,7 +59,8 @@ class _Batch(ctypes.Structure):
                 ("workspace", ctypes.c_void_p), ("workspace_bytes", ctypes.c_size_t),
                 ("logits", ctypes.c_void_p), ("stats", ctypes.c_void_p), ("count_is_set", ctypes.c_int),
                 ("dropout_p", ctypes.c_float), ("dropout_step", ctypes.c_uint), ("dropout_seed", ctypes.c_ulonglong),
-                ("cu_seqlens", ctypes.c_void_p), ("packed_tokens", ctypes.c_int), ("stage_events", ctypes.c_void_p)]
+                ("cu_seqlens", ctypes.c_void_p), ("packed_tokens", ctypes.c_int), ("stage_events", ctypes.c_void_p),
+                ("labels_are_decoder_ids", ctypes.c_int), ("precision", ctypes.c_int)]
 
 
 class FiDT5Config:
@@ -140,6 +141,16 @@ def _enc_name(i, wrapped=True):
     return f"encoder.encoder.block.{i}.module.layer" if wrapped else f"encoder.block.{i}.layer"
 
 
+class ReaderOutput(tuple):
+    """What FiDT5.forward returns: indexable like the reference's tuple (`model(...)[0]` is the loss,
+    train_reader.py:67-71) and attribute-readable like HF's Seq2SeqLMOutput (.loss, .logits)."""
+
+    def __new__(cls, loss, logits):
+        self = super().__new__(cls, (logits,) if loss is None else (loss, logits))
+        self.loss, self.logits = loss, logits
+        return self
+
+
 class _LossFn(torch.autograd.Function):
     """Ties `loss.backward()` (train_reader.py:73) to lako_fidt5_backward: gradients are accumulated by
     the CUDA side directly into the flat gradient buffer that every Parameter.grad is a view of."""
@@ -183,6 +194,8 @@ class FiDT5(nn.Module):
         self._build_tree()
         self._anchor = torch.zeros(1, requires_grad=True)
         self._ws = {}
+        self._ws_gen = 0
+        self.precision = "bf16"   # "bf16" (bf16 operands, fp32 accumulate) | "fp32" (evaluation only, see set_precision)
         self._capture = False
         self._tok_first = self._tok_last = None
         self.use_checkpoint = False
@@ -374,9 +387,35 @@ class FiDT5(nn.Module):
         with open(os.path.join(path, "config.json")) as f:
             cfg = json.load(f)
         model = cls(FiDT5Config(**cfg))
-        sd = torch.load(os.path.join(path, "pytorch_model.bin"), map_location="cpu")
-        model.load_state_dict(sd)
+        sd = cls._read_checkpoint(path)
+        if any(k.startswith("encoder.block.") for k in sd):   # a plain T5 checkpoint written by transformers
+            model.load_t5(sd)
+        else:
+            model.load_state_dict(sd)
         return model
+
+    @staticmethod
+    def _read_checkpoint(path):
+        """Every on-disk form `PreTrainedModel.save_pretrained` produces: pytorch_model.bin, model.safetensors, or
+        either one sharded behind a *.index.json (src/util.py:128 loads the reader through from_pretrained)."""
+        def load_one(fn):
+            if fn.endswith(".safetensors"):
+                from safetensors.torch import load_file
+                return load_file(fn, device="cpu")
+            return torch.load(fn, map_location="cpu", weights_only=True)
+        for name in ("model.safetensors", "pytorch_model.bin"):
+            fn = os.path.join(path, name)
+            if os.path.exists(fn):
+                return load_one(fn)
+            idx = fn + ".index.json"
+            if os.path.exists(idx):
+                with open(idx) as f:
+                    shards = sorted(set(json.load(f)["weight_map"].values()))
+                sd = {}
+                for sh in shards:
+                    sd.update(load_one(os.path.join(path, sh)))
+                return sd
+        raise FileNotFoundError(f"no pytorch_model.bin / model.safetensors (or sharded index) under {path}")
 
     # ------------------------------------------------------------------ device state
     def _require_cuda(self):
@@ -396,6 +435,11 @@ class FiDT5(nn.Module):
                     p.grad = self._view(self._flat_grad, name)
 
     def _refresh_bf16(self):
+        sig = self._weights_signature()
+        if self._master_sync is not None and self._bf16 is not None and self._bf16_version != sig:
+            # sharded optimizer + someone touched the masters: foreign slices of the masters are stale, and casting them
+            # would overwrite the correct all-gathered bf16 weights -- bring the masters up to date first (collective)
+            self._master_sync()
         if self._bf16 is None:
             self._bf16 = torch.empty(self._total, dtype=torch.bfloat16, device=self._flat.device)
             self._bf16_version = -1
@@ -463,6 +507,21 @@ class FiDT5(nn.Module):
             return None, 0
         return cu.to(mask.device), total
 
+    def set_precision(self, precision):
+        """"bf16" (default): bf16 tensor-core operands with fp32 accumulation everywhere.  "fp32": the evaluation /
+        score-extraction path (forward without grad, generate, get_crossattention_scores) runs 3xTF32 split tcgen05
+        GEMMs on the fp32 master weights and fp32 attention kernels -- the reference itself is fp32-only
+        (train_reader.py:67, no autocast anywhere); north_star's 1e-4 logit tolerance is stated for this mode."""
+        if precision not in ("bf16", "fp32"):
+            raise ValueError("precision must be 'bf16' or 'fp32'")
+        self.precision = precision
+
+    def _precision_code(self, override=None):
+        p = self.precision if override is None else override
+        if p not in ("bf16", "fp32"):
+            raise ValueError("precision must be 'bf16' or 'fp32'")
+        return 1 if p == "fp32" else 0
+
     def set_dropout_seed(self, seed):
         """Seed of the dropout masks (defaults to torch.initial_seed() at the first training forward; use a
         different seed per data-parallel rank, as train_reader.py:39 does with torch.manual_seed(rank + seed))."""
@@ -470,12 +529,25 @@ class FiDT5(nn.Module):
         self._drop_step = 0
 
     # ------------------------------------------------------------------ forward / backward
-    def forward(self, input_ids=None, attention_mask=None, labels=None, global_target_count=None, passage_lengths=None,
-                **kwargs):
+    _IGNORED_KWARGS = ("return_dict", "use_cache", "output_attentions", "output_hidden_states")
+
+    def forward(self, input_ids=None, attention_mask=None, labels=None, decoder_input_ids=None,
+                global_target_count=None, passage_lengths=None, precision=None, **kwargs):
+        """model.py:39-51.  With `labels`: (loss, logits).  With `decoder_input_ids` and no labels (HF's other calling
+        convention): (logits,) for exactly those decoder inputs, no loss and no backward."""
         self._require_cuda()
-        if labels is None:
-            raise nat.LakoError("FiDT5.forward needs labels (the reader is only called as model(..., labels=...)[0], "
-                                "train_reader.py:67-71); use generate() for inference")
+        bad = [k for k, v in kwargs.items() if k not in self._IGNORED_KWARGS and v is not None]
+        if bad:
+            raise TypeError(f"FiDT5.forward: unsupported arguments {bad} (supported: input_ids, attention_mask, labels, "
+                            "decoder_input_ids; return_dict/use_cache/output_* are accepted and have no effect)")
+        if kwargs.get("output_attentions") or kwargs.get("output_hidden_states"):
+            raise TypeError("FiDT5.forward: attention maps / hidden states are never materialised by the fused kernels")
+        dec_given = labels is None
+        if dec_given:
+            if decoder_input_ids is None:
+                raise nat.LakoError("FiDT5.forward needs labels (model(..., labels=...)[0], train_reader.py:67-71) or "
+                                    "decoder_input_ids; use generate() for inference")
+            labels = decoder_input_ids
         if input_ids.dim() == 3:
             self.encoder.n_passages = input_ids.size(1)
         B = input_ids.size(0)
@@ -487,14 +559,19 @@ class FiDT5(nn.Module):
         mask = attention_mask.reshape(B, N, L).to(torch.bool).contiguous()
         labels = labels.contiguous()
         T = labels.size(1)
-        train = torch.is_grad_enabled()
+        train = torch.is_grad_enabled() and not dec_given
         mode = 1 if train else 0
+        prec = self._precision_code(precision)
+        if train and prec != 0:
+            raise nat.LakoError("precision='fp32' is an evaluation mode (forward / generate / score extraction); "
+                                "training runs bf16 operands with fp32 accumulation")
         if train:
             self._ensure_grad()
         L_ = nat.lib()
         L_.lako_fidt5_workspace_bytes.restype = ctypes.c_size_t
         nbytes = L_.lako_fidt5_workspace_bytes(ctypes.byref(self._dims), B, N, L, T, mode)
         ws = self._workspace(("fwd", B, N, L, T, mode), nbytes)
+        self._ws_gen += 1   # the workspace now holds THIS forward's activations (see _run_backward)
         logits = torch.empty(B, T, self.config.vocab_size, dtype=torch.float32, device=ids.device)
         stats = torch.zeros(2, dtype=torch.float32, device=ids.device)
         count_is_set = 0
@@ -511,13 +588,16 @@ class FiDT5(nn.Module):
         pack = (cu.data_ptr() if cu is not None else 0, packed)
         m = self._model_struct(with_grad=train)
         bt = _Batch(ids.data_ptr(), mask.data_ptr(), labels.data_ptr(), B, N, L, T, ws.data_ptr(), ws.numel(),
-                    logits.data_ptr(), stats.data_ptr(), count_is_set, *drop, *pack, 0)
+                    logits.data_ptr(), stats.data_ptr(), count_is_set, *drop, *pack, 0, int(dec_given), prec)
         nat.check(L_.lako_fidt5_forward(ctypes.byref(m), ctypes.byref(bt), mode, nat.stream_ptr()), "lako_fidt5_forward")
+        if dec_given:
+            return ReaderOutput(None, logits)
         loss = stats[0] / torch.clamp(stats[1], min=1.0)
         if train:
-            keep = (ids, mask, labels, ws, logits, stats, (B, N, L, T), drop, cu, pack)
+            keep = {"t": (ids, mask, labels, ws, logits, stats, (B, N, L, T), drop, cu, pack), "gen": self._ws_gen,
+                    "done": False}
             loss, logits = _LossFn.apply(self._anchor, self, keep, loss, logits)
-        return (loss, logits)
+        return ReaderOutput(loss, logits)
 
     def enable_grad_stage_events(self):
         """Create the 6 stage events + flat ranges used to overlap the gradient all-reduce with backward."""
@@ -533,19 +613,29 @@ class FiDT5(nn.Module):
         return self._stage_events, self._stage_ranges
 
     def _run_backward(self, keep, grad_loss):
-        ids, mask, labels, ws, logits, stats, (B, N, L, T), drop, _cu, pack = keep
+        # The activation workspace is one buffer per shape, reused by every forward: a later grad-enabled forward with the
+        # same shapes overwrites what this graph saved, and backward scales the stored dlogits in place.
+        if keep["gen"] != self._ws_gen:
+            raise nat.LakoError("loss.backward(): another forward with the same shapes ran after this loss was computed and "
+                                "overwrote its saved activations; call backward() before the next forward (gradient "
+                                "accumulation: forward -> backward per micro-batch, the gradients add up in .grad)")
+        if keep["done"]:
+            raise nat.LakoError("loss.backward() called twice on the same graph (retain_graph is not supported: backward "
+                                "consumes the saved activations)")
+        keep["done"] = True
+        ids, mask, labels, ws, logits, stats, (B, N, L, T), drop, _cu, pack = keep["t"]
         L_ = nat.lib()
         m = self._model_struct(with_grad=True)
         stage = ctypes.cast(self._stage_handles, ctypes.c_void_p).value if self._stage_events is not None else 0
         bt = _Batch(ids.data_ptr(), mask.data_ptr(), labels.data_ptr(), B, N, L, T, ws.data_ptr(), ws.numel(),
-                    logits.data_ptr(), stats.data_ptr(), 1, *drop, *pack, stage)
+                    logits.data_ptr(), stats.data_ptr(), 1, *drop, *pack, stage, 0, 0)
         gl = grad_loss.detach().to(torch.float32).reshape(1).contiguous()
         nat.check(L_.lako_fidt5_backward(ctypes.byref(m), ctypes.byref(bt), nat.ptr(gl), nat.stream_ptr()),
                   "lako_fidt5_backward")
 
     # ------------------------------------------------------------------ generate + scores
     @torch.no_grad()
-    def generate(self, input_ids, attention_mask, max_length):
+    def generate(self, input_ids, attention_mask, max_length, min_length=0, precision=None):
         self._require_cuda()
         B, N, L = input_ids.shape
         self.encoder.n_passages = N
@@ -565,9 +655,9 @@ class FiDT5(nn.Module):
         cu, packed = self._packing(mask)
         m = self._model_struct(with_grad=False)
         bt = _Batch(ids.data_ptr(), mask.data_ptr(), 0, B, N, L, 1, ws.data_ptr(), ws.numel(), 0, 0, 0, 0.0, 0, 0,
-                    cu.data_ptr() if cu is not None else 0, packed, 0)
+                    cu.data_ptr() if cu is not None else 0, packed, 0, 0, self._precision_code(precision))
         out_len = ctypes.c_int(0)
-        nat.check(L_.lako_fidt5_generate(ctypes.byref(m), ctypes.byref(bt), max_length, nat.ptr(out),
+        nat.check(L_.lako_fidt5_generate(ctypes.byref(m), ctypes.byref(bt), max_length, int(min_length), nat.ptr(out),
                                          ctypes.byref(out_len), nat.ptr(tf), nat.ptr(tl), nat.stream_ptr()),
                   "lako_fidt5_generate")
         return out[:, :out_len.value]

@@ -52,14 +52,19 @@ class FusedAdamW:
     """One pass over (p, m, v, g): g *= min(1, clip/(||g||+1e-6)); m,v update without bias correction;
     p -= lr*m/(sqrt(v)+eps); p -= lr*wd*p; bf16 copy of p refreshed in the same kernel.
 
-    Data parallel (world > 1), default mode "sharded": every gradient stage is REDUCE-SCATTERED while backward is still
-    running, each rank clips + updates only its 1/world slice of every stage (fp32 master, moments) and the refreshed
-    bf16 compute weights are ALL-GATHERED -- 6 B/parameter on the wire instead of the all-reduce's 8, and 1/world of
-    the optimizer's HBM traffic.  fp32 masters of foreign slices go stale; `sync_master_weights()` (called by
-    FiDT5.state_dict / save_pretrained) all-gathers them.  LAKO_DP_SHARD=0 selects the replicated all-reduce mode."""
+    Data parallel (world > 1).  Default = REPLICATED: the flat gradient is all-reduced (overlapped with backward) and
+    every rank runs the full update, so every rank's fp32 masters stay current and `model.state_dict()` /
+    `save_pretrained` on the main rank only (as the reference does, train_reader.py:107 `if opt.is_main`) just work.
+    `shard=True` (or LAKO_DP_SHARD=1) opts into SHARDED mode: every gradient stage is REDUCE-SCATTERED while backward is
+    still running, each rank clips + updates only its 1/world slice of every stage (fp32 master, moments) and the
+    refreshed bf16 compute weights are ALL-GATHERED -- 6 B/parameter on the wire instead of the all-reduce's 8, and
+    1/world of the optimizer's HBM traffic.  The price: fp32 masters of foreign slices go stale, and
+    `sync_master_weights()` -- a COLLECTIVE, also triggered by FiDT5.state_dict / save_pretrained and by anything that
+    re-casts the masters -- must then be reached by EVERY rank (call it, or state_dict(), on all ranks before a
+    main-rank-only save)."""
 
     def __init__(self, model, lr, weight_decay=0.0, betas=(0.9, 0.999), eps=1e-6, clip=1.0, schedule=None,
-                 process_group=None, allreduce_chunk_elems=64 * 1024 * 1024):
+                 process_group=None, allreduce_chunk_elems=64 * 1024 * 1024, shard=None):
         self.model = model
         self.lr, self.wd, self.betas, self.eps, self.clip = lr, weight_decay, betas, eps, clip
         self.schedule = schedule
@@ -79,7 +84,9 @@ class FusedAdamW:
             # range then runs on a communication stream while the rest of backward is still executing
             _, ranges = model.enable_grad_stage_events()
             self._comm_stream = torch.cuda.Stream()
-            if os.environ.get("LAKO_DP_SHARD", "1") != "0":
+            if shard is None:
+                shard = os.environ.get("LAKO_DP_SHARD", "0") == "1"
+            if shard:
                 self._plan = shard_plan(ranges, self.world(), dist.get_rank(self.group))
                 if self._plan is not None:
                     model._master_sync = self.sync_master_weights
@@ -277,3 +284,32 @@ def train_step(model, optimizer, input_ids, attention_mask, labels, group=None, 
         loss = loss.clone()
         dist.all_reduce(loss, op=dist.ReduceOp.SUM, group=group)
     return loss
+
+
+def gather_answers_and_scores(answers, scores, max_length, group=None):
+    """Inference side of the question-sharded layout: every rank decodes its own questions and only the
+    results travel -- `answers` int64 (B, <= max_length) as returned by FiDT5.generate (right-padded with pad id 0 to
+    `max_length` so that every rank contributes the same shape) and `scores` (B, n_context) as returned by
+    get_crossattention_scores.  Returns (answers (world*B, max_length), scores (world*B, n_context)) in rank order on
+    every rank; with one process the inputs are returned (answers padded).  The reference has no counterpart: it never
+    gathers predictions across ranks (test_reader.py writes per-rank files, src/util.py:248-273 reduces scalars only)."""
+    B, cols = answers.shape
+    if cols < max_length:
+        answers = torch.nn.functional.pad(answers, (0, max_length - cols))
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return answers, scores
+    world = dist.get_world_size(group)
+    dev = answers.device
+    scores = scores.to(dev)
+    out_a = torch.empty(world * B, max_length, dtype=answers.dtype, device=dev)
+    out_s = torch.empty(world * B, scores.shape[1], dtype=scores.dtype, device=dev)
+    if dist.get_backend(group) == "nccl":
+        dist.all_gather_into_tensor(out_a, answers.contiguous(), group=group)
+        dist.all_gather_into_tensor(out_s, scores.contiguous(), group=group)
+    else:
+        pa = [torch.empty_like(answers) for _ in range(world)]
+        ps = [torch.empty_like(scores) for _ in range(world)]
+        dist.all_gather(pa, answers.contiguous(), group=group)
+        dist.all_gather(ps, scores.contiguous(), group=group)
+        out_a, out_s = torch.cat(pa), torch.cat(ps)
+    return out_a, out_s

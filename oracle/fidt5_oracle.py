@@ -123,6 +123,17 @@ def init_state_dict(cfg: T5Dims, seed: int = 0, emb_std: float = 1.0, dtype=torc
     return sd
 
 
+def sd_to(sd, device):
+    """Copy of the state dict on `device` with the tying of the four embedding names preserved."""
+    moved, out = {}, {}
+    for k, v in sd.items():
+        key = v.data_ptr()
+        if key not in moved:
+            moved[key] = v.to(device)
+        out[k] = moved[key]
+    return out
+
+
 def perturb_norm_weights(sd, seed=1, scale=0.1):
     """Make layer-norm gains non-trivial so tests exercise them (init is all ones)."""
     g = torch.Generator().manual_seed(seed)
@@ -164,8 +175,8 @@ def bucket_table(bidirectional: bool, max_len: int, num_buckets: int = 32, max_d
 
 def compute_bias(table, qlen, klen, bidirectional, cfg: T5Dims, q_offset=0):
     """HF:modeling_t5.py:236-251 -> (1,H,qlen,klen)."""
-    ctx = torch.arange(qlen, dtype=torch.long)[:, None] + q_offset
-    mem = torch.arange(klen, dtype=torch.long)[None, :]
+    ctx = torch.arange(qlen, dtype=torch.long, device=table.device)[:, None] + q_offset
+    mem = torch.arange(klen, dtype=torch.long, device=table.device)[None, :]
     b = relative_position_bucket(mem - ctx, bidirectional, cfg.n_buckets, cfg.max_distance)
     return table.float()[b.to(table.device)].permute(2, 0, 1).unsqueeze(0)
 
@@ -249,11 +260,11 @@ def decoder_forward(sd, cfg: T5Dims, dec_ids, memory, mem_mask, cache=None, capt
     table = sd[f"{dec_prefix(0)}.0.SelfAttention.relative_attention_bias.weight"]
     total = past + T
     self_bias = compute_bias(table, T, total, False, cfg, q_offset=past).to(x.dtype)
-    qpos = torch.arange(T)[:, None] + past
-    kpos = torch.arange(total)[None, :]
-    causal = torch.zeros(T, total, dtype=x.dtype).masked_fill(kpos > qpos, NEG)
+    qpos = torch.arange(T, device=x.device)[:, None] + past
+    kpos = torch.arange(total, device=x.device)[None, :]
+    causal = torch.zeros(T, total, dtype=x.dtype, device=x.device).masked_fill(kpos > qpos, NEG)
     self_bias = self_bias + causal[None, None]
-    cross_bias = torch.zeros(mem_mask.shape, dtype=x.dtype).masked_fill(~mem_mask.bool(), NEG)[:, None, None, :]
+    cross_bias = torch.zeros(mem_mask.shape, dtype=x.dtype, device=x.device).masked_fill(~mem_mask.bool(), NEG)[:, None, None, :]
     for i in range(cfg.n_layers):
         p = dec_prefix(i)
         n = rmsnorm(x, sd[f"{p}.0.layer_norm.weight"], cfg.eps)
@@ -311,7 +322,7 @@ def fidt5_forward(sd, cfg: T5Dims, input_ids, attention_mask, labels):
 
 @torch.no_grad()
 def fidt5_generate(sd, cfg: T5Dims, input_ids, attention_mask, max_length, capture_scores=False,
-                   return_step_logits=False):
+                   return_step_logits=False, min_length=0):
     """Greedy decode as FiDT5.generate (src/model.py:54-60 -> HF greedy).
 
     Returns (ids (B,<=max_length) int64, score_storage list[Ld] of (B,H,1,M) or None[, logits list])."""
@@ -319,14 +330,18 @@ def fidt5_generate(sd, cfg: T5Dims, input_ids, attention_mask, max_length, captu
     B = input_ids.shape[0]
     cache = {"self": [None] * cfg.n_layers, "cross": [None] * cfg.n_layers, "len": 0}
     capture = [None] * cfg.n_layers if capture_scores else None
-    out = torch.zeros(B, 1, dtype=torch.long)
-    unfinished = torch.ones(B, dtype=torch.long)
+    dev = input_ids.device
+    out = torch.zeros(B, 1, dtype=torch.long, device=dev)
+    unfinished = torch.ones(B, dtype=torch.long, device=dev)
     step_logits = []
     while out.shape[1] < max_length:
         h = decoder_forward(sd, cfg, out[:, -1:], memory, mem_mask, cache=cache, capture=capture)
         logits = lm_logits(sd, cfg, h)[:, -1]
         if return_step_logits:
             step_logits.append(logits)
+        if out.shape[1] < min_length:   # HF MinLengthLogitsProcessor: no EOS while the decoder length is below min_length
+            logits = logits.clone()
+            logits[:, 1] = -float("inf")
         nxt = logits.argmax(-1)
         nxt = nxt * unfinished + 0 * (1 - unfinished)
         out = torch.cat([out, nxt[:, None]], dim=1)
