@@ -203,6 +203,28 @@ int lako_xattn_fwd(const void* q, const void* kv, const unsigned char* mask, voi
 int lako_xattn_bwd(const void* q, const void* kv, const unsigned char* mask, const void* out, const void* dout,
                    const float* lse, void* dkv, float* dq_f32, int B, int T, int M, int H, int ldq, int ldkv, int koff,
                    int voff, int ldo, void* stream);
+/* ---- KV-cached single-token decode (greedy generate, src/model.py:54-60 -> HF greedy search with use_cache) ----
+ * Few-row Linear: y[M][ldy] = epi(alpha * norm?(x) W[N][K]^T) for the M = batch rows of a decode step (any M; rows are
+ * processed 64 at a time).  x_f32 != NULL: x is the fp32 residual stream [M][K], RMS-normalised with gain ln_w / eps on
+ * the fly when ln_w != NULL (T5LayerNorm HF:55-68 fused as the prologue); else x_bf16 [M][ldx].
+ * epi: 0 bf16 store, 1 bf16 ReLU store, 2 fp32 store, 3 fp32 y += (residual add, HF:375,149). */
+int lako_smallm_linear(const float* x_f32, const void* x_bf16, int ldx, const float* ln_w, float eps, const void* W,
+                       void* y, int ldy, int M, int N, int K, int epi, float alpha, void* stream);
+/* cross_attention_forward (src/model.py:286-349) for ONE query token per question against K/V rows of the fused memory
+ * (kv row pitch ldkv, head h at column koff/voff + 64 h).  Packed memory: question b owns rows
+ * [cu[b*npsg], cu[(b+1)*npsg]) and tok_index maps a packed row to its index in the padded [B][M] score buffer;
+ * cu == NULL: padded rows [b*M, (b+1)*M) with the 0/1 key mask.  tok_score (may be NULL) += the pre-softmax scores of
+ * valid keys (summed over heads) when *step == 0 (step == NULL: always) -- the capture of src/model.py:327-329. */
+size_t lako_xattn_decode_workspace_bytes(int B, int H, int M);
+int lako_xattn_decode(const void* q, const void* kv, const unsigned char* mask, void* out, float* tok_score,
+                      const int* step, float* workspace, int B, int M, int H, int ldq, int ldkv, int koff, int voff,
+                      int ldo, const int* cu, int npsg, const int* tok_index, void* stream);
+/* decoder self-attention of the token at position pos (or *pos_dev when not NULL) against the KV cache
+ * [B][H][Tmax][64] (appends this step's k, v first); qkv bf16 [B][3*H*64], lut fp32 [H][2*Tmax-1] causal buckets */
+int lako_dself_step(const void* qkv, void* kcache, void* vcache, const float* lut, void* out, int B, int pos, int Tmax,
+                    int H, const int* pos_dev, void* stream);
+/* replay decode steps from a captured CUDA graph (default on; also env LAKO_DECODE_GRAPH=0) */
+void lako_set_decode_graph(int on);
 /* causal decoder self-attention HF:253-344,438-445 */
 int lako_dself_fwd(const void* qkv, const float* lut, void* out, float* probs, int B, int T, int H, void* stream);
 int lako_dself_bwd(const void* qkv, const void* dout, const float* probs, void* dqkv, float* dlut, int B, int T, int H,

@@ -118,4 +118,23 @@ int lako_dself_bwd(const void* qkv, const void* dout, const float* probs, void* 
   return dself_bwd(CBF(qkv), CBF(dout), probs, BF(dqkv), dlut, B, T, H, ST(stream));
 }
 
+int lako_smallm_linear(const float* x_f32, const void* x_bf16, int ldx, const float* ln_w, float eps, const void* W,
+                       void* y, int ldy, int M, int N, int K, int epi, float alpha, void* stream) {
+  ARCH_GUARD();
+  return smallm_linear(x_f32, CBF(x_bf16), ldx, ln_w, eps, CBF(W), y, ldy, M, N, K, epi, alpha, ST(stream));
+}
+size_t lako_xattn_decode_workspace_bytes(int B, int H, int M) { return xattn_decode_workspace_bytes(B, H, M); }
+int lako_xattn_decode(const void* q, const void* kv, const unsigned char* mask, void* out, float* tok_score,
+                      const int* step, float* workspace, int B, int M, int H, int ldq, int ldkv, int koff, int voff,
+                      int ldo, const int* cu, int npsg, const int* tok_index, void* stream) {
+  ARCH_GUARD();
+  return xattn_decode(CBF(q), CBF(kv), mask, BF(out), tok_score, step, workspace, B, M, H, ldq, ldkv, koff, voff, ldo,
+                      ST(stream), cu, npsg, tok_index);
+}
+int lako_dself_step(const void* qkv, void* kcache, void* vcache, const float* lut, void* out, int B, int pos, int Tmax,
+                    int H, const int* pos_dev, void* stream) {
+  ARCH_GUARD();
+  return dself_step(CBF(qkv), BF(kcache), BF(vcache), lut, BF(out), B, pos, Tmax, H, ST(stream), pos_dev);
+}
+
 }  // extern "C"

@@ -32,6 +32,8 @@ namespace lako {
 
 void set_last_error(const char* msg, const char* file, int line);
 void count_launch();
+void count_launches(long long n);  // kernels replayed from a captured graph / captured but not executed
+unsigned long long launch_count_value();
 bool pdl_enabled();
 
 // Optional per-category device timing (CUDA events on the launching stream), used by bench.py to report

@@ -276,10 +276,12 @@ __global__ void __launch_bounds__(64) dself_step_kernel(const __nv_bfloat16* __r
                                                         __nv_bfloat16* __restrict__ kcache,
                                                         __nv_bfloat16* __restrict__ vcache,
                                                         const float* __restrict__ lut, __nv_bfloat16* __restrict__ out,
-                                                        int pos, int Tmax, int H, int inner) {
+                                                        int pos, const int* __restrict__ pos_dev, int Tmax, int H,
+                                                        int inner) {
   pdl_launch_dependents();
   pdl_wait();
-  __shared__ float sQ[64], sS[256];
+  __shared__ float sQ[64], sS[1024];
+  if (pos_dev) pos = *pos_dev;  // step index kept on the device: one captured graph serves every decode step
   const int h = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
   const __nv_bfloat16* row = qkv + static_cast<size_t>(b) * 3 * inner + h * 64;
   __nv_bfloat16* kc = kcache + (static_cast<size_t>(b) * H + h) * Tmax * 64;
@@ -307,9 +309,10 @@ __global__ void __launch_bounds__(64) dself_step_kernel(const __nv_bfloat16* __r
 }
 
 int dself_step(const __nv_bfloat16* qkv, __nv_bfloat16* kcache, __nv_bfloat16* vcache, const float* lut,
-               __nv_bfloat16* out, int B, int pos, int Tmax, int H, cudaStream_t s) {
-  LAKO_REQUIRE(pos >= 0 && pos < Tmax && Tmax <= 256, LAKO_ERR_UNSUPPORTED);
-  launch_pdl(dself_step_kernel, dim3(dim3(H, B)), dim3(64), 0, s, qkv, kcache, vcache, lut, out, pos, Tmax, H, H * 64);
+               __nv_bfloat16* out, int B, int pos, int Tmax, int H, cudaStream_t s, const int* pos_dev) {
+  LAKO_REQUIRE(pos >= 0 && pos < Tmax && Tmax <= 1024, LAKO_ERR_UNSUPPORTED);
+  launch_pdl(dself_step_kernel, dim3(dim3(H, B)), dim3(64), 0, s, qkv, kcache, vcache, lut, out, pos, pos_dev, Tmax, H,
+             H * 64);
   LAKO_CHECK_LAUNCH();
   return LAKO_OK;
 }
@@ -319,12 +322,18 @@ int dself_step(const __nv_bfloat16* qkv, __nv_bfloat16* kcache, __nv_bfloat16* v
 __global__ void __launch_bounds__(256) greedy_pick_kernel(const float* __restrict__ logits, int V, int ld,
                                                           long long* __restrict__ out_ids, int out_ld, int step,
                                                           int* __restrict__ unfinished, int* __restrict__ n_unfinished,
-                                                          long long* __restrict__ next_ids, int ban_eos) {
+                                                          long long* __restrict__ next_ids, int ban_eos,
+                                                          int* __restrict__ step_dev, int* __restrict__ done_dev,
+                                                          int min_length) {
   pdl_launch_dependents();
   pdl_wait();
   __shared__ float s_v[8];
   __shared__ int s_i[8];
   const int b = blockIdx.x, tid = threadIdx.x;
+  if (step_dev) {  // device-resident step counter (decode step k writes output column k + 1)
+    step = *step_dev + 1;
+    ban_eos = step < min_length;
+  }
   const float* lr = logits + static_cast<size_t>(b) * ld;
   float best = -INFINITY;
   int bi = 0x7fffffff;
@@ -365,13 +374,21 @@ __global__ void __launch_bounds__(256) greedy_pick_kernel(const float* __restric
       unfinished[b] = 0;
       atomicSub(n_unfinished, 1);
     }
+    if (step_dev) {  // the last CTA to finish advances the counter (every CTA has read it by then)
+      __threadfence();
+      if (atomicAdd(done_dev, 1) == static_cast<int>(gridDim.x) - 1) {
+        *done_dev = 0;
+        *step_dev = step;
+      }
+    }
   }
 }
 
 int greedy_pick(const float* logits, int B, int V, int ld, long long* out_ids, int out_ld, int step, int* unfinished,
-                int* n_unfinished, long long* next_ids, cudaStream_t s, int ban_eos) {
+                int* n_unfinished, long long* next_ids, cudaStream_t s, int ban_eos, int* step_dev, int* done_dev,
+                int min_length) {
   launch_pdl(greedy_pick_kernel, dim3(B), dim3(256), 0, s, logits, V, ld, out_ids, out_ld, step, unfinished, n_unfinished, next_ids,
-             ban_eos);
+             ban_eos, step_dev, done_dev, min_length);
   LAKO_CHECK_LAUNCH();
   return LAKO_OK;
 }

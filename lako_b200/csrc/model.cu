@@ -599,9 +599,10 @@ namespace {
 struct GenWork {
   Work enc;  // encoder part (eval carve with T=1)
   bf16 *kc, *vc;  // [nl][B][H][Tmax][64]
-  float *lut_dec, *logits;
-  int *unfinished, *n_unf;
-  long long* next_ids;
+  float *lut_dec, *logits, *xdec_ws, *tok_first, *tok_last;
+  int *unfinished, *n_unf, *d_step, *d_done, *cu_copy;
+  unsigned char* mask_copy;
+  long long *next_ids, *out_ids;
   size_t bytes;
 };
 void carve_gen(const lako_dims& dm, int B, int N, int L, int Tmax, void* base, GenWork& gw) {
@@ -615,11 +616,19 @@ void carve_gen(const lako_dims& dm, int B, int N, int L, int Tmax, void* base, G
   gw.logits = b.take<float>(static_cast<size_t>(B) * dm.vocab);
   gw.unfinished = b.take<int>(B);
   gw.n_unf = b.take<int>(1);
+  gw.d_step = b.take<int>(1);
+  gw.d_done = b.take<int>(1);
   gw.next_ids = b.take<long long>(B);
+  gw.out_ids = b.take<long long>(static_cast<size_t>(B) * Tmax);
+  gw.cu_copy = b.take<int>(static_cast<size_t>(B) * N + 1);
+  gw.mask_copy = b.take<unsigned char>(static_cast<size_t>(B) * N * L);
+  gw.tok_first = b.take<float>(static_cast<size_t>(B) * N * L);
+  gw.tok_last = b.take<float>(static_cast<size_t>(B) * N * L);
+  gw.xdec_ws = b.take<float>(xattn_decode_workspace_bytes(B, dm.n_heads, N * L) / sizeof(float));
   gw.bytes = (b.off + 255) & ~size_t(255);
 }
-__global__ void gen_init_kernel(int* unfinished, int* n_unf, long long* next_ids, long long* out_ids, int B,
-                                int out_ld) {
+__global__ void gen_init_kernel(int* unfinished, int* n_unf, int* d_step, int* d_done, long long* next_ids,
+                                long long* out_ids, int B, int out_ld) {
   pdl_launch_dependents();
   pdl_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -628,9 +637,92 @@ __global__ void gen_init_kernel(int* unfinished, int* n_unf, long long* next_ids
     next_ids[i] = 0;  // decoder_start_token_id = pad = 0
     for (int t = 0; t < out_ld; ++t) out_ids[static_cast<size_t>(i) * out_ld + t] = 0;
   }
-  if (i == 0) *n_unf = B;
+  if (i == 0) {
+    *n_unf = B;
+    *d_step = 0;
+    *d_done = 0;
+  }
+}
+
+struct DecodeCtx {
+  const Ptrs* p;
+  GenWork* gw;
+  int B, N, max_length, min_length;
+  bool packed, capture;
+};
+
+// One cached decoder pass over the last generated token of every question (HF T5Block with use_cache, HF:411-498):
+// 10 launches per layer -- fused RMSNorm -> projection GEMVs, KV-cached self-attention, split cross-attention over the
+// packed memory (+ step-0 score capture), residual-add epilogues -- then the tied LM head and the greedy pick.  Every
+// step-dependent quantity (cache position, output column, EOS ban, "is this step 0") is read from the device counter
+// d_step, so the enqueued work is identical for every step and can be replayed from a captured CUDA graph.
+int enqueue_decode_step(const DecodeCtx& c, cudaStream_t s) {
+  const Ptrs& p = *c.p;
+  GenWork& gw = *c.gw;
+  Work& w = gw.enc;
+  const int d = p.d, inner = p.inner, ff = p.ff, nl = p.nl, B = c.B, H = p.H;
+  const int first_half = (nl + 1) / 2;
+  const size_t cache_l = static_cast<size_t>(B) * H * c.max_length * 64;
+  const int* cu = c.packed ? gw.cu_copy : nullptr;
+  const unsigned char* xmask = c.packed ? nullptr : gw.mask_copy;
+  DecLayerAct& a = w.dec[0];
+  float* Y = w.Y[0];
+  RC(embed_gather(gw.next_ids, p.wf + p.lo.shared, Y, B, d, p.V, s));
+  for (int l = 0; l < nl; ++l) {
+    RC(smallm_linear(Y, nullptr, 0, p.wf + p.lo.dec_ln0[l], p.eps, p.wb + p.lo.dec_qkv[l], a.qkv, 3 * inner, B, 3 * inner,
+                     d, SL_BF16, 1.f, s));
+    RC(dself_step(a.qkv, gw.kc + l * cache_l, gw.vc + l * cache_l, gw.lut_dec, a.ao, B, 0, c.max_length, H, s, gw.d_step));
+    RC(smallm_linear(nullptr, a.ao, inner, nullptr, 0.f, p.wb + p.lo.dec_o[l], Y, d, B, d, inner, SL_F32_ADD, 1.f, s));
+    RC(smallm_linear(Y, nullptr, 0, p.wf + p.lo.dec_ln1[l], p.eps, p.wb + p.lo.dec_xq[l], a.q, inner, B, inner, d,
+                     SL_BF16, 1.f, s));
+    float* ts = c.capture ? ((l < first_half) ? gw.tok_first : gw.tok_last) : nullptr;
+    RC(xattn_decode(a.q, w.kv_all, xmask, a.xo, ts, gw.d_step, gw.xdec_ws, B, w.M, H, inner, nl * 2 * inner,
+                    l * 2 * inner, l * 2 * inner + inner, inner, s, cu, c.N, c.packed ? w.tok_index : nullptr));
+    RC(smallm_linear(nullptr, a.xo, inner, nullptr, 0.f, p.wb + p.lo.dec_xo[l], Y, d, B, d, inner, SL_F32_ADD, 1.f, s));
+    RC(smallm_linear(Y, nullptr, 0, p.wf + p.lo.dec_ln2[l], p.eps, p.wb + p.lo.dec_wi[l], a.h, ff, B, ff, d, SL_BF16_RELU,
+                     1.f, s));
+    RC(smallm_linear(nullptr, a.h, ff, nullptr, 0.f, p.wb + p.lo.dec_wo[l], Y, d, B, d, ff, SL_F32_ADD, 1.f, s));
+  }
+  // final norm + tied LM head: logits = (norm(h) * d^-0.5) E^T  (HF:1107-1110), fp32
+  RC(smallm_linear(Y, nullptr, 0, p.wf + p.lo.dec_final_ln, p.eps, p.wb + p.lo.shared, gw.logits, p.V, B, p.V, d, SL_F32,
+                   1.0f / sqrtf(static_cast<float>(d)), s));
+  RC(greedy_pick(gw.logits, B, p.V, p.V, gw.out_ids, c.max_length, 0, gw.unfinished, gw.n_unf, gw.next_ids, s, 0,
+                 gw.d_step, gw.d_done, c.min_length));
+  return LAKO_OK;
+}
+
+// One cached cudaGraphExec_t per host thread: a decode step replayed max_length - 2 times per call and unchanged
+// between calls as long as the buffers it was captured on are the same (the Python side keeps one workspace per shape).
+struct GraphKey {
+  const void *wf, *wb, *ws;
+  int d, H, ff, nl, V, B, N, L, max_length, min_length, packed, capture, precision;
+  bool operator==(const GraphKey& o) const {
+    return wf == o.wf && wb == o.wb && ws == o.ws && d == o.d && H == o.H && ff == o.ff && nl == o.nl && V == o.V &&
+           B == o.B && N == o.N && L == o.L && max_length == o.max_length && min_length == o.min_length &&
+           packed == o.packed && capture == o.capture && precision == o.precision;
+  }
+};
+struct DecodeGraphCache {
+  bool valid = false, broken = false;
+  GraphKey key{};
+  cudaGraphExec_t exec = nullptr;
+  long long kernels = 0;  // kernel nodes of the captured step
+  int* h_unf = nullptr;  // pinned: n_unfinished after every step
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+};
+thread_local DecodeGraphCache g_dgraph;
+
+int g_decode_graph = -1;
+bool decode_graph_enabled() {
+  if (g_decode_graph < 0) {
+    const char* e = getenv("LAKO_DECODE_GRAPH");
+    g_decode_graph = (e && e[0] == '0') ? 0 : 1;
+  }
+  return g_decode_graph != 0;
 }
 }  // namespace
+
+extern "C" void lako_set_decode_graph(int on) { g_decode_graph = on ? 1 : 0; }
 
 extern "C" size_t lako_fidt5_generate_workspace_bytes(const lako_dims* dm, int B, int N, int L, int max_length) {
   GenWork gw;
@@ -639,9 +731,13 @@ extern "C" size_t lako_fidt5_generate_workspace_bytes(const lako_dims* dm, int B
 }
 
 // out_ids int64 [B][max_length] (device), *out_len (host) = number of generated columns incl. the start
-// token.  tok_score_first/last fp32 [B][N*L] (device, pre-zeroed by the caller, may be null):
-// sum over heads and over the first ceil(nl/2) / the remaining decoder layers of the masked step-0
-// pre-softmax cross-attention scores.
+// token.  tok_score_first/last fp32 [B][N*L] (device, may be null): sum over heads and over the first
+// ceil(nl/2) / the remaining decoder layers of the masked step-0 pre-softmax cross-attention scores.
+// min_length: HF's MinLengthLogitsProcessor (EOS cannot be produced while the decoder length is below it); the
+// reference never sets it (0), bench.py uses it to time full-length decodes with random-init weights.
+// Host synchronisation: none per token.  The count of unfinished rows is copied to pinned host memory after every step
+// and examined two steps later (HF's early stop, pipelined), and the stream is synchronised once at the end because
+// *out_len is a host value.
 extern "C" int lako_fidt5_generate(const lako_fidt5* m, const lako_batch* bt, int max_length, int min_length,
                                    int64_t* out_ids, int* out_len, float* tok_score_first, float* tok_score_last,
                                    void* stream) {
@@ -650,59 +746,111 @@ extern "C" int lako_fidt5_generate(const lako_fidt5* m, const lako_batch* bt, in
   Ptrs p;
   RC(make_ptrs(m, p));
   LAKO_REQUIRE(bt && bt->ids && bt->mask && bt->workspace && out_ids && out_len, LAKO_ERR_BAD_ARG);
-  LAKO_REQUIRE(max_length >= 2 && max_length <= 256 && bt->L <= 256, LAKO_ERR_UNSUPPORTED);
+  LAKO_REQUIRE(max_length >= 2 && max_length <= 1024 && bt->L <= 256, LAKO_ERR_UNSUPPORTED);
+  LAKO_REQUIRE((tok_score_first == nullptr) == (tok_score_last == nullptr), LAKO_ERR_BAD_ARG);
+  LAKO_REQUIRE(bt->precision == 0, LAKO_ERR_UNSUPPORTED);
   GenWork gw;
   carve_gen(m->dims, bt->B, bt->N, bt->L, max_length, bt->workspace, gw);
   LAKO_REQUIRE(gw.bytes <= bt->workspace_bytes, LAKO_ERR_WORKSPACE);
   Work& w = gw.enc;
-  const int d = p.d, inner = p.inner, ff = p.ff, nl = p.nl, B = bt->B, H = p.H;
+  const int B = bt->B, H = p.H;
   RC(set_packing(w, bt, s));
-  const unsigned char* xmask = w.cu ? nullptr : bt->mask;
+  const bool packed = w.cu != nullptr, capture = tok_score_first != nullptr;
+  const size_t ntok = static_cast<size_t>(B) * bt->N * bt->L;
+  if (packed)
+    cudaMemcpyAsync(gw.cu_copy, bt->cu_seqlens, sizeof(int) * (static_cast<size_t>(B) * bt->N + 1), cudaMemcpyDeviceToDevice, s);
+  else
+    cudaMemcpyAsync(gw.mask_copy, bt->mask, ntok, cudaMemcpyDeviceToDevice, s);
+  if (capture) {
+    cudaMemsetAsync(gw.tok_first, 0, sizeof(float) * ntok, s);
+    cudaMemsetAsync(gw.tok_last, 0, sizeof(float) * ntok, s);
+  }
   RC(encode(p, m, w, reinterpret_cast<const long long*>(bt->ids), bt->mask, false, s, Dropper{0, 0, 0.f}));
   RC(build_bias_lut(p.wf + p.lo.dec_relbias, m->dec_buckets, gw.lut_dec, H, max_length, m->bucket_center, s));
-  launch_pdl(gen_init_kernel, dim3((B + 127) / 128), dim3(128), 0, s, gw.unfinished, gw.n_unf, gw.next_ids,
-                                                   reinterpret_cast<long long*>(out_ids), B, max_length);
+  launch_pdl(gen_init_kernel, dim3((B + 127) / 128), dim3(128), 0, s, gw.unfinished, gw.n_unf, gw.d_step, gw.d_done,
+             gw.next_ids, gw.out_ids, B, max_length);
   LAKO_CHECK_LAUNCH();
-  const float alpha = 1.0f / sqrtf(static_cast<float>(d));
-  const int first_half = (nl + 1) / 2;
-  const size_t cache_l = static_cast<size_t>(B) * H * max_length * 64;
-  DecLayerAct& a = w.dec[0];
-  int len = 1;
-  for (int step = 0; step + 1 < max_length; ++step) {
-    RC(embed_gather(gw.next_ids, p.wf + p.lo.shared, w.Y[0], B, d, p.V, s));
-    for (int l = 0; l < nl; ++l) {
-      if (l == 0)
-        RC(rmsnorm_fwd(w.Y[0], nullptr, nullptr, p.wf + p.lo.dec_ln0[l], a.n_s, nullptr, B, d, p.eps, 1.f, s));
-      else
-        RC(rmsnorm_fwd(w.Y[0], w.delta_dec, w.Y[0], p.wf + p.lo.dec_ln0[l], a.n_s, nullptr, B, d, p.eps, 1.f, s));
-      RC(lin_fwd(a.n_s, p.wb + p.lo.dec_qkv[l], a.qkv, B, 3 * inner, d, EPI_BF16, 1.f, s));
-      RC(dself_step(a.qkv, gw.kc + l * cache_l, gw.vc + l * cache_l, gw.lut_dec, a.ao, B, step, max_length, H, s));
-      RC(lin_fwd(a.ao, p.wb + p.lo.dec_o[l], w.delta_dec, B, d, inner, EPI_BF16, 1.f, s));
-      RC(rmsnorm_fwd(w.Y[0], w.delta_dec, w.Y[0], p.wf + p.lo.dec_ln1[l], a.n_c, nullptr, B, d, p.eps, 1.f, s));
-      RC(lin_fwd(a.n_c, p.wb + p.lo.dec_xq[l], a.q, B, inner, d, EPI_BF16, 1.f, s));
-      float* ts = nullptr;
-      if (step == 0) ts = (l < first_half) ? tok_score_first : tok_score_last;
-      RC(xattn_fwd(a.q, w.kv_all, xmask, a.xo, nullptr, ts, w.xattn_ws, B, 1, w.M, H, inner, nl * 2 * inner,
-                   l * 2 * inner, l * 2 * inner + inner, inner, s, DropSpec{}, w.cu, bt->N, w.cu ? w.tok_index : nullptr));
-      RC(lin_fwd(a.xo, p.wb + p.lo.dec_xo[l], w.delta_dec, B, d, inner, EPI_BF16, 1.f, s));
-      RC(rmsnorm_fwd(w.Y[0], w.delta_dec, w.Y[0], p.wf + p.lo.dec_ln2[l], a.n_f, nullptr, B, d, p.eps, 1.f, s));
-      RC(lin_fwd(a.n_f, p.wb + p.lo.dec_wi[l], a.h, B, ff, d, EPI_BF16_RELU, 1.f, s));
-      RC(lin_fwd(a.h, p.wb + p.lo.dec_wo[l], w.delta_dec, B, d, ff, EPI_BF16, 1.f, s));
+
+  DecodeGraphCache& gc = g_dgraph;
+  if (!gc.h_unf) {
+    if (cudaHostAlloc(reinterpret_cast<void**>(&gc.h_unf), sizeof(int) * 1024, cudaHostAllocDefault) != cudaSuccess) {
+      set_last_error("cudaHostAlloc failed", __FILE__, __LINE__);
+      return LAKO_ERR_DRIVER;
     }
-    RC(rmsnorm_fwd(w.Y[0], w.delta_dec, w.Y[0], p.wf + p.lo.dec_final_ln, w.hn, nullptr, B, d, p.eps, 1.f, s));
-    RC(lin_fwd(w.hn, p.wb + p.lo.shared, gw.logits, B, p.V, d, EPI_F32, alpha, s));
-    RC(greedy_pick(gw.logits, B, p.V, p.V, reinterpret_cast<long long*>(out_ids), max_length, step + 1, gw.unfinished,
-                   gw.n_unf, gw.next_ids, s, (step + 1 < min_length) ? 1 : 0));
-    len = step + 2;
-    int n_unf = 0;
-    cudaMemcpyAsync(&n_unf, gw.n_unf, sizeof(int), cudaMemcpyDeviceToHost, s);
-    cudaError_t e = cudaStreamSynchronize(s);
-    if (e != cudaSuccess) {
-      set_last_error(cudaGetErrorString(e), __FILE__, __LINE__);
-      return LAKO_ERR_LAUNCH;
-    }
-    if (n_unf == 0) break;
+    for (auto& e : gc.ev) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
   }
-  *out_len = len;
+  DecodeCtx ctx{&p, &gw, B, bt->N, max_length, min_length, packed, capture};
+  const GraphKey key{p.wf, p.wb, bt->workspace, p.d, p.H, p.ff, p.nl, p.V, B, bt->N, bt->L, max_length, min_length,
+                     packed ? 1 : 0, capture ? 1 : 0, bt->precision};
+  const bool want_graph = decode_graph_enabled() && !gc.broken && !prof_enabled();
+  const int nsteps = max_length - 1;
+  constexpr int LAG = 2;
+  int stop_at = -1;  // first step after which no row is unfinished
+  for (int step = 0; step < nsteps; ++step) {
+    bool launched = false;
+    if (want_graph && step >= 1) {
+      if (!(gc.valid && gc.key == key)) {
+        // (re)capture: step 0 ran directly, so every lazily configured kernel attribute is set by now
+        if (gc.exec) cudaGraphExecDestroy(gc.exec);
+        gc.exec = nullptr;
+        gc.valid = false;
+        cudaGraph_t graph = nullptr;
+        if (cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+          const unsigned long long n0 = launch_count_value();
+          const int rc = enqueue_decode_step(ctx, s);
+          gc.kernels = static_cast<long long>(launch_count_value() - n0);
+          count_launches(-gc.kernels);  // captured, not executed
+          const cudaError_t ee = cudaStreamEndCapture(s, &graph);
+          if (rc == LAKO_OK && ee == cudaSuccess && graph &&
+              cudaGraphInstantiate(&gc.exec, graph, 0) == cudaSuccess) {
+            gc.valid = true;
+            gc.key = key;
+          }
+          if (graph) cudaGraphDestroy(graph);
+        }
+        if (!gc.valid) {
+          cudaGetLastError();
+          gc.broken = true;  // this driver cannot capture the step: plain stream launches from now on
+        }
+      }
+      if (gc.valid) {
+        if (cudaGraphLaunch(gc.exec, s) != cudaSuccess) {
+          set_last_error("cudaGraphLaunch failed", __FILE__, __LINE__);
+          return LAKO_ERR_LAUNCH;
+        }
+        count_launches(gc.kernels);
+        launched = true;
+      }
+    }
+    if (!launched) RC(enqueue_decode_step(ctx, s));
+    cudaMemcpyAsync(&gc.h_unf[step], gw.n_unf, sizeof(int), cudaMemcpyDeviceToHost, s);
+    cudaEventRecord(gc.ev[step & 3], s);
+    if (step >= LAG) {
+      cudaEventSynchronize(gc.ev[(step - LAG) & 3]);
+      if (gc.h_unf[step - LAG] == 0) {
+        stop_at = step - LAG;
+        break;
+      }
+    }
+  }
+  cudaError_t e = cudaStreamSynchronize(s);
+  if (e != cudaSuccess) {
+    set_last_error(cudaGetErrorString(e), __FILE__, __LINE__);
+    return LAKO_ERR_LAUNCH;
+  }
+  if (stop_at < 0)
+    for (int step = 0; step < nsteps; ++step)
+      if (gc.h_unf[step] == 0) {
+        stop_at = step;
+        break;
+      }
+  // columns: start token + one per executed step up to and including the step that finished the last row; steps
+  // launched beyond it only wrote pad ids (every row was finished), exactly what HF's early stop leaves out
+  *out_len = (stop_at >= 0) ? stop_at + 2 : max_length;
+  cudaMemcpyAsync(out_ids, gw.out_ids, sizeof(long long) * B * max_length, cudaMemcpyDeviceToDevice, s);
+  if (capture) {
+    cudaMemcpyAsync(tok_score_first, gw.tok_first, sizeof(float) * ntok, cudaMemcpyDeviceToDevice, s);
+    cudaMemcpyAsync(tok_score_last, gw.tok_last, sizeof(float) * ntok, cudaMemcpyDeviceToDevice, s);
+  }
   return LAKO_OK;
 }

@@ -77,8 +77,20 @@ int dself_fwd(const __nv_bfloat16* qkv, const float* lut, __nv_bfloat16* out, fl
 int dself_bwd(const __nv_bfloat16* qkv, const __nv_bfloat16* dout, const float* probs, __nv_bfloat16* dqkv, float* dlut,
               int B, int T, int H, cudaStream_t s, DropSpec drop = DropSpec{});
 int dself_step(const __nv_bfloat16* qkv, __nv_bfloat16* kcache, __nv_bfloat16* vcache, const float* lut,
-               __nv_bfloat16* out, int B, int pos, int Tmax, int H, cudaStream_t s);
+               __nv_bfloat16* out, int B, int pos, int Tmax, int H, cudaStream_t s, const int* pos_dev = nullptr);
 int greedy_pick(const float* logits, int B, int V, int ld, long long* out_ids, int out_ld, int step, int* unfinished,
-                int* n_unfinished, long long* next_ids, cudaStream_t s, int ban_eos = 0);
+                int* n_unfinished, long long* next_ids, cudaStream_t s, int ban_eos = 0, int* step_dev = nullptr,
+                int* done_dev = nullptr, int min_length = 0);
+
+// decode.cu
+int smallm_linear(const float* x_f32, const __nv_bfloat16* x_b16, int ldx, const float* ln_w, float eps,
+                  const __nv_bfloat16* W, void* y, int ldy, int M, int N, int K, int epi, float alpha, cudaStream_t s);
+enum : int { SL_BF16 = 0, SL_BF16_RELU = 1, SL_F32 = 2, SL_F32_ADD = 3 };
+size_t xattn_decode_workspace_bytes(int B, int H, int M);
+int xattn_decode(const __nv_bfloat16* q, const __nv_bfloat16* kv, const unsigned char* mask, __nv_bfloat16* out,
+                 float* tok_score, const int* step, float* workspace, int B, int M, int H, int ldq, int ldkv, int koff,
+                 int voff, int ldo, cudaStream_t s, const int* cu = nullptr, int npsg = 1,
+                 const int* tok_index = nullptr);
+bool prof_enabled();
 
 }  // namespace lako

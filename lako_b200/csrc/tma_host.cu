@@ -30,6 +30,8 @@ bool pdl_enabled() {
 }
 static unsigned long long g_launches = 0;
 void count_launch() { ++g_launches; }
+void count_launches(long long n) { g_launches += n; }
+unsigned long long launch_count_value() { return g_launches; }
 
 // ---------------------------------------------------------------- profiling scopes
 struct ProfRec {
@@ -39,6 +41,7 @@ struct ProfRec {
   cudaStream_t stream;
 };
 static bool g_prof_on = false;
+bool prof_enabled() { return g_prof_on; }
 static std::vector<ProfRec*> g_prof_recs;
 static std::vector<ProfRec*> g_prof_pool;
 
