@@ -182,6 +182,14 @@ size_t lako_fidt5_generate_workspace_bytes(const lako_dims* dims, int B, int N, 
 int lako_fidt5_generate(const lako_fidt5* m, const lako_batch* b, int max_length, int min_length, int64_t* out_ids,
                         int* out_len, float* tok_score_first, float* tok_score_last, void* stream);
 
+/* ---- per-fact segmentation of the step-0 token scores: src/model.py:166-203 (+ test_reader.py:76 softmax) --------
+ * tok_a (+ tok_b when not NULL) fp32 [B][N*L] as produced by lako_fidt5_generate; ids1 int64 [B][ld_ids] = token ids
+ * of passage 1; scores are read from passage `score_passage` ((N+1)/2 reproduces torch.chunk(.., 2, dim=1)[1][:, 0]).
+ * out float64 [B][n_context]; style 0 mean, 1 max, 2 "21mean"; missing facts -5; all / divisor; softmax != 0: softmax over
+ * the n_context entries of each row. */
+int lako_fact_scores(const float* tok_a, const float* tok_b, const int64_t* ids1, int ld_ids, double* out, int B, int N,
+                     int L, int score_passage, int n_context, int style, double divisor, int softmax, void* stream);
+
 /* ---- attention kernels (unit-test entry points; the model calls them internally) --------------- */
 int lako_build_bias_lut(const float* table, const int* buckets, float* lut, int H, int L, int bucket_center,
                         void* stream);

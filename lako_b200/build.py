@@ -61,8 +61,11 @@ def build(force=False, verbose=False):
                     sys.stderr.write(f"[{os.path.basename(src)}] {line}\n")
     if failed:
         raise RuntimeError("nvcc compilation failed")
-    cmd = [nvcc, "-shared", "-arch=sm_100a", "-o", LIB_PATH] + objs + ["-lcudart"]
+    # link beside the target and rename: a concurrent reader (a gpurun snapshot, another process) never sees a partial .so
+    tmp = LIB_PATH + ".tmp"
+    cmd = [nvcc, "-shared", "-arch=sm_100a", "-o", tmp] + objs + ["-lcudart"]
     subprocess.check_call(cmd)
+    os.replace(tmp, LIB_PATH)
     return LIB_PATH
 
 

@@ -680,50 +680,34 @@ class FiDT5(nn.Module):
             return self._tok_last, (nl - (nl + 1) // 2) * H
         return self._tok_first + self._tok_last, nl * H
 
-    @staticmethod
-    def find_index(fact_list, start):
-        try:
-            return fact_list.index(5, start)
-        except ValueError:
-            return -1
+    SCORE_STYLES = {"mean": 0, "max": 1, "21mean": 2}
 
-    @staticmethod
-    def get_attention_score(fact_score_list, start, end, style):
-        if style == "mean":
-            return sum(fact_score_list[start:end]) / (end - start)
-        elif style == "max":
-            return max(fact_score_list[start:end])
-        elif style == "21mean":
-            num = max(int((end - start + 1) / 2), 1)
-            return sum(heapq.nlargest(num, fact_score_list[start:end])) / num
-
-    def get_crossattention_scores(self, opt, context_ids, tokenizer, context_mask):
-        """model.py:143-204 on the fused token-score tensor (same argument list, same float64 CPU result)."""
+    def get_crossattention_scores(self, opt, context_ids, tokenizer, context_mask, softmax=False):
+        """model.py:143-204 (same argument list, same float64 CPU (B, opt.n_context) result) on the fused token-score
+        tensor.  The per-example fact segmentation of passage 1 (split on token id 5 from index 2, mean / max / 21mean,
+        -5 fillers, / (layers * heads)) runs in ONE kernel (lako_fact_scores) instead of the reference's Python loop over
+        a (B, N, L) device->host copy: what crosses the bus is the (B, L) ids of passage 1 in and the (B, n_context)
+        result out.  softmax=True additionally applies test_reader.py:76's torch.softmax(scores, dim=-1)."""
         assert opt.stream == 2
-        fact_num = opt.n_context
+        if opt.attention_score_style not in self.SCORE_STYLES:
+            raise ValueError(f"attention_score_style must be one of {sorted(self.SCORE_STYLES)}")
         bsz, n_passages, L = context_mask.shape
-        tok, div = self.token_scores(opt.use_last_half_layer_attention == "yes")
-        tok = tok.view(bsz, n_passages, L)
-        _, fact_scores = torch.chunk(tok, 2, dim=1)
-        fact_scores = fact_scores[:, 0].cpu().numpy()
-        ids_cpu = context_ids[:, 1].cpu().numpy()
-        out = []
-        for b in range(bsz):
-            fact_list = ids_cpu[b].tolist()
-            sc = fact_scores[b].tolist()
-            res, start = [], 2
-            for _ in range(fact_num):
-                end = self.find_index(fact_list, start) + 1
-                if end == 0:
-                    break
-                res.append(self.get_attention_score(sc, start, end, opt.attention_score_style))
-                start = end
-            if len(res) < fact_num and fact_list[-1] != 0:
-                end = len(fact_list)
-                if end > start:
-                    res.append(self.get_attention_score(sc, start, end, opt.attention_score_style))
-            while len(res) < fact_num:
-                res.append(-5)
-            assert len(res) == fact_num
-            out.append(np.array(res))
-        return torch.from_numpy(np.array(out)) / div
+        assert n_passages >= 2, "the score pass needs the fact passage (stream 2: passage 1)"
+        if self._tok_first is None:
+            raise nat.LakoError("no scores stored: call overwrite_forward_crossattention() and generate() first")
+        nl, H = self.config.num_layers, self.config.num_heads
+        if opt.use_last_half_layer_attention == "yes":
+            a, b2, div = self._tok_last, None, (nl - (nl + 1) // 2) * H
+        else:
+            a, b2, div = self._tok_first, self._tok_last, nl * H
+        dev = a.device
+        ids1 = context_ids[:, 1].to(dev, non_blocking=True).contiguous()
+        out = torch.empty(bsz, int(opt.n_context), dtype=torch.float64, device=dev)
+        # torch.chunk(scores, 2, dim=1)[1][:, 0]: the first passage of the second half (model.py:166,175)
+        nat.check(nat.lib().lako_fact_scores(nat.ptr(a), nat.ptr(b2), nat.ptr(ids1), ctypes.c_int(L), nat.ptr(out),
+                                             ctypes.c_int(bsz), ctypes.c_int(n_passages), ctypes.c_int(L),
+                                             ctypes.c_int((n_passages + 1) // 2), ctypes.c_int(int(opt.n_context)),
+                                             ctypes.c_int(self.SCORE_STYLES[opt.attention_score_style]),
+                                             ctypes.c_double(float(div)), ctypes.c_int(int(bool(softmax))),
+                                             nat.stream_ptr()), "lako_fact_scores")
+        return out.cpu()

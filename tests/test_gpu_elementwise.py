@@ -120,3 +120,51 @@ def test_adamw_clip_and_cast():
     torch.cuda.synchronize()
     assert torch.allclose(p.cpu(), p_ref, atol=1e-6, rtol=1e-5)
     assert torch.allclose(wb.float().cpu(), p_ref, atol=2e-2, rtol=1e-2)
+
+
+@pytest.mark.parametrize("style", ["mean", "max", "21mean"])
+@pytest.mark.parametrize("N,L,n_context", [(2, 64, 4), (2, 130, 10), (20, 250, 10), (3, 40, 50), (2, 7, 3)])
+def test_fact_scores_kernel_bit_exact_vs_oracle_host_loop(style, N, L, n_context):
+    """lako_fact_scores vs the oracle's restatement of the reference's Python loop (src/model.py:166-203) on the SAME
+    token scores: segment boundaries, counts, -5 fillers and the float64 arithmetic order are identical, so the
+    results must be equal to the last bit."""
+    import ctypes
+    from oracle import fidt5_oracle as O
+    from lako_b200 import _native as nat
+    g = torch.Generator().manual_seed(N * 1000 + L + n_context)
+    B = 9
+    tok = torch.randn(B, N, L, generator=g)
+    ids = torch.randint(6, 100, (B, N, L), generator=g)
+    ids[:, 1, 0], ids[:, 1, 1] = 6, 10
+    for b in range(B):
+        kind = b % 5
+        if kind == 0:      # regular facts, padded tail
+            pos = torch.randperm(L - 3, generator=g)[: max(1, L // 9)] + 2
+            ids[b, 1, pos] = 5
+            ids[b, 1, int(pos.max()) + 1:] = 0
+        elif kind == 1:    # unterminated last fact, no padding
+            pos = torch.randperm(L - 3, generator=g)[: max(1, L // 12)] + 2
+            ids[b, 1, pos] = 5
+            ids[b, 1, -1] = 77
+        elif kind == 2:    # no separator at all
+            pass
+        elif kind == 3:    # separators back to back (one-token facts) and one at the very end
+            ids[b, 1, 2:min(L, 8)] = 5
+            ids[b, 1, -1] = 5
+        else:              # all padding after the prefix
+            ids[b, 1, 2:] = 0
+    half = (N + 1) // 2
+    ref = O.fact_scores_from_token_scores(tok, ids, n_context, style, 24.0)
+    out = torch.empty(B, n_context, dtype=torch.float64, device="cuda")
+    tok_d, ids1 = tok.cuda().contiguous(), ids[:, 1].cuda().contiguous()
+    nat.check(nat.lib().lako_fact_scores(nat.ptr(tok_d), None, nat.ptr(ids1), ctypes.c_int(L), nat.ptr(out), ctypes.c_int(B),
+                                         ctypes.c_int(N), ctypes.c_int(L), ctypes.c_int(half), ctypes.c_int(n_context),
+                                         ctypes.c_int({"mean": 0, "max": 1, "21mean": 2}[style]), ctypes.c_double(24.0),
+                                         ctypes.c_int(0), nat.stream_ptr()))
+    assert torch.equal(out.cpu(), ref), (out.cpu() - ref).abs().max()
+    sm = torch.empty_like(out)
+    nat.check(nat.lib().lako_fact_scores(nat.ptr(tok_d), None, nat.ptr(ids1), ctypes.c_int(L), nat.ptr(sm), ctypes.c_int(B),
+                                         ctypes.c_int(N), ctypes.c_int(L), ctypes.c_int(half), ctypes.c_int(n_context),
+                                         ctypes.c_int({"mean": 0, "max": 1, "21mean": 2}[style]), ctypes.c_double(24.0),
+                                         ctypes.c_int(1), nat.stream_ptr()))
+    assert torch.allclose(sm.cpu(), torch.softmax(ref, dim=-1), atol=1e-14, rtol=1e-12)
