@@ -78,6 +78,28 @@ int lako_count_valid(const int64_t* labels, int n, float* stats, void* stream);
 int lako_ce_fwd_bwd(const float* logits, const int64_t* labels, float* stats, float* row_loss, void* dlogits_bf16,
                     int rows, int V, int ld, int ld_d, void* stream);
 
+/* ---- precision = fp32: 3xTF32-split tensor-core GEMM (the reference computes in plain fp32, train_reader.py:67) ----
+ * hi[i] = x[i] with the low 13 mantissa bits cleared, lo[i] = the same truncation of x[i] - hi[i]. */
+int lako_split_tf32(const float* x, float* hi, float* lo, size_t n, void* stream);
+/* C[M][ldc] (and / or its hi, lo split; any of C, C_hi may be NULL) = relu?(alpha * A B^T) with A = A_hi + A_lo [M][lda],
+ * B = B_hi + B_lo [N][ldb], all fp32 row-major; three tcgen05.mma.kind::tf32 products per k-step (lo*hi, hi*lo, hi*hi)
+ * accumulated in fp32 TMEM. */
+int lako_gemm_tf32x3(const float* A_hi, const float* A_lo, const float* B_hi, const float* B_lo, float* C, float* C_hi,
+                     float* C_lo, int M, int N, int K, int lda, int ldb, int ldc, int relu, float alpha, void* stream);
+
+/* fp32-mode attention / normalisation (SIMT fp32; outputs optionally as the (hi, lo) TF32 pair the next GEMM reads):
+ * encoder self-attention HF:253-344 per passage for any L (qkv fp32 [rows][3*H*64], cu = packed row offsets or NULL),
+ * cross_attention_forward src/model.py:286-349 for T query rows per question against fp32 K/V (arguments as
+ * lako_xattn_decode; the capture applies to query row 0), T5LayerNorm + residual add HF:55-68. */
+int lako_enc_attn_f32(const float* qkv, const unsigned char* mask, const float* lut, float* out, float* out_hi,
+                      float* out_lo, int P, int L, int H, const int* cu, void* stream);
+size_t lako_xattn_f32_workspace_bytes(int B, int T, int H, int M);
+int lako_xattn_f32(const float* q, const float* kv, const unsigned char* mask, float* out, float* out_hi, float* out_lo,
+                   float* tok_score, const int* step, float* workspace, int B, int T, int M, int H, int ldq, int ldkv,
+                   int koff, int voff, int ldo, const int* cu, int npsg, const int* tok_index, void* stream);
+int lako_rmsnorm_f32(const float* x, const float* delta, float* x_out, const float* w, float* out, float* out_hi,
+                     float* out_lo, int rows, int d, float eps, void* stream);
+
 /* ---- utilities --------------------------------------------------------------------------------- */
 int lako_cast_f32_to_bf16(const float* in, void* out_bf16, size_t n, void* stream);
 int lako_transpose_bf16(const void* in, void* out, int rows, int cols, int ld_in, int ld_out, void* stream);
@@ -127,6 +149,10 @@ typedef struct {
   const int* enc_buckets; /* int32 device tables: bucket(rel) at index rel + bucket_center, HF:188-234 */
   const int* dec_buckets;
   int bucket_center;
+  /* precision = fp32 only (else NULL): the TF32 split of w_f32 made by lako_split_tf32 (hi = low 13 mantissa bits
+   * cleared, lo = the same truncation of w - hi), same element offsets */
+  const float* w_tf32_hi;
+  const float* w_tf32_lo;
 } lako_fidt5;
 
 typedef struct {
@@ -164,7 +190,8 @@ typedef struct {
 } lako_batch;
 
 int lako_fidt5_layout(const lako_dims* dims, lako_layout* out);
-/* mode 0 = forward only (eval loss), 1 = training (keeps activations for lako_fidt5_backward) */
+/* mode 0 = forward only (eval loss), 1 = training (keeps activations for lako_fidt5_backward), 2 = forward only with
+ * lako_batch.precision = 1 (fp32) */
 size_t lako_fidt5_workspace_bytes(const lako_dims* dims, int B, int N, int L, int T, int mode);
 /* FiDT5.forward (src/model.py:39-51) + T5 loss (HF:1105-1117) */
 int lako_fidt5_forward(const lako_fidt5* m, const lako_batch* b, int mode, void* stream);
@@ -178,7 +205,7 @@ int lako_fidt5_grad_stages(const lako_dims* dims, size_t* ranges);
 /* FiDT5.generate (src/model.py:54-60), greedy with KV cache; synchronises the stream once per token
  * to test for early stop.  tok_score_* (may be NULL) receive the step-0 cross-attention score sums
  * that src/model.py:327-329 + :152-167 derive from score_storage. */
-size_t lako_fidt5_generate_workspace_bytes(const lako_dims* dims, int B, int N, int L, int max_length);
+size_t lako_fidt5_generate_workspace_bytes(const lako_dims* dims, int B, int N, int L, int max_length, int precision);
 int lako_fidt5_generate(const lako_fidt5* m, const lako_batch* b, int max_length, int min_length, int64_t* out_ids,
                         int* out_len, float* tok_score_first, float* tok_score_last, void* stream);
 
@@ -218,21 +245,27 @@ int lako_xattn_bwd(const void* q, const void* kv, const unsigned char* mask, con
  * epi: 0 bf16 store, 1 bf16 ReLU store, 2 fp32 store, 3 fp32 y += (residual add, HF:375,149). */
 int lako_smallm_linear(const float* x_f32, const void* x_bf16, int ldx, const float* ln_w, float eps, const void* W,
                        void* y, int ldy, int M, int N, int K, int epi, float alpha, void* stream);
-/* cross_attention_forward (src/model.py:286-349) for ONE query token per question against K/V rows of the fused memory
- * (kv row pitch ldkv, head h at column koff/voff + 64 h).  Packed memory: question b owns rows
- * [cu[b*npsg], cu[(b+1)*npsg]) and tok_index maps a packed row to its index in the padded [B][M] score buffer;
- * cu == NULL: padded rows [b*M, (b+1)*M) with the 0/1 key mask.  tok_score (may be NULL) += the pre-softmax scores of
- * valid keys (summed over heads) when *step == 0 (step == NULL: always) -- the capture of src/model.py:327-329. */
+/* cross_attention_forward (src/model.py:286-349) for ONE query token per question (q fp32 [B][ldq]) against the bf16
+ * K/V rows of the fused memory (kv_rows rows of pitch ldkv, head h at column koff/voff + 64 h; tiles arrive by TMA).
+ * Packed memory: question b owns rows [cu[b*npsg], cu[(b+1)*npsg]) and tok_index maps a packed row to its index in
+ * the padded [B][M] score buffer; cu == NULL: padded rows [b*M, (b+1)*M) with the 0/1 key mask.  tok_score (may be
+ * NULL) += the pre-softmax scores of valid keys (summed over heads) when *step == 0 (step == NULL: always) -- the
+ * capture of src/model.py:327-329.  The flash-decoding combine of the 256-key chunks is done by the last chunk CTA
+ * to arrive; `workspace` (lako_xattn_decode_workspace_bytes) must be ZERO before the first call and is left with its
+ * arrival counters zeroed.  zero_q != 0: q[b][64 h .. 64 h + 64) is cleared once (b, h) is finished (the K-split
+ * projection that produces q accumulates into it). */
 size_t lako_xattn_decode_workspace_bytes(int B, int H, int M);
-int lako_xattn_decode(const void* q, const void* kv, const unsigned char* mask, void* out, float* tok_score,
-                      const int* step, float* workspace, int B, int M, int H, int ldq, int ldkv, int koff, int voff,
-                      int ldo, const int* cu, int npsg, const int* tok_index, void* stream);
+int lako_xattn_decode(const float* q, const void* kv, size_t kv_rows, const unsigned char* mask, void* out,
+                      float* tok_score, const int* step, float* workspace, int B, int M, int H, int ldq, int ldkv, int koff,
+                      int voff, int ldo, const int* cu, int npsg, const int* tok_index, int zero_q, void* stream);
 /* decoder self-attention of the token at position pos (or *pos_dev when not NULL) against the KV cache
  * [B][H][Tmax][64] (appends this step's k, v first); qkv bf16 [B][3*H*64], lut fp32 [H][2*Tmax-1] causal buckets */
 int lako_dself_step(const void* qkv, void* kcache, void* vcache, const float* lut, void* out, int B, int pos, int Tmax,
                     int H, const int* pos_dev, void* stream);
 /* replay decode steps from a captured CUDA graph (default on; also env LAKO_DECODE_GRAPH=0) */
 void lako_set_decode_graph(int on);
+/* counters since process start: graphs captured, decode steps replayed from a graph, failed captures */
+void lako_decode_graph_stats(long long* captures, long long* launches, long long* failures);
 /* causal decoder self-attention HF:253-344,438-445 */
 int lako_dself_fwd(const void* qkv, const float* lut, void* out, float* probs, int B, int T, int H, void* stream);
 int lako_dself_bwd(const void* qkv, const void* dout, const float* probs, void* dqkv, float* dlut, int B, int T, int H,

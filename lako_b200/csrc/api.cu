@@ -124,17 +124,36 @@ int lako_smallm_linear(const float* x_f32, const void* x_bf16, int ldx, const fl
   return smallm_linear(x_f32, CBF(x_bf16), ldx, ln_w, eps, CBF(W), y, ldy, M, N, K, epi, alpha, ST(stream));
 }
 size_t lako_xattn_decode_workspace_bytes(int B, int H, int M) { return xattn_decode_workspace_bytes(B, H, M); }
-int lako_xattn_decode(const void* q, const void* kv, const unsigned char* mask, void* out, float* tok_score,
-                      const int* step, float* workspace, int B, int M, int H, int ldq, int ldkv, int koff, int voff,
-                      int ldo, const int* cu, int npsg, const int* tok_index, void* stream) {
+int lako_xattn_decode(const float* q, const void* kv, size_t kv_rows, const unsigned char* mask, void* out,
+                      float* tok_score, const int* step, float* workspace, int B, int M, int H, int ldq, int ldkv, int koff,
+                      int voff, int ldo, const int* cu, int npsg, const int* tok_index, int zero_q, void* stream) {
   ARCH_GUARD();
-  return xattn_decode(CBF(q), CBF(kv), mask, BF(out), tok_score, step, workspace, B, M, H, ldq, ldkv, koff, voff, ldo,
-                      ST(stream), cu, npsg, tok_index);
+  return xattn_decode(q, CBF(kv), kv_rows, mask, BF(out), tok_score, step, workspace, B, M, H, ldq, ldkv, koff, voff, ldo,
+                      ST(stream), cu, npsg, tok_index, zero_q != 0);
 }
 int lako_dself_step(const void* qkv, void* kcache, void* vcache, const float* lut, void* out, int B, int pos, int Tmax,
                     int H, const int* pos_dev, void* stream) {
   ARCH_GUARD();
   return dself_step(CBF(qkv), BF(kcache), BF(vcache), lut, BF(out), B, pos, Tmax, H, ST(stream), pos_dev);
+}
+
+int lako_enc_attn_f32(const float* qkv, const unsigned char* mask, const float* lut, float* out, float* out_hi,
+                      float* out_lo, int P, int L, int H, const int* cu, void* stream) {
+  ARCH_GUARD();
+  return enc_attn_f32(qkv, mask, lut, out, out_hi, out_lo, P, L, H, ST(stream), cu);
+}
+size_t lako_xattn_f32_workspace_bytes(int B, int T, int H, int M) { return xattn_f32_workspace_bytes(B, T, H, M); }
+int lako_xattn_f32(const float* q, const float* kv, const unsigned char* mask, float* out, float* out_hi, float* out_lo,
+                   float* tok_score, const int* step, float* workspace, int B, int T, int M, int H, int ldq, int ldkv,
+                   int koff, int voff, int ldo, const int* cu, int npsg, const int* tok_index, void* stream) {
+  ARCH_GUARD();
+  return xattn_f32(q, kv, mask, out, out_hi, out_lo, tok_score, step, workspace, B, T, M, H, ldq, ldkv, koff, voff, ldo,
+                   ST(stream), cu, npsg, tok_index);
+}
+int lako_rmsnorm_f32(const float* x, const float* delta, float* x_out, const float* w, float* out, float* out_hi,
+                     float* out_lo, int rows, int d, float eps, void* stream) {
+  ARCH_GUARD();
+  return rmsnorm_f32(x, delta, x_out, w, out, out_hi, out_lo, rows, d, eps, ST(stream));
 }
 
 }  // extern "C"

@@ -78,16 +78,29 @@ int xattn_bwd(const __nv_bfloat16* q, const __nv_bfloat16* kv, const unsigned ch
 // decoder self-attention, teacher-forced (training): one CTA per (head, question), T <= 64.
 // qkv bf16 [B*T][3*inner]; lut fp32 [H][2T-1] (causal buckets; only rel <= 0 is used).
 // ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float ldf(const __nv_bfloat16& v) { return __bfloat162float(v); }
+__device__ __forceinline__ float ldf(const float& v) { return v; }
+__device__ __forceinline__ void stf(__nv_bfloat16* p, __nv_bfloat16*, float v) { *p = __float2bfloat16(v); }
+// fp32 mode: the result feeds a 3xTF32 GEMM, so it is stored as its (hi, lo) TF32 pair
+__device__ __forceinline__ void stf(float* hi, float* lo, float v) {
+  const float h = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
+  *hi = h;
+  if (lo) *lo = __uint_as_float(__float_as_uint(v - h) & 0xffffe000u);
+}
+
+template <typename E>
 struct DSelfParams {
-  const __nv_bfloat16* qkv;
+  const E* qkv;
   const float* lut;
-  __nv_bfloat16* out;       // [B*T][inner]
+  E* out;                   // [B*T][inner]  (fp32: hi part)
+  E* out_lo;                // fp32 only: lo part
   float* probs;             // [B][H][T][T] fp32 saved for backward (un-dropped)
   int T, H, inner;
   DropSpec drop;            // group = ((b*H+h)*T + t)*8 + j/8
 };
 
-__global__ void __launch_bounds__(128) dself_fwd_kernel(const DSelfParams p) {
+template <typename E>
+__global__ void __launch_bounds__(128) dself_fwd_kernel(const DSelfParams<E> p) {
   pdl_launch_dependents();
   pdl_wait();
   extern __shared__ float dyn[];
@@ -99,10 +112,10 @@ __global__ void __launch_bounds__(128) dself_fwd_kernel(const DSelfParams p) {
   const int T = p.T;
   for (int i = tid; i < T * 64; i += 128) {
     const int t = i >> 6, d = i & 63;
-    const __nv_bfloat16* row = p.qkv + (static_cast<size_t>(b) * T + t) * 3 * p.inner + h * 64 + d;
-    sQ[t][d] = __bfloat162float(row[0]);
-    sK[t][d] = __bfloat162float(row[p.inner]);
-    sV[t][d] = __bfloat162float(row[2 * p.inner]);
+    const E* row = p.qkv + (static_cast<size_t>(b) * T + t) * 3 * p.inner + h * 64 + d;
+    sQ[t][d] = ldf(row[0]);
+    sK[t][d] = ldf(row[p.inner]);
+    sV[t][d] = ldf(row[2 * p.inner]);
   }
   __syncthreads();
   const float* lut = p.lut + h * (2 * T - 1) + (T - 1);
@@ -147,7 +160,8 @@ __global__ void __launch_bounds__(128) dself_fwd_kernel(const DSelfParams p) {
       const int d = lane + i * 32;
       float acc = 0.f;
       for (int j = 0; j <= t; ++j) acc += sP[warp][j] * sV[j][d];
-      p.out[(static_cast<size_t>(b) * T + t) * p.inner + h * 64 + d] = __float2bfloat16(acc);
+      const size_t oi = (static_cast<size_t>(b) * T + t) * p.inner + h * 64 + d;
+      stf(p.out + oi, p.out_lo ? p.out_lo + oi : nullptr, acc);
     }
     __syncwarp();
   }
@@ -156,14 +170,28 @@ __global__ void __launch_bounds__(128) dself_fwd_kernel(const DSelfParams p) {
 int dself_fwd(const __nv_bfloat16* qkv, const float* lut, __nv_bfloat16* out, float* probs, int B, int T, int H,
               cudaStream_t s, DropSpec drop) {
   LAKO_REQUIRE(T > 0 && T <= XA_TMAX, LAKO_ERR_UNSUPPORTED);
-  DSelfParams p{qkv, lut, out, probs, T, H, H * 64, drop};
+  DSelfParams<__nv_bfloat16> p{qkv, lut, out, nullptr, probs, T, H, H * 64, drop};
   constexpr int smem = (3 * XA_TMAX * 65 + 4 * XA_TMAX) * (int)sizeof(float);
   static bool configured = false;
   if (!configured) {
-    cudaFuncSetAttribute(dself_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaFuncSetAttribute(dself_fwd_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     configured = true;
   }
-  launch_pdl(dself_fwd_kernel, dim3(dim3(H, B)), dim3(128), smem, s, p);
+  launch_pdl(dself_fwd_kernel<__nv_bfloat16>, dim3(dim3(H, B)), dim3(128), smem, s, p);
+  LAKO_CHECK_LAUNCH();
+  return LAKO_OK;
+}
+// fp32 mode: qkv fp32, result as its (hi, lo) TF32 pair
+int dself_fwd_f32(const float* qkv, const float* lut, float* out_hi, float* out_lo, int B, int T, int H, cudaStream_t s) {
+  LAKO_REQUIRE(T > 0 && T <= XA_TMAX, LAKO_ERR_UNSUPPORTED);
+  DSelfParams<float> p{qkv, lut, out_hi, out_lo, nullptr, T, H, H * 64, DropSpec{}};
+  constexpr int smem = (3 * XA_TMAX * 65 + 4 * XA_TMAX) * (int)sizeof(float);
+  static bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute(dself_fwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    configured = true;
+  }
+  launch_pdl(dself_fwd_kernel<float>, dim3(dim3(H, B)), dim3(128), smem, s, p);
   LAKO_CHECK_LAUNCH();
   return LAKO_OK;
 }
@@ -272,28 +300,27 @@ int dself_bwd(const __nv_bfloat16* qkv, const __nv_bfloat16* dout, const float* 
 // appends this step's k,v to the cache and attends over positions 0..pos.
 // qkv bf16 [B][3*inner]; cache bf16 [B][H][Tmax][64] x2; lut fp32 [H][2*Tmax-1] (causal buckets)
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(64) dself_step_kernel(const __nv_bfloat16* __restrict__ qkv,
-                                                        __nv_bfloat16* __restrict__ kcache,
-                                                        __nv_bfloat16* __restrict__ vcache,
-                                                        const float* __restrict__ lut, __nv_bfloat16* __restrict__ out,
-                                                        int pos, const int* __restrict__ pos_dev, int Tmax, int H,
-                                                        int inner) {
+template <typename E>
+__global__ void __launch_bounds__(64) dself_step_kernel(const E* __restrict__ qkv, E* __restrict__ kcache,
+                                                        E* __restrict__ vcache, const float* __restrict__ lut,
+                                                        E* __restrict__ out, E* __restrict__ out_lo, int pos,
+                                                        const int* __restrict__ pos_dev, int Tmax, int H, int inner) {
   pdl_launch_dependents();
   pdl_wait();
   __shared__ float sQ[64], sS[1024];
   if (pos_dev) pos = *pos_dev;  // step index kept on the device: one captured graph serves every decode step
   const int h = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
-  const __nv_bfloat16* row = qkv + static_cast<size_t>(b) * 3 * inner + h * 64;
-  __nv_bfloat16* kc = kcache + (static_cast<size_t>(b) * H + h) * Tmax * 64;
-  __nv_bfloat16* vc = vcache + (static_cast<size_t>(b) * H + h) * Tmax * 64;
-  sQ[tid] = __bfloat162float(row[tid]);
+  const E* row = qkv + static_cast<size_t>(b) * 3 * inner + h * 64;
+  E* kc = kcache + (static_cast<size_t>(b) * H + h) * Tmax * 64;
+  E* vc = vcache + (static_cast<size_t>(b) * H + h) * Tmax * 64;
+  sQ[tid] = ldf(row[tid]);
   kc[pos * 64 + tid] = row[inner + tid];
   vc[pos * 64 + tid] = row[2 * inner + tid];
   __syncthreads();
   const float* l = lut + h * (2 * Tmax - 1) + (Tmax - 1);
   for (int j = tid; j <= pos; j += 64) {
     float acc = 0.f;
-    for (int d = 0; d < 64; ++d) acc += sQ[d] * __bfloat162float(kc[j * 64 + d]);
+    for (int d = 0; d < 64; ++d) acc += sQ[d] * ldf(kc[j * 64 + d]);
     sS[j] = acc + l[j - pos];
   }
   __syncthreads();
@@ -303,23 +330,32 @@ __global__ void __launch_bounds__(64) dself_step_kernel(const __nv_bfloat16* __r
   for (int j = 0; j <= pos; ++j) {
     const float e = __expf(sS[j] - m);
     lsum += e;
-    acc += e * __bfloat162float(vc[j * 64 + tid]);
+    acc += e * ldf(vc[j * 64 + tid]);
   }
-  out[static_cast<size_t>(b) * inner + h * 64 + tid] = __float2bfloat16(acc / lsum);
+  const size_t oi = static_cast<size_t>(b) * inner + h * 64 + tid;
+  stf(out + oi, out_lo ? out_lo + oi : nullptr, acc / lsum);
 }
 
 int dself_step(const __nv_bfloat16* qkv, __nv_bfloat16* kcache, __nv_bfloat16* vcache, const float* lut,
                __nv_bfloat16* out, int B, int pos, int Tmax, int H, cudaStream_t s, const int* pos_dev) {
   LAKO_REQUIRE(pos >= 0 && pos < Tmax && Tmax <= 1024, LAKO_ERR_UNSUPPORTED);
-  launch_pdl(dself_step_kernel, dim3(dim3(H, B)), dim3(64), 0, s, qkv, kcache, vcache, lut, out, pos, pos_dev, Tmax, H,
-             H * 64);
+  launch_pdl(dself_step_kernel<__nv_bfloat16>, dim3(dim3(H, B)), dim3(64), 0, s, qkv, kcache, vcache, lut, out,
+             static_cast<__nv_bfloat16*>(nullptr), pos, pos_dev, Tmax, H, H * 64);
+  LAKO_CHECK_LAUNCH();
+  return LAKO_OK;
+}
+int dself_step_f32(const float* qkv, float* kcache, float* vcache, const float* lut, float* out_hi, float* out_lo, int B,
+                   int pos, int Tmax, int H, cudaStream_t s, const int* pos_dev) {
+  LAKO_REQUIRE(pos >= 0 && pos < Tmax && Tmax <= 1024, LAKO_ERR_UNSUPPORTED);
+  launch_pdl(dself_step_kernel<float>, dim3(dim3(H, B)), dim3(64), 0, s, qkv, kcache, vcache, lut, out_hi, out_lo, pos,
+             pos_dev, Tmax, H, H * 64);
   LAKO_CHECK_LAUNCH();
   return LAKO_OK;
 }
 
 // greedy token selection: argmax over fp32 logits [B][ld], EOS/pad bookkeeping as HF greedy search
 // (SURVEY 3.3): finished rows emit pad (0); a row finishes when it emits EOS (1).
-__global__ void __launch_bounds__(256) greedy_pick_kernel(const float* __restrict__ logits, int V, int ld,
+__global__ void __launch_bounds__(1024) greedy_pick_kernel(const float* __restrict__ logits, int V, int ld,
                                                           long long* __restrict__ out_ids, int out_ld, int step,
                                                           int* __restrict__ unfinished, int* __restrict__ n_unfinished,
                                                           long long* __restrict__ next_ids, int ban_eos,
@@ -327,8 +363,8 @@ __global__ void __launch_bounds__(256) greedy_pick_kernel(const float* __restric
                                                           int min_length) {
   pdl_launch_dependents();
   pdl_wait();
-  __shared__ float s_v[8];
-  __shared__ int s_i[8];
+  __shared__ float s_v[32];
+  __shared__ int s_i[32];
   const int b = blockIdx.x, tid = threadIdx.x;
   if (step_dev) {  // device-resident step counter (decode step k writes output column k + 1)
     step = *step_dev + 1;
@@ -337,12 +373,23 @@ __global__ void __launch_bounds__(256) greedy_pick_kernel(const float* __restric
   const float* lr = logits + static_cast<size_t>(b) * ld;
   float best = -INFINITY;
   int bi = 0x7fffffff;
-  for (int c = tid; c < V; c += 256) {
-    const float v = lr[c];
-    if (ban_eos && c == 1) continue;  // HF MinLengthLogitsProcessor: EOS logit = -inf below min_length
-    if (v > best || (v == best && c < bi)) {
-      best = v;
-      bi = c;
+  for (int c4 = tid * 4; c4 < V; c4 += 4096) {  // ld % 4 == 0: rows are 16-byte aligned
+    float vv[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+    if (c4 + 4 <= V) {
+      const float4 t = *reinterpret_cast<const float4*>(lr + c4);
+      vv[0] = t.x; vv[1] = t.y; vv[2] = t.z; vv[3] = t.w;
+    } else {
+      for (int e = 0; c4 + e < V; ++e) vv[e] = lr[c4 + e];
+    }
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int c = c4 + e;
+      if (c >= V || (ban_eos && c == 1)) continue;  // HF MinLengthLogitsProcessor: EOS logit = -inf below min_length
+      const float v = vv[e];
+      if (v > best || (v == best && c < bi)) {
+        best = v;
+        bi = c;
+      }
     }
   }
 #pragma unroll
@@ -360,7 +407,7 @@ __global__ void __launch_bounds__(256) greedy_pick_kernel(const float* __restric
   }
   __syncthreads();
   if (tid == 0) {
-    for (int w = 1; w < 8; ++w)
+    for (int w = 1; w < static_cast<int>(blockDim.x >> 5); ++w)
       if (s_v[w] > best || (s_v[w] == best && s_i[w] < bi)) {
         best = s_v[w];
         bi = s_i[w];
@@ -387,8 +434,9 @@ __global__ void __launch_bounds__(256) greedy_pick_kernel(const float* __restric
 int greedy_pick(const float* logits, int B, int V, int ld, long long* out_ids, int out_ld, int step, int* unfinished,
                 int* n_unfinished, long long* next_ids, cudaStream_t s, int ban_eos, int* step_dev, int* done_dev,
                 int min_length) {
-  launch_pdl(greedy_pick_kernel, dim3(B), dim3(256), 0, s, logits, V, ld, out_ids, out_ld, step, unfinished, n_unfinished, next_ids,
-             ban_eos, step_dev, done_dev, min_length);
+  LAKO_REQUIRE(ld % 4 == 0, LAKO_ERR_BAD_ARG);
+  launch_pdl(greedy_pick_kernel, dim3(B), dim3(1024), 0, s, logits, V, ld, out_ids, out_ld, step, unfinished, n_unfinished,
+             next_ids, ban_eos, step_dev, done_dev, min_length);
   LAKO_CHECK_LAUNCH();
   return LAKO_OK;
 }

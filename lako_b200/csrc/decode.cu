@@ -50,12 +50,14 @@ struct SmallLinParams {
   void* y;                     // see epi
   int M, N, K, ldx, ldy;
   float eps, alpha;
-  int epi;  // 0 bf16 store, 1 bf16 ReLU store, 2 fp32 store, 3 fp32 accumulate (y += : residual add)
-  int kc;   // K chunk staged per pass (multiple of 32)
+  int epi;     // 0 bf16 store, 1 bf16 ReLU store, 2 fp32 store, 3 fp32 accumulate (y += : residual add; atomic when K is split)
+  int kc;      // K chunk staged per pass (multiple of 32)
+  int kb_per;  // 32-wide k blocks per K split (gridDim.y splits; epi 3 only when > 1 split)
+  int ntiles;  // 16-row output tiles; a CTA loops over tiles blockIdx.x, blockIdx.x + gridDim.x, ...
 };
 
 constexpr int SL_WARPS = 8;
-constexpr int SL_ROWS = 16;   // weight rows (output features) per CTA
+constexpr int SL_ROWS = 16;   // weight rows (output features) per tile
 constexpr int SL_UNROLL = 4;  // 32-wide k blocks in flight per warp
 
 // dynamic smem: xs bf16 [NT*8][kc + 32]  (row pitch = 2*kc + 64 bytes: the 8 lanes of a quarter-warp LDS.128 hit all
@@ -70,32 +72,35 @@ __global__ void __launch_bounds__(SL_WARPS * 32) smallm_linear_kernel(const Smal
   float* red = reinterpret_cast<float*>(sl_smem + static_cast<size_t>(MP) * pitch);
   float* s_rstd = red + SL_WARPS * 16 * MP;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t4 = lane & 3;
-  const int n0 = blockIdx.x * SL_ROWS;
-  // the two weight rows of this lane (clamped: rows past N are computed on a valid row and never stored)
-  const int r_lo = min(n0 + g, p.N - 1), r_hi = min(n0 + g + 8, p.N - 1);
-  const __nv_bfloat16* w_lo = p.W + static_cast<size_t>(r_lo) * p.K + t4 * 8;
-  const __nv_bfloat16* w_hi = p.W + static_cast<size_t>(r_hi) * p.K + t4 * 8;
-  float acc[NT][4];
-#pragma unroll
-  for (int i = 0; i < NT; ++i)
-#pragma unroll
-    for (int e = 0; e < 4; ++e) acc[i][e] = 0.f;
+  // this CTA's K range (in 32-wide blocks) and whether the staged activations can be kept across output tiles
+  const int kblocks_all = p.K >> 5;
+  const int kb_lo = blockIdx.y * p.kb_per, kb_hi = min(kblocks_all, kb_lo + p.kb_per);
+  const int k_lo = kb_lo << 5, k_hi = kb_hi << 5;
+  const bool single_chunk = (k_hi - k_lo) <= p.kc;
 
-  // weights do not depend on the predecessor kernel: start streaming the first blocks before the grid dependency
-  const int kblocks = p.K >> 5;
+  auto row_ptrs = [&](int tile, const __nv_bfloat16*& w_lo, const __nv_bfloat16*& w_hi) {
+    const int n0 = tile * SL_ROWS;
+    // the two weight rows of this lane (clamped: rows past N are computed on a valid row and never stored)
+    const int r_lo = min(n0 + g, p.N - 1), r_hi = min(n0 + g + 8, p.N - 1);
+    w_lo = p.W + static_cast<size_t>(r_lo) * p.K + t4 * 8;
+    w_hi = p.W + static_cast<size_t>(r_hi) * p.K + t4 * 8;
+  };
+  // weights do not depend on the predecessor kernel: start streaming the first tile's blocks before the grid dependency
   uint4 pa_lo[SL_UNROLL], pa_hi[SL_UNROLL];
-  int kb_next = warp;  // this warp owns k blocks warp, warp + 8, ...
+  const __nv_bfloat16 *w_lo, *w_hi;
+  int tile = blockIdx.x;
+  row_ptrs(tile, w_lo, w_hi);
 #pragma unroll
   for (int u = 0; u < SL_UNROLL; ++u) {
-    const int kb = kb_next + u * SL_WARPS;
-    if (kb < kblocks) {
+    const int kb = kb_lo + warp + u * SL_WARPS;
+    if (kb < kb_hi) {
       pa_lo[u] = ldg_nc_v4(w_lo + kb * 32);
       pa_hi[u] = ldg_nc_v4(w_hi + kb * 32);
     }
   }
   pdl_wait();
 
-  if (p.x_f32 && p.ln_w) {  // T5 RMSNorm statistics: one warp per row, same summation order as rmsnorm_fwd_kernel
+  if (p.x_f32 && p.ln_w) {  // T5 RMSNorm statistics over the WHOLE row: one warp per row, order of rmsnorm_fwd_kernel
     for (int m = warp; m < MP; m += SL_WARPS) {
       float ss = 0.f;
       if (m < p.M) {
@@ -111,97 +116,126 @@ __global__ void __launch_bounds__(SL_WARPS * 32) smallm_linear_kernel(const Smal
     __syncthreads();
   }
 
-  for (int kc0 = 0; kc0 < p.K; kc0 += p.kc) {
-    const int kcn = min(p.kc, p.K - kc0);
-    if (kc0 > 0) __syncthreads();  // every warp is done with the previous chunk
-    // ---- stage x[:, kc0 : kc0 + kcn] as bf16 (normalised when the prologue is on); rows >= M are zero
-    for (int i = tid; i < MP * (kcn >> 2); i += SL_WARPS * 32) {
-      const int m = i / (kcn >> 2), c = (i - m * (kcn >> 2)) * 4;
-      uint2 o = make_uint2(0u, 0u);
-      if (m < p.M) {
-        if (p.x_f32) {
-          float4 v = *reinterpret_cast<const float4*>(p.x_f32 + static_cast<size_t>(m) * p.K + kc0 + c);
-          if (p.ln_w) {
-            const float rs = s_rstd[m];
-            const float4 wv = *reinterpret_cast<const float4*>(p.ln_w + kc0 + c);
-            v = make_float4(wv.x * (v.x * rs), wv.y * (v.y * rs), wv.z * (v.z * rs), wv.w * (v.w * rs));
+  bool staged = false;
+  for (; tile < p.ntiles; tile += gridDim.x) {
+    const int n0 = tile * SL_ROWS;
+    float acc[NT][4];
+#pragma unroll
+    for (int i = 0; i < NT; ++i)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) acc[i][e] = 0.f;
+    int kb_next = kb_lo + warp;  // this warp owns k blocks kb_lo + warp, + 8, ...
+    for (int kc0 = k_lo; kc0 < k_hi; kc0 += p.kc) {
+      const int kcn = min(p.kc, k_hi - kc0);
+      if (!(single_chunk && staged)) {
+        if (kc0 > k_lo || staged) __syncthreads();  // every warp is done with what the buffer held
+        // ---- stage x[:, kc0 : kc0 + kcn] as bf16 (normalised when the prologue is on); rows >= M are zero
+        for (int i = tid; i < MP * (kcn >> 2); i += SL_WARPS * 32) {
+          const int m = i / (kcn >> 2), c = (i - m * (kcn >> 2)) * 4;
+          uint2 o = make_uint2(0u, 0u);
+          if (m < p.M) {
+            if (p.x_f32) {
+              float4 v = *reinterpret_cast<const float4*>(p.x_f32 + static_cast<size_t>(m) * p.K + kc0 + c);
+              if (p.ln_w) {
+                const float rs = s_rstd[m];
+                const float4 wv = *reinterpret_cast<const float4*>(p.ln_w + kc0 + c);
+                v = make_float4(wv.x * (v.x * rs), wv.y * (v.y * rs), wv.z * (v.z * rs), wv.w * (v.w * rs));
+              }
+              o.x = pack_bf16x2(v.x, v.y);
+              o.y = pack_bf16x2(v.z, v.w);
+            } else {
+              o = *reinterpret_cast<const uint2*>(p.x_b16 + static_cast<size_t>(m) * p.ldx + kc0 + c);
+            }
           }
-          o.x = pack_bf16x2(v.x, v.y);
-          o.y = pack_bf16x2(v.z, v.w);
-        } else {
-          o = *reinterpret_cast<const uint2*>(p.x_b16 + static_cast<size_t>(m) * p.ldx + kc0 + c);
+          *reinterpret_cast<uint2*>(xs + static_cast<size_t>(m) * pitch + c * 2) = o;
         }
+        __syncthreads();
+        staged = true;
       }
-      *reinterpret_cast<uint2*>(xs + static_cast<size_t>(m) * pitch + c * 2) = o;
+      // ---- this warp's k blocks inside the chunk, SL_UNROLL at a time.  Chunks are whole multiples of
+      //      32 * SL_WARPS * SL_UNROLL k (or one chunk covers the CTA's whole K range), so a group never straddles a
+      //      chunk boundary and the prefetch queue simply runs ahead into the next chunk.
+      const int kb_end = (kc0 + kcn) >> 5;
+      while (kb_next < kb_end) {
+        uint4 a_lo[SL_UNROLL], a_hi[SL_UNROLL];
+#pragma unroll
+        for (int u = 0; u < SL_UNROLL; ++u) {
+          a_lo[u] = pa_lo[u];
+          a_hi[u] = pa_hi[u];
+        }
+#pragma unroll
+        for (int u = 0; u < SL_UNROLL; ++u) {
+          const int kb = kb_next + (SL_UNROLL + u) * SL_WARPS;
+          if (kb < kb_hi) {
+            pa_lo[u] = ldg_nc_v4(w_lo + kb * 32);
+            pa_hi[u] = ldg_nc_v4(w_hi + kb * 32);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < SL_UNROLL; ++u) {
+          const int kb = kb_next + u * SL_WARPS;
+          if (kb < kb_hi) {
+            const uint8_t* xb = xs + ((kb << 5) - kc0 + t4 * 8) * 2;
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt) {
+              const uint4 xv = *reinterpret_cast<const uint4*>(xb + static_cast<size_t>(nt * 8 + g) * pitch);
+              mma_16816(acc[nt], a_lo[u].x, a_hi[u].x, a_lo[u].y, a_hi[u].y, xv.x, xv.y);
+              mma_16816(acc[nt], a_lo[u].z, a_hi[u].z, a_lo[u].w, a_hi[u].w, xv.z, xv.w);
+            }
+          }
+        }
+        kb_next += SL_UNROLL * SL_WARPS;
+      }
     }
-    __syncthreads();
-    // ---- this warp's k blocks inside the chunk, SL_UNROLL at a time.  Chunks are whole multiples of
-    //      32 * SL_WARPS * SL_UNROLL k (or the single chunk is all of K), so a group never straddles a chunk boundary
-    //      and the prefetch queue simply runs ahead into the next chunk.
-    const int kb_end = (kc0 + kcn) >> 5;
-    while (kb_next < kb_end) {
-      uint4 a_lo[SL_UNROLL], a_hi[SL_UNROLL];
+    // the next tile's first weight blocks: in flight while this tile is reduced and stored
+    const int next_tile = tile + gridDim.x;
+    if (next_tile < p.ntiles) {
+      row_ptrs(next_tile, w_lo, w_hi);
 #pragma unroll
       for (int u = 0; u < SL_UNROLL; ++u) {
-        a_lo[u] = pa_lo[u];
-        a_hi[u] = pa_hi[u];
-      }
-#pragma unroll
-      for (int u = 0; u < SL_UNROLL; ++u) {
-        const int kb = kb_next + (SL_UNROLL + u) * SL_WARPS;
-        if (kb < kblocks) {
+        const int kb = kb_lo + warp + u * SL_WARPS;
+        if (kb < kb_hi) {
           pa_lo[u] = ldg_nc_v4(w_lo + kb * 32);
           pa_hi[u] = ldg_nc_v4(w_hi + kb * 32);
         }
       }
+    }
+    // ---- reduce the 8 warps' partial sums: red[warp][row 0..15][m 0..MP)
 #pragma unroll
-      for (int u = 0; u < SL_UNROLL; ++u) {
-        const int kb = kb_next + u * SL_WARPS;
-        if (kb < kblocks) {
-          const uint8_t* xb = xs + ((kb << 5) - kc0 + t4 * 8) * 2;
+    for (int nt = 0; nt < NT; ++nt) {
+      float* r0 = red + (warp * 16 + g) * MP + nt * 8 + t4 * 2;
+      float* r1 = red + (warp * 16 + g + 8) * MP + nt * 8 + t4 * 2;
+      *reinterpret_cast<float2*>(r0) = make_float2(acc[nt][0], acc[nt][1]);
+      *reinterpret_cast<float2*>(r1) = make_float2(acc[nt][2], acc[nt][3]);
+    }
+    __syncthreads();
+    for (int i = tid; i < MP * 16; i += SL_WARPS * 32) {
+      const int m = i >> 4, r = i & 15;  // 16 consecutive output features of one activation row are contiguous in y
+      const int n = n0 + r;
+      if (m >= p.M || n >= p.N) continue;
+      float v = 0.f;
 #pragma unroll
-          for (int nt = 0; nt < NT; ++nt) {
-            const uint4 xv = *reinterpret_cast<const uint4*>(xb + static_cast<size_t>(nt * 8 + g) * pitch);
-            mma_16816(acc[nt], a_lo[u].x, a_hi[u].x, a_lo[u].y, a_hi[u].y, xv.x, xv.y);
-            mma_16816(acc[nt], a_lo[u].z, a_hi[u].z, a_lo[u].w, a_hi[u].w, xv.z, xv.w);
-          }
-        }
+      for (int w = 0; w < SL_WARPS; ++w) v += red[(w * 16 + r) * MP + m];
+      v *= p.alpha;
+      const size_t o = static_cast<size_t>(m) * p.ldy + n;
+      if (p.epi == 0) {
+        reinterpret_cast<__nv_bfloat16*>(p.y)[o] = __float2bfloat16(v);
+      } else if (p.epi == 1) {
+        reinterpret_cast<__nv_bfloat16*>(p.y)[o] = __float2bfloat16(fmaxf(v, 0.f));
+      } else if (p.epi == 2) {
+        reinterpret_cast<float*>(p.y)[o] = v;
+      } else if (gridDim.y == 1) {
+        reinterpret_cast<float*>(p.y)[o] += v;
+      } else {
+        atomicAdd(reinterpret_cast<float*>(p.y) + o, v);
       }
-      kb_next += SL_UNROLL * SL_WARPS;
     }
-  }
-  // ---- reduce the 8 warps' partial sums: red[warp][row 0..15][m 0..MP)
-#pragma unroll
-  for (int nt = 0; nt < NT; ++nt) {
-    float* r0 = red + (warp * 16 + g) * MP + nt * 8 + t4 * 2;
-    float* r1 = red + (warp * 16 + g + 8) * MP + nt * 8 + t4 * 2;
-    *reinterpret_cast<float2*>(r0) = make_float2(acc[nt][0], acc[nt][1]);
-    *reinterpret_cast<float2*>(r1) = make_float2(acc[nt][2], acc[nt][3]);
-  }
-  __syncthreads();
-  for (int i = tid; i < MP * 16; i += SL_WARPS * 32) {
-    const int m = i >> 4, r = i & 15;  // 16 consecutive output features of one activation row are contiguous in y
-    const int n = n0 + r;
-    if (m >= p.M || n >= p.N) continue;
-    float v = 0.f;
-#pragma unroll
-    for (int w = 0; w < SL_WARPS; ++w) v += red[(w * 16 + r) * MP + m];
-    v *= p.alpha;
-    const size_t o = static_cast<size_t>(m) * p.ldy + n;
-    if (p.epi == 0) {
-      reinterpret_cast<__nv_bfloat16*>(p.y)[o] = __float2bfloat16(v);
-    } else if (p.epi == 1) {
-      reinterpret_cast<__nv_bfloat16*>(p.y)[o] = __float2bfloat16(fmaxf(v, 0.f));
-    } else if (p.epi == 2) {
-      reinterpret_cast<float*>(p.y)[o] = v;
-    } else {
-      reinterpret_cast<float*>(p.y)[o] += v;
-    }
+    if (next_tile < p.ntiles) __syncthreads();  // red is reused by the next tile
   }
 }
 
 template <int NT>
-int launch_smallm(const SmallLinParams& p, cudaStream_t s) {
+int launch_smallm(const SmallLinParams& p, int grid_x, int ksplit, cudaStream_t s) {
   constexpr int MP = NT * 8;
   const size_t smem = static_cast<size_t>(MP) * (p.kc * 2 + 64) + sizeof(float) * (SL_WARPS * 16 * MP + MP);
   static size_t configured = 0;
@@ -214,15 +248,16 @@ int launch_smallm(const SmallLinParams& p, cudaStream_t s) {
     }
     configured = smem;
   }
-  launch_pdl(smallm_linear_kernel<NT>, dim3((p.N + SL_ROWS - 1) / SL_ROWS), dim3(SL_WARPS * 32), smem, s, p);
+  launch_pdl(smallm_linear_kernel<NT>, dim3(grid_x, ksplit), dim3(SL_WARPS * 32), smem, s, p);
   LAKO_CHECK_LAUNCH();
   return LAKO_OK;
 }
 
 }  // namespace
 
-// y = epi(alpha * norm?(x) W^T) for M <= 64 activation rows.  x_f32 != null: the input is the fp32 residual stream
-// [M][K]; with ln_w it is RMS-normalised (eps) on the fly.  Otherwise x_b16 [M][ldx] bf16.
+// y = epi(alpha * norm?(x) W^T) for few activation rows.  x_f32 != null: the input is the fp32 residual stream [M][K];
+// with ln_w it is RMS-normalised (eps) on the fly.  Otherwise x_b16 [M][ldx] bf16.  With the accumulate epilogue
+// (SL_F32_ADD) and few output tiles, K is split over gridDim.y CTAs that add their partial sums atomically.
 int smallm_linear(const float* x_f32, const __nv_bfloat16* x_b16, int ldx, const float* ln_w, float eps,
                   const __nv_bfloat16* W, void* y, int ldy, int M, int N, int K, int epi, float alpha, cudaStream_t s) {
   LAKO_REQUIRE(M > 0 && N > 0 && K > 0 && K % 32 == 0, LAKO_ERR_UNSUPPORTED);
@@ -239,20 +274,35 @@ int smallm_linear(const float* x_f32, const __nv_bfloat16* x_b16, int ldx, const
     }
     return LAKO_OK;
   }
-  SmallLinParams p{x_f32, x_b16, ln_w, W, y, M, N, K, ldx, ldy, eps, alpha, epi, 0};
+  SmallLinParams p{x_f32, x_b16, ln_w, W, y, M, N, K, ldx, ldy, eps, alpha, epi, 0, 0, 0};
   const int nt = (M + 7) / 8;
   const int NT = nt <= 1 ? 1 : nt <= 2 ? 2 : nt <= 4 ? 4 : 8;
-  // x chunk staged per pass: ~128 KB of bf16 activations at most, a whole multiple of 32 * SL_WARPS * SL_UNROLL k
   constexpr int KGROUP = 32 * SL_WARPS * SL_UNROLL;
+  p.ntiles = (N + SL_ROWS - 1) / SL_ROWS;
+  // K split: only the accumulate epilogue can combine partial sums; used when the output alone gives too few CTAs to
+  // stream the weights (N = d_model: 48-64 tiles for 148 SMs).  Every split keeps >= 2 k blocks per warp.
+  const int kblocks = K >> 5;
+  int ksplit = 1;
+  if (epi == SL_F32_ADD && p.ntiles < 2 * device_sm_count()) {
+    const int want = (2 * device_sm_count() + p.ntiles - 1) / p.ntiles;
+    for (int c = 1; c <= want; ++c)
+      if (kblocks % (c * 2 * SL_WARPS) == 0) ksplit = c;
+  }
+  p.kb_per = kblocks / ksplit;
+  // x chunk staged per pass: ~128 KB of bf16 activations at most, a whole multiple of the prefetch group
+  const int krange = p.kb_per * 32;
   const int kc = (131072 / (NT * 8 * 2)) / KGROUP * KGROUP;
-  p.kc = K <= kc ? K : kc;
-  LAKO_REQUIRE(K <= kc || K % KGROUP == 0, LAKO_ERR_UNSUPPORTED);
+  p.kc = krange <= kc ? krange : kc;
+  LAKO_REQUIRE(krange <= kc || (ksplit == 1 && krange % KGROUP == 0), LAKO_ERR_UNSUPPORTED);
+  // persistent over output tiles when the staged activations can be kept (single chunk): ~2 CTAs per SM
+  int grid_x = p.ntiles;
+  if (krange <= kc) grid_x = min(p.ntiles, 2 * device_sm_count());
   ProfScope prof(PROF_GEMM_SMALL, 2.0 * M * N * static_cast<double>(K), s);
   switch (NT) {
-    case 1: return launch_smallm<1>(p, s);
-    case 2: return launch_smallm<2>(p, s);
-    case 4: return launch_smallm<4>(p, s);
-    default: return launch_smallm<8>(p, s);
+    case 1: return launch_smallm<1>(p, grid_x, ksplit, s);
+    case 2: return launch_smallm<2>(p, grid_x, ksplit, s);
+    case 4: return launch_smallm<4>(p, grid_x, ksplit, s);
+    default: return launch_smallm<8>(p, grid_x, ksplit, s);
   }
 }
 
@@ -262,70 +312,81 @@ int smallm_linear(const float* x_f32, const __nv_bfloat16* x_b16, int ldx, const
 namespace {
 
 constexpr int XD_CH = 256;  // keys per CTA (4 warps x 64)
+constexpr int XD_TILE = XD_CH * 128;  // bytes of one 256-key x 64-dim bf16 tile
+constexpr int XD_SMEM = 2 * XD_TILE + 1024 + 64;
 
 struct XDecParams {
-  const __nv_bfloat16* q;    // [B][ldq]
-  const __nv_bfloat16* kv;   // rows = memory tokens, row pitch ldkv
+  const float* q;            // [B][ldq] fp32 (accumulated by the K-split projection; zeroed again here after use)
+  float* q_zero;             // same buffer (non-const) or null: zero q[b][h*64 .. +64) once (b, h) is finished
   const unsigned char* mask; // padded layout only: [B][M]
   float* part;               // [B][H][splits][66]
+  int* counters;             // [B][H] arrival counters of the chunk CTAs (zero between launches)
+  __nv_bfloat16* out;        // [B][ldo]
   float* tok_score;          // [B][M] fp32 accumulated when *step == 0 (may be null)
   const int* step;           // device step index (null: always capture when tok_score != null)
   const int* cu;
   const int* tok_index;
-  int M, H, ldq, ldkv, koff, voff, splits, npsg;
+  int M, H, ldq, ldo, koff, voff, splits, npsg;
 };
 
-__global__ void __launch_bounds__(128) xattn_decode_kernel(const XDecParams p) {
+// One CTA = 256 keys of one (question, head).  K and V tiles arrive by TMA (issued before the grid dependency: the
+// K/V cache does not depend on the preceding kernel) into 128B-swizzled shared memory; lane group kg (8 lanes) of warp w
+// owns keys w*64 + j*4 + kg, each lane 8 of the 64 dims.  Scores for the warp's 64 keys are formed while V is still in
+// flight; the last CTA of a (question, head) to arrive merges the chunk partials (flash-decoding combine) and writes
+// the bf16 context row, so no separate combine launch is needed.
+__global__ void __launch_bounds__(128) xattn_decode_kernel(const __grid_constant__ CUtensorMap tm_kv, const XDecParams p) {
   pdl_launch_dependents();
-  pdl_wait();
+  extern __shared__ uint8_t xd_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(xd_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sK = smem;
+  uint8_t* sV = smem + XD_TILE;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + 2 * XD_TILE);
   __shared__ float s_m[4], s_l[4], s_o[4][64];
+  __shared__ int s_last;
   const int split = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, kg = lane >> 3, c = lane & 7;
   int kstart = b * p.M, Mb = p.M;
-  if (p.cu) {
+  if (p.cu) {  // written before the encoder ran: older than the immediate predecessor, safe before pdl_wait
     kstart = p.cu[b * p.npsg];
     Mb = p.cu[(b + 1) * p.npsg] - kstart;
   }
   const int k0 = split * XD_CH;
-  if (k0 >= Mb) return;
+  if (k0 >= Mb) return;  // CTA-uniform
+  if (tid == 0) {
+    tma_prefetch_desc(&tm_kv);
+    mbar_init(&bar[0], 1);
+    mbar_init(&bar[1], 1);
+    fence_barrier_init();
+    mbar_arrive_expect_tx(&bar[0], XD_TILE);
+    tma_load_2d(sK, &tm_kv, &bar[0], p.koff + h * 64, kstart + k0);
+    mbar_arrive_expect_tx(&bar[1], XD_TILE);
+    tma_load_2d(sV, &tm_kv, &bar[1], p.voff + h * 64, kstart + k0);
+  }
+  __syncthreads();  // barrier initialisation visible to the waiting threads
+  pdl_wait();
   const bool capture = p.tok_score != nullptr && (p.step == nullptr || *p.step == 0);
-  // this lane's 8 of the 64 query dims
   float qv[8];
   {
-    const uint4 qq = *reinterpret_cast<const uint4*>(p.q + static_cast<size_t>(b) * p.ldq + h * 64 + c * 8);
-    qv[0] = bf16_lo(qq.x); qv[1] = bf16_hi(qq.x); qv[2] = bf16_lo(qq.y); qv[3] = bf16_hi(qq.y);
-    qv[4] = bf16_lo(qq.z); qv[5] = bf16_hi(qq.z); qv[6] = bf16_lo(qq.w); qv[7] = bf16_hi(qq.w);
+    const float4 q0 = *reinterpret_cast<const float4*>(p.q + static_cast<size_t>(b) * p.ldq + h * 64 + c * 8);
+    const float4 q1 = *reinterpret_cast<const float4*>(p.q + static_cast<size_t>(b) * p.ldq + h * 64 + c * 8 + 4);
+    qv[0] = q0.x; qv[1] = q0.y; qv[2] = q0.z; qv[3] = q0.w; qv[4] = q1.x; qv[5] = q1.y; qv[6] = q1.z; qv[7] = q1.w;
   }
-  float m_run = -INFINITY, l_run = 0.f, o[8];
+  const int wk0 = warp * 64;  // this warp's keys within the chunk
+  float sc[16];
+  float m_g = -INFINITY;
+  mbar_wait(&bar[0], 0);
 #pragma unroll
-  for (int i = 0; i < 8; ++i) o[i] = 0.f;
-  const int wk0 = k0 + warp * 64;  // this warp's 64 keys; lane group kg takes keys wk0 + j*4 + kg
-  const __nv_bfloat16* kbase = p.kv + (static_cast<size_t>(kstart) + wk0 + kg) * p.ldkv + h * 64 + c * 8;
-  const size_t step4 = static_cast<size_t>(4) * p.ldkv;
-#pragma unroll 1
-  for (int j0 = 0; j0 < 16; j0 += 8) {
-    if (wk0 + j0 * 4 >= Mb) break;  // warp-uniform
-    uint4 kr[8], vr[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int key = wk0 + (j0 + j) * 4 + kg;
-      if (key < Mb) {
-        kr[j] = ldg_nc_v4(kbase + (j0 + j) * step4 + p.koff);
-        vr[j] = ldg_nc_v4(kbase + (j0 + j) * step4 + p.voff);
-      } else {
-        kr[j] = make_uint4(0, 0, 0, 0);
-        vr[j] = make_uint4(0, 0, 0, 0);
-      }
-    }
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int key = wk0 + (j0 + j) * 4 + kg;
-      float s = qv[0] * bf16_lo(kr[j].x) + qv[1] * bf16_hi(kr[j].x) + qv[2] * bf16_lo(kr[j].y) + qv[3] * bf16_hi(kr[j].y) +
-                qv[4] * bf16_lo(kr[j].z) + qv[5] * bf16_hi(kr[j].z) + qv[6] * bf16_lo(kr[j].w) + qv[7] * bf16_hi(kr[j].w);
-      s += __shfl_xor_sync(0xffffffffu, s, 1);
-      s += __shfl_xor_sync(0xffffffffu, s, 2);
-      s += __shfl_xor_sync(0xffffffffu, s, 4);
-      if (key >= Mb) continue;  // uniform within the 8-lane group; the shuffles above ran on all lanes
+  for (int j = 0; j < 16; ++j) {
+    const int kl = wk0 + j * 4 + kg, key = k0 + kl;
+    const uint4 kr = *reinterpret_cast<const uint4*>(sK + kl * 128 + ((c ^ (kl & 7)) << 4));
+    float s = qv[0] * bf16_lo(kr.x) + qv[1] * bf16_hi(kr.x) + qv[2] * bf16_lo(kr.y) + qv[3] * bf16_hi(kr.y) +
+              qv[4] * bf16_lo(kr.z) + qv[5] * bf16_hi(kr.z) + qv[6] * bf16_lo(kr.w) + qv[7] * bf16_hi(kr.w);
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    s += __shfl_xor_sync(0xffffffffu, s, 2);
+    s += __shfl_xor_sync(0xffffffffu, s, 4);
+    if (key >= Mb) {
+      s = -INFINITY;  // rows past this question's memory (the next question's rows / TMA zero fill)
+    } else {
       bool valid = true;
       if (p.mask) valid = p.mask[static_cast<size_t>(b) * p.M + key] != 0;
       if (capture && valid && c == 0) {
@@ -333,18 +394,27 @@ __global__ void __launch_bounds__(128) xattn_decode_kernel(const XDecParams p) {
         atomicAdd(p.tok_score + ti, s);
       }
       if (!valid) s += DC_MASK_MIN;  // HF's additive mask (finfo.min): a fully masked question degrades to uniform
-      const float m_new = fmaxf(m_run, s);
-      const float sc = (m_run == -INFINITY) ? 0.f : fast_exp2((m_run - m_new) * DC_LOG2E);
-      const float pj = fast_exp2((s - m_new) * DC_LOG2E);
-      l_run = l_run * sc + pj;
-      const float vv[8] = {bf16_lo(vr[j].x), bf16_hi(vr[j].x), bf16_lo(vr[j].y), bf16_hi(vr[j].y),
-                           bf16_lo(vr[j].z), bf16_hi(vr[j].z), bf16_lo(vr[j].w), bf16_hi(vr[j].w)};
-#pragma unroll
-      for (int i = 0; i < 8; ++i) o[i] = o[i] * sc + pj * vv[i];
-      m_run = m_new;
     }
+    sc[j] = s;
+    m_g = fmaxf(m_g, s);
+  }
+  float l_g = 0.f, o[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) o[i] = 0.f;
+  mbar_wait(&bar[1], 0);
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    const int kl = wk0 + j * 4 + kg;
+    const float pj = (m_g == -INFINITY) ? 0.f : fast_exp2((sc[j] - m_g) * DC_LOG2E);
+    l_g += pj;
+    const uint4 vr = *reinterpret_cast<const uint4*>(sV + kl * 128 + ((c ^ (kl & 7)) << 4));
+    o[0] = fmaf(pj, bf16_lo(vr.x), o[0]); o[1] = fmaf(pj, bf16_hi(vr.x), o[1]);
+    o[2] = fmaf(pj, bf16_lo(vr.y), o[2]); o[3] = fmaf(pj, bf16_hi(vr.y), o[3]);
+    o[4] = fmaf(pj, bf16_lo(vr.z), o[4]); o[5] = fmaf(pj, bf16_hi(vr.z), o[5]);
+    o[6] = fmaf(pj, bf16_lo(vr.w), o[6]); o[7] = fmaf(pj, bf16_hi(vr.w), o[7]);
   }
   // ---- merge the 4 lane groups of the warp (same dims c, different keys)
+  float m_run = m_g, l_run = l_g;
 #pragma unroll
   for (int off = 8; off <= 16; off <<= 1) {
     const float m_o = __shfl_xor_sync(0xffffffffu, m_run, off);
@@ -370,63 +440,86 @@ __global__ void __launch_bounds__(128) xattn_decode_kernel(const XDecParams p) {
   }
   __syncthreads();
   // ---- merge the 4 warps, write the chunk partial (o[64], m, l)
+  const size_t pbase = (static_cast<size_t>(b) * p.H + h) * p.splits;
   if (tid < 64) {
     const float m = fmaxf(fmaxf(s_m[0], s_m[1]), fmaxf(s_m[2], s_m[3]));
     float ov = 0.f, l = 0.f;
 #pragma unroll
     for (int w = 0; w < 4; ++w) {
-      const float sc = (s_m[w] == -INFINITY) ? 0.f : fast_exp2((s_m[w] - m) * DC_LOG2E);
-      ov += s_o[w][tid] * sc;
-      l += s_l[w] * sc;
+      const float scw = (s_m[w] == -INFINITY) ? 0.f : fast_exp2((s_m[w] - m) * DC_LOG2E);
+      ov += s_o[w][tid] * scw;
+      l += s_l[w] * scw;
     }
-    float* part = p.part + ((static_cast<size_t>(b) * p.H + h) * p.splits + split) * 66;
+    float* part = p.part + (pbase + split) * 66;
     part[tid] = ov;
     if (tid == 0) {
       part[64] = m;
       part[65] = l;
     }
   }
-}
-
-// out[b][h*64+d] = sum_s w_s o_s / sum_s w_s l_s over the chunk partials of (b, h); 64 threads
-__global__ void __launch_bounds__(64) xattn_decode_combine_kernel(const float* __restrict__ part,
-                                                                  __nv_bfloat16* __restrict__ out, int H, int splits,
-                                                                  int ldo, const int* __restrict__ cu, int npsg) {
-  pdl_launch_dependents();
-  pdl_wait();
-  const int h = blockIdx.x, b = blockIdx.y, d = threadIdx.x;
-  int ns = splits;
-  if (cu) ns = (cu[(b + 1) * npsg] - cu[b * npsg] + XD_CH - 1) / XD_CH;
-  const float* pp = part + (static_cast<size_t>(b) * H + h) * splits * 66;
-  float m = -INFINITY;
-  for (int s = 0; s < ns; ++s) m = fmaxf(m, pp[s * 66 + 64]);
-  float l = 0.f, o = 0.f;
-  for (int s = 0; s < ns; ++s) {
-    const float w = fast_exp2((pp[s * 66 + 64] - m) * DC_LOG2E);
-    l += w * pp[s * 66 + 65];
-    o += w * pp[s * 66 + d];
+  // ---- last CTA of this (question, head): combine the chunk partials
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) {
+    const int ns = (Mb + XD_CH - 1) / XD_CH;
+    const int prev = atomicAdd(&p.counters[b * p.H + h], 1);
+    s_last = (prev == ns - 1) ? ns : 0;
+    if (prev == ns - 1) p.counters[b * p.H + h] = 0;  // ready for the next launch
   }
-  out[static_cast<size_t>(b) * ldo + h * 64 + d] = __float2bfloat16(o / l);
+  __syncthreads();
+  const int ns = s_last;
+  if (ns == 0) return;
+  __threadfence();
+  if (tid < 64) {
+    const float* pp = p.part + pbase * 66;
+    float m = -INFINITY;
+    for (int s2 = 0; s2 < ns; ++s2) m = fmaxf(m, __ldcg(pp + s2 * 66 + 64));
+    float l = 0.f, ov = 0.f;
+#pragma unroll 4
+    for (int s2 = 0; s2 < ns; ++s2) {
+      const float w = fast_exp2((__ldcg(pp + s2 * 66 + 64) - m) * DC_LOG2E);
+      l += w * __ldcg(pp + s2 * 66 + 65);
+      ov += w * __ldcg(pp + s2 * 66 + tid);
+    }
+    p.out[static_cast<size_t>(b) * p.ldo + h * 64 + tid] = __float2bfloat16(ov / l);
+    if (p.q_zero) p.q_zero[static_cast<size_t>(b) * p.ldq + h * 64 + tid] = 0.f;
+  }
 }
 
 }  // namespace
 
 size_t xattn_decode_workspace_bytes(int B, int H, int M) {
-  return static_cast<size_t>(B) * H * ((M + XD_CH - 1) / XD_CH) * 66 * sizeof(float);
+  // chunk partials + one arrival counter per (question, head)
+  return static_cast<size_t>(B) * H * ((M + XD_CH - 1) / XD_CH) * 66 * sizeof(float) + static_cast<size_t>(B) * H * sizeof(int) + 256;
 }
 
-int xattn_decode(const __nv_bfloat16* q, const __nv_bfloat16* kv, const unsigned char* mask, __nv_bfloat16* out,
+// q fp32 [B][ldq]; kv bf16 rows of pitch ldkv (kv_rows of them); workspace must be zero before the FIRST call (the
+// kernel leaves its counters zeroed again).  zero_q: clear each question's query slice after use (the K-split
+// projection that produces q accumulates into it).
+int xattn_decode(const float* q, const __nv_bfloat16* kv, size_t kv_rows, const unsigned char* mask, __nv_bfloat16* out,
                  float* tok_score, const int* step, float* workspace, int B, int M, int H, int ldq, int ldkv, int koff,
-                 int voff, int ldo, cudaStream_t s, const int* cu, int npsg, const int* tok_index) {
-  LAKO_REQUIRE(B > 0 && M > 0 && H > 0, LAKO_ERR_BAD_ARG);
-  LAKO_REQUIRE(ldq % 8 == 0 && ldkv % 8 == 0 && koff % 8 == 0 && voff % 8 == 0, LAKO_ERR_BAD_ARG);
-  XDecParams p{q, kv, mask, workspace, tok_score, step, cu, tok_index, M, H, ldq, ldkv, koff, voff, (M + XD_CH - 1) / XD_CH,
-               npsg};
+                 int voff, int ldo, cudaStream_t s, const int* cu, int npsg, const int* tok_index, bool zero_q) {
+  LAKO_REQUIRE(B > 0 && M > 0 && H > 0 && kv_rows > 0, LAKO_ERR_BAD_ARG);
+  LAKO_REQUIRE(ldq % 4 == 0 && ldkv % 8 == 0 && koff % 8 == 0 && voff % 8 == 0, LAKO_ERR_BAD_ARG);
+  const int splits = (M + XD_CH - 1) / XD_CH;
+  int* counters = reinterpret_cast<int*>(workspace + static_cast<size_t>(B) * H * splits * 66);
+  XDecParams p{q, zero_q ? const_cast<float*>(q) : nullptr, mask, workspace, counters, out, tok_score, step, cu, tok_index,
+               M, H, ldq, ldo, koff, voff, splits, npsg};
+  CUtensorMap tm;
+  int rc = get_tensor_map_2d(&tm, kv, static_cast<uint64_t>(ldkv), kv_rows, static_cast<uint64_t>(ldkv), 64, XD_CH);
+  if (rc) return rc;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(xattn_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, XD_SMEM);
+    if (e != cudaSuccess) {
+      set_last_error(cudaGetErrorString(e), __FILE__, __LINE__);
+      return LAKO_ERR_LAUNCH;
+    }
+    configured = true;
+  }
   // algorithmic bytes: K and V rows of every memory token of the batch for this layer
   ProfScope prof(PROF_XATTN, 4.0 * B * H * static_cast<double>(M) * 64, s);
-  launch_pdl(xattn_decode_kernel, dim3(p.splits, H, B), dim3(128), 0, s, p);
-  LAKO_CHECK_LAUNCH();
-  launch_pdl(xattn_decode_combine_kernel, dim3(H, B), dim3(64), 0, s, workspace, out, H, p.splits, ldo, cu, npsg);
+  launch_pdl(xattn_decode_kernel, dim3(splits, H, B), dim3(128), XD_SMEM, s, tm, p);
   LAKO_CHECK_LAUNCH();
   return LAKO_OK;
 }

@@ -374,9 +374,17 @@ int encode(const Ptrs& p, const lako_fidt5* m, Work& w, const long long* ids, co
   return LAKO_OK;
 }
 
+#include "model_f32.inc"
+
 }  // namespace
 
+// mode 0 eval forward, 1 training forward (+ backward), 2 eval forward with precision = fp32
 extern "C" size_t lako_fidt5_workspace_bytes(const lako_dims* dm, int B, int N, int L, int T, int mode) {
+  if (mode == 2) {
+    WorkF32 wf;
+    carve_f32(*dm, B, N, L, T, T, nullptr, wf);
+    return wf.bytes + 256;
+  }
   Work w;
   carve(*dm, B, N, L, T, mode, nullptr, w);
   return w.bytes + 256;
@@ -389,6 +397,10 @@ extern "C" int lako_fidt5_forward(const lako_fidt5* m, const lako_batch* bt, int
   Ptrs p;
   RC(make_ptrs(m, p));
   LAKO_REQUIRE(bt && bt->ids && bt->mask && bt->labels && bt->workspace && bt->logits && bt->stats, LAKO_ERR_BAD_ARG);
+  if (bt->precision == 1) {
+    LAKO_REQUIRE(mode == 0, LAKO_ERR_UNSUPPORTED);  // evaluation only
+    return forward_f32(m, bt, p, s);
+  }
   LAKO_REQUIRE(bt->T >= 1 && bt->T <= 64 && bt->L >= 1 && bt->L <= 256, LAKO_ERR_UNSUPPORTED);
   Work w;
   carve(m->dims, bt->B, bt->N, bt->L, bt->T, mode, bt->workspace, w);
@@ -599,7 +611,7 @@ namespace {
 struct GenWork {
   Work enc;  // encoder part (eval carve with T=1)
   bf16 *kc, *vc;  // [nl][B][H][Tmax][64]
-  float *lut_dec, *logits, *xdec_ws, *tok_first, *tok_last;
+  float *lut_dec, *logits, *xdec_ws, *tok_first, *tok_last, *q_f32;
   int *unfinished, *n_unf, *d_step, *d_done, *cu_copy;
   unsigned char* mask_copy;
   long long *next_ids, *out_ids;
@@ -624,7 +636,8 @@ void carve_gen(const lako_dims& dm, int B, int N, int L, int Tmax, void* base, G
   gw.mask_copy = b.take<unsigned char>(static_cast<size_t>(B) * N * L);
   gw.tok_first = b.take<float>(static_cast<size_t>(B) * N * L);
   gw.tok_last = b.take<float>(static_cast<size_t>(B) * N * L);
-  gw.xdec_ws = b.take<float>(xattn_decode_workspace_bytes(B, dm.n_heads, N * L) / sizeof(float));
+  gw.xdec_ws = b.take<float>(xattn_decode_workspace_bytes(B, dm.n_heads, N * L) / sizeof(float) + 1);
+  gw.q_f32 = b.take<float>(static_cast<size_t>(B) * H * 64);
   gw.bytes = (b.off + 255) & ~size_t(255);
 }
 __global__ void gen_init_kernel(int* unfinished, int* n_unf, int* d_step, int* d_done, long long* next_ids,
@@ -673,11 +686,13 @@ int enqueue_decode_step(const DecodeCtx& c, cudaStream_t s) {
                      d, SL_BF16, 1.f, s));
     RC(dself_step(a.qkv, gw.kc + l * cache_l, gw.vc + l * cache_l, gw.lut_dec, a.ao, B, 0, c.max_length, H, s, gw.d_step));
     RC(smallm_linear(nullptr, a.ao, inner, nullptr, 0.f, p.wb + p.lo.dec_o[l], Y, d, B, d, inner, SL_F32_ADD, 1.f, s));
-    RC(smallm_linear(Y, nullptr, 0, p.wf + p.lo.dec_ln1[l], p.eps, p.wb + p.lo.dec_xq[l], a.q, inner, B, inner, d,
-                     SL_BF16, 1.f, s));
+    // q accumulates (K-split, atomic) into the zeroed fp32 buffer; the cross-attention kernel clears it again after use
+    RC(smallm_linear(Y, nullptr, 0, p.wf + p.lo.dec_ln1[l], p.eps, p.wb + p.lo.dec_xq[l], gw.q_f32, inner, B, inner, d,
+                     SL_F32_ADD, 1.f, s));
     float* ts = c.capture ? ((l < first_half) ? gw.tok_first : gw.tok_last) : nullptr;
-    RC(xattn_decode(a.q, w.kv_all, xmask, a.xo, ts, gw.d_step, gw.xdec_ws, B, w.M, H, inner, nl * 2 * inner,
-                    l * 2 * inner, l * 2 * inner + inner, inner, s, cu, c.N, c.packed ? w.tok_index : nullptr));
+    RC(xattn_decode(gw.q_f32, w.kv_all, static_cast<size_t>(w.Mrows), xmask, a.xo, ts, gw.d_step, gw.xdec_ws, B, w.M, H,
+                    inner, nl * 2 * inner, l * 2 * inner, l * 2 * inner + inner, inner, s, cu, c.N,
+                    c.packed ? w.tok_index : nullptr, true));
     RC(smallm_linear(nullptr, a.xo, inner, nullptr, 0.f, p.wb + p.lo.dec_xo[l], Y, d, B, d, inner, SL_F32_ADD, 1.f, s));
     RC(smallm_linear(Y, nullptr, 0, p.wf + p.lo.dec_ln2[l], p.eps, p.wb + p.lo.dec_wi[l], a.h, ff, B, ff, d, SL_BF16_RELU,
                      1.f, s));
@@ -711,6 +726,33 @@ struct DecodeGraphCache {
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
 };
 thread_local DecodeGraphCache g_dgraph;
+long long g_graph_captures = 0, g_graph_launches = 0, g_graph_failures = 0;
+
+struct GenWorkF32 {
+  WorkF32 w;
+  float *kc, *vc, *logits, *tok_first, *tok_last;
+  int *unfinished, *n_unf, *d_step, *d_done;
+  long long *next_ids, *out_ids;
+  size_t bytes;
+};
+void carve_gen_f32(const lako_dims& dm, int B, int N, int L, int Tmax, void* base, GenWorkF32& gw) {
+  carve_f32(dm, B, N, L, 1, Tmax, base, gw.w);
+  Bump b(base);
+  b.off = gw.w.bytes;
+  const size_t H = dm.n_heads, nl = dm.n_layers;
+  gw.kc = b.take<float>(nl * B * H * Tmax * 64);
+  gw.vc = b.take<float>(nl * B * H * Tmax * 64);
+  gw.logits = b.take<float>(static_cast<size_t>(B) * dm.vocab);
+  gw.tok_first = b.take<float>(static_cast<size_t>(B) * N * L);
+  gw.tok_last = b.take<float>(static_cast<size_t>(B) * N * L);
+  gw.unfinished = b.take<int>(B);
+  gw.n_unf = b.take<int>(1);
+  gw.d_step = b.take<int>(1);
+  gw.d_done = b.take<int>(1);
+  gw.next_ids = b.take<long long>(B);
+  gw.out_ids = b.take<long long>(static_cast<size_t>(B) * Tmax);
+  gw.bytes = (b.off + 255) & ~size_t(255);
+}
 
 int g_decode_graph = -1;
 bool decode_graph_enabled() {
@@ -723,8 +765,19 @@ bool decode_graph_enabled() {
 }  // namespace
 
 extern "C" void lako_set_decode_graph(int on) { g_decode_graph = on ? 1 : 0; }
+extern "C" void lako_decode_graph_stats(long long* captures, long long* launches, long long* failures) {
+  if (captures) *captures = g_graph_captures;
+  if (launches) *launches = g_graph_launches;
+  if (failures) *failures = g_graph_failures;
+}
 
-extern "C" size_t lako_fidt5_generate_workspace_bytes(const lako_dims* dm, int B, int N, int L, int max_length) {
+extern "C" size_t lako_fidt5_generate_workspace_bytes(const lako_dims* dm, int B, int N, int L, int max_length,
+                                                      int precision) {
+  if (precision == 1) {
+    GenWorkF32 gf;
+    carve_gen_f32(*dm, B, N, L, max_length, nullptr, gf);
+    return gf.bytes + 256;
+  }
   GenWork gw;
   carve_gen(*dm, B, N, L, max_length, nullptr, gw);
   return gw.bytes + 256;
@@ -746,30 +799,80 @@ extern "C" int lako_fidt5_generate(const lako_fidt5* m, const lako_batch* bt, in
   Ptrs p;
   RC(make_ptrs(m, p));
   LAKO_REQUIRE(bt && bt->ids && bt->mask && bt->workspace && out_ids && out_len, LAKO_ERR_BAD_ARG);
-  LAKO_REQUIRE(max_length >= 2 && max_length <= 1024 && bt->L <= 256, LAKO_ERR_UNSUPPORTED);
+  LAKO_REQUIRE(max_length >= 2 && max_length <= 1024 && (bt->L <= 256 || bt->precision == 1), LAKO_ERR_UNSUPPORTED);
   LAKO_REQUIRE((tok_score_first == nullptr) == (tok_score_last == nullptr), LAKO_ERR_BAD_ARG);
-  LAKO_REQUIRE(bt->precision == 0, LAKO_ERR_UNSUPPORTED);
-  GenWork gw;
-  carve_gen(m->dims, bt->B, bt->N, bt->L, max_length, bt->workspace, gw);
-  LAKO_REQUIRE(gw.bytes <= bt->workspace_bytes, LAKO_ERR_WORKSPACE);
-  Work& w = gw.enc;
   const int B = bt->B, H = p.H;
-  RC(set_packing(w, bt, s));
-  const bool packed = w.cu != nullptr, capture = tok_score_first != nullptr;
   const size_t ntok = static_cast<size_t>(B) * bt->N * bt->L;
-  if (packed)
-    cudaMemcpyAsync(gw.cu_copy, bt->cu_seqlens, sizeof(int) * (static_cast<size_t>(B) * bt->N + 1), cudaMemcpyDeviceToDevice, s);
-  else
-    cudaMemcpyAsync(gw.mask_copy, bt->mask, ntok, cudaMemcpyDeviceToDevice, s);
-  if (capture) {
-    cudaMemsetAsync(gw.tok_first, 0, sizeof(float) * ntok, s);
-    cudaMemsetAsync(gw.tok_last, 0, sizeof(float) * ntok, s);
+  const bool capture = tok_score_first != nullptr;
+  const bool f32 = bt->precision == 1;
+  GenWork gw;
+  GenWorkF32 gf;
+  PtrsF32 pw{m->w_tf32_hi, m->w_tf32_lo};
+  bool packed = false;
+  int *d_n_unf = nullptr;
+  long long* d_out_ids = nullptr;
+  float *d_tok_first = nullptr, *d_tok_last = nullptr;
+  if (f32) {
+    LAKO_REQUIRE(m->w_tf32_hi && m->w_tf32_lo, LAKO_ERR_BAD_ARG);
+    carve_gen_f32(m->dims, B, bt->N, bt->L, max_length, bt->workspace, gf);
+    LAKO_REQUIRE(gf.bytes <= bt->workspace_bytes, LAKO_ERR_WORKSPACE);
+    WorkF32& w = gf.w;
+    if (bt->cu_seqlens) {
+      LAKO_REQUIRE(bt->packed_tokens > 0 && bt->packed_tokens <= w.Mtok, LAKO_ERR_BAD_ARG);
+      w.cu = bt->cu_seqlens;
+      w.Mrows = bt->packed_tokens;
+    }
+    packed = w.cu != nullptr;
+    if (capture) {
+      cudaMemsetAsync(gf.tok_first, 0, sizeof(float) * ntok, s);
+      cudaMemsetAsync(gf.tok_last, 0, sizeof(float) * ntok, s);
+    }
+    RC(encode_f32(p, pw, m, w, reinterpret_cast<const long long*>(bt->ids), bt->mask, s));
+    RC(build_bias_lut(p.wf + p.lo.dec_relbias, m->dec_buckets, w.lut_dec, H, max_length, m->bucket_center, s));
+    launch_pdl(gen_init_kernel, dim3((B + 127) / 128), dim3(128), 0, s, gf.unfinished, gf.n_unf, gf.d_step, gf.d_done,
+               gf.next_ids, gf.out_ids, B, max_length);
+    LAKO_CHECK_LAUNCH();
+    d_n_unf = gf.n_unf;
+    d_out_ids = gf.out_ids;
+    d_tok_first = gf.tok_first;
+    d_tok_last = gf.tok_last;
+  } else {
+    carve_gen(m->dims, bt->B, bt->N, bt->L, max_length, bt->workspace, gw);
+    LAKO_REQUIRE(gw.bytes <= bt->workspace_bytes, LAKO_ERR_WORKSPACE);
+    Work& w = gw.enc;
+    RC(set_packing(w, bt, s));
+    packed = w.cu != nullptr;
+    if (packed)
+      cudaMemcpyAsync(gw.cu_copy, bt->cu_seqlens, sizeof(int) * (static_cast<size_t>(B) * bt->N + 1), cudaMemcpyDeviceToDevice, s);
+    else
+      cudaMemcpyAsync(gw.mask_copy, bt->mask, ntok, cudaMemcpyDeviceToDevice, s);
+    if (capture) {
+      cudaMemsetAsync(gw.tok_first, 0, sizeof(float) * ntok, s);
+      cudaMemsetAsync(gw.tok_last, 0, sizeof(float) * ntok, s);
+    }
+    cudaMemsetAsync(gw.xdec_ws, 0, xattn_decode_workspace_bytes(B, H, bt->N * bt->L), s);  // arrival counters
+    cudaMemsetAsync(gw.q_f32, 0, sizeof(float) * B * H * 64, s);
+    RC(encode(p, m, w, reinterpret_cast<const long long*>(bt->ids), bt->mask, false, s, Dropper{0, 0, 0.f}));
+    RC(build_bias_lut(p.wf + p.lo.dec_relbias, m->dec_buckets, gw.lut_dec, H, max_length, m->bucket_center, s));
+    launch_pdl(gen_init_kernel, dim3((B + 127) / 128), dim3(128), 0, s, gw.unfinished, gw.n_unf, gw.d_step, gw.d_done,
+               gw.next_ids, gw.out_ids, B, max_length);
+    LAKO_CHECK_LAUNCH();
+    d_n_unf = gw.n_unf;
+    d_out_ids = gw.out_ids;
+    d_tok_first = gw.tok_first;
+    d_tok_last = gw.tok_last;
   }
-  RC(encode(p, m, w, reinterpret_cast<const long long*>(bt->ids), bt->mask, false, s, Dropper{0, 0, 0.f}));
-  RC(build_bias_lut(p.wf + p.lo.dec_relbias, m->dec_buckets, gw.lut_dec, H, max_length, m->bucket_center, s));
-  launch_pdl(gen_init_kernel, dim3((B + 127) / 128), dim3(128), 0, s, gw.unfinished, gw.n_unf, gw.d_step, gw.d_done,
-             gw.next_ids, gw.out_ids, B, max_length);
-  LAKO_CHECK_LAUNCH();
+  // one fp32-mode decode step: embedding of the last token, cached decoder pass, greedy pick (no graph: this mode is
+  // for numerics, its launches go straight to the stream)
+  auto enqueue_step_f32 = [&]() -> int {
+    WorkF32& w = gf.w;
+    RC(embed_gather(gf.next_ids, p.wf + p.lo.shared, w.Y, B, p.d, p.V, s));
+    RC(decoder_f32(p, pw, w, packed ? nullptr : bt->mask, gf.logits, bt->N, gf.kc, gf.vc, max_length, gf.d_step,
+                   capture ? gf.tok_first : nullptr, capture ? gf.tok_last : nullptr, s));
+    RC(greedy_pick(gf.logits, B, p.V, p.V, gf.out_ids, max_length, 0, gf.unfinished, gf.n_unf, gf.next_ids, s, 0, gf.d_step,
+                   gf.d_done, min_length));
+    return LAKO_OK;
+  };
 
   DecodeGraphCache& gc = g_dgraph;
   if (!gc.h_unf) {
@@ -782,7 +885,7 @@ extern "C" int lako_fidt5_generate(const lako_fidt5* m, const lako_batch* bt, in
   DecodeCtx ctx{&p, &gw, B, bt->N, max_length, min_length, packed, capture};
   const GraphKey key{p.wf, p.wb, bt->workspace, p.d, p.H, p.ff, p.nl, p.V, B, bt->N, bt->L, max_length, min_length,
                      packed ? 1 : 0, capture ? 1 : 0, bt->precision};
-  const bool want_graph = decode_graph_enabled() && !gc.broken && !prof_enabled();
+  const bool want_graph = decode_graph_enabled() && !gc.broken && !prof_enabled() && !f32;
   const int nsteps = max_length - 1;
   constexpr int LAG = 2;
   int stop_at = -1;  // first step after which no row is unfinished
@@ -805,12 +908,14 @@ extern "C" int lako_fidt5_generate(const lako_fidt5* m, const lako_batch* bt, in
               cudaGraphInstantiate(&gc.exec, graph, 0) == cudaSuccess) {
             gc.valid = true;
             gc.key = key;
+            ++g_graph_captures;
           }
           if (graph) cudaGraphDestroy(graph);
         }
         if (!gc.valid) {
           cudaGetLastError();
           gc.broken = true;  // this driver cannot capture the step: plain stream launches from now on
+          ++g_graph_failures;
         }
       }
       if (gc.valid) {
@@ -819,11 +924,17 @@ extern "C" int lako_fidt5_generate(const lako_fidt5* m, const lako_batch* bt, in
           return LAKO_ERR_LAUNCH;
         }
         count_launches(gc.kernels);
+        ++g_graph_launches;
         launched = true;
       }
     }
-    if (!launched) RC(enqueue_decode_step(ctx, s));
-    cudaMemcpyAsync(&gc.h_unf[step], gw.n_unf, sizeof(int), cudaMemcpyDeviceToHost, s);
+    if (!launched) {
+      if (f32)
+        RC(enqueue_step_f32());
+      else
+        RC(enqueue_decode_step(ctx, s));
+    }
+    cudaMemcpyAsync(&gc.h_unf[step], d_n_unf, sizeof(int), cudaMemcpyDeviceToHost, s);
     cudaEventRecord(gc.ev[step & 3], s);
     if (step >= LAG) {
       cudaEventSynchronize(gc.ev[(step - LAG) & 3]);
@@ -847,10 +958,10 @@ extern "C" int lako_fidt5_generate(const lako_fidt5* m, const lako_batch* bt, in
   // columns: start token + one per executed step up to and including the step that finished the last row; steps
   // launched beyond it only wrote pad ids (every row was finished), exactly what HF's early stop leaves out
   *out_len = (stop_at >= 0) ? stop_at + 2 : max_length;
-  cudaMemcpyAsync(out_ids, gw.out_ids, sizeof(long long) * B * max_length, cudaMemcpyDeviceToDevice, s);
+  cudaMemcpyAsync(out_ids, d_out_ids, sizeof(long long) * B * max_length, cudaMemcpyDeviceToDevice, s);
   if (capture) {
-    cudaMemcpyAsync(tok_score_first, gw.tok_first, sizeof(float) * ntok, cudaMemcpyDeviceToDevice, s);
-    cudaMemcpyAsync(tok_score_last, gw.tok_last, sizeof(float) * ntok, cudaMemcpyDeviceToDevice, s);
+    cudaMemcpyAsync(tok_score_first, d_tok_first, sizeof(float) * ntok, cudaMemcpyDeviceToDevice, s);
+    cudaMemcpyAsync(tok_score_last, d_tok_last, sizeof(float) * ntok, cudaMemcpyDeviceToDevice, s);
   }
   return LAKO_OK;
 }

@@ -87,10 +87,26 @@ int smallm_linear(const float* x_f32, const __nv_bfloat16* x_b16, int ldx, const
                   const __nv_bfloat16* W, void* y, int ldy, int M, int N, int K, int epi, float alpha, cudaStream_t s);
 enum : int { SL_BF16 = 0, SL_BF16_RELU = 1, SL_F32 = 2, SL_F32_ADD = 3 };
 size_t xattn_decode_workspace_bytes(int B, int H, int M);
-int xattn_decode(const __nv_bfloat16* q, const __nv_bfloat16* kv, const unsigned char* mask, __nv_bfloat16* out,
+int xattn_decode(const float* q, const __nv_bfloat16* kv, size_t kv_rows, const unsigned char* mask, __nv_bfloat16* out,
                  float* tok_score, const int* step, float* workspace, int B, int M, int H, int ldq, int ldkv, int koff,
                  int voff, int ldo, cudaStream_t s, const int* cu = nullptr, int npsg = 1,
-                 const int* tok_index = nullptr);
+                 const int* tok_index = nullptr, bool zero_q = false);
 bool prof_enabled();
+
+// fp32 evaluation mode: gemm_tf32.cu, attn_f32.cu, dec_attn.cu
+int split_tf32(const float* x, float* hi, float* lo, size_t n, cudaStream_t s);
+int gemm_tf32x3(const float* A_hi, const float* A_lo, const float* B_hi, const float* B_lo, float* C, float* C_hi,
+                float* C_lo, int M, int N, int K, int lda, int ldb, int ldc, int relu, float alpha, cudaStream_t s);
+int enc_attn_f32(const float* qkv, const unsigned char* mask, const float* lut, float* out, float* out_hi, float* out_lo,
+                 int P, int L, int H, cudaStream_t s, const int* cu = nullptr);
+size_t xattn_f32_workspace_bytes(int B, int T, int H, int M);
+int xattn_f32(const float* q, const float* kv, const unsigned char* mask, float* out, float* out_hi, float* out_lo,
+              float* tok_score, const int* step, float* workspace, int B, int T, int M, int H, int ldq, int ldkv, int koff,
+              int voff, int ldo, cudaStream_t s, const int* cu = nullptr, int npsg = 1, const int* tok_index = nullptr);
+int rmsnorm_f32(const float* x, const float* delta, float* x_out, const float* w, float* out, float* out_hi, float* out_lo,
+                int rows, int d, float eps, cudaStream_t s);
+int dself_fwd_f32(const float* qkv, const float* lut, float* out_hi, float* out_lo, int B, int T, int H, cudaStream_t s);
+int dself_step_f32(const float* qkv, float* kcache, float* vcache, const float* lut, float* out_hi, float* out_lo, int B,
+                   int pos, int Tmax, int H, cudaStream_t s, const int* pos_dev = nullptr);
 
 }  // namespace lako

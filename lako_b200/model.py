@@ -50,7 +50,8 @@ class _Layout(ctypes.Structure):
 
 class _Model(ctypes.Structure):
     _fields_ = [("dims", _Dims), ("w_f32", ctypes.c_void_p), ("w_bf16", ctypes.c_void_p), ("g_f32", ctypes.c_void_p),
-                ("enc_buckets", ctypes.c_void_p), ("dec_buckets", ctypes.c_void_p), ("bucket_center", ctypes.c_int)]
+                ("enc_buckets", ctypes.c_void_p), ("dec_buckets", ctypes.c_void_p), ("bucket_center", ctypes.c_int),
+                ("w_tf32_hi", ctypes.c_void_p), ("w_tf32_lo", ctypes.c_void_p)]
 
 
 class _Batch(ctypes.Structure):
@@ -188,6 +189,8 @@ class FiDT5(nn.Module):
         self._flat_grad = None
         self._bf16 = None
         self._bf16_version = -1
+        self._tf32 = None
+        self._tf32_version = -1
         self._enc_buckets = bucket_table(True, c.relative_attention_num_buckets, c.relative_attention_max_distance)
         self._dec_buckets = bucket_table(False, c.relative_attention_num_buckets, c.relative_attention_max_distance)
         self._specs = self._param_specs()
@@ -295,6 +298,8 @@ class FiDT5(nn.Module):
             self._anchor = fn(self._anchor.detach()).requires_grad_(True)
         self._bf16 = None
         self._bf16_version = -1
+        self._tf32 = None
+        self._tf32_version = -1
         self._ws = {}
         self._tok_first = self._tok_last = None
         self._rebind()
@@ -459,11 +464,27 @@ class FiDT5(nn.Module):
             self._bf16 = torch.empty(self._total, dtype=torch.bfloat16, device=self._flat.device)
         self._bf16_version = self._weights_signature()
 
-    def _model_struct(self, with_grad):
+    def _refresh_tf32(self):
+        """(hi, lo) TF32 split of the fp32 masters for precision='fp32' (re-made when the weights change)."""
+        sig = self._weights_signature()
+        if self._tf32 is None or self._tf32_version != sig:
+            if self._master_sync is not None:
+                self._master_sync()
+            if self._tf32 is None:
+                self._tf32 = (torch.empty_like(self._flat), torch.empty_like(self._flat))
+            nat.check(nat.lib().lako_split_tf32(nat.ptr(self._flat), nat.ptr(self._tf32[0]), nat.ptr(self._tf32[1]),
+                                                ctypes.c_size_t(self._total), nat.stream_ptr()), "lako_split_tf32")
+            self._tf32_version = self._weights_signature()
+
+    def _model_struct(self, with_grad, precision=0):
         self._refresh_bf16()
+        hi = lo = 0
+        if precision == 1:
+            self._refresh_tf32()
+            hi, lo = self._tf32[0].data_ptr(), self._tf32[1].data_ptr()
         return _Model(self._dims, self._flat.data_ptr(), self._bf16.data_ptr(),
                       self._flat_grad.data_ptr() if with_grad else 0,
-                      self._enc_buckets.data_ptr(), self._dec_buckets.data_ptr(), BUCKET_CENTER)
+                      self._enc_buckets.data_ptr(), self._dec_buckets.data_ptr(), BUCKET_CENTER, hi, lo)
 
     def _workspace(self, key, nbytes):
         ws = self._ws.get(key[0])
@@ -569,8 +590,8 @@ class FiDT5(nn.Module):
             self._ensure_grad()
         L_ = nat.lib()
         L_.lako_fidt5_workspace_bytes.restype = ctypes.c_size_t
-        nbytes = L_.lako_fidt5_workspace_bytes(ctypes.byref(self._dims), B, N, L, T, mode)
-        ws = self._workspace(("fwd", B, N, L, T, mode), nbytes)
+        nbytes = L_.lako_fidt5_workspace_bytes(ctypes.byref(self._dims), B, N, L, T, 2 if prec == 1 else mode)
+        ws = self._workspace(("fwd", B, N, L, T, mode, prec), nbytes)
         self._ws_gen += 1   # the workspace now holds THIS forward's activations (see _run_backward)
         logits = torch.empty(B, T, self.config.vocab_size, dtype=torch.float32, device=ids.device)
         stats = torch.zeros(2, dtype=torch.float32, device=ids.device)
@@ -586,7 +607,7 @@ class FiDT5(nn.Module):
         drop = (drop_p, self._drop_step & 0xFFFFFFFF, self._drop_seed or 0)
         cu, packed = self._packing(mask, passage_lengths)
         pack = (cu.data_ptr() if cu is not None else 0, packed)
-        m = self._model_struct(with_grad=train)
+        m = self._model_struct(with_grad=train, precision=prec)
         bt = _Batch(ids.data_ptr(), mask.data_ptr(), labels.data_ptr(), B, N, L, T, ws.data_ptr(), ws.numel(),
                     logits.data_ptr(), stats.data_ptr(), count_is_set, *drop, *pack, 0, int(dec_given), prec)
         nat.check(L_.lako_fidt5_forward(ctypes.byref(m), ctypes.byref(bt), mode, nat.stream_ptr()), "lako_fidt5_forward")
@@ -643,8 +664,9 @@ class FiDT5(nn.Module):
         mask = attention_mask.to(torch.bool).contiguous()
         L_ = nat.lib()
         L_.lako_fidt5_generate_workspace_bytes.restype = ctypes.c_size_t
-        nbytes = L_.lako_fidt5_generate_workspace_bytes(ctypes.byref(self._dims), B, N, L, max_length)
-        ws = self._workspace(("gen", B, N, L, max_length), nbytes)
+        prec = self._precision_code(precision)
+        nbytes = L_.lako_fidt5_generate_workspace_bytes(ctypes.byref(self._dims), B, N, L, max_length, prec)
+        ws = self._workspace(("gen", B, N, L, max_length, prec), nbytes)
         out = torch.empty(B, max_length, dtype=torch.long, device=ids.device)
         tf = tl = None
         if self._capture and self._tok_first is None:
@@ -653,9 +675,9 @@ class FiDT5(nn.Module):
             self._tok_last = torch.zeros(B, N * L, dtype=torch.float32, device=ids.device)
             tf, tl = self._tok_first, self._tok_last
         cu, packed = self._packing(mask)
-        m = self._model_struct(with_grad=False)
+        m = self._model_struct(with_grad=False, precision=prec)
         bt = _Batch(ids.data_ptr(), mask.data_ptr(), 0, B, N, L, 1, ws.data_ptr(), ws.numel(), 0, 0, 0, 0.0, 0, 0,
-                    cu.data_ptr() if cu is not None else 0, packed, 0, 0, self._precision_code(precision))
+                    cu.data_ptr() if cu is not None else 0, packed, 0, 0, prec)
         out_len = ctypes.c_int(0)
         nat.check(L_.lako_fidt5_generate(ctypes.byref(m), ctypes.byref(bt), max_length, int(min_length), nat.ptr(out),
                                          ctypes.byref(out_len), nat.ptr(tf), nat.ptr(tl), nat.stream_ptr()),

@@ -93,8 +93,10 @@ def test_no_cpu_fallback():
         assert nat.lib().lako_check_device() != 0
 
 
+@pytest.mark.gpu
 def test_crossattention_score_postprocessing_matches_oracle():
-    """get_crossattention_scores host logic (src/model.py:143-204) on synthetic token scores."""
+    """get_crossattention_scores (src/model.py:143-204; now the device-side lako_fact_scores kernel) on synthetic
+    token scores: equal to the oracle's restatement of the reference's host loop."""
     from lako_b200.model import FiDT5, FiDT5Config
     m = FiDT5(FiDT5Config(vocab_size=512, d_model=128, d_ff=256, num_layers=2, num_heads=2))
     B, N, L = 3, 2, 48
@@ -102,16 +104,16 @@ def test_crossattention_score_postprocessing_matches_oracle():
     g = torch.Generator().manual_seed(0)
     first = torch.randn(B, N * L, generator=g) * mask.reshape(B, -1)
     last = torch.randn(B, N * L, generator=g) * mask.reshape(B, -1)
-    m._tok_first, m._tok_last = first, last
+    m._tok_first, m._tok_last = first.cuda(), last.cuda()
     for style in ("mean", "max", "21mean"):
         for lh in ("yes", "no"):
             opt = types.SimpleNamespace(stream=2, n_context=5, attention_score_style=style,
                                         use_last_half_layer_attention=lh)
-            got = m.get_crossattention_scores(opt, ids, None, mask)
+            got = m.get_crossattention_scores(opt, ids, None, mask.cuda())
             tok = (last if lh == "yes" else first + last).view(B, N, L)
             div = (1 if lh == "yes" else 2) * 2
             ref = O.fact_scores_from_token_scores(tok, ids, 5, style, div)
-            assert got.dtype == torch.float64 and torch.allclose(got, ref)
+            assert got.dtype == torch.float64 and not got.is_cuda and torch.equal(got, ref)
 
 
 def test_schedule_matches_oracle():

@@ -86,9 +86,10 @@ def test_xattn_decode(packed, B, N, L, H):
     M = N * L
     lens = torch.randint(int(0.5 * L), L + 1, (B, N))
     mask = (torch.arange(L)[None, None] < lens[..., None]).cuda()
-    q = (torch.randn(B, inner, device="cuda") * 0.6).to(torch.bfloat16)
+    q = (torch.randn(B, inner, device="cuda") * 0.6).to(torch.bfloat16).float()   # fp32 buffer, bf16-representable values
+    q_keep = q.clone()
     step = torch.zeros(1, dtype=torch.int32, device="cuda")
-    ws = torch.empty(lib.lako_xattn_decode_workspace_bytes(B, H, M), dtype=torch.uint8, device="cuda")
+    ws = torch.zeros(lib.lako_xattn_decode_workspace_bytes(B, H, M), dtype=torch.uint8, device="cuda")
     out = torch.zeros(B, inner, device="cuda", dtype=torch.bfloat16)
     tok = torch.zeros(B, M, device="cuda")
     if packed:
@@ -103,12 +104,16 @@ def test_xattn_decode(packed, B, N, L, H):
         kv = (torch.randn(B * M, ld, device="cuda") * 0.6).to(torch.bfloat16)
         flat_mask = mask.reshape(B, M).contiguous()
         args = (nat.ptr(flat_mask), None, c_int(N), None)
-    for it in range(2):   # second call: step != 0 -> no capture
-        nat.check(lib.lako_xattn_decode(nat.ptr(q), nat.ptr(kv), args[0], nat.ptr(out), nat.ptr(tok), nat.ptr(step), nat.ptr(ws),
-                                        c_int(B), c_int(M), c_int(H), c_int(inner), c_int(ld), c_int(koff), c_int(voff),
-                                        c_int(inner), args[1], args[2], args[3], nat.stream_ptr()))
+    for it in range(2):   # second call: step != 0 -> no capture; the last call also clears q (zero_q)
+        nat.check(lib.lako_xattn_decode(nat.ptr(q), nat.ptr(kv), ctypes.c_size_t(kv.shape[0]), args[0], nat.ptr(out), nat.ptr(tok),
+                                        nat.ptr(step), nat.ptr(ws), c_int(B), c_int(M), c_int(H), c_int(inner), c_int(ld),
+                                        c_int(koff), c_int(voff), c_int(inner), args[1], args[2], args[3], c_int(it),
+                                        nat.stream_ptr()))
         step.fill_(1)
     torch.cuda.synchronize()
+    assert int(q.abs().sum()) == 0          # cleared for the next accumulating projection
+    assert int(ws.view(torch.int32)[-(B * H + 64):].abs().sum()) == 0   # arrival counters left at zero
+    q = q_keep
     for b in range(B):
         if packed:
             r0, r1 = int(cu[b * N]), int(cu[(b + 1) * N])
@@ -139,18 +144,26 @@ def test_generate_graph_replay_equals_stream_launches():
     model.overwrite_forward_crossattention()
     ids, mask, _ = O.synth_batch(6, 3, 40, 4, cfg.vocab, seed=9, fact_format=True)
     res = []
+    stats = []
     for graph in (1, 0, 1):
         nat.lib().lako_set_decode_graph(graph)
         model.reset_score_storage()
         out = model.generate(ids.cuda(), mask.cuda(), max_length=12, min_length=12)
         tok, _ = model.token_scores(last_half=False)
         res.append((out.clone(), tok.clone()))
+        cap, lau, fail = ctypes.c_longlong(0), ctypes.c_longlong(0), ctypes.c_longlong(0)
+        nat.lib().lako_decode_graph_stats(ctypes.byref(cap), ctypes.byref(lau), ctypes.byref(fail))
+        stats.append((cap.value, lau.value, fail.value))
     nat.lib().lako_set_decode_graph(1)
+    # the first call captured the step and replayed it for steps 1..10; the second launched everything directly; the
+    # third reused the cached graph (same workspace and weights)
+    assert stats[0][2] == 0 and stats[0][1] >= 10
+    assert stats[1][1] == stats[0][1] and stats[2][1] == stats[1][1] + 10 and stats[2][0] == stats[0][0]
     ref, storage = O.fidt5_generate(sd, cfg, ids, mask, 12, capture_scores=True, min_length=12)
     assert res[0][0].shape[1] == 12
     for out, tok in res[1:]:
         assert torch.equal(out, res[0][0])
-        assert torch.equal(tok, res[0][1])
+        assert torch.allclose(tok, res[0][1], atol=1e-4, rtol=1e-5)   # fp32 atomics: order-dependent last bits
     assert res[0][0].cpu().tolist() == ref.tolist()
 
 
