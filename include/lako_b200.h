@@ -52,6 +52,12 @@ int lako_check_device(void); /* 0 iff the current device is sm_100 */
  *       width, 512 = CTA-pair kernel (256x256 per 2-CTA cluster). */
 int lako_gemm_bf16(const void* A, const void* B, void* C, int M, int N, int K, int lda, int ldb, int ldc, int a_mn,
                    int b_mn, int epi, float alpha, const void* aux, int ld_aux, int splitk, int bn, void* stream);
+/* Same product (A [M][lda], B [N][ldb], both K-major, bf16 store) with C written HEAD-MAJOR: C[n / 64][m][n % 64], one
+ * contiguous [M][64] slab per 64-column head (N % 64 == 0), through the CTA-pair kernel's 3D TMA-store epilogue.  Used by
+ * lako_fidt5_generate for the cross-attention K/V projection of all decoder layers (src/model.py:311-312), so that every
+ * decode step streams contiguous K / V slabs. */
+int lako_gemm_bf16_head_major(const void* A, const void* B, void* C, int M, int N, int K, int lda, int ldb, float alpha,
+                              void* stream);
 /* nbatch same-shape weight-gradient products in one launch: C_z[M][ldc] (fp32) += alpha * A_z^T B_z with
    A_z row-major [K][lda >= M], B_z row-major [K][ldb >= N] (host arrays of device pointers).  Replaces the per-layer
    dW accumulation autograd performs for every decoder Linear (HF modeling_t5.py: nn.Linear backward of
@@ -253,11 +259,13 @@ int lako_smallm_linear(const float* x_f32, const void* x_bf16, int ldx, const fl
  * capture of src/model.py:327-329.  The flash-decoding combine of the 256-key chunks is done by the last chunk CTA
  * to arrive; `workspace` (lako_xattn_decode_workspace_bytes) must be ZERO before the first call and is left with its
  * arrival counters zeroed.  zero_q != 0: q[b][64 h .. 64 h + 64) is cleared once (b, h) is finished (the K-split
- * projection that produces q accumulates into it). */
+ * projection that produces q accumulates into it).  head_major != 0: kv is stored [ldkv/64][kv_rows][64] (one contiguous
+ * slab per 64-column head, what lako_fidt5_generate's K/V projection writes) instead of row-major [kv_rows][ldkv]. */
 size_t lako_xattn_decode_workspace_bytes(int B, int H, int M);
 int lako_xattn_decode(const float* q, const void* kv, size_t kv_rows, const unsigned char* mask, void* out,
                       float* tok_score, const int* step, float* workspace, int B, int M, int H, int ldq, int ldkv, int koff,
-                      int voff, int ldo, const int* cu, int npsg, const int* tok_index, int zero_q, void* stream);
+                      int voff, int ldo, const int* cu, int npsg, const int* tok_index, int zero_q, int head_major,
+                      void* stream);
 /* decoder self-attention of the token at position pos (or *pos_dev when not NULL) against the KV cache
  * [B][H][Tmax][64] (appends this step's k, v first); qkv bf16 [B][3*H*64], lut fp32 [H][2*Tmax-1] causal buckets */
 int lako_dself_step(const void* qkv, void* kcache, void* vcache, const float* lut, void* out, int B, int pos, int Tmax,

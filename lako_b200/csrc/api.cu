@@ -126,10 +126,11 @@ int lako_smallm_linear(const float* x_f32, const void* x_bf16, int ldx, const fl
 size_t lako_xattn_decode_workspace_bytes(int B, int H, int M) { return xattn_decode_workspace_bytes(B, H, M); }
 int lako_xattn_decode(const float* q, const void* kv, size_t kv_rows, const unsigned char* mask, void* out,
                       float* tok_score, const int* step, float* workspace, int B, int M, int H, int ldq, int ldkv, int koff,
-                      int voff, int ldo, const int* cu, int npsg, const int* tok_index, int zero_q, void* stream) {
+                      int voff, int ldo, const int* cu, int npsg, const int* tok_index, int zero_q, int head_major,
+                      void* stream) {
   ARCH_GUARD();
   return xattn_decode(q, CBF(kv), kv_rows, mask, BF(out), tok_score, step, workspace, B, M, H, ldq, ldkv, koff, voff, ldo,
-                      ST(stream), cu, npsg, tok_index, zero_q != 0);
+                      ST(stream), cu, npsg, tok_index, zero_q != 0, head_major != 0);
 }
 int lako_dself_step(const void* qkv, void* kcache, void* vcache, const float* lut, void* out, int B, int pos, int Tmax,
                     int H, const int* pos_dev, void* stream) {

@@ -327,6 +327,7 @@ struct XDecParams {
   const int* cu;
   const int* tok_index;
   int M, H, ldq, ldo, koff, voff, splits, npsg;
+  long long hm_rows;  // > 0: K/V live head-major, [plane = column / 64][hm_rows tokens][64] (contiguous 32 KB per tile)
 };
 
 // One CTA = 256 keys of one (question, head).  K and V tiles arrive by TMA (issued before the grid dependency: the
@@ -357,10 +358,16 @@ __global__ void __launch_bounds__(128) xattn_decode_kernel(const __grid_constant
     mbar_init(&bar[0], 1);
     mbar_init(&bar[1], 1);
     fence_barrier_init();
+    int kc0 = p.koff + h * 64, kr0 = kstart + k0, vc0 = p.voff + h * 64, vr0 = kstart + k0;
+    if (p.hm_rows > 0) {  // row of the [planes * tokens][64] view
+      kr0 += static_cast<int>((kc0 >> 6) * p.hm_rows);
+      vr0 += static_cast<int>((vc0 >> 6) * p.hm_rows);
+      kc0 = vc0 = 0;
+    }
     mbar_arrive_expect_tx(&bar[0], XD_TILE);
-    tma_load_2d(sK, &tm_kv, &bar[0], p.koff + h * 64, kstart + k0);
+    tma_load_2d(sK, &tm_kv, &bar[0], kc0, kr0);
     mbar_arrive_expect_tx(&bar[1], XD_TILE);
-    tma_load_2d(sV, &tm_kv, &bar[1], p.voff + h * 64, kstart + k0);
+    tma_load_2d(sV, &tm_kv, &bar[1], vc0, vr0);
   }
   __syncthreads();  // barrier initialisation visible to the waiting threads
   pdl_wait();
@@ -498,15 +505,22 @@ size_t xattn_decode_workspace_bytes(int B, int H, int M) {
 // projection that produces q accumulates into it).
 int xattn_decode(const float* q, const __nv_bfloat16* kv, size_t kv_rows, const unsigned char* mask, __nv_bfloat16* out,
                  float* tok_score, const int* step, float* workspace, int B, int M, int H, int ldq, int ldkv, int koff,
-                 int voff, int ldo, cudaStream_t s, const int* cu, int npsg, const int* tok_index, bool zero_q) {
+                 int voff, int ldo, cudaStream_t s, const int* cu, int npsg, const int* tok_index, bool zero_q,
+                 bool head_major) {
   LAKO_REQUIRE(B > 0 && M > 0 && H > 0 && kv_rows > 0, LAKO_ERR_BAD_ARG);
   LAKO_REQUIRE(ldq % 4 == 0 && ldkv % 8 == 0 && koff % 8 == 0 && voff % 8 == 0, LAKO_ERR_BAD_ARG);
+  LAKO_REQUIRE(!head_major || (ldkv % 64 == 0 && koff % 64 == 0 && voff % 64 == 0 &&
+                               static_cast<uint64_t>(ldkv / 64) * kv_rows < (1ull << 31)), LAKO_ERR_UNSUPPORTED);
   const int splits = (M + XD_CH - 1) / XD_CH;
   int* counters = reinterpret_cast<int*>(workspace + static_cast<size_t>(B) * H * splits * 66);
   XDecParams p{q, zero_q ? const_cast<float*>(q) : nullptr, mask, workspace, counters, out, tok_score, step, cu, tok_index,
-               M, H, ldq, ldo, koff, voff, splits, npsg};
+               M, H, ldq, ldo, koff, voff, splits, npsg, head_major ? static_cast<long long>(kv_rows) : 0};
   CUtensorMap tm;
-  int rc = get_tensor_map_2d(&tm, kv, static_cast<uint64_t>(ldkv), kv_rows, static_cast<uint64_t>(ldkv), 64, XD_CH);
+  int rc;
+  if (head_major)  // [ldkv/64 planes][kv_rows][64] seen as one tall [planes * kv_rows][64] matrix
+    rc = get_tensor_map_2d(&tm, kv, 64, static_cast<uint64_t>(ldkv / 64) * kv_rows, 64, 64, XD_CH);
+  else
+    rc = get_tensor_map_2d(&tm, kv, static_cast<uint64_t>(ldkv), kv_rows, static_cast<uint64_t>(ldkv), 64, XD_CH);
   if (rc) return rc;
   static bool configured = false;
   if (!configured) {

@@ -41,6 +41,8 @@ struct GemmParams {
   int tiles_m, tiles_n, splitk, kb_total, kb_per_split;
   float alpha;
   DropSpec drop;  // EPI_BF16_RELU only: dropout after the activation (HF:95), element index = row * ldc + col
+  int c_head_major;  // bf16 TMA epilogue: C is stored as [N/64][M][64] (one contiguous slab per 64-column head) through a
+                     // 3D tensor map -- the layout the decode cross-attention streams
 };
 
 // Epilogue of one 128-row x BN-column accumulator tile for a warp owning TMEM lane quarter q: its 64-column
@@ -140,7 +142,10 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t t_ac
           fence_proxy_async_smem();  // generic-proxy writes of the slot -> visible to the TMA (async proxy)
           __syncwarp();
           if (lane == 0) {
-            tma_store_2d(tmC, stg, col0, m0 + q * 32);
+            if (p.c_head_major)
+              tma_store_3d(tmC, stg, 0, m0 + q * 32, col0 >> 6);
+            else
+              tma_store_2d(tmC, stg, col0, m0 + q * 32);
             tma_store_commit();
           }
           continue;
@@ -700,7 +705,7 @@ static int dispatch_major(int a_mn, int b_mn, int epi, const CUtensorMap& tmA, c
 //  splitk<=0 -> chosen automatically (only for EPI_F32_ATOMIC); bn: 0 auto, 128 or 256.
 int gemm_bf16(const void* A, const void* B, void* C, int M, int N, int K, int lda, int ldb, int ldc, int a_mn,
               int b_mn, int epi, float alpha, const void* aux, int ld_aux, int splitk, int bn, cudaStream_t stream,
-              DropSpec drop) {
+              DropSpec drop, int c_head_major) {
   int rc = check_arch();
   if (rc) return rc;
   LAKO_REQUIRE(M > 0 && N > 0 && K > 0, LAKO_ERR_BAD_ARG);
@@ -717,6 +722,10 @@ int gemm_bf16(const void* A, const void* B, void* C, int M, int N, int K, int ld
 
   const int sms = device_sm_count();
   // bn: 0 = auto, 128 / 256 = single-CTA kernel with that tile width, 512 = CTA-pair kernel (256x256 per cluster)
+  if (c_head_major) {  // [N/64][M][64] output: only the CTA-pair kernel's TMA-store epilogue writes it
+    LAKO_REQUIRE(epi == EPI_BF16 && N % 64 == 0, LAKO_ERR_UNSUPPORTED);
+    bn = 512;
+  }
   bool use_pair = (bn == 512);
   if (bn == 0 && M >= 512 && N >= 256) {
     // the pair kernel needs ~1/3 less L2->SM operand traffic per FLOP; use it whenever the problem fills the chip
@@ -739,6 +748,7 @@ int gemm_bf16(const void* A, const void* B, void* C, int M, int N, int K, int ld
   p.ld_aux = ld_aux;
   p.alpha = alpha;
   p.drop = drop;
+  p.c_head_major = c_head_major;
   p.tiles_m = use_pair ? (M + 255) / 256 : (M + BM - 1) / BM;
   p.tiles_n = (N + bn - 1) / bn;
   p.kb_total = (K + BK - 1) / BK;
@@ -789,7 +799,11 @@ int gemm_bf16(const void* A, const void* B, void* C, int M, int N, int K, int ld
         const char* e = getenv("LAKO_TMA_EPILOGUE");
         return !(e && e[0] == '0');
       }();
-      if (tma_epi) {
+      if (c_head_major) {
+        rc = get_tensor_map_3d(&tmC, C, 64, M, N / 64, 64, static_cast<uint64_t>(M) * 64, 64, 32, 1);
+        if (rc) return rc;
+        use_tmc = 1;
+      } else if (tma_epi) {
         rc = get_tensor_map_2d(&tmC, C, N, M, ldc, 64, 32);
         if (rc) return rc;
         use_tmc = 1;
@@ -831,6 +845,7 @@ int gemm_bf16_wgrad_batched(const void* const* A, const void* const* B, float* c
   p.ld_aux = 0;
   p.alpha = alpha;
   p.drop = DropSpec{};
+  p.c_head_major = 0;
   p.tiles_m = (M + 255) / 256;
   p.tiles_n = (N + 255) / 256;
   p.kb_total = (K + BK - 1) / BK;
@@ -879,6 +894,12 @@ int gemm_bf16_wgrad_batched(const void* const* A, const void* const* B, float* c
 extern "C" int lako_gemm_bf16_wgrad_batched(const void* const* A, const void* const* B, float* const* C, int nbatch, int M,
                                             int N, int K, int lda, int ldb, int ldc, float alpha, void* stream) {
   return lako::gemm_bf16_wgrad_batched(A, B, C, nbatch, M, N, K, lda, ldb, ldc, alpha, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int lako_gemm_bf16_head_major(const void* A, const void* B, void* C, int M, int N, int K, int lda, int ldb,
+                                         float alpha, void* stream) {
+  return lako::gemm_bf16(A, B, C, M, N, K, lda, ldb, N, 0, 0, lako::EPI_BF16, alpha, nullptr, 0, 1, 0,
+                         static_cast<cudaStream_t>(stream), lako::DropSpec{}, 1);
 }
 
 extern "C" int lako_gemm_bf16(const void* A, const void* B, void* C, int M, int N, int K, int lda, int ldb, int ldc,

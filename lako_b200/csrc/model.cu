@@ -345,7 +345,7 @@ int make_ptrs(const lako_fidt5* m, Ptrs& p) {
 
 // ---- encoder: ids (P*L) -> mem bf16 [Mtok][d] and kv_all bf16 [Mtok][nl*2*inner]
 int encode(const Ptrs& p, const lako_fidt5* m, Work& w, const long long* ids, const unsigned char* mask, bool train,
-           cudaStream_t s, const Dropper& dr) {
+           cudaStream_t s, const Dropper& dr, bool kv_head_major = false) {
   const int d = p.d, inner = p.inner, ff = p.ff, nl = p.nl, Mt = w.Mrows;
   const unsigned char* amask = w.cu ? nullptr : mask;  // packed rows are all valid tokens
   if (w.cu) RC(build_tok_index(w.cu, w.tok_index, w.P, w.L, s));
@@ -369,7 +369,9 @@ int encode(const Ptrs& p, const lako_fidt5* m, Work& w, const long long* ids, co
   RC(rmsnorm_fwd(w.X[2 * nl - 1], w.delta_enc, w.X[2 * nl], p.wf + p.lo.enc_final_ln, w.mem, w.rstd_enc_final, Mt, d,
                  p.eps, 1.f, s, dr(nl - 1, E_FF), dr(0, E_FINAL)));
   // cross-attention K/V of ALL decoder layers in one GEMM (13.8 % of the model's FLOPs)
-  RC(lin_fwd(w.mem, p.wb + p.lo.dec_xkv, w.kv_all, Mt, nl * 2 * inner, d, EPI_BF16, 1.f, s));
+  // (generate: written head-major, [layer][k|v][head][token][64], so that a decode step streams contiguous slabs)
+  RC(gemm_bf16(w.mem, p.wb + p.lo.dec_xkv, w.kv_all, Mt, nl * 2 * inner, d, d, d, nl * 2 * inner, 0, 0, EPI_BF16, 1.f, nullptr,
+               0, 1, 0, s, DropSpec{}, kv_head_major ? 1 : 0));
   (void)train;
   return LAKO_OK;
 }
@@ -692,7 +694,7 @@ int enqueue_decode_step(const DecodeCtx& c, cudaStream_t s) {
     float* ts = c.capture ? ((l < first_half) ? gw.tok_first : gw.tok_last) : nullptr;
     RC(xattn_decode(gw.q_f32, w.kv_all, static_cast<size_t>(w.Mrows), xmask, a.xo, ts, gw.d_step, gw.xdec_ws, B, w.M, H,
                     inner, nl * 2 * inner, l * 2 * inner, l * 2 * inner + inner, inner, s, cu, c.N,
-                    c.packed ? w.tok_index : nullptr, true));
+                    c.packed ? w.tok_index : nullptr, true, true));
     RC(smallm_linear(nullptr, a.xo, inner, nullptr, 0.f, p.wb + p.lo.dec_xo[l], Y, d, B, d, inner, SL_F32_ADD, 1.f, s));
     RC(smallm_linear(Y, nullptr, 0, p.wf + p.lo.dec_ln2[l], p.eps, p.wb + p.lo.dec_wi[l], a.h, ff, B, ff, d, SL_BF16_RELU,
                      1.f, s));
@@ -724,6 +726,8 @@ struct DecodeGraphCache {
   long long kernels = 0;  // kernel nodes of the captured step
   int* h_unf = nullptr;  // pinned: n_unfinished after every step
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  cudaStream_t stream = nullptr;  // the decode loop's own stream: the caller's may be the legacy default stream, which
+  cudaEvent_t ev_in = nullptr;    // cannot be captured into a graph
 };
 thread_local DecodeGraphCache g_dgraph;
 long long g_graph_captures = 0, g_graph_launches = 0, g_graph_failures = 0;
@@ -852,7 +856,7 @@ extern "C" int lako_fidt5_generate(const lako_fidt5* m, const lako_batch* bt, in
     }
     cudaMemsetAsync(gw.xdec_ws, 0, xattn_decode_workspace_bytes(B, H, bt->N * bt->L), s);  // arrival counters
     cudaMemsetAsync(gw.q_f32, 0, sizeof(float) * B * H * 64, s);
-    RC(encode(p, m, w, reinterpret_cast<const long long*>(bt->ids), bt->mask, false, s, Dropper{0, 0, 0.f}));
+    RC(encode(p, m, w, reinterpret_cast<const long long*>(bt->ids), bt->mask, false, s, Dropper{0, 0, 0.f}, true));
     RC(build_bias_lut(p.wf + p.lo.dec_relbias, m->dec_buckets, gw.lut_dec, H, max_length, m->bucket_center, s));
     launch_pdl(gen_init_kernel, dim3((B + 127) / 128), dim3(128), 0, s, gw.unfinished, gw.n_unf, gw.d_step, gw.d_done,
                gw.next_ids, gw.out_ids, B, max_length);
@@ -881,7 +885,18 @@ extern "C" int lako_fidt5_generate(const lako_fidt5* m, const lako_batch* bt, in
       return LAKO_ERR_DRIVER;
     }
     for (auto& e : gc.ev) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&gc.ev_in, cudaEventDisableTiming);
+    if (cudaStreamCreateWithFlags(&gc.stream, cudaStreamNonBlocking) != cudaSuccess) {
+      set_last_error("cudaStreamCreate failed", __FILE__, __LINE__);
+      return LAKO_ERR_DRIVER;
+    }
   }
+  // everything enqueued so far (encoder, K/V projection, init) is ordered before the decode loop, which runs on the
+  // library's own stream and is joined (synchronised) before this function returns
+  cudaStream_t s_user = s;
+  cudaEventRecord(gc.ev_in, s_user);
+  s = gc.stream;
+  cudaStreamWaitEvent(s, gc.ev_in, 0);
   DecodeCtx ctx{&p, &gw, B, bt->N, max_length, min_length, packed, capture};
   const GraphKey key{p.wf, p.wb, bt->workspace, p.d, p.H, p.ff, p.nl, p.V, B, bt->N, bt->L, max_length, min_length,
                      packed ? 1 : 0, capture ? 1 : 0, bt->precision};
@@ -958,6 +973,7 @@ extern "C" int lako_fidt5_generate(const lako_fidt5* m, const lako_batch* bt, in
   // columns: start token + one per executed step up to and including the step that finished the last row; steps
   // launched beyond it only wrote pad ids (every row was finished), exactly what HF's early stop leaves out
   *out_len = (stop_at >= 0) ? stop_at + 2 : max_length;
+  s = s_user;  // the decode stream is idle (synchronised above): results are copied out on the caller's stream
   cudaMemcpyAsync(out_ids, d_out_ids, sizeof(long long) * B * max_length, cudaMemcpyDeviceToDevice, s);
   if (capture) {
     cudaMemcpyAsync(tok_score_first, d_tok_first, sizeof(float) * ntok, cudaMemcpyDeviceToDevice, s);

@@ -7,7 +7,7 @@ namespace lako {
 // gemm.cu
 int gemm_bf16(const void* A, const void* B, void* C, int M, int N, int K, int lda, int ldb, int ldc, int a_mn,
               int b_mn, int epi, float alpha, const void* aux, int ld_aux, int splitk, int bn, cudaStream_t stream,
-              DropSpec drop = DropSpec{});
+              DropSpec drop = DropSpec{}, int c_head_major = 0);
 int gemm_bf16_wgrad_batched(const void* const* A, const void* const* B, float* const* C, int nbatch, int M, int N, int K,
                             int lda, int ldb, int ldc, float alpha, cudaStream_t stream);
 enum : int { EPI_BF16 = 0, EPI_BF16_RELU = 1, EPI_F32 = 2, EPI_F32_ATOMIC = 3, EPI_BF16_MASK = 4, EPI_BF16_BITMASK = 5 };
@@ -90,7 +90,7 @@ size_t xattn_decode_workspace_bytes(int B, int H, int M);
 int xattn_decode(const float* q, const __nv_bfloat16* kv, size_t kv_rows, const unsigned char* mask, __nv_bfloat16* out,
                  float* tok_score, const int* step, float* workspace, int B, int M, int H, int ldq, int ldkv, int koff,
                  int voff, int ldo, cudaStream_t s, const int* cu = nullptr, int npsg = 1,
-                 const int* tok_index = nullptr, bool zero_q = false);
+                 const int* tok_index = nullptr, bool zero_q = false, bool head_major = false);
 bool prof_enabled();
 
 // fp32 evaluation mode: gemm_tf32.cu, attn_f32.cu, dec_attn.cu

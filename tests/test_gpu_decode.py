@@ -72,9 +72,10 @@ def _xattn_ref(q, kv, koff, voff, H, rows, valid):
     return torch.cat(outs), torch.stack(scs)
 
 
+@pytest.mark.parametrize("head_major", [0, 1])
 @pytest.mark.parametrize("packed", [True, False])
 @pytest.mark.parametrize("B,N,L,H", [(2, 2, 64, 2), (3, 4, 250, 3), (1, 10, 200, 4)])
-def test_xattn_decode(packed, B, N, L, H):
+def test_xattn_decode(packed, B, N, L, H, head_major):
     nat = _nat()
     lib = nat.lib()
     lib.lako_xattn_decode_workspace_bytes.restype = ctypes.c_size_t
@@ -104,11 +105,13 @@ def test_xattn_decode(packed, B, N, L, H):
         kv = (torch.randn(B * M, ld, device="cuda") * 0.6).to(torch.bfloat16)
         flat_mask = mask.reshape(B, M).contiguous()
         args = (nat.ptr(flat_mask), None, c_int(N), None)
+    # head-major storage: [ld/64 planes][rows][64]
+    kv_dev = kv.view(kv.shape[0], ld // 64, 64).transpose(0, 1).contiguous() if head_major else kv
     for it in range(2):   # second call: step != 0 -> no capture; the last call also clears q (zero_q)
-        nat.check(lib.lako_xattn_decode(nat.ptr(q), nat.ptr(kv), ctypes.c_size_t(kv.shape[0]), args[0], nat.ptr(out), nat.ptr(tok),
-                                        nat.ptr(step), nat.ptr(ws), c_int(B), c_int(M), c_int(H), c_int(inner), c_int(ld),
-                                        c_int(koff), c_int(voff), c_int(inner), args[1], args[2], args[3], c_int(it),
-                                        nat.stream_ptr()))
+        nat.check(lib.lako_xattn_decode(nat.ptr(q), nat.ptr(kv_dev), ctypes.c_size_t(kv.shape[0]), args[0], nat.ptr(out),
+                                        nat.ptr(tok), nat.ptr(step), nat.ptr(ws), c_int(B), c_int(M), c_int(H), c_int(inner),
+                                        c_int(ld), c_int(koff), c_int(voff), c_int(inner), args[1], args[2], args[3],
+                                        c_int(it), c_int(head_major), nat.stream_ptr()))
         step.fill_(1)
     torch.cuda.synchronize()
     assert int(q.abs().sum()) == 0          # cleared for the next accumulating projection

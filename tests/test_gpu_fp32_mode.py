@@ -50,7 +50,9 @@ def test_gemm_tf32x3_is_fp32_accurate(M, N, K, relu):
     err = (C.double() - ref).abs().max().item()
     scale = ref.abs().max().item()
     print(f"tf32x3 {M}x{N}x{K}: max err {err:.3e} (max |C| {scale:.2f})")
-    assert err < 4e-6 * max(1.0, scale)
+    # the tensor core's fp32 accumulation truncates instead of rounding to nearest, so the error grows ~K * 2^-24
+    # (measured 5.8e-6 * |C| at K = 768, 3.2e-5 * |C| at K = 4096); a single-pass kind::tf32 product is at 1e-3
+    assert err < (3e-6 + 1.2e-8 * K) * max(1.0, scale)
     assert (C - Ch - Cl).abs().max().item() <= scale * 2.0 ** -20
 
 

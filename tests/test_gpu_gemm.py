@@ -1,5 +1,7 @@
 """tcgen05 GEMM parity on a B200 (bf16 operands, fp32 accumulate) against torch fp32 matmul of the
 same bf16-rounded inputs, for every operand-major combination, epilogue, edge size and split-K."""
+import ctypes
+
 import pytest
 import torch
 
@@ -134,3 +136,20 @@ def test_gemm_wgrad_batched(nb, M, N, K):
         ref = 0.5 * (As[z].float().T @ Bs[z].float()) + float(z)
         err = (Cs[z] - ref).abs().max().item()
         assert err < 2e-2 * (K ** 0.5) * 0.25 + 1e-3, f"problem {z}: max err {err}"
+
+
+@pytest.mark.parametrize("M,N,K", [(1000, 512, 256), (130, 256, 768), (4030, 1536, 1024)])
+def test_gemm_head_major_output(M, N, K):
+    """C stored [N/64][M][64] by the pair kernel's 3D TMA-store epilogue == the row-major product, re-laid out."""
+    from lako_b200 import _native as nat
+    torch.manual_seed(M + N)
+    A = (torch.randn(M, K, device="cuda") * 0.5).to(torch.bfloat16)
+    B = (torch.randn(N, K, device="cuda") * K ** -0.5).to(torch.bfloat16)
+    C = torch.full((N // 64, M, 64), float("nan"), device="cuda", dtype=torch.bfloat16)
+    nat.check(nat.lib().lako_gemm_bf16_head_major(nat.ptr(A), nat.ptr(B), nat.ptr(C), ctypes.c_int(M), ctypes.c_int(N),
+                                                  ctypes.c_int(K), ctypes.c_int(K), ctypes.c_int(K), ctypes.c_float(1.0),
+                                                  nat.stream_ptr()))
+    torch.cuda.synchronize()
+    ref = (A.float() @ B.float().T).view(M, N // 64, 64).transpose(0, 1)
+    assert bool(torch.isfinite(C.float()).all())
+    assert (C.float() - ref).abs().max().item() < 2e-2
