@@ -53,11 +53,12 @@ int lako_check_device(void); /* 0 iff the current device is sm_100 */
 int lako_gemm_bf16(const void* A, const void* B, void* C, int M, int N, int K, int lda, int ldb, int ldc, int a_mn,
                    int b_mn, int epi, float alpha, const void* aux, int ld_aux, int splitk, int bn, void* stream);
 /* Same product (A [M][lda], B [N][ldb], both K-major, bf16 store) with C written HEAD-MAJOR: C[n / 64][m][n % 64], one
- * contiguous [M][64] slab per 64-column head (N % 64 == 0), through the CTA-pair kernel's 3D TMA-store epilogue.  Used by
+ * contiguous slab of plane_rows >= M rows per 64-column head (N % 64 == 0; rows M..plane_rows-1 of a slab are not
+ * touched), through the CTA-pair kernel's 3D TMA-store epilogue.  Used by
  * lako_fidt5_generate for the cross-attention K/V projection of all decoder layers (src/model.py:311-312), so that every
  * decode step streams contiguous K / V slabs. */
-int lako_gemm_bf16_head_major(const void* A, const void* B, void* C, int M, int N, int K, int lda, int ldb, float alpha,
-                              void* stream);
+int lako_gemm_bf16_head_major(const void* A, const void* B, void* C, int M, int N, int K, int lda, int ldb,
+                              int plane_rows, float alpha, void* stream);
 /* nbatch same-shape weight-gradient products in one launch: C_z[M][ldc] (fp32) += alpha * A_z^T B_z with
    A_z row-major [K][lda >= M], B_z row-major [K][ldb >= N] (host arrays of device pointers).  Replaces the per-layer
    dW accumulation autograd performs for every decoder Linear (HF modeling_t5.py: nn.Linear backward of

@@ -18,6 +18,8 @@
 //    step-0 pre-softmax scores (summed over heads) into tok_score on the fly.
 //  * dself_step / greedy_pick variants that read the step index from device memory, so that ONE captured CUDA graph
 //    serves every decode step.
+#include <algorithm>
+
 #include "ops.cuh"
 
 namespace lako {
@@ -311,185 +313,231 @@ int smallm_linear(const float* x_f32, const __nv_bfloat16* x_b16, int ldx, const
 // ------------------------------------------------------------------------------------------------
 namespace {
 
-constexpr int XD_CH = 256;  // keys per CTA (4 warps x 64)
-constexpr int XD_TILE = XD_CH * 128;  // bytes of one 256-key x 64-dim bf16 tile
-constexpr int XD_SMEM = 2 * XD_TILE + 1024 + 64;
+constexpr int XD_CH = 128;            // keys per work item (4 warps x 32)
+constexpr int XD_TILE = XD_CH * 128;  // bytes of one 128-key x 64-dim bf16 tile
+constexpr int XD_STAGES = 3;          // K+V tile pairs in flight per CTA
+constexpr int XD_SMEM = XD_STAGES * 2 * XD_TILE + 1024 + 64;
+constexpr int XD_MAXB = 1024;         // questions per launch (prefix table in shared memory)
 
 struct XDecParams {
   const float* q;            // [B][ldq] fp32 (accumulated by the K-split projection; zeroed again here after use)
   float* q_zero;             // same buffer (non-const) or null: zero q[b][h*64 .. +64) once (b, h) is finished
   const unsigned char* mask; // padded layout only: [B][M]
   float* part;               // [B][H][splits][66]
-  int* counters;             // [B][H] arrival counters of the chunk CTAs (zero between launches)
+  int* counters;             // [B][H] arrival counters of the chunk items (zero between launches)
   __nv_bfloat16* out;        // [B][ldo]
   float* tok_score;          // [B][M] fp32 accumulated when *step == 0 (may be null)
   const int* step;           // device step index (null: always capture when tok_score != null)
   const int* cu;
   const int* tok_index;
-  int M, H, ldq, ldo, koff, voff, splits, npsg;
-  long long hm_rows;  // > 0: K/V live head-major, [plane = column / 64][hm_rows tokens][64] (contiguous 32 KB per tile)
+  int B, M, H, ldq, ldo, koff, voff, splits, npsg;
+  long long hm_rows;  // > 0: K/V live head-major, [plane = column / 64][hm_rows tokens][64] (contiguous 16 KB per tile)
 };
 
-// One CTA = 256 keys of one (question, head).  K and V tiles arrive by TMA (issued before the grid dependency: the
-// K/V cache does not depend on the preceding kernel) into 128B-swizzled shared memory; lane group kg (8 lanes) of warp w
-// owns keys w*64 + j*4 + kg, each lane 8 of the 64 dims.  Scores for the warp's 64 keys are formed while V is still in
-// flight; the last CTA of a (question, head) to arrive merges the chunk partials (flash-decoding combine) and writes
-// the bf16 context row, so no separate combine launch is needed.
+// Persistent CTAs (2 per SM) walk the work items (question, head, 128-key chunk) with a 3-stage ring of K / V tiles fed
+// by TMA: while an item is being reduced, the tiles of the next two are in flight, so every SM keeps ~128 KB of loads
+// outstanding for the whole launch (the one-shot version left the memory system idle during each CTA's compute phase:
+// 3.1 TB/s).  The first tiles are requested before the grid dependency (the K/V cache does not depend on the preceding
+// kernel).  Lane group kg (8 lanes) of warp w owns keys w*32 + j*4 + kg of the item, each lane 8 of the 64 dims.  The
+// last item of a (question, head) to arrive merges the chunk partials (flash-decoding combine) and writes the bf16
+// context row -- no separate combine launch.
 __global__ void __launch_bounds__(128) xattn_decode_kernel(const __grid_constant__ CUtensorMap tm_kv, const XDecParams p) {
   pdl_launch_dependents();
   extern __shared__ uint8_t xd_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(xd_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sK = smem;
-  uint8_t* sV = smem + XD_TILE;
-  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + 2 * XD_TILE);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + XD_STAGES * 2 * XD_TILE);
   __shared__ float s_m[4], s_l[4], s_o[4][64];
   __shared__ int s_last;
-  const int split = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  __shared__ int s_pref[XD_MAXB + 1];  // s_pref[b] = number of work items of questions < b
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, kg = lane >> 3, c = lane & 7;
-  int kstart = b * p.M, Mb = p.M;
-  if (p.cu) {  // written before the encoder ran: older than the immediate predecessor, safe before pdl_wait
-    kstart = p.cu[b * p.npsg];
-    Mb = p.cu[(b + 1) * p.npsg] - kstart;
+  // ---- item table: question b has H * ceil(len_b / 128) items (cu is older than the immediate predecessor: safe here)
+  for (int b = tid; b < p.B; b += 128) {
+    int Mb = p.M;
+    if (p.cu) Mb = p.cu[(b + 1) * p.npsg] - p.cu[b * p.npsg];
+    s_pref[b + 1] = p.H * ((Mb + XD_CH - 1) / XD_CH);
   }
-  const int k0 = split * XD_CH;
-  if (k0 >= Mb) return;  // CTA-uniform
   if (tid == 0) {
+    s_pref[0] = 0;
     tma_prefetch_desc(&tm_kv);
-    mbar_init(&bar[0], 1);
-    mbar_init(&bar[1], 1);
+    for (int i = 0; i < XD_STAGES; ++i) mbar_init(&bar[i], 1);
     fence_barrier_init();
+  }
+  __syncthreads();
+  if (tid == 0)
+    for (int b = 0; b < p.B; ++b) s_pref[b + 1] += s_pref[b];
+  __syncthreads();
+  const int total = s_pref[p.B];
+  auto decode = [&](int t, int& b, int& h, int& k0, int& kstart, int& Mb) {
+    int lo = 0, hi = p.B - 1;  // largest b with s_pref[b] <= t
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (s_pref[mid] <= t) lo = mid; else hi = mid - 1;
+    }
+    b = lo;
+    kstart = b * p.M;
+    Mb = p.M;
+    if (p.cu) {
+      kstart = p.cu[b * p.npsg];
+      Mb = p.cu[(b + 1) * p.npsg] - kstart;
+    }
+    const int ns = (Mb + XD_CH - 1) / XD_CH;
+    const int r = t - s_pref[b];
+    h = r / ns;           // items of one (b, h) are consecutive
+    k0 = (r - h * ns) * XD_CH;
+  };
+  auto issue = [&](int t, int stage) {  // thread 0 only
+    int b, h, k0, kstart, Mb;
+    decode(t, b, h, k0, kstart, Mb);
     int kc0 = p.koff + h * 64, kr0 = kstart + k0, vc0 = p.voff + h * 64, vr0 = kstart + k0;
     if (p.hm_rows > 0) {  // row of the [planes * tokens][64] view
       kr0 += static_cast<int>((kc0 >> 6) * p.hm_rows);
       vr0 += static_cast<int>((vc0 >> 6) * p.hm_rows);
       kc0 = vc0 = 0;
     }
-    mbar_arrive_expect_tx(&bar[0], XD_TILE);
-    tma_load_2d(sK, &tm_kv, &bar[0], kc0, kr0);
-    mbar_arrive_expect_tx(&bar[1], XD_TILE);
-    tma_load_2d(sV, &tm_kv, &bar[1], vc0, vr0);
-  }
-  __syncthreads();  // barrier initialisation visible to the waiting threads
+    uint8_t* st = smem + stage * 2 * XD_TILE;
+    mbar_arrive_expect_tx(&bar[stage], 2 * XD_TILE);
+    tma_load_2d(st, &tm_kv, &bar[stage], kc0, kr0);
+    tma_load_2d(st + XD_TILE, &tm_kv, &bar[stage], vc0, vr0);
+  };
+  if (tid == 0)
+    for (int i = 0; i < XD_STAGES - 1; ++i) {
+      const int t = blockIdx.x + i * gridDim.x;
+      if (t < total) issue(t, i);
+    }
   pdl_wait();
   const bool capture = p.tok_score != nullptr && (p.step == nullptr || *p.step == 0);
-  float qv[8];
-  {
-    const float4 q0 = *reinterpret_cast<const float4*>(p.q + static_cast<size_t>(b) * p.ldq + h * 64 + c * 8);
-    const float4 q1 = *reinterpret_cast<const float4*>(p.q + static_cast<size_t>(b) * p.ldq + h * 64 + c * 8 + 4);
-    qv[0] = q0.x; qv[1] = q0.y; qv[2] = q0.z; qv[3] = q0.w; qv[4] = q1.x; qv[5] = q1.y; qv[6] = q1.z; qv[7] = q1.w;
-  }
-  const int wk0 = warp * 64;  // this warp's keys within the chunk
-  float sc[16];
-  float m_g = -INFINITY;
-  mbar_wait(&bar[0], 0);
-#pragma unroll
-  for (int j = 0; j < 16; ++j) {
-    const int kl = wk0 + j * 4 + kg, key = k0 + kl;
-    const uint4 kr = *reinterpret_cast<const uint4*>(sK + kl * 128 + ((c ^ (kl & 7)) << 4));
-    float s = qv[0] * bf16_lo(kr.x) + qv[1] * bf16_hi(kr.x) + qv[2] * bf16_lo(kr.y) + qv[3] * bf16_hi(kr.y) +
-              qv[4] * bf16_lo(kr.z) + qv[5] * bf16_hi(kr.z) + qv[6] * bf16_lo(kr.w) + qv[7] * bf16_hi(kr.w);
-    s += __shfl_xor_sync(0xffffffffu, s, 1);
-    s += __shfl_xor_sync(0xffffffffu, s, 2);
-    s += __shfl_xor_sync(0xffffffffu, s, 4);
-    if (key >= Mb) {
-      s = -INFINITY;  // rows past this question's memory (the next question's rows / TMA zero fill)
-    } else {
-      bool valid = true;
-      if (p.mask) valid = p.mask[static_cast<size_t>(b) * p.M + key] != 0;
-      if (capture && valid && c == 0) {
-        const size_t ti = p.tok_index ? static_cast<size_t>(p.tok_index[kstart + key]) : static_cast<size_t>(b) * p.M + key;
-        atomicAdd(p.tok_score + ti, s);
-      }
-      if (!valid) s += DC_MASK_MIN;  // HF's additive mask (finfo.min): a fully masked question degrades to uniform
-    }
-    sc[j] = s;
-    m_g = fmaxf(m_g, s);
-  }
-  float l_g = 0.f, o[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) o[i] = 0.f;
-  mbar_wait(&bar[1], 0);
-#pragma unroll
-  for (int j = 0; j < 16; ++j) {
-    const int kl = wk0 + j * 4 + kg;
-    const float pj = (m_g == -INFINITY) ? 0.f : fast_exp2((sc[j] - m_g) * DC_LOG2E);
-    l_g += pj;
-    const uint4 vr = *reinterpret_cast<const uint4*>(sV + kl * 128 + ((c ^ (kl & 7)) << 4));
-    o[0] = fmaf(pj, bf16_lo(vr.x), o[0]); o[1] = fmaf(pj, bf16_hi(vr.x), o[1]);
-    o[2] = fmaf(pj, bf16_lo(vr.y), o[2]); o[3] = fmaf(pj, bf16_hi(vr.y), o[3]);
-    o[4] = fmaf(pj, bf16_lo(vr.z), o[4]); o[5] = fmaf(pj, bf16_hi(vr.z), o[5]);
-    o[6] = fmaf(pj, bf16_lo(vr.w), o[6]); o[7] = fmaf(pj, bf16_hi(vr.w), o[7]);
-  }
-  // ---- merge the 4 lane groups of the warp (same dims c, different keys)
-  float m_run = m_g, l_run = l_g;
-#pragma unroll
-  for (int off = 8; off <= 16; off <<= 1) {
-    const float m_o = __shfl_xor_sync(0xffffffffu, m_run, off);
-    const float l_o = __shfl_xor_sync(0xffffffffu, l_run, off);
-    const float m_new = fmaxf(m_run, m_o);
-    const float sa = (m_run == -INFINITY) ? 0.f : fast_exp2((m_run - m_new) * DC_LOG2E);
-    const float sb = (m_o == -INFINITY) ? 0.f : fast_exp2((m_o - m_new) * DC_LOG2E);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const float o_o = __shfl_xor_sync(0xffffffffu, o[i], off);
-      o[i] = o[i] * sa + o_o * sb;
-    }
-    l_run = l_run * sa + l_o * sb;
-    m_run = m_new;
-  }
-  if (kg == 0) {
-#pragma unroll
-    for (int i = 0; i < 8; ++i) s_o[warp][c * 8 + i] = o[i];
-    if (c == 0) {
-      s_m[warp] = m_run;
-      s_l[warp] = l_run;
-    }
-  }
-  __syncthreads();
-  // ---- merge the 4 warps, write the chunk partial (o[64], m, l)
-  const size_t pbase = (static_cast<size_t>(b) * p.H + h) * p.splits;
-  if (tid < 64) {
-    const float m = fmaxf(fmaxf(s_m[0], s_m[1]), fmaxf(s_m[2], s_m[3]));
-    float ov = 0.f, l = 0.f;
-#pragma unroll
-    for (int w = 0; w < 4; ++w) {
-      const float scw = (s_m[w] == -INFINITY) ? 0.f : fast_exp2((s_m[w] - m) * DC_LOG2E);
-      ov += s_o[w][tid] * scw;
-      l += s_l[w] * scw;
-    }
-    float* part = p.part + (pbase + split) * 66;
-    part[tid] = ov;
+  uint32_t phase_bits = 0;  // parity of each stage's barrier
+  int it = 0;
+  for (int t = blockIdx.x; t < total; t += gridDim.x, ++it) {
+    const int stage = it % XD_STAGES;
+    // keep two items in flight: the stage that item it + 2 will use was released by the barrier at the end of item it - 1
     if (tid == 0) {
-      part[64] = m;
-      part[65] = l;
+      const int tn = t + (XD_STAGES - 1) * gridDim.x;
+      if (tn < total) issue(tn, (it + XD_STAGES - 1) % XD_STAGES);
     }
-  }
-  // ---- last CTA of this (question, head): combine the chunk partials
-  __threadfence();
-  __syncthreads();
-  if (tid == 0) {
+    int b, h, k0, kstart, Mb;
+    decode(t, b, h, k0, kstart, Mb);
+    float qv[8];
+    {
+      const float4 q0 = *reinterpret_cast<const float4*>(p.q + static_cast<size_t>(b) * p.ldq + h * 64 + c * 8);
+      const float4 q1 = *reinterpret_cast<const float4*>(p.q + static_cast<size_t>(b) * p.ldq + h * 64 + c * 8 + 4);
+      qv[0] = q0.x; qv[1] = q0.y; qv[2] = q0.z; qv[3] = q0.w; qv[4] = q1.x; qv[5] = q1.y; qv[6] = q1.z; qv[7] = q1.w;
+    }
+    const uint8_t* sK = smem + stage * 2 * XD_TILE;
+    const uint8_t* sV = sK + XD_TILE;
+    mbar_wait(&bar[stage], (phase_bits >> stage) & 1u);
+    phase_bits ^= 1u << stage;
+    const int wk0 = warp * 32;  // this warp's keys within the item
+    float sc[8];
+    float m_g = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int kl = wk0 + j * 4 + kg, key = k0 + kl;
+      const uint4 kr = *reinterpret_cast<const uint4*>(sK + kl * 128 + ((c ^ (kl & 7)) << 4));
+      float s = qv[0] * bf16_lo(kr.x) + qv[1] * bf16_hi(kr.x) + qv[2] * bf16_lo(kr.y) + qv[3] * bf16_hi(kr.y) +
+                qv[4] * bf16_lo(kr.z) + qv[5] * bf16_hi(kr.z) + qv[6] * bf16_lo(kr.w) + qv[7] * bf16_hi(kr.w);
+      s += __shfl_xor_sync(0xffffffffu, s, 1);
+      s += __shfl_xor_sync(0xffffffffu, s, 2);
+      s += __shfl_xor_sync(0xffffffffu, s, 4);
+      if (key >= Mb) {
+        s = -INFINITY;  // rows past this question's memory (the next question's rows / next plane / TMA zero fill)
+      } else {
+        bool valid = true;
+        if (p.mask) valid = p.mask[static_cast<size_t>(b) * p.M + key] != 0;
+        if (capture && valid && c == 0) {
+          const size_t ti = p.tok_index ? static_cast<size_t>(p.tok_index[kstart + key]) : static_cast<size_t>(b) * p.M + key;
+          atomicAdd(p.tok_score + ti, s);
+        }
+        if (!valid) s += DC_MASK_MIN;  // HF's additive mask (finfo.min): a fully masked question degrades to uniform
+      }
+      sc[j] = s;
+      m_g = fmaxf(m_g, s);
+    }
+    float l_g = 0.f, o[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o[i] = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int kl = wk0 + j * 4 + kg;
+      const float pj = (m_g == -INFINITY) ? 0.f : fast_exp2((sc[j] - m_g) * DC_LOG2E);
+      l_g += pj;
+      const uint4 vr = *reinterpret_cast<const uint4*>(sV + kl * 128 + ((c ^ (kl & 7)) << 4));
+      o[0] = fmaf(pj, bf16_lo(vr.x), o[0]); o[1] = fmaf(pj, bf16_hi(vr.x), o[1]);
+      o[2] = fmaf(pj, bf16_lo(vr.y), o[2]); o[3] = fmaf(pj, bf16_hi(vr.y), o[3]);
+      o[4] = fmaf(pj, bf16_lo(vr.z), o[4]); o[5] = fmaf(pj, bf16_hi(vr.z), o[5]);
+      o[6] = fmaf(pj, bf16_lo(vr.w), o[6]); o[7] = fmaf(pj, bf16_hi(vr.w), o[7]);
+    }
+    // ---- merge the 4 lane groups of the warp (same dims c, different keys)
+    float m_run = m_g, l_run = l_g;
+#pragma unroll
+    for (int off = 8; off <= 16; off <<= 1) {
+      const float m_o = __shfl_xor_sync(0xffffffffu, m_run, off);
+      const float l_o = __shfl_xor_sync(0xffffffffu, l_run, off);
+      const float m_new = fmaxf(m_run, m_o);
+      const float sa = (m_run == -INFINITY) ? 0.f : fast_exp2((m_run - m_new) * DC_LOG2E);
+      const float sb = (m_o == -INFINITY) ? 0.f : fast_exp2((m_o - m_new) * DC_LOG2E);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float o_o = __shfl_xor_sync(0xffffffffu, o[i], off);
+        o[i] = o[i] * sa + o_o * sb;
+      }
+      l_run = l_run * sa + l_o * sb;
+      m_run = m_new;
+    }
+    if (kg == 0) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) s_o[warp][c * 8 + i] = o[i];
+      if (c == 0) {
+        s_m[warp] = m_run;
+        s_l[warp] = l_run;
+      }
+    }
+    __syncthreads();  // (A) warp partials visible; every thread is done reading this stage's tiles
+    // ---- merge the 4 warps, write the item partial (o[64], m, l)
     const int ns = (Mb + XD_CH - 1) / XD_CH;
-    const int prev = atomicAdd(&p.counters[b * p.H + h], 1);
-    s_last = (prev == ns - 1) ? ns : 0;
-    if (prev == ns - 1) p.counters[b * p.H + h] = 0;  // ready for the next launch
-  }
-  __syncthreads();
-  const int ns = s_last;
-  if (ns == 0) return;
-  __threadfence();
-  if (tid < 64) {
-    const float* pp = p.part + pbase * 66;
-    float m = -INFINITY;
-    for (int s2 = 0; s2 < ns; ++s2) m = fmaxf(m, __ldcg(pp + s2 * 66 + 64));
-    float l = 0.f, ov = 0.f;
-#pragma unroll 4
-    for (int s2 = 0; s2 < ns; ++s2) {
-      const float w = fast_exp2((__ldcg(pp + s2 * 66 + 64) - m) * DC_LOG2E);
-      l += w * __ldcg(pp + s2 * 66 + 65);
-      ov += w * __ldcg(pp + s2 * 66 + tid);
+    const size_t pbase = (static_cast<size_t>(b) * p.H + h) * p.splits;
+    if (tid < 64) {
+      const float m = fmaxf(fmaxf(s_m[0], s_m[1]), fmaxf(s_m[2], s_m[3]));
+      float ov = 0.f, l = 0.f;
+#pragma unroll
+      for (int w = 0; w < 4; ++w) {
+        const float scw = (s_m[w] == -INFINITY) ? 0.f : fast_exp2((s_m[w] - m) * DC_LOG2E);
+        ov += s_o[w][tid] * scw;
+        l += s_l[w] * scw;
+      }
+      float* part = p.part + (pbase + k0 / XD_CH) * 66;
+      part[tid] = ov;
+      if (tid == 0) {
+        part[64] = m;
+        part[65] = l;
+      }
     }
-    p.out[static_cast<size_t>(b) * p.ldo + h * 64 + tid] = __float2bfloat16(ov / l);
-    if (p.q_zero) p.q_zero[static_cast<size_t>(b) * p.ldq + h * 64 + tid] = 0.f;
+    __syncthreads();  // (B) partial stored by this CTA's threads
+    if (tid == 0) {
+      __threadfence();  // cumulative: the CTA's partial is visible device-wide before the arrival is counted
+      const int prev = atomicAdd(&p.counters[b * p.H + h], 1);
+      s_last = (prev == ns - 1) ? 1 : 0;
+      if (prev == ns - 1) p.counters[b * p.H + h] = 0;  // ready for the next launch
+    }
+    __syncthreads();  // (C)
+    if (s_last) {
+      // ---- last item of this (question, head): combine the chunk partials
+      __threadfence();
+      if (tid < 64) {
+        const float* pp = p.part + pbase * 66;
+        float m = -INFINITY;
+        for (int s2 = 0; s2 < ns; ++s2) m = fmaxf(m, __ldcg(pp + s2 * 66 + 64));
+        float l = 0.f, ov = 0.f;
+#pragma unroll 4
+        for (int s2 = 0; s2 < ns; ++s2) {
+          const float w = fast_exp2((__ldcg(pp + s2 * 66 + 64) - m) * DC_LOG2E);
+          l += w * __ldcg(pp + s2 * 66 + 65);
+          ov += w * __ldcg(pp + s2 * 66 + tid);
+        }
+        p.out[static_cast<size_t>(b) * p.ldo + h * 64 + tid] = __float2bfloat16(ov / l);
+        if (p.q_zero) p.q_zero[static_cast<size_t>(b) * p.ldq + h * 64 + tid] = 0.f;
+      }
+    }
   }
 }
 
@@ -513,8 +561,9 @@ int xattn_decode(const float* q, const __nv_bfloat16* kv, size_t kv_rows, const 
                                static_cast<uint64_t>(ldkv / 64) * kv_rows < (1ull << 31)), LAKO_ERR_UNSUPPORTED);
   const int splits = (M + XD_CH - 1) / XD_CH;
   int* counters = reinterpret_cast<int*>(workspace + static_cast<size_t>(B) * H * splits * 66);
+  LAKO_REQUIRE(B <= XD_MAXB, LAKO_ERR_UNSUPPORTED);
   XDecParams p{q, zero_q ? const_cast<float*>(q) : nullptr, mask, workspace, counters, out, tok_score, step, cu, tok_index,
-               M, H, ldq, ldo, koff, voff, splits, npsg, head_major ? static_cast<long long>(kv_rows) : 0};
+               B, M, H, ldq, ldo, koff, voff, splits, npsg, head_major ? static_cast<long long>(kv_rows) : 0};
   CUtensorMap tm;
   int rc;
   if (head_major)  // [ldkv/64 planes][kv_rows][64] seen as one tall [planes * kv_rows][64] matrix
@@ -533,7 +582,10 @@ int xattn_decode(const float* q, const __nv_bfloat16* kv, size_t kv_rows, const 
   }
   // algorithmic bytes: K and V rows of every memory token of the batch for this layer
   ProfScope prof(PROF_XATTN, 4.0 * B * H * static_cast<double>(M) * 64, s);
-  launch_pdl(xattn_decode_kernel, dim3(splits, H, B), dim3(128), XD_SMEM, s, tm, p);
+  // persistent: two CTAs per SM (2 x 96 KB of tile ring), never more CTAs than work items
+  const long long max_items = static_cast<long long>(B) * H * splits;
+  const int grid = static_cast<int>(std::min<long long>(max_items, 2LL * device_sm_count()));
+  launch_pdl(xattn_decode_kernel, dim3(grid), dim3(128), XD_SMEM, s, tm, p);
   LAKO_CHECK_LAUNCH();
   return LAKO_OK;
 }

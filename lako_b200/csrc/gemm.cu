@@ -41,8 +41,8 @@ struct GemmParams {
   int tiles_m, tiles_n, splitk, kb_total, kb_per_split;
   float alpha;
   DropSpec drop;  // EPI_BF16_RELU only: dropout after the activation (HF:95), element index = row * ldc + col
-  int c_head_major;  // bf16 TMA epilogue: C is stored as [N/64][M][64] (one contiguous slab per 64-column head) through a
-                     // 3D tensor map -- the layout the decode cross-attention streams
+  int c_head_major;  // bf16 TMA epilogue: C is stored as [N/64][plane_rows >= M][64] (one contiguous slab per 64-column
+                     // head) through a 3D tensor map -- the layout the decode cross-attention streams
 };
 
 // Epilogue of one 128-row x BN-column accumulator tile for a warp owning TMEM lane quarter q: its 64-column
@@ -800,7 +800,8 @@ int gemm_bf16(const void* A, const void* B, void* C, int M, int N, int K, int ld
         return !(e && e[0] == '0');
       }();
       if (c_head_major) {
-        rc = get_tensor_map_3d(&tmC, C, 64, M, N / 64, 64, static_cast<uint64_t>(M) * 64, 64, 32, 1);
+        LAKO_REQUIRE(c_head_major >= M, LAKO_ERR_BAD_ARG);  // the value is the row capacity of one head's slab
+        rc = get_tensor_map_3d(&tmC, C, 64, M, N / 64, 64, static_cast<uint64_t>(c_head_major) * 64, 64, 32, 1);
         if (rc) return rc;
         use_tmc = 1;
       } else if (tma_epi) {
@@ -897,9 +898,9 @@ extern "C" int lako_gemm_bf16_wgrad_batched(const void* const* A, const void* co
 }
 
 extern "C" int lako_gemm_bf16_head_major(const void* A, const void* B, void* C, int M, int N, int K, int lda, int ldb,
-                                         float alpha, void* stream) {
+                                         int plane_rows, float alpha, void* stream) {
   return lako::gemm_bf16(A, B, C, M, N, K, lda, ldb, N, 0, 0, lako::EPI_BF16, alpha, nullptr, 0, 1, 0,
-                         static_cast<cudaStream_t>(stream), lako::DropSpec{}, 1);
+                         static_cast<cudaStream_t>(stream), lako::DropSpec{}, plane_rows);
 }
 
 extern "C" int lako_gemm_bf16(const void* A, const void* B, void* C, int M, int N, int K, int lda, int ldb, int ldc,

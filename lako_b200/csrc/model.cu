@@ -371,7 +371,8 @@ int encode(const Ptrs& p, const lako_fidt5* m, Work& w, const long long* ids, co
   // cross-attention K/V of ALL decoder layers in one GEMM (13.8 % of the model's FLOPs)
   // (generate: written head-major, [layer][k|v][head][token][64], so that a decode step streams contiguous slabs)
   RC(gemm_bf16(w.mem, p.wb + p.lo.dec_xkv, w.kv_all, Mt, nl * 2 * inner, d, d, d, nl * 2 * inner, 0, 0, EPI_BF16, 1.f, nullptr,
-               0, 1, 0, s, DropSpec{}, kv_head_major ? 1 : 0));
+               0, 1, 0, s, DropSpec{}, kv_head_major ? w.Mtok : 0));  // slab capacity = the padded token count, so the
+                                                                       // layout does not depend on the batch's lengths
   (void)train;
   return LAKO_OK;
 }
@@ -692,7 +693,7 @@ int enqueue_decode_step(const DecodeCtx& c, cudaStream_t s) {
     RC(smallm_linear(Y, nullptr, 0, p.wf + p.lo.dec_ln1[l], p.eps, p.wb + p.lo.dec_xq[l], gw.q_f32, inner, B, inner, d,
                      SL_F32_ADD, 1.f, s));
     float* ts = c.capture ? ((l < first_half) ? gw.tok_first : gw.tok_last) : nullptr;
-    RC(xattn_decode(gw.q_f32, w.kv_all, static_cast<size_t>(w.Mrows), xmask, a.xo, ts, gw.d_step, gw.xdec_ws, B, w.M, H,
+    RC(xattn_decode(gw.q_f32, w.kv_all, static_cast<size_t>(w.Mtok), xmask, a.xo, ts, gw.d_step, gw.xdec_ws, B, w.M, H,
                     inner, nl * 2 * inner, l * 2 * inner, l * 2 * inner + inner, inner, s, cu, c.N,
                     c.packed ? w.tok_index : nullptr, true, true));
     RC(smallm_linear(nullptr, a.xo, inner, nullptr, 0.f, p.wb + p.lo.dec_xo[l], Y, d, B, d, inner, SL_F32_ADD, 1.f, s));

@@ -110,3 +110,30 @@ def test_dp2_sharded_step_host_logic(tmp_path):
     assert torch.allclose(r["w"], ref, atol=1e-6)                       # masters complete after the sync
     assert torch.equal(r["bf16"], ref.to(torch.bfloat16))               # compute weights identical on every rank
     assert not torch.allclose(r["stale"], ref, atol=1e-6)               # ... while foreign master slices were stale
+
+
+def _gather_worker(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from lako_b200.optim import gather_answers_and_scores
+    answers = torch.full((2, 3 + rank), rank + 1, dtype=torch.long)          # ragged widths: early stop differs per rank
+    scores = torch.arange(2 * 4, dtype=torch.float64).reshape(2, 4) + 100 * rank
+    a, s = gather_answers_and_scores(answers, scores, max_length=6)
+    if rank == 1:
+        torch.save((a, s), out)
+    dist.destroy_process_group()
+
+
+def test_inference_gather_of_answers_and_scores(tmp_path):
+    """SURVEY 8(e) inference side: ranks decode their own questions; answers (right-padded to max_length with pad id 0)
+    and per-fact scores are all-gathered in rank order."""
+    out = str(tmp_path / "gather.pt")
+    mp.spawn(_gather_worker, args=(2, 29735, out), nprocs=2, join=True)
+    a, s = torch.load(out)
+    assert a.shape == (4, 6) and s.shape == (4, 4) and s.dtype == torch.float64
+    assert a[:2, :3].eq(1).all() and a[:2, 3:].eq(0).all() and a[2:, :4].eq(2).all() and a[2:, 4:].eq(0).all()
+    assert torch.equal(s[2:], torch.arange(8, dtype=torch.float64).reshape(2, 4) + 100)
+    from lako_b200.optim import gather_answers_and_scores
+    a1, s1 = gather_answers_and_scores(torch.ones(2, 3, dtype=torch.long), torch.zeros(2, 4), max_length=5)
+    assert a1.shape == (2, 5) and s1.shape == (2, 4)      # single process: padded pass-through

@@ -188,3 +188,27 @@ def test_generate_early_stop_matches_oracle_width():
             out = model.generate(ids.cuda(), mask.cuda(), max_length=20).cpu()
             ref, _ = O.fidt5_generate(sd, cfg, ids, mask, 20)
             assert out.shape == ref.shape, (out.shape, ref.shape)
+
+
+def test_generate_cached_graph_survives_a_new_batch():
+    """The captured decode step is reused across generate() calls of the same shape; nothing baked into it may depend
+    on the batch's contents (e.g. the packed token count).  t5-base width so that the K-split / head-major paths run."""
+    from oracle import fidt5_oracle as O
+    from lako_b200.model import FiDT5, FiDT5Config
+    cfg = O.T5Dims(d_model=768, n_heads=12, d_kv=64, d_ff=3072, n_layers=2, vocab=2048)
+    sd = O.perturb_norm_weights(O.init_state_dict(cfg, seed=8, emb_std=0.25), seed=9)
+    model = FiDT5(FiDT5Config(vocab_size=cfg.vocab, d_model=cfg.d_model, d_ff=cfg.d_ff, num_layers=cfg.n_layers,
+                              num_heads=cfg.n_heads, dropout_rate=0.0))
+    model.load_state_dict(sd)
+    model = model.cuda().eval()
+    sd_gpu = O.sd_to(sd, "cuda")
+    for seed in (1, 2, 3):
+        ids, mask, _ = [t.cuda() for t in O.synth_batch(40, 2, 64, 4, cfg.vocab, seed=seed)]
+        out = model.generate(ids, mask, max_length=8, min_length=8)
+        ref, _, logits = O.fidt5_generate(sd_gpu, cfg, ids, mask, 8, return_step_logits=True, min_length=8)
+        bad = (out != ref).any(dim=1).nonzero().flatten().tolist()
+        for row in bad:   # only near-ties of the reference's own top-2 logits may differ (bf16)
+            t = int((out[row] != ref[row]).nonzero()[0])
+            top2 = logits[t - 1][row].float().topk(2).values
+            assert float(top2[0] - top2[1]) < 4e-2, (seed, row, t, float(top2[0] - top2[1]))
+        assert len(bad) <= 2

@@ -1,0 +1,100 @@
+"""Question-sharded data parallelism on real GPUs over NCCL, world_size 2 (skipped on a 1-GPU box):
+  * training: two ranks with B questions each == one process with the 2B-question batch (first-step loss, gradient norm,
+    updated weights), in the replicated all-reduce mode and in the sharded reduce-scatter / all-gather mode, and every
+    rank ends with identical weights;
+  * inference: every rank decodes its own questions and only answers and scores are all-gathered
+    (lako_b200.optim.gather_answers_and_scores)."""
+import os
+import types
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _data(B, N, L, T, seed):
+    g = torch.Generator().manual_seed(seed)
+    ids = torch.randint(11, 500, (B, N, L), generator=g)
+    lens = torch.randint(L // 2, L + 1, (B, N), generator=g)
+    mask = torch.arange(L)[None, None, :] < lens[:, :, None]
+    ids = ids * mask
+    ids[:, 1, 0], ids[:, 1, 1] = 6, 10
+    ids[:, 1, 9::11] = 5
+    ids = ids * mask
+    labels = torch.randint(11, 500, (B, T), generator=g)
+    labels[:, -2:] = -100
+    return ids, mask, labels
+
+
+def _model():
+    from lako_b200.model import FiDT5, FiDT5Config
+    cfg = FiDT5Config(vocab_size=512, d_model=256, d_ff=512, num_layers=4, num_heads=4, dropout_rate=0.0)
+    return FiDT5(cfg, emb_std=0.3, seed=0)
+
+
+def _worker(rank, world, port, out_dir):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    from lako_b200.optim import FusedAdamW, gather_answers_and_scores, train_step
+    B, N, L, T = 3, 2, 48, 6
+    ids, mask, labels = _data(world * B, N, L, T, seed=5)
+    sl = slice(rank * B, (rank + 1) * B)
+    res = {}
+    for shard in (False, True):
+        model = _model().cuda().train()
+        opt = FusedAdamW(model, lr=1e-3, weight_decay=1e-4, clip=1.0, shard=shard)
+        assert (opt._plan is not None) == shard
+        loss = train_step(model, opt, ids[sl].cuda(), mask[sl].cuda(), labels[sl].cuda())
+        sd = {k: v.detach().float().cpu().clone() for k, v in model.state_dict().items()}   # sharded: collective
+        res[shard] = (float(loss), float(opt.grad_norm()), sd, model._bf16.float().sum().item())
+        del opt
+    # inference: local decode + gather
+    model.eval()
+    model.overwrite_forward_crossattention()
+    model.reset_score_storage()
+    out = model.generate(ids[sl].cuda(), mask[sl].cuda(), max_length=8, min_length=8)
+    opt_ns = types.SimpleNamespace(stream=2, n_context=3, attention_score_style="mean", use_last_half_layer_attention="no")
+    sc = model.get_crossattention_scores(opt_ns, ids[sl], None, mask[sl].cuda())
+    ans_all, sc_all = gather_answers_and_scores(out, sc.cuda(), 8)
+    torch.save({"res": res, "answers": ans_all.cpu(), "scores": sc_all.cpu(), "local_answers": out.cpu(), "local_scores": sc},
+               os.path.join(out_dir, f"rank{rank}.pt"))
+    dist.destroy_process_group()
+
+
+def test_dp2_nccl_training_and_inference_gather(tmp_path):
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
+    import torch.multiprocessing as mp
+    from lako_b200.optim import FusedAdamW, train_step
+    mp.spawn(_worker, args=(2, 29741, str(tmp_path)), nprocs=2, join=True)
+    r0 = torch.load(tmp_path / "rank0.pt", weights_only=False)
+    r1 = torch.load(tmp_path / "rank1.pt", weights_only=False)
+    # single process, global batch
+    B, N, L, T = 3, 2, 48, 6
+    ids, mask, labels = _data(2 * B, N, L, T, seed=5)
+    model = _model().cuda().train()
+    opt = FusedAdamW(model, lr=1e-3, weight_decay=1e-4, clip=1.0)
+    loss = float(train_step(model, opt, ids.cuda(), mask.cuda(), labels.cuda()))
+    gn = float(opt.grad_norm())
+    sd = {k: v.detach().float().cpu() for k, v in model.state_dict().items()}
+    for shard in (False, True):
+        l0, g0, sd0, chk0 = r0["res"][shard]
+        l1, g1, sd1, chk1 = r1["res"][shard]
+        print(f"shard={shard}: loss {l0:.6f} / {l1:.6f} vs single {loss:.6f}; grad norm {g0:.5f} vs {gn:.5f}")
+        assert abs(l0 - loss) < 1e-5 and abs(l1 - loss) < 1e-5          # global-count normalisation + loss all-reduce
+        assert abs(g0 - gn) < 2e-4 * gn and abs(g1 - gn) < 2e-4 * gn      # clip norm of the reduced gradient
+        assert chk0 == chk1                                               # identical bf16 weights on every rank
+        diff = torch.cat([(sd0[k] - sd[k]).abs().reshape(-1) for k in sd])
+        same = torch.cat([(sd0[k] - sd1[k]).abs().reshape(-1) for k in sd])
+        assert float(same.max()) == 0.0                                   # fp32 masters identical across ranks
+        # one AdamW step without bias correction moves a weight by ~3.2 lr sign(g): elements whose gradient is at the
+        # fp32-summation-order noise level may flip, the bulk must agree
+        assert float((diff > 1e-4).float().mean()) < 2e-2, float((diff > 1e-4).float().mean())
+    # inference gather: rank order, identical on both ranks, equal to the local pieces
+    assert torch.equal(r0["answers"], r1["answers"]) and torch.equal(r0["scores"], r1["scores"])
+    assert r0["answers"].shape == (2 * B, 8) and r0["scores"].shape == (2 * B, 3)
+    assert torch.equal(r0["answers"][:B], r0["local_answers"]) and torch.equal(r0["answers"][B:], r1["local_answers"])
+    assert torch.equal(r0["scores"][B:], r1["local_scores"])

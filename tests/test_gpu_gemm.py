@@ -145,11 +145,12 @@ def test_gemm_head_major_output(M, N, K):
     torch.manual_seed(M + N)
     A = (torch.randn(M, K, device="cuda") * 0.5).to(torch.bfloat16)
     B = (torch.randn(N, K, device="cuda") * K ** -0.5).to(torch.bfloat16)
-    C = torch.full((N // 64, M, 64), float("nan"), device="cuda", dtype=torch.bfloat16)
+    cap = M + 37    # slab capacity > M: the rows beyond M must stay untouched
+    C = torch.full((N // 64, cap, 64), 7.0, device="cuda", dtype=torch.bfloat16)
     nat.check(nat.lib().lako_gemm_bf16_head_major(nat.ptr(A), nat.ptr(B), nat.ptr(C), ctypes.c_int(M), ctypes.c_int(N),
-                                                  ctypes.c_int(K), ctypes.c_int(K), ctypes.c_int(K), ctypes.c_float(1.0),
-                                                  nat.stream_ptr()))
+                                                  ctypes.c_int(K), ctypes.c_int(K), ctypes.c_int(K), ctypes.c_int(cap),
+                                                  ctypes.c_float(1.0), nat.stream_ptr()))
     torch.cuda.synchronize()
     ref = (A.float() @ B.float().T).view(M, N // 64, 64).transpose(0, 1)
-    assert bool(torch.isfinite(C.float()).all())
-    assert (C.float() - ref).abs().max().item() < 2e-2
+    assert (C[:, :M].float() - ref).abs().max().item() < 2e-2
+    assert bool((C[:, M:] == 7.0).all())
