@@ -334,13 +334,15 @@ struct XDecParams {
   long long hm_rows;  // > 0: K/V live head-major, [plane = column / 64][hm_rows tokens][64] (contiguous 16 KB per tile)
 };
 
-// Persistent CTAs (2 per SM) walk the work items (question, head, 128-key chunk) with a 3-stage ring of K / V tiles fed
-// by TMA: while an item is being reduced, the tiles of the next two are in flight, so every SM keeps ~128 KB of loads
-// outstanding for the whole launch (the one-shot version left the memory system idle during each CTA's compute phase:
-// 3.1 TB/s).  The first tiles are requested before the grid dependency (the K/V cache does not depend on the preceding
-// kernel).  Lane group kg (8 lanes) of warp w owns keys w*32 + j*4 + kg of the item, each lane 8 of the 64 dims.  The
-// last item of a (question, head) to arrive merges the chunk partials (flash-decoding combine) and writes the bf16
-// context row -- no separate combine launch.
+// Persistent CTAs (2 per SM) each take a CONTIGUOUS range of work items (question, head, 128-key chunk) and stream
+// their K / V tiles through a 3-stage TMA ring: while an item is being reduced, the tiles of the next two are in
+// flight, so every SM keeps loads outstanding for the whole launch (a one-shot CTA per chunk left the memory system
+// idle during each CTA's compute phase and paid a query load + an atomic ticket per 32 KB: 3.1 TB/s).  Consecutive
+// items of a CTA are consecutive chunks of the same (question, head): the online-softmax state (m, l, o) stays in
+// registers across them and only one partial per segment is published.  The last segment of a (question, head) to
+// arrive merges the partials (flash-decoding combine) and writes the bf16 context row -- no separate combine launch.
+// The first tiles are requested before the grid dependency (the K/V cache does not depend on the preceding kernel).
+// Lane group kg (8 lanes) of warp w owns keys w*32 + j*4 + kg of an item, each lane 8 of the 64 dims.
 __global__ void __launch_bounds__(128) xattn_decode_kernel(const __grid_constant__ CUtensorMap tm_kv, const XDecParams p) {
   pdl_launch_dependents();
   extern __shared__ uint8_t xd_raw[];
@@ -367,28 +369,49 @@ __global__ void __launch_bounds__(128) xattn_decode_kernel(const __grid_constant
     for (int b = 0; b < p.B; ++b) s_pref[b + 1] += s_pref[b];
   __syncthreads();
   const int total = s_pref[p.B];
-  auto decode = [&](int t, int& b, int& h, int& k0, int& kstart, int& Mb) {
-    int lo = 0, hi = p.B - 1;  // largest b with s_pref[b] <= t
+  const int per = (total + gridDim.x - 1) / gridDim.x;  // items per CTA
+  const int g_lo = blockIdx.x * per, g_hi = min(total, g_lo + per);
+  if (g_lo >= g_hi) return;
+
+  // walking cursor over the items: (b, h, chunk) and the question's geometry
+  struct Cur { int b, h, ch, ns, kstart, Mb; };
+  auto seek = [&](int g) {
+    Cur q;
+    int lo = 0, hi = p.B - 1;  // largest b with s_pref[b] <= g
     while (lo < hi) {
       const int mid = (lo + hi + 1) >> 1;
-      if (s_pref[mid] <= t) lo = mid; else hi = mid - 1;
+      if (s_pref[mid] <= g) lo = mid; else hi = mid - 1;
     }
-    b = lo;
-    kstart = b * p.M;
-    Mb = p.M;
+    q.b = lo;
+    q.kstart = q.b * p.M;
+    q.Mb = p.M;
     if (p.cu) {
-      kstart = p.cu[b * p.npsg];
-      Mb = p.cu[(b + 1) * p.npsg] - kstart;
+      q.kstart = p.cu[q.b * p.npsg];
+      q.Mb = p.cu[(q.b + 1) * p.npsg] - q.kstart;
     }
-    const int ns = (Mb + XD_CH - 1) / XD_CH;
-    const int r = t - s_pref[b];
-    h = r / ns;           // items of one (b, h) are consecutive
-    k0 = (r - h * ns) * XD_CH;
+    q.ns = (q.Mb + XD_CH - 1) / XD_CH;
+    const int r = g - s_pref[q.b];
+    q.h = r / q.ns;  // items of one (b, h) are consecutive
+    q.ch = r - q.h * q.ns;
+    return q;
   };
-  auto issue = [&](int t, int stage) {  // thread 0 only
-    int b, h, k0, kstart, Mb;
-    decode(t, b, h, k0, kstart, Mb);
-    int kc0 = p.koff + h * 64, kr0 = kstart + k0, vc0 = p.voff + h * 64, vr0 = kstart + k0;
+  auto advance = [&](Cur& q) {
+    if (++q.ch < q.ns) return;
+    q.ch = 0;
+    if (++q.h < p.H) return;
+    q.h = 0;
+    ++q.b;
+    if (q.b >= p.B) return;
+    q.kstart = q.b * p.M;
+    q.Mb = p.M;
+    if (p.cu) {
+      q.kstart = p.cu[q.b * p.npsg];
+      q.Mb = p.cu[(q.b + 1) * p.npsg] - q.kstart;
+    }
+    q.ns = (q.Mb + XD_CH - 1) / XD_CH;
+  };
+  auto issue = [&](const Cur& q, int stage) {  // thread 0 only
+    int kc0 = p.koff + q.h * 64, kr0 = q.kstart + q.ch * XD_CH, vc0 = p.voff + q.h * 64, vr0 = kr0;
     if (p.hm_rows > 0) {  // row of the [planes * tokens][64] view
       kr0 += static_cast<int>((kc0 >> 6) * p.hm_rows);
       vr0 += static_cast<int>((vc0 >> 6) * p.hm_rows);
@@ -399,89 +422,41 @@ __global__ void __launch_bounds__(128) xattn_decode_kernel(const __grid_constant
     tma_load_2d(st, &tm_kv, &bar[stage], kc0, kr0);
     tma_load_2d(st + XD_TILE, &tm_kv, &bar[stage], vc0, vr0);
   };
+  Cur cur = seek(g_lo);
+  Cur nxt = cur;  // producer cursor (thread 0): the next item to request
+  int g_issued = g_lo;
   if (tid == 0)
-    for (int i = 0; i < XD_STAGES - 1; ++i) {
-      const int t = blockIdx.x + i * gridDim.x;
-      if (t < total) issue(t, i);
+    for (int i = 0; i < XD_STAGES - 1 && g_issued < g_hi; ++i) {
+      issue(nxt, i);
+      advance(nxt);
+      ++g_issued;
     }
   pdl_wait();
   const bool capture = p.tok_score != nullptr && (p.step == nullptr || *p.step == 0);
   uint32_t phase_bits = 0;  // parity of each stage's barrier
-  int it = 0;
-  for (int t = blockIdx.x; t < total; t += gridDim.x, ++it) {
-    const int stage = it % XD_STAGES;
-    // keep two items in flight: the stage that item it + 2 will use was released by the barrier at the end of item it - 1
-    if (tid == 0) {
-      const int tn = t + (XD_STAGES - 1) * gridDim.x;
-      if (tn < total) issue(tn, (it + XD_STAGES - 1) % XD_STAGES);
-    }
-    int b, h, k0, kstart, Mb;
-    decode(t, b, h, k0, kstart, Mb);
-    float qv[8];
-    {
-      const float4 q0 = *reinterpret_cast<const float4*>(p.q + static_cast<size_t>(b) * p.ldq + h * 64 + c * 8);
-      const float4 q1 = *reinterpret_cast<const float4*>(p.q + static_cast<size_t>(b) * p.ldq + h * 64 + c * 8 + 4);
-      qv[0] = q0.x; qv[1] = q0.y; qv[2] = q0.z; qv[3] = q0.w; qv[4] = q1.x; qv[5] = q1.y; qv[6] = q1.z; qv[7] = q1.w;
-    }
-    const uint8_t* sK = smem + stage * 2 * XD_TILE;
-    const uint8_t* sV = sK + XD_TILE;
-    mbar_wait(&bar[stage], (phase_bits >> stage) & 1u);
-    phase_bits ^= 1u << stage;
-    const int wk0 = warp * 32;  // this warp's keys within the item
-    float sc[8];
-    float m_g = -INFINITY;
+  // online-softmax state of this lane group over the current segment (consecutive chunks of one (b, h))
+  float m_run = -INFINITY, l_run = 0.f, o[8], qv[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int kl = wk0 + j * 4 + kg, key = k0 + kl;
-      const uint4 kr = *reinterpret_cast<const uint4*>(sK + kl * 128 + ((c ^ (kl & 7)) << 4));
-      float s = qv[0] * bf16_lo(kr.x) + qv[1] * bf16_hi(kr.x) + qv[2] * bf16_lo(kr.y) + qv[3] * bf16_hi(kr.y) +
-                qv[4] * bf16_lo(kr.z) + qv[5] * bf16_hi(kr.z) + qv[6] * bf16_lo(kr.w) + qv[7] * bf16_hi(kr.w);
-      s += __shfl_xor_sync(0xffffffffu, s, 1);
-      s += __shfl_xor_sync(0xffffffffu, s, 2);
-      s += __shfl_xor_sync(0xffffffffu, s, 4);
-      if (key >= Mb) {
-        s = -INFINITY;  // rows past this question's memory (the next question's rows / next plane / TMA zero fill)
-      } else {
-        bool valid = true;
-        if (p.mask) valid = p.mask[static_cast<size_t>(b) * p.M + key] != 0;
-        if (capture && valid && c == 0) {
-          const size_t ti = p.tok_index ? static_cast<size_t>(p.tok_index[kstart + key]) : static_cast<size_t>(b) * p.M + key;
-          atomicAdd(p.tok_score + ti, s);
-        }
-        if (!valid) s += DC_MASK_MIN;  // HF's additive mask (finfo.min): a fully masked question degrades to uniform
-      }
-      sc[j] = s;
-      m_g = fmaxf(m_g, s);
-    }
-    float l_g = 0.f, o[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) o[i] = 0.f;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int kl = wk0 + j * 4 + kg;
-      const float pj = (m_g == -INFINITY) ? 0.f : fast_exp2((sc[j] - m_g) * DC_LOG2E);
-      l_g += pj;
-      const uint4 vr = *reinterpret_cast<const uint4*>(sV + kl * 128 + ((c ^ (kl & 7)) << 4));
-      o[0] = fmaf(pj, bf16_lo(vr.x), o[0]); o[1] = fmaf(pj, bf16_hi(vr.x), o[1]);
-      o[2] = fmaf(pj, bf16_lo(vr.y), o[2]); o[3] = fmaf(pj, bf16_hi(vr.y), o[3]);
-      o[4] = fmaf(pj, bf16_lo(vr.z), o[4]); o[5] = fmaf(pj, bf16_hi(vr.z), o[5]);
-      o[6] = fmaf(pj, bf16_lo(vr.w), o[6]); o[7] = fmaf(pj, bf16_hi(vr.w), o[7]);
-    }
-    // ---- merge the 4 lane groups of the warp (same dims c, different keys)
-    float m_run = m_g, l_run = l_g;
+  for (int i = 0; i < 8; ++i) o[i] = qv[i] = 0.f;
+  int seg_g0 = g_lo;  // first item of the current segment
+
+  // publish the finished segment [seg_g0, g_end) of (sb, sh): merge lane groups and warps, store the partial, count
+  // the arrival; the last segment of the (question, head) merges all of its partials
+  auto flush = [&](int sb, int sh, int sns, int g_end) {
+    (void)g_end;
 #pragma unroll
     for (int off = 8; off <= 16; off <<= 1) {
       const float m_o = __shfl_xor_sync(0xffffffffu, m_run, off);
       const float l_o = __shfl_xor_sync(0xffffffffu, l_run, off);
       const float m_new = fmaxf(m_run, m_o);
       const float sa = (m_run == -INFINITY) ? 0.f : fast_exp2((m_run - m_new) * DC_LOG2E);
-      const float sb = (m_o == -INFINITY) ? 0.f : fast_exp2((m_o - m_new) * DC_LOG2E);
+      const float sb2 = (m_o == -INFINITY) ? 0.f : fast_exp2((m_o - m_new) * DC_LOG2E);
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const float o_o = __shfl_xor_sync(0xffffffffu, o[i], off);
-        o[i] = o[i] * sa + o_o * sb;
+        o[i] = o[i] * sa + o_o * sb2;
       }
-      l_run = l_run * sa + l_o * sb;
+      l_run = l_run * sa + l_o * sb2;
       m_run = m_new;
     }
     if (kg == 0) {
@@ -492,10 +467,13 @@ __global__ void __launch_bounds__(128) xattn_decode_kernel(const __grid_constant
         s_l[warp] = l_run;
       }
     }
-    __syncthreads();  // (A) warp partials visible; every thread is done reading this stage's tiles
-    // ---- merge the 4 warps, write the item partial (o[64], m, l)
-    const int ns = (Mb + XD_CH - 1) / XD_CH;
-    const size_t pbase = (static_cast<size_t>(b) * p.H + h) * p.splits;
+    __syncthreads();
+    // segments of (sb, sh) are cut at multiples of `per` in the global item order
+    const int gq0 = s_pref[sb] + sh * sns;  // first item of this (question, head)
+    const int first_cta = gq0 / per;
+    const int nseg = (gq0 + sns - 1) / per - first_cta + 1;
+    const int ord = seg_g0 / per - first_cta;
+    const size_t pbase = (static_cast<size_t>(sb) * p.H + sh) * p.splits;
     if (tid < 64) {
       const float m = fmaxf(fmaxf(s_m[0], s_m[1]), fmaxf(s_m[2], s_m[3]));
       float ov = 0.f, l = 0.f;
@@ -505,40 +483,118 @@ __global__ void __launch_bounds__(128) xattn_decode_kernel(const __grid_constant
         ov += s_o[w][tid] * scw;
         l += s_l[w] * scw;
       }
-      float* part = p.part + (pbase + k0 / XD_CH) * 66;
+      float* part = p.part + (pbase + ord) * 66;
       part[tid] = ov;
       if (tid == 0) {
         part[64] = m;
         part[65] = l;
       }
     }
-    __syncthreads();  // (B) partial stored by this CTA's threads
+    __syncthreads();  // partial stored by this CTA's threads
     if (tid == 0) {
       __threadfence();  // cumulative: the CTA's partial is visible device-wide before the arrival is counted
-      const int prev = atomicAdd(&p.counters[b * p.H + h], 1);
-      s_last = (prev == ns - 1) ? 1 : 0;
-      if (prev == ns - 1) p.counters[b * p.H + h] = 0;  // ready for the next launch
+      const int prev = atomicAdd(&p.counters[sb * p.H + sh], 1);
+      s_last = (prev == nseg - 1) ? 1 : 0;
+      if (prev == nseg - 1) p.counters[sb * p.H + sh] = 0;  // ready for the next launch
     }
-    __syncthreads();  // (C)
+    __syncthreads();
     if (s_last) {
-      // ---- last item of this (question, head): combine the chunk partials
       __threadfence();
       if (tid < 64) {
         const float* pp = p.part + pbase * 66;
         float m = -INFINITY;
-        for (int s2 = 0; s2 < ns; ++s2) m = fmaxf(m, __ldcg(pp + s2 * 66 + 64));
+        for (int s2 = 0; s2 < nseg; ++s2) m = fmaxf(m, __ldcg(pp + s2 * 66 + 64));
         float l = 0.f, ov = 0.f;
-#pragma unroll 4
-        for (int s2 = 0; s2 < ns; ++s2) {
+        for (int s2 = 0; s2 < nseg; ++s2) {
           const float w = fast_exp2((__ldcg(pp + s2 * 66 + 64) - m) * DC_LOG2E);
           l += w * __ldcg(pp + s2 * 66 + 65);
           ov += w * __ldcg(pp + s2 * 66 + tid);
         }
-        p.out[static_cast<size_t>(b) * p.ldo + h * 64 + tid] = __float2bfloat16(ov / l);
-        if (p.q_zero) p.q_zero[static_cast<size_t>(b) * p.ldq + h * 64 + tid] = 0.f;
+        p.out[static_cast<size_t>(sb) * p.ldo + sh * 64 + tid] = __float2bfloat16(ov / l);
+        if (p.q_zero) p.q_zero[static_cast<size_t>(sb) * p.ldq + sh * 64 + tid] = 0.f;
       }
     }
+    m_run = -INFINITY;
+    l_run = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o[i] = 0.f;
+  };
+
+  int seg_b = -1, seg_h = -1, seg_ns = 0;
+  for (int g = g_lo; g < g_hi; ++g) {
+    const int stage = (g - g_lo) % XD_STAGES;
+    if (cur.b != seg_b || cur.h != seg_h) {  // CTA-uniform: a new (question, head) starts
+      if (seg_b >= 0) flush(seg_b, seg_h, seg_ns, g);
+      seg_b = cur.b;
+      seg_h = cur.h;
+      seg_ns = cur.ns;
+      seg_g0 = g;
+      const float4 q0 = *reinterpret_cast<const float4*>(p.q + static_cast<size_t>(cur.b) * p.ldq + cur.h * 64 + c * 8);
+      const float4 q1 = *reinterpret_cast<const float4*>(p.q + static_cast<size_t>(cur.b) * p.ldq + cur.h * 64 + c * 8 + 4);
+      qv[0] = q0.x; qv[1] = q0.y; qv[2] = q0.z; qv[3] = q0.w; qv[4] = q1.x; qv[5] = q1.y; qv[6] = q1.z; qv[7] = q1.w;
+    }
+    // keep two items in flight: the stage that item g + 2 will use was released by the barrier at the end of item g - 1
+    if (tid == 0 && g_issued < g_hi) {
+      issue(nxt, (g_issued - g_lo) % XD_STAGES);
+      advance(nxt);
+      ++g_issued;
+    }
+    const uint8_t* sK = smem + stage * 2 * XD_TILE;
+    const uint8_t* sV = sK + XD_TILE;
+    const int k0 = cur.ch * XD_CH;
+    mbar_wait(&bar[stage], (phase_bits >> stage) & 1u);
+    phase_bits ^= 1u << stage;
+    const int wk0 = warp * 32;  // this warp's keys within the item
+    float sc[8];
+    float m_it = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int kl = wk0 + j * 4 + kg, key = k0 + kl;
+      const uint4 kr = *reinterpret_cast<const uint4*>(sK + kl * 128 + ((c ^ (kl & 7)) << 4));
+      float s = qv[0] * bf16_lo(kr.x) + qv[1] * bf16_hi(kr.x) + qv[2] * bf16_lo(kr.y) + qv[3] * bf16_hi(kr.y) +
+                qv[4] * bf16_lo(kr.z) + qv[5] * bf16_hi(kr.z) + qv[6] * bf16_lo(kr.w) + qv[7] * bf16_hi(kr.w);
+      s += __shfl_xor_sync(0xffffffffu, s, 1);
+      s += __shfl_xor_sync(0xffffffffu, s, 2);
+      s += __shfl_xor_sync(0xffffffffu, s, 4);
+      if (key >= cur.Mb) {
+        s = -INFINITY;  // rows past this question's memory: other questions' rows, unwritten slab rows, TMA zero fill
+      } else {
+        bool valid = true;
+        if (p.mask) valid = p.mask[static_cast<size_t>(cur.b) * p.M + key] != 0;
+        if (capture && valid && c == 0) {
+          const size_t ti = p.tok_index ? static_cast<size_t>(p.tok_index[cur.kstart + key])
+                                        : static_cast<size_t>(cur.b) * p.M + key;
+          atomicAdd(p.tok_score + ti, s);
+        }
+        if (!valid) s += DC_MASK_MIN;  // HF's additive mask (finfo.min): a fully masked question degrades to uniform
+      }
+      sc[j] = s;
+      m_it = fmaxf(m_it, s);
+    }
+    const float m_new = fmaxf(m_run, m_it);
+    if (m_new != -INFINITY) {  // lane-group uniform
+      const float sa = (m_run == -INFINITY) ? 0.f : fast_exp2((m_run - m_new) * DC_LOG2E);
+      l_run *= sa;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o[i] *= sa;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        if (sc[j] == -INFINITY) continue;  // never touch the V row of a key outside the question (may hold NaN bits)
+        const int kl = wk0 + j * 4 + kg;
+        const float pj = fast_exp2((sc[j] - m_new) * DC_LOG2E);
+        l_run += pj;
+        const uint4 vr = *reinterpret_cast<const uint4*>(sV + kl * 128 + ((c ^ (kl & 7)) << 4));
+        o[0] = fmaf(pj, bf16_lo(vr.x), o[0]); o[1] = fmaf(pj, bf16_hi(vr.x), o[1]);
+        o[2] = fmaf(pj, bf16_lo(vr.y), o[2]); o[3] = fmaf(pj, bf16_hi(vr.y), o[3]);
+        o[4] = fmaf(pj, bf16_lo(vr.z), o[4]); o[5] = fmaf(pj, bf16_hi(vr.z), o[5]);
+        o[6] = fmaf(pj, bf16_lo(vr.w), o[6]); o[7] = fmaf(pj, bf16_hi(vr.w), o[7]);
+      }
+      m_run = m_new;
+    }
+    advance(cur);
+    __syncthreads();  // every thread is done reading this stage's tiles: thread 0 may refill it
   }
+  flush(seg_b, seg_h, seg_ns, g_hi);
 }
 
 }  // namespace

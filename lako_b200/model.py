@@ -212,6 +212,9 @@ class FiDT5(nn.Module):
         self._stage_events = None
         self._stage_ranges = None
         self._master_sync = None   # set by a sharded FusedAdamW: all-gathers the fp32 masters before they are read
+        # transformers 3.0.2 (the version the reference pins, README.md:21) gives decoder block 0's cross-attention its
+        # own relative_attention_bias table (32, H); later versions have none.  Kept when a checkpoint carries it.
+        self._xattn_relbias = None
         self._init_weights(emb_std, seed)
 
     # ------------------------------------------------------------------ parameters
@@ -294,6 +297,8 @@ class FiDT5(nn.Module):
             self._flat_grad = fn(self._flat_grad)
         self._enc_buckets = fn(self._enc_buckets)
         self._dec_buckets = fn(self._dec_buckets)
+        if self._xattn_relbias is not None:
+            self._xattn_relbias = fn(self._xattn_relbias)
         with torch.no_grad():
             self._anchor = fn(self._anchor.detach()).requires_grad_(True)
         self._bf16 = None
@@ -337,11 +342,15 @@ class FiDT5(nn.Module):
         if self._master_sync is not None:   # sharded data-parallel optimizer: a collective, call it on every rank
             self._master_sync()
         sd = super().state_dict(*args, **kwargs)
+        if self._xattn_relbias is not None:
+            sd[kwargs.get("prefix", "") + self.XATTN_BIAS_KEY] = self._xattn_relbias.detach().clone()
         return sd
+
+    XATTN_BIAS_KEY = "decoder.block.0.layer.1.EncDecAttention.relative_attention_bias.weight"
 
     def load_state_dict(self, state_dict, strict=True, assign=False):
         own = set(self._specs) | set(self.TIED)
-        ignore = {"decoder.block.0.layer.1.EncDecAttention.relative_attention_bias.weight"}  # 3.0.2-era key (D1)
+        ignore = {self.XATTN_BIAS_KEY}  # 3.0.2-era key (SURVEY 8c deviation D1), handled below
         missing = [k for k in self._specs if k not in state_dict and k != "shared.weight"]
         if "shared.weight" not in state_dict and not any(t in state_dict for t in self.TIED):
             missing.append("shared.weight")
@@ -354,6 +363,22 @@ class FiDT5(nn.Module):
                     self._params[k].copy_(v.to(torch.float32))
                 elif k in self.TIED and "shared.weight" not in state_dict:
                     self._params["shared.weight"].copy_(v.to(torch.float32))
+        self._xattn_relbias = None
+        if self.XATTN_BIAS_KEY in state_dict:
+            t = state_dict[self.XATTN_BIAS_KEY].detach().to(torch.float32)
+            if tuple(t.shape) != (self.config.relative_attention_num_buckets, self.config.num_heads):
+                raise RuntimeError(f"load_state_dict: {self.XATTN_BIAS_KEY} has shape {tuple(t.shape)}")
+            self._xattn_relbias = t.clone().to(self._flat.device)
+            if bool((t != 0).any()):
+                import warnings
+                warnings.warn(
+                    "this checkpoint carries the cross-attention relative_attention_bias of transformers 3.0.2 (the version "
+                    "the reference pins).  generate() and get_crossattention_scores() reproduce it exactly: at every "
+                    "cached decode step it is the per-head constant table[0, h] (src/model.py:323-325 calls "
+                    "compute_bias(qlen=1, klen)), which leaves the softmax unchanged and shifts the stored step-0 "
+                    "scores.  forward(labels=...) does NOT apply its teacher-forced form (a t-dependent bias on the "
+                    "first T-1 memory tokens), so training-time logits differ slightly from a 3.0.2 run, and the table "
+                    "is carried through state_dict() unchanged (it receives no gradient).", stacklevel=2)
         return SimpleNamespace(missing_keys=missing, unexpected_keys=unexpected)
 
     # the reference wraps/unwraps the encoder to load plain T5 checkpoints (model.py:62-82); here it is a
@@ -682,6 +707,14 @@ class FiDT5(nn.Module):
         nat.check(L_.lako_fidt5_generate(ctypes.byref(m), ctypes.byref(bt), max_length, int(min_length), nat.ptr(out),
                                          ctypes.byref(out_len), nat.ptr(tf), nat.ptr(tl), nat.stream_ptr()),
                   "lako_fidt5_generate")
+        if tf is not None and self._xattn_relbias is not None:
+            # 3.0.2 semantics (see load_state_dict): every stored score carries + table[0, h]; after the masked sum over
+            # heads and layers (model.py:161-167) that is a constant per valid token and selected layer
+            c = self._xattn_relbias[0].sum()
+            nl = self.config.num_layers
+            valid = mask.reshape(B, N * L).to(torch.float32)
+            tf.add_(valid * (c * ((nl + 1) // 2)))
+            tl.add_(valid * (c * (nl - (nl + 1) // 2)))
         return out[:, :out_len.value]
 
     def overwrite_forward_crossattention(self):

@@ -176,3 +176,21 @@ def test_packing_plan_prefix_masks_and_host_lengths():
     model.unpad = True
     with pytest.raises(Exception):
         model._packing(mask, torch.tensor([1, 2, 3]))  # wrong number of lengths
+
+
+def test_transformers_302_cross_attention_bias_key_is_kept_and_announced():
+    """SURVEY 8c deviation D1: a checkpoint written under transformers 3.0.2 carries decoder block 0's cross-attention
+    relative_attention_bias; it must survive load -> state_dict and the load must say what is (not) reproduced."""
+    import warnings
+    from lako_b200.model import FiDT5, FiDT5Config
+    m = FiDT5(FiDT5Config(vocab_size=512, d_model=128, d_ff=256, num_layers=2, num_heads=2), seed=0)
+    sd = m.state_dict()
+    assert FiDT5.XATTN_BIAS_KEY not in sd
+    sd[FiDT5.XATTN_BIAS_KEY] = torch.randn(32, 2)
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        m.load_state_dict(sd)
+    assert len(w) == 1 and "3.0.2" in str(w[0].message)
+    assert torch.equal(m.state_dict()[FiDT5.XATTN_BIAS_KEY], sd[FiDT5.XATTN_BIAS_KEY])
+    with pytest.raises(RuntimeError):
+        m.load_state_dict({**sd, FiDT5.XATTN_BIAS_KEY: torch.zeros(3, 3)})

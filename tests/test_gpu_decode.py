@@ -74,7 +74,7 @@ def _xattn_ref(q, kv, koff, voff, H, rows, valid):
 
 @pytest.mark.parametrize("head_major", [0, 1])
 @pytest.mark.parametrize("packed", [True, False])
-@pytest.mark.parametrize("B,N,L,H", [(2, 2, 64, 2), (3, 4, 250, 3), (1, 10, 200, 4)])
+@pytest.mark.parametrize("B,N,L,H", [(2, 2, 64, 2), (3, 4, 250, 3), (1, 10, 200, 4), (4, 20, 250, 8)])
 def test_xattn_decode(packed, B, N, L, H, head_major):
     nat = _nat()
     lib = nat.lib()
@@ -106,9 +106,14 @@ def test_xattn_decode(packed, B, N, L, H, head_major):
         flat_mask = mask.reshape(B, M).contiguous()
         args = (nat.ptr(flat_mask), None, c_int(N), None)
     # head-major storage: [ld/64 planes][rows][64]
-    kv_dev = kv.view(kv.shape[0], ld // 64, 64).transpose(0, 1).contiguous() if head_major else kv
+    if head_major:   # slab capacity > rows in use; the unused tail holds NaN bit patterns (uninitialised workspace)
+        cap = kv.shape[0] + 50
+        kv_dev = torch.full((ld // 64, cap, 64), float("nan"), device="cuda", dtype=torch.bfloat16)
+        kv_dev[:, :kv.shape[0]] = kv.view(kv.shape[0], ld // 64, 64).transpose(0, 1)
+    else:
+        cap, kv_dev = kv.shape[0], kv
     for it in range(2):   # second call: step != 0 -> no capture; the last call also clears q (zero_q)
-        nat.check(lib.lako_xattn_decode(nat.ptr(q), nat.ptr(kv_dev), ctypes.c_size_t(kv.shape[0]), args[0], nat.ptr(out),
+        nat.check(lib.lako_xattn_decode(nat.ptr(q), nat.ptr(kv_dev), ctypes.c_size_t(cap), args[0], nat.ptr(out),
                                         nat.ptr(tok), nat.ptr(step), nat.ptr(ws), c_int(B), c_int(M), c_int(H), c_int(inner),
                                         c_int(ld), c_int(koff), c_int(voff), c_int(inner), args[1], args[2], args[3],
                                         c_int(it), c_int(head_major), nat.stream_ptr()))

@@ -203,3 +203,33 @@ def test_grad_stage_events_partition_and_fire():
     torch.cuda.synchronize()
     assert all(e.query() for e in evs)
     assert ((model._flat_grad - g0).norm() / g0.norm()).item() < 1e-3   # atomics reorder sums, nothing else changes
+
+
+def test_transformers_302_cross_attention_bias_shifts_the_stored_scores():
+    """With the 3.0.2 cross-attention bias table present, every stored step-0 score carries + table[0, h]
+    (src/model.py:323-329 with compute_bias(qlen=1, klen)): the generated ids are unchanged (softmax invariance) and the
+    token scores move by sum_h table[0, h] per selected layer on the valid tokens only."""
+    import warnings
+    from oracle import fidt5_oracle as O
+    from lako_b200.model import FiDT5, FiDT5Config
+    cfg = O.T5_TINY
+    sd = O.perturb_norm_weights(O.init_state_dict(cfg, seed=4, emb_std=0.3), seed=5)
+    ids, mask, _ = O.synth_batch(3, 2, 40, 4, cfg.vocab, seed=6, fact_format=True)
+    table = torch.randn(cfg.n_buckets, cfg.n_heads)
+    res = []
+    for with_bias in (False, True):
+        m = FiDT5(FiDT5Config(vocab_size=cfg.vocab, d_model=cfg.d_model, d_ff=cfg.d_ff, num_layers=cfg.n_layers,
+                              num_heads=cfg.n_heads, dropout_rate=0.0))
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            m.load_state_dict({**sd, **({FiDT5.XATTN_BIAS_KEY: table} if with_bias else {})})
+        m = m.cuda().eval()
+        m.overwrite_forward_crossattention()
+        m.reset_score_storage()
+        out = m.generate(ids.cuda(), mask.cuda(), max_length=6)
+        res.append((out.cpu(), m.token_scores(last_half=False)[0].cpu(), m.token_scores(last_half=True)[0].cpu()))
+    assert torch.equal(res[0][0], res[1][0])
+    c = float(table[0].sum())
+    valid = mask.reshape(3, -1).float()
+    assert torch.allclose(res[1][1] - res[0][1], valid * c * cfg.n_layers, atol=1e-4)
+    assert torch.allclose(res[1][2] - res[0][2], valid * c * (cfg.n_layers - (cfg.n_layers + 1) // 2), atol=1e-4)
