@@ -261,7 +261,9 @@ int lako_smallm_linear(const float* x_f32, const void* x_bf16, int ldx, const fl
  * to arrive; `workspace` (lako_xattn_decode_workspace_bytes) must be ZERO before the first call and is left with its
  * arrival counters zeroed.  zero_q != 0: q[b][64 h .. 64 h + 64) is cleared once (b, h) is finished (the K-split
  * projection that produces q accumulates into it).  head_major != 0: kv is stored [ldkv/64][kv_rows][64] (one contiguous
- * slab per 64-column head, what lako_fidt5_generate's K/V projection writes) instead of row-major [kv_rows][ldkv]. */
+ * slab per 64-column head, what lako_fidt5_generate's K/V projection writes) instead of row-major [kv_rows][ldkv].
+ * The 128-row tiles read up to 127 rows past a question's last token: rows that belong to no question (the unused tail
+ * of a slab) must hold finite values (zero them once), they are multiplied by zero probabilities. */
 size_t lako_xattn_decode_workspace_bytes(int B, int H, int M);
 int lako_xattn_decode(const float* q, const void* kv, size_t kv_rows, const unsigned char* mask, void* out,
                       float* tok_score, const int* step, float* workspace, int B, int M, int H, int ldq, int ldkv, int koff,

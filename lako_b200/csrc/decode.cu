@@ -44,6 +44,20 @@ __device__ __forceinline__ void mma_16816(float (&d)[4], uint32_t a0, uint32_t a
       : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
 
+__device__ __forceinline__ uint32_t dc_swz(int row, int chunk) {  // byte offset in a [rows][128 B] 128B-swizzled tile
+  return static_cast<uint32_t>(row * 128 + ((chunk ^ (row & 7)) << 4));
+}
+__device__ __forceinline__ void dc_ldsm_x4(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(addr));
+}
+__device__ __forceinline__ void dc_ldsm_x4_t(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(addr));
+}
+
 struct SmallLinParams {
   const float* x_f32;          // [M][K] fp32 residual stream -> RMSNorm prologue (ln_w != null), else plain cast
   const __nv_bfloat16* x_b16;  // [M][ldx] bf16 input (used when x_f32 == null)
@@ -351,7 +365,7 @@ __global__ void __launch_bounds__(128) xattn_decode_kernel(const __grid_constant
   __shared__ float s_m[4], s_l[4], s_o[4][64];
   __shared__ int s_last;
   __shared__ int s_pref[XD_MAXB + 1];  // s_pref[b] = number of work items of questions < b
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, kg = lane >> 3, c = lane & 7;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   // ---- item table: question b has H * ceil(len_b / 128) items (cu is older than the immediate predecessor: safe here)
   for (int b = tid; b < p.B; b += 128) {
     int Mb = p.M;
@@ -434,35 +448,37 @@ __global__ void __launch_bounds__(128) xattn_decode_kernel(const __grid_constant
   pdl_wait();
   const bool capture = p.tok_score != nullptr && (p.step == nullptr || *p.step == 0);
   uint32_t phase_bits = 0;  // parity of each stage's barrier
-  // online-softmax state of this lane group over the current segment (consecutive chunks of one (b, h))
-  float m_run = -INFINITY, l_run = 0.f, o[8], qv[8];
+  // Online-softmax state of this warp over the current segment (consecutive chunks of one (b, h)), in mma.sync
+  // m16n8k16 fragment layout with the query as row 0 of the 16-row A operand (rows 1..15 are zero): lanes 0..3 (g == 0)
+  // carry the real row -- m / l, and in oacc[nt][0..1] the output dims nt*8 + 2*t4 (+1).  Tensor-core dot products keep
+  // the instruction count per key ~4x below a SIMT reduction, which is what bounded the first versions of this kernel
+  // (issue-latency bound at 1 instruction/clock/SM, not memory bound).
+  const int fr = lane >> 2, t4 = lane & 3;  // fragment row (query row fr / fr + 8) and column pair
+  float m_run = -INFINITY, l_run = 0.f, oacc[8][4];
+  uint32_t qa[4][4];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) o[i] = qv[i] = 0.f;
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) oacc[i][e] = 0.f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) qa[i][e] = 0u;
   int seg_g0 = g_lo;  // first item of the current segment
 
-  // publish the finished segment [seg_g0, g_end) of (sb, sh): merge lane groups and warps, store the partial, count
-  // the arrival; the last segment of the (question, head) merges all of its partials
+  // publish the finished segment of (sb, sh): merge the 4 warps, store the partial, count the arrival; the last
+  // segment of the (question, head) merges all of its partials
   auto flush = [&](int sb, int sh, int sns, int g_end) {
     (void)g_end;
+    l_run += __shfl_xor_sync(0xffffffffu, l_run, 1);
+    l_run += __shfl_xor_sync(0xffffffffu, l_run, 2);
+    if (fr == 0) {
 #pragma unroll
-    for (int off = 8; off <= 16; off <<= 1) {
-      const float m_o = __shfl_xor_sync(0xffffffffu, m_run, off);
-      const float l_o = __shfl_xor_sync(0xffffffffu, l_run, off);
-      const float m_new = fmaxf(m_run, m_o);
-      const float sa = (m_run == -INFINITY) ? 0.f : fast_exp2((m_run - m_new) * DC_LOG2E);
-      const float sb2 = (m_o == -INFINITY) ? 0.f : fast_exp2((m_o - m_new) * DC_LOG2E);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float o_o = __shfl_xor_sync(0xffffffffu, o[i], off);
-        o[i] = o[i] * sa + o_o * sb2;
+      for (int nt = 0; nt < 8; ++nt) {
+        s_o[warp][nt * 8 + t4 * 2] = oacc[nt][0];
+        s_o[warp][nt * 8 + t4 * 2 + 1] = oacc[nt][1];
       }
-      l_run = l_run * sa + l_o * sb2;
-      m_run = m_new;
-    }
-    if (kg == 0) {
-#pragma unroll
-      for (int i = 0; i < 8; ++i) s_o[warp][c * 8 + i] = o[i];
-      if (c == 0) {
+      if (t4 == 0) {
         s_m[warp] = m_run;
         s_l[warp] = l_run;
       }
@@ -517,7 +533,9 @@ __global__ void __launch_bounds__(128) xattn_decode_kernel(const __grid_constant
     m_run = -INFINITY;
     l_run = 0.f;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) o[i] = 0.f;
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) oacc[i][e] = 0.f;
   };
 
   int seg_b = -1, seg_h = -1, seg_ns = 0;
@@ -529,9 +547,16 @@ __global__ void __launch_bounds__(128) xattn_decode_kernel(const __grid_constant
       seg_h = cur.h;
       seg_ns = cur.ns;
       seg_g0 = g;
-      const float4 q0 = *reinterpret_cast<const float4*>(p.q + static_cast<size_t>(cur.b) * p.ldq + cur.h * 64 + c * 8);
-      const float4 q1 = *reinterpret_cast<const float4*>(p.q + static_cast<size_t>(cur.b) * p.ldq + cur.h * 64 + c * 8 + 4);
-      qv[0] = q0.x; qv[1] = q0.y; qv[2] = q0.z; qv[3] = q0.w; qv[4] = q1.x; qv[5] = q1.y; qv[6] = q1.z; qv[7] = q1.w;
+      if (fr == 0) {  // A-operand fragments of the query row: a0 = dims ks*16 + 2*t4 (+1), a2 = the same + 8
+        const float* qp = p.q + static_cast<size_t>(cur.b) * p.ldq + cur.h * 64 + t4 * 2;
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+          const float2 lo = *reinterpret_cast<const float2*>(qp + ks * 16);
+          const float2 hi = *reinterpret_cast<const float2*>(qp + ks * 16 + 8);
+          qa[ks][0] = pack_bf16x2(lo.x, lo.y);
+          qa[ks][2] = pack_bf16x2(hi.x, hi.y);
+        }
+      }
     }
     // keep two items in flight: the stage that item g + 2 will use was released by the barrier at the end of item g - 1
     if (tid == 0 && g_issued < g_hi) {
@@ -539,57 +564,80 @@ __global__ void __launch_bounds__(128) xattn_decode_kernel(const __grid_constant
       advance(nxt);
       ++g_issued;
     }
-    const uint8_t* sK = smem + stage * 2 * XD_TILE;
-    const uint8_t* sV = sK + XD_TILE;
+    const uint32_t aK = smem_u32(smem + stage * 2 * XD_TILE), aV = aK + XD_TILE;
     const int k0 = cur.ch * XD_CH;
     mbar_wait(&bar[stage], (phase_bits >> stage) & 1u);
     phase_bits ^= 1u << stage;
-    const int wk0 = warp * 32;  // this warp's keys within the item
-    float sc[8];
+    const int kb = warp * 32;  // this warp's keys within the item
+    // ---- S = q K^T for 32 keys (4 n-tiles of 8): row 0 in lanes g == 0, keys kb + nt*8 + 2*t4 (+1)
+    float sacc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) sacc[i][e] = 0.f;
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+#pragma unroll
+      for (int np = 0; np < 2; ++np) {
+        uint32_t kb4[4];
+        dc_ldsm_x4(kb4, aK + dc_swz(kb + np * 16 + (lane & 7) + ((lane >> 4) & 1) * 8, ks * 2 + ((lane >> 3) & 1)));
+        mma_16816(sacc[np * 2], qa[ks][0], qa[ks][1], qa[ks][2], qa[ks][3], kb4[0], kb4[1]);
+        mma_16816(sacc[np * 2 + 1], qa[ks][0], qa[ks][1], qa[ks][2], qa[ks][3], kb4[2], kb4[3]);
+      }
+    }
+    // ---- validity, step-0 score capture, running softmax (row 0 only; the other 15 rows are zero padding)
+    float sv[8];
     float m_it = -INFINITY;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int kl = wk0 + j * 4 + kg, key = k0 + kl;
-      const uint4 kr = *reinterpret_cast<const uint4*>(sK + kl * 128 + ((c ^ (kl & 7)) << 4));
-      float s = qv[0] * bf16_lo(kr.x) + qv[1] * bf16_hi(kr.x) + qv[2] * bf16_lo(kr.y) + qv[3] * bf16_hi(kr.y) +
-                qv[4] * bf16_lo(kr.z) + qv[5] * bf16_hi(kr.z) + qv[6] * bf16_lo(kr.w) + qv[7] * bf16_hi(kr.w);
-      s += __shfl_xor_sync(0xffffffffu, s, 1);
-      s += __shfl_xor_sync(0xffffffffu, s, 2);
-      s += __shfl_xor_sync(0xffffffffu, s, 4);
-      if (key >= cur.Mb) {
-        s = -INFINITY;  // rows past this question's memory: other questions' rows, unwritten slab rows, TMA zero fill
-      } else {
-        bool valid = true;
-        if (p.mask) valid = p.mask[static_cast<size_t>(cur.b) * p.M + key] != 0;
-        if (capture && valid && c == 0) {
-          const size_t ti = p.tok_index ? static_cast<size_t>(p.tok_index[cur.kstart + key])
-                                        : static_cast<size_t>(cur.b) * p.M + key;
-          atomicAdd(p.tok_score + ti, s);
+    for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int key = k0 + kb + nt * 8 + t4 * 2 + e;
+        float sx = sacc[nt][e];
+        if (fr != 0 || key >= cur.Mb) {
+          sx = -INFINITY;  // padding rows; keys past this question's memory (other questions' rows / zeroed slab tail)
+        } else {
+          bool valid = true;
+          if (p.mask) valid = p.mask[static_cast<size_t>(cur.b) * p.M + key] != 0;
+          if (capture && valid) {
+            const size_t ti = p.tok_index ? static_cast<size_t>(p.tok_index[cur.kstart + key])
+                                          : static_cast<size_t>(cur.b) * p.M + key;
+            atomicAdd(p.tok_score + ti, sx);
+          }
+          if (!valid) sx += DC_MASK_MIN;  // HF's additive mask (finfo.min): a fully masked question degrades to uniform
         }
-        if (!valid) s += DC_MASK_MIN;  // HF's additive mask (finfo.min): a fully masked question degrades to uniform
+        sv[nt * 2 + e] = sx;
+        m_it = fmaxf(m_it, sx);
       }
-      sc[j] = s;
-      m_it = fmaxf(m_it, s);
-    }
+    m_it = fmaxf(m_it, __shfl_xor_sync(0xffffffffu, m_it, 1));
+    m_it = fmaxf(m_it, __shfl_xor_sync(0xffffffffu, m_it, 2));
     const float m_new = fmaxf(m_run, m_it);
-    if (m_new != -INFINITY) {  // lane-group uniform
-      const float sa = (m_run == -INFINITY) ? 0.f : fast_exp2((m_run - m_new) * DC_LOG2E);
-      l_run *= sa;
+    const float sa = (m_run == -INFINITY || m_new == -INFINITY) ? 0.f : fast_exp2((m_run - m_new) * DC_LOG2E);
+    uint32_t pa[2][4];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) o[i] *= sa;
+    for (int nt = 0; nt < 4; ++nt) {
+      const float e0 = (sv[nt * 2] == -INFINITY) ? 0.f : fast_exp2((sv[nt * 2] - m_new) * DC_LOG2E);
+      const float e1 = (sv[nt * 2 + 1] == -INFINITY) ? 0.f : fast_exp2((sv[nt * 2 + 1] - m_new) * DC_LOG2E);
+      l_run = (nt == 0 ? l_run * sa : l_run) + e0 + e1;
+      pa[nt >> 1][(nt & 1) * 2 + 0] = pack_bf16x2(e0, e1);  // row g (only g == 0 is non-zero)
+      pa[nt >> 1][(nt & 1) * 2 + 1] = 0u;                   // row g + 8: padding
+    }
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        if (sc[j] == -INFINITY) continue;  // never touch the V row of a key outside the question (may hold NaN bits)
-        const int kl = wk0 + j * 4 + kg;
-        const float pj = fast_exp2((sc[j] - m_new) * DC_LOG2E);
-        l_run += pj;
-        const uint4 vr = *reinterpret_cast<const uint4*>(sV + kl * 128 + ((c ^ (kl & 7)) << 4));
-        o[0] = fmaf(pj, bf16_lo(vr.x), o[0]); o[1] = fmaf(pj, bf16_hi(vr.x), o[1]);
-        o[2] = fmaf(pj, bf16_lo(vr.y), o[2]); o[3] = fmaf(pj, bf16_hi(vr.y), o[3]);
-        o[4] = fmaf(pj, bf16_lo(vr.z), o[4]); o[5] = fmaf(pj, bf16_hi(vr.z), o[5]);
-        o[6] = fmaf(pj, bf16_lo(vr.w), o[6]); o[7] = fmaf(pj, bf16_hi(vr.w), o[7]);
+    for (int i = 0; i < 8; ++i) {
+      oacc[i][0] *= sa;
+      oacc[i][1] *= sa;
+    }
+    m_run = m_new;
+    // ---- O += P V over this warp's 32 keys (V as the k16 x n8 B operand via ldmatrix.trans)
+#pragma unroll
+    for (int kk = 0; kk < 2; ++kk) {
+#pragma unroll
+      for (int dp = 0; dp < 4; ++dp) {
+        uint32_t vb[4];
+        dc_ldsm_x4_t(vb, aV + dc_swz(kb + kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8, dp * 2 + (lane >> 4)));
+        mma_16816(oacc[dp * 2], pa[kk][0], pa[kk][1], pa[kk][2], pa[kk][3], vb[0], vb[1]);
+        mma_16816(oacc[dp * 2 + 1], pa[kk][0], pa[kk][1], pa[kk][2], pa[kk][3], vb[2], vb[3]);
       }
-      m_run = m_new;
     }
     advance(cur);
     __syncthreads();  // every thread is done reading this stage's tiles: thread 0 may refill it

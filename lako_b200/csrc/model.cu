@@ -8,6 +8,7 @@
 //   loss.backward()          /root/reference/train_reader.py:73   -> lako_fidt5_backward
 //   FiDT5.generate           /root/reference/src/model.py:54-60   -> lako_fidt5_generate
 //   score capture            /root/reference/src/model.py:327-329 -> tok_score accumulation in generate
+#include <algorithm>
 #include <cstdlib>
 #include <vector>
 
@@ -858,6 +859,13 @@ extern "C" int lako_fidt5_generate(const lako_fidt5* m, const lako_batch* bt, in
     cudaMemsetAsync(gw.xdec_ws, 0, xattn_decode_workspace_bytes(B, H, bt->N * bt->L), s);  // arrival counters
     cudaMemsetAsync(gw.q_f32, 0, sizeof(float) * B * H * 64, s);
     RC(encode(p, m, w, reinterpret_cast<const long long*>(bt->ids), bt->mask, false, s, Dropper{0, 0, 0.f}, true));
+    if (w.Mrows < w.Mtok) {
+      // the decode kernel's 128-row TMA boxes reach up to 127 rows past the last token of a head's slab: those rows
+      // were never written (workspace memory) and must not hold NaN bit patterns (0 * NaN in the P V product)
+      const size_t tail = static_cast<size_t>(std::min(128, w.Mtok - w.Mrows));
+      cudaMemset2DAsync(w.kv_all + static_cast<size_t>(w.Mrows) * 64, static_cast<size_t>(w.Mtok) * 128, 0, tail * 128,
+                        static_cast<size_t>(p.nl) * 2 * H, s);
+    }
     RC(build_bias_lut(p.wf + p.lo.dec_relbias, m->dec_buckets, gw.lut_dec, H, max_length, m->bucket_center, s));
     launch_pdl(gen_init_kernel, dim3((B + 127) / 128), dim3(128), 0, s, gw.unfinished, gw.n_unf, gw.d_step, gw.d_done,
                gw.next_ids, gw.out_ids, B, max_length);

@@ -106,10 +106,11 @@ def test_xattn_decode(packed, B, N, L, H, head_major):
         flat_mask = mask.reshape(B, M).contiguous()
         args = (nat.ptr(flat_mask), None, c_int(N), None)
     # head-major storage: [ld/64 planes][rows][64]
-    if head_major:   # slab capacity > rows in use; the unused tail holds NaN bit patterns (uninitialised workspace)
-        cap = kv.shape[0] + 50
+    if head_major:   # slab capacity > rows in use: the first 128 tail rows are zeroed by the caller (the tiles reach
+        cap = kv.shape[0] + 200   # into them), whatever lies beyond may hold NaN bit patterns (uninitialised workspace)
         kv_dev = torch.full((ld // 64, cap, 64), float("nan"), device="cuda", dtype=torch.bfloat16)
         kv_dev[:, :kv.shape[0]] = kv.view(kv.shape[0], ld // 64, 64).transpose(0, 1)
+        kv_dev[:, kv.shape[0]:kv.shape[0] + 128] = 0
     else:
         cap, kv_dev = kv.shape[0], kv
     for it in range(2):   # second call: step != 0 -> no capture; the last call also clears q (zero_q)
