@@ -233,6 +233,9 @@ int lako_fold_dlut(const float* dlut, const int* buckets, float* dtable, int H, 
 /* test support: overwrite every TMEM column of every SM with NaN bit patterns (tcgen05.alloc hands out columns
    uncleared; a kernel that reads columns it did not write would pick these up) */
 int lako_debug_poison_tmem(void* stream);
+/* encoder self-attention forward implementation: 2 (default) = persistent warp-specialised kernel with the softmax
+ * probabilities kept in tensor memory; 1 = the one-shot kernel of round 1 (also env LAKO_ATTN_FWD=1) */
+void lako_set_attn_impl(int v);
 int lako_enc_attn_fwd(const void* qkv, const unsigned char* mask, const float* bias_lut, void* out, float* lse, int P,
                       int L, int H, void* stream);
 int lako_enc_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse, const unsigned char* mask,

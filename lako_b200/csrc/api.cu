@@ -83,6 +83,7 @@ int lako_fold_dlut(const float* dlut, const int* buckets, float* dtable, int H, 
   return fold_dlut(dlut, buckets, dtable, H, L, bucket_center, nb, ST(stream));
 }
 int lako_debug_poison_tmem(void* stream) { return poison_tmem(ST(stream)); }
+void lako_set_attn_impl(int v) { set_enc_attn_impl(v); }
 int lako_enc_attn_fwd(const void* qkv, const unsigned char* mask, const float* bias_lut, void* out, float* lse, int P,
                       int L, int H, void* stream) {
   ARCH_GUARD();

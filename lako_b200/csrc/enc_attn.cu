@@ -13,9 +13,24 @@
 // the same TMEM columns.  Q/K/V tiles come in by TMA from the fused qkv activation
 // [tokens][3*inner]; two CTAs are co-resident per SM (256 TMEM columns, ~97 KB smem each) so one
 // CTA's softmax overlaps the other's loads/MMAs.
+#include <algorithm>
+#include <cstdlib>
+
 #include "ops.cuh"
 
 namespace lako {
+
+// forward implementation: 1 = one-shot CTA per (query tile, head, passage); 2 = persistent warp-specialised kernel with
+// the probabilities kept in tensor memory (default).  LAKO_ATTN_FWD=1 / lako_set_attn_impl(1) selects the former.
+static int g_attn_impl = -1;
+int enc_attn_impl() {
+  if (g_attn_impl < 0) {
+    const char* e = getenv("LAKO_ATTN_FWD");
+    g_attn_impl = (e && e[0] == '1') ? 1 : 2;
+  }
+  return g_attn_impl;
+}
+void set_enc_attn_impl(int v) { g_attn_impl = (v == 1) ? 1 : 2; }
 
 constexpr float MASK_MIN = -3.4028234663852886e38f;  // torch.finfo(float32).min, as HF's additive mask
 
@@ -284,6 +299,302 @@ enc_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const EncAttnPar
   }
 }
 
+// ================================================================================================
+// forward, version 2: persistent, warp-specialised, probabilities kept in tensor memory
+// ================================================================================================
+// One CTA per SM walks (passage, head) units.  Roles: warp 0 = producer (TMA loads of the unit's Q / K / V into a
+// 2-deep ring of shared-memory stages + the unit's bias LUT and key mask), warp 1 = one thread issuing every MMA,
+// warps 2-5 and 6-9 = two softmax groups, each bound to one 256-column TMEM slot and taking every other 128-query tile:
+//   S = Q K^T (SS MMA, N = keys rounded to 32) -> slot columns [0, LK)
+//   softmax thread = one query row (TMEM lane): pass 1 row max of s + bias + mask, pass 2 exp -> bf16 pairs written
+//   IN PLACE over the consumed S columns ([0, LK/2)) by tcgen05.st
+//   O = P V with P as the TMEM A operand (TS MMA) -> slot columns [128, 192); read back, scaled by 1 / row sum, stored.
+// While one group runs its SIMT softmax the other group's loads / MMAs / epilogue proceed, the next unit's tiles are
+// already in flight, and nothing is allocated or staged per tile: the one-shot kernel above spends ~80 % of a CTA's
+// life in exposed latencies (TMEM allocation, LUT staging, TMA, MMA and tcgen05.ld round trips) at 2 CTAs per SM.
+constexpr int A2_STAGE = 98304;  // Q0 16K | Q1 16K | K 32K | V 32K
+constexpr int A2_K_OFF = 32768, A2_V_OFF = 65536;
+constexpr int A2_LUT_OFF = 2 * A2_STAGE;
+constexpr int A2_KMASK_OFF = A2_LUT_OFF + 2 * 4 * LUTCOPY * 4;
+constexpr int A2_BAR_OFF = A2_KMASK_OFF + 2 * 1024;
+constexpr int A2_SMEM_BYTES = A2_BAR_OFF + 256 + 1024;
+constexpr int A2_THREADS = 64 + 256;
+constexpr int A2_O_COL = 128;  // O accumulator columns inside a slot
+
+__global__ void __launch_bounds__(A2_THREADS, 1)
+enc_attn_fwd2_kernel(const __grid_constant__ CUtensorMap tm_qkv, const EncAttnParams p, const int P) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + A2_BAR_OFF);
+  uint64_t* stage_full = bars;        // [2] TMA bytes of a unit landed
+  uint64_t* stage_free = bars + 2;    // [2] every MMA reading the stage has completed
+  uint64_t* aux_full = bars + 4;      // [2] LUT + key mask of the unit staged
+  uint64_t* s_full = bars + 6;        // [2] S of a tile is in the slot
+  uint64_t* p_ready = bars + 8;       // [2] P of a tile is in the slot (128 softmax threads)
+  uint64_t* o_full = bars + 10;       // [2] O of a tile is in the slot
+  uint64_t* slot_free = bars + 12;    // [2] the slot's O has been read out (128 softmax threads)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int Lmax = p.L, H = p.H, nunits = P * H;
+  pdl_launch_dependents();
+  if (tid == 0) {
+    tma_prefetch_desc(&tm_qkv);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&stage_full[i], 1);
+      mbar_init(&stage_free[i], 1);
+      mbar_init(&aux_full[i], 1);
+      mbar_init(&s_full[i], 1);
+      mbar_init(&p_ready[i], 128);
+      mbar_init(&o_full[i], 1);
+      mbar_init(&slot_free[i], 128);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  pdl_wait();
+
+  // unit geometry, recomputed identically by every role
+  auto unit_geom = [&](int u, int& psg, int& h, int& row0, int& L) {
+    psg = u / H;
+    h = u - psg * H;
+    row0 = psg * Lmax;
+    L = Lmax;
+    if (p.cu) {
+      row0 = p.cu[psg];
+      L = p.cu[psg + 1] - row0;
+    }
+  };
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ producer
+    int ui = 0;
+    for (int u = blockIdx.x; u < nunits; u += gridDim.x) {
+      int psg, h, row0, L;
+      unit_geom(u, psg, h, row0, L);
+      if (L <= 0) continue;
+      const int stage = ui & 1;
+      const int LK = (L + 31) / 32 * 32, ktiles = (LK + 127) / 128, nt = (L + 127) / 128;
+      mbar_wait(&stage_free[stage], ((ui >> 1) & 1) ^ 1);
+      uint8_t* st = smem + stage * A2_STAGE;
+      if (lane == 0) {
+        mbar_arrive_expect_tx(&stage_full[stage], 16384 * (nt + 2 * ktiles));
+        for (int t = 0; t < nt; ++t) tma_load_2d(st + t * 16384, &tm_qkv, &stage_full[stage], h * 64, row0 + t * 128);
+        for (int t = 0; t < ktiles; ++t) {
+          tma_load_2d(st + A2_K_OFF + t * 16384, &tm_qkv, &stage_full[stage], p.inner + h * 64, row0 + t * 128);
+          tma_load_2d(st + A2_V_OFF + t * 16384, &tm_qkv, &stage_full[stage], 2 * p.inner + h * 64, row0 + t * 128);
+        }
+      }
+      stage_lut4(reinterpret_cast<float*>(smem + A2_LUT_OFF) + stage * 4 * LUTCOPY, p.bias_lut + h * (2 * Lmax - 1),
+                 2 * Lmax - 1, lane, 32);
+      stage_kmask(reinterpret_cast<float*>(smem + A2_KMASK_OFF) + stage * 256,
+                  p.mask ? p.mask + static_cast<size_t>(psg) * Lmax : nullptr, L, lane, 32);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&aux_full[stage]);  // release: the warp's LUT / mask writes precede it
+      ++ui;
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc_pv = make_idesc_bf16(128, 64, false, true);
+      int ui = 0, n = 0;
+      bool pend = false;
+      int pend_slot = 0, pend_stage = 0, pend_LK = 0, pend_k = 0;
+      bool pend_last = false;
+      auto do_pv = [&]() {
+        mbar_wait(&p_ready[pend_slot], pend_k & 1);
+        tc_fence_after();
+        const uint32_t t_slot = tmem + pend_slot * 256;
+        const uint32_t va = smem_u32(smem + pend_stage * A2_STAGE + A2_V_OFF);
+        const int ksteps = pend_LK / 16;
+        for (int j = 0; j < ksteps; ++j)
+          umma_bf16_ts(t_slot + A2_O_COL, t_slot + j * 8, make_smem_desc_sw128(va + j * 2048, 8192, 1024), idesc_pv, j > 0);
+        umma_commit(&o_full[pend_slot]);
+        if (pend_last) umma_commit(&stage_free[pend_stage]);
+        pend = false;
+      };
+      for (int u = blockIdx.x; u < nunits; u += gridDim.x) {
+        int psg, h, row0, L;
+        unit_geom(u, psg, h, row0, L);
+        if (L <= 0) continue;
+        const int stage = ui & 1;
+        const int LK = (L + 31) / 32 * 32, nt = (L + 127) / 128;
+        mbar_wait(&stage_full[stage], (ui >> 1) & 1);
+        tc_fence_after();
+        const uint32_t qa = smem_u32(smem + stage * A2_STAGE), ka = qa + A2_K_OFF;
+        const uint32_t idesc_s = make_idesc_bf16(128, LK, false, false);
+        for (int t = 0; t < nt; ++t) {
+          const int slot = n & 1, k = n >> 1;
+          mbar_wait(&slot_free[slot], (k & 1) ^ 1);
+          tc_fence_after();
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk)
+            umma_bf16(tmem + slot * 256, make_smem_desc_sw128(qa + t * 16384 + kk * 32, 16, 1024),
+                      make_smem_desc_sw128(ka + kk * 32, 16, 1024), idesc_s, kk > 0);
+          umma_commit(&s_full[slot]);
+          if (pend) do_pv();  // the previous tile's P V goes behind this tile's Q K^T: its softmax ran meanwhile
+          pend = true;
+          pend_slot = slot;
+          pend_stage = stage;
+          pend_LK = LK;
+          pend_k = k;
+          pend_last = (t == nt - 1);
+          ++n;
+        }
+        ++ui;
+      }
+      if (pend) do_pv();
+    }
+  } else {
+    // ------------------------------------------------------------------ softmax groups
+    const int group = (warp - 2) >> 2;   // == TMEM slot
+    const int quarter = warp & 3;        // TMEM lane quarter this warp may access
+    const int r = quarter * 32 + lane;   // query row within the tile == TMEM lane
+    const uint32_t t_row = tmem + group * 256 + (static_cast<uint32_t>(quarter * 32) << 16);
+    int ui = 0, n = 0;
+    for (int u = blockIdx.x; u < nunits; u += gridDim.x) {
+      int psg, h, row0, L;
+      unit_geom(u, psg, h, row0, L);
+      if (L <= 0) continue;
+      const int stage = ui & 1;
+      const int LK = (L + 31) / 32 * 32, nt = (L + 127) / 128, nchunks = LK / 32;
+      const float* s_lut4 = reinterpret_cast<const float*>(smem + A2_LUT_OFF) + stage * 4 * LUTCOPY;
+      const float* s_kmask = reinterpret_cast<const float*>(smem + A2_KMASK_OFF) + stage * 256;
+      for (int t = 0; t < nt; ++t, ++n) {
+        if ((n & 1) != group) continue;
+        const int k = n >> 1;
+        const int q0 = t * 128;
+        const int q = q0 + r, qc = min(q, L - 1);
+        const int b = Lmax - 1 - qc;
+        const float* lutp = s_lut4 + (b & 3) * LUTCOPY + (b & ~3);
+        mbar_wait(&aux_full[stage], (ui >> 1) & 1);
+        mbar_wait(&s_full[group], k & 1);
+        tc_fence_after();
+        // rows of this warp all beyond the passage: no arithmetic, but the protocol (P defined, arrivals) is kept
+        const bool warp_live = (q0 + quarter * 32) < L;
+        // ---- pass 1: row max of s + bias + mask
+        float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
+        if (warp_live) {
+          for (int c = 0; c < nchunks; ++c) {
+            uint32_t v[32];
+            tmem_ld_32x32(t_row + c * 32, v);
+            tmem_ld_wait();
+            const bool need_km = (p.mask != nullptr) || (c * 32 + 32 > L);  // warp-uniform
+#pragma unroll
+            for (int gq = 0; gq < 8; ++gq) {
+              const float4 lb = *reinterpret_cast<const float4*>(lutp + c * 32 + gq * 4);
+              float a0 = __uint_as_float(v[gq * 4 + 0]) + lb.x, a1 = __uint_as_float(v[gq * 4 + 1]) + lb.y;
+              float a2 = __uint_as_float(v[gq * 4 + 2]) + lb.z, a3 = __uint_as_float(v[gq * 4 + 3]) + lb.w;
+              if (need_km) {
+                const float4 km = *reinterpret_cast<const float4*>(s_kmask + c * 32 + gq * 4);
+                a0 += km.x;
+                a1 += km.y;
+                a2 += km.z;
+                a3 += km.w;
+              }
+              m0 = fmaxf(m0, a0);
+              m1 = fmaxf(m1, a1);
+              m2 = fmaxf(m2, a2);
+              m3 = fmaxf(m3, a3);
+            }
+          }
+        }
+        const float m = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+        const float nm = -m * LOG2E_F;
+        // ---- pass 2: p = exp(s - m) (un-normalised), row sum; bf16 pairs overwrite the consumed S columns in place
+        float lsum = 0.f;
+        for (int c = 0; c < nchunks; ++c) {
+          uint32_t pk[16];
+          uint32_t kword = 0u;
+          if (warp_live) {
+            uint32_t v[32];
+            tmem_ld_32x32(t_row + c * 32, v);
+            tmem_ld_wait();
+            const bool need_km = (p.mask != nullptr) || (c * 32 + 32 > L);
+#pragma unroll
+            for (int uu = 0; uu < 4; ++uu) {
+              float e[8];
+#pragma unroll
+              for (int hh = 0; hh < 2; ++hh) {
+                const float4 lb = *reinterpret_cast<const float4*>(lutp + c * 32 + uu * 8 + hh * 4);
+                float a0 = __uint_as_float(v[uu * 8 + hh * 4 + 0]) + lb.x, a1 = __uint_as_float(v[uu * 8 + hh * 4 + 1]) + lb.y;
+                float a2 = __uint_as_float(v[uu * 8 + hh * 4 + 2]) + lb.z, a3 = __uint_as_float(v[uu * 8 + hh * 4 + 3]) + lb.w;
+                if (need_km) {
+                  const float4 km = *reinterpret_cast<const float4*>(s_kmask + c * 32 + uu * 8 + hh * 4);
+                  a0 += km.x;
+                  a1 += km.y;
+                  a2 += km.z;
+                  a3 += km.w;
+                }
+                e[hh * 4 + 0] = fast_exp2(fmaf(a0, LOG2E_F, nm));
+                e[hh * 4 + 1] = fast_exp2(fmaf(a1, LOG2E_F, nm));
+                e[hh * 4 + 2] = fast_exp2(fmaf(a2, LOG2E_F, nm));
+                e[hh * 4 + 3] = fast_exp2(fmaf(a3, LOG2E_F, nm));
+              }
+#pragma unroll
+              for (int i = 0; i < 8; ++i) lsum += e[i];
+              if (p.drop.thresh) {  // the row sum normalises the UNdropped probabilities; only the P V operand is masked
+                const uint32_t kb = drop_keep8(p.drop, (static_cast<unsigned long long>(psg * H + h) * Lmax + qc) * 32 + c * 4 + uu);
+                kword |= kb << (uu * 8);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) e[i] = ((kb >> i) & 1u) ? e[i] * p.drop.scale : 0.f;
+              }
+#pragma unroll
+              for (int i = 0; i < 4; ++i) pk[uu * 4 + i] = pack_bf16x2(e[2 * i], e[2 * i + 1]);
+            }
+            if (p.keepbits && p.drop.thresh && q < L)
+              p.keepbits[((static_cast<size_t>(psg) * H + h) * Lmax + q) * 8 + c] = kword;
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) pk[i] = 0u;
+          }
+          tmem_st_32x16(t_row + c * 16, pk);
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(&p_ready[group]);
+        // ---- epilogue: O / row sum
+        mbar_wait(&o_full[group], k & 1);
+        tc_fence_after();
+        {
+          uint32_t o0[32], o1[32];
+          tmem_ld_32x32(t_row + A2_O_COL, o0);
+          tmem_ld_32x32(t_row + A2_O_COL + 32, o1);
+          tmem_ld_wait();
+          tc_fence_before();
+          mbar_arrive(&slot_free[group]);  // the slot may take the next tile's S while the stores below drain
+          if (q < L) {
+            const float inv = 1.f / lsum;
+            __nv_bfloat16* orow = p.out + static_cast<size_t>(row0 + q) * p.inner + h * 64;
+#pragma unroll
+            for (int uu = 0; uu < 8; ++uu) {
+              const uint32_t* oo = (uu < 4) ? o0 : o1;
+              const int o = (uu & 3) * 8;
+              uint4 w;
+              w.x = pack_bf16x2(__uint_as_float(oo[o + 0]) * inv, __uint_as_float(oo[o + 1]) * inv);
+              w.y = pack_bf16x2(__uint_as_float(oo[o + 2]) * inv, __uint_as_float(oo[o + 3]) * inv);
+              w.z = pack_bf16x2(__uint_as_float(oo[o + 4]) * inv, __uint_as_float(oo[o + 5]) * inv);
+              w.w = pack_bf16x2(__uint_as_float(oo[o + 6]) * inv, __uint_as_float(oo[o + 7]) * inv);
+              *reinterpret_cast<uint4*>(orow + uu * 8) = w;
+            }
+            if (p.lse) p.lse[(static_cast<size_t>(psg) * H + h) * Lmax + q] = m + logf(lsum);
+          }
+        }
+      }
+      ++ui;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
 // Test support: fill all 512 TMEM columns of every SM with NaN bit patterns (what a previous tenant of the GPU may
 // leave behind), so that tests can prove no kernel consumes TMEM it did not write.
 __global__ void __launch_bounds__(128, 1) poison_tmem_kernel() {
@@ -354,6 +665,21 @@ int enc_attn_fwd(const __nv_bfloat16* qkv, const unsigned char* mask, const floa
   p.drop = drop;
   p.keepbits = keepbits;
   ProfScope prof(PROF_ENC_ATTN_FWD, 4.0 * P * H * static_cast<double>(L) * L * 64, s);
+  if (enc_attn_impl() == 2) {
+    static bool configured2 = false;
+    if (!configured2) {
+      cudaError_t e = cudaFuncSetAttribute(enc_attn_fwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, A2_SMEM_BYTES);
+      if (e != cudaSuccess) {
+        set_last_error(cudaGetErrorString(e), __FILE__, __LINE__);
+        return LAKO_ERR_LAUNCH;
+      }
+      configured2 = true;
+    }
+    const int grid2 = std::min(P * H, device_sm_count());
+    launch_pdl(enc_attn_fwd2_kernel, dim3(grid2), dim3(A2_THREADS), A2_SMEM_BYTES, s, tm, p, P);
+    LAKO_CHECK_LAUNCH();
+    return LAKO_OK;
+  }
   dim3 grid((L + 127) / 128, H, P);
   launch_pdl(enc_attn_fwd_kernel, grid, dim3(256), EA_SMEM_BYTES, s, tm, p);
   LAKO_CHECK_LAUNCH();

@@ -42,6 +42,8 @@ int adamw_step(float* p, float* m, float* v, const float* g, __nv_bfloat16* w_bf
 
 
 // enc_attn.cu
+int enc_attn_impl();
+void set_enc_attn_impl(int v);
 int poison_tmem(cudaStream_t s);  // test support
 int build_bias_lut(const float* table, const int* buckets, float* lut, int H, int L, int bucket_center, cudaStream_t s);
 int fold_dlut(const float* dlut, const int* buckets, float* dtable, int H, int L, int bucket_center, int nb,

@@ -20,10 +20,13 @@ def _bias_lut(nat, table, buckets, H, L, center=511):
     return lut
 
 
-@pytest.mark.parametrize("P,L,H", [(3, 64, 2), (4, 200, 3), (2, 250, 2), (2, 256, 1), (5, 40, 2), (2, 130, 4)])
-def test_enc_attn_fwd_bwd(P, L, H):
+@pytest.mark.parametrize("impl", [2, 1])
+@pytest.mark.parametrize("P,L,H", [(3, 64, 2), (4, 200, 3), (2, 250, 2), (2, 256, 1), (5, 40, 2), (2, 130, 4), (40, 250, 16)])
+def test_enc_attn_fwd_bwd(P, L, H, impl):
+    """impl 2 = persistent warp-specialised forward with P in tensor memory (default), 1 = round 1's one-shot kernel."""
     nat = _nat()
     lib = nat.lib()
+    lib.lako_set_attn_impl(impl)
     from lako_b200.model import bucket_table
     torch.manual_seed(L)
     inner = H * 64
@@ -55,6 +58,7 @@ def test_enc_attn_fwd_bwd(P, L, H):
     ref = (pr @ v).transpose(1, 2).reshape(P * L, inner)
     assert torch.allclose(out.float(), ref, atol=3e-2, rtol=3e-2), (out.float() - ref).abs().max().item()
     assert torch.allclose(lse, torch.logsumexp(s, dim=-1), atol=2e-3, rtol=1e-4)
+    lib.lako_set_attn_impl(2)
     # backward
     dout = (torch.randn(P * L, inner, device="cuda") * 0.5).to(torch.bfloat16)
     ref.backward(dout.float())
