@@ -173,7 +173,8 @@ enc_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const EncAttnPar
   const int q = q0 + r;                // query position in the passage
   const int qc = min(q, L - 1);        // rows beyond the passage compute on a clamped position, never stored
   const int b = Lmax - 1 - qc;
-  const float* lutp = s_lut4 + (b & 3) * LUTCOPY + (b & ~3);
+  const uint32_t lut_a = smem_u32(s_lut4) + ((b & 3) * LUTCOPY + (b & ~3)) * 4;  // explicit shared addresses (common.cuh)
+  const uint32_t kmask_a = smem_u32(s_kmask), red_a = smem_u32(s_red_m), smem_a = smem_u32(smem);
   const uint32_t t_row = tmem + (static_cast<uint32_t>(quarter * 32) << 16);
   const int nchunks = (LK + 31) / 32;
   const int c_begin = chalf * 4, c_end = min(nchunks, chalf * 4 + 4);
@@ -193,13 +194,13 @@ enc_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const EncAttnPar
     const bool need_km = (p.mask != nullptr) || (c * 32 + 32 > L);  // warp-uniform
 #pragma unroll
     for (int g = 0; g < 8; ++g) {
-      const float4 lb = *reinterpret_cast<const float4*>(lutp + c * 32 + g * 4);
+      const float4 lb = lds_f4(lut_a + (c * 32 + g * 4) * 4);
       float s0 = __uint_as_float(v[g * 4 + 0]) + lb.x;
       float s1 = __uint_as_float(v[g * 4 + 1]) + lb.y;
       float s2 = __uint_as_float(v[g * 4 + 2]) + lb.z;
       float s3 = __uint_as_float(v[g * 4 + 3]) + lb.w;
       if (need_km) {
-        const float4 km = *reinterpret_cast<const float4*>(s_kmask + c * 32 + g * 4);
+        const float4 km = lds_f4(kmask_a + (c * 32 + g * 4) * 4);
         s0 += km.x;
         s1 += km.y;
         s2 += km.z;
@@ -214,9 +215,9 @@ enc_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const EncAttnPar
     tmem_st_32x32(t_row + c * 32, v);
   }
   tmem_st_wait();
-  s_red_m[chalf * 128 + r] = m;
+  sts_f(red_a + (chalf * 128 + r) * 4, m);
   __syncthreads();
-  m = fmaxf(s_red_m[r], s_red_m[128 + r]);
+  m = fmaxf(lds_f(red_a + r * 4), lds_f(red_a + (128 + r) * 4));
   // ---- pass 2: p = exp(s - m) (un-normalised), row sum, P -> shared (bf16, K-major 128B swizzle)
   const float nm = -m * LOG2E_F;
   float lsum = 0.f;
@@ -224,7 +225,7 @@ enc_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const EncAttnPar
     uint32_t v[32];
     tmem_ld_32x32(t_row + c * 32, v);
     tmem_ld_wait();
-    uint8_t* chunk = smem + (c >> 1) * 16384 + r * 128;
+    const uint32_t chunk_a = smem_a + (c >> 1) * 16384 + r * 128;
     uint32_t kword = 0u;
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
@@ -246,12 +247,12 @@ enc_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const EncAttnPar
       o.y = pack_bf16x2(e[2], e[3]);
       o.z = pack_bf16x2(e[4], e[5]);
       o.w = pack_bf16x2(e[6], e[7]);
-      *reinterpret_cast<uint4*>(chunk + ((unit ^ (r & 7)) << 4)) = o;
+      sts_u4(chunk_a + ((unit ^ (r & 7)) << 4), o);
     }
     if (p.keepbits && p.drop.thresh && q < L)
       p.keepbits[((static_cast<size_t>(psg) * p.H + h) * Lmax + q) * 8 + c] = kword;
   }
-  s_red_l[chalf * 128 + r] = lsum;
+  sts_f(red_a + (256 + chalf * 128 + r) * 4, lsum);
   fence_proxy_async_smem();
   tc_fence_before();
   __syncthreads();
@@ -269,7 +270,7 @@ enc_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const EncAttnPar
                 make_smem_desc_sw128(va + j * 2048, 8192, 1024), idesc, j > 0);
     umma_commit(bar_o);
   }
-  lsum = s_red_l[r] + s_red_l[128 + r];
+  lsum = lds_f(red_a + (256 + r) * 4) + lds_f(red_a + (256 + 128 + r) * 4);
   mbar_wait(bar_o, 0);
   tc_fence_after();
   {
@@ -302,65 +303,80 @@ enc_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const EncAttnPar
 // ================================================================================================
 // forward, version 2: persistent, warp-specialised, probabilities kept in tensor memory
 // ================================================================================================
-// One CTA per SM walks (passage, head) units.  Roles: warp 0 = producer (TMA loads of the unit's Q / K / V into a
-// 2-deep ring of shared-memory stages + the unit's bias LUT and key mask), warp 1 = one thread issuing every MMA,
-// warps 2-5 and 6-9 = two softmax groups, each bound to one 256-column TMEM slot and taking every other 128-query tile:
+// One CTA per SM serves ONE head (CTA c -> head c % H) and walks that head's passages, so the shifted bias LUTs are
+// staged once per CTA.  Roles: warp 0 = producer (TMA loads of a passage's Q / K / V into a 2-deep ring of
+// shared-memory stages), warp 1 = one thread issuing every MMA, warps 2-9 and 10-17 = two softmax groups, each bound to
+// one 256-column TMEM slot and taking every other 128-query tile:
 //   S = Q K^T (SS MMA, N = keys rounded to 32) -> slot columns [0, LK)
-//   softmax thread = one query row (TMEM lane): pass 1 row max of s + bias + mask, pass 2 exp -> bf16 pairs written
-//   IN PLACE over the consumed S columns ([0, LK/2)) by tcgen05.st
-//   O = P V with P as the TMEM A operand (TS MMA) -> slot columns [128, 192); read back, scaled by 1 / row sum, stored.
-// While one group runs its SIMT softmax the other group's loads / MMAs / epilogue proceed, the next unit's tiles are
-// already in flight, and nothing is allocated or staged per tile: the one-shot kernel above spends ~80 % of a CTA's
-// life in exposed latencies (TMEM allocation, LUT staging, TMA, MMA and tcgen05.ld round trips) at 2 CTAs per SM.
+//   two threads per query row (TMEM lane), one per half of the keys: pass 1 row max of s + bias + mask (exchanged
+//   through shared memory), pass 2 exp -> bf16 pairs written IN PLACE over the consumed S columns by tcgen05.st
+//   (keys 0-127 -> columns [0, 64), keys 128-255 -> columns [128, 192))
+//   O = P V with P as the TMEM A operand (TS MMA) -> slot columns [64, 128); read back, scaled by 1 / row sum, stored.
+// While one group runs its SIMT softmax the other group's MMAs / epilogue proceed and the next passage's tiles are
+// already in flight; nothing is allocated or staged per tile.  (The one-shot kernel above spends most of a CTA's life
+// in exposed latencies -- TMEM allocation, LUT staging, TMA, MMA and tcgen05.ld round trips -- at 2 CTAs per SM.)
 constexpr int A2_STAGE = 98304;  // Q0 16K | Q1 16K | K 32K | V 32K
 constexpr int A2_K_OFF = 32768, A2_V_OFF = 65536;
-constexpr int A2_LUT_OFF = 2 * A2_STAGE;
-constexpr int A2_KMASK_OFF = A2_LUT_OFF + 2 * 4 * LUTCOPY * 4;
-constexpr int A2_BAR_OFF = A2_KMASK_OFF + 2 * 1024;
+constexpr int A2_LUT_OFF = 2 * A2_STAGE;                      // 4 shifted LUT copies of this CTA's head
+constexpr int A2_KMASK_OFF = A2_LUT_OFF + 4 * LUTCOPY * 4;    // 2 stages x 256 floats (explicit key masks only)
+constexpr int A2_RED_OFF = A2_KMASK_OFF + 2 * 1024;           // row max / row sum exchange: [2 groups][2][2 halves][128]
+constexpr int A2_BAR_OFF = A2_RED_OFF + 2 * 2 * 2 * 128 * 4;
 constexpr int A2_SMEM_BYTES = A2_BAR_OFF + 256 + 1024;
-constexpr int A2_THREADS = 64 + 256;
-constexpr int A2_O_COL = 128;  // O accumulator columns inside a slot
+constexpr int A2_THREADS = 64 + 512;
+constexpr int A2_O_COL = 64;  // O accumulator columns inside a slot
+
+#ifdef LAKO_TRACE
+__device__ long long g_a2_trace[256];
+// role: 0 producer, 1 MMA, 2 softmax group 0, 3 softmax group 1; 64 stamps each (CTA 0 only)
+#define A2T(role, i, cond) do { if (blockIdx.x == 0 && (cond) && (i) < 64) g_a2_trace[(role) * 64 + (i)] = clock64(); } while (0)
+#else
+#define A2T(role, i, cond) do { } while (0)
+#endif
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
 
 __global__ void __launch_bounds__(A2_THREADS, 1)
 enc_attn_fwd2_kernel(const __grid_constant__ CUtensorMap tm_qkv, const EncAttnParams p, const int P) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  float* s_lut4 = reinterpret_cast<float*>(smem + A2_LUT_OFF);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + A2_BAR_OFF);
-  uint64_t* stage_full = bars;        // [2] TMA bytes of a unit landed
+  uint64_t* stage_full = bars;        // [2] TMA bytes of a passage landed (+ its key mask staged)
   uint64_t* stage_free = bars + 2;    // [2] every MMA reading the stage has completed
-  uint64_t* aux_full = bars + 4;      // [2] LUT + key mask of the unit staged
-  uint64_t* s_full = bars + 6;        // [2] S of a tile is in the slot
-  uint64_t* p_ready = bars + 8;       // [2] P of a tile is in the slot (128 softmax threads)
-  uint64_t* o_full = bars + 10;       // [2] O of a tile is in the slot
-  uint64_t* slot_free = bars + 12;    // [2] the slot's O has been read out (128 softmax threads)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+  uint64_t* s_full = bars + 4;        // [2] S of a tile is in the slot
+  uint64_t* p_ready = bars + 6;       // [2] P of a tile is in the slot (256 softmax threads)
+  uint64_t* o_full = bars + 8;        // [2] O of a tile is in the slot
+  uint64_t* slot_free = bars + 10;    // [2] the slot's O has been read out (256 softmax threads)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int Lmax = p.L, H = p.H, nunits = P * H;
+  const int Lmax = p.L, H = p.H;
+  const int h = blockIdx.x % H;                  // this CTA's head
+  const int pstep = gridDim.x / H;               // CTAs serving this head
+  const int p_first = blockIdx.x / H;            // first passage of this CTA
   pdl_launch_dependents();
   if (tid == 0) {
     tma_prefetch_desc(&tm_qkv);
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&stage_full[i], 1);
+      mbar_init(&stage_full[i], 2);   // the TMA's expect_tx arrival + the producer warp's "mask staged" arrival
       mbar_init(&stage_free[i], 1);
-      mbar_init(&aux_full[i], 1);
       mbar_init(&s_full[i], 1);
-      mbar_init(&p_ready[i], 128);
+      mbar_init(&p_ready[i], 256);
       mbar_init(&o_full[i], 1);
-      mbar_init(&slot_free[i], 128);
+      mbar_init(&slot_free[i], 256);
     }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, 512);
+  pdl_wait();
+  stage_lut4(s_lut4, p.bias_lut + h * (2 * Lmax - 1), 2 * Lmax - 1, tid, A2_THREADS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
-  pdl_wait();
 
-  // unit geometry, recomputed identically by every role
-  auto unit_geom = [&](int u, int& psg, int& h, int& row0, int& L) {
-    psg = u / H;
-    h = u - psg * H;
+  // passage geometry, recomputed identically by every role
+  auto psg_geom = [&](int psg, int& row0, int& L) {
     row0 = psg * Lmax;
     L = Lmax;
     if (p.cu) {
@@ -372,13 +388,15 @@ enc_attn_fwd2_kernel(const __grid_constant__ CUtensorMap tm_qkv, const EncAttnPa
   if (warp == 0) {
     // ------------------------------------------------------------------ producer
     int ui = 0;
-    for (int u = blockIdx.x; u < nunits; u += gridDim.x) {
-      int psg, h, row0, L;
-      unit_geom(u, psg, h, row0, L);
+    for (int psg = p_first; psg < P; psg += pstep) {
+      int row0, L;
+      psg_geom(psg, row0, L);
       if (L <= 0) continue;
       const int stage = ui & 1;
       const int LK = (L + 31) / 32 * 32, ktiles = (LK + 127) / 128, nt = (L + 127) / 128;
+      A2T(0, ui * 3 + 0, lane == 0);
       mbar_wait(&stage_free[stage], ((ui >> 1) & 1) ^ 1);
+      A2T(0, ui * 3 + 1, lane == 0);
       uint8_t* st = smem + stage * A2_STAGE;
       if (lane == 0) {
         mbar_arrive_expect_tx(&stage_full[stage], 16384 * (nt + 2 * ktiles));
@@ -388,12 +406,12 @@ enc_attn_fwd2_kernel(const __grid_constant__ CUtensorMap tm_qkv, const EncAttnPa
           tma_load_2d(st + A2_V_OFF + t * 16384, &tm_qkv, &stage_full[stage], 2 * p.inner + h * 64, row0 + t * 128);
         }
       }
-      stage_lut4(reinterpret_cast<float*>(smem + A2_LUT_OFF) + stage * 4 * LUTCOPY, p.bias_lut + h * (2 * Lmax - 1),
-                 2 * Lmax - 1, lane, 32);
-      stage_kmask(reinterpret_cast<float*>(smem + A2_KMASK_OFF) + stage * 256,
-                  p.mask ? p.mask + static_cast<size_t>(psg) * Lmax : nullptr, L, lane, 32);
+      if (p.mask)  // explicit key mask (padded layout): additive form for this passage
+        stage_kmask(reinterpret_cast<float*>(smem + A2_KMASK_OFF) + stage * 256, p.mask + static_cast<size_t>(psg) * Lmax, L,
+                    lane, 32);
       __syncwarp();
-      if (lane == 0) mbar_arrive(&aux_full[stage]);  // release: the warp's LUT / mask writes precede it
+      if (lane == 0) mbar_arrive(&stage_full[stage]);  // release: the warp's mask writes precede it
+      A2T(0, ui * 3 + 2, lane == 0);
       ++ui;
     }
   } else if (warp == 1) {
@@ -407,18 +425,20 @@ enc_attn_fwd2_kernel(const __grid_constant__ CUtensorMap tm_qkv, const EncAttnPa
       auto do_pv = [&]() {
         mbar_wait(&p_ready[pend_slot], pend_k & 1);
         tc_fence_after();
+        A2T(1, (pend_k * 2 + pend_slot) * 4 + 2, true);
         const uint32_t t_slot = tmem + pend_slot * 256;
         const uint32_t va = smem_u32(smem + pend_stage * A2_STAGE + A2_V_OFF);
         const int ksteps = pend_LK / 16;
-        for (int j = 0; j < ksteps; ++j)
-          umma_bf16_ts(t_slot + A2_O_COL, t_slot + j * 8, make_smem_desc_sw128(va + j * 2048, 8192, 1024), idesc_pv, j > 0);
+        for (int j = 0; j < ksteps; ++j)  // P: keys 0-127 at columns [0, 64), keys 128-255 at [128, 192)
+          umma_bf16_ts(t_slot + A2_O_COL, t_slot + (j < 8 ? j * 8 : 128 + (j - 8) * 8),
+                       make_smem_desc_sw128(va + j * 2048, 8192, 1024), idesc_pv, j > 0);
         umma_commit(&o_full[pend_slot]);
         if (pend_last) umma_commit(&stage_free[pend_stage]);
         pend = false;
       };
-      for (int u = blockIdx.x; u < nunits; u += gridDim.x) {
-        int psg, h, row0, L;
-        unit_geom(u, psg, h, row0, L);
+      for (int psg = p_first; psg < P; psg += pstep) {
+        int row0, L;
+        psg_geom(psg, row0, L);
         if (L <= 0) continue;
         const int stage = ui & 1;
         const int LK = (L + 31) / 32 * 32, nt = (L + 127) / 128;
@@ -428,8 +448,10 @@ enc_attn_fwd2_kernel(const __grid_constant__ CUtensorMap tm_qkv, const EncAttnPa
         const uint32_t idesc_s = make_idesc_bf16(128, LK, false, false);
         for (int t = 0; t < nt; ++t) {
           const int slot = n & 1, k = n >> 1;
+          A2T(1, n * 4 + 0, true);
           mbar_wait(&slot_free[slot], (k & 1) ^ 1);
           tc_fence_after();
+          A2T(1, n * 4 + 1, true);
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk)
             umma_bf16(tmem + slot * 256, make_smem_desc_sw128(qa + t * 16384 + kk * 32, 16, 1024),
@@ -450,139 +472,172 @@ enc_attn_fwd2_kernel(const __grid_constant__ CUtensorMap tm_qkv, const EncAttnPa
     }
   } else {
     // ------------------------------------------------------------------ softmax groups
-    const int group = (warp - 2) >> 2;   // == TMEM slot
+    const int sw = warp - 2;
+    const int group = sw >> 3;           // == TMEM slot
     const int quarter = warp & 3;        // TMEM lane quarter this warp may access
+    const int chalf = (sw >> 2) & 1;     // key half: chunks [4 chalf, 4 chalf + 4)
     const int r = quarter * 32 + lane;   // query row within the tile == TMEM lane
     const uint32_t t_row = tmem + group * 256 + (static_cast<uint32_t>(quarter * 32) << 16);
+    float* s_red = reinterpret_cast<float*>(smem + A2_RED_OFF) + group * 512;  // [max | sum][2 halves][128]
     int ui = 0, n = 0;
-    for (int u = blockIdx.x; u < nunits; u += gridDim.x) {
-      int psg, h, row0, L;
-      unit_geom(u, psg, h, row0, L);
+    for (int psg = p_first; psg < P; psg += pstep) {
+      int row0, L;
+      psg_geom(psg, row0, L);
       if (L <= 0) continue;
       const int stage = ui & 1;
       const int LK = (L + 31) / 32 * 32, nt = (L + 127) / 128, nchunks = LK / 32;
-      const float* s_lut4 = reinterpret_cast<const float*>(smem + A2_LUT_OFF) + stage * 4 * LUTCOPY;
       const float* s_kmask = reinterpret_cast<const float*>(smem + A2_KMASK_OFF) + stage * 256;
+      const int c_begin = chalf * 4, c_end = min(nchunks, chalf * 4 + 4);
       for (int t = 0; t < nt; ++t, ++n) {
         if ((n & 1) != group) continue;
         const int k = n >> 1;
         const int q0 = t * 128;
         const int q = q0 + r, qc = min(q, L - 1);
         const int b = Lmax - 1 - qc;
-        const float* lutp = s_lut4 + (b & 3) * LUTCOPY + (b & ~3);
-        mbar_wait(&aux_full[stage], (ui >> 1) & 1);
+        const uint32_t lut_a = smem_u32(s_lut4) + ((b & 3) * LUTCOPY + (b & ~3)) * 4;  // shared address of this row's biases
+        const bool trace = sw == (group * 8) && lane == 0;
+        (void)trace;
+        A2T(2 + group, k * 6 + 0, trace);
+        if (p.mask) mbar_wait(&stage_full[stage], (ui >> 1) & 1);  // the passage's key mask is staged
         mbar_wait(&s_full[group], k & 1);
         tc_fence_after();
+        A2T(2 + group, k * 6 + 1, trace);
         // rows of this warp all beyond the passage: no arithmetic, but the protocol (P defined, arrivals) is kept
         const bool warp_live = (q0 + quarter * 32) < L;
-        // ---- pass 1: row max of s + bias + mask
+        const int c_lim = warp_live ? c_end : c_begin;
+        // additive mask of one key: explicit mask table, or just "beyond the passage" for packed rows
+        auto kmask4 = [&](int key0) -> float4 {
+          if (p.mask) return lds_f4(smem_u32(s_kmask) + key0 * 4);
+          return make_float4(key0 + 0 < L ? 0.f : -INFINITY, key0 + 1 < L ? 0.f : -INFINITY,
+                             key0 + 2 < L ? 0.f : -INFINITY, key0 + 3 < L ? 0.f : -INFINITY);
+        };
+        // ---- pass 1: row max of s + bias + mask over this thread's half of the keys
         float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
-        if (warp_live) {
-          for (int c = 0; c < nchunks; ++c) {
-            uint32_t v[32];
-            tmem_ld_32x32(t_row + c * 32, v);
-            tmem_ld_wait();
-            const bool need_km = (p.mask != nullptr) || (c * 32 + 32 > L);  // warp-uniform
+        for (int c = c_begin; c < c_lim; ++c) {
+          uint32_t v[32];
+          tmem_ld_32x32(t_row + c * 32, v);
+          tmem_ld_wait();
+          const bool need_km = (p.mask != nullptr) || (c * 32 + 32 > L);  // warp-uniform
 #pragma unroll
-            for (int gq = 0; gq < 8; ++gq) {
-              const float4 lb = *reinterpret_cast<const float4*>(lutp + c * 32 + gq * 4);
-              float a0 = __uint_as_float(v[gq * 4 + 0]) + lb.x, a1 = __uint_as_float(v[gq * 4 + 1]) + lb.y;
-              float a2 = __uint_as_float(v[gq * 4 + 2]) + lb.z, a3 = __uint_as_float(v[gq * 4 + 3]) + lb.w;
-              if (need_km) {
-                const float4 km = *reinterpret_cast<const float4*>(s_kmask + c * 32 + gq * 4);
-                a0 += km.x;
-                a1 += km.y;
-                a2 += km.z;
-                a3 += km.w;
-              }
-              m0 = fmaxf(m0, a0);
-              m1 = fmaxf(m1, a1);
-              m2 = fmaxf(m2, a2);
-              m3 = fmaxf(m3, a3);
+          for (int gq = 0; gq < 8; ++gq) {
+            const float4 lb = lds_f4(lut_a + (c * 32 + gq * 4) * 4);
+            float a0 = __uint_as_float(v[gq * 4 + 0]) + lb.x, a1 = __uint_as_float(v[gq * 4 + 1]) + lb.y;
+            float a2 = __uint_as_float(v[gq * 4 + 2]) + lb.z, a3 = __uint_as_float(v[gq * 4 + 3]) + lb.w;
+            if (need_km) {
+              const float4 km = kmask4(c * 32 + gq * 4);
+              a0 += km.x;
+              a1 += km.y;
+              a2 += km.z;
+              a3 += km.w;
             }
+            m0 = fmaxf(m0, a0);
+            m1 = fmaxf(m1, a1);
+            m2 = fmaxf(m2, a2);
+            m3 = fmaxf(m3, a3);
           }
         }
-        const float m = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+        float m = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+        const uint32_t red_a = smem_u32(s_red);
+        sts_f(red_a + (chalf * 128 + r) * 4, m);
+        named_bar_sync(1 + group, 256);
+        m = fmaxf(lds_f(red_a + r * 4), lds_f(red_a + (128 + r) * 4));
         const float nm = -m * LOG2E_F;
-        // ---- pass 2: p = exp(s - m) (un-normalised), row sum; bf16 pairs overwrite the consumed S columns in place
-        float lsum = 0.f;
-        for (int c = 0; c < nchunks; ++c) {
-          uint32_t pk[16];
-          uint32_t kword = 0u;
-          if (warp_live) {
-            uint32_t v[32];
-            tmem_ld_32x32(t_row + c * 32, v);
-            tmem_ld_wait();
-            const bool need_km = (p.mask != nullptr) || (c * 32 + 32 > L);
+        A2T(2 + group, k * 6 + 2, trace);
+        // ---- pass 2: p = exp(s - m) (un-normalised), row sum; bf16 pairs overwrite the consumed S columns in place:
+        //      16-column piece j of this half (S columns chalf*128 + 16 j ..) -> P columns chalf*128 + 8 j ..
+        float ls0 = 0.f, ls1 = 0.f, ls2 = 0.f, ls3 = 0.f;
+        for (int c = c_begin; c < c_end; ++c) {
+          uint32_t kword = 0u;  // keep bits of the chunk's 32 keys
 #pragma unroll
-            for (int uu = 0; uu < 4; ++uu) {
-              float e[8];
+          for (int hp = 0; hp < 2; ++hp) {  // two 16-column pieces per 32-key chunk
+            uint32_t pk[8];
+            if (c < c_lim) {
+              uint32_t v[16];
+              tmem_ld_32x16(t_row + c * 32 + hp * 16, v);
+              tmem_ld_wait();
+              const bool need_km = (p.mask != nullptr) || (c * 32 + 32 > L);
 #pragma unroll
-              for (int hh = 0; hh < 2; ++hh) {
-                const float4 lb = *reinterpret_cast<const float4*>(lutp + c * 32 + uu * 8 + hh * 4);
-                float a0 = __uint_as_float(v[uu * 8 + hh * 4 + 0]) + lb.x, a1 = __uint_as_float(v[uu * 8 + hh * 4 + 1]) + lb.y;
-                float a2 = __uint_as_float(v[uu * 8 + hh * 4 + 2]) + lb.z, a3 = __uint_as_float(v[uu * 8 + hh * 4 + 3]) + lb.w;
-                if (need_km) {
-                  const float4 km = *reinterpret_cast<const float4*>(s_kmask + c * 32 + uu * 8 + hh * 4);
-                  a0 += km.x;
-                  a1 += km.y;
-                  a2 += km.z;
-                  a3 += km.w;
+              for (int uu = 0; uu < 2; ++uu) {
+                float e[8];
+#pragma unroll
+                for (int hh = 0; hh < 2; ++hh) {
+                  const int col = c * 32 + hp * 16 + uu * 8 + hh * 4;
+                  const float4 lb = lds_f4(lut_a + col * 4);
+                  float a0 = __uint_as_float(v[uu * 8 + hh * 4 + 0]) + lb.x, a1 = __uint_as_float(v[uu * 8 + hh * 4 + 1]) + lb.y;
+                  float a2 = __uint_as_float(v[uu * 8 + hh * 4 + 2]) + lb.z, a3 = __uint_as_float(v[uu * 8 + hh * 4 + 3]) + lb.w;
+                  if (need_km) {
+                    const float4 km = kmask4(col);
+                    a0 += km.x;
+                    a1 += km.y;
+                    a2 += km.z;
+                    a3 += km.w;
+                  }
+                  e[hh * 4 + 0] = fast_exp2(fmaf(a0, LOG2E_F, nm));
+                  e[hh * 4 + 1] = fast_exp2(fmaf(a1, LOG2E_F, nm));
+                  e[hh * 4 + 2] = fast_exp2(fmaf(a2, LOG2E_F, nm));
+                  e[hh * 4 + 3] = fast_exp2(fmaf(a3, LOG2E_F, nm));
                 }
-                e[hh * 4 + 0] = fast_exp2(fmaf(a0, LOG2E_F, nm));
-                e[hh * 4 + 1] = fast_exp2(fmaf(a1, LOG2E_F, nm));
-                e[hh * 4 + 2] = fast_exp2(fmaf(a2, LOG2E_F, nm));
-                e[hh * 4 + 3] = fast_exp2(fmaf(a3, LOG2E_F, nm));
+                ls0 += e[0] + e[4];
+                ls1 += e[1] + e[5];
+                ls2 += e[2] + e[6];
+                ls3 += e[3] + e[7];
+                if (p.drop.thresh) {  // the row sum normalises the UNdropped probabilities; only the P V operand is masked
+                  const int u4 = hp * 2 + uu;  // 8-key group within the chunk
+                  const uint32_t kb = drop_keep8(p.drop, (static_cast<unsigned long long>(psg * H + h) * Lmax + qc) * 32 + c * 4 + u4);
+                  kword |= kb << (u4 * 8);
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) e[i] = ((kb >> i) & 1u) ? e[i] * p.drop.scale : 0.f;
+                }
+#pragma unroll
+                for (int i = 0; i < 4; ++i) pk[uu * 4 + i] = pack_bf16x2(e[2 * i], e[2 * i + 1]);
               }
+            } else {
 #pragma unroll
-              for (int i = 0; i < 8; ++i) lsum += e[i];
-              if (p.drop.thresh) {  // the row sum normalises the UNdropped probabilities; only the P V operand is masked
-                const uint32_t kb = drop_keep8(p.drop, (static_cast<unsigned long long>(psg * H + h) * Lmax + qc) * 32 + c * 4 + uu);
-                kword |= kb << (uu * 8);
-#pragma unroll
-                for (int i = 0; i < 8; ++i) e[i] = ((kb >> i) & 1u) ? e[i] * p.drop.scale : 0.f;
-              }
-#pragma unroll
-              for (int i = 0; i < 4; ++i) pk[uu * 4 + i] = pack_bf16x2(e[2 * i], e[2 * i + 1]);
+              for (int i = 0; i < 8; ++i) pk[i] = 0u;
             }
-            if (p.keepbits && p.drop.thresh && q < L)
-              p.keepbits[((static_cast<size_t>(psg) * H + h) * Lmax + q) * 8 + c] = kword;
-          } else {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) pk[i] = 0u;
+            // tcgen05.st of 8 columns: two bf16 per column
+            asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(
+                             t_row + chalf * 128 + (c - c_begin) * 16 + hp * 8),
+                         "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]), "r"(pk[4]), "r"(pk[5]), "r"(pk[6]), "r"(pk[7])
+                         : "memory");
           }
-          tmem_st_32x16(t_row + c * 16, pk);
+          if (c < c_lim && p.keepbits && p.drop.thresh && q < L)
+            p.keepbits[((static_cast<size_t>(psg) * H + h) * Lmax + q) * 8 + c] = kword;
         }
+        const float lsum_half = (ls0 + ls1) + (ls2 + ls3);
+        sts_f(red_a + (256 + chalf * 128 + r) * 4, lsum_half);
         tmem_st_wait();
         tc_fence_before();
         mbar_arrive(&p_ready[group]);
-        // ---- epilogue: O / row sum
+        A2T(2 + group, k * 6 + 3, trace);
+        // ---- epilogue: O / row sum (each half reads 32 of the 64 head dims)
         mbar_wait(&o_full[group], k & 1);
         tc_fence_after();
+        A2T(2 + group, k * 6 + 4, trace);
+        named_bar_sync(1 + group, 256);  // both halves' row sums are in shared memory
+        const float lsum = lds_f(red_a + (256 + r) * 4) + lds_f(red_a + (256 + 128 + r) * 4);
         {
-          uint32_t o0[32], o1[32];
-          tmem_ld_32x32(t_row + A2_O_COL, o0);
-          tmem_ld_32x32(t_row + A2_O_COL + 32, o1);
+          uint32_t o0[32];
+          tmem_ld_32x32(t_row + A2_O_COL + chalf * 32, o0);
           tmem_ld_wait();
           tc_fence_before();
           mbar_arrive(&slot_free[group]);  // the slot may take the next tile's S while the stores below drain
           if (q < L) {
             const float inv = 1.f / lsum;
-            __nv_bfloat16* orow = p.out + static_cast<size_t>(row0 + q) * p.inner + h * 64;
+            __nv_bfloat16* orow = p.out + static_cast<size_t>(row0 + q) * p.inner + h * 64 + chalf * 32;
 #pragma unroll
-            for (int uu = 0; uu < 8; ++uu) {
-              const uint32_t* oo = (uu < 4) ? o0 : o1;
-              const int o = (uu & 3) * 8;
+            for (int uu = 0; uu < 4; ++uu) {
               uint4 w;
-              w.x = pack_bf16x2(__uint_as_float(oo[o + 0]) * inv, __uint_as_float(oo[o + 1]) * inv);
-              w.y = pack_bf16x2(__uint_as_float(oo[o + 2]) * inv, __uint_as_float(oo[o + 3]) * inv);
-              w.z = pack_bf16x2(__uint_as_float(oo[o + 4]) * inv, __uint_as_float(oo[o + 5]) * inv);
-              w.w = pack_bf16x2(__uint_as_float(oo[o + 6]) * inv, __uint_as_float(oo[o + 7]) * inv);
+              w.x = pack_bf16x2(__uint_as_float(o0[uu * 8 + 0]) * inv, __uint_as_float(o0[uu * 8 + 1]) * inv);
+              w.y = pack_bf16x2(__uint_as_float(o0[uu * 8 + 2]) * inv, __uint_as_float(o0[uu * 8 + 3]) * inv);
+              w.z = pack_bf16x2(__uint_as_float(o0[uu * 8 + 4]) * inv, __uint_as_float(o0[uu * 8 + 5]) * inv);
+              w.w = pack_bf16x2(__uint_as_float(o0[uu * 8 + 6]) * inv, __uint_as_float(o0[uu * 8 + 7]) * inv);
               *reinterpret_cast<uint4*>(orow + uu * 8) = w;
             }
-            if (p.lse) p.lse[(static_cast<size_t>(psg) * H + h) * Lmax + q] = m + logf(lsum);
+            if (p.lse && chalf == 0) p.lse[(static_cast<size_t>(psg) * H + h) * Lmax + q] = m + logf(lsum);
           }
         }
+        A2T(2 + group, k * 6 + 5, trace);
       }
       ++ui;
     }
@@ -665,7 +720,7 @@ int enc_attn_fwd(const __nv_bfloat16* qkv, const unsigned char* mask, const floa
   p.drop = drop;
   p.keepbits = keepbits;
   ProfScope prof(PROF_ENC_ATTN_FWD, 4.0 * P * H * static_cast<double>(L) * L * 64, s);
-  if (enc_attn_impl() == 2) {
+  if (enc_attn_impl() == 2 && H <= device_sm_count()) {
     static bool configured2 = false;
     if (!configured2) {
       cudaError_t e = cudaFuncSetAttribute(enc_attn_fwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, A2_SMEM_BYTES);
@@ -675,8 +730,9 @@ int enc_attn_fwd(const __nv_bfloat16* qkv, const unsigned char* mask, const floa
       }
       configured2 = true;
     }
-    const int grid2 = std::min(P * H, device_sm_count());
-    launch_pdl(enc_attn_fwd2_kernel, dim3(grid2), dim3(A2_THREADS), A2_SMEM_BYTES, s, tm, p, P);
+    // every CTA serves one head: (SMs / H) CTAs per head (at most one per passage)
+    const int per_head = std::max(1, std::min(P, device_sm_count() / H));
+    launch_pdl(enc_attn_fwd2_kernel, dim3(per_head * H), dim3(A2_THREADS), A2_SMEM_BYTES, s, tm, p, P);
     LAKO_CHECK_LAUNCH();
     return LAKO_OK;
   }
@@ -920,7 +976,7 @@ enc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
       const int q = qt * 128 + r;
       const int qc = min(q, L - 1);
       const int b = Lmax - 1 - qc;
-      const float* lutp = s_lut4 + (b & 3) * LUTCOPY + (b & ~3);
+      const uint32_t lut_a = smem_u32(s_lut4) + ((b & 3) * LUTCOPY + (b & ~3)) * 4;  // explicit shared addresses
       const bool rows_live = (qt * 128 + quarter * 32) < L;  // warp-uniform: any of this warp's queries in the passage
       const int kbase = kt * 128 + cq * 32;                  // first key of this warp's 32-column chunk
       // the forward's keep mask of this row's 32 keys (fetched ahead of the MMA wait)
@@ -931,8 +987,8 @@ enc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
       s_phase ^= 1;
       tc_fence_after();
       EB_TRACE(8 + (kt * 2 + qt) * 6 + 0);
-      const float nlse_q = -s_lse[q] * LOG2E_F;  // lse = +inf beyond the passage -> exp2(-inf) = 0
-      const float D_q = s_D[q];
+      const float nlse_q = -lds_f(smem_u32(s_lse) + q * 4) * LOG2E_F;  // lse = +inf beyond the passage -> exp2(-inf) = 0
+      const float D_q = lds_f(smem_u32(s_D) + q * 4);
       const bool live = rows_live && kbase < L;
       const bool need_km = (p.mask != nullptr) || (kbase + 32 > L);
       // !live: nothing of this 32x32 sub-block lies inside the passage: P = dS = 0 (dV / dK sum over all 128 rows of
@@ -945,8 +1001,8 @@ enc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
       // column i (parked in lane i's Rdone), and after the last column lane l holds the complete d = 31 - l (>= 0).
       float Rup = 0.f, Rdone = 0.f;
       // 64-key chunk (cq >> 1) of the K-major P / dS tiles; this warp's 32 keys are 16-byte units (cq & 1)*4..+4
-      uint8_t* prow = smem + EB_P_OFF + (cq >> 1) * 16384 + r * 128;
-      uint8_t* dsrow = smem + EB_DS_OFF + (cq >> 1) * 16384 + r * 128;
+      const uint32_t prow = smem_u32(smem) + EB_P_OFF + (cq >> 1) * 16384 + r * 128;
+      const uint32_t dsrow = smem_u32(smem) + EB_DS_OFF + (cq >> 1) * 16384 + r * 128;
 #pragma unroll
       for (int hh = 0; hh < 2; ++hh) {  // two 16-column halves keep the live register set small
         uint32_t ppk[8], dpk[8];        // bf16x2-packed P_drop and dS of 16 columns
@@ -966,15 +1022,15 @@ enc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
 #pragma unroll
           for (int uu = 0; uu < 2; ++uu) {
             const int u = hh * 2 + uu;
-            const float4 lb0 = *reinterpret_cast<const float4*>(lutp + kbase + u * 8);
-            const float4 lb1 = *reinterpret_cast<const float4*>(lutp + kbase + u * 8 + 4);
+            const float4 lb0 = lds_f4(lut_a + (kbase + u * 8) * 4);
+            const float4 lb1 = lds_f4(lut_a + (kbase + u * 8 + 4) * 4);
             const float lbv[8] = {lb0.x, lb0.y, lb0.z, lb0.w, lb1.x, lb1.y, lb1.z, lb1.w};
             float sc[8], pr[8], ds[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) sc[i] = __uint_as_float(sv[uu * 8 + i]) + lbv[i];
             if (need_km) {  // warp-uniform: a key mask was given, or the chunk straddles the end of the passage
-              const float4 km0 = *reinterpret_cast<const float4*>(s_kmask + kbase + u * 8);
-              const float4 km1 = *reinterpret_cast<const float4*>(s_kmask + kbase + u * 8 + 4);
+              const float4 km0 = lds_f4(smem_u32(s_kmask) + (kbase + u * 8) * 4);
+              const float4 km1 = lds_f4(smem_u32(s_kmask) + (kbase + u * 8 + 4) * 4);
               const float kmv[8] = {km0.x, km0.y, km0.z, km0.w, km1.x, km1.y, km1.z, km1.w};
 #pragma unroll
               for (int i = 0; i < 8; ++i) sc[i] += kmv[i];
@@ -1017,15 +1073,15 @@ enc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
 #pragma unroll
         for (int uu = 0; uu < 2; ++uu) {
           const int unit = (((cq & 1) * 4 + hh * 2 + uu) ^ (r & 7)) << 4;
-          *reinterpret_cast<uint4*>(prow + unit) = make_uint4(ppk[uu * 4], ppk[uu * 4 + 1], ppk[uu * 4 + 2], ppk[uu * 4 + 3]);
-          *reinterpret_cast<uint4*>(dsrow + unit) = make_uint4(dpk[uu * 4], dpk[uu * 4 + 1], dpk[uu * 4 + 2], dpk[uu * 4 + 3]);
+          sts_u4(prow + unit, make_uint4(ppk[uu * 4], ppk[uu * 4 + 1], ppk[uu * 4 + 2], ppk[uu * 4 + 3]));
+          sts_u4(dsrow + unit, make_uint4(dpk[uu * 4], dpk[uu * 4 + 1], dpk[uu * 4 + 2], dpk[uu * 4 + 3]));
         }
       }
       if (live) {
         const int iu = idx0 + 31 - lane;
-        if (iu >= 0 && iu < nlut) atomicAdd(&s_dlut[iu], Rup);
+        if (iu >= 0 && iu < nlut) red_shared_add_f(smem_u32(s_dlut) + iu * 4, Rup);
         const int id = idx0 + lane - 31;
-        if (lane != 31 && id >= 0 && id < nlut) atomicAdd(&s_dlut[id], Rdone);  // d = 0 is already in Rup (lane 31)
+        if (lane != 31 && id >= 0 && id < nlut) red_shared_add_f(smem_u32(s_dlut) + id * 4, Rdone);  // d = 0 is in Rup (lane 31)
       }
       EB_TRACE(8 + (kt * 2 + qt) * 6 + 2);
       fence_proxy_async_smem();
@@ -1113,6 +1169,9 @@ enc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
 }
 
 #ifdef LAKO_TRACE
+extern "C" int lako_debug_a2_trace(long long* out) {
+  return cudaMemcpyFromSymbol(out, g_a2_trace, sizeof(long long) * 256) == cudaSuccess ? 0 : 1;
+}
 extern "C" int lako_debug_eb_trace(long long* out) {
   return cudaMemcpyFromSymbol(out, g_eb_trace, sizeof(long long) * 64) == cudaSuccess ? 0 : 1;
 }
