@@ -67,6 +67,28 @@ struct EncAttnParams {
 };
 
 constexpr float LOG2E_F = 1.4426950408889634f;
+constexpr float LN2_F = 0.6931471805599453f;
+
+// Packed fp32 pairs (sm_100: FFMA2 / FADD2 work on 64-bit register pairs): (a0, a1) = (a0, a1) * s + (b0, b1)
+__device__ __forceinline__ void ffma2(uint32_t& a0, uint32_t& a1, float s, float b0, float b1) {
+  asm("{\n\t.reg .b64 ra, rs, rb;\n\tmov.b64 ra, {%0, %1};\n\tmov.b64 rs, {%2, %2};\n\tmov.b64 rb, {%3, %4};\n\t"
+      "fma.rn.f32x2 ra, ra, rs, rb;\n\tmov.b64 {%0, %1}, ra;\n\t}"
+      : "+r"(a0), "+r"(a1)
+      : "f"(s), "f"(b0), "f"(b1));
+}
+// (a0, a1) += (b0, b1)
+__device__ __forceinline__ void fadd2(uint32_t& a0, uint32_t& a1, float b0, float b1) {
+  asm("{\n\t.reg .b64 ra, rb;\n\tmov.b64 ra, {%0, %1};\n\tmov.b64 rb, {%2, %3};\n\tadd.rn.f32x2 ra, ra, rb;\n\t"
+      "mov.b64 {%0, %1}, ra;\n\t}"
+      : "+r"(a0), "+r"(a1)
+      : "f"(b0), "f"(b1));
+}
+__device__ __forceinline__ void fadd2(float& a0, float& a1, float b0, float b1) {
+  asm("{\n\t.reg .b64 ra, rb;\n\tmov.b64 ra, {%0, %1};\n\tmov.b64 rb, {%2, %3};\n\tadd.rn.f32x2 ra, ra, rb;\n\t"
+      "mov.b64 {%0, %1}, ra;\n\t}"
+      : "+f"(a0), "+f"(a1)
+      : "f"(b0), "f"(b1));
+}
 constexpr int LUTCOPY = 520;  // floats per shifted LUT copy (max index (L-1) + 255 + 3 < 520 for L <= 256)
 
 // Four copies of the per-head bias LUT, copy j shifted left by j floats, so that every thread can fetch
@@ -80,7 +102,20 @@ __device__ __forceinline__ void stage_lut4(float* s_lut4, const float* __restric
     s_lut4[i] = (src < nlut) ? lut[src] : 0.f;
   }
 }
-// additive key mask: 0 valid, finfo.min for padded keys (HF semantics), -inf beyond the passage
+// The same biases as a table of overlapping windows, win[x] = (lut[x], lut[x+1], lut[x+2], lut[x+3]) * scale: the thread
+// of query q fetches the biases of keys k..k+3 (k % 4 == 0) as the 16-byte entry x = (L-1-q) + k.  Consecutive lanes
+// (consecutive queries) read consecutive entries, so every 8 lanes cover 128 contiguous bytes: conflict free (the 4
+// shifted copies above cost 2 wavefronts per 8 lanes).
+constexpr int LUTWIN = 512;  // entries; x <= 255 + 252
+__device__ __forceinline__ void stage_lut_win(float* s_win, const float* __restrict__ lut, int nlut, int tid, int nthreads,
+                                              float scale) {
+  for (int i = tid; i < 4 * LUTWIN; i += nthreads) {
+    const int src = (i >> 2) + (i & 3);
+    s_win[i] = (src < nlut) ? lut[src] * scale : 0.f;
+  }
+}
+// additive key mask: 0 valid, finfo.min for padded keys (HF semantics; it stays finfo.min in the log2 domain of the v2
+// kernel, so a fully masked row still degrades to the uniform distribution), -inf beyond the passage
 __device__ __forceinline__ void stage_kmask(float* s_kmask, const unsigned char* __restrict__ mask, int L, int tid,
                                             int nthreads) {
   for (int i = tid; i < 256; i += nthreads)
@@ -318,7 +353,7 @@ enc_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const EncAttnPar
 constexpr int A2_STAGE = 98304;  // Q0 16K | Q1 16K | K 32K | V 32K
 constexpr int A2_K_OFF = 32768, A2_V_OFF = 65536;
 constexpr int A2_LUT_OFF = 2 * A2_STAGE;                      // 4 shifted LUT copies of this CTA's head
-constexpr int A2_KMASK_OFF = A2_LUT_OFF + 4 * LUTCOPY * 4;    // 2 stages x 256 floats (explicit key masks only)
+constexpr int A2_KMASK_OFF = A2_LUT_OFF + 4 * LUTWIN * 4;    // 2 stages x 256 floats (explicit key masks only)
 constexpr int A2_RED_OFF = A2_KMASK_OFF + 2 * 1024;           // row max / row sum exchange: [2 groups][2][2 halves][128]
 constexpr int A2_BAR_OFF = A2_RED_OFF + 2 * 2 * 2 * 128 * 4;
 constexpr int A2_SMEM_BYTES = A2_BAR_OFF + 256 + 1024;
@@ -336,6 +371,7 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
+template <bool kMask, bool kDrop>
 __global__ void __launch_bounds__(A2_THREADS, 1)
 enc_attn_fwd2_kernel(const __grid_constant__ CUtensorMap tm_qkv, const EncAttnParams p, const int P) {
   extern __shared__ uint8_t smem_raw[];
@@ -349,7 +385,8 @@ enc_attn_fwd2_kernel(const __grid_constant__ CUtensorMap tm_qkv, const EncAttnPa
   uint64_t* o_full = bars + 8;        // [2] O of a tile is in the slot
   uint64_t* slot_free = bars + 10;    // [2] the slot's O has been read out (256 softmax threads)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  // warp index through a shuffle: provably warp-uniform, so roles, TMEM addresses and loop state live in uniform registers
+  const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
   const int Lmax = p.L, H = p.H;
   const int h = blockIdx.x % H;                  // this CTA's head
   const int pstep = gridDim.x / H;               // CTAs serving this head
@@ -369,7 +406,7 @@ enc_attn_fwd2_kernel(const __grid_constant__ CUtensorMap tm_qkv, const EncAttnPa
   }
   if (warp == 1) tmem_alloc(tmem_slot, 512);
   pdl_wait();
-  stage_lut4(s_lut4, p.bias_lut + h * (2 * Lmax - 1), 2 * Lmax - 1, tid, A2_THREADS);
+  stage_lut_win(s_lut4, p.bias_lut + h * (2 * Lmax - 1), 2 * Lmax - 1, tid, A2_THREADS, LOG2E_F);  // log2 domain
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -406,7 +443,7 @@ enc_attn_fwd2_kernel(const __grid_constant__ CUtensorMap tm_qkv, const EncAttnPa
           tma_load_2d(st + A2_V_OFF + t * 16384, &tm_qkv, &stage_full[stage], 2 * p.inner + h * 64, row0 + t * 128);
         }
       }
-      if (p.mask)  // explicit key mask (padded layout): additive form for this passage
+      if (kMask)  // explicit key mask (padded layout): additive form for this passage
         stage_kmask(reinterpret_cast<float*>(smem + A2_KMASK_OFF) + stage * 256, p.mask + static_cast<size_t>(psg) * Lmax, L,
                     lane, 32);
       __syncwarp();
@@ -494,115 +531,99 @@ enc_attn_fwd2_kernel(const __grid_constant__ CUtensorMap tm_qkv, const EncAttnPa
         const int q0 = t * 128;
         const int q = q0 + r, qc = min(q, L - 1);
         const int b = Lmax - 1 - qc;
-        const uint32_t lut_a = smem_u32(s_lut4) + ((b & 3) * LUTCOPY + (b & ~3)) * 4;  // shared address of this row's biases
+        const uint32_t lut_a = smem_u32(s_lut4) + b * 16;  // shared address of this row's bias windows
         const bool trace = sw == (group * 8) && lane == 0;
         (void)trace;
         A2T(2 + group, k * 6 + 0, trace);
-        if (p.mask) mbar_wait(&stage_full[stage], (ui >> 1) & 1);  // the passage's key mask is staged
+        if (kMask) mbar_wait(&stage_full[stage], (ui >> 1) & 1);  // the passage's key mask is staged
         mbar_wait(&s_full[group], k & 1);
         tc_fence_after();
         A2T(2 + group, k * 6 + 1, trace);
-        // rows of this warp all beyond the passage: no arithmetic, but the protocol (P defined, arrivals) is kept
+        // warps whose 32 query rows all lie beyond the passage do no arithmetic (the MMA is row independent: whatever their
+        // P rows hold only reaches O rows that are never stored) but keep the protocol (barriers, arrivals)
         const bool warp_live = (q0 + quarter * 32) < L;
-        const int c_lim = warp_live ? c_end : c_begin;
-        // additive mask of one key: explicit mask table, or just "beyond the passage" for packed rows
-        auto kmask4 = [&](int key0) -> float4 {
-          if (p.mask) return lds_f4(smem_u32(s_kmask) + key0 * 4);
-          return make_float4(key0 + 0 < L ? 0.f : -INFINITY, key0 + 1 < L ? 0.f : -INFINITY,
-                             key0 + 2 < L ? 0.f : -INFINITY, key0 + 3 < L ? 0.f : -INFINITY);
-        };
-        // ---- pass 1: row max of s + bias + mask over this thread's half of the keys
-        float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
-        for (int c = c_begin; c < c_lim; ++c) {
-          uint32_t v[32];
-          tmem_ld_32x32(t_row + c * 32, v);
-          tmem_ld_wait();
-          const bool need_km = (p.mask != nullptr) || (c * 32 + 32 > L);  // warp-uniform
+        const int nlive = warp_live ? (c_end - c_begin) : 0;  // 32-key chunks of this half: 0..4, warp-uniform
+        const uint32_t t_half = t_row + chalf * 128;            // this half's S columns
+        const uint32_t lut_h = lut_a + chalf * 2048;            // ... and its (log2e-scaled) bias windows
+        const uint32_t km_h = smem_u32(s_kmask) + chalf * 512;
+        // ---- pass 1: t = s * log2(e) + bias' (+ mask), row max; t goes back to its TMEM columns so that pass 2 is
+        //      exp2(t - max) only.  Everything is unrolled over the 4 chunks: TMEM / shared addresses are immediates.
+        float m0 = -INFINITY, m1 = -INFINITY;
 #pragma unroll
-          for (int gq = 0; gq < 8; ++gq) {
-            const float4 lb = lds_f4(lut_a + (c * 32 + gq * 4) * 4);
-            float a0 = __uint_as_float(v[gq * 4 + 0]) + lb.x, a1 = __uint_as_float(v[gq * 4 + 1]) + lb.y;
-            float a2 = __uint_as_float(v[gq * 4 + 2]) + lb.z, a3 = __uint_as_float(v[gq * 4 + 3]) + lb.w;
-            if (need_km) {
-              const float4 km = kmask4(c * 32 + gq * 4);
-              a0 += km.x;
-              a1 += km.y;
-              a2 += km.z;
-              a3 += km.w;
+        for (int ci = 0; ci < 4; ++ci) {
+          if (ci < nlive) {
+            uint32_t v[32];
+            tmem_ld_32x32(t_half + ci * 32, v);
+            tmem_ld_wait();
+            if (!kMask && (c_begin + ci) * 32 + 32 > L) {  // packed rows: only the passage's last chunk has dead keys
+#pragma unroll
+              for (int i = 0; i < 32; ++i)
+                if ((c_begin + ci) * 32 + i >= L) v[i] = 0xff800000u;  // -inf
             }
-            m0 = fmaxf(m0, a0);
-            m1 = fmaxf(m1, a1);
-            m2 = fmaxf(m2, a2);
-            m3 = fmaxf(m3, a3);
+#pragma unroll
+            for (int g = 0; g < 8; ++g) {
+              const float4 lb = lds_f4(lut_h + (ci * 32 + g * 4) * 16);
+              ffma2(v[g * 4 + 0], v[g * 4 + 1], LOG2E_F, lb.x, lb.y);
+              ffma2(v[g * 4 + 2], v[g * 4 + 3], LOG2E_F, lb.z, lb.w);
+              if (kMask) {
+                const float4 km = lds_f4(km_h + (ci * 32 + g * 4) * 4);
+                fadd2(v[g * 4 + 0], v[g * 4 + 1], km.x, km.y);
+                fadd2(v[g * 4 + 2], v[g * 4 + 3], km.z, km.w);
+              }
+              m0 = fmaxf(m0, fmaxf(__uint_as_float(v[g * 4 + 0]), __uint_as_float(v[g * 4 + 1])));
+              m1 = fmaxf(m1, fmaxf(__uint_as_float(v[g * 4 + 2]), __uint_as_float(v[g * 4 + 3])));
+            }
+            tmem_st_32x32(t_half + ci * 32, v);
           }
         }
-        float m = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+        float m = fmaxf(m0, m1);
         const uint32_t red_a = smem_u32(s_red);
         sts_f(red_a + (chalf * 128 + r) * 4, m);
+        tmem_st_wait();
         named_bar_sync(1 + group, 256);
-        m = fmaxf(lds_f(red_a + r * 4), lds_f(red_a + (128 + r) * 4));
-        const float nm = -m * LOG2E_F;
+        m = fmaxf(lds_f(red_a + r * 4), lds_f(red_a + (128 + r) * 4));  // log2 domain
+        const float nm = -m;
         A2T(2 + group, k * 6 + 2, trace);
-        // ---- pass 2: p = exp(s - m) (un-normalised), row sum; bf16 pairs overwrite the consumed S columns in place:
-        //      16-column piece j of this half (S columns chalf*128 + 16 j ..) -> P columns chalf*128 + 8 j ..
+        // ---- pass 2: p = exp2(t - max) (un-normalised), row sum; bf16 pairs overwrite consumed S columns in place:
+        //      chunk ci of this half (S columns chalf*128 + 32 ci ..) -> P columns chalf*128 + 16 ci ..  Dropout only
+        //      zeroes entries here (the 1/(1-p) factor is applied with 1 / row sum in the epilogue).
         float ls0 = 0.f, ls1 = 0.f, ls2 = 0.f, ls3 = 0.f;
-        for (int c = c_begin; c < c_end; ++c) {
-          uint32_t kword = 0u;  // keep bits of the chunk's 32 keys
 #pragma unroll
-          for (int hp = 0; hp < 2; ++hp) {  // two 16-column pieces per 32-key chunk
-            uint32_t pk[8];
-            if (c < c_lim) {
-              uint32_t v[16];
-              tmem_ld_32x16(t_row + c * 32 + hp * 16, v);
-              tmem_ld_wait();
-              const bool need_km = (p.mask != nullptr) || (c * 32 + 32 > L);
+        for (int ci = 0; ci < 4; ++ci) {
+          if (ci < nlive) {
+            uint32_t v[32];
+            tmem_ld_32x32(t_half + ci * 32, v);
+            tmem_ld_wait();
+            uint32_t pk[16];
+            uint32_t kword = 0xffffffffu;
+            if (kDrop) {
+              kword = 0u;
 #pragma unroll
-              for (int uu = 0; uu < 2; ++uu) {
-                float e[8];
-#pragma unroll
-                for (int hh = 0; hh < 2; ++hh) {
-                  const int col = c * 32 + hp * 16 + uu * 8 + hh * 4;
-                  const float4 lb = lds_f4(lut_a + col * 4);
-                  float a0 = __uint_as_float(v[uu * 8 + hh * 4 + 0]) + lb.x, a1 = __uint_as_float(v[uu * 8 + hh * 4 + 1]) + lb.y;
-                  float a2 = __uint_as_float(v[uu * 8 + hh * 4 + 2]) + lb.z, a3 = __uint_as_float(v[uu * 8 + hh * 4 + 3]) + lb.w;
-                  if (need_km) {
-                    const float4 km = kmask4(col);
-                    a0 += km.x;
-                    a1 += km.y;
-                    a2 += km.z;
-                    a3 += km.w;
-                  }
-                  e[hh * 4 + 0] = fast_exp2(fmaf(a0, LOG2E_F, nm));
-                  e[hh * 4 + 1] = fast_exp2(fmaf(a1, LOG2E_F, nm));
-                  e[hh * 4 + 2] = fast_exp2(fmaf(a2, LOG2E_F, nm));
-                  e[hh * 4 + 3] = fast_exp2(fmaf(a3, LOG2E_F, nm));
-                }
-                ls0 += e[0] + e[4];
-                ls1 += e[1] + e[5];
-                ls2 += e[2] + e[6];
-                ls3 += e[3] + e[7];
-                if (p.drop.thresh) {  // the row sum normalises the UNdropped probabilities; only the P V operand is masked
-                  const int u4 = hp * 2 + uu;  // 8-key group within the chunk
-                  const uint32_t kb = drop_keep8(p.drop, (static_cast<unsigned long long>(psg * H + h) * Lmax + qc) * 32 + c * 4 + u4);
-                  kword |= kb << (u4 * 8);
-#pragma unroll
-                  for (int i = 0; i < 8; ++i) e[i] = ((kb >> i) & 1u) ? e[i] * p.drop.scale : 0.f;
-                }
-#pragma unroll
-                for (int i = 0; i < 4; ++i) pk[uu * 4 + i] = pack_bf16x2(e[2 * i], e[2 * i + 1]);
-              }
-            } else {
-#pragma unroll
-              for (int i = 0; i < 8; ++i) pk[i] = 0u;
+              for (int u4 = 0; u4 < 4; ++u4)
+                kword |= drop_keep8(p.drop, (static_cast<unsigned long long>(psg * H + h) * Lmax + qc) * 32 + (c_begin + ci) * 4 + u4)
+                         << (u4 * 8);
             }
-            // tcgen05.st of 8 columns: two bf16 per column
-            asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(
-                             t_row + chalf * 128 + (c - c_begin) * 16 + hp * 8),
-                         "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]), "r"(pk[4]), "r"(pk[5]), "r"(pk[6]), "r"(pk[7])
-                         : "memory");
+#pragma unroll
+            for (int g = 0; g < 8; ++g) {
+              fadd2(v[g * 4 + 0], v[g * 4 + 1], nm, nm);
+              fadd2(v[g * 4 + 2], v[g * 4 + 3], nm, nm);
+              float e0 = fast_exp2(__uint_as_float(v[g * 4 + 0])), e1 = fast_exp2(__uint_as_float(v[g * 4 + 1]));
+              float e2 = fast_exp2(__uint_as_float(v[g * 4 + 2])), e3 = fast_exp2(__uint_as_float(v[g * 4 + 3]));
+              fadd2(ls0, ls1, e0, e1);
+              fadd2(ls2, ls3, e2, e3);
+              pk[g * 2 + 0] = pack_bf16x2(e0, e1);
+              pk[g * 2 + 1] = pack_bf16x2(e2, e3);
+            }
+            if (kDrop) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                const uint32_t two = (kword >> (2 * i)) & 3u;
+                pk[i] &= (two & 1u ? 0x0000ffffu : 0u) | (two & 2u ? 0xffff0000u : 0u);
+              }
+              if (p.keepbits && q < L) p.keepbits[((static_cast<size_t>(psg) * H + h) * Lmax + q) * 8 + c_begin + ci] = kword;
+            }
+            tmem_st_32x16(t_row + chalf * 128 + ci * 16, pk);
           }
-          if (c < c_lim && p.keepbits && p.drop.thresh && q < L)
-            p.keepbits[((static_cast<size_t>(psg) * H + h) * Lmax + q) * 8 + c] = kword;
         }
         const float lsum_half = (ls0 + ls1) + (ls2 + ls3);
         sts_f(red_a + (256 + chalf * 128 + r) * 4, lsum_half);
@@ -623,7 +644,7 @@ enc_attn_fwd2_kernel(const __grid_constant__ CUtensorMap tm_qkv, const EncAttnPa
           tc_fence_before();
           mbar_arrive(&slot_free[group]);  // the slot may take the next tile's S while the stores below drain
           if (q < L) {
-            const float inv = 1.f / lsum;
+            const float inv = (kDrop ? p.drop.scale : 1.f) / lsum;
             __nv_bfloat16* orow = p.out + static_cast<size_t>(row0 + q) * p.inner + h * 64 + chalf * 32;
 #pragma unroll
             for (int uu = 0; uu < 4; ++uu) {
@@ -634,7 +655,7 @@ enc_attn_fwd2_kernel(const __grid_constant__ CUtensorMap tm_qkv, const EncAttnPa
               w.w = pack_bf16x2(__uint_as_float(o0[uu * 8 + 6]) * inv, __uint_as_float(o0[uu * 8 + 7]) * inv);
               *reinterpret_cast<uint4*>(orow + uu * 8) = w;
             }
-            if (p.lse && chalf == 0) p.lse[(static_cast<size_t>(psg) * H + h) * Lmax + q] = m + logf(lsum);
+            if (p.lse && chalf == 0) p.lse[(static_cast<size_t>(psg) * H + h) * Lmax + q] = (m + log2f(lsum)) * LN2_F;
           }
         }
         A2T(2 + group, k * 6 + 5, trace);
@@ -721,18 +742,23 @@ int enc_attn_fwd(const __nv_bfloat16* qkv, const unsigned char* mask, const floa
   p.keepbits = keepbits;
   ProfScope prof(PROF_ENC_ATTN_FWD, 4.0 * P * H * static_cast<double>(L) * L * 64, s);
   if (enc_attn_impl() == 2 && H <= device_sm_count()) {
+    using Kern = void (*)(CUtensorMap, EncAttnParams, int);
+    static const Kern kerns[4] = {enc_attn_fwd2_kernel<false, false>, enc_attn_fwd2_kernel<false, true>,
+                                  enc_attn_fwd2_kernel<true, false>, enc_attn_fwd2_kernel<true, true>};
     static bool configured2 = false;
     if (!configured2) {
-      cudaError_t e = cudaFuncSetAttribute(enc_attn_fwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, A2_SMEM_BYTES);
-      if (e != cudaSuccess) {
-        set_last_error(cudaGetErrorString(e), __FILE__, __LINE__);
-        return LAKO_ERR_LAUNCH;
+      for (Kern kf : kerns) {
+        cudaError_t e = cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, A2_SMEM_BYTES);
+        if (e != cudaSuccess) {
+          set_last_error(cudaGetErrorString(e), __FILE__, __LINE__);
+          return LAKO_ERR_LAUNCH;
+        }
       }
       configured2 = true;
     }
     // every CTA serves one head: (SMs / H) CTAs per head (at most one per passage)
     const int per_head = std::max(1, std::min(P, device_sm_count() / H));
-    launch_pdl(enc_attn_fwd2_kernel, dim3(per_head * H), dim3(A2_THREADS), A2_SMEM_BYTES, s, tm, p, P);
+    launch_pdl(kerns[(mask ? 2 : 0) + (drop.thresh ? 1 : 0)], dim3(per_head * H), dim3(A2_THREADS), A2_SMEM_BYTES, s, tm, p, P);
     LAKO_CHECK_LAUNCH();
     return LAKO_OK;
   }
