@@ -827,7 +827,8 @@ enc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
   uint64_t* bar_sfree = bar_load + 4;  // all softmax threads: S / dP of the block are in registers (TMEM columns free)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_load + 5);
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  // warp index through a shuffle: provably warp-uniform (the issuing warp's loops then run on uniform registers)
+  const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
   const int quarter = warp & 3, cq = warp >> 2;
   const bool issuer = tid == EB_SOFTMAX_THREADS;  // lane 0 of the 17th warp
   const int h = blockIdx.x, psg = blockIdx.y;
@@ -930,57 +931,65 @@ enc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
   constexpr uint32_t idesc_tn = make_idesc_bf16(128, 64, true, true);      // dV, dK: MN-major x MN-major
   constexpr uint32_t idesc_dq = make_idesc_bf16(128, 64, false, true);     // dQ    : K-major x MN-major
 
+  // descriptor start-address fields count 16-byte units: + 2 per 32-byte K step of a K-major tile, + 128 per 2048-byte
+  // step of an MN-major one, + 1024 per 16 KB tile
+  const uint64_t qd = make_smem_desc_sw128(qa, 16, 1024), dod = make_smem_desc_sw128(doa, 16, 1024),
+                 kd = make_smem_desc_sw128(ka, 16, 1024), vd = make_smem_desc_sw128(va, 16, 1024);
+  const uint64_t p_t = make_smem_desc_sw128(pa, 16384, 1024), ds_t = make_smem_desc_sw128(dsa, 16384, 1024),
+                 ds_k = make_smem_desc_sw128(dsa, 16, 1024);
+  const uint64_t do_mn = make_smem_desc_sw128(doa, 8192, 1024), q_mn = make_smem_desc_sw128(qa, 8192, 1024),
+                 k_mn = make_smem_desc_sw128(ka, 8192, 1024);
   auto issue_s_dp = [&](int qt, int kt) {
 #pragma unroll
-    for (int k = 0; k < 4; ++k)
-      umma_bf16(tmem + TM_S, make_smem_desc_sw128(qa + qt * 16384 + k * 32, 16, 1024),
-                make_smem_desc_sw128(ka + kt * 16384 + k * 32, 16, 1024), idesc_s, k > 0);
+    for (int k = 0; k < 4; ++k) umma_bf16(tmem + TM_S, qd + qt * 1024 + k * 2, kd + kt * 1024 + k * 2, idesc_s, k > 0);
 #pragma unroll
-    for (int k = 0; k < 4; ++k)
-      umma_bf16(tmem + TM_DP, make_smem_desc_sw128(doa + qt * 16384 + k * 32, 16, 1024),
-                make_smem_desc_sw128(va + kt * 16384 + k * 32, 16, 1024), idesc_s, k > 0);
+    for (int k = 0; k < 4; ++k) umma_bf16(tmem + TM_DP, dod + qt * 1024 + k * 2, vd + kt * 1024 + k * 2, idesc_s, k > 0);
   };
 
   if (warp == EB_SOFTMAX_THREADS / 32) {
-    // ---------------- issuing warp: one thread drives every MMA of the CTA
-    if (issuer) {
-      mbar_wait(bar_load, 0);
-      tc_fence_after();
+    // ---------------- issuing warp: the whole warp walks the loop and waits (uniform control flow, descriptors in uniform
+    // registers), one elected lane issues.  With the loop inside an `if (one thread)` region every MMA is wrapped in a
+    // divergence "waterfall" (ELECT / R2UR.BROADCAST / BRA.U.ANY, ~130 cycles per MMA): 32 MMAs per block then cost more
+    // issue time than the block's softmax arithmetic.
+    const bool el = elect_one();  // (MMA only: a TMA producer written this way lost its loads' byte counts)
+    mbar_wait_warp(bar_load, 0);
+    tc_fence_after();
+    if (el) {
       issue_s_dp(0, 0);
       umma_commit(bar_mma);
-      uint32_t r_phase = 0;
-      for (int kt = 0; kt < nt; ++kt) {
-        for (int qt = 0; qt < nt; ++qt) {
-          // The softmax threads release the S / dP columns as soon as their values are in registers (about half way
-          // through the block's arithmetic): the next block's S / dP are computed underneath the rest of it.
-          mbar_wait(bar_sfree, r_phase);
-          tc_fence_after();
-          int nq = qt + 1, nk = kt;
-          if (nq == nt) {
-            nq = 0;
-            nk = kt + 1;
-          }
-          if (nk < nt) {
-            issue_s_dp(nq, nk);
-            umma_commit(bar_mma);
-          }
-          mbar_wait(bar_ready, r_phase);  // P / dS of this block are in shared memory
-          r_phase ^= 1;
-          tc_fence_after();
+    }
+    uint32_t r_phase = 0;
+    for (int kt = 0; kt < nt; ++kt) {
+      for (int qt = 0; qt < nt; ++qt) {
+        // The softmax threads release the S / dP columns as soon as their values are in registers (about half way
+        // through the block's arithmetic): the next block's S / dP are computed underneath the rest of it.
+        mbar_wait_warp(bar_sfree, r_phase);
+        tc_fence_after();
+        int nq = qt + 1, nk = kt;
+        if (nq == nt) {
+          nq = 0;
+          nk = kt + 1;
+        }
+        if (nk < nt && el) {
+          issue_s_dp(nq, nk);
+          umma_commit(bar_mma);
+        }
+        mbar_wait_warp(bar_ready, r_phase);  // P / dS of this block are in shared memory
+        r_phase ^= 1;
+        tc_fence_after();
+        if (el) {
           // dV[kt] += P^T dO[qt] ; dK[kt] += dS^T Q[qt]   (M = 128 keys, N = 64, K = 128 queries)
 #pragma unroll
           for (int j = 0; j < 8; ++j)
-            umma_bf16(tmem + TM_DV, make_smem_desc_sw128(pa + j * 2048, 16384, 1024),
-                      make_smem_desc_sw128(doa + qt * 16384 + j * 2048, 8192, 1024), idesc_tn, (qt > 0 || j > 0));
+            umma_bf16(tmem + TM_DV, p_t + j * 128, do_mn + qt * 1024 + j * 128, idesc_tn, (qt > 0 || j > 0));
 #pragma unroll
           for (int j = 0; j < 8; ++j)
-            umma_bf16(tmem + TM_DK, make_smem_desc_sw128(dsa + j * 2048, 16384, 1024),
-                      make_smem_desc_sw128(qa + qt * 16384 + j * 2048, 8192, 1024), idesc_tn, (qt > 0 || j > 0));
+            umma_bf16(tmem + TM_DK, ds_t + j * 128, q_mn + qt * 1024 + j * 128, idesc_tn, (qt > 0 || j > 0));
           // dQ[qt] += dS K[kt]   (M = 128 queries, N = 64, K = 128 keys)
 #pragma unroll
           for (int j = 0; j < 8; ++j)
-            umma_bf16(tmem + TM_DQ + qt * 64, make_smem_desc_sw128(dsa + (j >> 2) * 16384 + (j & 3) * 32, 16, 1024),
-                      make_smem_desc_sw128(ka + kt * 16384 + j * 2048, 8192, 1024), idesc_dq, (kt > 0 || j > 0));
+            umma_bf16(tmem + TM_DQ + qt * 64, ds_k + (j >> 2) * 1024 + (j & 3) * 2, k_mn + kt * 1024 + j * 128, idesc_dq,
+                      (kt > 0 || j > 0));
           umma_commit(bar_grad);
         }
       }

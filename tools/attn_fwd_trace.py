@@ -39,6 +39,6 @@ print("MMA (tile n: reach QK, slot free, -, PV issue):")
 for n in range(8):
     print("  tile", n, [rel(t[64 + n * 4 + j]) for j in range(4)])
 for g in (0, 1):
-    print(f"softmax group {g} (k-th tile: reach, S ready, pass1 done, P ready, O ready, stored):")
-    for k in range(5):
+    print(f"softmax group {g} (k-th tile: reach, S ready, pass1 done + turn, P ready, O ready, stored):")
+    for k in range(6):
         print("  ", k, [rel(t[(2 + g) * 64 + k * 6 + j]) for j in range(6)])
