@@ -240,6 +240,17 @@ int lako_enc_attn_fwd(const void* qkv, const unsigned char* mask, const float* b
                       int L, int H, void* stream);
 int lako_enc_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse, const unsigned char* mask,
                       const float* bias_lut, void* dqkv, float* dlut, int P, int L, int H, void* stream);
+/* the same with dropout on the attention probabilities (HF modeling_t5.py:332, active in model.train()): keep decisions
+ * from Philox4x32-7 keyed by (seed, step, site), one bit-sliced comparison per (query row, 32-key chunk)
+ * (csrc/common.cuh drop_keep32_sliced; lako_b200/philox.py attn_keep_words restates it).  keepbits [P][H][L][8] receives
+ * (forward) / supplies (backward; NULL = regenerate) the keep words. */
+int lako_enc_attn_fwd_dropout(const void* qkv, const unsigned char* mask, const float* bias_lut, void* out, float* lse,
+                              unsigned int* keepbits, int P, int L, int H, unsigned long long seed, unsigned int step,
+                              unsigned int site, float p, void* stream);
+int lako_enc_attn_bwd_dropout(const void* qkv, const void* out, const void* dout, const float* lse,
+                              const unsigned char* mask, const float* bias_lut, void* dqkv, float* dlut,
+                              const unsigned int* keepbits, int P, int L, int H, unsigned long long seed,
+                              unsigned int step, unsigned int site, float p, void* stream);
 /* cross-attention over the fused memory, src/model.py:286-349 */
 size_t lako_xattn_workspace_bytes(int B, int H, int T, int M);
 int lako_xattn_fwd(const void* q, const void* kv, const unsigned char* mask, void* out, float* lse, float* tok_score,

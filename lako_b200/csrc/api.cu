@@ -94,6 +94,21 @@ int lako_enc_attn_bwd(const void* qkv, const void* out, const void* dout, const 
   ARCH_GUARD();
   return enc_attn_bwd(CBF(qkv), CBF(out), CBF(dout), lse, mask, bias_lut, BF(dqkv), dlut, P, L, H, ST(stream));
 }
+int lako_enc_attn_fwd_dropout(const void* qkv, const unsigned char* mask, const float* bias_lut, void* out, float* lse,
+                              unsigned int* keepbits, int P, int L, int H, unsigned long long seed, unsigned int step,
+                              unsigned int site, float p, void* stream) {
+  ARCH_GUARD();
+  return enc_attn_fwd(CBF(qkv), mask, bias_lut, BF(out), lse, P, L, H, ST(stream), make_drop(seed, step, site, p), nullptr, 0,
+                      keepbits);
+}
+int lako_enc_attn_bwd_dropout(const void* qkv, const void* out, const void* dout, const float* lse,
+                              const unsigned char* mask, const float* bias_lut, void* dqkv, float* dlut,
+                              const unsigned int* keepbits, int P, int L, int H, unsigned long long seed,
+                              unsigned int step, unsigned int site, float p, void* stream) {
+  ARCH_GUARD();
+  return enc_attn_bwd(CBF(qkv), CBF(out), CBF(dout), lse, mask, bias_lut, BF(dqkv), dlut, P, L, H, ST(stream),
+                      make_drop(seed, step, site, p), nullptr, 0, keepbits);
+}
 size_t lako_xattn_workspace_bytes(int B, int H, int T, int M) { return xattn_workspace_bytes(B, H, T, M); }
 int lako_xattn_fwd(const void* q, const void* kv, const unsigned char* mask, void* out, float* lse, float* tok_score,
                    float* workspace, int B, int T, int M, int H, int ldq, int ldkv, int koff, int voff, int ldo,

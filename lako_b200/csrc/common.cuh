@@ -454,6 +454,39 @@ __device__ __forceinline__ uint32_t drop_keep8(const DropSpec& d, unsigned long 
   return m;
 }
 
+// Attention-probability dropout (HF:332), 32 keys at a time: the keep decisions of one (query row, 32-key chunk) as ONE
+// bit-sliced threshold comparison.  The 16 words of 4 consecutive Philox counters are the bit planes of 32 independent
+// 16-bit uniforms U_b (bit k of U_b = bit b of word k); keep_b = (U_b >= thresh), evaluated from the least significant
+// plane up with one 3-input logic op per plane:  ge = thresh_k ? (w_k & ge) : (w_k | ge).  Same Philox work and the same
+// keep probability 1 - thresh / 65536 as drop_keep8, but 16 logic ops per 32 keys instead of ~4 per key, and the result
+// is already the packed word the backward reads.  Bit b <-> key: key j of the chunk is bit (j >> 1) + 16 (j & 1), so the
+// bf16 pair (2i, 2i+1) owns bits i and i + 16: `word << (15 - i)` puts them on the sign bits of the two halfwords and one
+// PRMT (sign replicate) turns that into the pair's AND mask.  lako_b200/philox.py (attn_keep_words) restates it.
+__device__ __forceinline__ uint32_t drop_keep32_sliced(const DropSpec& d, unsigned long long group4) {
+  uint32_t ge = 0xffffffffu;
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const unsigned long long g = group4 + u;
+    const uint4 r = philox4x32(make_uint4(static_cast<uint32_t>(g), static_cast<uint32_t>(g >> 32), d.site, d.step),
+                                  make_uint2(static_cast<uint32_t>(d.seed), static_cast<uint32_t>(d.seed >> 32)));
+    const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const uint32_t tm = 0u - ((d.thresh >> (u * 4 + j)) & 1u);  // warp-uniform: all ones where the threshold bit is set
+      ge = (tm & w[j] & ge) | (~tm & (w[j] | ge));
+    }
+  }
+  return ge;
+}
+// bit of key j (0..31) in a drop_keep32_sliced word
+__host__ __device__ constexpr int sliced_bit(int j) { return (j >> 1) + 16 * (j & 1); }
+// AND mask of the bf16 pair (keys 2i, 2i+1) of the chunk
+__device__ __forceinline__ uint32_t sliced_pair_mask(uint32_t word, int i) {
+  uint32_t m;  // prmt's sign-replicate mode (selector nibble bit 3); __byte_perm only honours 3 bits per nibble
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(m) : "r"(word << (15 - i)), "r"(0u), "r"(0xbb99u));
+  return m;
+}
+
 #endif  // __CUDACC__
 
 #ifdef __CUDACC__

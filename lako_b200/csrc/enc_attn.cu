@@ -261,7 +261,9 @@ enc_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const EncAttnPar
     tmem_ld_32x32(t_row + c * 32, v);
     tmem_ld_wait();
     const uint32_t chunk_a = smem_a + (c >> 1) * 16384 + r * 128;
-    uint32_t kword = 0u;
+    uint32_t kword = 0xffffffffu;  // keep bits of the chunk's 32 keys (drop_keep32_sliced order)
+    if (p.drop.thresh)
+      kword = drop_keep32_sliced(p.drop, (static_cast<unsigned long long>(psg * p.H + h) * Lmax + qc) * 32 + c * 4);
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       float e[8];
@@ -271,10 +273,8 @@ enc_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const EncAttnPar
         lsum += e[i];
       }
       if (p.drop.thresh) {  // the row sum normalises the UNdropped probabilities; only the P V operand is masked
-        const uint32_t k = drop_keep8(p.drop, (static_cast<unsigned long long>(psg * p.H + h) * Lmax + qc) * 32 + c * 4 + u);
-        kword |= k << (u * 8);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) e[i] = ((k >> i) & 1u) ? e[i] * p.drop.scale : 0.f;
+        for (int i = 0; i < 8; ++i) e[i] = ((kword >> sliced_bit(u * 8 + i)) & 1u) ? e[i] * p.drop.scale : 0.f;
       }
       const int unit = (c & 1) * 4 + u;  // 16-byte unit index within the 128-byte row
       uint4 o;
@@ -535,6 +535,14 @@ enc_attn_fwd2_kernel(const __grid_constant__ CUtensorMap tm_qkv, const EncAttnPa
         const bool trace = sw == (group * 8) && lane == 0;
         (void)trace;
         A2T(2 + group, k * 6 + 0, trace);
+        // dropout keep words of this thread's four 32-key chunks, drawn under the wait for S
+        uint32_t kw[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
+        if (kDrop) {
+#pragma unroll
+          for (int ci = 0; ci < 4; ++ci)
+            if (c_begin + ci < c_end)
+              kw[ci] = drop_keep32_sliced(p.drop, (static_cast<unsigned long long>(psg * H + h) * Lmax + qc) * 32 + (c_begin + ci) * 4);
+        }
         if (kMask) mbar_wait(&stage_full[stage], (ui >> 1) & 1);  // the passage's key mask is staged
         mbar_wait(&s_full[group], k & 1);
         tc_fence_after();
@@ -595,14 +603,6 @@ enc_attn_fwd2_kernel(const __grid_constant__ CUtensorMap tm_qkv, const EncAttnPa
             tmem_ld_32x32(t_half + ci * 32, v);
             tmem_ld_wait();
             uint32_t pk[16];
-            uint32_t kword = 0xffffffffu;
-            if (kDrop) {
-              kword = 0u;
-#pragma unroll
-              for (int u4 = 0; u4 < 4; ++u4)
-                kword |= drop_keep8(p.drop, (static_cast<unsigned long long>(psg * H + h) * Lmax + qc) * 32 + (c_begin + ci) * 4 + u4)
-                         << (u4 * 8);
-            }
 #pragma unroll
             for (int g = 0; g < 8; ++g) {
               fadd2(v[g * 4 + 0], v[g * 4 + 1], nm, nm);
@@ -616,11 +616,8 @@ enc_attn_fwd2_kernel(const __grid_constant__ CUtensorMap tm_qkv, const EncAttnPa
             }
             if (kDrop) {
 #pragma unroll
-              for (int i = 0; i < 16; ++i) {
-                const uint32_t two = (kword >> (2 * i)) & 3u;
-                pk[i] &= (two & 1u ? 0x0000ffffu : 0u) | (two & 2u ? 0xffff0000u : 0u);
-              }
-              if (p.keepbits && q < L) p.keepbits[((static_cast<size_t>(psg) * H + h) * Lmax + q) * 8 + c_begin + ci] = kword;
+              for (int i = 0; i < 16; ++i) pk[i] &= sliced_pair_mask(kw[ci], i);
+              if (p.keepbits && q < L) p.keepbits[((static_cast<size_t>(psg) * H + h) * Lmax + q) * 8 + c_begin + ci] = kw[ci];
             }
             tmem_st_32x16(t_row + chalf * 128 + ci * 16, pk);
           }
@@ -1015,9 +1012,11 @@ enc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
       const bool rows_live = (qt * 128 + quarter * 32) < L;  // warp-uniform: any of this warp's queries in the passage
       const int kbase = kt * 128 + cq * 32;                  // first key of this warp's 32-column chunk
       // the forward's keep mask of this row's 32 keys (fetched ahead of the MMA wait)
-      uint32_t kword = 0xffffffffu;
-      if (p.keepbits && p.drop.thresh && q < L && kbase < L)
-        kword = __ldg(p.keepbits + ((static_cast<size_t>(psg) * p.H + h) * Lmax + q) * 8 + (kbase >> 5));
+      uint32_t kword = 0xffffffffu;  // drop_keep32_sliced order
+      if (p.drop.thresh && q < L && kbase < L)
+        kword = p.keepbits ? __ldg(p.keepbits + ((static_cast<size_t>(psg) * p.H + h) * Lmax + q) * 8 + (kbase >> 5))
+                           : drop_keep32_sliced(p.drop, (static_cast<unsigned long long>(psg * p.H + h) * Lmax + qc) * 32 +
+                                                            (kbase >> 3));
       mbar_wait(bar_mma, s_phase);
       s_phase ^= 1;
       tc_fence_after();
@@ -1070,18 +1069,11 @@ enc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
 #pragma unroll
               for (int i = 0; i < 8; ++i) sc[i] += kmv[i];
             }
-            uint32_t keepm = 0xffu;
-            float dscale = 1.f;
-            if (p.drop.thresh) {
-              keepm = p.keepbits ? ((kword >> (u * 8)) & 0xffu)
-                                 : drop_keep8(p.drop, (static_cast<unsigned long long>(psg * p.H + h) * Lmax + qc) * 32 +
-                                                          (kbase >> 3) + u);
-              dscale = p.drop.scale;
-            }
+            const float dscale = p.drop.thresh ? p.drop.scale : 1.f;
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
               const float pv = fast_exp2(fmaf(sc[i], LOG2E_F, nlse_q));          // P = exp(s - lse)
-              const float mi = ((keepm >> i) & 1u) ? dscale : 0.f;                 // dropout keep * 1/(1-p)
+              const float mi = ((kword >> sliced_bit(u * 8 + i)) & 1u) ? dscale : 0.f;  // dropout keep * 1/(1-p)
               ds[i] = pv * fmaf(__uint_as_float(dpv[uu * 8 + i]), mi, -D_q);      // dS = P (dP_drop - D)
               pr[i] = pv * mi;                                                     // the dV = P_drop^T dO operand
             }

@@ -48,3 +48,34 @@ def keep_mask(seed, step, site, n_elems, p):
         lanes[:, 2 * j] = r[j] & np.uint32(0xFFFF)
         lanes[:, 2 * j + 1] = r[j] >> np.uint32(16)
     return (lanes >= thresh_of(p)).reshape(-1)[:n_elems]
+
+
+def attn_keep_words(seed, step, site, group4, p):
+    """uint32 numpy array like group4: the keep word of one (query row, 32-key chunk) of the attention-probability dropout
+    (csrc/common.cuh drop_keep32_sliced).  group4 = index of the first of its 4 consecutive Philox counters
+    (((passage * H + head) * L + query) * 32 + chunk * 4).  The 16 output words are bit planes of 32 independent 16-bit
+    uniforms, compared with the threshold from the least significant plane up."""
+    group4 = np.asarray(group4, dtype=np.uint64)
+    ge = np.full(group4.shape, 0xFFFFFFFF, dtype=np.uint32)
+    if p <= 0:
+        return ge
+    t = thresh_of(p)
+    for u in range(4):
+        g = group4 + np.uint64(u)
+        r = philox4x32((g & MASK32).astype(np.uint32), (g >> np.uint64(32)).astype(np.uint32),
+                          np.full(g.shape, site, dtype=np.uint32), np.full(g.shape, step, dtype=np.uint32),
+                          seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)
+        for j in range(4):
+            ge = (r[j] & ge) if (t >> (u * 4 + j)) & 1 else (r[j] | ge)
+    return ge
+
+
+def attn_keep_mask(seed, step, site, P, H, L, p):
+    """bool numpy array [P, H, L, 256]: keep decision of every (passage, head, query, key), keys beyond L included
+    (key j of chunk c is bit (j >> 1) + 16 (j & 1) of that chunk's word)."""
+    rows = np.arange(P * H * L, dtype=np.uint64).reshape(P, H, L, 1)
+    chunks = np.arange(8, dtype=np.uint64).reshape(1, 1, 1, 8)
+    words = attn_keep_words(seed, step, site, rows * np.uint64(32) + chunks * np.uint64(4), p)  # [P, H, L, 8]
+    j = np.arange(32)
+    bit = (j >> 1) + 16 * (j & 1)
+    return ((words[..., None] >> bit.astype(np.uint32)) & np.uint32(1)).astype(bool).reshape(P, H, L, 256)

@@ -78,6 +78,71 @@ def test_enc_attn_fwd_bwd(P, L, H, impl):
     assert terr < 0.02 * tab.grad.abs().max().item() + 1e-2, (terr, tab.grad.abs().max().item())
 
 
+@pytest.mark.parametrize("impl", [2, 1])
+@pytest.mark.parametrize("P,L,H,with_mask", [(3, 250, 2, False), (2, 100, 3, True), (2, 256, 1, False)])
+def test_enc_attn_dropout_matches_host_mask(P, L, H, with_mask, impl):
+    """Dropout on the attention probabilities (HF:332): the keep words the forward saves equal the host restatement
+    (lako_b200/philox.py attn_keep_mask) bit for bit, the output equals softmax * mask / (1 - p) @ v in torch, and the
+    backward -- reading the saved words, and regenerating them -- gives that graph's gradients."""
+    import ctypes as C
+    import numpy as np
+    nat = _nat()
+    lib = nat.lib()
+    lib.lako_set_attn_impl(impl)
+    from lako_b200.model import bucket_table
+    from lako_b200.philox import attn_keep_mask, scale_of
+    torch.manual_seed(7 * L + H)
+    inner = H * 64
+    seed, step, site, pdrop = 0x1234567890ABCDEF, 5, 77, 0.1
+    qkv = (torch.randn(P * L, 3 * inner, device="cuda") * 0.6).to(torch.bfloat16)
+    lens = torch.randint(int(0.6 * L), L + 1, (P,), device="cuda")
+    lens[0] = L
+    mask = (torch.arange(L, device="cuda")[None] < lens[:, None]) if with_mask else None
+    table = torch.randn(32, H, device="cuda")
+    buckets = bucket_table(True, 32, 128).cuda()
+    lut = _bias_lut(nat, table, buckets, H, L)
+    out = torch.zeros(P * L, inner, device="cuda", dtype=torch.bfloat16)
+    lse = torch.zeros(P, H, L, device="cuda")
+    keep = torch.zeros(P, H, L, 8, device="cuda", dtype=torch.int32)
+    args = (C.c_ulonglong(seed), C.c_uint(step), C.c_uint(site), C.c_float(pdrop), nat.stream_ptr())
+    nat.check(lib.lako_enc_attn_fwd_dropout(nat.ptr(qkv), nat.ptr(mask), nat.ptr(lut), nat.ptr(out), nat.ptr(lse),
+                                            nat.ptr(keep), P, L, H, *args))
+    torch.cuda.synchronize()
+    lib.lako_set_attn_impl(2)
+    km = attn_keep_mask(seed, step, site, P, H, L, pdrop)                       # [P, H, L, 256] bool
+    got = keep.cpu().numpy().view(np.uint32)
+    j = np.arange(32)
+    bit = ((j >> 1) + 16 * (j & 1)).astype(np.uint32)
+    got_mask = ((got[..., None] >> bit) & 1).astype(bool).reshape(P, H, L, 256)
+    nch = (L + 31) // 32                                                        # chunks the kernels touch
+    assert (got_mask[..., :nch * 32] == km[..., :nch * 32]).all()
+    assert abs(km[..., :L].mean() - (1 - pdrop)) < 5e-3
+    keep_t = torch.from_numpy(km[..., :L]).cuda()
+    x = qkv.float().view(P, L, 3, H, 64).requires_grad_(True)
+    q, k, v = x[:, :, 0].transpose(1, 2), x[:, :, 1].transpose(1, 2), x[:, :, 2].transpose(1, 2)
+    tab = table.clone().requires_grad_(True)
+    rel = torch.arange(L, device="cuda")[None, :] - torch.arange(L, device="cuda")[:, None]
+    bias = tab[buckets[rel + 511].long()].permute(2, 0, 1)[None]
+    s = q @ k.transpose(-1, -2) + bias
+    if with_mask:
+        s = s + torch.zeros(P, 1, 1, L, device="cuda").masked_fill(~mask[:, None, None, :], NEG)
+    pr = torch.softmax(s, dim=-1) * keep_t * scale_of(pdrop)
+    ref = (pr @ v).transpose(1, 2).reshape(P * L, inner)
+    assert torch.allclose(out.float(), ref, atol=3e-2, rtol=3e-2), (out.float() - ref).abs().max().item()
+    dout = (torch.randn(P * L, inner, device="cuda") * 0.5).to(torch.bfloat16)
+    ref.backward(dout.float())
+    gref = x.grad.reshape(P * L, 3 * inner)
+    for saved in (keep, None):
+        dqkv = torch.zeros_like(qkv)
+        dlut = torch.zeros(H, 2 * L - 1, device="cuda")
+        nat.check(lib.lako_enc_attn_bwd_dropout(nat.ptr(qkv), nat.ptr(out), nat.ptr(dout), nat.ptr(lse), nat.ptr(mask),
+                                                nat.ptr(lut), nat.ptr(dqkv), nat.ptr(dlut), nat.ptr(saved), P, L, H, *args))
+        torch.cuda.synchronize()
+        scale = gref.abs().max().item()
+        err = (dqkv.float() - gref).abs().max().item()
+        assert err < 0.03 * scale + 1e-3, (err, scale, saved is None)
+
+
 @pytest.mark.parametrize("B,T,M,H,nl", [(2, 6, 96, 2, 2), (3, 10, 500, 3, 1), (1, 1, 333, 2, 2), (2, 20, 2000, 12, 1), (2, 40, 300, 2, 1), (1, 64, 129, 1, 1)])
 def test_xattn_fwd_bwd(B, T, M, H, nl):
     nat = _nat()
