@@ -76,6 +76,20 @@ __device__ __forceinline__ void ffma2(uint32_t& a0, uint32_t& a1, float s, float
       : "+r"(a0), "+r"(a1)
       : "f"(s), "f"(b0), "f"(b1));
 }
+// (d0, d1) = (a0, a1) * (b0, b1) + (c0, c1)
+__device__ __forceinline__ void ffma2v(float& d0, float& d1, float a0, float a1, float b0, float b1, float c0, float c1) {
+  asm("{\n\t.reg .b64 ra, rb, rc;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmov.b64 rc, {%6, %7};\n\t"
+      "fma.rn.f32x2 ra, ra, rb, rc;\n\tmov.b64 {%0, %1}, ra;\n\t}"
+      : "=f"(d0), "=f"(d1)
+      : "f"(a0), "f"(a1), "f"(b0), "f"(b1), "f"(c0), "f"(c1));
+}
+// (d0, d1) = (a0, a1) * (b0, b1)
+__device__ __forceinline__ void fmul2v(float& d0, float& d1, float a0, float a1, float b0, float b1) {
+  asm("{\n\t.reg .b64 ra, rb;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmul.rn.f32x2 ra, ra, rb;\n\t"
+      "mov.b64 {%0, %1}, ra;\n\t}"
+      : "=f"(d0), "=f"(d1)
+      : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
+}
 // (a0, a1) += (b0, b1)
 __device__ __forceinline__ void fadd2(uint32_t& a0, uint32_t& a1, float b0, float b1) {
   asm("{\n\t.reg .b64 ra, rb;\n\tmov.b64 ra, {%0, %1};\n\tmov.b64 rb, {%2, %3};\n\tadd.rn.f32x2 ra, ra, rb;\n\t"
@@ -786,10 +800,13 @@ struct EncAttnBwdParams {
   const uint32_t* keepbits;      // keep masks saved by the forward (null: regenerate them with Philox)
 };
 
+// bias-gradient bins in shared memory: bin EB_DLUT_PAD + (k - q + L - 1); the padding takes the (all-zero) sums of the
+// diagonals of a 32x32 sub-block that fall outside the table, so no sum needs a range check
+constexpr int EB_DLUT_PAD = 32, EB_DLUT_BINS = 576;
 constexpr int EB_Q_OFF = 0, EB_DO_OFF = 32768, EB_K_OFF = 65536, EB_V_OFF = 98304, EB_P_OFF = 131072,
-              EB_DS_OFF = 163840, EB_LUT_OFF = 196608, EB_DLUT_OFF = EB_LUT_OFF + 4 * LUTCOPY * 4,
-              EB_KMASK_OFF = EB_DLUT_OFF + 2048, EB_LSE_OFF = EB_KMASK_OFF + 1024, EB_D_OFF = EB_LSE_OFF + 1024,
-              EB_BAR_OFF = EB_D_OFF + 1024;
+              EB_DS_OFF = 163840, EB_LUT_OFF = 196608, EB_DLUT_OFF = EB_LUT_OFF + 4 * LUTWIN * 4,
+              EB_KMASK_OFF = EB_DLUT_OFF + EB_DLUT_BINS * 4, EB_LSE_OFF = EB_KMASK_OFF + 1024, EB_D_OFF = EB_LSE_OFF + 1024,
+              EB_SCR_OFF = EB_D_OFF + 1024, EB_BAR_OFF = EB_SCR_OFF + 16 * 128;
 constexpr int EB_SMEM_BYTES = EB_BAR_OFF + 64 + 1024;
 constexpr int TM_S = 0, TM_DP = 128, TM_DQ = 256, TM_DK = 384, TM_DV = 448;
 
@@ -807,9 +824,10 @@ __device__ long long g_eb_trace[64];
 #else
 #define EB_TRACE(i) do { } while (0)
 #endif
+template <bool kDrop>
 __global__ void __launch_bounds__(EB_THREADS, 1)
 enc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_do,
-                    const EncAttnBwdParams p) {
+                    const EncAttnBwdParams p, const int P) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   float* s_lut4 = reinterpret_cast<float*>(smem + EB_LUT_OFF);
@@ -828,20 +846,17 @@ enc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
   const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
   const int quarter = warp & 3, cq = warp >> 2;
   const bool issuer = tid == EB_SOFTMAX_THREADS;  // lane 0 of the 17th warp
-  const int h = blockIdx.x, psg = blockIdx.y;
+  // Persistent: CTA c serves head c % H and walks that head's passages (c / H, + CTAs per head, ...): barriers, tensor
+  // memory, the bias windows and the bias-gradient accumulator are set up once per CTA, and the next passage's operand
+  // tiles stream in (TMA) underneath the current passage's dQ read-out and the next one's lse / D staging.  (One CTA per
+  // (head, passage) spent ~35 % of its life in that un-overlapped prologue and epilogue.)
+  const int H = p.H;
+  const int h = blockIdx.x % H;
+  const int pstep = gridDim.x / H, p_first = blockIdx.x / H;
   const int Lmax = p.L;  // LUT geometry / lse pitch
   const int nlut = 2 * Lmax - 1;
   EB_TRACE(0);
   pdl_launch_dependents();
-  int row0 = psg * Lmax, L = Lmax;  // L = this passage's token count
-  if (p.cu) {
-    pdl_wait();
-    row0 = p.cu[psg];
-    L = p.cu[psg + 1] - row0;
-    if (L <= 0) return;
-  }
-  const int nt = (L + 127) / 128;  // 128-row tiles of queries == of keys
-
   if (issuer) {
     tma_prefetch_desc(&tm_qkv);
     tma_prefetch_desc(&tm_do);
@@ -855,72 +870,23 @@ enc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
   if (warp == 0) tmem_alloc(tmem_slot, 512);
   pdl_wait();
   EB_TRACE(1);
-  if (issuer) {  // operand tiles: start the TMA traffic before the SIMT staging below
-    mbar_arrive_expect_tx(bar_load, 16384 * 4 * nt);
-    for (int t = 0; t < nt; ++t) {
-      tma_load_2d(smem + EB_Q_OFF + t * 16384, &tm_qkv, bar_load, h * 64, row0 + t * 128);
-      tma_load_2d(smem + EB_K_OFF + t * 16384, &tm_qkv, bar_load, p.inner + h * 64, row0 + t * 128);
-      tma_load_2d(smem + EB_V_OFF + t * 16384, &tm_qkv, bar_load, 2 * p.inner + h * 64, row0 + t * 128);
-      tma_load_2d(smem + EB_DO_OFF + t * 16384, &tm_do, bar_load, h * 64, row0 + t * 128);
-    }
-  }
-  if (tid < EB_SOFTMAX_THREADS) {
-    // Staging of the bias LUT (4 shifted copies, see stage_lut4), the additive key mask, lse and D[q] = sum_d dO*O.
-    // Every global load is issued before the first dependent instruction, so the prologue exposes ONE memory
-    // latency, not one per table.
-    const float* lut = p.bias_lut + h * nlut;
-    constexpr int NLV = (4 * LUTCOPY + EB_SOFTMAX_THREADS - 1) / EB_SOFTMAX_THREADS;
-    float lv[NLV];
-#pragma unroll
-    for (int j = 0; j < NLV; ++j) {
-      const int i = tid + j * EB_SOFTMAX_THREADS;
-      const int c = i / LUTCOPY, src = i - c * LUTCOPY + c;
-      lv[j] = (i < 4 * LUTCOPY && src < nlut) ? __ldg(lut + src) : 0.f;
-    }
-    unsigned char mk = 1;
-    if (tid < L && p.mask) mk = __ldg(p.mask + static_cast<size_t>(psg) * Lmax + tid);
-    // two threads per query row (256 rows max): each sums 32 of the 64 head dims
-    const int q = tid >> 1, part = tid & 1;
-    uint4 ov[4], dv[4];
-    float lse_q = INFINITY;  // rows beyond the passage -> P = exp(s - inf) = 0
-    if (q < L) {
-      const uint4* o4 = reinterpret_cast<const uint4*>(p.out + static_cast<size_t>(row0 + q) * p.inner + h * 64) + part * 4;
-      const uint4* d4 = reinterpret_cast<const uint4*>(p.dout + static_cast<size_t>(row0 + q) * p.inner + h * 64) + part * 4;
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        ov[u] = __ldg(o4 + u);
-        dv[u] = __ldg(d4 + u);
-      }
-      if (part == 0) lse_q = __ldg(p.lse + (static_cast<size_t>(psg) * p.H + h) * Lmax + q);
-    }
-#pragma unroll
-    for (int j = 0; j < NLV; ++j) {
-      const int i = tid + j * EB_SOFTMAX_THREADS;
-      if (i < 4 * LUTCOPY) s_lut4[i] = lv[j];
-    }
-    if (tid < 256) s_kmask[tid] = (tid < L) ? (mk ? 0.f : MASK_MIN) : -INFINITY;
-    s_dlut[tid] = 0.f;
-    float dsum = 0.f;
-    if (q < L) {
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const uint4 a = ov[u], b = dv[u];
-        dsum += bf16_lo(a.x) * bf16_lo(b.x) + bf16_hi(a.x) * bf16_hi(b.x) + bf16_lo(a.y) * bf16_lo(b.y) +
-                bf16_hi(a.y) * bf16_hi(b.y) + bf16_lo(a.z) * bf16_lo(b.z) + bf16_hi(a.z) * bf16_hi(b.z) +
-                bf16_lo(a.w) * bf16_lo(b.w) + bf16_hi(a.w) * bf16_hi(b.w);
-      }
-    }
-    dsum += __shfl_xor_sync(0xffffffffu, dsum, 1);
-    if (part == 0) {
-      s_D[q] = dsum;
-      s_lse[q] = lse_q;
-    }
-  }
+  stage_lut_win(s_lut4, p.bias_lut + h * nlut, nlut, tid, EB_THREADS, LOG2E_F);  // log2 domain
+  for (int i = tid; i < EB_DLUT_BINS; i += EB_THREADS) s_dlut[i] = 0.f;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   EB_TRACE(2);
   const uint32_t tmem = *tmem_slot;
+  auto psg_geom = [&](int psg, int& row0, int& L) {  // recomputed identically by every role
+    row0 = psg * Lmax;
+    L = Lmax;
+    if (p.cu) {
+      row0 = p.cu[psg];
+      L = p.cu[psg + 1] - row0;
+    }
+    row0 = __shfl_sync(0xffffffffu, row0, 0);  // provably warp-uniform
+    L = __shfl_sync(0xffffffffu, L, 0);
+  };
 
   const uint32_t qa = smem_u32(smem + EB_Q_OFF), doa = smem_u32(smem + EB_DO_OFF), ka = smem_u32(smem + EB_K_OFF),
                  va = smem_u32(smem + EB_V_OFF), pa = smem_u32(smem + EB_P_OFF), dsa = smem_u32(smem + EB_DS_OFF);
@@ -948,46 +914,69 @@ enc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
     // registers), one elected lane issues.  With the loop inside an `if (one thread)` region every MMA is wrapped in a
     // divergence "waterfall" (ELECT / R2UR.BROADCAST / BRA.U.ANY, ~130 cycles per MMA): 32 MMAs per block then cost more
     // issue time than the block's softmax arithmetic.
-    const bool el = elect_one();  // (MMA only: a TMA producer written this way lost its loads' byte counts)
-    mbar_wait_warp(bar_load, 0);
-    tc_fence_after();
-    if (el) {
-      issue_s_dp(0, 0);
-      umma_commit(bar_mma);
-    }
-    uint32_t r_phase = 0;
-    for (int kt = 0; kt < nt; ++kt) {
-      for (int qt = 0; qt < nt; ++qt) {
-        // The softmax threads release the S / dP columns as soon as their values are in registers (about half way
-        // through the block's arithmetic): the next block's S / dP are computed underneath the rest of it.
-        mbar_wait_warp(bar_sfree, r_phase);
-        tc_fence_after();
-        int nq = qt + 1, nk = kt;
-        if (nq == nt) {
-          nq = 0;
-          nk = kt + 1;
+    const bool el = elect_one();  // (MMA / TMA issue only inside real branches on it; see DESIGN.md on elected producers)
+    uint32_t r_phase = 0, l_phase = 0;
+    uint32_t n_commits = 0;  // gradient commits (= bar_grad phases) issued so far
+    for (int psg = p_first; psg < P; psg += pstep) {
+      int row0, L;
+      psg_geom(psg, row0, L);
+      if (L <= 0) continue;
+      const int nt = (L + 127) / 128;
+      // the previous passage's gradient MMAs have finished reading Q / K / V / dO / P / dS: its tiles may be replaced
+      // (only the LAST commit can still be pending: every earlier phase completed before the softmax threads released
+      // the block after it; an mbarrier parity wait can only tell the current phase from the one before)
+      if (n_commits > 0) mbar_wait_warp(bar_grad, (n_commits - 1) & 1);
+      if (lane == 0) {
+        mbar_arrive_expect_tx(bar_load, 16384 * 4 * nt);
+        for (int t = 0; t < nt; ++t) {
+          tma_load_2d(smem + EB_Q_OFF + t * 16384, &tm_qkv, bar_load, h * 64, row0 + t * 128);
+          tma_load_2d(smem + EB_K_OFF + t * 16384, &tm_qkv, bar_load, p.inner + h * 64, row0 + t * 128);
+          tma_load_2d(smem + EB_V_OFF + t * 16384, &tm_qkv, bar_load, 2 * p.inner + h * 64, row0 + t * 128);
+          tma_load_2d(smem + EB_DO_OFF + t * 16384, &tm_do, bar_load, h * 64, row0 + t * 128);
         }
-        if (nk < nt && el) {
-          issue_s_dp(nq, nk);
-          umma_commit(bar_mma);
-        }
-        mbar_wait_warp(bar_ready, r_phase);  // P / dS of this block are in shared memory
-        r_phase ^= 1;
-        tc_fence_after();
-        if (el) {
-          // dV[kt] += P^T dO[qt] ; dK[kt] += dS^T Q[qt]   (M = 128 keys, N = 64, K = 128 queries)
+      }
+      __syncwarp();
+      mbar_wait_warp(bar_load, l_phase);
+      l_phase ^= 1;
+      tc_fence_after();
+      if (el) {
+        issue_s_dp(0, 0);
+        umma_commit(bar_mma);
+      }
+      for (int kt = 0; kt < nt; ++kt) {
+        for (int qt = 0; qt < nt; ++qt) {
+          // The softmax threads release the S / dP columns as soon as their values are in registers (about half way
+          // through the block's arithmetic): the next block's S / dP are computed underneath the rest of it.
+          mbar_wait_warp(bar_sfree, r_phase);
+          tc_fence_after();
+          int nq = qt + 1, nk = kt;
+          if (nq == nt) {
+            nq = 0;
+            nk = kt + 1;
+          }
+          if (nk < nt && el) {
+            issue_s_dp(nq, nk);
+            umma_commit(bar_mma);
+          }
+          mbar_wait_warp(bar_ready, r_phase);  // P / dS of this block are in shared memory
+          r_phase ^= 1;
+          tc_fence_after();
+          if (el) {
+            // dV[kt] += P^T dO[qt] ; dK[kt] += dS^T Q[qt]   (M = 128 keys, N = 64, K = 128 queries)
 #pragma unroll
-          for (int j = 0; j < 8; ++j)
-            umma_bf16(tmem + TM_DV, p_t + j * 128, do_mn + qt * 1024 + j * 128, idesc_tn, (qt > 0 || j > 0));
+            for (int j = 0; j < 8; ++j)
+              umma_bf16(tmem + TM_DV, p_t + j * 128, do_mn + qt * 1024 + j * 128, idesc_tn, (qt > 0 || j > 0));
 #pragma unroll
-          for (int j = 0; j < 8; ++j)
-            umma_bf16(tmem + TM_DK, ds_t + j * 128, q_mn + qt * 1024 + j * 128, idesc_tn, (qt > 0 || j > 0));
-          // dQ[qt] += dS K[kt]   (M = 128 queries, N = 64, K = 128 keys)
+            for (int j = 0; j < 8; ++j)
+              umma_bf16(tmem + TM_DK, ds_t + j * 128, q_mn + qt * 1024 + j * 128, idesc_tn, (qt > 0 || j > 0));
+            // dQ[qt] += dS K[kt]   (M = 128 queries, N = 64, K = 128 keys)
 #pragma unroll
-          for (int j = 0; j < 8; ++j)
-            umma_bf16(tmem + TM_DQ + qt * 64, ds_k + (j >> 2) * 1024 + (j & 3) * 2, k_mn + kt * 1024 + j * 128, idesc_dq,
-                      (kt > 0 || j > 0));
-          umma_commit(bar_grad);
+            for (int j = 0; j < 8; ++j)
+              umma_bf16(tmem + TM_DQ + qt * 64, ds_k + (j >> 2) * 1024 + (j & 3) * 2, k_mn + kt * 1024 + j * 128, idesc_dq,
+                        (kt > 0 || j > 0));
+            umma_commit(bar_grad);
+          }
+          ++n_commits;
         }
       }
     }
@@ -1003,17 +992,60 @@ enc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
   uint32_t s_phase = 0, g_phase = 0;
   bool g_pending = false;
 
+  for (int psg = p_first; psg < P; psg += pstep) {
+  int row0, L;
+  psg_geom(psg, row0, L);
+  if (L <= 0) continue;
+  const int nt = (L + 127) / 128;  // 128-row tiles of queries == of keys
+  {
+    // Per-passage staging: additive key mask, lse and D[q] = sum_d dO * O (two threads per query row, 32 head dims
+    // each).  No thread gets here before every thread has read the previous passage's values for the last time (the last
+    // block's gradient MMAs, which everybody waits for, are only issued once all have arrived on bar_ready).
+    unsigned char mk = 1;
+    if (tid < L && p.mask) mk = __ldg(p.mask + static_cast<size_t>(psg) * Lmax + tid);
+    const int q = tid >> 1, part = tid & 1;
+    uint4 ov[4], dv[4];
+    float lse_q = INFINITY;  // rows beyond the passage -> P = exp(s - inf) = 0
+    if (q < L) {
+      const uint4* o4 = reinterpret_cast<const uint4*>(p.out + static_cast<size_t>(row0 + q) * p.inner + h * 64) + part * 4;
+      const uint4* d4 = reinterpret_cast<const uint4*>(p.dout + static_cast<size_t>(row0 + q) * p.inner + h * 64) + part * 4;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        ov[u] = __ldg(o4 + u);
+        dv[u] = __ldg(d4 + u);
+      }
+      if (part == 0) lse_q = __ldg(p.lse + (static_cast<size_t>(psg) * H + h) * Lmax + q);
+    }
+    if (tid < 256) s_kmask[tid] = (tid < L) ? (mk ? 0.f : MASK_MIN) : -INFINITY;
+    float dsum = 0.f;
+    if (q < L) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const uint4 a = ov[u], b = dv[u];
+        dsum += bf16_lo(a.x) * bf16_lo(b.x) + bf16_hi(a.x) * bf16_hi(b.x) + bf16_lo(a.y) * bf16_lo(b.y) +
+                bf16_hi(a.y) * bf16_hi(b.y) + bf16_lo(a.z) * bf16_lo(b.z) + bf16_hi(a.z) * bf16_hi(b.z) +
+                bf16_lo(a.w) * bf16_lo(b.w) + bf16_hi(a.w) * bf16_hi(b.w);
+      }
+    }
+    dsum += __shfl_xor_sync(0xffffffffu, dsum, 1);
+    if (part == 0) {
+      s_D[q] = dsum;
+      s_lse[q] = lse_q;
+    }
+    named_bar_sync(1, EB_SOFTMAX_THREADS);
+  }
+
   for (int kt = 0; kt < nt; ++kt) {
     for (int qt = 0; qt < nt; ++qt) {
       const int q = qt * 128 + r;
       const int qc = min(q, L - 1);
       const int b = Lmax - 1 - qc;
-      const uint32_t lut_a = smem_u32(s_lut4) + ((b & 3) * LUTCOPY + (b & ~3)) * 4;  // explicit shared addresses
+      const uint32_t lut_a = smem_u32(s_lut4) + b * 16;  // this row's bias windows (stage_lut_win)
       const bool rows_live = (qt * 128 + quarter * 32) < L;  // warp-uniform: any of this warp's queries in the passage
       const int kbase = kt * 128 + cq * 32;                  // first key of this warp's 32-column chunk
       // the forward's keep mask of this row's 32 keys (fetched ahead of the MMA wait)
       uint32_t kword = 0xffffffffu;  // drop_keep32_sliced order
-      if (p.drop.thresh && q < L && kbase < L)
+      if (kDrop && q < L && kbase < L)
         kword = p.keepbits ? __ldg(p.keepbits + ((static_cast<size_t>(psg) * p.H + h) * Lmax + q) * 8 + (kbase >> 5))
                            : drop_keep32_sliced(p.drop, (static_cast<unsigned long long>(psg * p.H + h) * Lmax + qc) * 32 +
                                                             (kbase >> 3));
@@ -1033,10 +1065,16 @@ enc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
       // exact in fp32: with ascending columns and the partial sum moving one lane UP per column, lane 0 starts a
       // fresh diagonal each step (keep = 0 there), lane 31 holds the COMPLETE diagonal d = i - 31 (<= 0) after
       // column i (parked in lane i's Rdone), and after the last column lane l holds the complete d = 31 - l (>= 0).
-      float Rup = 0.f, Rdone = 0.f;
+      float Rup = 0.f;
       // 64-key chunk (cq >> 1) of the K-major P / dS tiles; this warp's 32 keys are 16-byte units (cq & 1)*4..+4
       const uint32_t prow = smem_u32(smem) + EB_P_OFF + (cq >> 1) * 16384 + r * 128;
       const uint32_t dsrow = smem_u32(smem) + EB_DS_OFF + (cq >> 1) * 16384 + r * 128;
+      // bins of this sub-block's diagonals: column i completes d = i - 31 in lane 31 (parked in the warp's scratch row for
+      // lane i); after the last column lane l holds d = 31 - l
+      const uint32_t dl_a = smem_u32(s_dlut) + (EB_DLUT_PAD + idx0 - 31) * 4;
+      const uint32_t scr_a = smem_u32(smem) + EB_SCR_OFF + warp * 128;  // this warp's 32 parked diagonal sums
+      const float nD = -D_q;
+      const float dscale = kDrop ? p.drop.scale : 1.f;
 #pragma unroll
       for (int hh = 0; hh < 2; ++hh) {  // two 16-column halves keep the live register set small
         uint32_t ppk[8], dpk[8];        // bf16x2-packed P_drop and dS of 16 columns
@@ -1054,39 +1092,56 @@ enc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
             mbar_arrive(bar_sfree);
           }
 #pragma unroll
-          for (int uu = 0; uu < 2; ++uu) {
-            const int u = hh * 2 + uu;
-            const float4 lb0 = lds_f4(lut_a + (kbase + u * 8) * 4);
-            const float4 lb1 = lds_f4(lut_a + (kbase + u * 8 + 4) * 4);
-            const float lbv[8] = {lb0.x, lb0.y, lb0.z, lb0.w, lb1.x, lb1.y, lb1.z, lb1.w};
-            float sc[8], pr[8], ds[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) sc[i] = __uint_as_float(sv[uu * 8 + i]) + lbv[i];
+          for (int g = 0; g < 4; ++g) {  // 4 keys at a time (one bias window); packed fp32 pair arithmetic
+            const int col = hh * 16 + g * 4;  // first of the 4 keys within this warp's 32-key chunk
+            float s0 = __uint_as_float(sv[g * 4 + 0]), s1 = __uint_as_float(sv[g * 4 + 1]);
+            float s2 = __uint_as_float(sv[g * 4 + 2]), s3 = __uint_as_float(sv[g * 4 + 3]);
             if (need_km) {  // warp-uniform: a key mask was given, or the chunk straddles the end of the passage
-              const float4 km0 = lds_f4(smem_u32(s_kmask) + (kbase + u * 8) * 4);
-              const float4 km1 = lds_f4(smem_u32(s_kmask) + (kbase + u * 8 + 4) * 4);
-              const float kmv[8] = {km0.x, km0.y, km0.z, km0.w, km1.x, km1.y, km1.z, km1.w};
-#pragma unroll
-              for (int i = 0; i < 8; ++i) sc[i] += kmv[i];
+              const float4 km = lds_f4(smem_u32(s_kmask) + (kbase + col) * 4);
+              fadd2(s0, s1, km.x, km.y);
+              fadd2(s2, s3, km.z, km.w);
             }
-            const float dscale = p.drop.thresh ? p.drop.scale : 1.f;
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const float pv = fast_exp2(fmaf(sc[i], LOG2E_F, nlse_q));          // P = exp(s - lse)
-              const float mi = ((kword >> sliced_bit(u * 8 + i)) & 1u) ? dscale : 0.f;  // dropout keep * 1/(1-p)
-              ds[i] = pv * fmaf(__uint_as_float(dpv[uu * 8 + i]), mi, -D_q);      // dS = P (dP_drop - D)
-              pr[i] = pv * mi;                                                     // the dV = P_drop^T dO operand
+            const float4 lb = lds_f4(lut_a + (kbase + col) * 16);  // biases * log2(e)
+            ffma2v(s0, s1, s0, s1, LOG2E_F, LOG2E_F, lb.x, lb.y);
+            ffma2v(s2, s3, s2, s3, LOG2E_F, LOG2E_F, lb.z, lb.w);
+            fadd2(s0, s1, nlse_q, nlse_q);
+            fadd2(s2, s3, nlse_q, nlse_q);
+            const float p0 = fast_exp2(s0), p1 = fast_exp2(s1), p2 = fast_exp2(s2), p3 = fast_exp2(s3);  // P = exp(s - lse)
+            float d0 = __uint_as_float(dpv[g * 4 + 0]), d1 = __uint_as_float(dpv[g * 4 + 1]);
+            float d2 = __uint_as_float(dpv[g * 4 + 2]), d3 = __uint_as_float(dpv[g * 4 + 3]);
+            if (kDrop) {  // dP_drop: dropped keys pass no gradient
+              d0 = ((kword >> sliced_bit(col + 0)) & 1u) ? d0 : 0.f;
+              d1 = ((kword >> sliced_bit(col + 1)) & 1u) ? d1 : 0.f;
+              d2 = ((kword >> sliced_bit(col + 2)) & 1u) ? d2 : 0.f;
+              d3 = ((kword >> sliced_bit(col + 3)) & 1u) ? d3 : 0.f;
             }
+            // dS = P (dP_drop / (1 - p) - D)
+            ffma2v(d0, d1, d0, d1, dscale, dscale, nD, nD);
+            ffma2v(d2, d3, d2, d3, dscale, dscale, nD, nD);
+            float ds[4];
+            fmul2v(ds[0], ds[1], p0, p1, d0, d1);
+            fmul2v(ds[2], ds[3], p2, p3, d2, d3);
+            // the dV = P_drop^T dO operand: P / (1 - p) with the dropped keys zeroed (pair masks on the packed words)
+            uint32_t w0, w1;
+            if (kDrop) {
+              float q0, q1, q2, q3;
+              fmul2v(q0, q1, p0, p1, dscale, dscale);
+              fmul2v(q2, q3, p2, p3, dscale, dscale);
+              w0 = pack_bf16x2(q0, q1) & sliced_pair_mask(kword, (col >> 1) + 0);
+              w1 = pack_bf16x2(q2, q3) & sliced_pair_mask(kword, (col >> 1) + 1);
+            } else {
+              w0 = pack_bf16x2(p0, p1);
+              w1 = pack_bf16x2(p2, p3);
+            }
+            ppk[g * 2 + 0] = w0;
+            ppk[g * 2 + 1] = w1;
+            dpk[g * 2 + 0] = pack_bf16x2(ds[0], ds[1]);
+            dpk[g * 2 + 1] = pack_bf16x2(ds[2], ds[3]);
+            // bias gradient: systolic diagonal sums, lane 31 retires one complete diagonal per column
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-              ppk[uu * 4 + i] = pack_bf16x2(pr[2 * i], pr[2 * i + 1]);
-              dpk[uu * 4 + i] = pack_bf16x2(ds[2 * i], ds[2 * i + 1]);
-            }
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
               Rup = fmaf(__shfl_up_sync(0xffffffffu, Rup, 1), keep, ds[i]);
-              const float done = __shfl_sync(0xffffffffu, Rup, 31);
-              Rdone = (lane == u * 8 + i) ? done : Rdone;
+              if (lane == 31) sts_f(scr_a + (col + i) * 4, Rup);  // parked for lane (col + i)
             }
           }
         }
@@ -1105,10 +1160,12 @@ enc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
         }
       }
       if (live) {
-        const int iu = idx0 + 31 - lane;
-        if (iu >= 0 && iu < nlut) red_shared_add_f(smem_u32(s_dlut) + iu * 4, Rup);
-        const int id = idx0 + lane - 31;
-        if (lane != 31 && id >= 0 && id < nlut) red_shared_add_f(smem_u32(s_dlut) + id * 4, Rdone);  // d = 0 is in Rup (lane 31)
+        // lane l: the parked diagonal d = l - 31 and its own d = 31 - l (d = 0 once: lane 31's Rup)
+        __syncwarp();
+        const float Rdone = lds_f(scr_a + lane * 4);
+        red_shared_add_f(dl_a + (62 - lane) * 4, Rup);
+        if (lane != 31) red_shared_add_f(dl_a + lane * 4, Rdone);
+        __syncwarp();  // the scratch row is rewritten in the next block
       }
       EB_TRACE(8 + (kt * 2 + qt) * 6 + 2);
       fence_proxy_async_smem();
@@ -1177,12 +1234,13 @@ enc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
       }
     }
   }
+  }  // passages
   }  // softmax warps
   __syncthreads();
   EB_TRACE(5);
   if (p.dlut) {
     for (int i = tid; i < nlut; i += EB_THREADS) {
-      const float v = s_dlut[i];
+      const float v = s_dlut[EB_DLUT_PAD + i];
       if (v != 0.f) atomicAdd(&p.dlut[h * nlut + i], v);
     }
   }
@@ -1219,12 +1277,16 @@ int enc_attn_bwd(const __nv_bfloat16* qkv, const __nv_bfloat16* out, const __nv_
   if (rc) return rc;
   rc = get_tensor_map_2d(&tm_do, dout, inner, total_rows, inner, 64, 128);
   if (rc) return rc;
+  using BwdKern = void (*)(CUtensorMap, CUtensorMap, EncAttnBwdParams, int);
+  static const BwdKern bwd_kerns[2] = {enc_attn_bwd_kernel<false>, enc_attn_bwd_kernel<true>};
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(enc_attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, EB_SMEM_BYTES);
-    if (e != cudaSuccess) {
-      set_last_error(cudaGetErrorString(e), __FILE__, __LINE__);
-      return LAKO_ERR_LAUNCH;
+    for (BwdKern kf : bwd_kerns) {
+      cudaError_t e = cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, EB_SMEM_BYTES);
+      if (e != cudaSuccess) {
+        set_last_error(cudaGetErrorString(e), __FILE__, __LINE__);
+        return LAKO_ERR_LAUNCH;
+      }
     }
     configured = true;
   }
@@ -1243,8 +1305,13 @@ int enc_attn_bwd(const __nv_bfloat16* qkv, const __nv_bfloat16* out, const __nv_
   p.drop = drop;
   p.keepbits = keepbits;
   ProfScope prof(PROF_ENC_ATTN_BWD, 10.0 * P * H * static_cast<double>(L) * L * 64, s);
-  dim3 grid(H, P);
-  launch_pdl(enc_attn_bwd_kernel, grid, dim3(EB_THREADS), EB_SMEM_BYTES, s, tm_qkv, tm_do, p);
+  if (H > device_sm_count()) {
+    set_last_error("enc_attn_bwd: more heads than SMs", __FILE__, __LINE__);
+    return LAKO_ERR_UNSUPPORTED;
+  }
+  // every CTA serves one head: (SMs / H) CTAs per head (at most one per passage)
+  const int per_head = std::max(1, std::min(P, device_sm_count() / H));
+  launch_pdl(bwd_kerns[drop.thresh ? 1 : 0], dim3(per_head * H), dim3(EB_THREADS), EB_SMEM_BYTES, s, tm_qkv, tm_do, p, P);
   LAKO_CHECK_LAUNCH();
   return LAKO_OK;
 }
