@@ -936,6 +936,22 @@ enc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
         }
       }
       __syncwarp();
+      {
+        // The NEXT passage's tiles go to L2 now: all CTAs change passage at about the same time, and without this the
+        // ~190 KB each then asks for arrive as one HBM burst (~28 MB chip-wide) that the staging has to sit out.
+        int nrow0 = 0, nL = 0;
+        const int npsg = psg + pstep;
+        if (npsg < P) psg_geom(npsg, nrow0, nL);
+        if (lane == 0 && nL > 0) {
+          for (int t = 0; t < (nL + 127) / 128; ++t) {
+            tma_prefetch_2d(&tm_qkv, h * 64, nrow0 + t * 128);
+            tma_prefetch_2d(&tm_qkv, p.inner + h * 64, nrow0 + t * 128);
+            tma_prefetch_2d(&tm_qkv, 2 * p.inner + h * 64, nrow0 + t * 128);
+            tma_prefetch_2d(&tm_do, h * 64, nrow0 + t * 128);
+          }
+        }
+        __syncwarp();
+      }
       mbar_wait_warp(bar_load, l_phase);
       l_phase ^= 1;
       tc_fence_after();
@@ -997,6 +1013,7 @@ enc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
   psg_geom(psg, row0, L);
   if (L <= 0) continue;
   const int nt = (L + 127) / 128;  // 128-row tiles of queries == of keys
+  EB_TRACE(3);
   {
     // Per-passage staging: additive key mask, lse and D[q] = sum_d dO * O (two threads per query row, 32 head dims
     // each).  No thread gets here before every thread has read the previous passage's values for the last time (the last
@@ -1033,7 +1050,44 @@ enc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
       s_lse[q] = lse_q;
     }
     named_bar_sync(1, EB_SOFTMAX_THREADS);
+    {  // the next passage's O rows (one 128-byte line per query and head) and lse to L2
+      int nrow0 = 0, nL = 0;
+      const int npsg = psg + pstep;
+      if (npsg < P) psg_geom(npsg, nrow0, nL);
+      if (part == 0 && q < nL) prefetch_l2_line(p.out + static_cast<size_t>(nrow0 + q) * p.inner + h * 64);
+      if (tid < 8 && tid * 32 < nL) prefetch_l2_line(p.lse + (static_cast<size_t>(npsg) * H + h) * Lmax + tid * 32);
+    }
   }
+  EB_TRACE(7);
+
+  // dK / dV of key tile `kt_done` out of tensor memory (its last gradient MMAs have completed)
+  auto store_dk_dv = [&](int kt_done) {
+    tc_fence_after();
+    const int key = kt_done * 128 + r;
+    uint32_t a[16], bb[16];
+    tmem_ld_32x16(t_row + TM_DK + cq * 16, a);
+    tmem_ld_32x16(t_row + TM_DV + cq * 16, bb);
+    tmem_ld_wait();
+    if (key < L) {
+      __nv_bfloat16* dk = p.dqkv + static_cast<size_t>(row0 + key) * 3 * p.inner + p.inner + h * 64 + cq * 16;
+      __nv_bfloat16* dv = dk + p.inner;
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        uint4 o;
+        o.x = pack_bf16x2(__uint_as_float(a[u * 8 + 0]), __uint_as_float(a[u * 8 + 1]));
+        o.y = pack_bf16x2(__uint_as_float(a[u * 8 + 2]), __uint_as_float(a[u * 8 + 3]));
+        o.z = pack_bf16x2(__uint_as_float(a[u * 8 + 4]), __uint_as_float(a[u * 8 + 5]));
+        o.w = pack_bf16x2(__uint_as_float(a[u * 8 + 6]), __uint_as_float(a[u * 8 + 7]));
+        *reinterpret_cast<uint4*>(dk + u * 8) = o;
+        o.x = pack_bf16x2(__uint_as_float(bb[u * 8 + 0]), __uint_as_float(bb[u * 8 + 1]));
+        o.y = pack_bf16x2(__uint_as_float(bb[u * 8 + 2]), __uint_as_float(bb[u * 8 + 3]));
+        o.z = pack_bf16x2(__uint_as_float(bb[u * 8 + 4]), __uint_as_float(bb[u * 8 + 5]));
+        o.w = pack_bf16x2(__uint_as_float(bb[u * 8 + 6]), __uint_as_float(bb[u * 8 + 7]));
+        *reinterpret_cast<uint4*>(dv + u * 8) = o;
+      }
+    }
+    tc_fence_before();
+  };
 
   for (int kt = 0; kt < nt; ++kt) {
     for (int qt = 0; qt < nt; ++qt) {
@@ -1175,37 +1229,13 @@ enc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
       EB_TRACE(8 + (kt * 2 + qt) * 6 + 4);
       g_pending = true;
       if (qt == nt - 1) {
-        // dK[kt], dV[kt] are final once the gradient MMAs just issued complete
+        // dK[kt], dV[kt] are final once the gradient MMAs just issued complete.  (Reading them out one block later instead,
+        // without this drain, measured SLOWER -- 447 vs 391 us per layer at cfg4 shapes: every block's softmax then runs
+        // against the previous block's gradient MMAs, and tcgen05.ld under MMA traffic to the same tensor memory is slow.)
         mbar_wait(bar_grad, g_phase);
         g_phase ^= 1;
         g_pending = false;
-        tc_fence_after();
-        const int key = kt * 128 + r;
-        uint32_t a[16], bb[16];
-        tmem_ld_32x16(t_row + TM_DK + cq * 16, a);
-        tmem_ld_32x16(t_row + TM_DV + cq * 16, bb);
-        tmem_ld_wait();
-        if (key < L) {
-          __nv_bfloat16* dk = p.dqkv + static_cast<size_t>(row0 + key) * 3 * p.inner + p.inner + h * 64 + cq * 16;
-          __nv_bfloat16* dv = dk + p.inner;
-#pragma unroll
-          for (int u = 0; u < 2; ++u) {
-            uint4 o;
-            o.x = pack_bf16x2(__uint_as_float(a[u * 8 + 0]), __uint_as_float(a[u * 8 + 1]));
-            o.y = pack_bf16x2(__uint_as_float(a[u * 8 + 2]), __uint_as_float(a[u * 8 + 3]));
-            o.z = pack_bf16x2(__uint_as_float(a[u * 8 + 4]), __uint_as_float(a[u * 8 + 5]));
-            o.w = pack_bf16x2(__uint_as_float(a[u * 8 + 6]), __uint_as_float(a[u * 8 + 7]));
-            *reinterpret_cast<uint4*>(dk + u * 8) = o;
-            o.x = pack_bf16x2(__uint_as_float(bb[u * 8 + 0]), __uint_as_float(bb[u * 8 + 1]));
-            o.y = pack_bf16x2(__uint_as_float(bb[u * 8 + 2]), __uint_as_float(bb[u * 8 + 3]));
-            o.z = pack_bf16x2(__uint_as_float(bb[u * 8 + 4]), __uint_as_float(bb[u * 8 + 5]));
-            o.w = pack_bf16x2(__uint_as_float(bb[u * 8 + 6]), __uint_as_float(bb[u * 8 + 7]));
-            *reinterpret_cast<uint4*>(dv + u * 8) = o;
-          }
-        }
-        // the next key tile's first gradient MMA (which overwrites dK / dV) is only issued after every softmax
-        // thread has arrived on bar_ready for that block, i.e. after these TMEM reads
-        tc_fence_before();
+        store_dk_dv(kt);
       }
       EB_TRACE(8 + (kt * 2 + qt) * 6 + 5);
     }
