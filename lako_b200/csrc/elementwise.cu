@@ -651,10 +651,17 @@ int transpose_bf16(const __nv_bfloat16* in, __nv_bfloat16* out, int rows, int co
 // --------------------------------------------------------------------------------------------
 // gradient global-norm + fused clip / AdamW / bf16 re-cast over the flat parameter buffer
 // --------------------------------------------------------------------------------------------
+// Deterministic: block partials are combined in index order by whichever block finishes last (an atomicAdd per block
+// made ||g||^2 -- hence the clip coefficient and, one ulp at a time, the updated weights -- depend on block scheduling:
+// data-parallel replicas that must stay bit-identical drifted apart).
+constexpr int SUMSQ_MAX_BLOCKS = 4096;
+__device__ float g_sumsq_part[SUMSQ_MAX_BLOCKS];
+__device__ unsigned int g_sumsq_ticket;
 __global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ g, size_t n, float* __restrict__ out) {
   pdl_launch_dependents();
   pdl_wait();
   __shared__ float s_w[8];
+  __shared__ bool s_last;
   float acc = 0.f;
   const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x * 4;
   for (size_t i = (static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x) * 4; i < n; i += stride) {
@@ -671,13 +678,32 @@ __global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ g,
   if (threadIdx.x < 32) {
     float v = (threadIdx.x < 8) ? s_w[threadIdx.x] : 0.f;
     v = warp_sum(v);
-    if (threadIdx.x == 0) atomicAdd(out, v);
+    if (threadIdx.x == 0) {
+      g_sumsq_part[blockIdx.x] = v;
+      __threadfence();
+      s_last = atomicAdd(&g_sumsq_ticket, 1u) == gridDim.x - 1;
+    }
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  float tot = 0.f;
+  for (unsigned i = threadIdx.x; i < gridDim.x; i += 256) tot += __ldcg(&g_sumsq_part[i]);
+  tot = warp_sum(tot);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = tot;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float v = 0.f;
+    for (int w = 0; w < 8; ++w) v += s_w[w];
+    *out += v;  // the stream serialises the calls that accumulate into *out
+    g_sumsq_ticket = 0;
   }
 }
 int grad_sumsq(const float* g, size_t n, float* out, cudaStream_t s) {
   // caller zeroes *out
   ProfScope prof(PROF_OTHER, static_cast<double>(n) * 4.0, s);
-  const int grid = device_sm_count() * 8;
+  const int grid = std::min(device_sm_count() * 8, SUMSQ_MAX_BLOCKS);
   launch_pdl(sumsq_kernel, dim3(grid), dim3(256), 0, s, g, n, out);
   LAKO_CHECK_LAUNCH();
   return LAKO_OK;
