@@ -70,6 +70,8 @@ struct SmallLinParams {
   int kc;      // K chunk staged per pass (multiple of 32)
   int kb_per;  // 32-wide k blocks per K split (gridDim.y splits; epi 3 only when > 1 split)
   int ntiles;  // 16-row output tiles; a CTA loops over tiles blockIdx.x, blockIdx.x + gridDim.x, ...
+  const uint8_t* pf;  // optional: bytes the NEXT launches will stream (their weights), prefetched to L2 from here
+  unsigned pf_lines;  // in 128-byte lines
 };
 
 constexpr int SL_WARPS = 8;
@@ -88,6 +90,11 @@ __global__ void __launch_bounds__(SL_WARPS * 32) smallm_linear_kernel(const Smal
   float* red = reinterpret_cast<float*>(sl_smem + static_cast<size_t>(MP) * pitch);
   float* s_rstd = red + SL_WARPS * 16 * MP;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t4 = lane & 3;
+  if (p.pf) {  // weights of the following launches -> L2 (they do not depend on any predecessor)
+    const unsigned nthr = gridDim.x * gridDim.y * blockDim.x;
+    for (unsigned i = (blockIdx.y * gridDim.x + blockIdx.x) * blockDim.x + tid; i < p.pf_lines; i += nthr)
+      prefetch_l2_line(p.pf + static_cast<size_t>(i) * 128);
+  }
   // this CTA's K range (in 32-wide blocks) and whether the staged activations can be kept across output tiles
   const int kblocks_all = p.K >> 5;
   const int kb_lo = blockIdx.y * p.kb_per, kb_hi = min(kblocks_all, kb_lo + p.kb_per);
@@ -275,7 +282,8 @@ int launch_smallm(const SmallLinParams& p, int grid_x, int ksplit, cudaStream_t 
 // with ln_w it is RMS-normalised (eps) on the fly.  Otherwise x_b16 [M][ldx] bf16.  With the accumulate epilogue
 // (SL_F32_ADD) and few output tiles, K is split over gridDim.y CTAs that add their partial sums atomically.
 int smallm_linear(const float* x_f32, const __nv_bfloat16* x_b16, int ldx, const float* ln_w, float eps,
-                  const __nv_bfloat16* W, void* y, int ldy, int M, int N, int K, int epi, float alpha, cudaStream_t s) {
+                  const __nv_bfloat16* W, void* y, int ldy, int M, int N, int K, int epi, float alpha, cudaStream_t s,
+                  const void* prefetch, size_t prefetch_bytes) {
   LAKO_REQUIRE(M > 0 && N > 0 && K > 0 && K % 32 == 0, LAKO_ERR_UNSUPPORTED);
   LAKO_REQUIRE((x_f32 != nullptr) != (x_b16 != nullptr) && W && y && epi >= 0 && epi <= 3, LAKO_ERR_BAD_ARG);
   LAKO_REQUIRE(x_b16 == nullptr || ldx % 4 == 0, LAKO_ERR_BAD_ARG);
@@ -285,12 +293,13 @@ int smallm_linear(const float* x_f32, const __nv_bfloat16* x_b16, int ldx, const
       const int rc = smallm_linear(x_f32 ? x_f32 + static_cast<size_t>(m0) * K : nullptr,
                                    x_b16 ? x_b16 + static_cast<size_t>(m0) * ldx : nullptr, ldx, ln_w, eps, W,
                                    static_cast<uint8_t*>(y) + static_cast<size_t>(m0) * ldy * ysz, ldy, min(64, M - m0), N, K,
-                                   epi, alpha, s);
+                                   epi, alpha, s, m0 == 0 ? prefetch : nullptr, prefetch_bytes);
       if (rc) return rc;
     }
     return LAKO_OK;
   }
-  SmallLinParams p{x_f32, x_b16, ln_w, W, y, M, N, K, ldx, ldy, eps, alpha, epi, 0, 0, 0};
+  SmallLinParams p{x_f32, x_b16, ln_w, W, y, M, N, K, ldx, ldy, eps, alpha, epi, 0, 0, 0,
+                   static_cast<const uint8_t*>(prefetch), prefetch ? static_cast<unsigned>(prefetch_bytes / 128) : 0u};
   const int nt = (M + 7) / 8;
   const int NT = nt <= 1 ? 1 : nt <= 2 ? 2 : nt <= 4 ? 4 : 8;
   constexpr int KGROUP = 32 * SL_WARPS * SL_UNROLL;

@@ -657,7 +657,7 @@ int transpose_bf16(const __nv_bfloat16* in, __nv_bfloat16* out, int rows, int co
 constexpr int SUMSQ_MAX_BLOCKS = 4096;
 __device__ float g_sumsq_part[SUMSQ_MAX_BLOCKS];
 __device__ unsigned int g_sumsq_ticket;
-__global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ g, size_t n, float* __restrict__ out) {
+__global__ void __launch_bounds__(256, 8) sumsq_kernel(const float* __restrict__ g, size_t n, float* __restrict__ out) {
   pdl_launch_dependents();
   pdl_wait();
   __shared__ float s_w[8];

@@ -86,7 +86,8 @@ int greedy_pick(const float* logits, int B, int V, int ld, long long* out_ids, i
 
 // decode.cu
 int smallm_linear(const float* x_f32, const __nv_bfloat16* x_b16, int ldx, const float* ln_w, float eps,
-                  const __nv_bfloat16* W, void* y, int ldy, int M, int N, int K, int epi, float alpha, cudaStream_t s);
+                  const __nv_bfloat16* W, void* y, int ldy, int M, int N, int K, int epi, float alpha, cudaStream_t s,
+                  const void* prefetch = nullptr, size_t prefetch_bytes = 0);
 enum : int { SL_BF16 = 0, SL_BF16_RELU = 1, SL_F32 = 2, SL_F32_ADD = 3 };
 size_t xattn_decode_workspace_bytes(int B, int H, int M);
 int xattn_decode(const float* q, const __nv_bfloat16* kv, size_t kv_rows, const unsigned char* mask, __nv_bfloat16* out,
