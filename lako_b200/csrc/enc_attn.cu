@@ -798,6 +798,8 @@ struct EncAttnBwdParams {
   const int* cu;                 // packed layout offsets (see EncAttnParams); null = padded
   DropSpec drop;
   const uint32_t* keepbits;      // keep masks saved by the forward (null: regenerate them with Philox)
+  int d_in_out;                  // 1: `out` rows no longer hold O but, in their first H floats, D[q][h] = sum_d dO * O
+                                 // (attn_rowdot_inplace); 0: the kernel forms D from O and dO itself
 };
 
 // bias-gradient bins in shared memory: bin EB_DLUT_PAD + (k - q + L - 1); the padding takes the (all-zero) sums of the
@@ -1007,6 +1009,8 @@ enc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
   // MMAs of block i; only the P / dS stores wait for them.
   uint32_t s_phase = 0, g_phase = 0;
   bool g_pending = false;
+  float pre_lse = INFINITY, pre_D = 0.f;  // (lse, D) of this thread's row in the NEXT passage (d_in_out mode)
+  bool have_pre = false;
 
   for (int psg = p_first; psg < P; psg += pstep) {
   int row0, L;
@@ -1020,40 +1024,58 @@ enc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
     // block's gradient MMAs, which everybody waits for, are only issued once all have arrived on bar_ready).
     unsigned char mk = 1;
     if (tid < L && p.mask) mk = __ldg(p.mask + static_cast<size_t>(psg) * Lmax + tid);
-    const int q = tid >> 1, part = tid & 1;
-    uint4 ov[4], dv[4];
-    float lse_q = INFINITY;  // rows beyond the passage -> P = exp(s - inf) = 0
-    if (q < L) {
-      const uint4* o4 = reinterpret_cast<const uint4*>(p.out + static_cast<size_t>(row0 + q) * p.inner + h * 64) + part * 4;
-      const uint4* d4 = reinterpret_cast<const uint4*>(p.dout + static_cast<size_t>(row0 + q) * p.inner + h * 64) + part * 4;
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        ov[u] = __ldg(o4 + u);
-        dv[u] = __ldg(d4 + u);
-      }
-      if (part == 0) lse_q = __ldg(p.lse + (static_cast<size_t>(psg) * H + h) * Lmax + q);
-    }
     if (tid < 256) s_kmask[tid] = (tid < L) ? (mk ? 0.f : MASK_MIN) : -INFINITY;
-    float dsum = 0.f;
-    if (q < L) {
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const uint4 a = ov[u], b = dv[u];
-        dsum += bf16_lo(a.x) * bf16_lo(b.x) + bf16_hi(a.x) * bf16_hi(b.x) + bf16_lo(a.y) * bf16_lo(b.y) +
-                bf16_hi(a.y) * bf16_hi(b.y) + bf16_lo(a.z) * bf16_lo(b.z) + bf16_hi(a.z) * bf16_hi(b.z) +
-                bf16_lo(a.w) * bf16_lo(b.w) + bf16_hi(a.w) * bf16_hi(b.w);
+    int nrow0 = 0, nL = 0;  // the next passage of this CTA
+    const int npsg = psg + pstep;
+    if (npsg < P) psg_geom(npsg, nrow0, nL);
+    if (p.d_in_out) {
+      // D was formed by attn_rowdot_inplace: one (lse, D) pair per query row, and the NEXT passage's pair is fetched into
+      // two registers a whole passage ahead, so this staging exposes no memory latency at all.
+      if (!have_pre && tid < L) {
+        pre_lse = __ldg(p.lse + (static_cast<size_t>(psg) * H + h) * Lmax + tid);
+        pre_D = __ldg(reinterpret_cast<const float*>(p.out + static_cast<size_t>(row0 + tid) * p.inner) + h);
       }
-    }
-    dsum += __shfl_xor_sync(0xffffffffu, dsum, 1);
-    if (part == 0) {
-      s_D[q] = dsum;
-      s_lse[q] = lse_q;
-    }
-    named_bar_sync(1, EB_SOFTMAX_THREADS);
-    {  // the next passage's O rows (one 128-byte line per query and head) and lse to L2
-      int nrow0 = 0, nL = 0;
-      const int npsg = psg + pstep;
-      if (npsg < P) psg_geom(npsg, nrow0, nL);
+      if (tid < 256) {
+        s_lse[tid] = (tid < L) ? pre_lse : INFINITY;  // rows beyond the passage -> P = exp(s - inf) = 0
+        s_D[tid] = (tid < L) ? pre_D : 0.f;
+      }
+      named_bar_sync(1, EB_SOFTMAX_THREADS);
+      have_pre = true;
+      if (tid < nL) {
+        pre_lse = __ldg(p.lse + (static_cast<size_t>(npsg) * H + h) * Lmax + tid);
+        pre_D = __ldg(reinterpret_cast<const float*>(p.out + static_cast<size_t>(nrow0 + tid) * p.inner) + h);
+      }
+    } else {
+      const int q = tid >> 1, part = tid & 1;  // two threads per query row, 32 head dims each
+      uint4 ov[4], dv[4];
+      float lse_q = INFINITY;
+      if (q < L) {
+        const uint4* o4 = reinterpret_cast<const uint4*>(p.out + static_cast<size_t>(row0 + q) * p.inner + h * 64) + part * 4;
+        const uint4* d4 = reinterpret_cast<const uint4*>(p.dout + static_cast<size_t>(row0 + q) * p.inner + h * 64) + part * 4;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          ov[u] = __ldg(o4 + u);
+          dv[u] = __ldg(d4 + u);
+        }
+        if (part == 0) lse_q = __ldg(p.lse + (static_cast<size_t>(psg) * H + h) * Lmax + q);
+      }
+      float dsum = 0.f;
+      if (q < L) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const uint4 a = ov[u], b = dv[u];
+          dsum += bf16_lo(a.x) * bf16_lo(b.x) + bf16_hi(a.x) * bf16_hi(b.x) + bf16_lo(a.y) * bf16_lo(b.y) +
+                  bf16_hi(a.y) * bf16_hi(b.y) + bf16_lo(a.z) * bf16_lo(b.z) + bf16_hi(a.z) * bf16_hi(b.z) +
+                  bf16_lo(a.w) * bf16_lo(b.w) + bf16_hi(a.w) * bf16_hi(b.w);
+        }
+      }
+      dsum += __shfl_xor_sync(0xffffffffu, dsum, 1);
+      if (part == 0) {
+        s_D[q] = dsum;
+        s_lse[q] = lse_q;
+      }
+      named_bar_sync(1, EB_SOFTMAX_THREADS);
+      // the next passage's O rows (one 128-byte line per query and head) and lse to L2
       if (part == 0 && q < nL) prefetch_l2_line(p.out + static_cast<size_t>(nrow0 + q) * p.inner + h * 64);
       if (tid < 8 && tid * 32 < nL) prefetch_l2_line(p.lse + (static_cast<size_t>(npsg) * H + h) * Lmax + tid * 32);
     }
@@ -1292,9 +1314,54 @@ extern "C" int lako_debug_eb_trace(long long* out) {
 }
 #endif
 
+// D[row][h] = sum_d dO[row][h*64 + d] * O[row][h*64 + d], written IN PLACE over the first H floats of O's row (the
+// attention output is dead once its o-projection weight gradient has been formed): one warp per row, every lane holds
+// its 16-byte pieces of the row before any lane writes.
+__global__ void __launch_bounds__(256) attn_rowdot_inplace_kernel(__nv_bfloat16* __restrict__ o, const __nv_bfloat16* __restrict__ dout,
+                                                                  int rows, int H) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= rows) return;
+  const int inner = H * 64;
+  const uint4* o4 = reinterpret_cast<const uint4*>(o + static_cast<size_t>(warp) * inner);
+  const uint4* d4 = reinterpret_cast<const uint4*>(dout + static_cast<size_t>(warp) * inner);
+  float acc[4];
+  const int nit = (H * 8 + 31) / 32;  // 8 lanes of 16 bytes per head; at most 4 passes (H <= 16 per pass of 4 heads)
+#pragma unroll
+  for (int it = 0; it < 4; ++it) {
+    acc[it] = 0.f;
+    const int u = it * 32 + lane;
+    if (it < nit && u < H * 8) {
+      const uint4 a = __ldg(o4 + u), b = __ldg(d4 + u);
+      acc[it] = bf16_lo(a.x) * bf16_lo(b.x) + bf16_hi(a.x) * bf16_hi(b.x) + bf16_lo(a.y) * bf16_lo(b.y) +
+                bf16_hi(a.y) * bf16_hi(b.y) + bf16_lo(a.z) * bf16_lo(b.z) + bf16_hi(a.z) * bf16_hi(b.z) +
+                bf16_lo(a.w) * bf16_lo(b.w) + bf16_hi(a.w) * bf16_hi(b.w);
+    }
+    acc[it] += __shfl_xor_sync(0xffffffffu, acc[it], 1);
+    acc[it] += __shfl_xor_sync(0xffffffffu, acc[it], 2);
+    acc[it] += __shfl_xor_sync(0xffffffffu, acc[it], 4);
+  }
+  __syncwarp();  // every lane has read its part of the row
+  float* dst = reinterpret_cast<float*>(o + static_cast<size_t>(warp) * inner);
+#pragma unroll
+  for (int it = 0; it < 4; ++it) {
+    const int hh = it * 4 + (lane >> 3);
+    if (it < nit && (lane & 7) == 0 && hh < H) dst[hh] = acc[it];
+  }
+}
+int attn_rowdot_inplace(__nv_bfloat16* o, const __nv_bfloat16* dout, int rows, int H, cudaStream_t s) {
+  LAKO_REQUIRE(rows > 0 && H > 0 && H <= 16, LAKO_ERR_UNSUPPORTED);
+  ProfScope prof(PROF_ENC_ATTN_BWD, 0.0, s);
+  launch_pdl(attn_rowdot_inplace_kernel, dim3((rows + 7) / 8), dim3(256), 0, s, o, dout, rows, H);
+  LAKO_CHECK_LAUNCH();
+  return LAKO_OK;
+}
+
 int enc_attn_bwd(const __nv_bfloat16* qkv, const __nv_bfloat16* out, const __nv_bfloat16* dout, const float* lse,
                  const unsigned char* mask, const float* bias_lut, __nv_bfloat16* dqkv, float* dlut, int P, int L,
-                 int H, cudaStream_t s, DropSpec drop, const int* cu, int packed_rows, const uint32_t* keepbits) {
+                 int H, cudaStream_t s, DropSpec drop, const int* cu, int packed_rows, const uint32_t* keepbits,
+                 bool d_in_out) {
   int rc = check_arch();
   if (rc) return rc;
   LAKO_REQUIRE(P > 0 && H > 0 && L > 0, LAKO_ERR_BAD_ARG);
@@ -1334,6 +1401,7 @@ int enc_attn_bwd(const __nv_bfloat16* qkv, const __nv_bfloat16* out, const __nv_
   p.cu = cu;
   p.drop = drop;
   p.keepbits = keepbits;
+  p.d_in_out = d_in_out ? 1 : 0;
   ProfScope prof(PROF_ENC_ATTN_BWD, 10.0 * P * H * static_cast<double>(L) * L * 64, s);
   if (H > device_sm_count()) {
     set_last_error("enc_attn_bwd: more heads than SMs", __FILE__, __LINE__);

@@ -590,8 +590,11 @@ extern "C" int lako_fidt5_backward(const lako_fidt5* m, const lako_batch* bt, co
                    g + p.lo.enc_ln1[l], Mt, d, 1, 1.f, s, dr.none(), dr(l, E_O)));
     RC(lin_dgrad(w.dres_enc_b, p.wb + p.lo.enc_o[l], w.dao_enc, Mt, d, inner, nullptr, 1.f, s));
     RC(lin_wgrad(w.dres_enc_b, a.ao, g + p.lo.enc_o[l], Mt, d, inner, 1.f, s));
+    // D = rowsum(dO * O) once per (token, head), over the now dead attention output (its wgrad was the last reader)
+    const bool d_pre = H <= 16;
+    if (d_pre) RC(attn_rowdot_inplace(a.ao, w.dao_enc, Mt, H, s));
     RC(enc_attn_bwd(a.qkv, a.ao, w.dao_enc, a.lse, xmask, w.lut_enc, w.dqkv_enc, w.dlut_enc, w.P, w.L, H, s,
-                    dr(l, E_ATTN), w.cu, Mt, a.akeep));
+                    dr(l, E_ATTN), w.cu, Mt, a.akeep, d_pre));
     RC(lin_dgrad(w.dqkv_enc, p.wb + p.lo.enc_qkv[l], w.dn_enc, Mt, 3 * inner, d, nullptr, 1.f, s));
     RC(lin_wgrad(w.dqkv_enc, a.n_a, g + p.lo.enc_qkv[l], Mt, 3 * inner, d, 1.f, s));
     RC(rmsnorm_bwd(w.dn_enc, w.X[2 * l], a.rstd_a, p.wf + p.lo.enc_ln0[l], w.dres_enc, w.dres_enc_b,

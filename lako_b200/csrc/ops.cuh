@@ -54,7 +54,9 @@ int enc_attn_fwd(const __nv_bfloat16* qkv, const unsigned char* mask, const floa
 int enc_attn_bwd(const __nv_bfloat16* qkv, const __nv_bfloat16* out, const __nv_bfloat16* dout, const float* lse,
                  const unsigned char* mask, const float* bias_lut, __nv_bfloat16* dqkv, float* dlut, int P, int L,
                  int H, cudaStream_t s, DropSpec drop = DropSpec{}, const int* cu = nullptr, int packed_rows = 0,
-                 const uint32_t* keepbits = nullptr);
+                 const uint32_t* keepbits = nullptr, bool d_in_out = false);
+// D[row][h] = sum_d dO * O written over the first H floats of O's row (H <= 16); enc_attn_bwd(..., d_in_out = true)
+int attn_rowdot_inplace(__nv_bfloat16* o, const __nv_bfloat16* dout, int rows, int H, cudaStream_t s);
 
 // dec_attn.cu
 size_t xattn_workspace_bytes(int B, int H, int T, int M);
