@@ -147,6 +147,34 @@ def test_padded_and_packed_paths_agree(path):
     assert (a[4] - b[4]).abs().max().item() < 2e-2 * b[4].abs().max().item()
 
 
+def test_all_padding_passage_and_oracle():
+    """Edge case: one passage of a question is ENTIRELY padding (mask all zero).  The packed execution skips it (zero
+    rows), the padded execution carries its fully masked rows (HF semantics: uniform attention over masked keys, then
+    masked out as cross-attention keys); both must match the fp32 oracle in loss and logits, and each other in
+    gradients."""
+    from oracle import fidt5_oracle as O
+    c, cfg, sd, model = _load(GOLDEN[0])
+    ids, mask, labels = c["ids"].clone(), c["mask"].clone(), c["labels"]
+    ids[0, 1] = 0
+    mask[0, 1] = False
+    with torch.no_grad():
+        ref_loss, ref_logits = O.fidt5_forward(sd, cfg, ids, mask, labels)[:2]
+    res = {}
+    for unpad in (True, False):
+        model.unpad = unpad
+        model.train()          # dropout_rate is 0 in these golden configs
+        model.zero_grad()
+        loss, logits = model(input_ids=ids.cuda(), attention_mask=mask.cuda(), labels=labels.cuda())
+        loss.backward()
+        torch.cuda.synchronize()
+        assert bool(torch.isfinite(model._flat_grad).all())
+        res[unpad] = (loss.item(), logits.detach().float().cpu(), model._flat_grad.clone())
+        assert abs(loss.item() - float(ref_loss)) < 5e-3, (unpad, loss.item(), float(ref_loss))
+        assert (res[unpad][1] - ref_logits.reshape(res[unpad][1].shape)).abs().max().item() < 2e-2
+    model.unpad = True
+    assert ((res[True][2] - res[False][2]).norm() / res[False][2].norm()).item() < 0.05
+
+
 def test_host_passage_lengths_skip_the_readback():
     """Passing the Collator's host-side prefix lengths gives the same step as letting forward() read them back."""
     c, cfg, sd, model = _load(GOLDEN[0])
