@@ -196,6 +196,7 @@ def run_reference(args):
     if rank != 0:
         return
     size, B, N, L, T, kind = WORKLOADS[args.workload]
+    B = args.batch or B
     steps = max(1, args.steps)
     warmup = max(1, min(args.warmup, 2))
     # bounded: cap the number of timed CPU steps so the arm ends within minutes (one t5-large step of ONE question
@@ -310,6 +311,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="lako_b200", choices=["lako_b200", "reference"])
     ap.add_argument("--workload", default="cfg4", choices=sorted(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=0, help="per-GPU questions (default: the workload's own; cfg3 is also "
+                    "quoted at B = 1 and 32)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip generate / gpu_eager_baseline probes")
@@ -351,6 +354,7 @@ def main():
     steps = max(1, args.steps)
 
     size, B, N, L, T, kind = WORKLOADS[args.workload]
+    B = args.batch or B
     conf = FiDT5Config.t5(size)
     model = FiDT5(conf, emb_std=EMB_STD, seed=0).cuda()
     peaks, which = measured_peaks()
