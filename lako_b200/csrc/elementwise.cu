@@ -75,6 +75,16 @@ __global__ void __launch_bounds__(256) rmsnorm_fwd_kernel(const float* x, const 
   const float* xr = x + static_cast<size_t>(warp) * d;
   float* xo = x_out ? x_out + static_cast<size_t>(warp) * d : nullptr;
   const __nv_bfloat16* dr = delta ? delta + static_cast<size_t>(warp) * d : nullptr;
+  // every load of the row is issued before the Philox work of the dropout masks, which then runs under their latency
+  uint2 dvv[NORM_MAX_VEC];
+#pragma unroll
+  for (int i = 0; i < NORM_MAX_VEC; ++i) {
+    if (i < nvec) {
+      const int c = (i * 32 + lane) * 4;
+      xv[i] = *reinterpret_cast<const float4*>(xr + c);
+      if (dr) dvv[i] = *reinterpret_cast<const uint2*>(dr + c);
+    }
+  }
   uint32_t kdd[NORM_MAX_VEC], kod[NORM_MAX_VEC];
   if (dr && dd.thresh) keep_row<NORM_MAX_VEC>(dd, static_cast<size_t>(warp) * d, lane, nvec, kdd);
   if (out && od.thresh) keep_row<NORM_MAX_VEC>(od, static_cast<size_t>(warp) * d, lane, nvec, kod);
@@ -83,9 +93,9 @@ __global__ void __launch_bounds__(256) rmsnorm_fwd_kernel(const float* x, const 
   for (int i = 0; i < NORM_MAX_VEC; ++i) {
     if (i < nvec) {
       const int c = (i * 32 + lane) * 4;
-      float4 v = *reinterpret_cast<const float4*>(xr + c);
+      float4 v = xv[i];
       if (dr) {
-        const uint2 dv = *reinterpret_cast<const uint2*>(dr + c);
+        const uint2 dv = dvv[i];
         float4 a = make_float4(bf16_lo(dv.x), bf16_hi(dv.x), bf16_lo(dv.y), bf16_hi(dv.y));
         if (dd.thresh) {  // dropout on the sub-layer output before the residual add (HF:375, :149)
           const uint32_t k = kdd[i];

@@ -1,6 +1,5 @@
 #!/bin/bash
-for b in 1 32; do
-timeout 900 python bench.py --workload cfg3 --batch $b --steps 4 --warmup 3 --no-cpu-baseline > gpurun_out/r2w_bench_cfg3_b$b.json 2> gpurun_out/r2w_bench_cfg3_b$b.err
-python -c "
-import json; d=json.load(open('gpurun_out/r2w_bench_cfg3_b$b.json')); print($b, d['value'], d['ms_per_step'], d.get('generate',{}).get('decode_step'), d['e2e']['value'])" || tail -3 gpurun_out/r2w_bench_cfg3_b$b.err
+for f in lako_b200/_lib/liblako_b200.so lako_b200/_lib/liblako_b200_old.so lako_b200/_lib/liblako_b200.so lako_b200/_lib/liblako_b200_old.so; do echo "== $f"
+LAKO_B200_LIB=$PWD/$f timeout 600 python tools/dropout_cost.py 2>&1 | tail -2 | head -1 | cut -c1-135
 done
+timeout 600 python -m pytest tests/test_gpu_elementwise.py tests/test_gpu_dropout.py -m gpu -q -x 2>&1 | tail -2
