@@ -209,19 +209,23 @@ __global__ void __launch_bounds__(256, 2) rmsnorm_bwd_kernel(const __nv_bfloat16
     float4 xv[NV];
     uint2 dyp[NV];
     uint32_t kyd[NV], kbd[NV];
-    if (yd.thresh) keep_row<NV>(yd, static_cast<size_t>(row) * d, lane, NV, kyd);
-    if (dres_bf16 && bd.thresh) keep_row<NV>(bd, static_cast<size_t>(row) * d, lane, NV, kbd);
+    // the row's loads go out first; the Philox work of the dropout masks runs under their latency
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       const int c = (i * 32 + lane) * 4;
       xv[i] = *reinterpret_cast<const float4*>(xr + c);
       dyp[i] = *reinterpret_cast<const uint2*>(dyr + c);
-      if (yd.thresh) {  // gradient of the post-norm dropout: zero the dropped elements (the 1/(1-p) is in dy_scale)
+    }
+    if (yd.thresh) {  // gradient of the post-norm dropout: zero the dropped elements (the 1/(1-p) is in dy_scale)
+      keep_row<NV>(yd, static_cast<size_t>(row) * d, lane, NV, kyd);
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
         const uint32_t k = kyd[i];
         dyp[i].x &= ((k & 1) ? 0x0000ffffu : 0u) | ((k & 2) ? 0xffff0000u : 0u);
         dyp[i].y &= ((k & 4) ? 0x0000ffffu : 0u) | ((k & 8) ? 0xffff0000u : 0u);
       }
     }
+    if (dres_bf16 && bd.thresh) keep_row<NV>(bd, static_cast<size_t>(row) * d, lane, NV, kbd);
     float s = 0.f;
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
