@@ -5,14 +5,17 @@
 // bucketed relative-position bias (shared by all layers, HF:755-758) + key-padding mask (finfo.min),
 // fp32 softmax, probs @ v.   One "unit" = (passage, head); L = text_maxlength <= 256, d_kv = 64.
 //
-// Because a whole passage fits one tile (L <= 256 keys), softmax is single pass (no online
-// rescaling): S = Q K^T lands in TMEM (128 lanes x LK fp32 columns), two threads share a query row
-// (one key half each), read it with tcgen05.ld, adds the bias from a per-head LUT in shared memory
-// (2L-1 entries), writes un-normalised bf16 probabilities into 128B-swizzled shared memory, and
-// the second MMA O = P V (V as an MN-major operand straight from the qkv buffer) accumulates into
-// the same TMEM columns.  Q/K/V tiles come in by TMA from the fused qkv activation
-// [tokens][3*inner]; two CTAs are co-resident per SM (256 TMEM columns, ~97 KB smem each) so one
-// CTA's softmax overlaps the other's loads/MMAs.
+// Because a whole passage fits one key tile row (L <= 256 keys) the softmax needs no online rescaling: S = Q K^T lands
+// in tensor memory (128 lanes x LK fp32 columns) and two threads share a query row (one key half each).
+//   * forward, default (enc_attn_fwd2_kernel): persistent warp-specialised CTA per SM and head -- TMA producer warp,
+//     MMA warp, two softmax groups ping-ponging over two 256-column TMEM slots; probabilities stay in tensor memory
+//     (bf16 pairs written in place over the consumed scores, O = P V with P as the TMEM A operand).
+//   * forward, round 1 (enc_attn_fwd_kernel; LAKO_ATTN_FWD=1): one-shot CTA per (query tile, head, passage), P through
+//     128B-swizzled shared memory, two CTAs per SM.
+//   * backward (enc_attn_bwd_kernel): persistent CTA per SM and head, 16 softmax warps + an issuing warp, all 512 TMEM
+//     columns (S | dP | dQ x2 | dK | dV).
+// Q/K/V tiles come in by TMA from the fused qkv activation [tokens][3*inner]; V is an MN-major operand straight from
+// that buffer.  DESIGN.md section 3.2 has the measurements behind each choice.
 #include <algorithm>
 #include <cstdlib>
 
@@ -812,7 +815,8 @@ constexpr int EB_Q_OFF = 0, EB_DO_OFF = 32768, EB_K_OFF = 65536, EB_V_OFF = 9830
 constexpr int EB_SMEM_BYTES = EB_BAR_OFF + 64 + 1024;
 constexpr int TM_S = 0, TM_DP = 128, TM_DQ = 256, TM_DK = 384, TM_DV = 448;
 
-// One CTA per (head, passage); 16 softmax warps (the arithmetic between the MMAs is latency bound, so the CTA carries
+// One persistent CTA per SM, bound to a head, walks that head's passages; 16 softmax warps (the arithmetic between the
+// MMAs is latency bound, so the CTA carries
 // as many warps as the register file allows) + 1 warp that issues the TMA loads and every MMA: softmax warp w owns
 // TMEM lane quarter (w & 3) = 32 query rows and key columns (w >> 2)*32..+32 of each 128x128 (query tile x key tile)
 // block.  The issuing warp runs ahead: S/dP of block i+1 and the 24 gradient MMAs of block i overlap the softmax
@@ -822,7 +826,7 @@ constexpr int EB_SOFTMAX_THREADS = 512;
 constexpr int EB_THREADS = EB_SOFTMAX_THREADS + 32;
 #ifdef LAKO_TRACE
 __device__ long long g_eb_trace[64];
-#define EB_TRACE(i) do { if (tid == 0 && blockIdx.x == 0 && blockIdx.y == 0) g_eb_trace[i] = clock64(); } while (0)
+#define EB_TRACE(i) do { if (tid == 0 && blockIdx.x == 0) g_eb_trace[i] = clock64(); } while (0)
 #else
 #define EB_TRACE(i) do { } while (0)
 #endif
