@@ -194,3 +194,27 @@ def test_transformers_302_cross_attention_bias_key_is_kept_and_announced():
     assert torch.equal(m.state_dict()[FiDT5.XATTN_BIAS_KEY], sd[FiDT5.XATTN_BIAS_KEY])
     with pytest.raises(RuntimeError):
         m.load_state_dict({**sd, FiDT5.XATTN_BIAS_KEY: torch.zeros(3, 3)})
+
+
+def test_attention_keep_words_host_restatement():
+    """lako_b200/philox.py attn_keep_words / attn_keep_mask (the bit-sliced attention-dropout masks): keep rate, determinism,
+    dependence on (seed, step, site), and the word <-> key mapping key j = bit (j >> 1) + 16 (j & 1)."""
+    import numpy as np
+    from lako_b200.philox import attn_keep_mask, attn_keep_words, thresh_of
+    P, H, L = 3, 2, 70
+    m = attn_keep_mask(9, 4, 21, P, H, L, 0.1)
+    assert m.shape == (P, H, L, 256) and m.dtype == bool
+    assert abs(m.mean() - (1 - thresh_of(0.1) / 65536.0)) < 4e-3
+    assert (attn_keep_mask(9, 4, 21, P, H, L, 0.1) == m).all()
+    for other in ((10, 4, 21), (9, 5, 21), (9, 4, 22)):
+        assert (attn_keep_mask(*other, P, H, L, 0.1) != m).any()
+    assert attn_keep_mask(9, 4, 21, P, H, L, 0.0).all()
+    # one (passage, head, query, chunk): rebuild the 32 keys from the word by hand
+    psg, h, q, c = 2, 1, 33, 5
+    word = int(attn_keep_words(9, 4, 21, np.array([(((psg * H + h) * L + q) * 32 + c * 4)], dtype=np.uint64), 0.1)[0])
+    for j in range(32):
+        assert m[psg, h, q, c * 32 + j] == bool((word >> ((j >> 1) + 16 * (j & 1))) & 1)
+    # the bit-sliced comparison IS a 16-bit threshold test of 32 independent uniforms: p = 1 - thresh / 65536 exactly
+    big = attn_keep_words(1, 2, 3, np.arange(0, 4 * 20000, 4, dtype=np.uint64), 0.25)
+    ones = sum(bin(int(w)).count("1") for w in big) / (32.0 * len(big))
+    assert abs(ones - 0.75) < 3e-3
