@@ -197,6 +197,7 @@ def run_reference(args):
         return
     size, B, N, L, T, kind = WORKLOADS[args.workload]
     B = args.batch or B
+    N = args.passages or N
     steps = max(1, args.steps)
     warmup = max(1, min(args.warmup, 2))
     # bounded: cap the number of timed CPU steps so the arm ends within minutes (one t5-large step of ONE question
@@ -313,6 +314,8 @@ def main():
     ap.add_argument("--workload", default="cfg4", choices=sorted(WORKLOADS))
     ap.add_argument("--batch", type=int, default=0, help="per-GPU questions (default: the workload's own; cfg3 is also "
                     "quoted at B = 1 and 32)")
+    ap.add_argument("--passages", type=int, default=0, help="passages per question (default: the workload's own; cfg5 is "
+                    "also quoted at N = 100)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip generate / gpu_eager_baseline probes")
@@ -355,6 +358,7 @@ def main():
 
     size, B, N, L, T, kind = WORKLOADS[args.workload]
     B = args.batch or B
+    N = args.passages or N
     conf = FiDT5Config.t5(size)
     model = FiDT5(conf, emb_std=EMB_STD, seed=0).cuda()
     peaks, which = measured_peaks()
