@@ -433,6 +433,7 @@ __global__ void __launch_bounds__(128) xattn_decode_kernel(const __grid_constant
     }
     q.ns = (q.Mb + XD_CH - 1) / XD_CH;
   };
+  const uint64_t kv_policy = l2_policy_evict_first();
   auto issue = [&](const Cur& q, int stage) {  // thread 0 only
     int kc0 = p.koff + q.h * 64, kr0 = q.kstart + q.ch * XD_CH, vc0 = p.voff + q.h * 64, vr0 = kr0;
     if (p.hm_rows > 0) {  // row of the [planes * tokens][64] view
@@ -442,8 +443,10 @@ __global__ void __launch_bounds__(128) xattn_decode_kernel(const __grid_constant
     }
     uint8_t* st = smem + stage * 2 * XD_TILE;
     mbar_arrive_expect_tx(&bar[stage], 2 * XD_TILE);
-    tma_load_2d(st, &tm_kv, &bar[stage], kc0, kr0);
-    tma_load_2d(st + XD_TILE, &tm_kv, &bar[stage], vc0, vr0);
+    // K / V of a layer are read exactly once per token: evict_first, so that the decoder weights the neighbouring
+    // Linears prefetch to L2 survive this ~130 MB stream
+    tma_load_2d_hint(st, &tm_kv, &bar[stage], kc0, kr0, kv_policy);
+    tma_load_2d_hint(st + XD_TILE, &tm_kv, &bar[stage], vc0, vr0, kv_policy);
   };
   Cur cur = seek(g_lo);
   Cur nxt = cur;  // producer cursor (thread 0): the next item to request

@@ -688,29 +688,31 @@ int enqueue_decode_step(const DecodeCtx& c, cudaStream_t s) {
   DecLayerAct& a = w.dec[0];
   float* Y = w.Y[0];
   RC(embed_gather(gw.next_ids, p.wf + p.lo.shared, Y, B, d, p.V, s));
-  // Every Linear asks for the NEXT Linear's weights to be brought to L2 (prefetch.global.L2 from its first
-  // instructions): a launch here lives 5-8 us, mostly the latency of its first weight bytes from HBM.
-  const size_t b_qkv = static_cast<size_t>(3) * inner * d * 2, b_o = static_cast<size_t>(d) * inner * 2,
-               b_ff = static_cast<size_t>(ff) * d * 2;
+  // Weight prefetch to L2 (prefetch.global.L2 from the first instructions of a Linear): the Linear before the
+  // cross-attention asks for the three weights after it (xo, wi, wo: one contiguous range of the flat buffer) -- they
+  // arrive while the cross-attention streams K / V, whose own loads are evict_first -- and the last Linear of a layer for
+  // the next layer's qkv .. xq range.  A launch here otherwise lives 5-8 us, mostly the latency of its first bytes.
+  auto range_bytes = [&](size_t first, size_t last, size_t last_elems) { return (last + last_elems - first) * 2; };
   for (int l = 0; l < nl; ++l) {
     RC(smallm_linear(Y, nullptr, 0, p.wf + p.lo.dec_ln0[l], p.eps, p.wb + p.lo.dec_qkv[l], a.qkv, 3 * inner, B, 3 * inner,
-                     d, SL_BF16, 1.f, s, p.wb + p.lo.dec_o[l], b_o));
+                     d, SL_BF16, 1.f, s));
     RC(dself_step(a.qkv, gw.kc + l * cache_l, gw.vc + l * cache_l, gw.lut_dec, a.ao, B, 0, c.max_length, H, s, gw.d_step));
-    RC(smallm_linear(nullptr, a.ao, inner, nullptr, 0.f, p.wb + p.lo.dec_o[l], Y, d, B, d, inner, SL_F32_ADD, 1.f, s,
-                     p.wb + p.lo.dec_xq[l], b_o));
+    RC(smallm_linear(nullptr, a.ao, inner, nullptr, 0.f, p.wb + p.lo.dec_o[l], Y, d, B, d, inner, SL_F32_ADD, 1.f, s));
     // q accumulates (K-split, atomic) into the zeroed fp32 buffer; the cross-attention kernel clears it again after use
     RC(smallm_linear(Y, nullptr, 0, p.wf + p.lo.dec_ln1[l], p.eps, p.wb + p.lo.dec_xq[l], gw.q_f32, inner, B, inner, d,
-                     SL_F32_ADD, 1.f, s, p.wb + p.lo.dec_xo[l], b_o));
+                     SL_F32_ADD, 1.f, s, p.wb + p.lo.dec_xo[l],
+                     range_bytes(p.lo.dec_xo[l], p.lo.dec_wo[l], static_cast<size_t>(d) * ff)));
     float* ts = c.capture ? ((l < first_half) ? gw.tok_first : gw.tok_last) : nullptr;
     RC(xattn_decode(gw.q_f32, w.kv_all, static_cast<size_t>(w.Mtok), xmask, a.xo, ts, gw.d_step, gw.xdec_ws, B, w.M, H,
                     inner, nl * 2 * inner, l * 2 * inner, l * 2 * inner + inner, inner, s, cu, c.N,
                     c.packed ? w.tok_index : nullptr, true, true));
-    RC(smallm_linear(nullptr, a.xo, inner, nullptr, 0.f, p.wb + p.lo.dec_xo[l], Y, d, B, d, inner, SL_F32_ADD, 1.f, s,
-                     p.wb + p.lo.dec_wi[l], b_ff));
+    RC(smallm_linear(nullptr, a.xo, inner, nullptr, 0.f, p.wb + p.lo.dec_xo[l], Y, d, B, d, inner, SL_F32_ADD, 1.f, s));
     RC(smallm_linear(Y, nullptr, 0, p.wf + p.lo.dec_ln2[l], p.eps, p.wb + p.lo.dec_wi[l], a.h, ff, B, ff, d, SL_BF16_RELU,
-                     1.f, s, p.wb + p.lo.dec_wo[l], b_ff));
+                     1.f, s));
+    const bool more = l + 1 < nl;
     RC(smallm_linear(nullptr, a.h, ff, nullptr, 0.f, p.wb + p.lo.dec_wo[l], Y, d, B, d, ff, SL_F32_ADD, 1.f, s,
-                     l + 1 < nl ? p.wb + p.lo.dec_qkv[l + 1] : nullptr, b_qkv));
+                     more ? p.wb + p.lo.dec_qkv[l + 1] : nullptr,
+                     more ? range_bytes(p.lo.dec_qkv[l + 1], p.lo.dec_xq[l + 1], static_cast<size_t>(inner) * d) : 0));
   }
   // final norm + tied LM head: logits = (norm(h) * d^-0.5) E^T  (HF:1107-1110), fp32
   RC(smallm_linear(Y, nullptr, 0, p.wf + p.lo.dec_final_ln, p.eps, p.wb + p.lo.shared, gw.logits, p.V, B, p.V, d, SL_F32,
