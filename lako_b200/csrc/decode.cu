@@ -338,7 +338,12 @@ namespace {
 
 constexpr int XD_CH = 128;            // keys per work item (4 warps x 32)
 constexpr int XD_TILE = XD_CH * 128;  // bytes of one 128-key x 64-dim bf16 tile
-constexpr int XD_STAGES = 3;          // K+V tile pairs in flight per CTA
+#ifndef LAKO_XD_STAGES
+#define LAKO_XD_STAGES 3
+#define LAKO_XD_CTAS 2
+#endif
+constexpr int XD_STAGES = LAKO_XD_STAGES;  // K+V tile pairs in flight per CTA
+constexpr int XD_CTAS = LAKO_XD_CTAS;      // resident CTAs per SM (XD_CTAS x XD_STAGES x 32 KB of tile ring)
 constexpr int XD_SMEM = XD_STAGES * 2 * XD_TILE + 1024 + 64;
 constexpr int XD_MAXB = 1024;         // questions per launch (prefix table in shared memory)
 
@@ -700,7 +705,7 @@ int xattn_decode(const float* q, const __nv_bfloat16* kv, size_t kv_rows, const 
   ProfScope prof(PROF_XATTN, 4.0 * B * H * static_cast<double>(M) * 64, s);
   // persistent: two CTAs per SM (2 x 96 KB of tile ring), never more CTAs than work items
   const long long max_items = static_cast<long long>(B) * H * splits;
-  const int grid = static_cast<int>(std::min<long long>(max_items, 2LL * device_sm_count()));
+  const int grid = static_cast<int>(std::min<long long>(max_items, static_cast<long long>(XD_CTAS) * device_sm_count()));
   launch_pdl(xattn_decode_kernel, dim3(grid), dim3(128), XD_SMEM, s, tm, p);
   LAKO_CHECK_LAUNCH();
   return LAKO_OK;

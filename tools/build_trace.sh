@@ -6,7 +6,7 @@ tmp=$(mktemp -d)
 objs=()
 for f in "$root"/lako_b200/csrc/*.cu; do
   o="$tmp/$(basename "${f%.cu}").o"
-  nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -DLAKO_TRACE $LAKO_EXTRA_DEFS -I "$root/include" -c "$f" -o "$o" &
+  nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC ${LAKO_TRACE_DEF--DLAKO_TRACE} $LAKO_EXTRA_DEFS -I "$root/include" -c "$f" -o "$o" &
   objs+=("$o")
 done
 wait

@@ -1,10 +1,8 @@
 #!/bin/bash
-# same-box A/B of the decode step (expects _lib/liblako_b200_old.so next to the new one)
-timeout 600 python -m pytest tests/test_gpu_decode.py tests/test_gpu_model.py -m gpu -q -x 2>&1 | tail -2
-for f in old "" old "" ; do
-lib=lako_b200/_lib/liblako_b200${f:+_$f}.so
+# same-box comparison of decode-kernel variants (every _lib/liblako_b200*.so) on the cfg3 decode step
+for r in 1 2; do for lib in lako_b200/_lib/liblako_b200*.so; do
 echo "== $lib"
 LAKO_B200_LIB=$PWD/$lib timeout 600 python bench.py --workload cfg3 --steps 4 --warmup 3 --no-cpu-baseline 2>/dev/null | python -c "
 import json,sys
-d=json.loads(sys.stdin.readline()); print(round(d['value'],2), d['generate']['decode_step'])"
-done
+d=json.loads(sys.stdin.readline()); print(round(d['value'],2), d['generate']['decode_step']['ms_per_token'])"
+done; done
