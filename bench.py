@@ -316,6 +316,8 @@ def main():
                     "quoted at B = 1 and 32)")
     ap.add_argument("--passages", type=int, default=0, help="passages per question (default: the workload's own; cfg5 is "
                     "also quoted at N = 100)")
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"],
+                    help="evaluation workloads only: fp32 = 3xTF32 GEMMs + fp32 attention (the mode that meets 1e-4 / 1e-2)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip generate / gpu_eager_baseline probes")
@@ -616,6 +618,8 @@ def run_eval_workload(args, model, size, B, N, L, dev, rank, world, peaks, which
     opt = types.SimpleNamespace(stream=2, n_context=10, attention_score_style="21mean",
                                 use_last_half_layer_attention="yes")
     model.eval()
+    if args.precision == "fp32":
+        model.set_precision("fp32")
     model.overwrite_forward_crossattention()
 
     def step(ids, mask):
@@ -671,7 +675,7 @@ def run_eval_workload(args, model, size, B, N, L, dev, rank, world, peaks, which
                     "frac": ds.get("frac_hbm_peak"), "traffic": None, "peak_source": f"{which} copy bandwidth"}
         line = {"metric": METRIC_EVAL, "value": world * B * steps / (ms * 1e-3), "unit": "questions/s", "n_gpus": world,
                 "steps": steps, "warmup": warmup, "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak",
-                "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                "vs_baseline": None, "dtype": ("tf32x3" if args.precision == "fp32" else "bf16"), "data": "synthetic",
                 "config": {"workload": f"{args.workload}: FiDT5 t5-{size} evaluation + attention-signal pass, per-GPU batch {B} "
                                        f"questions, n_passages={N}, text_maxlength={L}, greedy generate(max_length={ML}) forced "
                                        f"to full length + get_crossattention_scores(21mean, last half)",
