@@ -218,3 +218,38 @@ def test_attention_keep_words_host_restatement():
     big = attn_keep_words(1, 2, 3, np.arange(0, 4 * 20000, 4, dtype=np.uint64), 0.25)
     ones = sum(bin(int(w)).count("1") for w in big) / (32.0 * len(big))
     assert abs(ones - 0.75) < 3e-3
+
+
+def test_ctypes_mirrors_match_the_c_header(tmp_path):
+    """include/lako_b200.h compiled as plain C (gcc): sizeof and the offset of every field of lako_dims / lako_layout /
+    lako_fidt5 / lako_batch equal the ctypes mirrors in lako_b200/model.py -- the binding a maintainer writes from INTEGRATION.md must
+    not drift from the header."""
+    import ctypes, os, shutil, subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    from lako_b200 import model as M
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    mirrors = {"lako_dims": M._Dims, "lako_layout": M._Layout, "lako_fidt5": M._Model, "lako_batch": M._Batch}
+    lines = ["#include <stdio.h>", "#include <stddef.h>", '#include "lako_b200.h"', "int main(void) {"]
+    for cname, cls in mirrors.items():
+        lines.append(f'  printf("{cname} size %zu\\n", sizeof({cname}));')
+        for fname, _ in cls._fields_:
+            lines.append(f'  printf("{cname} {fname} %zu\\n", offsetof({cname}, {fname}));')
+    lines += ["  return 0;", "}"]
+    src = tmp_path / "abi.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "abi"
+    subprocess.run(["gcc", "-std=c99", "-I", os.path.join(root, "include"), str(src), "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split("\n")
+    seen = 0
+    for ln in out:
+        if not ln:
+            continue
+        cname, what, val = ln.split()
+        cls = mirrors[cname]
+        if what == "size":
+            assert ctypes.sizeof(cls) == int(val), (cname, ctypes.sizeof(cls), val)
+        else:
+            assert getattr(cls, what).offset == int(val), (cname, what, getattr(cls, what).offset, val)
+        seen += 1
+    assert seen == sum(len(c._fields_) + 1 for c in mirrors.values())
