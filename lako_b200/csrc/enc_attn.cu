@@ -858,7 +858,13 @@ enc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
   // (head, passage) spent ~35 % of its life in that un-overlapped prologue and epilogue.)
   const int H = p.H;
   const int h = blockIdx.x % H;
-  const int pstep = gridDim.x / H, p_first = blockIdx.x / H;
+  const int p_first = blockIdx.x / H;
+  // CTAs per head = the passage stride of this CTA, kept in shared memory and re-read at each passage change: as a
+  // register it was spilled, and its reload (local memory = the global-store path) sat behind the dQ / dK / dV stores
+  // for ~8 % of the kernel's warp samples.
+  int* s_misc = reinterpret_cast<int*>(tmem_slot + 1);
+  if (tid == 0) s_misc[0] = gridDim.x / H;
+  auto pstep_v = [&]() -> int { return static_cast<int>(lds_u32(smem_u32(s_misc))); };
   const int Lmax = p.L;  // LUT geometry / lse pitch
   const int nlut = 2 * Lmax - 1;
   EB_TRACE(0);
@@ -923,7 +929,7 @@ enc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
     const bool el = elect_one();  // (MMA / TMA issue only inside real branches on it; see DESIGN.md on elected producers)
     uint32_t r_phase = 0, l_phase = 0;
     uint32_t n_commits = 0;  // gradient commits (= bar_grad phases) issued so far
-    for (int psg = p_first; psg < P; psg += pstep) {
+    for (int psg = p_first; psg < P; psg += pstep_v()) {
       int row0, L;
       psg_geom(psg, row0, L);
       if (L <= 0) continue;
@@ -946,7 +952,7 @@ enc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
         // The NEXT passage's tiles go to L2 now: all CTAs change passage at about the same time, and without this the
         // ~190 KB each then asks for arrive as one HBM burst (~28 MB chip-wide) that the staging has to sit out.
         int nrow0 = 0, nL = 0;
-        const int npsg = psg + pstep;
+        const int npsg = psg + pstep_v();
         if (npsg < P) psg_geom(npsg, nrow0, nL);
         if (lane == 0 && nL > 0) {
           for (int t = 0; t < (nL + 127) / 128; ++t) {
@@ -1016,7 +1022,7 @@ enc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
   float pre_lse = INFINITY, pre_D = 0.f;  // (lse, D) of this thread's row in the NEXT passage (d_in_out mode)
   bool have_pre = false;
 
-  for (int psg = p_first; psg < P; psg += pstep) {
+  for (int psg = p_first; psg < P; psg += pstep_v()) {
   int row0, L;
   psg_geom(psg, row0, L);
   if (L <= 0) continue;
@@ -1030,7 +1036,7 @@ enc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
     if (tid < L && p.mask) mk = __ldg(p.mask + static_cast<size_t>(psg) * Lmax + tid);
     if (tid < 256) s_kmask[tid] = (tid < L) ? (mk ? 0.f : MASK_MIN) : -INFINITY;
     int nrow0 = 0, nL = 0;  // the next passage of this CTA
-    const int npsg = psg + pstep;
+    const int npsg = psg + pstep_v();
     if (npsg < P) psg_geom(npsg, nrow0, nL);
     if (p.d_in_out) {
       // D was formed by attn_rowdot_inplace: one (lse, D) pair per query row, and the NEXT passage's pair is fetched into
