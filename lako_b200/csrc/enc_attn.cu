@@ -846,7 +846,8 @@ enc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
   uint64_t* bar_grad = bar_load + 2;
   uint64_t* bar_ready = bar_load + 3;  // all softmax threads: P / dS of the block stored
   uint64_t* bar_sfree = bar_load + 4;  // all softmax threads: S / dP of the block are in registers (TMEM columns free)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_load + 5);
+  uint64_t* bar_kv = bar_load + 5;     // dK / dV of a key tile are final (committed before that block's 8 dQ MMAs)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_load + 6);
 
   // warp index through a shuffle: provably warp-uniform (the issuing warp's loops then run on uniform registers)
   const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
@@ -877,6 +878,7 @@ enc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
     mbar_init(bar_grad, 1);
     mbar_init(bar_ready, EB_SOFTMAX_THREADS);
     mbar_init(bar_sfree, EB_SOFTMAX_THREADS);
+    mbar_init(bar_kv, 1);
     fence_barrier_init();
   }
   if (warp == 0) tmem_alloc(tmem_slot, 512);
@@ -997,6 +999,8 @@ enc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
 #pragma unroll
             for (int j = 0; j < 8; ++j)
               umma_bf16(tmem + TM_DK, ds_t + j * 128, q_mn + qt * 1024 + j * 128, idesc_tn, (qt > 0 || j > 0));
+            // the key tile's last block: its dK / dV can be read out while the 8 dQ MMAs below still run
+            if (qt == nt - 1) umma_commit(bar_kv);
             // dQ[qt] += dS K[kt]   (M = 128 queries, N = 64, K = 128 keys)
 #pragma unroll
             for (int j = 0; j < 8; ++j)
@@ -1017,7 +1021,7 @@ enc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
   // previous block have finished reading P / dS from shared memory".  The S/dP MMAs of block i+1 are issued AHEAD of
   // the gradient MMAs of block i, so the softmax arithmetic of block i+1 (registers only) overlaps the 24 gradient
   // MMAs of block i; only the P / dS stores wait for them.
-  uint32_t s_phase = 0, g_phase = 0;
+  uint32_t s_phase = 0, g_phase = 0, kv_phase = 0;
   bool g_pending = false;
   float pre_lse = INFINITY, pre_D = 0.f;  // (lse, D) of this thread's row in the NEXT passage (d_in_out mode)
   bool have_pre = false;
@@ -1264,10 +1268,14 @@ enc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
         // dK[kt], dV[kt] are final once the gradient MMAs just issued complete.  (Reading them out one block later instead,
         // without this drain, measured SLOWER -- 447 vs 391 us per layer at cfg4 shapes: every block's softmax then runs
         // against the previous block's gradient MMAs, and tcgen05.ld under MMA traffic to the same tensor memory is slow.)
-        mbar_wait(bar_grad, g_phase);
-        g_phase ^= 1;
-        g_pending = false;
+        mbar_wait(bar_kv, kv_phase);
+        kv_phase ^= 1;
         store_dk_dv(kt);
+        if (kt == nt - 1) {  // last block of the passage: dQ is read out next, everything has to be complete
+          mbar_wait(bar_grad, g_phase);
+          g_phase ^= 1;
+          g_pending = false;
+        }
       }
       EB_TRACE(8 + (kt * 2 + qt) * 6 + 5);
     }
