@@ -24,16 +24,17 @@
 namespace lako {
 
 // forward implementation: 1 = one-shot CTA per (query tile, head, passage); 2 = persistent warp-specialised kernel with
-// the probabilities kept in tensor memory (default).  LAKO_ATTN_FWD=1 / lako_set_attn_impl(1) selects the former.
+// the probabilities kept in tensor memory (default).  LAKO_ATTN_FWD=1 / lako_set_attn_impl(1) selects the former;
+// 3 sends forward AND backward through the any-length tiled kernels of enc_attn_long.cu (what L > 256 always uses).
 static int g_attn_impl = -1;
 int enc_attn_impl() {
   if (g_attn_impl < 0) {
     const char* e = getenv("LAKO_ATTN_FWD");
-    g_attn_impl = (e && e[0] == '1') ? 1 : 2;
+    g_attn_impl = (e && e[0] == '1') ? 1 : (e && e[0] == '3') ? 3 : 2;
   }
   return g_attn_impl;
 }
-void set_enc_attn_impl(int v) { g_attn_impl = (v == 1) ? 1 : 2; }
+void set_enc_attn_impl(int v) { g_attn_impl = (v == 1 || v == 3) ? v : 2; }
 
 constexpr float MASK_MIN = -3.4028234663852886e38f;  // torch.finfo(float32).min, as HF's additive mask
 
@@ -727,7 +728,9 @@ int enc_attn_fwd(const __nv_bfloat16* qkv, const unsigned char* mask, const floa
   int rc = check_arch();
   if (rc) return rc;
   LAKO_REQUIRE(P > 0 && H > 0 && L > 0, LAKO_ERR_BAD_ARG);
-  LAKO_REQUIRE(L <= 256, LAKO_ERR_UNSUPPORTED);  // single-tile softmax; longer passages need the looped variant
+  // the kernels below hold a passage's whole key range in one softmax tile; longer passages take the tiled path (which
+  // regenerates the keep words in its backward and leaves `keepbits` untouched)
+  if (L > 256 || enc_attn_impl() == 3) return enc_attn_long_fwd(qkv, mask, bias_lut, out, lse, P, L, H, s, drop, cu);
   const int inner = H * 64;
   CUtensorMap tm;
   const uint64_t total_rows = cu ? static_cast<uint64_t>(packed_rows) : static_cast<uint64_t>(P) * L;
@@ -1383,7 +1386,8 @@ int enc_attn_bwd(const __nv_bfloat16* qkv, const __nv_bfloat16* out, const __nv_
   int rc = check_arch();
   if (rc) return rc;
   LAKO_REQUIRE(P > 0 && H > 0 && L > 0, LAKO_ERR_BAD_ARG);
-  LAKO_REQUIRE(L <= 256, LAKO_ERR_UNSUPPORTED);
+  if (L > 256 || enc_attn_impl() == 3)
+    return enc_attn_long_bwd(qkv, out, dout, lse, mask, bias_lut, dqkv, dlut, P, L, H, s, drop, cu, d_in_out);
   const int inner = H * 64;
   CUtensorMap tm_qkv, tm_do;
   const uint64_t total_rows = cu ? static_cast<uint64_t>(packed_rows) : static_cast<uint64_t>(P) * L;

@@ -161,7 +161,7 @@ void carve(const lako_dims& dm, int B, int N, int L, int T, int mode, void* base
     a.h = b.take<bf16>(Mt * ff);
     a.hbits = b.take<unsigned char>(Mt * ff / 8);
     a.lse = b.take<float>(static_cast<size_t>(w.P) * H * L);
-    a.akeep = b.take<uint32_t>(static_cast<size_t>(w.P) * H * L * 8);
+    a.akeep = L <= 256 ? b.take<uint32_t>(static_cast<size_t>(w.P) * H * L * 8) : nullptr;  // longer passages regenerate the words
     a.rstd_a = b.take<float>(Mt);
     a.rstd_f = b.take<float>(Mt);
   }
@@ -405,7 +405,10 @@ extern "C" int lako_fidt5_forward(const lako_fidt5* m, const lako_batch* bt, int
     LAKO_REQUIRE(mode == 0, LAKO_ERR_UNSUPPORTED);  // evaluation only
     return forward_f32(m, bt, p, s);
   }
-  LAKO_REQUIRE(bt->T >= 1 && bt->T <= 64 && bt->L >= 1 && bt->L <= 256, LAKO_ERR_UNSUPPORTED);
+  // L > 256 runs the encoder attention through the tiled kernels of enc_attn_long.cu; the bucket tables cover offsets up
+  // to +-bucket_center
+  LAKO_REQUIRE(bt->T >= 1 && bt->T <= 64 && bt->L >= 1 && bt->L <= ENC_ATTN_LONG_MAX_L && bt->L - 1 <= m->bucket_center,
+               LAKO_ERR_UNSUPPORTED);
   Work w;
   carve(m->dims, bt->B, bt->N, bt->L, bt->T, mode, bt->workspace, w);
   LAKO_REQUIRE(w.bytes <= bt->workspace_bytes, LAKO_ERR_WORKSPACE);
@@ -817,7 +820,9 @@ extern "C" int lako_fidt5_generate(const lako_fidt5* m, const lako_batch* bt, in
   Ptrs p;
   RC(make_ptrs(m, p));
   LAKO_REQUIRE(bt && bt->ids && bt->mask && bt->workspace && out_ids && out_len, LAKO_ERR_BAD_ARG);
-  LAKO_REQUIRE(max_length >= 2 && max_length <= 1024 && (bt->L <= 256 || bt->precision == 1), LAKO_ERR_UNSUPPORTED);
+  LAKO_REQUIRE(max_length >= 2 && max_length <= 1024 && max_length - 1 <= m->bucket_center && bt->L >= 1 &&
+                   bt->L - 1 <= m->bucket_center && (bt->L <= ENC_ATTN_LONG_MAX_L || bt->precision == 1),
+               LAKO_ERR_UNSUPPORTED);
   LAKO_REQUIRE((tok_score_first == nullptr) == (tok_score_last == nullptr), LAKO_ERR_BAD_ARG);
   const int B = bt->B, H = p.H;
   const size_t ntok = static_cast<size_t>(B) * bt->N * bt->L;

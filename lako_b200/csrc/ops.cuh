@@ -55,6 +55,15 @@ int enc_attn_bwd(const __nv_bfloat16* qkv, const __nv_bfloat16* out, const __nv_
                  const unsigned char* mask, const float* bias_lut, __nv_bfloat16* dqkv, float* dlut, int P, int L,
                  int H, cudaStream_t s, DropSpec drop = DropSpec{}, const int* cu = nullptr, int packed_rows = 0,
                  const uint32_t* keepbits = nullptr, bool d_in_out = false);
+// enc_attn_long.cu: the same contract for any L <= ENC_ATTN_LONG_MAX_L (64 x 64 tiles, online softmax, fp32 SIMT); enc_attn_fwd /
+// enc_attn_bwd route here when L > 256 (or when set_enc_attn_impl(3) forces it, for the tests)
+constexpr int ENC_ATTN_LONG_MAX_L = 2048;
+unsigned enc_attn_keep_stride(int L);  // Philox counters per query row of the probability dropout: 4 * max(8, ceil(L / 32))
+int enc_attn_long_fwd(const __nv_bfloat16* qkv, const unsigned char* mask, const float* bias_lut, __nv_bfloat16* out, float* lse,
+                      int P, int L, int H, cudaStream_t s, DropSpec drop, const int* cu);
+int enc_attn_long_bwd(const __nv_bfloat16* qkv, const __nv_bfloat16* out, const __nv_bfloat16* dout, const float* lse,
+                      const unsigned char* mask, const float* bias_lut, __nv_bfloat16* dqkv, float* dlut, int P, int L, int H,
+                      cudaStream_t s, DropSpec drop, const int* cu, bool d_in_out);
 // D[row][h] = sum_d dO * O written over the first H floats of O's row (H <= 16); enc_attn_bwd(..., d_in_out = true)
 int attn_rowdot_inplace(__nv_bfloat16* o, const __nv_bfloat16* dout, int rows, int H, cudaStream_t s);
 

@@ -123,7 +123,7 @@ def relative_position_bucket(rel, bidirectional, num_buckets=32, max_distance=12
     return ret + torch.where(is_small, rel, large)
 
 
-BUCKET_CENTER = 511
+BUCKET_CENTER = 2047  # offsets covered by the device bucket tables: text_maxlength and max_length up to 2048
 
 
 def bucket_table(bidirectional, num_buckets, max_distance):

@@ -71,11 +71,13 @@ def attn_keep_words(seed, step, site, group4, p):
 
 
 def attn_keep_mask(seed, step, site, P, H, L, p):
-    """bool numpy array [P, H, L, 256]: keep decision of every (passage, head, query, key), keys beyond L included
-    (key j of chunk c is bit (j >> 1) + 16 (j & 1) of that chunk's word)."""
+    """bool numpy array [P, H, L, 32 * nch]: keep decision of every (passage, head, query, key), keys beyond L included
+    (key j of chunk c is bit (j >> 1) + 16 (j & 1) of that chunk's word).  nch = max(8, ceil(L / 32)) chunks per query row
+    -- 8 for the single-tile kernels (L <= 256), more for the tiled path (csrc/enc_attn_long.cu enc_attn_keep_stride)."""
+    nch = max(8, (L + 31) // 32)
     rows = np.arange(P * H * L, dtype=np.uint64).reshape(P, H, L, 1)
-    chunks = np.arange(8, dtype=np.uint64).reshape(1, 1, 1, 8)
-    words = attn_keep_words(seed, step, site, rows * np.uint64(32) + chunks * np.uint64(4), p)  # [P, H, L, 8]
+    chunks = np.arange(nch, dtype=np.uint64).reshape(1, 1, 1, nch)
+    words = attn_keep_words(seed, step, site, rows * np.uint64(4 * nch) + chunks * np.uint64(4), p)  # [P, H, L, nch]
     j = np.arange(32)
     bit = (j >> 1) + 16 * (j & 1)
-    return ((words[..., None] >> bit.astype(np.uint32)) & np.uint32(1)).astype(bool).reshape(P, H, L, 256)
+    return ((words[..., None] >> bit.astype(np.uint32)) & np.uint32(1)).astype(bool).reshape(P, H, L, 32 * nch)

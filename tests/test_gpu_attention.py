@@ -4,6 +4,8 @@ import ctypes
 import pytest
 import torch
 
+from lako_b200.model import BUCKET_CENTER as CENTER
+
 pytestmark = pytest.mark.gpu
 NEG = torch.finfo(torch.float32).min
 
@@ -13,7 +15,7 @@ def _nat():
     return nat
 
 
-def _bias_lut(nat, table, buckets, H, L, center=511):
+def _bias_lut(nat, table, buckets, H, L, center=CENTER):
     lut = torch.empty(H, 2 * L - 1, device="cuda")
     nat.check(nat.lib().lako_build_bias_lut(nat.ptr(table), nat.ptr(buckets), nat.ptr(lut), H, L, center,
                                             nat.stream_ptr()))
@@ -24,6 +26,18 @@ def _bias_lut(nat, table, buckets, H, L, center=511):
 @pytest.mark.parametrize("P,L,H", [(3, 64, 2), (4, 200, 3), (2, 250, 2), (2, 256, 1), (5, 40, 2), (2, 130, 4), (40, 250, 16)])
 def test_enc_attn_fwd_bwd(P, L, H, impl):
     """impl 2 = persistent warp-specialised forward with P in tensor memory (default), 1 = round 1's one-shot kernel."""
+    _enc_attn_fwd_bwd(P, L, H, impl)
+
+
+@pytest.mark.parametrize("P,L,H,impl", [(2, 300, 2, 2), (2, 512, 3, 2), (1, 700, 1, 2), (2, 1100, 1, 2), (3, 257, 2, 2),
+                                        (3, 200, 2, 3), (2, 64, 1, 3), (2, 130, 4, 3), (5, 40, 2, 3)])
+def test_enc_attn_fwd_bwd_any_length(P, L, H, impl):
+    """The reference takes any --text_maxlength (src/options.py:60): passages longer than 256 tokens go through the tiled
+    kernels of csrc/enc_attn_long.cu (impl 3 forces that path at lengths the tensor-memory kernels also serve)."""
+    _enc_attn_fwd_bwd(P, L, H, impl)
+
+
+def _enc_attn_fwd_bwd(P, L, H, impl):
     nat = _nat()
     lib = nat.lib()
     lib.lako_set_attn_impl(impl)
@@ -51,14 +65,14 @@ def test_enc_attn_fwd_bwd(P, L, H, impl):
     q, k, v = x[:, :, 0].transpose(1, 2), x[:, :, 1].transpose(1, 2), x[:, :, 2].transpose(1, 2)
     tab = table.clone().requires_grad_(True)
     rel = torch.arange(L, device="cuda")[None, :] - torch.arange(L, device="cuda")[:, None]
-    bias = tab[buckets[rel + 511].long()].permute(2, 0, 1)[None]
+    bias = tab[buckets[rel + CENTER].long()].permute(2, 0, 1)[None]
     add = torch.zeros(P, 1, 1, L, device="cuda").masked_fill(~mask[:, None, None, :], NEG)
     s = q @ k.transpose(-1, -2) + (bias + add)
     pr = torch.softmax(s, dim=-1)
     ref = (pr @ v).transpose(1, 2).reshape(P * L, inner)
     assert torch.allclose(out.float(), ref, atol=3e-2, rtol=3e-2), (out.float() - ref).abs().max().item()
     assert torch.allclose(lse, torch.logsumexp(s, dim=-1), atol=2e-3, rtol=1e-4)
-    lib.lako_set_attn_impl(2)
+    lib.lako_set_attn_impl(3 if impl == 3 else 2)
     # backward
     dout = (torch.randn(P * L, inner, device="cuda") * 0.5).to(torch.bfloat16)
     ref.backward(dout.float())
@@ -68,18 +82,21 @@ def test_enc_attn_fwd_bwd(P, L, H, impl):
     nat.check(lib.lako_enc_attn_bwd(nat.ptr(qkv), nat.ptr(out), nat.ptr(dout), nat.ptr(lse), nat.ptr(mask), nat.ptr(lut),
                                     nat.ptr(dqkv), nat.ptr(dlut), P, L, H, nat.stream_ptr()))
     dtab = torch.zeros(32, H, device="cuda")
-    nat.check(lib.lako_fold_dlut(nat.ptr(dlut), nat.ptr(buckets), nat.ptr(dtab), H, L, 511, 32, nat.stream_ptr()))
+    nat.check(lib.lako_fold_dlut(nat.ptr(dlut), nat.ptr(buckets), nat.ptr(dtab), H, L, CENTER, 32, nat.stream_ptr()))
     torch.cuda.synchronize()
     gref = x.grad.reshape(P * L, 3 * inner)
     scale = gref.abs().max().item()
     err = (dqkv.float() - gref).abs().max().item()
     assert err < 0.03 * scale + 1e-3, (err, scale)
     terr = (dtab - tab.grad).abs().max().item()
+    lib.lako_set_attn_impl(2)
     assert terr < 0.02 * tab.grad.abs().max().item() + 1e-2, (terr, tab.grad.abs().max().item())
 
 
-@pytest.mark.parametrize("impl", [2, 1])
-@pytest.mark.parametrize("P,L,H,with_mask", [(3, 250, 2, False), (2, 100, 3, True), (2, 256, 1, False)])
+@pytest.mark.parametrize("P,L,H,with_mask,impl", [(3, 250, 2, False, 2), (2, 100, 3, True, 2), (2, 256, 1, False, 2),
+                                                  (3, 250, 2, False, 1), (2, 100, 3, True, 1), (2, 256, 1, False, 1),
+                                                  (2, 100, 3, True, 3), (2, 250, 2, False, 3), (2, 300, 2, True, 2),
+                                                  (1, 520, 1, False, 2)])
 def test_enc_attn_dropout_matches_host_mask(P, L, H, with_mask, impl):
     """Dropout on the attention probabilities (HF:332): the keep words the forward saves equal the host restatement
     (lako_b200/philox.py attn_keep_mask) bit for bit, the output equals softmax * mask / (1 - p) @ v in torch, and the
@@ -108,21 +125,23 @@ def test_enc_attn_dropout_matches_host_mask(P, L, H, with_mask, impl):
     nat.check(lib.lako_enc_attn_fwd_dropout(nat.ptr(qkv), nat.ptr(mask), nat.ptr(lut), nat.ptr(out), nat.ptr(lse),
                                             nat.ptr(keep), P, L, H, *args))
     torch.cuda.synchronize()
-    lib.lako_set_attn_impl(2)
-    km = attn_keep_mask(seed, step, site, P, H, L, pdrop)                       # [P, H, L, 256] bool
-    got = keep.cpu().numpy().view(np.uint32)
-    j = np.arange(32)
-    bit = ((j >> 1) + 16 * (j & 1)).astype(np.uint32)
-    got_mask = ((got[..., None] >> bit) & 1).astype(bool).reshape(P, H, L, 256)
-    nch = (L + 31) // 32                                                        # chunks the kernels touch
-    assert (got_mask[..., :nch * 32] == km[..., :nch * 32]).all()
+    tiled = impl == 3 or L > 256      # csrc/enc_attn_long.cu: saves no keep words, its backward regenerates them
+    lib.lako_set_attn_impl(3 if tiled else 2)
+    km = attn_keep_mask(seed, step, site, P, H, L, pdrop)                       # [P, H, L, 32 * max(8, ceil(L/32))] bool
+    if not tiled:
+        got = keep.cpu().numpy().view(np.uint32)
+        j = np.arange(32)
+        bit = ((j >> 1) + 16 * (j & 1)).astype(np.uint32)
+        got_mask = ((got[..., None] >> bit) & 1).astype(bool).reshape(P, H, L, 256)
+        nch = (L + 31) // 32                                                    # chunks the kernels touch
+        assert (got_mask[..., :nch * 32] == km[..., :nch * 32]).all()
     assert abs(km[..., :L].mean() - (1 - pdrop)) < 5e-3
     keep_t = torch.from_numpy(km[..., :L]).cuda()
     x = qkv.float().view(P, L, 3, H, 64).requires_grad_(True)
     q, k, v = x[:, :, 0].transpose(1, 2), x[:, :, 1].transpose(1, 2), x[:, :, 2].transpose(1, 2)
     tab = table.clone().requires_grad_(True)
     rel = torch.arange(L, device="cuda")[None, :] - torch.arange(L, device="cuda")[:, None]
-    bias = tab[buckets[rel + 511].long()].permute(2, 0, 1)[None]
+    bias = tab[buckets[rel + CENTER].long()].permute(2, 0, 1)[None]
     s = q @ k.transpose(-1, -2) + bias
     if with_mask:
         s = s + torch.zeros(P, 1, 1, L, device="cuda").masked_fill(~mask[:, None, None, :], NEG)
@@ -132,7 +151,7 @@ def test_enc_attn_dropout_matches_host_mask(P, L, H, with_mask, impl):
     dout = (torch.randn(P * L, inner, device="cuda") * 0.5).to(torch.bfloat16)
     ref.backward(dout.float())
     gref = x.grad.reshape(P * L, 3 * inner)
-    for saved in (keep, None):
+    for saved in ((None,) if tiled else (keep, None)):
         dqkv = torch.zeros_like(qkv)
         dlut = torch.zeros(H, 2 * L - 1, device="cuda")
         nat.check(lib.lako_enc_attn_bwd_dropout(nat.ptr(qkv), nat.ptr(out), nat.ptr(dout), nat.ptr(lse), nat.ptr(mask),
@@ -141,6 +160,7 @@ def test_enc_attn_dropout_matches_host_mask(P, L, H, with_mask, impl):
         scale = gref.abs().max().item()
         err = (dqkv.float() - gref).abs().max().item()
         assert err < 0.03 * scale + 1e-3, (err, scale, saved is None)
+    lib.lako_set_attn_impl(2)
 
 
 @pytest.mark.parametrize("B,T,M,H,nl", [(2, 6, 96, 2, 2), (3, 10, 500, 3, 1), (1, 1, 333, 2, 2), (2, 20, 2000, 12, 1), (2, 40, 300, 2, 1), (1, 64, 129, 1, 1)])
@@ -209,7 +229,7 @@ def test_dself_fwd_bwd(B, T, H):
     q, k, v = x[:, :, 0].transpose(1, 2), x[:, :, 1].transpose(1, 2), x[:, :, 2].transpose(1, 2)
     tab = table.clone().requires_grad_(True)
     rel = torch.arange(T, device="cuda")[None, :] - torch.arange(T, device="cuda")[:, None]
-    bias = tab[buckets[rel + 511].long()].permute(2, 0, 1)[None]
+    bias = tab[buckets[rel + CENTER].long()].permute(2, 0, 1)[None]
     causal = torch.zeros(T, T, device="cuda").masked_fill(rel > 0, NEG)
     s = q @ k.transpose(-1, -2) + (bias + causal)
     pr = torch.softmax(s, dim=-1)
@@ -223,7 +243,7 @@ def test_dself_fwd_bwd(B, T, H):
     nat.check(lib.lako_dself_bwd(nat.ptr(qkv), nat.ptr(dout), nat.ptr(probs), nat.ptr(dqkv), nat.ptr(dlut), B, T, H,
                                  nat.stream_ptr()))
     dtab = torch.zeros(32, H, device="cuda")
-    nat.check(lib.lako_fold_dlut(nat.ptr(dlut), nat.ptr(buckets), nat.ptr(dtab), H, T, 511, 32, nat.stream_ptr()))
+    nat.check(lib.lako_fold_dlut(nat.ptr(dlut), nat.ptr(buckets), nat.ptr(dtab), H, T, CENTER, 32, nat.stream_ptr()))
     torch.cuda.synchronize()
     g = x.grad.reshape(B * T, 3 * inner)
     assert (dqkv.float() - g).abs().max().item() < 0.02 * g.abs().max().item() + 1e-3

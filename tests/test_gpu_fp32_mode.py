@@ -9,6 +9,8 @@ import types
 import pytest
 import torch
 
+from lako_b200.model import BUCKET_CENTER as CENTER
+
 pytestmark = pytest.mark.gpu
 c_int, c_float = ctypes.c_int, ctypes.c_float
 NEG = torch.finfo(torch.float32).min
@@ -71,7 +73,7 @@ def test_fp32_attention_kernels_vs_torch():
     table = torch.randn(32, H, device="cuda")
     buckets = bucket_table(True, 32, 128).cuda()
     lut = torch.empty(H, 2 * L - 1, device="cuda")
-    nat.check(lib.lako_build_bias_lut(nat.ptr(table), nat.ptr(buckets), nat.ptr(lut), H, L, 511, nat.stream_ptr()))
+    nat.check(lib.lako_build_bias_lut(nat.ptr(table), nat.ptr(buckets), nat.ptr(lut), H, L, CENTER, nat.stream_ptr()))
     out = torch.zeros(rows, inner, device="cuda")
     hi, lo = torch.zeros_like(out), torch.zeros_like(out)
     cu_d = cu.cuda()
@@ -83,7 +85,7 @@ def test_fp32_attention_kernels_vs_torch():
         x = qkv[r0:r0 + n].view(n, 3, H, 64)
         q, k, v = x[:, 0].transpose(0, 1), x[:, 1].transpose(0, 1), x[:, 2].transpose(0, 1)
         rel = torch.arange(n, device="cuda")[None, :] - torch.arange(n, device="cuda")[:, None]
-        bias = table[buckets[rel + 511].long()].permute(2, 0, 1)
+        bias = table[buckets[rel + CENTER].long()].permute(2, 0, 1)
         ref = (torch.softmax(q @ k.transpose(-1, -2) + bias, -1) @ v).transpose(0, 1).reshape(n, inner)
         assert (out[r0:r0 + n] - ref).abs().max().item() < 2e-5
     assert (out - hi - lo).abs().max().item() < 1e-6
@@ -96,7 +98,7 @@ def test_fp32_attention_kernels_vs_torch():
     x = qkv2.view(P, L, 3, H, 64)
     q, k, v = x[:, :, 0].transpose(1, 2), x[:, :, 1].transpose(1, 2), x[:, :, 2].transpose(1, 2)
     rel = torch.arange(L, device="cuda")[None, :] - torch.arange(L, device="cuda")[:, None]
-    bias = table[buckets[rel + 511].long()].permute(2, 0, 1)[None]
+    bias = table[buckets[rel + CENTER].long()].permute(2, 0, 1)[None]
     add = torch.zeros(P, 1, 1, L, device="cuda").masked_fill(~mask[:, None, None, :], NEG)
     ref = (torch.softmax(q @ k.transpose(-1, -2) + bias + add, -1) @ v).transpose(1, 2).reshape(P * L, inner)
     assert (out2 - ref).abs().max().item() < 2e-5

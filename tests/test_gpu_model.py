@@ -175,6 +175,42 @@ def test_all_padding_passage_and_oracle():
     assert ((res[True][2] - res[False][2]).norm() / res[False][2].norm()).item() < 0.05
 
 
+@pytest.mark.parametrize("L", [300, 520])
+def test_passages_longer_than_256_tokens_vs_oracle(L):
+    """--text_maxlength is free in the reference (src/options.py:60).  Above 256 tokens the encoder attention runs the
+    tiled kernels of csrc/enc_attn_long.cu: loss / logits / greedy tokens / token scores against the fp32 oracle, the
+    packed and padded executions against each other in gradients, and (dropout on) a finite training step."""
+    from oracle import fidt5_oracle as O
+    c, cfg, sd, model = _load(GOLDEN[0])
+    ids, mask, labels = O.synth_batch(2, 2, L, 6, cfg.vocab, seed=L)
+    with torch.no_grad():
+        ref_loss, ref_logits = O.fidt5_forward(sd, cfg, ids, mask, labels)[:2]
+    res = {}
+    for unpad in (True, False):
+        model.unpad = unpad
+        model.train()          # dropout_rate is 0 in this config
+        model.zero_grad()
+        loss, logits = model(input_ids=ids.cuda(), attention_mask=mask.cuda(), labels=labels.cuda())
+        loss.backward()
+        torch.cuda.synchronize()
+        assert bool(torch.isfinite(model._flat_grad).all())
+        res[unpad] = (logits.detach().float().cpu(), model._flat_grad.clone())
+        assert abs(loss.item() - float(ref_loss)) < 5e-3, (unpad, loss.item(), float(ref_loss))
+        assert (res[unpad][0] - ref_logits.reshape(res[unpad][0].shape)).abs().max().item() < LOGIT_ATOL_BF16
+    model.unpad = True
+    assert ((res[True][1] - res[False][1]).norm() / res[False][1].norm()).item() < 0.05
+    model.eval()
+    model.overwrite_forward_crossattention()
+    model.reset_score_storage()
+    out = model.generate(input_ids=ids.cuda(), attention_mask=mask.cuda(), max_length=8)
+    ref_out, storage = O.fidt5_generate(sd, cfg, ids, mask, 8, capture_scores=True)
+    assert out.cpu().tolist() == ref_out.tolist()
+    tok, _ = model.token_scores(last_half=False)
+    ref_tok, _ = O.token_scores_from_storage(storage, mask, last_half=False)
+    B, N, _ = ids.shape
+    assert (tok.cpu().view(B, N, L) - ref_tok.view(B, N, L)).abs().max().item() < SCORE_RTOL * ref_tok.abs().max().item()
+
+
 def test_host_passage_lengths_skip_the_readback():
     """Passing the Collator's host-side prefix lengths gives the same step as letting forward() read them back."""
     c, cfg, sd, model = _load(GOLDEN[0])

@@ -5,6 +5,7 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from lako_b200 import _native as nat
+from lako_b200.model import BUCKET_CENTER as CENTER
 from lako_b200.model import bucket_table
 lib = nat.lib()
 P, L, H = (int(x) for x in (sys.argv[1:4] if len(sys.argv) > 3 else (160, 250, 16)))
@@ -13,7 +14,7 @@ torch.manual_seed(0)
 qkv = (torch.randn(Mt, 3 * inner, device="cuda") * 0.5).to(torch.bfloat16)
 table = torch.randn(32, H, device="cuda"); buckets = bucket_table(True, 32, 128).cuda()
 lut = torch.empty(H, 2 * L - 1, device="cuda")
-nat.check(lib.lako_build_bias_lut(nat.ptr(table), nat.ptr(buckets), nat.ptr(lut), H, L, 511, nat.stream_ptr()))
+nat.check(lib.lako_build_bias_lut(nat.ptr(table), nat.ptr(buckets), nat.ptr(lut), H, L, CENTER, nat.stream_ptr()))
 out = torch.zeros(Mt, inner, device="cuda", dtype=torch.bfloat16); lse = torch.zeros(P, H, L, device="cuda")
 dout = (torch.randn(Mt, inner, device="cuda") * 0.1).to(torch.bfloat16)
 dqkv = torch.zeros_like(qkv); dlut = torch.zeros(H, 2 * L - 1, device="cuda")

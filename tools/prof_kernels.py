@@ -11,7 +11,7 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from lako_b200 import _native as nat  # noqa: E402
-from lako_b200.model import bucket_table  # noqa: E402
+from lako_b200.model import BUCKET_CENTER as CENTER, bucket_table  # noqa: E402
 
 which = sys.argv[1] if len(sys.argv) > 1 else "all"
 lib = nat.lib()
@@ -31,7 +31,7 @@ if which in ("all", "attn"):
     table = torch.randn(32, H, device="cuda")
     buckets = bucket_table(True, 32, 128).cuda()
     lut = torch.empty(H, 2 * L - 1, device="cuda")
-    nat.check(lib.lako_build_bias_lut(nat.ptr(table), nat.ptr(buckets), nat.ptr(lut), H, L, 511, nat.stream_ptr()))
+    nat.check(lib.lako_build_bias_lut(nat.ptr(table), nat.ptr(buckets), nat.ptr(lut), H, L, CENTER, nat.stream_ptr()))
     out = torch.zeros(Mt, inner, device="cuda", dtype=torch.bfloat16)
     lse = torch.zeros(P, H, L, device="cuda")
     dout = bf(Mt, inner)
