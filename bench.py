@@ -318,6 +318,9 @@ def main():
                     "also quoted at N = 100)")
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"],
                     help="evaluation workloads only: fp32 = 3xTF32 GEMMs + fp32 attention (the mode that meets 1e-4 / 1e-2)")
+    ap.add_argument("--use-checkpoint", action="store_true",
+                    help="training workloads: model.set_checkpoint(True) (the reference's --use_checkpoint): encoder "
+                         "activations recomputed in backward")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip generate / gpu_eager_baseline probes")
@@ -380,6 +383,7 @@ def main():
         return
 
     model.train()
+    model.set_checkpoint(args.use_checkpoint)
     opt = FusedAdamW(model, lr=1e-4, weight_decay=1e-4, clip=1.0, shard=True)
     n_batches = 4  # rotate distinct synthetic batches
     host = synth_host_batches(B, N, L, T, rank, n_batches)
@@ -575,7 +579,8 @@ def main():
                        "global_batch": world * B, "parallelism": f"dp{world}",
                        "inputs": "ids / masks / labels + the Collator's host-side passage lengths",
                        "l2": "step working set (>4 GB of activations) far exceeds the 126 MB L2; batches rotate; no explicit flush",
-                       "emb_std": EMB_STD},
+                       "emb_std": EMB_STD, "use_checkpoint": bool(args.use_checkpoint),
+                       "peak_mem_gb": round(torch.cuda.max_memory_allocated() / 1e9, 1)},
             # algorithmic = SURVEY 8(d)'s dense count on the padded shapes (what the reference's own path computes);
             # executed = the same formula on the valid tokens only (the packed execution skips the pad rows).  The
             # tensor-pipe utilisation claim is the EXECUTED figure.

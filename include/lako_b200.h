@@ -194,11 +194,17 @@ typedef struct {
    * master weights + fp32 attention kernels; forward (mode 0) and generate only -- the reference is fp32-only
    * (train_reader.py:67) and north_star's 1e-4 logit tolerance is stated for this mode. */
   int precision;
+  /* 1 (training, mode 1, and the matching lako_fidt5_backward): recompute the encoder layers' activations in backward
+   * instead of keeping them -- the reference's CheckpointWrapper (src/model.py:236-284, --use_checkpoint).  Per layer
+   * only the fp32 layer input stays resident (4 d bytes per token instead of ~29 d); backward re-runs each layer's
+   * forward (minus its last GEMM) from it, with the same Philox dropout masks, so gradients are those of recompute = 0.
+   * Size the workspace with lako_fidt5_workspace_bytes(..., mode = 3). */
+  int recompute;
 } lako_batch;
 
 int lako_fidt5_layout(const lako_dims* dims, lako_layout* out);
 /* mode 0 = forward only (eval loss), 1 = training (keeps activations for lako_fidt5_backward), 2 = forward only with
- * lako_batch.precision = 1 (fp32) */
+ * lako_batch.precision = 1 (fp32), 3 = training with lako_batch.recompute = 1 (a size query only: the calls take mode 1) */
 size_t lako_fidt5_workspace_bytes(const lako_dims* dims, int B, int N, int L, int T, int mode);
 /* FiDT5.forward (src/model.py:39-51) + T5 loss (HF:1105-1117) */
 int lako_fidt5_forward(const lako_fidt5* m, const lako_batch* b, int mode, void* stream);

@@ -97,6 +97,7 @@ struct Work {
   std::vector<DecGrad> dg;
   // sizes
   int B, N, L, T, P, M, Mtok, BT;
+  bool recompute;  // mode 3: encoder activations are recomputed layer by layer in backward
   // packed (un-padded) execution: Mrows = number of token rows actually processed
   int Mrows;
   const int* cu;
@@ -128,28 +129,43 @@ void carve(const lako_dims& dm, int B, int N, int L, int T, int mode, void* base
   w.P = B * N; w.M = N * L; w.Mtok = B * N * L; w.BT = B * T;
   const size_t Mt = w.Mtok, BT = w.BT;
   Bump b(base);
-  const bool train = mode == 1;
-  const int nX = train ? 2 * nl + 1 : 2;
+  // mode 3: training with the encoder layers' activations recomputed in backward (the reference's CheckpointWrapper,
+  // src/model.py:236-284 under --use_checkpoint): per layer only its fp32 input X[2l] is kept; everything else a layer's
+  // backward reads lives in ONE set of buffers that enc_layer_recompute() refills from X[2l] just before that backward
+  const bool recompute = mode == 3;
+  const bool train = mode == 1 || recompute;
+  w.recompute = recompute;
   w.X.resize(2 * nl + 1);
-  {
+  if (recompute) {
+    float* odd = b.take<float>(Mt * d);  // X[2l+1] (residual stream between a layer's two sub-blocks) is recomputed too
+    for (int i = 0; i <= 2 * nl; ++i) w.X[i] = (i & 1) ? odd : b.take<float>(Mt * d);
+  } else {
+    const int nX = train ? 2 * nl + 1 : 2;
     std::vector<float*> bufs(nX);
     for (int i = 0; i < nX; ++i) bufs[i] = b.take<float>(Mt * d);
     for (int i = 0; i <= 2 * nl; ++i) w.X[i] = bufs[train ? i : (i & 1)];
   }
   w.enc.resize(nl);
   EncLayerAct shared_e{};
-  if (!train) {
+  if (!train || recompute) {
     shared_e.n_a = b.take<bf16>(Mt * d);
     shared_e.qkv = b.take<bf16>(Mt * 3 * inner);
     shared_e.ao = b.take<bf16>(Mt * inner);
-    shared_e.n_f = shared_e.n_a;
+    shared_e.n_f = recompute ? b.take<bf16>(Mt * d) : shared_e.n_a;
     shared_e.h = b.take<bf16>(Mt * ff);
     shared_e.lse = nullptr;
     shared_e.akeep = nullptr;
     shared_e.rstd_a = shared_e.rstd_f = nullptr;
+    if (recompute) {
+      shared_e.hbits = b.take<unsigned char>(Mt * ff / 8);
+      shared_e.lse = b.take<float>(static_cast<size_t>(w.P) * H * L);
+      shared_e.akeep = L <= 256 ? b.take<uint32_t>(static_cast<size_t>(w.P) * H * L * 8) : nullptr;
+      shared_e.rstd_a = b.take<float>(Mt);
+      shared_e.rstd_f = b.take<float>(Mt);
+    }
   }
   for (int l = 0; l < nl; ++l) {
-    if (!train) {
+    if (!train || recompute) {
       w.enc[l] = shared_e;
       continue;
     }
@@ -344,6 +360,28 @@ int make_ptrs(const lako_fidt5* m, Ptrs& p) {
   return LAKO_OK;
 }
 
+// One encoder layer from its normed input n_a (already in place) up to the ReLU output h: q|k|v, self-attention, o-projection,
+// residual + second norm, wi + ReLU (+ dropout).  Shared by the forward pass and by the recompute of mode 3.
+int enc_layer_body(const Ptrs& p, Work& w, int l, const unsigned char* amask, cudaStream_t s, const Dropper& dr) {
+  const int d = p.d, inner = p.inner, ff = p.ff, Mt = w.Mrows;
+  EncLayerAct& a = w.enc[l];
+  RC(lin_fwd(a.n_a, p.wb + p.lo.enc_qkv[l], a.qkv, Mt, 3 * inner, d, EPI_BF16, 1.f, s));
+  RC(enc_attn_fwd(a.qkv, amask, w.lut_enc, a.ao, a.lse, w.P, w.L, p.H, s, dr(l, E_ATTN), w.cu, Mt, a.akeep));
+  RC(lin_fwd(a.ao, p.wb + p.lo.enc_o[l], w.delta_enc, Mt, d, inner, EPI_BF16, 1.f, s));
+  RC(rmsnorm_fwd(w.X[2 * l], w.delta_enc, w.X[2 * l + 1], p.wf + p.lo.enc_ln1[l], a.n_f, a.rstd_f, Mt, d, p.eps, 1.f, s,
+                 dr(l, E_O)));
+  RC(lin_fwd(a.n_f, p.wb + p.lo.enc_wi[l], a.h, Mt, ff, d, EPI_BF16_RELU, 1.f, s, dr(l, E_RELU), a.hbits));
+  return LAKO_OK;
+}
+// mode 3 (CheckpointWrapper): refill the shared activation buffers with layer l's forward from its saved input X[2l].
+// The dropout masks are functions of (seed, step, site, element), so the recomputed activations are the forward's, bit
+// for bit; the layer's wo GEMM is not repeated (its output only fed X[2l+2], which is saved).
+int enc_layer_recompute(const Ptrs& p, Work& w, int l, const unsigned char* amask, cudaStream_t s, const Dropper& dr) {
+  EncLayerAct& a = w.enc[l];
+  RC(rmsnorm_fwd(w.X[2 * l], nullptr, nullptr, p.wf + p.lo.enc_ln0[l], a.n_a, a.rstd_a, w.Mrows, p.d, p.eps, 1.f, s));
+  return enc_layer_body(p, w, l, amask, s, dr);
+}
+
 // ---- encoder: ids (P*L) -> mem bf16 [Mtok][d] and kv_all bf16 [Mtok][nl*2*inner]
 int encode(const Ptrs& p, const lako_fidt5* m, Work& w, const long long* ids, const unsigned char* mask, bool train,
            cudaStream_t s, const Dropper& dr, bool kv_head_major = false) {
@@ -359,12 +397,7 @@ int encode(const Ptrs& p, const lako_fidt5* m, Work& w, const long long* ids, co
     else
       RC(rmsnorm_fwd(w.X[2 * l - 1], w.delta_enc, w.X[2 * l], p.wf + p.lo.enc_ln0[l], a.n_a, a.rstd_a, Mt, d, p.eps,
                      1.f, s, dr(l - 1, E_FF)));
-    RC(lin_fwd(a.n_a, p.wb + p.lo.enc_qkv[l], a.qkv, Mt, 3 * inner, d, EPI_BF16, 1.f, s));
-    RC(enc_attn_fwd(a.qkv, amask, w.lut_enc, a.ao, a.lse, w.P, w.L, p.H, s, dr(l, E_ATTN), w.cu, Mt, a.akeep));
-    RC(lin_fwd(a.ao, p.wb + p.lo.enc_o[l], w.delta_enc, Mt, d, inner, EPI_BF16, 1.f, s));
-    RC(rmsnorm_fwd(w.X[2 * l], w.delta_enc, w.X[2 * l + 1], p.wf + p.lo.enc_ln1[l], a.n_f, a.rstd_f, Mt, d, p.eps, 1.f,
-                   s, dr(l, E_O)));
-    RC(lin_fwd(a.n_f, p.wb + p.lo.enc_wi[l], a.h, Mt, ff, d, EPI_BF16_RELU, 1.f, s, dr(l, E_RELU), a.hbits));
+    RC(enc_layer_body(p, w, l, amask, s, dr));
     RC(lin_fwd(a.h, p.wb + p.lo.enc_wo[l], w.delta_enc, Mt, d, ff, EPI_BF16, 1.f, s));
   }
   RC(rmsnorm_fwd(w.X[2 * nl - 1], w.delta_enc, w.X[2 * nl], p.wf + p.lo.enc_final_ln, w.mem, w.rstd_enc_final, Mt, d,
@@ -409,10 +442,12 @@ extern "C" int lako_fidt5_forward(const lako_fidt5* m, const lako_batch* bt, int
   // to +-bucket_center
   LAKO_REQUIRE(bt->T >= 1 && bt->T <= 64 && bt->L >= 1 && bt->L <= ENC_ATTN_LONG_MAX_L && bt->L - 1 <= m->bucket_center,
                LAKO_ERR_UNSUPPORTED);
+  LAKO_REQUIRE(mode == 0 || mode == 1, LAKO_ERR_BAD_ARG);
+  if (mode == 1 && bt->recompute) mode = 3;  // same pass, smaller activation footprint (see carve)
   Work w;
   carve(m->dims, bt->B, bt->N, bt->L, bt->T, mode, bt->workspace, w);
   LAKO_REQUIRE(w.bytes <= bt->workspace_bytes, LAKO_ERR_WORKSPACE);
-  const bool train = mode == 1;
+  const bool train = mode == 1 || mode == 3;
   const int d = p.d, inner = p.inner, ff = p.ff, nl = p.nl, BT = w.BT;
   Dropper dr{bt->dropout_seed, bt->dropout_step, train ? bt->dropout_p : 0.f};
   LAKO_REQUIRE(dr.p >= 0.f && dr.p < 0.9f, LAKO_ERR_BAD_ARG);
@@ -503,7 +538,7 @@ extern "C" int lako_fidt5_backward(const lako_fidt5* m, const lako_batch* bt, co
   RC(make_ptrs(m, p));
   LAKO_REQUIRE(p.g != nullptr && bt && bt->workspace, LAKO_ERR_BAD_ARG);
   Work w;
-  carve(m->dims, bt->B, bt->N, bt->L, bt->T, 1, bt->workspace, w);
+  carve(m->dims, bt->B, bt->N, bt->L, bt->T, bt->recompute ? 3 : 1, bt->workspace, w);
   LAKO_REQUIRE(w.bytes <= bt->workspace_bytes, LAKO_ERR_WORKSPACE);
   RC(set_packing(w, bt, s));
   const unsigned char* xmask = w.cu ? nullptr : bt->mask;
@@ -585,6 +620,7 @@ extern "C" int lako_fidt5_backward(const lako_fidt5* m, const lako_batch* bt, co
   // ---- encoder layers
   for (int l = nl - 1; l >= 0; --l) {
     EncLayerAct& a = w.enc[l];
+    if (w.recompute) RC(enc_layer_recompute(p, w, l, xmask, s, dr));
     RC(lin_dgrad(w.dres_enc_b, p.wb + p.lo.enc_wo[l], w.dh_enc, Mt, d, ff, a.hbits, dsc, s));
     RC(lin_wgrad(w.dres_enc_b, a.h, g + p.lo.enc_wo[l], Mt, d, ff, 1.f, s));
     RC(lin_dgrad(w.dh_enc, p.wb + p.lo.enc_wi[l], w.dn_enc, Mt, ff, d, nullptr, 1.f, s));

@@ -61,7 +61,7 @@ class _Batch(ctypes.Structure):
                 ("logits", ctypes.c_void_p), ("stats", ctypes.c_void_p), ("count_is_set", ctypes.c_int),
                 ("dropout_p", ctypes.c_float), ("dropout_step", ctypes.c_uint), ("dropout_seed", ctypes.c_ulonglong),
                 ("cu_seqlens", ctypes.c_void_p), ("packed_tokens", ctypes.c_int), ("stage_events", ctypes.c_void_p),
-                ("labels_are_decoder_ids", ctypes.c_int), ("precision", ctypes.c_int)]
+                ("labels_are_decoder_ids", ctypes.c_int), ("precision", ctypes.c_int), ("recompute", ctypes.c_int)]
 
 
 class FiDT5Config:
@@ -402,9 +402,11 @@ class FiDT5(nn.Module):
         self.load_state_dict({self._t5_to_fid_key(k): v for k, v in state_dict.items()})
 
     def set_checkpoint(self, use_checkpoint):
-        # Activation recompute is not needed at 180 GB HBM for the shipped shapes; the flag is kept for
-        # API parity (model.py:84-90) and has no numerical effect there either.
-        self.use_checkpoint = use_checkpoint
+        """model.py:84-90 (--use_checkpoint): recompute the encoder layers' activations in backward instead of keeping
+        them (lako_batch.recompute).  Same loss and gradients; ~7x less encoder activation memory for ~25 % more step
+        time.  Not needed at 180 GB for the reference's shapes (cfg4 trains in 45 GB); it is what lets N = 100 passages
+        at B = 8 train on one GPU."""
+        self.use_checkpoint = bool(use_checkpoint)
 
     def save_pretrained(self, path):
         os.makedirs(path, exist_ok=True)
@@ -615,8 +617,10 @@ class FiDT5(nn.Module):
             self._ensure_grad()
         L_ = nat.lib()
         L_.lako_fidt5_workspace_bytes.restype = ctypes.c_size_t
-        nbytes = L_.lako_fidt5_workspace_bytes(ctypes.byref(self._dims), B, N, L, T, 2 if prec == 1 else mode)
-        ws = self._workspace(("fwd", B, N, L, T, mode, prec), nbytes)
+        recompute = int(train and self.use_checkpoint)
+        nbytes = L_.lako_fidt5_workspace_bytes(ctypes.byref(self._dims), B, N, L, T,
+                                               2 if prec == 1 else (3 if recompute else mode))
+        ws = self._workspace(("fwd", B, N, L, T, mode, prec, recompute), nbytes)
         self._ws_gen += 1   # the workspace now holds THIS forward's activations (see _run_backward)
         logits = torch.empty(B, T, self.config.vocab_size, dtype=torch.float32, device=ids.device)
         stats = torch.zeros(2, dtype=torch.float32, device=ids.device)
@@ -634,14 +638,14 @@ class FiDT5(nn.Module):
         pack = (cu.data_ptr() if cu is not None else 0, packed)
         m = self._model_struct(with_grad=train, precision=prec)
         bt = _Batch(ids.data_ptr(), mask.data_ptr(), labels.data_ptr(), B, N, L, T, ws.data_ptr(), ws.numel(),
-                    logits.data_ptr(), stats.data_ptr(), count_is_set, *drop, *pack, 0, int(dec_given), prec)
+                    logits.data_ptr(), stats.data_ptr(), count_is_set, *drop, *pack, 0, int(dec_given), prec, recompute)
         nat.check(L_.lako_fidt5_forward(ctypes.byref(m), ctypes.byref(bt), mode, nat.stream_ptr()), "lako_fidt5_forward")
         if dec_given:
             return ReaderOutput(None, logits)
         loss = stats[0] / torch.clamp(stats[1], min=1.0)
         if train:
             keep = {"t": (ids, mask, labels, ws, logits, stats, (B, N, L, T), drop, cu, pack), "gen": self._ws_gen,
-                    "done": False}
+                    "done": False, "recompute": recompute}
             loss, logits = _LossFn.apply(self._anchor, self, keep, loss, logits)
         return ReaderOutput(loss, logits)
 
@@ -674,7 +678,7 @@ class FiDT5(nn.Module):
         m = self._model_struct(with_grad=True)
         stage = ctypes.cast(self._stage_handles, ctypes.c_void_p).value if self._stage_events is not None else 0
         bt = _Batch(ids.data_ptr(), mask.data_ptr(), labels.data_ptr(), B, N, L, T, ws.data_ptr(), ws.numel(),
-                    logits.data_ptr(), stats.data_ptr(), 1, *drop, *pack, stage, 0, 0)
+                    logits.data_ptr(), stats.data_ptr(), 1, *drop, *pack, stage, 0, 0, keep["recompute"])
         gl = grad_loss.detach().to(torch.float32).reshape(1).contiguous()
         nat.check(L_.lako_fidt5_backward(ctypes.byref(m), ctypes.byref(bt), nat.ptr(gl), nat.stream_ptr()),
                   "lako_fidt5_backward")

@@ -211,6 +211,41 @@ def test_passages_longer_than_256_tokens_vs_oracle(L):
     assert (tok.cpu().view(B, N, L) - ref_tok.view(B, N, L)).abs().max().item() < SCORE_RTOL * ref_tok.abs().max().item()
 
 
+@pytest.mark.parametrize("unpad", [True, False])
+def test_use_checkpoint_recomputes_encoder_activations(unpad):
+    """model.py:84-90 / CheckpointWrapper (src/model.py:236-284): with set_checkpoint(True) the encoder layers are re-run in
+    backward from their saved inputs.  Same loss, same gradients (dropout ON: the recomputed masks must be the forward's),
+    and a smaller activation workspace."""
+    import ctypes
+    from lako_b200 import _native as nat
+    c, cfg, sd, model = _load(GOLDEN[0])
+    model.config.dropout_rate = 0.1
+    model.unpad = unpad
+    model.train()
+    ids, mask, labels = c["ids"].cuda(), c["mask"].cuda(), c["labels"].cuda()
+    res = {}
+    for ckpt in (False, True):
+        model.set_checkpoint(ckpt)
+        model._drop_seed, model._drop_step = 1234, 0
+        model.zero_grad()
+        loss, logits = model(input_ids=ids, attention_mask=mask, labels=labels)
+        loss.backward()
+        torch.cuda.synchronize()
+        res[ckpt] = (loss.item(), logits.detach().clone(), model._flat_grad.clone())
+    model.set_checkpoint(False)
+    assert res[True][0] == res[False][0] and torch.equal(res[True][1], res[False][1])
+    g0, g1 = res[False][2], res[True][2]
+    assert bool(torch.isfinite(g1).all()) and g0.norm().item() > 0
+    assert ((g1 - g0).norm() / g0.norm()).item() < 1e-5      # split-K weight gradients add in a different order
+    B, N, L = c["ids"].shape
+    T = labels.size(1)
+    lib = nat.lib()
+    lib.lako_fidt5_workspace_bytes.restype = ctypes.c_size_t
+    full = lib.lako_fidt5_workspace_bytes(ctypes.byref(model._dims), B, N, L, T, 1)
+    small = lib.lako_fidt5_workspace_bytes(ctypes.byref(model._dims), B, N, L, T, 3)
+    assert small < full
+
+
 def test_host_passage_lengths_skip_the_readback():
     """Passing the Collator's host-side prefix lengths gives the same step as letting forward() read them back."""
     c, cfg, sd, model = _load(GOLDEN[0])
