@@ -58,7 +58,8 @@ class FusedAdamW:
     `shard=True` (or LAKO_DP_SHARD=1) opts into SHARDED mode: every gradient stage is REDUCE-SCATTERED while backward is
     still running, each rank clips + updates only its 1/world slice of every stage (fp32 master, moments) and the
     refreshed bf16 compute weights are ALL-GATHERED -- 6 B/parameter on the wire instead of the all-reduce's 8, and
-    1/world of the optimizer's HBM traffic.  The price: fp32 masters of foreign slices go stale, and
+    1/world of the optimizer's HBM traffic (the parameters the kernels read in fp32 -- shared embedding, norm gains, bias
+    tables -- are gathered in fp32, _index_fp32_reads).  The price: fp32 masters of the other foreign slices go stale, and
     `sync_master_weights()` -- a COLLECTIVE, also triggered by FiDT5.state_dict / save_pretrained and by anything that
     re-casts the masters -- must then be reached by EVERY rank (call it, or state_dict(), on all ranks before a
     main-rank-only save)."""
@@ -90,6 +91,36 @@ class FusedAdamW:
                 self._plan = shard_plan(ranges, self.world(), dist.get_rank(self.group))
                 if self._plan is not None:
                     model._master_sync = self.sync_master_weights
+                    self._index_fp32_reads()
+
+    def _index_fp32_reads(self):
+        """The kernels read three kinds of parameters from the fp32 MASTERS, not from the bf16 copy: the shared embedding
+        (embed_gather), every T5LayerNorm gain and the two relative-bias tables.  In sharded mode those must therefore be
+        current on every rank after each step, not only the bf16 weights: the embedding range is all-gathered in fp32
+        (and re-cast locally), the small vectors travel in one packed all-reduce (each rank contributes the elements it
+        owns, zeros elsewhere)."""
+        model = self.model
+        off, shape = model._specs["shared.weight"]
+        n = 1
+        for d in shape:
+            n *= d
+        self._emb_range = next(((lo, hi) for lo, hi, _, _ in self._plan if lo == off and hi == off + n), None)
+        if self._emb_range is None:
+            raise nat.LakoError("sharded optimizer: the shared embedding is not a gradient stage range of its own")
+        idx = []
+        for name, (o, shp) in model._specs.items():
+            if name.endswith("layer_norm.weight") or name.endswith("relative_attention_bias.weight"):
+                cnt = 1
+                for d in shp:
+                    cnt *= d
+                idx.append(torch.arange(o, o + cnt, dtype=torch.long))
+        idx = torch.cat(idx)
+        own = torch.zeros(idx.numel(), dtype=torch.bool)
+        for _, _, plo, phi in self._plan:
+            own |= (idx >= plo) & (idx < phi)
+        dev = model._flat.device
+        self._small_idx = idx.to(dev)
+        self._small_own = own.to(dev, torch.float32)
 
     def world(self):
         if dist.is_available() and dist.is_initialized():
@@ -178,8 +209,19 @@ class FusedAdamW:
         dist.all_reduce(self.sumsq, op=dist.ReduceOp.SUM, group=self.group)   # pieces are disjoint: global ||g||^2
         for lo, hi, plo, phi in self._plan:
             self._update_piece(plo, phi - plo, lr)
+        emb = getattr(self, "_emb_range", None)
         for lo, hi, plo, phi in self._plan:
-            self._all_gather(model._bf16, lo, hi, plo, phi)
+            if emb == (lo, hi):   # read in fp32 by embed_gather: gather the masters, re-cast the whole range locally
+                self._all_gather(model._flat, lo, hi, plo, phi)
+                nat.check(nat.lib().lako_cast_f32_to_bf16(nat.ptr(model._flat[lo:]), nat.ptr(model._bf16[lo:]),
+                                                          ctypes.c_size_t(hi - lo), nat.stream_ptr()), "lako_cast_f32_to_bf16")
+            else:
+                self._all_gather(model._bf16, lo, hi, plo, phi)
+        small = getattr(self, "_small_idx", None)
+        if small is not None:     # norm gains and bias tables, also read in fp32 (see _index_fp32_reads)
+            buf = model._flat[small] * self._small_own
+            dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=self.group)
+            model._flat.index_copy_(0, small, buf)
         self._masters_stale = True
 
     @torch.no_grad()
