@@ -200,6 +200,12 @@ typedef struct {
    * forward (minus its last GEMM) from it, with the same Philox dropout masks, so gradients are those of recompute = 0.
    * Size the workspace with lako_fidt5_workspace_bytes(..., mode = 3). */
   int recompute;
+  /* training forward only, optional: LAKO_N_GRAD_STAGES cudaEvent_t (entries may be NULL), indexed like stage_events,
+   * that the forward WAITS on before it first touches the weights of that range -- event 5 (shared embedding, norm
+   * gains, bias tables) before the embedding gather, events 4..1 before the first layer of that encoder group, event 0
+   * before the cross-K/V projection and the decoder.  Lets a sharded data-parallel optimizer all-gather the updated
+   * weights on another stream while the next forward is already running (lako_b200/optim.py). */
+  void* weight_events;
 } lako_batch;
 
 int lako_fidt5_layout(const lako_dims* dims, lako_layout* out);

@@ -60,6 +60,12 @@ extern "C" int lako_fidt5_layout(const lako_dims* dm, lako_layout* lo) {
   return LAKO_OK;
 }
 
+static inline int enc_group_begin(int nl, int k) {  // first layer of encoder group k (k = 0 is the TOP quarter)
+  const int gsz = (nl + 3) / 4;
+  const int lo = nl - (k + 1) * gsz;
+  return lo < 0 ? 0 : lo;
+}
+
 namespace {
 
 struct Bump {
@@ -384,14 +390,21 @@ int enc_layer_recompute(const Ptrs& p, Work& w, int l, const unsigned char* amas
 
 // ---- encoder: ids (P*L) -> mem bf16 [Mtok][d] and kv_all bf16 [Mtok][nl*2*inner]
 int encode(const Ptrs& p, const lako_fidt5* m, Work& w, const long long* ids, const unsigned char* mask, bool train,
-           cudaStream_t s, const Dropper& dr, bool kv_head_major = false) {
+           cudaStream_t s, const Dropper& dr, bool kv_head_major = false, const cudaEvent_t* wev = nullptr) {
   const int d = p.d, inner = p.inner, ff = p.ff, nl = p.nl, Mt = w.Mrows;
   const unsigned char* amask = w.cu ? nullptr : mask;  // packed rows are all valid tokens
+  // weight-ready events of an overlapped all-gather (lako_batch.weight_events): wait right before the first use
+  auto wait_w = [&](int stage) {
+    if (wev && wev[stage]) cudaStreamWaitEvent(s, wev[stage], 0);
+  };
   if (w.cu) RC(build_tok_index(w.cu, w.tok_index, w.P, w.L, s));
+  wait_w(5);
   RC(embed_gather(ids, p.wf + p.lo.shared, w.X[0], Mt, d, p.V, s, dr(0, E_EMB), w.cu ? w.tok_index : nullptr));
   RC(build_bias_lut(p.wf + p.lo.enc_relbias, m->enc_buckets, w.lut_enc, p.H, w.L, m->bucket_center, s));
   for (int l = 0; l < nl; ++l) {
     EncLayerAct& a = w.enc[l];
+    for (int k = 0; k < 4; ++k)
+      if (l == enc_group_begin(nl, k) && (k == 0 || enc_group_begin(nl, k - 1) > l)) wait_w(1 + k);
     if (l == 0)
       RC(rmsnorm_fwd(w.X[0], nullptr, nullptr, p.wf + p.lo.enc_ln0[l], a.n_a, a.rstd_a, Mt, d, p.eps, 1.f, s));
     else
@@ -402,6 +415,7 @@ int encode(const Ptrs& p, const lako_fidt5* m, Work& w, const long long* ids, co
   }
   RC(rmsnorm_fwd(w.X[2 * nl - 1], w.delta_enc, w.X[2 * nl], p.wf + p.lo.enc_final_ln, w.mem, w.rstd_enc_final, Mt, d,
                  p.eps, 1.f, s, dr(nl - 1, E_FF), dr(0, E_FINAL)));
+  wait_w(0);
   // cross-attention K/V of ALL decoder layers in one GEMM (13.8 % of the model's FLOPs)
   // (generate: written head-major, [layer][k|v][head][token][64], so that a decode step streams contiguous slabs)
   RC(gemm_bf16(w.mem, p.wb + p.lo.dec_xkv, w.kv_all, Mt, nl * 2 * inner, d, d, d, nl * 2 * inner, 0, 0, EPI_BF16, 1.f, nullptr,
@@ -453,7 +467,8 @@ extern "C" int lako_fidt5_forward(const lako_fidt5* m, const lako_batch* bt, int
   LAKO_REQUIRE(dr.p >= 0.f && dr.p < 0.9f, LAKO_ERR_BAD_ARG);
   RC(set_packing(w, bt, s));
   const unsigned char* xmask = w.cu ? nullptr : bt->mask;
-  RC(encode(p, m, w, reinterpret_cast<const long long*>(bt->ids), bt->mask, train, s, dr));
+  RC(encode(p, m, w, reinterpret_cast<const long long*>(bt->ids), bt->mask, train, s, dr, false,
+            train ? reinterpret_cast<const cudaEvent_t*>(bt->weight_events) : nullptr));
 
   const long long* labels = reinterpret_cast<const long long*>(bt->labels);
   if (bt->labels_are_decoder_ids) {
@@ -505,11 +520,6 @@ extern "C" int lako_fidt5_forward(const lako_fidt5* m, const lako_batch* bt, int
 // becomes final, event 5 at the end (shared embedding, encoder bias table and final norm).
 // lako_fidt5_grad_stages() reports the element ranges: ranges[i] for i < 5 belongs to stage i, ranges[5] and
 // ranges[6] to stage 5.
-static inline int enc_group_begin(int nl, int k) {  // first layer of encoder group k (k = 0 is the TOP quarter)
-  const int gsz = (nl + 3) / 4;
-  const int lo = nl - (k + 1) * gsz;
-  return lo < 0 ? 0 : lo;
-}
 extern "C" int lako_fidt5_grad_stages(const lako_dims* dm, size_t* ranges /* [7][2] begin,end */) {
   lako_layout lo;
   RC(lako_fidt5_layout(dm, &lo));

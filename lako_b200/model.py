@@ -61,7 +61,8 @@ class _Batch(ctypes.Structure):
                 ("logits", ctypes.c_void_p), ("stats", ctypes.c_void_p), ("count_is_set", ctypes.c_int),
                 ("dropout_p", ctypes.c_float), ("dropout_step", ctypes.c_uint), ("dropout_seed", ctypes.c_ulonglong),
                 ("cu_seqlens", ctypes.c_void_p), ("packed_tokens", ctypes.c_int), ("stage_events", ctypes.c_void_p),
-                ("labels_are_decoder_ids", ctypes.c_int), ("precision", ctypes.c_int), ("recompute", ctypes.c_int)]
+                ("labels_are_decoder_ids", ctypes.c_int), ("precision", ctypes.c_int), ("recompute", ctypes.c_int),
+                ("weight_events", ctypes.c_void_p)]
 
 
 class FiDT5Config:
@@ -212,6 +213,7 @@ class FiDT5(nn.Module):
         self._stage_events = None
         self._stage_ranges = None
         self._master_sync = None   # set by a sharded FusedAdamW: all-gathers the fp32 masters before they are read
+        self._pending_wev = None   # (events, handle array): an all-gather of updated weights still running on another stream
         # transformers 3.0.2 (the version the reference pins, README.md:21) gives decoder block 0's cross-attention its
         # own relative_attention_bias table (32, H); later versions have none.  Kept when a checkpoint carries it.
         self._xattn_relbias = None
@@ -339,6 +341,7 @@ class FiDT5(nn.Module):
 
     # ------------------------------------------------------------------ state dict plumbing
     def state_dict(self, *args, **kwargs):
+        self._wait_weights()
         if self._master_sync is not None:   # sharded data-parallel optimizer: a collective, call it on every rank
             self._master_sync()
         sd = super().state_dict(*args, **kwargs)
@@ -466,8 +469,21 @@ class FiDT5(nn.Module):
                 if p.grad is None:
                     p.grad = self._view(self._flat_grad, name)
 
+    def _wait_weights(self):
+        """A sharded optimizer may still be all-gathering the updated weights on its communication stream
+        (FusedAdamW._step_sharded): make the current stream wait for all of it.  The training forward does not come here --
+        it hands the events to the C side, which waits range by range right before first use."""
+        if self._pending_wev is not None:
+            cur = torch.cuda.current_stream()
+            for e in self._pending_wev[0]:
+                if e is not None:
+                    cur.wait_event(e)
+            self._pending_wev = None
+
     def _refresh_bf16(self):
         sig = self._weights_signature()
+        if self._bf16 is None or self._bf16_version != sig:
+            self._wait_weights()
         if self._master_sync is not None and self._bf16 is not None and self._bf16_version != sig:
             # sharded optimizer + someone touched the masters: foreign slices of the masters are stale, and casting them
             # would overwrite the correct all-gathered bf16 weights -- bring the masters up to date first (collective)
@@ -503,7 +519,9 @@ class FiDT5(nn.Module):
                                                 ctypes.c_size_t(self._total), nat.stream_ptr()), "lako_split_tf32")
             self._tf32_version = self._weights_signature()
 
-    def _model_struct(self, with_grad, precision=0):
+    def _model_struct(self, with_grad, precision=0, wait=True):
+        if wait:
+            self._wait_weights()
         self._refresh_bf16()
         hi = lo = 0
         if precision == 1:
@@ -636,10 +654,15 @@ class FiDT5(nn.Module):
         drop = (drop_p, self._drop_step & 0xFFFFFFFF, self._drop_seed or 0)
         cu, packed = self._packing(mask, passage_lengths)
         pack = (cu.data_ptr() if cu is not None else 0, packed)
-        m = self._model_struct(with_grad=train, precision=prec)
+        # a training forward waits for an overlapped weight all-gather range by range inside the C call
+        wev = self._pending_wev if (train and prec == 0) else None
+        m = self._model_struct(with_grad=train, precision=prec, wait=wev is None)
         bt = _Batch(ids.data_ptr(), mask.data_ptr(), labels.data_ptr(), B, N, L, T, ws.data_ptr(), ws.numel(),
-                    logits.data_ptr(), stats.data_ptr(), count_is_set, *drop, *pack, 0, int(dec_given), prec, recompute)
+                    logits.data_ptr(), stats.data_ptr(), count_is_set, *drop, *pack, 0, int(dec_given), prec, recompute,
+                    ctypes.cast(wev[1], ctypes.c_void_p).value if wev is not None else 0)
         nat.check(L_.lako_fidt5_forward(ctypes.byref(m), ctypes.byref(bt), mode, nat.stream_ptr()), "lako_fidt5_forward")
+        if wev is not None:
+            self._pending_wev = None   # the stream has now waited on every range
         if dec_given:
             return ReaderOutput(None, logits)
         loss = stats[0] / torch.clamp(stats[1], min=1.0)

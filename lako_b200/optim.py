@@ -92,6 +92,28 @@ class FusedAdamW:
                 if self._plan is not None:
                     model._master_sync = self.sync_master_weights
                     self._index_fp32_reads()
+                    # opt-in: measured at cfg4 on 2 and 8 GPUs it changes nothing (91.63 vs 91.66 ms/step at 8) -- the
+                    # all-gather is not what separates the 8-GPU step from the 1-GPU step
+                    if os.environ.get("LAKO_DP_GATHER_OVERLAP", "0") == "1":
+                        self._init_gather_overlap(ranges)
+
+    def _init_gather_overlap(self, ranges):
+        """The all-gather of the updated weights runs on the communication stream and the next training forward starts
+        without waiting for it: one event per gradient stage (recorded when that stage's weights are complete) is handed
+        to lako_fidt5_forward (lako_batch.weight_events), which waits right before the first kernel that reads the
+        range.  Ranges are gathered in the order the forward uses them: embedding and small vectors, encoder groups from
+        the bottom up, decoder last."""
+        stage_of = {lo: min(i, 5) for i, (lo, hi) in enumerate(ranges)}
+        use_order = {5: 0, 4: 1, 3: 2, 2: 3, 1: 4, 0: 5}
+        self._gather_order = sorted(self._plan, key=lambda e: (use_order[stage_of[e[0]]], e[0]))
+        self._gather_stage = [stage_of[e[0]] for e in self._gather_order]
+        self._wevents = [None] * 6
+        for st in set(self._gather_stage):
+            e = torch.cuda.Event()
+            e.record()             # forces creation of the underlying cudaEvent_t
+            self._wevents[st] = e
+        self._wevent_handles = (ctypes.c_void_p * 6)(*[(e.cuda_event if e is not None else 0) for e in self._wevents])
+        self._upd_event = torch.cuda.Event()
 
     def _index_fp32_reads(self):
         """The kernels read three kinds of parameters from the fp32 MASTERS, not from the bf16 copy: the shared embedding
@@ -209,26 +231,44 @@ class FusedAdamW:
         dist.all_reduce(self.sumsq, op=dist.ReduceOp.SUM, group=self.group)   # pieces are disjoint: global ||g||^2
         for lo, hi, plo, phi in self._plan:
             self._update_piece(plo, phi - plo, lr)
+        if getattr(self, "_wevents", None) is not None:
+            main = torch.cuda.current_stream()
+            self._upd_event.record(main)
+            with torch.cuda.stream(self._comm_stream):
+                self._comm_stream.wait_event(self._upd_event)
+                self._gather_weights(self._gather_order, self._gather_stage)
+            model._pending_wev = (self._wevents, self._wevent_handles)
+        else:
+            self._gather_weights(self._plan, None)
+        self._masters_stale = True
+
+    def _gather_weights(self, entries, stages):
+        """All-gather the refreshed weights range by range (on the current stream); with `stages`, record that stage's
+        event once its last range is complete."""
+        model = self.model
         emb = getattr(self, "_emb_range", None)
-        for lo, hi, plo, phi in self._plan:
+        small = getattr(self, "_small_idx", None)
+        for i, (lo, hi, plo, phi) in enumerate(entries):
             if emb == (lo, hi):   # read in fp32 by embed_gather: gather the masters, re-cast the whole range locally
                 self._all_gather(model._flat, lo, hi, plo, phi)
                 nat.check(nat.lib().lako_cast_f32_to_bf16(nat.ptr(model._flat[lo:]), nat.ptr(model._bf16[lo:]),
                                                           ctypes.c_size_t(hi - lo), nat.stream_ptr()), "lako_cast_f32_to_bf16")
+                if small is not None:     # norm gains and bias tables, also read in fp32 (see _index_fp32_reads)
+                    buf = model._flat[small] * self._small_own
+                    dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=self.group)
+                    model._flat.index_copy_(0, small, buf)
             else:
                 self._all_gather(model._bf16, lo, hi, plo, phi)
-        small = getattr(self, "_small_idx", None)
-        if small is not None:     # norm gains and bias tables, also read in fp32 (see _index_fp32_reads)
-            buf = model._flat[small] * self._small_own
-            dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=self.group)
-            model._flat.index_copy_(0, small, buf)
-        self._masters_stale = True
+            if stages is not None and (i + 1 == len(entries) or stages[i + 1] != stages[i]):
+                self._wevents[stages[i]].record()
 
     @torch.no_grad()
     def sync_master_weights(self):
         """All-gather the fp32 master weights (each rank only keeps its own slices current in sharded mode)."""
         if self._plan is None or not self._masters_stale:
             return
+        if hasattr(self.model, "_wait_weights"):
+            self.model._wait_weights()
         for lo, hi, plo, phi in self._plan:
             self._all_gather(self.model._flat, lo, hi, plo, phi)
         self._masters_stale = False
@@ -243,6 +283,7 @@ class FusedAdamW:
         if self._plan is not None and not self._skip_allreduce:
             lr = self.lr * (self.schedule(self.step_count) if self.schedule is not None else 1.0)
             self.last_lr = lr
+            model._wait_weights()   # (no forward since the last step: its all-gather may still be running)
             if model._bf16 is None:
                 model._refresh_bf16()
             self._step_sharded(lr)

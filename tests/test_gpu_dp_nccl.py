@@ -43,10 +43,12 @@ def _worker(rank, world, port, out_dir):
     ids, mask, labels = _data(world * B, N, L, T, seed=5)
     sl = slice(rank * B, (rank + 1) * B)
     res = {}
-    for shard in (False, True):
+    for shard in (False, True, "overlap"):   # "overlap": sharded, weights all-gathered under the next forward
         model = _model().cuda().train()
-        opt = FusedAdamW(model, lr=1e-3, weight_decay=1e-4, clip=1.0, shard=shard)
-        assert (opt._plan is not None) == shard
+        os.environ["LAKO_DP_GATHER_OVERLAP"] = "1" if shard == "overlap" else "0"
+        opt = FusedAdamW(model, lr=1e-3, weight_decay=1e-4, clip=1.0, shard=bool(shard))
+        assert (opt._plan is not None) == bool(shard)
+        assert (getattr(opt, "_wevents", None) is not None) == (shard == "overlap")
         loss = train_step(model, opt, ids[sl].cuda(), mask[sl].cuda(), labels[sl].cuda())
         sd = {k: v.detach().float().cpu().clone() for k, v in model.state_dict().items()}   # sharded: collective
         res[shard] = (float(loss), float(opt.grad_norm()), sd, model._bf16.float().sum().item())
@@ -95,7 +97,7 @@ def test_dp2_nccl_training_and_inference_gather(tmp_path):
     loss = float(train_step(model, opt, ids.cuda(), mask.cuda(), labels.cuda()))
     gn = float(opt.grad_norm())
     sd = {k: v.detach().float().cpu() for k, v in model.state_dict().items()}
-    for shard in (False, True):
+    for shard in (False, True, "overlap"):
         l0, g0, sd0, chk0, later0 = r0["res"][shard]
         l1, g1, sd1, chk1, later1 = r1["res"][shard]
         assert later0 == later1
@@ -109,9 +111,11 @@ def test_dp2_nccl_training_and_inference_gather(tmp_path):
         # one AdamW step without bias correction moves a weight by ~3.2 lr sign(g): elements whose gradient is at the
         # fp32-summation-order noise level may flip, the bulk must agree
         assert float((diff > 1e-4).float().mean()) < 2e-2, float((diff > 1e-4).float().mean())
-    rep, shd = r0["res"][False][4], r0["res"][True][4]
-    print(f"steps 2-3: replicated {rep} sharded {shd}")
+    rep, shd, ovl = r0["res"][False][4], r0["res"][True][4], r0["res"]["overlap"][4]
+    print(f"steps 2-3: replicated {rep} sharded {shd} sharded+overlapped gather {ovl}")
     assert all(abs(a - b) < 5e-5 for a, b in zip(rep, shd)), (rep, shd)   # measured: 5e-7
+    assert all(abs(a - b) < 5e-5 for a, b in zip(ovl, shd)), (ovl, shd)   # same arithmetic on another stream (run-to-run
+                                                                           # noise of the split-K atomics: ~5e-7)
     # inference gather: rank order, identical on both ranks, equal to the local pieces
     assert torch.equal(r0["answers"], r1["answers"]) and torch.equal(r0["scores"], r1["scores"])
     assert r0["answers"].shape == (2 * B, 8) and r0["scores"].shape == (2 * B, 3)
