@@ -536,6 +536,8 @@ class FiDT5(nn.Module):
         if ws is None or ws[0] != key or ws[1].numel() < nbytes:
             self._ws.pop(key[0], None)
             ws = (key, torch.empty(nbytes, dtype=torch.uint8, device=self._flat.device))
+            if os.environ.get("LAKO_POISON_WORKSPACE") == "1":   # test support: every fp32 / bf16 word a NaN, so that a
+                ws[1].fill_(0xFF)                                # kernel reading what nobody wrote shows up in the results
             self._ws[key[0]] = ws
         return ws[1]
 
