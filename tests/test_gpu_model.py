@@ -206,7 +206,8 @@ def test_passages_longer_than_256_tokens_vs_oracle(L):
     torch.cuda.synchronize()
     model.set_checkpoint(False)
     # not 1e-5 as at the golden shapes: with M = 2L > 128 keys the cross-attention dq is an fp32 atomic sum over key
-    # chunks, and its summation order occasionally flips the bf16 rounding of one element (two steps of the SAME mode
+    # chunks (and the split-K dgrads likewise): a different summation order can flip the bf16 rounding of an element of the
+    # gradient signal -- the likely cause of what tools/race_probe.py shows (two steps of the SAME mode
     # differ by 1.4e-3 about once in twelve runs, tools/race_probe.py)
     assert ((model._flat_grad - res[True][1]).norm() / res[True][1].norm()).item() < 5e-3
     model.eval()
