@@ -234,20 +234,25 @@ def test_use_checkpoint_recomputes_encoder_activations(unpad):
     model.unpad = unpad
     model.train()
     ids, mask, labels = c["ids"].cuda(), c["mask"].cuda(), c["labels"].cuda()
-    res = {}
-    for ckpt in (False, True):
-        model.set_checkpoint(ckpt)
-        model._drop_seed, model._drop_step = 1234, 0
-        model.zero_grad()
-        loss, logits = model(input_ids=ids, attention_mask=mask, labels=labels)
-        loss.backward()
-        torch.cuda.synchronize()
-        res[ckpt] = (loss.item(), logits.detach().clone(), model._flat_grad.clone())
+    res = {False: [], True: []}
+    for rep in range(3):
+        for ckpt in (False, True):
+            model.set_checkpoint(ckpt)
+            model._drop_seed, model._drop_step = 1234, 0
+            model.zero_grad()
+            loss, logits = model(input_ids=ids, attention_mask=mask, labels=labels)
+            loss.backward()
+            torch.cuda.synchronize()
+            res[ckpt].append((loss.item(), logits.detach().clone(), model._flat_grad.clone()))
     model.set_checkpoint(False)
-    assert res[True][0] == res[False][0] and torch.equal(res[True][1], res[False][1])
-    g0, g1 = res[False][2], res[True][2]
-    assert bool(torch.isfinite(g1).all()) and g0.norm().item() > 0
-    assert ((g1 - g0).norm() / g0.norm()).item() < 1e-5      # split-K weight gradients add in a different order
+    assert all(r[0] == res[False][0][0] and torch.equal(r[1], res[False][0][1]) for r in res[False] + res[True])
+    assert all(bool(torch.isfinite(r[2]).all()) for r in res[True]) and res[False][0][2].norm().item() > 0
+    # Gradients: the backward sums fp32 partials with atomics (split-K dgrads / wgrads, cross-attention dq); the order
+    # changes the last bits and, where such a sum is then rounded to bf16, occasionally one element by a bf16 ulp -- two
+    # steps of the SAME mode differ by ~1e-3 about once in twelve runs (tools/race_probe.py).  So: some pair of
+    # (normal, recompute) runs agrees to summation noise, and no pair differs by more than such a flip.
+    dist = [((a[2] - b[2]).norm() / b[2].norm()).item() for a in res[True] for b in res[False]]
+    assert min(dist) < 1e-5 and max(dist) < 5e-3, dist
     B, N, L = c["ids"].shape
     T = labels.size(1)
     lib = nat.lib()
