@@ -245,7 +245,8 @@ def test_use_checkpoint_recomputes_encoder_activations(unpad):
             torch.cuda.synchronize()
             res[ckpt].append((loss.item(), logits.detach().clone(), model._flat_grad.clone()))
     model.set_checkpoint(False)
-    assert all(r[0] == res[False][0][0] and torch.equal(r[1], res[False][0][1]) for r in res[False] + res[True])
+    # logits bit-identical; the loss is an atomic fp32 sum over target rows (last-bit noise)
+    assert all(abs(r[0] - res[False][0][0]) < 1e-5 and torch.equal(r[1], res[False][0][1]) for r in res[False] + res[True])
     assert all(bool(torch.isfinite(r[2]).all()) for r in res[True]) and res[False][0][2].norm().item() > 0
     # Gradients: the backward sums fp32 partials with atomics (split-K dgrads / wgrads, cross-attention dq); the order
     # changes the last bits and, where such a sum is then rounded to bf16, occasionally one element by a bf16 ulp -- two
