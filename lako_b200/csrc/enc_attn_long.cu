@@ -333,7 +333,7 @@ __global__ void __launch_bounds__(128) enc_attn_long_dq_kernel(const LongAttnPar
 // ------------------------------------------------------------------------------------------------ backward: dK, dV
 constexpr int LK_SMEM_BYTES = 4 * LTILE_B + (3 * 64 + 128) * 4;  // + (2L-1) LUT floats
 template <bool kDrop>
-__global__ void __launch_bounds__(128) enc_attn_long_dkv_kernel(const LongAttnParams p) {
+__global__ void __launch_bounds__(128, 3) enc_attn_long_dkv_kernel(const LongAttnParams p) {
   pdl_launch_dependents();
   pdl_wait();
   extern __shared__ __align__(1024) uint8_t lsm[];
