@@ -198,6 +198,7 @@ def run_reference(args):
     size, B, N, L, T, kind = WORKLOADS[args.workload]
     B = args.batch or B
     N = args.passages or N
+    L = args.text_maxlength or L
     steps = max(1, args.steps)
     warmup = max(1, min(args.warmup, 2))
     # bounded: cap the number of timed CPU steps so the arm ends within minutes (one t5-large step of ONE question
@@ -318,6 +319,8 @@ def main():
                     "also quoted at N = 100)")
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"],
                     help="evaluation workloads only: fp32 = 3xTF32 GEMMs + fp32 attention (the mode that meets 1e-4 / 1e-2)")
+    ap.add_argument("--text-maxlength", type=int, default=0, help="tokens per passage (default: the workload's own; above "
+                    "256 the encoder attention takes the tiled mma.sync path)")
     ap.add_argument("--use-checkpoint", action="store_true",
                     help="training workloads: model.set_checkpoint(True) (the reference's --use_checkpoint): encoder "
                          "activations recomputed in backward")
@@ -364,6 +367,7 @@ def main():
     size, B, N, L, T, kind = WORKLOADS[args.workload]
     B = args.batch or B
     N = args.passages or N
+    L = args.text_maxlength or L
     conf = FiDT5Config.t5(size)
     model = FiDT5(conf, emb_std=EMB_STD, seed=0).cuda()
     peaks, which = measured_peaks()
