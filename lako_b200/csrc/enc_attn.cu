@@ -158,8 +158,7 @@ enc_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const EncAttnPar
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   float* s_lut4 = reinterpret_cast<float*>(smem + EA_LUT_OFF);
   float* s_kmask = reinterpret_cast<float*>(smem + EA_KMASK_OFF);
-  float* s_red_m = reinterpret_cast<float*>(smem + EA_RED_OFF);  // [2][128]
-  float* s_red_l = s_red_m + 256;                                // [2][128]
+  float* s_red_m = reinterpret_cast<float*>(smem + EA_RED_OFF);  // row maxima [2][128], then row sums [2][128] (red_a + 1024)
   uint64_t* bar_qk = reinterpret_cast<uint64_t*>(smem + EA_BAR_OFF);
   uint64_t* bar_v = bar_qk + 1;
   uint64_t* bar_s = bar_qk + 2;
