@@ -21,7 +21,8 @@ namespace {
 
 constexpr int LT = 64;          // tile edge (queries, keys, head dim)
 constexpr int LTILE_B = 8192;   // one [64][64] bf16 tile, 128B-swizzled rows
-constexpr int LDS_P = 65;       // pitch of the fp32 dS tile (diagonal walks are conflict-free)
+constexpr int LDS_P = 72;       // pitch of the fp32 dS tile: float2 stores of a half-warp (rows g, column pairs t4) and the
+                                // diagonal walks are both conflict-free
 constexpr float LONG_MASK_MIN = -3.4028234663852886e38f;  // torch.finfo(float32).min, HF's additive mask
 
 struct LongAttnParams {
@@ -304,10 +305,15 @@ __global__ void __launch_bounds__(128) enc_attn_long_dq_kernel(const LongAttnPar
         const int kpos = min(kt * LT + kl, Lmax - 1);
         const float pv = expf(s[nt][e] + sLut[kpos - qpos[r] + Lmax - 1] + sKm[kl] - lse[r]);
         const float kf = (!kDrop || keep_of(sKeep, rl[r], kl)) ? keep_scale : 0.f;
-        const float ds = pv * (kf * dp[nt][e] - D[r]);
-        s[nt][e] = ds;
-        if (p.dlut) sDS[rl[r] * LDS_P + kl] = ds;
+        s[nt][e] = pv * (kf * dp[nt][e] - D[r]);
       }
+    if (p.dlut) {
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        *reinterpret_cast<float2*>(sDS + rl[0] * LDS_P + nt * 8 + t4 * 2) = make_float2(s[nt][0], s[nt][1]);
+        *reinterpret_cast<float2*>(sDS + rl[1] * LDS_P + nt * 8 + t4 * 2) = make_float2(s[nt][2], s[nt][3]);
+      }
+    }
     uint32_t dsa[4][4];
     acc_to_afrag(dsa, s);
     mma_fragrow(dq, dsa, aK, lane);
