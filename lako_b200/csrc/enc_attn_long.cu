@@ -24,6 +24,9 @@ constexpr int LTILE_B = 8192;   // one [64][64] bf16 tile, 128B-swizzled rows
 constexpr int LDS_P = 72;       // pitch of the fp32 dS tile: float2 stores of a half-warp (rows g, column pairs t4) and the
                                 // diagonal walks are both conflict-free
 constexpr float LONG_MASK_MIN = -3.4028234663852886e38f;  // torch.finfo(float32).min, HF's additive mask
+constexpr float LONG_LOG2E = 1.4426950408889634f;
+// exp(x) as one MUFU.EX2 (the tcgen05 kernels do the same); exp(-inf) = 0
+__device__ __forceinline__ float exp_fast(float x) { return fast_exp2(x * LONG_LOG2E); }
 
 struct LongAttnParams {
   const __nv_bfloat16* qkv;   // [rows][3*inner]
@@ -206,7 +209,7 @@ __global__ void __launch_bounds__(128) enc_attn_long_fwd_kernel(const LongAttnPa
       mt[r] = fmaxf(mt[r], __shfl_xor_sync(0xffffffffu, mt[r], 1));
       mt[r] = fmaxf(mt[r], __shfl_xor_sync(0xffffffffu, mt[r], 2));
       m_new[r] = fmaxf(m[r], mt[r]);
-      sc[r] = (m[r] == -INFINITY) ? 0.f : expf(m[r] - m_new[r]);
+      sc[r] = (m[r] == -INFINITY) ? 0.f : exp_fast(m[r] - m_new[r]);
       m[r] = m_new[r];
     }
 #pragma unroll
@@ -214,7 +217,7 @@ __global__ void __launch_bounds__(128) enc_attn_long_fwd_kernel(const LongAttnPa
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const int r = e >> 1;
-        const float ex = expf(s[nt][e] - m_new[r]);  // -inf (beyond the passage) -> 0
+        const float ex = exp_fast(s[nt][e] - m_new[r]);  // -inf (beyond the passage) -> 0
         rs[r] += ex;  // the normaliser is the sum before dropout (HF:331-332: softmax, then dropout)
         s[nt][e] = (!kDrop || keep_of(sKeep, rl[r], nt * 8 + t4 * 2 + (e & 1))) ? ex : 0.f;
         o[nt][e] *= sc[r];
@@ -303,7 +306,7 @@ __global__ void __launch_bounds__(128) enc_attn_long_dq_kernel(const LongAttnPar
       for (int e = 0; e < 4; ++e) {
         const int kl = nt * 8 + t4 * 2 + (e & 1), r = e >> 1;
         const int kpos = min(kt * LT + kl, Lmax - 1);
-        const float pv = expf(s[nt][e] + sLut[kpos - qpos[r] + Lmax - 1] + sKm[kl] - lse[r]);
+        const float pv = exp_fast(s[nt][e] + sLut[kpos - qpos[r] + Lmax - 1] + sKm[kl] - lse[r]);
         const float kf = (!kDrop || keep_of(sKeep, rl[r], kl)) ? keep_scale : 0.f;
         s[nt][e] = pv * (kf * dp[nt][e] - D[r]);
       }
@@ -396,7 +399,7 @@ __global__ void __launch_bounds__(128, 3) enc_attn_long_dkv_kernel(const LongAtt
       for (int e = 0; e < 4; ++e) {
         const int r = nt * 8 + t4 * 2 + (e & 1), k = e >> 1;
         const int qp = min(q0 + r, Lp - 1);
-        const float pv = expf(st[nt][e] + sLut[kpos[k] - qp + Lmax - 1] + km[k] - sLse[r]);
+        const float pv = exp_fast(st[nt][e] + sLut[kpos[k] - qp + Lmax - 1] + km[k] - sLse[r]);
         const float kf = (!kDrop || keep_of(sKeep, r, kl2[k])) ? keep_scale : 0.f;
         st[nt][e] = pv * kf;                           // dropped probabilities (transposed)
         dpt[nt][e] = pv * (kf * dpt[nt][e] - sD[r]);   // dS^T
