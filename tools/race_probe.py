@@ -23,7 +23,7 @@ def step(junk):
 for pdl in (1, 0):
     nat.lib().lako_set_pdl(pdl)
     outs = []
-    for i in range(12):
+    for i in range(int(os.environ.get("ITERS", "12"))):
         lg, g = step((i % 3) * 1000003)
         outs.append((lg, g))
     ref_lg, ref_g = outs[0]
