@@ -246,7 +246,10 @@ int lako_fold_dlut(const float* dlut, const int* buckets, float* dtable, int H, 
    uncleared; a kernel that reads columns it did not write would pick these up) */
 int lako_debug_poison_tmem(void* stream);
 /* encoder self-attention forward implementation: 2 (default) = persistent warp-specialised kernel with the softmax
- * probabilities kept in tensor memory; 1 = the one-shot kernel of round 1 (also env LAKO_ATTN_FWD=1) */
+ * probabilities kept in tensor memory; 1 = the one-shot kernel of round 1 (also env LAKO_ATTN_FWD=1); 3 = forward AND
+ * backward through the tiled any-length kernels (csrc/enc_attn_long.cu) that L > 256 always takes (L <= 2048; they
+ * neither write nor read the keep-word buffer of the _dropout entry points: the backward regenerates the words, with
+ * 4 * max(8, ceil(L / 32)) Philox counters per query row) */
 void lako_set_attn_impl(int v);
 int lako_enc_attn_fwd(const void* qkv, const unsigned char* mask, const float* bias_lut, void* out, float* lse, int P,
                       int L, int H, void* stream);
