@@ -64,14 +64,35 @@ int xattn_fwd(const __nv_bfloat16* q, const __nv_bfloat16* kv, const unsigned ch
   return LAKO_OK;
 }
 
+// dq[b*T+t][h*64+d] = sum over the question's key chunks, in chunk order, of the partials xattn_bwd_mma left
+__global__ void xattn_dq_reduce_kernel(const float* __restrict__ part, __nv_bfloat16* __restrict__ dq, int T, int H, int splits,
+                                       const int* __restrict__ cu, int npsg) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int t = blockIdx.x, h = blockIdx.y, b = blockIdx.z, d = threadIdx.x;  // 64 threads
+  const int stride_s = splits;
+  if (cu) splits = (cu[(b + 1) * npsg] - cu[b * npsg] + XA_CH - 1) / XA_CH;
+  const float* pp = part + (((static_cast<size_t>(b) * H + h) * stride_s) * T + t) * 64 + d;
+  float acc = 0.f;
+  for (int s = 0; s < splits; ++s) acc += pp[static_cast<size_t>(s) * T * 64];
+  dq[(static_cast<size_t>(b) * T + t) * (H * 64) + h * 64 + d] = __float2bfloat16(acc);
+}
+
 int xattn_bwd(const __nv_bfloat16* q, const __nv_bfloat16* kv, const unsigned char* mask, const __nv_bfloat16* out,
               const __nv_bfloat16* dout, const float* lse, __nv_bfloat16* dkv, float* dq_f32, int B, int T, int M,
               int H, int ldq, int ldkv, int koff, int voff, int ldo, cudaStream_t s, DropSpec drop, const int* cu,
-              int npsg) {
+              int npsg, float* dq_part, __nv_bfloat16* dq_bf16) {
   LAKO_REQUIRE(B > 0 && T > 0 && T <= XA_TMAX && M > 0 && H > 0, LAKO_ERR_UNSUPPORTED);
+  LAKO_REQUIRE((dq_part == nullptr) == (dq_bf16 == nullptr) && (dq_part || dq_f32), LAKO_ERR_BAD_ARG);
   ProfScope prof(PROF_XATTN, 8.0 * B * H * static_cast<double>(T) * M * 64, s);
-  return xattn_bwd_mma(q, kv, mask, out, dout, lse, dkv, dq_f32, B, T, M, H, ldq, ldkv, koff, voff, ldo, s, drop, cu,
-                       npsg);
+  int rc = xattn_bwd_mma(q, kv, mask, out, dout, lse, dkv, dq_f32, B, T, M, H, ldq, ldkv, koff, voff, ldo, s, drop, cu,
+                         npsg, dq_part);
+  if (rc || !dq_part) return rc;
+  const int splits = (M + XA_CH - 1) / XA_CH;
+  launch_pdl(xattn_dq_reduce_kernel, dim3(T, H, B), dim3(64), 0, s, static_cast<const float*>(dq_part), dq_bf16, T, H, splits,
+             cu, npsg);
+  LAKO_CHECK_LAUNCH();
+  return LAKO_OK;
 }
 
 // ------------------------------------------------------------------------------------------------

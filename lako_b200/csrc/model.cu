@@ -562,7 +562,6 @@ extern "C" int lako_fidt5_backward(const lako_fidt5* m, const lako_batch* bt, co
   cudaMemsetAsync(w.dlut_enc, 0, sizeof(float) * H * (2 * w.L - 1), s);
   cudaMemsetAsync(w.dlut_dec, 0, sizeof(float) * H * (2 * w.T - 1), s);
   cudaMemsetAsync(w.dsk_f32, 0, sizeof(float) * BT * d, s);
-  cudaMemsetAsync(w.dq_f32, 0, sizeof(float) * BT * inner, s);
 
   // ---- LM head
   if (loss_grad) RC(scale_bf16_dev(w.dlogits, static_cast<size_t>(BT) * vpad, loss_grad, s));
@@ -583,9 +582,10 @@ extern "C" int lako_fidt5_backward(const lako_fidt5* m, const lako_batch* bt, co
                    g + p.lo.dec_ln2[l], BT, d, 1, 1.f, s, dr.none(), dr(l, D_XO)));
     // cross-attention
     RC(lin_dgrad(dg.g1, p.wb + p.lo.dec_xo[l], w.dao_dec, BT, d, inner, nullptr, 1.f, s));
-    RC(xattn_bwd(a.q, w.kv_all, xmask, a.xo, w.dao_dec, a.lse, w.dkv_all, w.dq_f32, bt->B, bt->T, w.M, H, inner,
-                 nl * 2 * inner, l * 2 * inner, l * 2 * inner + inner, inner, s, dr(l, D_XP), w.cu, bt->N));
-    RC(cast_f32_to_bf16(w.dq_f32, dg.dq, static_cast<size_t>(BT) * inner, s, true));
+    // dq: per-chunk partials in the (now idle) forward workspace, summed in chunk order -- no atomics, so the gradient
+    // signal below this point does not depend on the order the chunk CTAs finish in
+    RC(xattn_bwd(a.q, w.kv_all, xmask, a.xo, w.dao_dec, a.lse, w.dkv_all, nullptr, bt->B, bt->T, w.M, H, inner,
+                 nl * 2 * inner, l * 2 * inner, l * 2 * inner + inner, inner, s, dr(l, D_XP), w.cu, bt->N, w.xattn_ws, dg.dq));
     RC(lin_dgrad(dg.dq, p.wb + p.lo.dec_xq[l], w.dn_dec, BT, inner, d, nullptr, 1.f, s));
     RC(rmsnorm_bwd(w.dn_dec, w.Y[3 * l + 1], a.rstd_c, p.wf + p.lo.dec_ln1[l], w.dres_dec, dg.g2,
                    g + p.lo.dec_ln1[l], BT, d, 1, 1.f, s, dr.none(), dr(l, D_O)));

@@ -68,6 +68,8 @@ int enc_attn_long_bwd(const __nv_bfloat16* qkv, const __nv_bfloat16* out, const 
 int attn_rowdot_inplace(__nv_bfloat16* o, const __nv_bfloat16* dout, int rows, int H, cudaStream_t s);
 
 // dec_attn.cu
+// xattn_bwd with dq_part (>= xattn_workspace_bytes) and dq_bf16: the per-chunk dq partials are summed in chunk order into
+// the bf16 dq (deterministic); without them dq_f32 (pre-zeroed) is accumulated with atomics
 size_t xattn_workspace_bytes(int B, int H, int T, int M);
 int xattn_fwd(const __nv_bfloat16* q, const __nv_bfloat16* kv, const unsigned char* mask, __nv_bfloat16* out, float* lse,
               float* tok_score, float* workspace, int B, int T, int M, int H, int ldq, int ldkv, int koff, int voff,
@@ -76,7 +78,8 @@ int xattn_fwd(const __nv_bfloat16* q, const __nv_bfloat16* kv, const unsigned ch
 int xattn_bwd(const __nv_bfloat16* q, const __nv_bfloat16* kv, const unsigned char* mask, const __nv_bfloat16* out,
               const __nv_bfloat16* dout, const float* lse, __nv_bfloat16* dkv, float* dq_f32, int B, int T, int M,
               int H, int ldq, int ldkv, int koff, int voff, int ldo, cudaStream_t s, DropSpec drop = DropSpec{},
-              const int* cu = nullptr, int npsg = 1);
+              const int* cu = nullptr, int npsg = 1, float* dq_part = nullptr,
+              __nv_bfloat16* dq_bf16 = nullptr);
 // xattn_mma.cu
 int xattn_fwd_mma(const __nv_bfloat16* q, const __nv_bfloat16* kv, const unsigned char* mask, float* tok_score,
                   float* workspace, int B, int T, int M, int H, int ldq, int ldkv, int koff, int voff, cudaStream_t s,
@@ -84,7 +87,7 @@ int xattn_fwd_mma(const __nv_bfloat16* q, const __nv_bfloat16* kv, const unsigne
 int xattn_bwd_mma(const __nv_bfloat16* q, const __nv_bfloat16* kv, const unsigned char* mask, const __nv_bfloat16* out,
                   const __nv_bfloat16* dout, const float* lse, __nv_bfloat16* dkv, float* dq_f32, int B, int T, int M,
                   int H, int ldq, int ldkv, int koff, int voff, int ldo, cudaStream_t s, DropSpec drop = DropSpec{},
-                  const int* cu = nullptr, int npsg = 1);
+                  const int* cu = nullptr, int npsg = 1, float* dq_part = nullptr);
 int dself_fwd(const __nv_bfloat16* qkv, const float* lut, __nv_bfloat16* out, float* probs, int B, int T, int H,
               cudaStream_t s, DropSpec drop = DropSpec{});
 int dself_bwd(const __nv_bfloat16* qkv, const __nv_bfloat16* dout, const float* probs, __nv_bfloat16* dqkv, float* dlut,

@@ -7,7 +7,9 @@
 //   forward : S = Q K^T (+mask) -> chunk-local softmax -> O_partial = P V, partial (o, m, l) per chunk;
 //             xattn_combine_kernel (dec_attn.cu) merges the chunks.
 //   backward: S^T, dP^T per 16-key tile, P^T = exp(S^T - lse), dS^T = P^T (dP^T - D);
-//             dV = P^T dO, dK = dS^T Q written in place (bf16); dq += dS K via shared memory + fp32 atomics.
+//             dV = P^T dO, dK = dS^T Q written in place (bf16); dq = dS K of the chunk via shared memory, left as a
+//             per-chunk partial that xattn_dq_reduce_kernel (dec_attn.cu) sums in chunk order (the model's path), or
+//             added to a pre-zeroed fp32 buffer with atomics (the stand-alone entry point).
 #include "mma_sync.cuh"
 #include "ops.cuh"
 
@@ -27,7 +29,8 @@ struct XMParams {
   const __nv_bfloat16* dout;  // bwd
   const float* lse;           // bwd [B][H][T]
   __nv_bfloat16* dkv;         // bwd
-  float* dq;                  // bwd [B*T][H*64] fp32 (pre-zeroed)
+  float* dq;                  // bwd [B*T][H*64] fp32 (pre-zeroed), accumulated with atomics -- or, when dq_part is set:
+  float* dq_part;             // bwd [B][H][splits][T][64] fp32 per-chunk partials (summed in chunk order by xattn_dq_reduce)
   int T, TP, M, H, ldq, ldkv, koff, voff, ldo, splits;
   // packed (un-padded) memory: question b owns kv rows [cu[b*npsg], cu[(b+1)*npsg]); null = padded [B][M]
   const int* cu;
@@ -443,7 +446,10 @@ __global__ void __launch_bounds__(128, TPC == 16 ? 5 : 3) xattn_bwd_mma_kernel(c
       const int t = mt * 16 + row;
       if (t < p.T) {
         const float v = sO[row * 68 + d] + sO[(16 + row) * 68 + d] + sO[(32 + row) * 68 + d] + sO[(48 + row) * 68 + d];
-        atomicAdd(&p.dq[(static_cast<size_t>(b) * p.T + t) * (p.H * 64) + h * 64 + d], v);
+        if (p.dq_part)
+          p.dq_part[(((static_cast<size_t>(b) * p.H + h) * p.splits + split) * p.T + t) * 64 + d] = v;
+        else
+          atomicAdd(&p.dq[(static_cast<size_t>(b) * p.T + t) * (p.H * 64) + h * 64 + d], v);
       }
     }
     __syncthreads();
@@ -486,11 +492,12 @@ int xattn_fwd_mma(const __nv_bfloat16* q, const __nv_bfloat16* kv, const unsigne
 int xattn_bwd_mma(const __nv_bfloat16* q, const __nv_bfloat16* kv, const unsigned char* mask, const __nv_bfloat16* out,
                   const __nv_bfloat16* dout, const float* lse, __nv_bfloat16* dkv, float* dq_f32, int B, int T, int M,
                   int H, int ldq, int ldkv, int koff, int voff, int ldo, cudaStream_t s, DropSpec drop, const int* cu,
-                  int npsg) {
+                  int npsg, float* dq_part) {
   LAKO_REQUIRE(B > 0 && T > 0 && T <= 64 && M > 0 && H > 0, LAKO_ERR_UNSUPPORTED);
   LAKO_REQUIRE(ldq % 8 == 0 && ldkv % 8 == 0 && koff % 8 == 0 && voff % 8 == 0 && ldo % 8 == 0, LAKO_ERR_BAD_ARG);
   XMParams p{};
   p.q = q; p.kv = kv; p.mask = mask; p.out = out; p.dout = dout; p.lse = lse; p.dkv = dkv; p.dq = dq_f32;
+  p.dq_part = dq_part;
   p.T = T; p.TP = (T + 15) / 16 * 16; p.M = M; p.H = H; p.ldq = ldq; p.ldkv = ldkv; p.koff = koff; p.voff = voff;
   p.ldo = ldo;
   p.splits = (M + XM_CH - 1) / XM_CH;
