@@ -205,10 +205,9 @@ def test_passages_longer_than_256_tokens_vs_oracle(L):
     loss.backward()
     torch.cuda.synchronize()
     model.set_checkpoint(False)
-    # not 1e-5 as at the golden shapes: with M = 2L > 128 keys the cross-attention dq is an fp32 atomic sum over key
-    # chunks (and the split-K dgrads likewise): a different summation order can flip the bf16 rounding of an element of the
-    # gradient signal -- the likely cause of what tools/race_probe.py shows (two steps of the SAME mode
-    # differ by 1.4e-3 about once in twelve runs, tools/race_probe.py)
+    # not 1e-5: the split-K dgrads sum fp32 partials with atomics and round the result to bf16, so a different summation
+    # order can flip one element of the gradient signal by a bf16 ulp (seen as two identical steps 1.4e-3 apart about
+    # once in twelve runs while the cross-attention dq was an atomic sum too, tools/race_probe.py)
     assert ((model._flat_grad - res[True][1]).norm() / res[True][1].norm()).item() < 5e-3
     model.eval()
     model.overwrite_forward_crossattention()
@@ -248,10 +247,10 @@ def test_use_checkpoint_recomputes_encoder_activations(unpad):
     # logits bit-identical; the loss is an atomic fp32 sum over target rows (last-bit noise)
     assert all(abs(r[0] - res[False][0][0]) < 1e-5 and torch.equal(r[1], res[False][0][1]) for r in res[False] + res[True])
     assert all(bool(torch.isfinite(r[2]).all()) for r in res[True]) and res[False][0][2].norm().item() > 0
-    # Gradients: the backward sums fp32 partials with atomics (split-K dgrads / wgrads, cross-attention dq); the order
-    # changes the last bits and, where such a sum is then rounded to bf16, occasionally one element by a bf16 ulp -- two
-    # steps of the SAME mode differ by ~1e-3 about once in twelve runs (tools/race_probe.py).  So: some pair of
-    # (normal, recompute) runs agrees to summation noise, and no pair differs by more than such a flip.
+    # Gradients: the backward sums fp32 partials with atomics (split-K dgrads / wgrads); the order changes the last bits
+    # and, where such a sum is then rounded to bf16, can flip one element by a bf16 ulp (~1e-3 of the gradient norm,
+    # tools/race_probe.py).  So: some pair of (normal, recompute) runs agrees to summation noise, and no pair differs
+    # by more than such a flip.
     dist = [((a[2] - b[2]).norm() / b[2].norm()).item() for a in res[True] for b in res[False]]
     assert min(dist) < 1e-5 and max(dist) < 5e-3, dist
     B, N, L = c["ids"].shape
