@@ -214,6 +214,14 @@ def test_attention_keep_words_host_restatement():
     word = int(attn_keep_words(9, 4, 21, np.array([(((psg * H + h) * L + q) * 32 + c * 4)], dtype=np.uint64), 0.1)[0])
     for j in range(32):
         assert m[psg, h, q, c * 32 + j] == bool((word >> ((j >> 1) + 16 * (j & 1))) & 1)
+    # passages longer than 256 tokens (csrc/enc_attn_long.cu): ceil(L / 32) chunks per query row, 4 counters each
+    L2 = 300
+    m2 = attn_keep_mask(9, 4, 21, 1, H, L2, 0.1)
+    assert m2.shape == (1, H, L2, 320)
+    h, q, c = 1, 299, 9
+    word = int(attn_keep_words(9, 4, 21, np.array([((h * L2 + q) * 40 + c * 4)], dtype=np.uint64), 0.1)[0])
+    for j in range(32):
+        assert m2[0, h, q, c * 32 + j] == bool((word >> ((j >> 1) + 16 * (j & 1))) & 1)
     # the bit-sliced comparison IS a 16-bit threshold test of 32 independent uniforms: p = 1 - thresh / 65536 exactly
     big = attn_keep_words(1, 2, 3, np.arange(0, 4 * 20000, 4, dtype=np.uint64), 0.25)
     ones = sum(bin(int(w)).count("1") for w in big) / (32.0 * len(big))
